@@ -1,0 +1,852 @@
+// IVF-PQ query on the device.  Replaces stored::Database::query
+// (src/db/stored.rs:331-442, 549-597), build::Database::query
+// (src/db/build.rs:307-382, 521-565), Partition::new (src/db/build.rs:446-482) and the
+// selection semantics of NBestByKey (src/nbest.rs:52-64).
+//
+// Pipeline for a batch of queries (all distances in the reference's summation order):
+//   1 coarse      d(q, c_p) for every partition           exact_tile_kernel (matrix)
+//   2 probe       nprobe nearest partitions per query     probe_select_kernel (warp / query)
+//   3 localise    l = q - c_p for every (query, probe)    localize_kernel
+//   4 ADC tables  t[di][ci] = |l_di - codebook[di][ci]|^2  exact_tile_kernel (matrix, nb = D)
+//   5 scan        dist(v) = sum_di t[di][code[v][di]] over the partition's code list;
+//                 128-bit coalesced loads of the u8 codes, table in shared memory;
+//                 n-best per partition                      scan_kernel (CTA / pair)
+//   6 merge       n-best over the probed partitions + sort merge_kernel (warp / query)
+// Device layout: codes are u8, partition-major, every partition's list starts on a
+// 16-byte boundary; ids are implicit positions (vector_index of QueryResult).
+#include "kmeans.cuh"
+
+#include <algorithm>
+#include <cstdlib>
+#include <memory>
+
+struct fdb_index {
+    fdb_ctx *ctx = nullptr;
+    size_t N = 0, P = 0, D = 0, C = 0, s = 0, M = 0;
+    fdb::DevBuf<float> coarse, codebooks;
+    fdb::DevBuf<uint8_t> codes;
+    fdb::DevBuf<uint32_t> part_off;    // [P+1] vectors before partition p
+    fdb::DevBuf<uint64_t> part_cstart; // [P] byte offset of the partition's code list
+    fdb::DevBuf<uint32_t> order;       // [M] global vector index at each partition-major position
+    std::vector<uint32_t> h_off;
+    std::vector<uint64_t> h_cstart;
+    // scratch
+    fdb::DevBuf<float> q_dev, dist, loc, tables, part_d, out_d, probe_d;
+    fdb::DevBuf<uint32_t> probes, part_v, part_cnt, out_p, out_v, out_c;
+    std::vector<cudaEvent_t> events;
+    float phase_ms[6] = {0, 0, 0, 0, 0, 0};
+    uint64_t scan_bytes = 0;
+    bool timing = false;
+    size_t chunk_pairs = 8192;
+};
+
+namespace fdb {
+namespace {
+
+constexpr float INF = __builtin_huge_valf();
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, off));
+    return v;
+}
+
+// ---- NBestByKey::push (src/nbest.rs:52-64), executed by one warp ---------------------
+// slots live in shared memory in the reference's slot order.  `maxd` caches the largest
+// key so that candidates that beat no slot are rejected without touching the slots
+// (exactly the candidates for which the reference's `find` returns None).
+struct WarpNBest {
+    float *d;
+    uint32_t *a;
+    int n, len;
+    float maxd;
+    __device__ void init(float *dd, uint32_t *aa, int nn) {
+        d = dd;
+        a = aa;
+        n = nn;
+        len = 0;
+        maxd = -INF;
+    }
+    __device__ void refresh_max(int lane) {
+        float m = -INF;
+        for (int s = lane; s < len; s += 32) m = fmaxf(m, d[s]);  // fmaxf drops NaN like `<` does
+        maxd = warp_max(m);
+    }
+    // all lanes call with the same candidate
+    __device__ void push(float cd, uint32_t ca, int lane) {
+        if (len < n) {
+            if (lane == 0) {
+                d[len] = cd;
+                a[len] = ca;
+            }
+            len++;
+            __syncwarp();
+            if (len == n) refresh_max(lane);
+            return;
+        }
+        if (!(cd < maxd)) return;
+        for (;;) {
+            int found = -1;
+            for (int base = 0; base < n; base += 32) {
+                const int s = base + lane;
+                const unsigned bal = __ballot_sync(0xffffffffu, s < n && cd < d[s]);
+                if (bal) {
+                    found = base + __ffs(bal) - 1;
+                    break;
+                }
+            }
+            if (found < 0) break;
+            const float od = d[found];
+            const uint32_t oa = a[found];
+            __syncwarp();
+            if (lane == 0) {
+                d[found] = cd;
+                a[found] = ca;
+            }
+            __syncwarp();
+            cd = od;
+            ca = oa;
+        }
+        refresh_max(lane);
+    }
+    // slice::sort_by(partial_cmp) on the slots: stable, so ties keep slot order.
+    // rank sort into (od, oa).
+    __device__ void sorted_out(float *od, uint32_t *oa, int lane) const {
+        for (int i = lane; i < len; i += 32) {
+            const float di = d[i];
+            int rank = 0;
+            for (int j = 0; j < len; ++j) {
+                const float dj = d[j];
+                rank += (dj < di) || (dj == di && j < i);
+            }
+            od[rank] = di;
+            oa[rank] = a[i];
+        }
+    }
+};
+
+// ---- "stable sort then truncate" (src/db/build.rs:334-337,370-371), by one warp -------
+// slots stay sorted; a candidate goes after every slot with key <= its key.
+struct WarpSorted {
+    float *d;
+    uint32_t *a;
+    int n, len;
+    __device__ void init(float *dd, uint32_t *aa, int nn) {
+        d = dd;
+        a = aa;
+        n = nn;
+        len = 0;
+    }
+    __device__ void push(float cd, uint32_t ca, int lane) {
+        if (len == n && !(cd < d[n - 1])) return;
+        int pos = len;
+        for (int base = 0; base < len; base += 32) {
+            const int s = base + lane;
+            const unsigned bal = __ballot_sync(0xffffffffu, s < len && cd < d[s]);
+            if (bal) {
+                pos = base + __ffs(bal) - 1;
+                break;
+            }
+        }
+        const int last = len < n ? len : n - 1;  // index that receives the shifted tail end
+        // shift [pos, last) right by one, highest first, 32 at a time
+        for (int hi = last; hi > pos;) {
+            const int lo = max(pos, hi - 32);
+            const int s = lo + lane;  // source index, moves to s+1
+            float td = 0.f;
+            uint32_t ta = 0;
+            const bool act = s < hi;
+            if (act) {
+                td = d[s];
+                ta = a[s];
+            }
+            __syncwarp();
+            if (act) {
+                d[s + 1] = td;
+                a[s + 1] = ta;
+            }
+            __syncwarp();
+            hi = lo;
+        }
+        if (lane == 0) {
+            d[pos] = cd;
+            a[pos] = ca;
+        }
+        if (len < n) len++;
+        __syncwarp();
+    }
+};
+
+// feed `cnt` keys (lane-parallel readable through key(i)) in index order
+template <typename KeyFn>
+__device__ void feed_nbest(WarpNBest &nb, int cnt, uint32_t payload0, KeyFn key, int lane) {
+    int i = 0;
+    for (; i < cnt && nb.len < nb.n; ++i) nb.push(key(i), payload0 + i, lane);  // fill phase
+    for (int base = i; base < cnt; base += 32) {
+        const int v = base + lane;
+        const float dv = v < cnt ? key(v) : INF;
+        unsigned bal = __ballot_sync(0xffffffffu, v < cnt && dv < nb.maxd);
+        while (bal) {
+            const int L = __ffs(bal) - 1;
+            bal &= bal - 1;
+            const float cd = __shfl_sync(0xffffffffu, dv, L);
+            nb.push(cd, payload0 + base + L, lane);
+        }
+    }
+}
+template <typename KeyFn>
+__device__ void feed_sorted(WarpSorted &sl, int cnt, uint32_t payload0, KeyFn key, int lane) {
+    int i = 0;
+    for (; i < cnt && sl.len < sl.n; ++i) sl.push(key(i), payload0 + i, lane);
+    for (int base = i; base < cnt; base += 32) {
+        const int v = base + lane;
+        const float dv = v < cnt ? key(v) : INF;
+        unsigned bal = __ballot_sync(0xffffffffu, v < cnt && dv < sl.d[sl.n - 1]);
+        while (bal) {
+            const int L = __ffs(bal) - 1;
+            bal &= bal - 1;
+            const float cd = __shfl_sync(0xffffffffu, dv, L);
+            sl.push(cd, payload0 + base + L, lane);
+        }
+    }
+}
+
+// ---- 2: probe selection (src/db/stored.rs:411-426 / src/db/build.rs:357-371) -----------
+constexpr int PROBE_WARPS = 4;
+__global__ void __launch_bounds__(PROBE_WARPS * 32) probe_select_kernel(
+    const float *dist, size_t nq, size_t P, int nprobe, int mode, uint32_t *probes, float *probe_d,
+    unsigned *flags) {
+    extern __shared__ unsigned char sm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t q = (size_t)blockIdx.x * PROBE_WARPS + warp;
+    if (q >= nq) return;
+    float *sd = reinterpret_cast<float *>(sm) + (size_t)warp * 2 * nprobe;
+    uint32_t *sa = reinterpret_cast<uint32_t *>(sd + nprobe);
+    const float *dq = dist + q * P;
+    auto key = [&](int i) { return dq[i]; };
+    uint32_t *op = probes + q * nprobe;
+    float *od = probe_d + q * nprobe;
+    bool nan = false;
+    if (mode == FDB_QUERY_STORED) {
+        WarpNBest nb;
+        nb.init(sd, sa, nprobe);
+        feed_nbest(nb, (int)P, 0u, key, lane);
+        __syncwarp();
+        nb.sorted_out(od, op, lane);
+        for (int i = lane; i < nb.len; i += 32) nan |= sd[i] != sd[i];
+    } else {
+        WarpSorted sl;
+        sl.init(sd, sa, nprobe);
+        feed_sorted(sl, (int)P, 0u, key, lane);
+        __syncwarp();
+        for (int i = lane; i < sl.len; i += 32) {
+            od[i] = sd[i];
+            op[i] = sa[i];
+        }
+        for (int i = lane; i < (int)P; i += 32) nan |= dq[i] != dq[i];  // the full sort sees every key
+    }
+    if (nan && (mode == FDB_QUERY_STORED ? nprobe > 1 : P > 1)) atomicOr(flags, FLAG_NAN);  // partial_cmp().unwrap()
+}
+
+// ---- 3: localise (src/db/stored.rs:421) ----------------------------------------------
+__global__ void localize_kernel(const float *q, const float *coarse, const uint32_t *probes,
+                                size_t pair0, size_t npairs, size_t nprobe, size_t N, float *loc) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= npairs * N) return;
+    const size_t pr = t / N, e = t - pr * N;
+    const size_t pair = pair0 + pr;
+    const size_t qi = pair / nprobe;
+    loc[t] = __fsub_rn(q[qi * N + e], coarse[(size_t)probes[pair] * N + e]);
+}
+
+// ---- 5: code scan + per-partition selection (src/db/stored.rs:575-596) -----------------
+struct ScanParams {
+    const float *tables;      // [npairs_chunk][D][C]
+    const uint8_t *codes;
+    const uint32_t *part_off;
+    const uint64_t *part_cstart;
+    const uint32_t *probes;   // [nq][nprobe]
+    size_t pair0, D, C;
+    int k, mode, chunk_vecs;
+    float *part_d;            // [npairs][k]
+    uint32_t *part_v;
+    uint32_t *part_cnt;
+};
+
+constexpr int SCAN_THREADS = 128;
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(ScanParams p) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    const size_t DC = p.D * p.C;
+    float *table = reinterpret_cast<float *>(sm);
+    float *dbuf = table + DC;
+    float *sd = dbuf + p.chunk_vecs;
+    uint32_t *sa = reinterpret_cast<uint32_t *>(sd + p.k);
+    unsigned char *cs = reinterpret_cast<unsigned char *>(sa + p.k);
+    cs += (16 - ((uintptr_t)cs & 15)) & 15;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t pair = p.pair0 + blockIdx.x;
+    const uint32_t part = p.probes[pair];
+    const float *tg = p.tables + (size_t)blockIdx.x * DC;
+    if ((DC & 3) == 0) {
+        for (size_t i = tid; i < DC / 4; i += SCAN_THREADS)
+            reinterpret_cast<float4 *>(table)[i] = reinterpret_cast<const float4 *>(tg)[i];
+    } else {
+        for (size_t i = tid; i < DC; i += SCAN_THREADS) table[i] = tg[i];
+    }
+    const int np = (int)(p.part_off[part + 1] - p.part_off[part]);
+    const uint8_t *cg = p.codes + p.part_cstart[part];
+    const int D = (int)p.D, C = (int)p.C;
+
+    WarpNBest nb;
+    WarpSorted sl;
+    nb.init(sd, sa, p.k);
+    sl.init(sd, sa, p.k);
+
+    for (int c0 = 0; c0 < np; c0 += p.chunk_vecs) {
+        const int cnt = min(p.chunk_vecs, np - c0);
+        // 128-bit coalesced copy of the chunk's codes (lists are padded to 16 bytes)
+        const size_t nbytes = ((size_t)cnt * D + 15) & ~(size_t)15;
+        const uint4 *src = reinterpret_cast<const uint4 *>(cg + (size_t)c0 * D);
+        __syncthreads();  // previous chunk fully consumed (also covers the table load)
+        for (size_t i = tid; i < nbytes / 16; i += SCAN_THREADS)
+            reinterpret_cast<uint4 *>(cs)[i] = __ldg(src + i);
+        __syncthreads();
+        if ((D & 3) == 0) {
+            const int W = D >> 2;
+            for (int v = tid; v < cnt; v += SCAN_THREADS) {
+                const uint32_t *cw = reinterpret_cast<const uint32_t *>(cs) + (size_t)v * W;
+                float dist = 0.0f;  // sequential f32 adds over divisions, :582-587
+                for (int w = 0; w < W; ++w) {
+                    const uint32_t x = cw[w];
+                    const float *t = table + (size_t)(4 * w) * C;
+                    dist = __fadd_rn(dist, t[x & 255u]);
+                    dist = __fadd_rn(dist, t[C + ((x >> 8) & 255u)]);
+                    dist = __fadd_rn(dist, t[2 * C + ((x >> 16) & 255u)]);
+                    dist = __fadd_rn(dist, t[3 * C + (x >> 24)]);
+                }
+                dbuf[v] = dist;
+            }
+        } else {
+            for (int v = tid; v < cnt; v += SCAN_THREADS) {
+                float dist = 0.0f;
+                for (int di = 0; di < D; ++di)
+                    dist = __fadd_rn(dist, table[(size_t)di * C + cs[(size_t)v * D + di]]);
+                dbuf[v] = dist;
+            }
+        }
+        __syncthreads();
+        if (warp == 0) {
+            auto key = [&](int i) { return dbuf[i]; };
+            if (p.mode == FDB_QUERY_STORED) feed_nbest(nb, cnt, (uint32_t)c0, key, lane);
+            else feed_sorted(sl, cnt, (uint32_t)c0, key, lane);
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const int len = p.mode == FDB_QUERY_STORED ? nb.len : sl.len;
+        for (int i = lane; i < len; i += 32) {
+            p.part_d[pair * p.k + i] = sd[i];
+            p.part_v[pair * p.k + i] = sa[i];
+        }
+        if (lane == 0) p.part_cnt[pair] = (uint32_t)len;
+    }
+}
+
+// ---- 6: merge across probed partitions (src/db/stored.rs:379-386 / build.rs:334-337) ----
+constexpr int MERGE_WARPS = 4;
+__global__ void __launch_bounds__(MERGE_WARPS * 32) merge_kernel(
+    const float *part_d, const uint32_t *part_v, const uint32_t *part_cnt, const uint32_t *probes,
+    size_t nq, int nprobe, int k, int mode, uint32_t *out_p, uint32_t *out_v, float *out_d,
+    uint32_t *out_c, unsigned *flags) {
+    extern __shared__ unsigned char sm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t q = (size_t)blockIdx.x * MERGE_WARPS + warp;
+    if (q >= nq) return;
+    float *sd = reinterpret_cast<float *>(sm) + (size_t)warp * 4 * k;
+    uint32_t *sa = reinterpret_cast<uint32_t *>(sd + k);
+    float *fd = reinterpret_cast<float *>(sa + k);
+    uint32_t *fa = reinterpret_cast<uint32_t *>(fd + k);
+    WarpNBest nb;
+    WarpSorted sl;
+    nb.init(sd, sa, k);
+    sl.init(sd, sa, k);
+    bool nan = false;
+    for (int pr = 0; pr < nprobe; ++pr) {
+        const size_t pair = q * nprobe + pr;
+        const int cnt = (int)part_cnt[pair];
+        const float *pd = part_d + pair * k;
+        auto key = [&](int i) { return pd[i]; };
+        // payload = flat position pr*k + slot; flatten() visits partitions in probe order
+        if (mode == FDB_QUERY_STORED) feed_nbest(nb, cnt, (uint32_t)(pr * k), key, lane);
+        else feed_sorted(sl, cnt, (uint32_t)(pr * k), key, lane);
+    }
+    __syncwarp();
+    int len;
+    const float *rd;
+    const uint32_t *ra;
+    if (mode == FDB_QUERY_STORED) {
+        len = nb.len;
+        nb.sorted_out(fd, fa, lane);
+        __syncwarp();
+        rd = fd;
+        ra = fa;
+    } else {
+        len = sl.len;
+        rd = sd;
+        ra = sa;
+    }
+    for (int i = lane; i < len; i += 32) {
+        const uint32_t flat = ra[i];
+        const uint32_t pr = flat / (uint32_t)k, slot = flat - pr * (uint32_t)k;
+        const size_t pair = q * nprobe + pr;
+        out_p[q * k + i] = probes[pair];
+        out_v[q * k + i] = part_v[pair * k + slot];
+        out_d[q * k + i] = rd[i];
+        nan |= rd[i] != rd[i];
+    }
+    if (lane == 0) out_c[q] = (uint32_t)len;
+    if (nan && len > 1) atomicOr(flags, FLAG_NAN);
+}
+
+// ---- Partition::new on the device (src/db/build.rs:459-473) ----------------------------
+__global__ void gather_codes_kernel(const uint32_t *order, const uint32_t *coarse_idx,
+                                    const uint32_t *pq_idx, const uint32_t *part_off,
+                                    const uint64_t *part_cstart, size_t M, size_t D, uint8_t *codes) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= M * D) return;
+    const size_t pos = t / D, di = t - pos * D;
+    const uint32_t v = order[pos];
+    const uint32_t part = coarse_idx[v];
+    codes[part_cstart[part] + (pos - part_off[part]) * D + di] = (uint8_t)pq_idx[di * M + v];
+}
+
+}  // namespace
+}  // namespace fdb
+
+using namespace fdb;
+
+#define ARG(cond, ...)                   \
+    do {                                 \
+        if (!(cond)) {                   \
+            set_error(__VA_ARGS__);      \
+            return FDB_ERR_INVALID_ARGS; \
+        }                                \
+    } while (0)
+
+static int index_alloc(fdb_ctx *ctx, size_t N, size_t P, size_t D, size_t C, fdb_index **out) {
+    ARG(ctx && out, "null argument");
+    ARG(N > 0 && P > 0 && D > 0 && C > 0, "N, P, D, C must be non-zero");
+    ARG(N % D == 0, "vector size (%zu) is not divisible by %zu (src/vector.rs:163-169)", N, D);
+    if (C > 256) {
+        set_error("C = %zu > 256: the device code layout stores u8 codes", C);
+        return FDB_ERR_UNSUPPORTED;
+    }
+    std::unique_ptr<fdb_index> ix(new fdb_index);
+    ix->ctx = ctx;
+    ix->N = N;
+    ix->P = P;
+    ix->D = D;
+    ix->C = C;
+    ix->s = N / D;
+    if (const char *e = getenv("FDB_QUERY_CHUNK_PAIRS")) ix->chunk_pairs = (size_t)std::max(1L, atol(e));
+    if (const char *e = getenv("FDB_QUERY_TIMING")) ix->timing = atoi(e) != 0;
+    FDB_TRY(ctx->use());
+    FDB_TRY(ix->coarse.alloc(P * N));
+    FDB_TRY(ix->codebooks.alloc(D * C * ix->s));
+    FDB_TRY(ix->part_off.alloc(P + 1));
+    FDB_TRY(ix->part_cstart.alloc(P));
+    *out = ix.release();
+    return FDB_OK;
+}
+
+// offsets (vectors) -> 16-byte aligned byte starts of the code lists
+static int index_layout(fdb_index *ix, const std::vector<uint32_t> &off) {
+    ix->h_off = off;
+    ix->h_cstart.resize(ix->P);
+    uint64_t cur = 0;
+    for (size_t p = 0; p < ix->P; ++p) {
+        ix->h_cstart[p] = cur;
+        cur += ((uint64_t)(off[p + 1] - off[p]) * ix->D + 15) & ~(uint64_t)15;
+    }
+    ix->M = off[ix->P];
+    FDB_TRY(ix->codes.alloc(cur + 16));
+    cudaStream_t st = ix->ctx->stream;
+    FDB_CUDA(cudaMemsetAsync(ix->codes.p, 0, cur + 16, st));
+    FDB_CUDA(cudaMemcpyAsync(ix->part_off.p, ix->h_off.data(), (ix->P + 1) * sizeof(uint32_t),
+                             cudaMemcpyHostToDevice, st));
+    FDB_CUDA(cudaMemcpyAsync(ix->part_cstart.p, ix->h_cstart.data(), ix->P * sizeof(uint64_t),
+                             cudaMemcpyHostToDevice, st));
+    FDB_CUDA(cudaStreamSynchronize(st));
+    return FDB_OK;
+}
+
+extern "C" {
+
+int fdb_index_create(fdb_ctx *ctx, size_t N, size_t P, size_t D, size_t C, const float *coarse,
+                     const float *codebooks, const uint64_t *offsets, const uint8_t *codes,
+                     fdb_index **out) {
+    ARG(coarse && codebooks && offsets && out, "null argument");
+    *out = nullptr;
+    fdb_index *raw = nullptr;
+    FDB_TRY(index_alloc(ctx, N, P, D, C, &raw));
+    std::unique_ptr<fdb_index> ix(raw);
+    std::vector<uint32_t> off(P + 1);
+    for (size_t p = 0; p <= P; ++p) {
+        if (offsets[p] >= (1ull << 32) || (p && offsets[p] < offsets[p - 1]) || offsets[0] != 0) {
+            set_error("partition offsets must start at 0, be non-decreasing and fit 32 bits");
+            return FDB_ERR_INVALID_DATA;
+        }
+        off[p] = (uint32_t)offsets[p];
+    }
+    ARG(codes || off[P] == 0, "codes is null");
+    FDB_TRY(index_layout(ix.get(), off));
+    cudaStream_t st = ctx->stream;
+    FDB_CUDA(cudaMemcpyAsync(ix->coarse.p, coarse, P * N * sizeof(float), cudaMemcpyHostToDevice, st));
+    FDB_CUDA(cudaMemcpyAsync(ix->codebooks.p, codebooks, D * C * ix->s * sizeof(float),
+                             cudaMemcpyHostToDevice, st));
+    for (size_t p = 0; p < P; ++p) {
+        const size_t bytes = (size_t)(off[p + 1] - off[p]) * D;
+        if (bytes)
+            FDB_CUDA(cudaMemcpyAsync(ix->codes.p + ix->h_cstart[p], codes + (size_t)off[p] * D, bytes,
+                                     cudaMemcpyHostToDevice, st));
+    }
+    FDB_CUDA(cudaStreamSynchronize(st));
+    *out = ix.release();
+    return FDB_OK;
+}
+
+int fdb_index_from_build(fdb_ctx *ctx, const fdb_km *coarse, const fdb_km *pq, fdb_index **out) {
+    ARG(ctx && coarse && pq && out, "null argument");
+    *out = nullptr;
+    ARG(coarse->nb == 1 && coarse->vs == pq->vs && coarse->n == pq->n, "coarse / pq mismatch");
+    ARG(coarse->m == pq->nb * pq->m && coarse->col_off == 0 && pq->col_off == 0,
+        "pq must divide the full vectors");
+    const size_t N = coarse->m, P = coarse->k, D = pq->nb, C = pq->k, M = coarse->n;
+    fdb_index *raw = nullptr;
+    FDB_TRY(index_alloc(ctx, N, P, D, C, &raw));
+    std::unique_ptr<fdb_index> ix(raw);
+    cudaStream_t st = ctx->stream;
+    // members grouped by partition in ascending vector index == Partition::new's filter order
+    fdb_km *ckm = const_cast<fdb_km *>(coarse);
+    FDB_TRY(km_sort_members(ckm, nullptr));
+    std::vector<uint32_t> off(P + 1);
+    FDB_CUDA(cudaMemcpyAsync(off.data(), ckm->cl_off.p, (P + 1) * sizeof(uint32_t),
+                             cudaMemcpyDeviceToHost, st));
+    FDB_CUDA(cudaStreamSynchronize(st));
+    FDB_TRY(index_layout(ix.get(), off));
+    FDB_TRY(ix->order.alloc(M));
+    FDB_CUDA(cudaMemcpyAsync(ix->order.p, ckm->members.p, M * sizeof(uint32_t),
+                             cudaMemcpyDeviceToDevice, st));
+    FDB_CUDA(cudaMemcpyAsync(ix->coarse.p, coarse->centroids.p, P * N * sizeof(float),
+                             cudaMemcpyDeviceToDevice, st));
+    FDB_CUDA(cudaMemcpyAsync(ix->codebooks.p, pq->centroids.p, D * C * ix->s * sizeof(float),
+                             cudaMemcpyDeviceToDevice, st));
+    if (M) {
+        gather_codes_kernel<<<(unsigned)((M * D + 255) / 256), 256, 0, st>>>(
+            ix->order.p, coarse->indices.p, pq->indices.p, ix->part_off.p, ix->part_cstart.p, M, D,
+            ix->codes.p);
+        ctx->launches++;
+        FDB_CHECK_LAUNCH();
+    }
+    FDB_CUDA(cudaStreamSynchronize(st));
+    *out = ix.release();
+    return FDB_OK;
+}
+
+int fdb_index_get_layout(fdb_index *ix, uint64_t *offsets, uint32_t *order, uint8_t *codes) {
+    ARG(ix, "ix is null");
+    FDB_TRY(ix->ctx->use());
+    cudaStream_t st = ix->ctx->stream;
+    if (offsets)
+        for (size_t p = 0; p <= ix->P; ++p) offsets[p] = ix->h_off[p];
+    if (order) {
+        ARG(ix->order.p, "index was not created from a build: no order");
+        FDB_CUDA(cudaMemcpyAsync(order, ix->order.p, ix->M * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    }
+    if (codes)
+        for (size_t p = 0; p < ix->P; ++p) {
+            const size_t bytes = (size_t)(ix->h_off[p + 1] - ix->h_off[p]) * ix->D;
+            if (bytes)
+                FDB_CUDA(cudaMemcpyAsync(codes + (size_t)ix->h_off[p] * ix->D,
+                                         ix->codes.p + ix->h_cstart[p], bytes, cudaMemcpyDeviceToHost, st));
+        }
+    FDB_CUDA(cudaStreamSynchronize(st));
+    return FDB_OK;
+}
+
+size_t fdb_index_num_vectors(const fdb_index *ix) { return ix ? ix->M : 0; }
+
+void fdb_index_destroy(fdb_index *ix) {
+    if (!ix) return;
+    cudaSetDevice(ix->ctx->device);
+    cudaStreamSynchronize(ix->ctx->stream);
+    for (cudaEvent_t e : ix->events) cudaEventDestroy(e);
+    delete ix;
+}
+
+}  // extern "C"
+
+namespace {
+
+struct EventLog {
+    fdb_index *ix;
+    size_t used = 0;
+    std::vector<std::pair<int, size_t>> marks;  // (phase, index of the start event)
+    int mark(int phase) {                        // records start; end = next event
+        if (!ix->timing) return FDB_OK;
+        if (used == ix->events.size()) {
+            cudaEvent_t e;
+            FDB_CUDA(cudaEventCreate(&e));
+            ix->events.push_back(e);
+        }
+        FDB_CUDA(cudaEventRecord(ix->events[used], ix->ctx->stream));
+        marks.emplace_back(phase, used);
+        used++;
+        return FDB_OK;
+    }
+    int finish() {
+        for (int i = 0; i < 6; ++i) ix->phase_ms[i] = 0.f;
+        if (!ix->timing) return FDB_OK;
+        for (size_t i = 0; i + 1 < marks.size(); ++i) {
+            if (marks[i].first < 0) continue;
+            float ms = 0.f;
+            FDB_CUDA(cudaEventElapsedTime(&ms, ix->events[marks[i].second], ix->events[marks[i + 1].second]));
+            ix->phase_ms[marks[i].first] += ms;
+        }
+        return FDB_OK;
+    }
+};
+
+int probe_device(fdb_index *ix, const float *d_q, size_t nq, size_t nprobe, int mode, EventLog *log) {
+    fdb_ctx *ctx = ix->ctx;
+    FDB_TRY(ix->dist.ensure(nq * ix->P));
+    FDB_TRY(ix->probes.ensure(nq * nprobe));
+    FDB_TRY(ix->probe_d.ensure(nq * nprobe));
+    if (log) FDB_TRY(log->mark(0));
+    DistProblem dp;
+    dp.x = d_q;
+    dp.n = nq;
+    dp.ldx = ix->N;
+    dp.col_off = 0;
+    dp.m = ix->N;
+    dp.nb = 1;
+    dp.c = ix->coarse.p;
+    dp.k = ix->P;
+    FDB_TRY(launch_exact_matrix(ctx, dp, ix->dist.p));
+    if (log) FDB_TRY(log->mark(1));
+    const size_t smem = (size_t)PROBE_WARPS * 2 * nprobe * sizeof(float);
+    probe_select_kernel<<<(unsigned)((nq + PROBE_WARPS - 1) / PROBE_WARPS), PROBE_WARPS * 32, smem,
+                          ctx->stream>>>(ix->dist.p, nq, ix->P, (int)nprobe, mode, ix->probes.p,
+                                         ix->probe_d.p, ctx->d_flags);
+    ctx->launches++;
+    FDB_CHECK_LAUNCH();
+    return FDB_OK;
+}
+
+int check_query_args(fdb_index *ix, size_t nq, size_t k, size_t nprobe, int mode) {
+    ARG(ix, "ix is null");
+    ARG(k > 0 && nprobe > 0, "k and nprobe must be non-zero (NonZeroUsize)");
+    ARG(mode == FDB_QUERY_STORED || mode == FDB_QUERY_BUILD, "unknown mode %d", mode);
+    /* src/db/stored.rs:403-409 */
+    ARG(nprobe <= ix->P, "nprobe %zu exceeds the number of partitions %zu", nprobe, ix->P);
+    if (k > 1024 || nprobe > 1024 || nq * nprobe >= (1ull << 31) || k * nprobe >= (1ull << 31)) {
+        set_error("unsupported query shape: nq=%zu k=%zu nprobe=%zu", nq, k, nprobe);
+        return FDB_ERR_UNSUPPORTED;
+    }
+    return FDB_OK;
+}
+
+int query_device(fdb_index *ix, const float *d_q, size_t nq, size_t k, size_t nprobe, int mode,
+                 uint32_t *d_p, uint32_t *d_v, float *d_d, uint32_t *d_c) {
+    fdb_ctx *ctx = ix->ctx;
+    EventLog log{ix};
+    ix->scan_bytes = 0;
+    if (nq == 0) return FDB_OK;
+    FDB_TRY(probe_device(ix, d_q, nq, nprobe, mode, &log));
+    const size_t npairs = nq * nprobe;
+    const size_t DC = ix->D * ix->C;
+    const size_t chunk = std::min(npairs, ix->chunk_pairs);
+    FDB_TRY(ix->loc.ensure(chunk * ix->N));
+    FDB_TRY(ix->tables.ensure(chunk * DC));
+    FDB_TRY(ix->part_d.ensure(npairs * k));
+    FDB_TRY(ix->part_v.ensure(npairs * k));
+    FDB_TRY(ix->part_cnt.ensure(npairs));
+
+    int chunk_vecs = (int)std::min<size_t>(1024, std::max<size_t>(32, (16384 / ix->D) & ~(size_t)31));
+    const size_t scan_smem = DC * 4 + (size_t)chunk_vecs * 4 + k * 8 + (size_t)chunk_vecs * ix->D + 32;
+    if (scan_smem > 200 * 1024) {
+        set_error("ADC table too large for shared memory: D*C = %zu", DC);
+        return FDB_ERR_UNSUPPORTED;
+    }
+    FDB_CUDA(cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem));
+
+    for (size_t pair0 = 0; pair0 < npairs; pair0 += chunk) {
+        const size_t np = std::min(chunk, npairs - pair0);
+        FDB_TRY(log.mark(2));
+        localize_kernel<<<(unsigned)((np * ix->N + 255) / 256), 256, 0, ctx->stream>>>(
+            d_q, ix->coarse.p, ix->probes.p, pair0, np, nprobe, ix->N, ix->loc.p);
+        ctx->launches++;
+        FDB_TRY(log.mark(3));
+        DistProblem dp;
+        dp.x = ix->loc.p;
+        dp.n = np;
+        dp.ldx = ix->N;
+        dp.col_off = 0;
+        dp.m = ix->s;
+        dp.nb = ix->D;
+        dp.c = ix->codebooks.p;
+        dp.k = ix->C;
+        FDB_TRY(launch_exact_matrix(ctx, dp, ix->tables.p));
+        FDB_TRY(log.mark(4));
+        ScanParams sp;
+        sp.tables = ix->tables.p;
+        sp.codes = ix->codes.p;
+        sp.part_off = ix->part_off.p;
+        sp.part_cstart = ix->part_cstart.p;
+        sp.probes = ix->probes.p;
+        sp.pair0 = pair0;
+        sp.D = ix->D;
+        sp.C = ix->C;
+        sp.k = (int)k;
+        sp.mode = mode;
+        sp.chunk_vecs = chunk_vecs;
+        sp.part_d = ix->part_d.p;
+        sp.part_v = ix->part_v.p;
+        sp.part_cnt = ix->part_cnt.p;
+        scan_kernel<<<(unsigned)np, SCAN_THREADS, scan_smem, ctx->stream>>>(sp);
+        ctx->launches++;
+        FDB_CHECK_LAUNCH();
+    }
+    FDB_TRY(log.mark(5));
+    const size_t msmem = (size_t)MERGE_WARPS * 4 * k * sizeof(float);
+    merge_kernel<<<(unsigned)((nq + MERGE_WARPS - 1) / MERGE_WARPS), MERGE_WARPS * 32, msmem, ctx->stream>>>(
+        ix->part_d.p, ix->part_v.p, ix->part_cnt.p, ix->probes.p, nq, (int)nprobe, (int)k, mode, d_p,
+        d_v, d_d, d_c, ctx->d_flags);
+    ctx->launches++;
+    FDB_CHECK_LAUNCH();
+    FDB_TRY(log.mark(-1));
+    // algorithmic scan bytes: sum over probed partitions of n_p * D
+    if (ix->timing) {
+        std::vector<uint32_t> hp(npairs);
+        FDB_CUDA(cudaMemcpyAsync(hp.data(), ix->probes.p, npairs * sizeof(uint32_t),
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+        FDB_CUDA(cudaStreamSynchronize(ctx->stream));
+        uint64_t bytes = 0;
+        for (uint32_t pp : hp) bytes += (uint64_t)(ix->h_off[pp + 1] - ix->h_off[pp]) * ix->D;
+        ix->scan_bytes = bytes;
+        FDB_TRY(log.finish());
+    }
+    return FDB_OK;
+}
+
+int finish_query(fdb_ctx *ctx) {
+    unsigned f = 0;
+    FDB_TRY(ctx->check_flags(&f));
+    return map_flags(f);
+}
+
+}  // namespace
+
+extern "C" {
+
+int fdb_index_query_device(fdb_index *ix, const float *d_queries, size_t nq, size_t k, size_t nprobe,
+                           int mode, uint32_t *d_partition, uint32_t *d_vector_index,
+                           float *d_sqdist, uint32_t *d_count) {
+    FDB_TRY(check_query_args(ix, nq, k, nprobe, mode));
+    ARG(nq == 0 || (d_queries && d_partition && d_vector_index && d_sqdist && d_count), "null argument");
+    FDB_TRY(ix->ctx->use());
+    FDB_TRY(query_device(ix, d_queries, nq, k, nprobe, mode, d_partition, d_vector_index, d_sqdist, d_count));
+    return finish_query(ix->ctx);
+}
+
+int fdb_index_query(fdb_index *ix, const float *queries, size_t nq, size_t k, size_t nprobe, int mode,
+                    uint32_t *out_partition, uint32_t *out_vector_index, float *out_sqdist,
+                    uint32_t *out_count) {
+    FDB_TRY(check_query_args(ix, nq, k, nprobe, mode));
+    ARG(nq == 0 || (queries && out_partition && out_vector_index && out_sqdist && out_count),
+        "null argument");
+    if (nq == 0) return FDB_OK;
+    fdb_ctx *ctx = ix->ctx;
+    FDB_TRY(ctx->use());
+    cudaStream_t st = ctx->stream;
+    FDB_TRY(ix->q_dev.ensure(nq * ix->N));
+    FDB_TRY(ix->out_p.ensure(nq * k));
+    FDB_TRY(ix->out_v.ensure(nq * k));
+    FDB_TRY(ix->out_d.ensure(nq * k));
+    FDB_TRY(ix->out_c.ensure(nq));
+    FDB_CUDA(cudaMemcpyAsync(ix->q_dev.p, queries, nq * ix->N * sizeof(float), cudaMemcpyHostToDevice, st));
+    FDB_TRY(query_device(ix, ix->q_dev.p, nq, k, nprobe, mode, ix->out_p.p, ix->out_v.p, ix->out_d.p,
+                         ix->out_c.p));
+    FDB_CUDA(cudaMemcpyAsync(out_partition, ix->out_p.p, nq * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    FDB_CUDA(cudaMemcpyAsync(out_vector_index, ix->out_v.p, nq * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    FDB_CUDA(cudaMemcpyAsync(out_sqdist, ix->out_d.p, nq * k * sizeof(float), cudaMemcpyDeviceToHost, st));
+    FDB_CUDA(cudaMemcpyAsync(out_count, ix->out_c.p, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    return finish_query(ctx);
+}
+
+int fdb_index_probe(fdb_index *ix, const float *queries, size_t nq, size_t nprobe, int mode,
+                    uint32_t *out_partition, float *out_sqdist) {
+    FDB_TRY(check_query_args(ix, nq, 1, nprobe, mode));
+    ARG(nq == 0 || (queries && out_partition), "null argument");
+    if (nq == 0) return FDB_OK;
+    fdb_ctx *ctx = ix->ctx;
+    FDB_TRY(ctx->use());
+    cudaStream_t st = ctx->stream;
+    FDB_TRY(ix->q_dev.ensure(nq * ix->N));
+    FDB_CUDA(cudaMemcpyAsync(ix->q_dev.p, queries, nq * ix->N * sizeof(float), cudaMemcpyHostToDevice, st));
+    FDB_TRY(probe_device(ix, ix->q_dev.p, nq, nprobe, mode, nullptr));
+    FDB_CUDA(cudaMemcpyAsync(out_partition, ix->probes.p, nq * nprobe * sizeof(uint32_t),
+                             cudaMemcpyDeviceToHost, st));
+    if (out_sqdist)
+        FDB_CUDA(cudaMemcpyAsync(out_sqdist, ix->probe_d.p, nq * nprobe * sizeof(float),
+                                 cudaMemcpyDeviceToHost, st));
+    return finish_query(ctx);
+}
+
+int fdb_index_table(fdb_index *ix, const float *query, uint32_t partition, float *table) {
+    ARG(ix && query && table, "null argument");
+    ARG(partition < ix->P, "partition out of range");
+    fdb_ctx *ctx = ix->ctx;
+    FDB_TRY(ctx->use());
+    cudaStream_t st = ctx->stream;
+    const size_t DC = ix->D * ix->C;
+    FDB_TRY(ix->q_dev.ensure(ix->N));
+    FDB_TRY(ix->probes.ensure(1));
+    FDB_TRY(ix->loc.ensure(ix->N));
+    FDB_TRY(ix->tables.ensure(DC));
+    FDB_CUDA(cudaMemcpyAsync(ix->q_dev.p, query, ix->N * sizeof(float), cudaMemcpyHostToDevice, st));
+    FDB_CUDA(cudaMemcpyAsync(ix->probes.p, &partition, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    FDB_CUDA(cudaStreamSynchronize(st));
+    localize_kernel<<<(unsigned)((ix->N + 255) / 256), 256, 0, st>>>(ix->q_dev.p, ix->coarse.p,
+                                                                    ix->probes.p, 0, 1, 1, ix->N, ix->loc.p);
+    ctx->launches++;
+    DistProblem dp;
+    dp.x = ix->loc.p;
+    dp.n = 1;
+    dp.ldx = ix->N;
+    dp.col_off = 0;
+    dp.m = ix->s;
+    dp.nb = ix->D;
+    dp.c = ix->codebooks.p;
+    dp.k = ix->C;
+    FDB_TRY(launch_exact_matrix(ctx, dp, ix->tables.p));
+    FDB_CUDA(cudaMemcpyAsync(table, ix->tables.p, DC * sizeof(float), cudaMemcpyDeviceToHost, st));
+    return finish_query(ctx);
+}
+
+int fdb_index_set_timing(fdb_index *ix, int enabled) {
+    ARG(ix, "ix is null");
+    ix->timing = enabled != 0;
+    return FDB_OK;
+}
+
+int fdb_index_last_timing(fdb_index *ix, float ms[6], uint64_t *scan_bytes) {
+    ARG(ix && ms, "null argument");
+    for (int i = 0; i < 6; ++i) ms[i] = ix->phase_ms[i];
+    if (scan_bytes) *scan_bytes = ix->scan_bytes;
+    return FDB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,277 @@
+"""Thin object wrappers over the C ABI handles (fdb_ctx / fdb_vs / fdb_km / fdb_index).
+
+Nothing is computed here: every method is one call into libflechasdb_b200.so.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi as capi
+from ._capi import check, f32p, u32p, u64p, u8p, as_f32, as_u32, VP
+
+
+class Context:
+    def __init__(self, device=0):
+        self.h = VP()
+        check(capi.lib().fdb_ctx_create(device, C.byref(self.h)))
+        self.device = device
+
+    def sync(self):
+        check(capi.lib().fdb_ctx_sync(self.h))
+
+    def timer_start(self):
+        check(capi.lib().fdb_ctx_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        check(capi.lib().fdb_ctx_timer_stop(self.h, C.byref(ms)))
+        return float(ms.value)
+
+    @property
+    def launches(self):
+        return int(capi.lib().fdb_ctx_launch_count(self.h))
+
+    def flush_l2(self):
+        check(capi.lib().fdb_device_flush_l2(self.h))
+
+    def alloc(self, nbytes):
+        p = VP()
+        check(capi.lib().fdb_device_alloc(self.h, nbytes, C.byref(p)))
+        return p
+
+    def free(self, p):
+        check(capi.lib().fdb_device_free(self.h, p))
+
+    def fill_uniform(self, dptr, count, seed, start=0):
+        check(capi.lib().fdb_device_fill_uniform(self.h, dptr, count, seed, start))
+
+    def close(self):
+        if self.h:
+            capi.lib().fdb_ctx_destroy(self.h)
+            self.h = VP()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+class VectorSet:
+    """BlockVectorSet<f32> in HBM (src/vector.rs:28-100)."""
+
+    def __init__(self, ctx, handle):
+        self.ctx = ctx
+        self.h = handle
+
+    @classmethod
+    def upload(cls, ctx, rows):
+        rows = as_f32(rows)
+        assert rows.ndim == 2
+        h = VP()
+        check(capi.lib().fdb_vs_upload(ctx.h, f32p(rows), rows.shape[0], rows.shape[1], C.byref(h)))
+        return cls(ctx, h)
+
+    @classmethod
+    def generate(cls, ctx, n, dim, seed, start=0):
+        h = VP()
+        check(capi.lib().fdb_vs_generate(ctx.h, n, dim, seed, start, C.byref(h)))
+        return cls(ctx, h)
+
+    def __len__(self):
+        return int(capi.lib().fdb_vs_len(self.h))
+
+    @property
+    def vector_size(self):
+        return int(capi.lib().fdb_vs_vector_size(self.h))
+
+    def download(self, first=0, nrows=None):
+        nrows = len(self) - first if nrows is None else nrows
+        out = np.empty((nrows, self.vector_size), np.float32)
+        check(capi.lib().fdb_vs_download_rows(self.h, first, nrows, f32p(out)))
+        return out
+
+    def subtract_assigned(self, km):
+        check(capi.lib().fdb_vs_subtract_assigned(self.h, km.h))
+
+    def close(self):
+        if self.h:
+            capi.lib().fdb_vs_destroy(self.h)
+            self.h = VP()
+
+
+class KMeans:
+    """nb side-by-side k-means problems over strided sub-vector views (src/kmeans.rs)."""
+
+    def __init__(self, vs, k, col_off=0, dim=None, nb=1):
+        dim = vs.vector_size if dim is None else dim
+        self.vs, self.k, self.dim, self.nb, self.n = vs, k, dim, nb, len(vs)
+        self.h = VP()
+        check(capi.lib().fdb_kmeans_begin(vs.h, col_off, dim, nb, k, C.byref(self.h)))
+
+    def seed_first(self, ci):
+        ci = as_u32(np.atleast_1d(ci))
+        check(capi.lib().fdb_kmeans_seed_first(self.h, u32p(ci)))
+
+    def seed_total(self):
+        t = np.zeros(self.nb, np.float32)
+        check(capi.lib().fdb_kmeans_seed_total(self.h, f32p(t)))
+        return t
+
+    def seed_pick(self, u01, exact=False):
+        u = as_f32(np.atleast_1d(u01))
+        out = np.zeros(self.nb, np.uint32)
+        check(capi.lib().fdb_kmeans_seed_pick(self.h, f32p(u), int(exact), u32p(out)))
+        return out
+
+    def seed_add(self, i, ci, exact=False):
+        ci = as_u32(np.atleast_1d(ci))
+        check(capi.lib().fdb_kmeans_seed_add(self.h, i, u32p(ci), int(exact)))
+
+    def seed_run(self, first, u01, exact=False):
+        first = as_u32(np.atleast_1d(first))
+        u = as_f32(u01).reshape(self.nb, max(self.k - 1, 0))
+        picked = np.zeros((self.nb, self.k), np.uint32)
+        check(capi.lib().fdb_kmeans_seed_run(self.h, u32p(first), f32p(u), int(exact), u32p(picked)))
+        return picked
+
+    def seed_chosen(self, chosen):
+        ch = as_u32(chosen).reshape(self.nb, self.k)
+        check(capi.lib().fdb_kmeans_seed_chosen(self.h, u32p(ch)))
+
+    def set_state(self, centroids, indices=None):
+        c = as_f32(centroids).reshape(self.nb, self.k, self.dim)
+        i = None if indices is None else as_u32(indices).reshape(self.nb, self.n)
+        check(capi.lib().fdb_kmeans_set_state(self.h, f32p(c), None if i is None else u32p(i)))
+
+    def _active(self, active):
+        if active is None:
+            return None, None
+        a = np.ascontiguousarray(active, np.uint8)
+        return a, u8p(a)
+
+    def update(self, active=None):
+        g = np.zeros(self.nb, np.float32)
+        keep, a = self._active(active)
+        check(capi.lib().fdb_kmeans_update(self.h, a, f32p(g)))
+        return g
+
+    def reassign(self, active=None):
+        keep, a = self._active(active)
+        check(capi.lib().fdb_kmeans_reassign(self.h, a))
+
+    def run(self, max_rounds=capi.KMEANS_MAX_ROUNDS, eps=capi.KMEANS_EPSILON):
+        g = np.zeros((self.nb, max_rounds), np.float32)
+        rounds = np.zeros(self.nb, np.uint32)
+        reas = np.zeros(self.nb, np.uint32)
+        check(capi.lib().fdb_kmeans_run(self.h, max_rounds, eps, f32p(g), u32p(rounds), u32p(reas)))
+        return [g[b, :rounds[b]].copy() for b in range(self.nb)], rounds, reas
+
+    def get(self):
+        c = np.zeros((self.nb, self.k, self.dim), np.float32)
+        i = np.zeros((self.nb, self.n), np.uint32)
+        check(capi.lib().fdb_kmeans_get(self.h, f32p(c), u32p(i)))
+        return c, i
+
+    def weights(self):
+        w = np.zeros((self.nb, self.n), np.float32)
+        check(capi.lib().fdb_kmeans_get_weights(self.h, f32p(w)))
+        return w
+
+    def update_partial(self):
+        p, n = VP(), C.c_size_t()
+        check(capi.lib().fdb_kmeans_update_partial(self.h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def update_finish(self):
+        g = np.zeros(self.nb, np.float32)
+        check(capi.lib().fdb_kmeans_update_finish(self.h, f32p(g)))
+        return g
+
+    def close(self):
+        if self.h:
+            capi.lib().fdb_kmeans_destroy(self.h)
+            self.h = VP()
+
+
+class Index:
+    """Queryable IVF-PQ index resident in HBM (stored::Database, src/db/stored.rs:41-57)."""
+
+    def __init__(self, ctx, handle, N, P, D, Cn):
+        self.ctx, self.h = ctx, handle
+        self.N, self.P, self.D, self.C = N, P, D, Cn
+
+    @classmethod
+    def create(cls, ctx, coarse, codebooks, offsets, codes):
+        coarse, codebooks = as_f32(coarse), as_f32(codebooks)
+        P, N = coarse.shape
+        D, Cn, _ = codebooks.shape
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        codes = np.ascontiguousarray(codes, np.uint8)
+        h = VP()
+        check(capi.lib().fdb_index_create(ctx.h, N, P, D, Cn, f32p(coarse), f32p(codebooks),
+                                          u64p(offsets), u8p(codes), C.byref(h)))
+        return cls(ctx, h, N, P, D, Cn)
+
+    @classmethod
+    def from_build(cls, ctx, coarse_km, pq_km):
+        h = VP()
+        check(capi.lib().fdb_index_from_build(ctx.h, coarse_km.h, pq_km.h, C.byref(h)))
+        return cls(ctx, h, coarse_km.dim, coarse_km.k, pq_km.nb, pq_km.k)
+
+    @property
+    def num_vectors(self):
+        return int(capi.lib().fdb_index_num_vectors(self.h))
+
+    def layout(self, order=True):
+        M = self.num_vectors
+        off = np.zeros(self.P + 1, np.uint64)
+        od = np.zeros(M, np.uint32) if order else None
+        codes = np.zeros((M, self.D), np.uint8)
+        check(capi.lib().fdb_index_get_layout(self.h, u64p(off), u32p(od) if order else None,
+                                              u8p(codes)))
+        return off, od, codes
+
+    def query(self, q, k, nprobe, mode=capi.QUERY_STORED):
+        q = as_f32(q).reshape(-1, self.N)
+        nq = q.shape[0]
+        part = np.zeros((nq, k), np.uint32)
+        vidx = np.zeros((nq, k), np.uint32)
+        dist = np.zeros((nq, k), np.float32)
+        cnt = np.zeros(nq, np.uint32)
+        check(capi.lib().fdb_index_query(self.h, f32p(q), nq, k, nprobe, mode, u32p(part),
+                                         u32p(vidx), f32p(dist), u32p(cnt)))
+        return part, vidx, dist, cnt
+
+    def query_device(self, d_q, nq, k, nprobe, d_part, d_vidx, d_dist, d_cnt,
+                     mode=capi.QUERY_STORED):
+        check(capi.lib().fdb_index_query_device(self.h, d_q, nq, k, nprobe, mode, d_part, d_vidx,
+                                                d_dist, d_cnt))
+
+    def probe(self, q, nprobe, mode=capi.QUERY_STORED):
+        q = as_f32(q).reshape(-1, self.N)
+        nq = q.shape[0]
+        part = np.zeros((nq, nprobe), np.uint32)
+        dist = np.zeros((nq, nprobe), np.float32)
+        check(capi.lib().fdb_index_probe(self.h, f32p(q), nq, nprobe, mode, u32p(part), f32p(dist)))
+        return part, dist
+
+    def table(self, q, partition):
+        q = as_f32(q).reshape(self.N)
+        t = np.zeros((self.D, self.C), np.float32)
+        check(capi.lib().fdb_index_table(self.h, f32p(q), int(partition), f32p(t)))
+        return t
+
+    def set_timing(self, on):
+        check(capi.lib().fdb_index_set_timing(self.h, int(on)))
+
+    def last_timing(self):
+        ms = np.zeros(6, np.float32)
+        b = C.c_uint64()
+        check(capi.lib().fdb_index_last_timing(self.h, f32p(ms), C.byref(b)))
+        return ms, int(b.value)
+
+    def close(self):
+        if self.h:
+            capi.lib().fdb_index_destroy(self.h)
+            self.h = VP()

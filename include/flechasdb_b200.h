@@ -1,0 +1,191 @@
+/*
+ * flechasdb_b200.h -- C ABI of libflechasdb_b200.so, the B200 (sm_100a) engine
+ * behind flechasdb's IVF-PQ build and query path.
+ *
+ * The reference (codemonger-io/flechasdb) is pure Rust with no FFI; this header
+ * is the boundary its hot-path bodies bind to (INTEGRATION.md shows the Rust
+ * `extern "C"` block and build.rs).  Every entry point names the reference code
+ * it replaces (paths relative to the reference repo root).
+ *
+ * Conventions
+ *  - plain C: pointers + sizes, no exceptions cross the boundary;
+ *  - every function returns FDB_OK (0) or a negative FDB_ERR_*; the message is
+ *    kept per thread and read with fdb_last_error();
+ *  - the caller owns all host buffers; the library owns device memory behind
+ *    opaque handles; one handle is used from one thread at a time;
+ *  - there is NO CPU fallback: without a CUDA device fdb_ctx_create fails.
+ *  - "nb" = number of independent k-means problems solved side by side on the
+ *    strided sub-vector views of one vector set (nb = 1 for the coarse
+ *    quantiser, nb = D for the PQ codebooks of all divisions at once).  All
+ *    per-problem arrays are laid out [nb][...].
+ */
+#ifndef FLECHASDB_B200_H
+#define FLECHASDB_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FDB_OK 0
+#define FDB_ERR_INVALID_ARGS (-1)    /* Error::InvalidArgs      src/error.rs:7   */
+#define FDB_ERR_INVALID_DATA (-2)    /* Error::InvalidData      src/error.rs:9   */
+#define FDB_ERR_INVALID_CONTEXT (-3) /* Error::InvalidContext   src/error.rs:11  */
+#define FDB_ERR_EMPTY_CLUSTER (-4)   /* panic: assert_ne!(count, 0) src/kmeans.rs:259 */
+#define FDB_ERR_WEIGHTS (-5)         /* panic: WeightedIndex .unwrap() src/kmeans.rs:199,207,216 */
+#define FDB_ERR_NAN (-6)             /* panic: min_index.unwrap() src/kmeans.rs:304; partial_cmp().unwrap() src/db/stored.rs:385,426 */
+#define FDB_ERR_CUDA (-7)            /* CUDA runtime failure (no reference analogue) */
+#define FDB_ERR_UNSUPPORTED (-8)     /* shape outside what the device layout supports (e.g. C > 256 with u8 codes) */
+
+#define FDB_KMEANS_MAX_ROUNDS 100    /* const R: usize = 100;   src/kmeans.rs:114 */
+#define FDB_KMEANS_EPSILON 1e-6f     /* f32 default_epsilon     src/kmeans.rs:24-28 */
+
+#define FDB_QUERY_STORED 0           /* stored::Database::query  (NBestByKey selection) */
+#define FDB_QUERY_BUILD 1            /* build::Database::query   (stable sort + truncate) */
+
+typedef struct fdb_ctx fdb_ctx;     /* one CUDA device + stream                                */
+typedef struct fdb_vs fdb_vs;       /* BlockVectorSet<f32> resident in HBM   src/vector.rs:28-100 */
+typedef struct fdb_km fdb_km;       /* nb k-means problems (Codebook<f32> each) src/kmeans.rs:62-68 */
+typedef struct fdb_index fdb_index; /* queryable IVF-PQ index: stored::Database src/db/stored.rs:41-57 */
+
+/* ---- library / context ------------------------------------------------------ */
+const char *fdb_last_error(void);
+int fdb_version(void);
+int fdb_device_count(void);
+int fdb_ctx_create(int device, fdb_ctx **out);
+void fdb_ctx_destroy(fdb_ctx *ctx);
+int fdb_ctx_sync(fdb_ctx *ctx);
+/* CUDA events on the library's stream, for callers that time device work */
+int fdb_ctx_timer_start(fdb_ctx *ctx);
+int fdb_ctx_timer_stop(fdb_ctx *ctx, float *milliseconds);
+/* number of kernels this context has launched so far */
+uint64_t fdb_ctx_launch_count(const fdb_ctx *ctx);
+
+/* ---- vector sets: BlockVectorSet::chunk + VectorSet  (src/vector.rs:40-100) ---- */
+/* copies n*dim floats host -> device.  Fails like chunk() on a zero dim. */
+int fdb_vs_upload(fdb_ctx *ctx, const float *rows, size_t n, size_t dim, fdb_vs **out);
+/* borrows caller-owned device memory (row-major n*dim, 16-byte aligned) */
+int fdb_vs_from_device(fdb_ctx *ctx, float *device_rows, size_t n, size_t dim, fdb_vs **out);
+/* synthetic uniform [0,1) rows generated on the device (bench / tests):
+ * element e of the set = (splitmix64(seed, start+e) >> 40) * 2^-24 */
+int fdb_vs_generate(fdb_ctx *ctx, size_t n, size_t dim, uint64_t seed, uint64_t start, fdb_vs **out);
+int fdb_vs_download(fdb_vs *vs, float *rows);
+int fdb_vs_download_rows(fdb_vs *vs, size_t first_row, size_t nrows, float *rows);
+size_t fdb_vs_len(const fdb_vs *vs);         /* VectorSet::len          */
+size_t fdb_vs_vector_size(const fdb_vs *vs); /* VectorSet::vector_size  */
+float *fdb_vs_device_ptr(fdb_vs *vs);
+void fdb_vs_destroy(fdb_vs *vs);
+/* v_j -= centroid[indices[j]] in place: Partitioning::partition_with_events,
+ * src/partitions.rs:128-138.  km must be an nb=1 problem over the full rows. */
+int fdb_vs_subtract_assigned(fdb_vs *vs, const fdb_km *km);
+
+/* ---- k-means: src/kmeans.rs ---------------------------------------------------- */
+/* Problem b clusters the SubVectorSet (src/vector.rs:103-149) made of columns
+ * [col_off + b*dim, col_off + (b+1)*dim) of vs.  divide_vector_set
+ * (src/vector.rs:154-174) is fdb_kmeans_begin(vs, 0, N/D, D, C).
+ * Err(InvalidArgs) when n < k, like cluster_with_events (src/kmeans.rs:116-120). */
+int fdb_kmeans_begin(fdb_vs *vs, size_t col_off, size_t dim, size_t nb, size_t k, fdb_km **out);
+void fdb_kmeans_destroy(fdb_km *km);
+
+/* k-means++ seeding, initialize_centroids (src/kmeans.rs:142-229), one call per
+ * reference statement group so the host keeps the RNG and the loop:
+ *   seed_first : ci = rng.gen_range(0..n); first centre; initial D^2 weights (:172-199)
+ *   seed_total : WeightedIndex::total_weight (src/distribution.rs:45,76)
+ *   seed_pick  : WeightedIndex::sample for the draw u in [0,1) (src/distribution.rs:104-121;
+ *                the sample value is u*total as rand 0.8.5 UniformFloat<f32> computes it)
+ *   seed_add   : round i for the chosen vector ci (:203-220)
+ * exact != 0 keeps the reference's sequential f32 running total and cumulative
+ * scan bit for bit (slow, single-threaded per problem); exact == 0 uses a
+ * deterministic parallel scan (same distribution, not bit-comparable at
+ * cumulative-sum boundaries).  ci / u01 / totals are arrays of nb. */
+int fdb_kmeans_seed_first(fdb_km *km, const uint32_t *ci);
+int fdb_kmeans_seed_total(fdb_km *km, float *totals);
+int fdb_kmeans_seed_pick(fdb_km *km, const float *u01, int exact, uint32_t *ci_out);
+int fdb_kmeans_seed_add(fdb_km *km, size_t i, const uint32_t *ci, int exact);
+/* the whole seeding loop on the device without host round trips:
+ * first[nb], u01[nb][k-1] -> picked[nb][k] (may be NULL) */
+int fdb_kmeans_seed_run(fdb_km *km, const uint32_t *first, const float *u01, int exact,
+                        uint32_t *picked);
+/* the same loop with the picks injected ("k-means++ seeds fixed"): chosen[nb][k] */
+int fdb_kmeans_seed_chosen(fdb_km *km, const uint32_t *chosen);
+/* test hook / resume: set centroids [nb][k][dim] and (optionally) indices [nb][n] */
+int fdb_kmeans_set_state(fdb_km *km, const float *centroids, const uint32_t *indices);
+
+/* update_centroids (src/kmeans.rs:232-276): members are added in ascending vector
+ * index, scaled by 1/count; gradients[nb] = max||old-new|| / max||new||.
+ * FDB_ERR_EMPTY_CLUSTER mirrors the reference's assert.  active (nb bytes, may be
+ * NULL = all) selects the problems to step. */
+int fdb_kmeans_update(fdb_km *km, const uint8_t *active, float *gradients);
+/* reassign_centroids (src/kmeans.rs:279-306): argmin_j dot(v-c_j, v-c_j) in the
+ * reference's summation order, lowest j wins ties. */
+int fdb_kmeans_reassign(fdb_km *km, const uint8_t *active);
+/* the loop of cluster_with_events (src/kmeans.rs:125-137) for all nb problems:
+ * gradients[nb][max_rounds] receives the FinishedCentroidUpdate values,
+ * rounds[nb] the number of updates, reassigns[nb] the number of reassignments. */
+int fdb_kmeans_run(fdb_km *km, size_t max_rounds, float epsilon, float *gradients,
+                   uint32_t *rounds, uint32_t *reassigns);
+/* Codebook { centroids, indices }: centroids [nb][k][dim], indices [nb][n] */
+int fdb_kmeans_get(fdb_km *km, float *centroids, uint32_t *indices);
+int fdb_kmeans_get_weights(fdb_km *km, float *weights); /* [nb][n] D^2 weights */
+
+/* multi-GPU build (rows sharded across processes, centroids replicated): the
+ * per-rank half of update_centroids.  update_partial leaves [nb][k][dim] sums
+ * followed by [nb][k] counts (as floats) in a device buffer the caller
+ * all-reduces (NCCL sum) in place; update_finish divides and computes the gradient. */
+int fdb_kmeans_update_partial(fdb_km *km, float **device_buf, size_t *nfloats);
+int fdb_kmeans_update_finish(fdb_km *km, float *gradients);
+
+/* ---- index + query: src/db/build.rs:446-482, src/db/stored.rs:331-442,549-597 ---- */
+/* Host-side constructor (what load_database/load_partition feed):
+ *   coarse    [P][N]       partition centroids
+ *   codebooks [D][C][N/D]  PQ code vectors
+ *   offsets   [P+1]        partition p holds vectors offsets[p]..offsets[p+1]
+ *   codes     [M][D] u8    partition-major, ascending vector index inside a partition
+ *                          (Partition::new order, src/db/build.rs:459-473) */
+int fdb_index_create(fdb_ctx *ctx, size_t N, size_t P, size_t D, size_t C, const float *coarse,
+                     const float *codebooks, const uint64_t *offsets, const uint8_t *codes,
+                     fdb_index **out);
+/* Device-side constructor straight from a finished build (no host round trip):
+ * coarse = nb=1 problem with k=P, pq = nb=D problem with k=C over the residues.
+ * order_out (may be NULL) receives [M] the global vector index stored at each
+ * partition-major position (the vector_ids order of Partition::new). */
+int fdb_index_from_build(fdb_ctx *ctx, const fdb_km *coarse, const fdb_km *pq, fdb_index **out);
+int fdb_index_get_layout(fdb_index *ix, uint64_t *offsets /*P+1*/, uint32_t *order /*M or NULL*/,
+                         uint8_t *codes /*M*D or NULL*/);
+size_t fdb_index_num_vectors(const fdb_index *ix);
+void fdb_index_destroy(fdb_index *ix);
+/* Database::query for a batch of nq queries (host buffers).  Outputs are [nq][k]
+ * in ascending distance; out_count[q] <= k entries are valid.  mode selects the
+ * selection semantics (FDB_QUERY_STORED / FDB_QUERY_BUILD).
+ * Err(InvalidArgs) when nprobe > P (src/db/stored.rs:403-409). */
+int fdb_index_query(fdb_index *ix, const float *queries, size_t nq, size_t k, size_t nprobe,
+                    int mode, uint32_t *out_partition, uint32_t *out_vector_index,
+                    float *out_sqdist, uint32_t *out_count);
+/* the same with queries already resident in HBM and results left there
+ * (device pointers; used to time the kernels without host copies) */
+int fdb_index_query_device(fdb_index *ix, const float *d_queries, size_t nq, size_t k,
+                           size_t nprobe, int mode, uint32_t *d_partition,
+                           uint32_t *d_vector_index, float *d_sqdist, uint32_t *d_count);
+/* step-wise pieces for parity tests: probe order and one ADC table */
+int fdb_index_probe(fdb_index *ix, const float *queries, size_t nq, size_t nprobe, int mode,
+                    uint32_t *out_partition /*[nq][nprobe]*/, float *out_sqdist /*[nq][nprobe]*/);
+int fdb_index_table(fdb_index *ix, const float *query, uint32_t partition, float *table /*[D][C]*/);
+/* per-phase timing is off by default (it adds events and one probe read-back per call) */
+int fdb_index_set_timing(fdb_index *ix, int enabled);
+/* per-phase device milliseconds of the last fdb_index_query* call (timing enabled):
+ * [0] coarse distances, [1] probe selection, [2] localise, [3] ADC tables,
+ * [4] code scan + per-partition n-best, [5] merge; and the algorithmic scan bytes */
+int fdb_index_last_timing(fdb_index *ix, float ms[6], uint64_t *scan_bytes);
+
+/* raw device buffers for benches that keep inputs resident */
+int fdb_device_alloc(fdb_ctx *ctx, size_t bytes, void **out);
+int fdb_device_free(fdb_ctx *ctx, void *p);
+int fdb_device_fill_uniform(fdb_ctx *ctx, float *d, size_t count, uint64_t seed, uint64_t start);
+int fdb_device_flush_l2(fdb_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

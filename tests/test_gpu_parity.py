@@ -1,0 +1,383 @@
+"""Parity of the CUDA path against the CPU oracle, through the C ABI (needs a B200).
+
+Bar (BASELINE.json north_star): cluster / PQ-code assignments bit-exact, centroids
+within 1e-4 relative (here: bit-exact, the update adds members in the reference's
+order), query ids bit-exact, distances within 1e-5 relative (here: bit-exact).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+SEED = 0xF1EC4A5D0001
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from flechasdb_b200 import engine
+    return engine
+
+
+@pytest.fixture(scope="module")
+def ctx(eng):
+    c = eng.Context(0)
+    yield c
+    c.close()
+
+
+def data(oracle, n, dim, seed=SEED):
+    return oracle.fill_uniform(n * dim, seed).reshape(n, dim)
+
+
+# ---- reassign_centroids: src/kmeans.rs:279-306 -------------------------------------------
+@pytest.mark.parametrize("n,m,k", [
+    (2000, 128, 256),   # PQ shape, KC=64 tile path
+    (1000, 1536, 100),  # coarse shape
+    (777, 32, 33),      # KC=32, ragged rows and centroids
+    (515, 48, 7),       # KC=16
+    (300, 16, 300),     # k == n
+    (400, 20, 9),       # r = 4 remainder lanes -> generic kernel
+    (400, 8, 16),       # m < 16 -> dot_naive order
+    (100, 1, 3),
+    (64, 35, 5),
+])
+def test_reassign_bit_exact(eng, ctx, oracle, n, m, k):
+    x = data(oracle, n, m)
+    cent = data(oracle, k, m, SEED + 7)
+    vs = eng.VectorSet.upload(ctx, x)
+    km = eng.KMeans(vs, k)
+    km.set_state(cent)
+    km.reassign()
+    _, idx = km.get()
+    rc, want = oracle.kmeans_reassign(x, k, cent)
+    assert rc == 0
+    assert (idx[0] == want).all()
+    km.close()
+    vs.close()
+
+
+def test_reassign_ties_pick_lowest_index(eng, ctx, oracle):
+    x = data(oracle, 200, 64)
+    cent = data(oracle, 40, 64, SEED + 1)
+    cent[17] = cent[3]      # exact duplicates: the lower index must win
+    cent[39] = cent[3]
+    cent[20] = cent[11]
+    vs = eng.VectorSet.upload(ctx, x)
+    km = eng.KMeans(vs, 40)
+    km.set_state(cent)
+    km.reassign()
+    _, idx = km.get()
+    rc, want = oracle.kmeans_reassign(x, 40, cent)
+    assert (idx[0] == want).all()
+    assert not np.isin(idx[0], [17, 39, 20]).any()
+    km.close()
+    vs.close()
+
+
+# ---- update_centroids: src/kmeans.rs:232-276 ---------------------------------------------
+@pytest.mark.parametrize("n,m,k", [(3000, 128, 256), (2000, 1536, 10), (500, 20, 7), (300, 8, 4),
+                                   (70000, 16, 300)])
+def test_update_bit_exact(eng, ctx, oracle, n, m, k):
+    x = data(oracle, n, m)
+    rng = np.random.default_rng(5)
+    idx = rng.integers(0, k, n).astype(np.uint32)
+    idx[:k] = np.arange(k)  # no empty cluster
+    cent0 = data(oracle, k, m, SEED + 3)
+    vs = eng.VectorSet.upload(ctx, x)
+    km = eng.KMeans(vs, k)
+    km.set_state(cent0, idx)
+    g = km.update()
+    cent, _ = km.get()
+    rc, want_c, want_g = oracle.kmeans_update(x, k, cent0, idx)
+    assert rc == 0
+    assert (cent[0] == want_c).all()
+    assert np.float32(g[0]) == np.float32(want_g)
+    km.close()
+    vs.close()
+
+
+def test_update_empty_cluster_is_an_error(eng, ctx, oracle):
+    from flechasdb_b200 import _capi as capi
+    x = data(oracle, 100, 16)
+    idx = np.zeros(100, np.uint32)  # cluster 1 is empty
+    vs = eng.VectorSet.upload(ctx, x)
+    km = eng.KMeans(vs, 2)
+    km.set_state(x[:2], idx)
+    with pytest.raises(capi.FdbError) as e:
+        km.update()
+    assert e.value.code == capi.ERR_EMPTY_CLUSTER
+    rc, _, _ = oracle.kmeans_update(x, 2, x[:2], idx)
+    assert rc == oracle.ERR_PANIC_EMPTY_CLUSTER
+    km.close()
+    vs.close()
+
+
+# ---- k-means++: src/kmeans.rs:142-229, src/distribution.rs ---------------------------------
+@pytest.mark.parametrize("n,m,k", [(3000, 128, 40), (1500, 1536, 12), (600, 20, 9), (500, 8, 6)])
+def test_seeding_with_fixed_seeds_bit_exact(eng, ctx, oracle, n, m, k):
+    """North-star contract: with the chosen seeds fixed, weights / indices / centroids match."""
+    x = data(oracle, n, m)
+    rng = np.random.default_rng(11)
+    chosen = rng.choice(n, k, replace=False).astype(np.uint32)
+    rc, want_c, want_i, want_w, _ = oracle.kmeans_init(x, k, int(chosen[0]), chosen=chosen[1:])
+    assert rc == 0
+    vs = eng.VectorSet.upload(ctx, x)
+    km = eng.KMeans(vs, k)
+    km.seed_chosen(chosen[None, :])
+    cent, idx = km.get()
+    assert (cent[0] == want_c).all()
+    assert (idx[0] == want_i).all()
+    assert (km.weights()[0] == want_w).all()
+    km.close()
+    vs.close()
+
+
+@pytest.mark.parametrize("n,m,k", [(4000, 64, 30), (900, 20, 8)])
+def test_seeding_exact_sampler_follows_the_same_draws(eng, ctx, oracle, n, m, k):
+    """exact mode reproduces WeightedIndex (running f32 total, cumulative scan) bit for bit."""
+    x = data(oracle, n, m)
+    rng = np.random.default_rng(3)
+    u = (rng.integers(0, 1 << 23, k - 1).astype(np.float32) * np.float32(2.0 ** -23))
+    first = 17
+    rc, want_c, want_i, want_w, want_p = oracle.kmeans_init(x, k, first, u01=u)
+    assert rc == 0
+    vs = eng.VectorSet.upload(ctx, x)
+    km = eng.KMeans(vs, k)
+    picked = km.seed_run([first], u[None, :], exact=True)
+    assert (picked[0] == want_p).all()
+    cent, idx = km.get()
+    assert (cent[0] == want_c).all() and (idx[0] == want_i).all()
+    assert (km.weights()[0] == want_w).all()
+    # the step-wise entry points walk the same path
+    km2 = eng.KMeans(vs, k)
+    km2.seed_first([first])
+    for i in range(1, k):
+        ci = km2.seed_pick([u[i - 1]], exact=True)
+        assert ci[0] == want_p[i]
+        km2.seed_add(i, ci, exact=True)
+    assert (km2.get()[1][0] == want_i).all()
+    # fast sampler: same distribution; picks agree except at cumulative-sum boundaries
+    km3 = eng.KMeans(vs, k)
+    p3 = km3.seed_run([first], u[None, :], exact=False)
+    assert len(set(p3[0].tolist())) == k
+    for a in (km, km2, km3):
+        a.close()
+    vs.close()
+
+
+def test_seeding_special_cases(eng, ctx, oracle):
+    x = data(oracle, 50, 24)
+    vs = eng.VectorSet.upload(ctx, x)
+    km = eng.KMeans(vs, 50)            # k == n, src/kmeans.rs:158-170
+    km.seed_run([0], np.zeros((1, 49), np.float32))
+    cent, idx = km.get()
+    assert (cent[0] == x).all() and (idx[0] == np.arange(50)).all()
+    km.close()
+    km = eng.KMeans(vs, 1)             # k == 1, :176-184
+    km.seed_run([7], np.zeros((1, 0), np.float32))
+    cent, idx = km.get()
+    assert (cent[0, 0] == x[7]).all() and (idx == 0).all()
+    km.close()
+    from flechasdb_b200 import _capi as capi
+    with pytest.raises(capi.FdbError) as e:  # n < k, :116-120
+        eng.KMeans(vs, 51)
+    assert e.value.code == capi.ERR_INVALID_ARGS
+    # all vectors identical -> WeightedIndex::new(...).unwrap() panics, :199
+    same = np.tile(x[:1], (20, 1))
+    vs2 = eng.VectorSet.upload(ctx, same)
+    km = eng.KMeans(vs2, 3)
+    with pytest.raises(capi.FdbError) as e:
+        km.seed_run([0], np.zeros((1, 2), np.float32), exact=True)
+    assert e.value.code == capi.ERR_WEIGHTS
+    rc, *_ = oracle.kmeans_init(same, 3, 0, u01=np.zeros(2, np.float32))
+    assert rc == oracle.ERR_PANIC_WEIGHTS
+    km.close()
+    vs2.close()
+    vs.close()
+
+
+# ---- cluster_with_events end to end: src/kmeans.rs:104-139 ---------------------------------
+@pytest.mark.parametrize("n,m,k,rounds", [(3000, 32, 16, 100), (2000, 128, 64, 12), (800, 20, 5, 100)])
+def test_lloyd_trajectory_bit_exact(eng, ctx, oracle, n, m, k, rounds):
+    x = data(oracle, n, m)
+    rng = np.random.default_rng(2)
+    chosen = rng.choice(n, k, replace=False).astype(np.uint32)
+    rc, c0, i0, _, _ = oracle.kmeans_init(x, k, int(chosen[0]), chosen=chosen[1:])
+    rc, want_c, want_i, want_g, want_nr = oracle.kmeans_lloyd(x, k, c0, i0, max_rounds=rounds)
+    assert rc == 0
+    vs = eng.VectorSet.upload(ctx, x)
+    km = eng.KMeans(vs, k)
+    km.seed_chosen(chosen[None, :])
+    grads, nrounds, nreas = km.run(max_rounds=rounds)
+    cent, idx = km.get()
+    assert nrounds[0] == len(want_g) and nreas[0] == want_nr
+    assert (grads[0] == want_g).all()
+    assert (cent[0] == want_c).all()
+    assert (idx[0] == want_i).all()
+    km.close()
+    vs.close()
+
+
+def test_batched_divisions_equal_one_by_one(eng, ctx, oracle):
+    """nb = D problems side by side == the reference's per-division loop (src/db/build.rs:110-118)."""
+    n, N, D, k = 2500, 96, 6, 32
+    x = data(oracle, n, N)
+    s = N // D
+    rng = np.random.default_rng(9)
+    chosen = np.stack([rng.choice(n, k, replace=False) for _ in range(D)]).astype(np.uint32)
+    vs = eng.VectorSet.upload(ctx, x)
+    km = eng.KMeans(vs, k, col_off=0, dim=s, nb=D)
+    km.seed_chosen(chosen)
+    grads, nrounds, nreas = km.run(max_rounds=30)
+    cent, idx = km.get()
+    for di in range(D):
+        rc, c0, i0, _, _ = oracle.kmeans_init(x, k, int(chosen[di, 0]), chosen=chosen[di, 1:],
+                                              off=di * s, dim=s)
+        rc, wc, wi, wg, wnr = oracle.kmeans_lloyd(x, k, c0, i0, max_rounds=30, off=di * s, dim=s)
+        assert rc == 0
+        assert nrounds[di] == len(wg) and nreas[di] == wnr
+        assert (grads[di] == wg).all()
+        assert (cent[di] == wc).all() and (idx[di] == wi).all()
+    km.close()
+    vs.close()
+
+
+# ---- residues + Partition::new: src/partitions.rs:128-138, src/db/build.rs:446-482 -----------
+def build_small(eng, ctx, oracle, M, N, P, D, Cn, rounds=8):
+    x = data(oracle, M, N)
+    rng = np.random.default_rng(21)
+    s = N // D
+    cch = rng.choice(M, P, replace=False).astype(np.uint32)
+    pch = np.stack([rng.choice(M, Cn, replace=False) for _ in range(D)]).astype(np.uint32)
+    vs = eng.VectorSet.upload(ctx, x)
+    ckm = eng.KMeans(vs, P)
+    ckm.seed_chosen(cch[None, :])
+    ckm.run(max_rounds=rounds)
+    vs.subtract_assigned(ckm)
+    pkm = eng.KMeans(vs, Cn, dim=s, nb=D)
+    pkm.seed_chosen(pch)
+    pkm.run(max_rounds=rounds)
+    # oracle twin
+    xo = x.copy()
+    rc, c0, i0, _, _ = oracle.kmeans_init(xo, P, int(cch[0]), chosen=cch[1:])
+    rc, cc, ci, _, _ = oracle.kmeans_lloyd(xo, P, c0, i0, max_rounds=rounds)
+    oracle.residues(xo, cc, ci)
+    cbs = np.zeros((D, Cn, s), np.float32)
+    codes = np.zeros((D, M), np.uint32)
+    for di in range(D):
+        rc, c0, i0, _, _ = oracle.kmeans_init(xo, Cn, int(pch[di, 0]), chosen=pch[di, 1:],
+                                              off=di * s, dim=s)
+        rc, cbs[di], codes[di], _, _ = oracle.kmeans_lloyd(xo, Cn, c0, i0, max_rounds=rounds,
+                                                          off=di * s, dim=s)
+    return vs, ckm, pkm, dict(coarse=cc, part_idx=ci, residues=xo, codebooks=cbs, codes=codes)
+
+
+def test_full_build_matches_oracle(eng, ctx, oracle):
+    M, N, P, D, Cn = 3000, 64, 12, 4, 32
+    vs, ckm, pkm, want = build_small(eng, ctx, oracle, M, N, P, D, Cn)
+    cc, ci = ckm.get()
+    assert (cc[0] == want["coarse"]).all() and (ci[0] == want["part_idx"]).all()
+    assert (vs.download() == want["residues"]).all()
+    cb, codes = pkm.get()
+    assert (cb == want["codebooks"]).all() and (codes == want["codes"]).all()
+    ix = eng.Index.from_build(ctx, ckm, pkm)
+    off, order, pm = ix.layout()
+    woff, worder, wpm = oracle.extract_partitions(want["part_idx"], want["codes"], P)
+    assert (off == woff).all() and (order == worder).all() and (pm == wpm.astype(np.uint8)).all()
+    # and the index answers queries like the oracle's
+    q = data(oracle, 40, N, SEED + 99)
+    oix = oracle.QueryIndex(want["coarse"], want["codebooks"], woff, wpm)
+    for mode in (0, 1):
+        part, vidx, dist, cnt = ix.query(q, 10, 3, mode)
+        rc, wp, wv, wd, wc = oix.query(q, 10, 3, mode)
+        assert rc == 0
+        assert (cnt == wc).all() and (part == wp).all() and (vidx == wv).all() and (dist == wd).all()
+    for h in (ix, pkm, ckm, vs):
+        h.close()
+
+
+# ---- query: src/db/stored.rs:331-442,549-597; src/db/build.rs:307-382,521-565 ---------------
+def random_index(oracle, N, P, D, Cn, M, seed=4, dup=False, empty=()):
+    rng = np.random.default_rng(seed)
+    s = N // D
+    coarse = data(oracle, P, N, SEED + 5)
+    cbs = (data(oracle, D * Cn, s, SEED + 6) - np.float32(0.5)).reshape(D, Cn, s)
+    sizes = rng.multinomial(M, np.ones(P) / P)
+    for e in empty:
+        sizes[e] = 0
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+    total = int(off[-1])
+    hi = 3 if dup else Cn  # few distinct codes -> many exactly tied distances
+    codes = rng.integers(0, hi, (total, D)).astype(np.uint32)
+    return coarse, cbs, off, codes
+
+
+@pytest.mark.parametrize("N,P,D,Cn,M,k,nprobe", [
+    (1536, 100, 12, 256, 20000, 10, 5),   # the README shape, smaller M
+    (96, 64, 12, 256, 30000, 10, 8),      # s = 8 (dot_naive order), D % 4 == 0
+    (120, 20, 5, 17, 3000, 7, 20),        # odd D / C, nprobe == P
+    (64, 9, 4, 256, 500, 100, 3),         # k larger than most partitions
+    (32, 40, 2, 16, 6000, 33, 40),        # k > 32: several slot rounds
+])
+def test_query_bit_exact(eng, ctx, oracle, N, P, D, Cn, M, k, nprobe):
+    coarse, cbs, off, codes = random_index(oracle, N, P, D, Cn, M, empty=(1,))
+    ix = eng.Index.create(ctx, coarse, cbs, off, codes.astype(np.uint8))
+    oix = oracle.QueryIndex(coarse, cbs, off, codes)
+    q = data(oracle, 64, N, SEED + 77)
+    for mode in (0, 1):
+        pp, pd = ix.probe(q, nprobe, mode)
+        for qi in range(4):
+            rc, wp, wd = oix.probe(q[qi], nprobe, mode)
+            assert (pp[qi] == wp).all() and (pd[qi] == wd).all()
+        part, vidx, dist, cnt = ix.query(q, k, nprobe, mode)
+        rc, wp, wv, wd, wc = oix.query(q, k, nprobe, mode)
+        assert rc == 0
+        assert (cnt == wc).all()
+        for qi in range(len(q)):
+            c = cnt[qi]
+            assert (part[qi, :c] == wp[qi, :c]).all(), (mode, qi)
+            assert (vidx[qi, :c] == wv[qi, :c]).all(), (mode, qi)
+            assert (dist[qi, :c] == wd[qi, :c]).all(), (mode, qi)
+    t = ix.table(q[0], 2)
+    assert (t == oix.table(q[0], 2)).all()
+    ix.close()
+
+
+def test_query_tie_semantics_follow_nbest_history(eng, ctx, oracle):
+    """Exactly tied ADC distances: which tied vector survives is history dependent in
+    NBestByKey (src/nbest.rs:52-64) and order dependent in the stable sorts; both modes
+    must reproduce it."""
+    N, P, D, Cn, M = 32, 6, 4, 16, 4000
+    coarse, cbs, off, codes = random_index(oracle, N, P, D, Cn, M, dup=True)
+    ix = eng.Index.create(ctx, coarse, cbs, off, codes.astype(np.uint8))
+    oix = oracle.QueryIndex(coarse, cbs, off, codes)
+    q = data(oracle, 50, N, SEED + 78)
+    for mode in (0, 1):
+        for k in (5, 40):
+            part, vidx, dist, cnt = ix.query(q, k, 4, mode)
+            rc, wp, wv, wd, wc = oix.query(q, k, 4, mode)
+            assert (dist == wd).all()
+            assert len(np.unique(wd[0])) < k  # there really are ties
+            assert (part == wp).all() and (vidx == wv).all()
+    ix.close()
+
+
+def test_query_errors(eng, ctx, oracle):
+    from flechasdb_b200 import _capi as capi
+    coarse, cbs, off, codes = random_index(oracle, 32, 5, 4, 16, 300)
+    ix = eng.Index.create(ctx, coarse, cbs, off, codes.astype(np.uint8))
+    q = data(oracle, 2, 32)
+    with pytest.raises(capi.FdbError) as e:  # nprobe > P, src/db/stored.rs:403-409
+        ix.query(q, 3, 6)
+    assert e.value.code == capi.ERR_INVALID_ARGS
+    assert oracle.QueryIndex(coarse, cbs, off, codes).query(q, 3, 6)[0] == oracle.ERR_INVALID_ARGS
+    qn = q.copy()
+    qn[0, 0] = np.nan                          # partial_cmp().unwrap() panics
+    with pytest.raises(capi.FdbError) as e:
+        ix.query(qn, 3, 2)
+    assert e.value.code == capi.ERR_NAN
+    ix.close()
+    with pytest.raises(capi.FdbError) as e:  # C > 256 does not fit u8 codes
+        big = np.zeros((4, 300, 8), np.float32)
+        eng.Index.create(ctx, coarse, big, off, codes.astype(np.uint8))
+    assert e.value.code == capi.ERR_UNSUPPORTED
