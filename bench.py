@@ -1,0 +1,426 @@
+#!/usr/bin/env python
+"""bench.py -- IVF-PQ query throughput (k=10, nprobe=5) on the README database shape,
+plus the build time of that database, on N B200s of one node.
+
+Contract: `python bench.py --gpus N --steps K --warmup W` prints ONE JSON line on rank 0.
+A "step" is one pass of the query hot path over one batch of 10 000 synthetic queries
+(BASELINE.json configs[1]: 10k queries vs the 100k x 1536 DB, P=100 D=12 C=256, K=10,
+NPROBE=5).  `value` = queries/s with queries resident in HBM (device-timed with CUDA
+events); `e2e` = the same through the host-buffer C-ABI call (H2D of the queries and D2H of
+the results inside the timed region).  N > 1: every rank holds a replica of the index and
+runs its own query batch (queries are the sharded unit; no data-path collective) -> weak
+scaling.  `--impl reference` times the CPU restatement of the reference (oracle/) instead.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED_DATA = 0xF1EC4A5D0001
+SEED_QUERY = 0xF1EC4A5D0002
+SEED_KMEANS = 0xF1EC4A5D0003
+
+M, N, P, D, CN = 100000, 1536, 100, 12, 256
+NQ, K, NPROBE = 10000, 10, 5
+METRIC = "ivfpq_query_qps_k10_nprobe5_100kx1536"
+WORKLOAD = "configs[1]: 10k random queries vs 100k x 1536 DB (P=100 D=12 C=256), K=10 NPROBE=5"
+
+
+def env_int(name, default):
+    return int(os.environ.get(name, default))
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md, 6.65 TB/s)"
+
+
+def splitmix64(seed, i):
+    mask = (1 << 64) - 1
+    z = (seed + (i + 1) * 0x9E3779B97F4A7C15) & mask
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & mask
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & mask
+    return z ^ (z >> 31)
+
+
+class BenchSeeds:
+    """Deterministic stand-in for thread_rng: sub-stream `s` = coarse 0, division di = 1+di."""
+
+    def __init__(self, seed):
+        self.seed = seed
+        self.stream = 0
+
+    def first(self, n, nb):
+        out = np.array([splitmix64(self.seed + 7919 * (self.stream + b), 0) % n for b in range(nb)],
+                       np.uint32)
+        return out
+
+    def draws(self, nb, count):
+        out = np.empty((nb, count), np.float32)
+        for b in range(nb):
+            s = self.seed + 7919 * (self.stream + b)
+            out[b] = [(splitmix64(s, 1 + i) >> 41) * 2.0 ** -23 for i in range(count)]
+        self.stream += nb
+        return out
+
+
+def pinned_empty(shape, dtype):
+    """Pinned host memory through torch (plumbing only)."""
+    import torch
+    tdt = {np.float32: torch.float32, np.uint32: torch.int32}[dtype]
+    t = torch.empty(shape, dtype=tdt, pin_memory=True)
+    a = t.numpy()
+    return t, (a.view(np.uint32) if dtype is np.uint32 else a)
+
+
+# ------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank, dist):
+    import ctypes as C
+    from flechasdb_b200 import _capi as capi
+    from flechasdb_b200 import engine
+    from flechasdb_b200.db import DatabaseBuilder
+
+    capi.lib()  # fails loudly when the CUDA library is missing: there is no fallback
+    ctx = engine.Context(local_rank)
+    m, nq = args.m, args.nq
+
+    # ---- the database: synthetic rows generated on the device, pulled to pinned host memory
+    #      once so that the build can be timed end to end from host buffers -----------------
+    gen = engine.VectorSet.generate(ctx, m, N, SEED_DATA)
+    keep_x, host_x = pinned_empty((m, N), np.float32)
+    capi.check(capi.lib().fdb_vs_download(gen.h, capi.f32p(host_x)))
+    gen.close()
+
+    t0 = time.perf_counter()
+    vs = engine.VectorSet.upload(ctx, host_x)
+    t_upload = time.perf_counter() - t0
+    launches0 = ctx.launches
+    ctx.timer_start()
+    t1 = time.perf_counter()
+    events = []
+    db = DatabaseBuilder(vs, ctx=ctx, seeds=BenchSeeds(SEED_KMEANS)) \
+        .with_partitions(P).with_divisions(D).with_clusters(CN) \
+        .build_with_events(events.append)
+    build_dev_ms = ctx.timer_stop()
+    t_build = time.perf_counter() - t1
+    build_launches = ctx.launches - launches0
+    rounds_coarse = sum(1 for e in events if e[0] == "ClusterEvent" and e[1][0] == "FinishedCentroidUpdate")
+    ix = db.index
+    ix.set_timing(True)
+
+    # ---- queries -------------------------------------------------------------------------
+    d_q = ctx.alloc(nq * N * 4)
+    ctx.fill_uniform(d_q, nq * N, SEED_QUERY + rank)
+    d_part, d_vidx = ctx.alloc(nq * K * 4), ctx.alloc(nq * K * 4)
+    d_dist, d_cnt = ctx.alloc(nq * K * 4), ctx.alloc(nq * 4)
+
+    def step_device():
+        ix.query_device(d_q, nq, K, NPROBE, d_part, d_vidx, d_dist, d_cnt)
+
+    for _ in range(args.warmup):
+        step_device()
+    ctx.sync()
+    if dist is not None:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = ctx.launches
+    step_ms, phase_ms = [], np.zeros(6)
+    scan_bytes = 0
+    for _ in range(args.steps):
+        ctx.flush_l2()           # untimed: evict the previous step's working set from the 126 MB L2
+        ctx.timer_start()
+        step_device()
+        step_ms.append(ctx.timer_stop())
+        ms, scan_bytes = ix.last_timing()
+        phase_ms += ms
+    step_launches = (ctx.launches - launches0) // max(args.steps, 1)
+    ctx.sync()
+    total_ms = float(sum(step_ms))
+
+    # ---- e2e: host buffers through the public call, copies inside the timed region ---------
+    keep_q, host_q = pinned_empty((nq, N), np.float32)
+    # device -> pinned host copy of the queries (once, untimed)
+    tmpvs = C.c_void_p()
+    capi.check(capi.lib().fdb_vs_from_device(ctx.h, d_q, nq, N, C.byref(tmpvs)))
+    capi.check(capi.lib().fdb_vs_download(tmpvs, capi.f32p(host_q)))
+    capi.lib().fdb_vs_destroy(tmpvs)
+    keep_o = [pinned_empty((nq, K), np.uint32), pinned_empty((nq, K), np.uint32),
+              pinned_empty((nq, K), np.float32), pinned_empty((nq,), np.uint32)]
+    o_part, o_vidx, o_dist, o_cnt = [a for _, a in keep_o]
+    ix.set_timing(False)
+
+    def step_e2e():
+        capi.check(capi.lib().fdb_index_query(ix.h, capi.f32p(host_q), nq, K, NPROBE, capi.QUERY_STORED,
+                                              capi.u32p(o_part), capi.u32p(o_vidx), capi.f32p(o_dist),
+                                              capi.u32p(o_cnt)))
+
+    for _ in range(max(1, args.warmup)):
+        step_e2e()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    ctx.sync()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+
+    # ---- max over ranks ------------------------------------------------------------------
+    if dist is not None:
+        import torch
+        t = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda:%d" % local_rank)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_ms = float(t[0]), float(t[1])
+    else:
+        e2e_ms = e2e_s * 1e3
+    if rank != 0:
+        return None
+
+    value = world * nq * args.steps / (total_ms * 1e-3)
+    e2e_value = world * nq * args.steps / (e2e_ms * 1e-3)
+
+    # ---- rooflines -----------------------------------------------------------------------
+    hbm_peak, peak_src = measured_peaks()
+    npairs = nq * NPROBE
+    scan_ms = phase_ms[4] / args.steps
+    table_ms = phase_ms[3] / args.steps
+    scan_gbs = scan_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else None
+    sm_clock = 1.965e9
+    fp32_peak = 148 * 128 * sm_clock / 1e12  # non-FMA: the reference's arithmetic forbids contraction
+    table_tflops = 3.0 * npairs * N * CN / (table_ms * 1e-3) / 1e12 if table_ms > 0 else None
+    names = ["coarse_distances", "probe_select", "localize", "adc_tables", "code_scan", "merge"]
+    roofline_scan = {
+        "kernel": "scan_kernel (code lists, u8)", "bound": "hbm", "achieved": scan_gbs,
+        "peak": hbm_peak, "unit": "GB/s", "frac": (scan_gbs / hbm_peak) if scan_gbs else None,
+        "peak_source": peak_src, "traffic": None,
+        "algorithmic_bytes_per_launch": scan_bytes / max(1, -(-npairs // 8192)),
+        "note": "1.2 MB of codes is L2 resident at this config: algorithmic GB/s, not DRAM traffic",
+    }
+    roofline_table = {
+        "kernel": "exact_tile_kernel<matrix> (ADC tables, dominant kernel of the step)",
+        "bound": "fp32_alu", "achieved": table_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
+        "frac": (table_tflops / fp32_peak) if table_tflops else None,
+        "peak_source": "148 SM x 128 lanes x 1.965 GHz, 1 flop/instr (separately rounded sub, mul, add)",
+        "share_of_step": table_ms / (total_ms / args.steps),
+    }
+
+    # ---- CPU baseline (oracle port, 1 thread like the reference) + parity on the sample ------
+    from oracle import pyoracle as oracle
+    try:
+        oracle.build(native=True)
+        native = True
+    except Exception:
+        native = False
+    coarse, _ = db.ckm.get()
+    cbs, _ = db.pkm.get()
+    off, order, codes = ix.layout()
+    oix = oracle.QueryIndex(coarse[0], cbs, off, codes.astype(np.uint32))
+    ns = min(nq, args.cpu_queries)
+    t0 = time.perf_counter()
+    rc, wp, wv, wd, wc = oix.query(host_q[:ns], K, NPROBE, 0, nthreads=1, native=native)
+    cpu_s = time.perf_counter() - t0
+    mism = int((wp != o_part[:ns]).any(axis=1).sum() + (wv != o_vidx[:ns]).any(axis=1).sum())
+    dist_bits = bool((wd == o_dist[:ns]).all())
+    cpu_baseline = {"value": ns / cpu_s, "unit": "queries/s", "cores": 1, "kind": "port",
+                    "sample": "first %d of the %d queries, oracle port of stored::Database::query, "
+                              "1 thread (the reference is single-threaded)" % (ns, nq)}
+    # CPU build, extrapolated from one reassignment of a row sample
+    ns_rows = min(m, 2000)
+    t0 = time.perf_counter()
+    oracle.kmeans_reassign(np.ascontiguousarray(host_x[:ns_rows]), P, coarse[0], native=native)
+    t_coarse = (time.perf_counter() - t0) * m / ns_rows
+    res = db.vs.download(0, ns_rows)
+    t0 = time.perf_counter()
+    oracle.kmeans_reassign(res, CN, cbs[0], off=0, dim=N // D, native=native)
+    t_pq = (time.perf_counter() - t0) * m / ns_rows
+    cl = [e[1] for e in events if e[0] == "ClusterEvent"]
+    upd = [e for e in cl if e[0] == "FinishedCentroidUpdate"]
+    rea = [e for e in cl if e[0] == "FinishedCentroidReassignment"]
+    starts = [i for i, e in enumerate(cl) if e[0] == "StartingCentroidInitialization"]
+    n_rea_coarse = sum(1 for e in cl[starts[0]:starts[1]] if e[0] == "FinishedCentroidReassignment")
+    n_rea_pq = len(rea) - n_rea_coarse
+    cpu_build = t_coarse * (1 + n_rea_coarse) + t_pq * (D + n_rea_pq)
+
+    out = {
+        "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "M": m, "N": N, "P": P, "D": D, "C": CN, "nq": nq, "k": K,
+                   "nprobe": NPROBE, "l2": "flushed between timed steps (256 MiB write)",
+                   "parallelism": "index replicated, queries sharded x%d" % world},
+        "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": nq * N * 4,
+                "d2h_bytes_per_step": nq * K * 12 + nq * 4, "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": int(step_launches),
+        "roofline": roofline_scan, "roofline_dominant_kernel": roofline_table,
+        "phase_ms_per_step": {n_: float(v / args.steps) for n_, v in zip(names, phase_ms)},
+        "cpu_baseline": cpu_baseline,
+        "parity": {"queries_checked": ns, "id_mismatches": mism, "distances_bit_equal": dist_bits},
+        "build": {"metric": "ivfpq_build_sec_100kx1536", "sec": build_dev_ms * 1e-3,
+                  "e2e_sec": t_upload + t_build, "h2d_sec": t_upload, "gpu_launches": int(build_launches),
+                  "lloyd_updates": len(upd), "lloyd_reassignments": len(rea),
+                  "reassignments_coarse": n_rea_coarse, "reassignments_pq_all_divisions": n_rea_pq,
+                  "cpu_port_extrapolated_sec": cpu_build,
+                  "cpu_sample": "1 reassignment of %d rows (coarse, and PQ division 0) x rows x passes, 1 thread" % ns_rows,
+                  "published_reference_sec": 906.5},
+        "clocks": clocks,
+    }
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+def synth_index(oracle, m):
+    """An index of the benchmark's shape without a build (the CPU build alone takes ~30 min):
+    uniform coarse centroids and code vectors, uniform u8 codes, multinomial partition sizes.
+    The work per query (P distances, nprobe tables, ~m/P code rows per probe) is the shape's."""
+    rng = np.random.default_rng(12345)
+    coarse = oracle.fill_uniform(P * N, SEED_DATA + 11).reshape(P, N)
+    cbs = (oracle.fill_uniform(D * CN * (N // D), SEED_DATA + 12) - np.float32(0.5)).reshape(D, CN, N // D)
+    sizes = rng.multinomial(m, np.ones(P) / P)
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+    codes = rng.integers(0, CN, (m, D)).astype(np.uint32)
+    return oracle.QueryIndex(coarse, cbs, off, codes)
+
+
+def run_reference(args, rank, world):
+    """The reference's CPU path (oracle port; the Rust crate cannot be compiled here) on all
+    host threads: independent queries run in parallel, each exactly as the reference runs it."""
+    if rank != 0:
+        return None
+    from oracle import pyoracle as oracle
+    try:
+        oracle.build(native=True)
+        native = True
+    except Exception:
+        native = False
+    cores = os.cpu_count() or 1
+    oix = synth_index(oracle, args.m)
+    ns = min(args.nq, max(cores * 8, args.cpu_queries))
+    q = oracle.fill_uniform(ns * N, SEED_QUERY).reshape(ns, N)
+    for _ in range(min(args.warmup, 1)):
+        oix.query(q[:cores], K, NPROBE, 0, nthreads=cores, native=native)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        rc, *_ = oix.query(q, K, NPROBE, 0, nthreads=cores, native=native)
+        assert rc == 0
+    s = time.perf_counter() - t0
+    value = ns * args.steps / s
+    sample = ("%d queries per step (of the %d-query batch) vs a synthesised index of the same shape, "
+              "oracle port of stored::Database::query, %d threads" % (ns, args.nq, cores))
+    return {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": s * 1e3 / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "M": args.m, "N": N, "P": P, "D": D, "C": CN, "nq": args.nq,
+                   "k": K, "nprobe": NPROBE},
+        "cpu_baseline": {"value": value, "unit": "queries/s", "cores": cores, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--m", type=int, default=M)
+    ap.add_argument("--nq", type=int, default=NQ)
+    ap.add_argument("--cpu-queries", type=int, default=2000)
+    args = ap.parse_args()
+
+    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if args.impl == "reference":
+        out = run_reference(args, rank, world)
+        if out is not None:
+            print(json.dumps(out), flush=True)
+        return
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+        torch.cuda.set_device(local_rank)
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda:%d" % local_rank))
+        dist = dist_mod
+    try:
+        out = run_ours(args, rank, world, local_rank, dist)
+        if out is not None:
+            print(json.dumps(out), flush=True)
+    finally:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

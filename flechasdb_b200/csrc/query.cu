@@ -36,6 +36,7 @@ struct fdb_index {
     std::vector<cudaEvent_t> events;
     float phase_ms[6] = {0, 0, 0, 0, 0, 0};
     uint64_t scan_bytes = 0;
+    size_t last_npairs = 0;
     bool timing = false;
     size_t chunk_pairs = 8192;
 };
@@ -112,6 +113,17 @@ struct WarpNBest {
     // slice::sort_by(partial_cmp) on the slots: stable, so ties keep slot order.
     // rank sort into (od, oa).
     __device__ void sorted_out(float *od, uint32_t *oa, int lane) const {
+        // a NaN key makes the reference panic (partial_cmp().unwrap()); the caller raises
+        // FLAG_NAN, here the slots are just copied so that every output entry is defined
+        bool nan = false;
+        for (int i = lane; i < len; i += 32) nan |= d[i] != d[i];
+        if (__any_sync(0xffffffffu, nan)) {
+            for (int i = lane; i < len; i += 32) {
+                od[i] = d[i];
+                oa[i] = a[i];
+            }
+            return;
+        }
         for (int i = lane; i < len; i += 32) {
             const float di = d[i];
             int rank = 0;
@@ -252,6 +264,18 @@ __global__ void __launch_bounds__(PROBE_WARPS * 32) probe_select_kernel(
 __global__ void localize_kernel(const float *q, const float *coarse, const uint32_t *probes,
                                 size_t pair0, size_t npairs, size_t nprobe, size_t N, float *loc) {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((N & 3) == 0) {  // 128-bit path (rows are 16-byte aligned when N % 4 == 0)
+        const size_t N4 = N >> 2;
+        if (t >= npairs * N4) return;
+        const size_t pr = t / N4, e = (t - pr * N4) << 2;
+        const size_t pair = pair0 + pr;
+        const size_t qi = pair / nprobe;
+        const float4 a = *reinterpret_cast<const float4 *>(q + qi * N + e);
+        const float4 b = *reinterpret_cast<const float4 *>(coarse + (size_t)probes[pair] * N + e);
+        *reinterpret_cast<float4 *>(loc + pr * N + e) =
+            make_float4(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y), __fsub_rn(a.z, b.z), __fsub_rn(a.w, b.w));
+        return;
+    }
     if (t >= npairs * N) return;
     const size_t pr = t / N, e = t - pr * N;
     const size_t pair = pair0 + pr;
@@ -352,6 +376,212 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(ScanParams p) {
         }
         if (lane == 0) p.part_cnt[pair] = (uint32_t)len;
     }
+}
+
+// ---- register-resident variants for n <= 32: lane s holds slot s --------------------------
+struct RegNBest {
+    float d;
+    uint32_t a;
+    int n, len;
+    float maxd;
+    __device__ void init(int nn) {
+        d = 0.f;
+        a = 0;
+        n = nn;
+        len = 0;
+        maxd = -INF;
+    }
+    __device__ void refresh_max(int lane) { maxd = warp_max(lane < len ? d : -INF); }
+    __device__ void push(float cd, uint32_t ca, int lane) {
+        if (len < n) {
+            if (lane == len) {
+                d = cd;
+                a = ca;
+            }
+            len++;
+            if (len == n) refresh_max(lane);
+            return;
+        }
+        if (!(cd < maxd)) return;
+        for (;;) {
+            const unsigned bal = __ballot_sync(0xffffffffu, lane < n && cd < d);
+            if (!bal) break;
+            const int f = __ffs(bal) - 1;
+            const float od = __shfl_sync(0xffffffffu, d, f);
+            const uint32_t oa = __shfl_sync(0xffffffffu, a, f);
+            if (lane == f) {
+                d = cd;
+                a = ca;
+            }
+            cd = od;
+            ca = oa;
+        }
+        refresh_max(lane);
+    }
+    // stable sort by key; result in lane order
+    __device__ void sort(int lane) {
+        const bool mine = lane < len;
+        const bool nan = __any_sync(0xffffffffu, mine && d != d);
+        if (nan) return;  // the caller raises FLAG_NAN
+        int rank = 0;
+        for (int j = 0; j < len; ++j) {
+            const float dj = __shfl_sync(0xffffffffu, d, j);
+            rank += (dj < d) || (dj == d && j < lane);
+        }
+        // scatter lane -> rank: every lane r fetches from the lane whose rank is r
+        int src = 0;
+        for (int j = 0; j < len; ++j) {
+            const int rj = __shfl_sync(0xffffffffu, rank, j);
+            if (rj == lane) src = j;
+        }
+        const float nd = __shfl_sync(0xffffffffu, d, src);
+        const uint32_t na = __shfl_sync(0xffffffffu, a, src);
+        if (mine) {
+            d = nd;
+            a = na;
+        }
+    }
+};
+
+struct RegSorted {
+    float d;
+    uint32_t a;
+    int n, len;
+    float last;  // key of slot n-1 once full
+    __device__ void init(int nn) {
+        d = 0.f;
+        a = 0;
+        n = nn;
+        len = 0;
+        last = INF;
+    }
+    __device__ void push(float cd, uint32_t ca, int lane) {
+        if (len == n && !(cd < last)) return;
+        const unsigned bal = __ballot_sync(0xffffffffu, lane < len && cd < d);
+        const int pos = bal ? __ffs(bal) - 1 : len;
+        const float ud = __shfl_up_sync(0xffffffffu, d, 1);
+        const uint32_t ua = __shfl_up_sync(0xffffffffu, a, 1);
+        if (lane > pos && lane < n) {
+            d = ud;
+            a = ua;
+        }
+        if (lane == pos) {
+            d = cd;
+            a = ca;
+        }
+        if (len < n) len++;
+        if (len == n) last = __shfl_sync(0xffffffffu, d, n - 1);
+    }
+};
+
+// feed one group of up to 32 keys (lane-held) in lane order
+__device__ __forceinline__ void feed_group(RegNBest &nb, float dv, bool valid, uint32_t payload0, int lane) {
+    unsigned bal = __ballot_sync(0xffffffffu, valid && (nb.len < nb.n || dv < nb.maxd));
+    while (bal) {
+        const int L = __ffs(bal) - 1;
+        bal &= bal - 1;
+        nb.push(__shfl_sync(0xffffffffu, dv, L), payload0 + L, lane);
+    }
+}
+__device__ __forceinline__ void feed_group(RegSorted &sl, float dv, bool valid, uint32_t payload0, int lane) {
+    unsigned bal = __ballot_sync(0xffffffffu, valid && (sl.len < sl.n || dv < sl.last));
+    while (bal) {
+        const int L = __ffs(bal) - 1;
+        bal &= bal - 1;
+        sl.push(__shfl_sync(0xffffffffu, dv, L), payload0 + L, lane);
+    }
+}
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int NWAIT>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(NWAIT));
+}
+
+// ---- 5 (fast path): one warp per (query, partition) pair, k <= 32 ------------------------
+// The warp keeps the pair's ADC table in shared memory, streams the partition's code list
+// through a double-buffered cp.async pipeline (16-byte coalesced copies), evaluates 32
+// vectors at a time and feeds them, in vector order, to the register-resident n-best.
+constexpr int SCANW_WARPS = 4;
+
+template <typename Sel>
+__global__ void __launch_bounds__(SCANW_WARPS * 32) scan_warp_kernel(ScanParams p, int npairs) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int local = blockIdx.x * SCANW_WARPS + warp;
+    if (local >= npairs) return;
+    const size_t DC = p.D * p.C;
+    const int D = (int)p.D, C = (int)p.C;
+    const size_t chunk_bytes = (size_t)p.chunk_vecs * D;
+    const size_t per_warp = DC * 4 + 2 * chunk_bytes;
+    float *table = reinterpret_cast<float *>(sm + (size_t)warp * per_warp);
+    unsigned char *cbuf = reinterpret_cast<unsigned char *>(table + DC);
+
+    const size_t pair = p.pair0 + local;
+    const uint32_t part = p.probes[pair];
+    const int np = (int)(p.part_off[part + 1] - p.part_off[part]);
+    const uint8_t *cg = p.codes + p.part_cstart[part];
+    const float *tg = p.tables + (size_t)local * DC;
+
+    // group 0: the table; then one group per code chunk
+    for (size_t i = lane; i < DC / 4; i += 32) cp_async16(table + 4 * i, tg + 4 * i);
+    auto issue_chunk = [&](int c) {
+        const int c0 = c * p.chunk_vecs;
+        if (c0 < np) {
+            const int cnt = min(p.chunk_vecs, np - c0);
+            const size_t n16 = ((size_t)cnt * D + 15) >> 4;
+            const uint8_t *src = cg + (size_t)c0 * D;
+            unsigned char *dst = cbuf + (size_t)(c & 1) * chunk_bytes;
+            for (size_t i = lane; i < n16; i += 32) cp_async16(dst + 16 * i, src + 16 * i);
+        }
+        cp_async_commit();
+    };
+    issue_chunk(0);
+
+    Sel sel;
+    sel.init(p.k);
+    const int nchunks = (np + p.chunk_vecs - 1) / p.chunk_vecs;
+    for (int c = 0; c < nchunks; ++c) {
+        issue_chunk(c + 1);
+        cp_async_wait<1>();
+        __syncwarp();
+        const int c0 = c * p.chunk_vecs;
+        const int cnt = min(p.chunk_vecs, np - c0);
+        const unsigned char *cs = cbuf + (size_t)(c & 1) * chunk_bytes;
+        for (int base = 0; base < cnt; base += 32) {
+            const int v = base + lane;
+            const bool valid = v < cnt;
+            float dist = 0.0f;  // sequential f32 adds over divisions, src/db/stored.rs:582-587
+            if (valid) {
+                if ((D & 3) == 0) {
+                    const uint32_t *cw = reinterpret_cast<const uint32_t *>(cs) + (size_t)v * (D >> 2);
+                    for (int w = 0; w < (D >> 2); ++w) {
+                        const uint32_t x = cw[w];
+                        const float *t = table + (size_t)(4 * w) * C;
+                        dist = __fadd_rn(dist, t[x & 255u]);
+                        dist = __fadd_rn(dist, t[C + ((x >> 8) & 255u)]);
+                        dist = __fadd_rn(dist, t[2 * C + ((x >> 16) & 255u)]);
+                        dist = __fadd_rn(dist, t[3 * C + (x >> 24)]);
+                    }
+                } else {
+                    for (int di = 0; di < D; ++di)
+                        dist = __fadd_rn(dist, table[(size_t)di * C + cs[(size_t)v * D + di]]);
+                }
+            }
+            feed_group(sel, dist, valid, (uint32_t)(c0 + base), lane);
+        }
+        __syncwarp();  // everyone is done with this buffer before it is refilled
+    }
+    cp_async_wait<0>();
+    if (lane < sel.len) {
+        p.part_d[pair * p.k + lane] = sel.d;
+        p.part_v[pair * p.k + lane] = sel.a;
+    }
+    if (lane == 0) p.part_cnt[pair] = (uint32_t)sel.len;
 }
 
 // ---- 6: merge across probed partitions (src/db/stored.rs:379-386 / build.rs:334-337) ----
@@ -681,12 +911,26 @@ int query_device(fdb_index *ix, const float *d_q, size_t nq, size_t k, size_t np
         return FDB_ERR_UNSUPPORTED;
     }
     FDB_CUDA(cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem));
+    // fast path: one warp per pair with register-resident selection
+    const int w_chunk_vecs = (int)std::max<size_t>(32, (2048 / ix->D) & ~(size_t)31);
+    const size_t w_per_warp = DC * 4 + 2 * (size_t)w_chunk_vecs * ix->D;
+    const bool warp_path = k <= 32 && (DC & 3) == 0 && w_per_warp * SCANW_WARPS <= 96 * 1024 &&
+                           !getenv("FDB_SCAN_BLOCK");
+    if (warp_path) {
+        FDB_CUDA(cudaFuncSetAttribute(scan_warp_kernel<RegNBest>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(w_per_warp * SCANW_WARPS)));
+        FDB_CUDA(cudaFuncSetAttribute(scan_warp_kernel<RegSorted>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(w_per_warp * SCANW_WARPS)));
+    }
 
     for (size_t pair0 = 0; pair0 < npairs; pair0 += chunk) {
         const size_t np = std::min(chunk, npairs - pair0);
         FDB_TRY(log.mark(2));
-        localize_kernel<<<(unsigned)((np * ix->N + 255) / 256), 256, 0, ctx->stream>>>(
-            d_q, ix->coarse.p, ix->probes.p, pair0, np, nprobe, ix->N, ix->loc.p);
+        {
+            const size_t work = (ix->N & 3) == 0 ? np * (ix->N >> 2) : np * ix->N;
+            localize_kernel<<<(unsigned)((work + 255) / 256), 256, 0, ctx->stream>>>(
+                d_q, ix->coarse.p, ix->probes.p, pair0, np, nprobe, ix->N, ix->loc.p);
+        }
         ctx->launches++;
         FDB_TRY(log.mark(3));
         DistProblem dp;
@@ -715,7 +959,16 @@ int query_device(fdb_index *ix, const float *d_q, size_t nq, size_t k, size_t np
         sp.part_d = ix->part_d.p;
         sp.part_v = ix->part_v.p;
         sp.part_cnt = ix->part_cnt.p;
-        scan_kernel<<<(unsigned)np, SCAN_THREADS, scan_smem, ctx->stream>>>(sp);
+        if (warp_path) {
+            sp.chunk_vecs = w_chunk_vecs;
+            const unsigned grid = (unsigned)((np + SCANW_WARPS - 1) / SCANW_WARPS);
+            if (mode == FDB_QUERY_STORED)
+                scan_warp_kernel<RegNBest><<<grid, SCANW_WARPS * 32, w_per_warp * SCANW_WARPS, ctx->stream>>>(sp, (int)np);
+            else
+                scan_warp_kernel<RegSorted><<<grid, SCANW_WARPS * 32, w_per_warp * SCANW_WARPS, ctx->stream>>>(sp, (int)np);
+        } else {
+            scan_kernel<<<(unsigned)np, SCAN_THREADS, scan_smem, ctx->stream>>>(sp);
+        }
         ctx->launches++;
         FDB_CHECK_LAUNCH();
     }
@@ -727,15 +980,9 @@ int query_device(fdb_index *ix, const float *d_q, size_t nq, size_t k, size_t np
     ctx->launches++;
     FDB_CHECK_LAUNCH();
     FDB_TRY(log.mark(-1));
-    // algorithmic scan bytes: sum over probed partitions of n_p * D
+    ix->last_npairs = npairs;
     if (ix->timing) {
-        std::vector<uint32_t> hp(npairs);
-        FDB_CUDA(cudaMemcpyAsync(hp.data(), ix->probes.p, npairs * sizeof(uint32_t),
-                                 cudaMemcpyDeviceToHost, ctx->stream));
         FDB_CUDA(cudaStreamSynchronize(ctx->stream));
-        uint64_t bytes = 0;
-        for (uint32_t pp : hp) bytes += (uint64_t)(ix->h_off[pp + 1] - ix->h_off[pp]) * ix->D;
-        ix->scan_bytes = bytes;
         FDB_TRY(log.finish());
     }
     return FDB_OK;
@@ -845,7 +1092,22 @@ int fdb_index_set_timing(fdb_index *ix, int enabled) {
 int fdb_index_last_timing(fdb_index *ix, float ms[6], uint64_t *scan_bytes) {
     ARG(ix && ms, "null argument");
     for (int i = 0; i < 6; ++i) ms[i] = ix->phase_ms[i];
-    if (scan_bytes) *scan_bytes = ix->scan_bytes;
+    if (scan_bytes) {
+        // algorithmic scan bytes of the last call: sum over its probed partitions of n_p * D
+        // (SURVEY.md section 8d); read back lazily so that the query itself never waits on it
+        fdb_ctx *ctx = ix->ctx;
+        FDB_TRY(ctx->use());
+        std::vector<uint32_t> hp(ix->last_npairs);
+        if (!hp.empty()) {
+            FDB_CUDA(cudaMemcpyAsync(hp.data(), ix->probes.p, hp.size() * sizeof(uint32_t),
+                                     cudaMemcpyDeviceToHost, ctx->stream));
+            FDB_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+        uint64_t bytes = 0;
+        for (uint32_t pp : hp) bytes += (uint64_t)(ix->h_off[pp + 1] - ix->h_off[pp]) * ix->D;
+        ix->scan_bytes = bytes;
+        *scan_bytes = bytes;
+    }
     return FDB_OK;
 }
 
