@@ -381,3 +381,46 @@ def test_query_errors(eng, ctx, oracle):
         big = np.zeros((4, 300, 8), np.float32)
         eng.Index.create(ctx, coarse, big, off, codes.astype(np.uint8))
     assert e.value.code == capi.ERR_UNSUPPORTED
+
+
+# ---- the committed golden fixture, without the oracle at run time ---------------------------
+def test_golden_fixture(eng, ctx):
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ivfpq_small.npz"))
+    # k-means++ from the injected draw stream (exact sampler) + Lloyd to convergence
+    n, m, k = int(g["km_n"]), int(g["km_m"]), int(g["km_k"])
+    vs = eng.VectorSet.generate(ctx, n, m, SEED)           # same counter-based generator on the device
+    km = eng.KMeans(vs, k)
+    picked = km.seed_run([int(g["km_first"])], g["km_u"][None, :], exact=True)
+    assert (picked[0] == g["km_picked"]).all()
+    c0, i0 = km.get()
+    assert (c0[0] == g["km_c0"]).all() and (i0[0] == g["km_i0"]).all()
+    assert (km.weights()[0] == g["km_w0"]).all()
+    grads, rounds, reas = km.run()
+    c1, i1 = km.get()
+    assert (grads[0] == g["km_grads"]).all() and reas[0] == int(g["km_reassigns"])
+    assert (c1[0] == g["km_c1"]).all() and (i1[0] == g["km_i1"]).all()
+    km.close()
+    vs.close()
+    # full build with the fixture's draws, then queries in both modes
+    M, N, P, D, Cn = (int(g[x]) for x in ("db_M", "db_N", "db_P", "db_D", "db_C"))
+    vs = eng.VectorSet.generate(ctx, M, N, SEED + 1)
+    ckm = eng.KMeans(vs, P)
+    ckm.seed_run([int(g["db_first_coarse"])], g["db_u_coarse"][None, :], exact=True)
+    ckm.run(max_rounds=20)
+    vs.subtract_assigned(ckm)
+    assert abs(float(vs.download().astype(np.float64).sum()) - float(g["db_residues_checksum"])) < 1e-9
+    pkm = eng.KMeans(vs, Cn, dim=N // D, nb=D)
+    pkm.seed_run(g["db_first_pq"], g["db_u_pq"], exact=True)
+    pkm.run(max_rounds=20)
+    assert (ckm.get()[0][0] == g["db_coarse"]).all() and (ckm.get()[1][0] == g["db_part_idx"]).all()
+    assert (pkm.get()[0] == g["db_codebooks"]).all() and (pkm.get()[1] == g["db_codes"]).all()
+    ix = eng.Index.from_build(ctx, ckm, pkm)
+    off, order, pm = ix.layout()
+    assert (off == g["db_offsets"]).all() and (order == g["db_order"]).all() and (pm == g["db_codes_pm"]).all()
+    for mode in (0, 1):
+        p, v, d, c = ix.query(g["q"], int(g["q_k"]), int(g["q_nprobe"]), mode)
+        assert (p == g["q%d_part" % mode]).all() and (v == g["q%d_vidx" % mode]).all()
+        assert (d == g["q%d_dist" % mode]).all() and (c == g["q%d_cnt" % mode]).all()
+    for h in (ix, pkm, ckm, vs):
+        h.close()
