@@ -67,6 +67,7 @@ SIGNATURES = {
     "fdb_kmeans_update": (C.c_int, [VP, U8P, F32P]),
     "fdb_kmeans_reassign": (C.c_int, [VP, U8P]),
     "fdb_kmeans_run": (C.c_int, [VP, SZ, C.c_float, F32P, U32P, U32P]),
+    "fdb_kmeans_last_assign_info": (C.c_int, [VP, U32P, U32P, U32P]),
     "fdb_kmeans_get": (C.c_int, [VP, F32P, U32P]),
     "fdb_kmeans_get_weights": (C.c_int, [VP, F32P]),
     "fdb_kmeans_update_partial": (C.c_int, [VP, C.POINTER(VP), C.POINTER(SZ)]),

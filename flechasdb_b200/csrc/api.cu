@@ -334,6 +334,7 @@ void fdb_kmeans_destroy(fdb_km *km) {
     if (!km) return;
     cudaSetDevice(km->ctx->device);
     cudaStreamSynchronize(km->ctx->stream);
+    tc_free(km);
     delete km;
 }
 
@@ -597,6 +598,17 @@ int fdb_kmeans_get_weights(fdb_km *km, float *weights) {
     FDB_CUDA(cudaMemcpyAsync(weights, km->weights.p, km->nb * km->n * sizeof(float),
                              cudaMemcpyDeviceToHost, km->ctx->stream));
     FDB_CUDA(cudaStreamSynchronize(km->ctx->stream));
+    return FDB_OK;
+}
+
+int fdb_kmeans_last_assign_info(fdb_km *km, uint32_t *used_tensor_cores, uint32_t *rechecked_rows,
+                                uint32_t *overflow_rows) {
+    ARG(km, "km is null");
+    if (used_tensor_cores) *used_tensor_cores = (uint32_t)km->last_assign_tc;
+    unsigned st[3] = {0, 0, 0};
+    if (km->last_assign_tc) tc_last_stats(km, st);
+    if (rechecked_rows) *rechecked_rows = st[2];
+    if (overflow_rows) *overflow_rows = st[1];
     return FDB_OK;
 }
 

@@ -90,6 +90,7 @@ struct fdb_vs {
     float *d = nullptr;
     bool owned = true;
     size_t n = 0, dim = 0;
+    uint64_t version = 0;  // bumped whenever the rows are modified in place
 };
 
 namespace fdb {

@@ -675,6 +675,12 @@ int km_update(fdb_km *km, const int *d_active, int loop_mode, float eps, size_t 
 }
 
 int km_reassign(fdb_km *km, const int *d_active) {
+    // tensor-core filter + exact re-check when the shape allows it, identical results
+    km->last_assign_tc = 0;
+    if (tc_eligible(km)) {
+        km->last_assign_tc = 1;
+        return tc_reassign(km, d_active);
+    }
     DistProblem q;
     q.x = km->vs->d;
     q.n = km->n;
@@ -786,6 +792,7 @@ int km_residuals(fdb_vs *vs, const fdb_km *km) {
     if (!total) return FDB_OK;
     residual_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(
         vs->d, vs->n, vs->dim, vs->dim, km->centroids.p, km->indices.p);
+    vs->version++;
     ctx->launches++;
     FDB_CHECK_LAUNCH();
     return FDB_OK;

@@ -2,6 +2,8 @@
 #pragma once
 #include "common.cuh"
 
+namespace fdb { struct TcState; }
+
 struct fdb_km {
     fdb_ctx *ctx = nullptr;
     fdb_vs *vs = nullptr;
@@ -21,6 +23,8 @@ struct fdb_km {
     fdb::DevBuf<float> partial;                     // multi-GPU sums ++ counts
     fdb::DevBuf<float> u01;                         // seeding draws staged on the device
     fdb::DevBuf<uint32_t> picked;                   // [k][nb] picks of seed_run
+    fdb::TcState *tc = nullptr;                     // tensor-core assignment state (tc_assign.cu)
+    int last_assign_tc = 0;                         // 1 if the last reassignment ran on the tensor pipe
 };
 
 namespace fdb {
@@ -34,4 +38,8 @@ int km_fill_int(fdb_ctx *ctx, int *p, size_t n, int v);
 int km_update_partial(fdb_km *km);
 int km_update_finish(fdb_km *km);
 int km_residuals(fdb_vs *vs, const fdb_km *km);
+bool tc_eligible(const fdb_km *km);
+int tc_reassign(fdb_km *km, const int *d_active);
+int tc_last_stats(const fdb_km *km, unsigned out[3]);
+void tc_free(fdb_km *km);
 }  // namespace fdb

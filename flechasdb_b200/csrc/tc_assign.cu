@@ -1,0 +1,699 @@
+// Lloyd assignment on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), sm_100a.
+// Replaces the O(n*k*m) loop of reassign_centroids (src/kmeans.rs:279-306) without changing
+// its result:
+//
+//   1. GEMM filter.  s_ij = x_i . c_j - |c_j|^2/2  (argmin_j |x_i-c_j|^2 == argmax_j s_ij) is
+//      evaluated on the tensor pipe with an fp32-accurate 3-term split: every f32 value v is
+//      stored as two bf16 pieces v1 = bf16(v), v2 = bf16(v - v1) (|v - v1 - v2| <= 2^-18 |v|)
+//      and  x.c ~= x1.c1 + x1.c2 + x2.c1  accumulates in fp32 in TMEM (kind::f16 UMMA,
+//      M=128, N<=256, K=16; operands staged by TMA into 128B-swizzled shared memory).
+//      The rows' pieces are written once per k-means problem (the rows do not change
+//      between Lloyd rounds) and cost the same 4 bytes/element as the f32 rows.
+//      Both operands are first shifted by the column mean mu of the rows (x' = fl(x - mu),
+//      c' = fl(c - mu)): distances are shift invariant, while the GEMM error bound scales with
+//      |x'||c'| instead of |x||c| (20x smaller on non-centred data such as uniform [0,1)).
+//   2. Band.  With E_i >= |s~_ij - s_ij| (split + accumulation error, proportional to
+//      |x_i| max_j|c_j|) and eta >= the relative rounding error of the reference's own f32
+//      evaluation, the reference's argmin j* satisfies s~_ij* >= max_j s~_ij - band_i,
+//      band_i = 2 (2 E_i + 1.01 eta d~_min).  The epilogue collects every j inside the band.
+//   3. Exact re-check.  Rows with one candidate are final; the others (a few %) are
+//      evaluated for their candidates only, in the reference's summation order and with its
+//      tie rule (lowest index), by recheck_kernel.  Rows with more than CAP candidates fall
+//      back to all k centroids.  Result: bit-identical indices at tensor-core speed.
+//
+// Kernel anatomy (persistent, one CTA per SM, 384 threads):
+//   warp 0   TMA producer   cp.async.bulk.tensor 2D, SWIZZLE_128B, mbarrier complete_tx
+//   warp 1   MMA issuer     one elected lane, tcgen05.mma.cta_group::1.kind::f16
+//   warp 2   TMEM allocator 512 columns = two accumulator stages of up to 256 columns
+//   warps 4-11 epilogue     tcgen05.ld 32x32b.x32, two passes (row max, band collection)
+#include "kmeans.cuh"
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <cstdlib>
+
+namespace fdb {
+
+namespace {
+
+constexpr int BM = 128;          // rows per tile (UMMA M)
+constexpr int BK = 64;           // bf16 elements per K chunk = one 128-byte swizzle row
+constexpr int CAP = 8;           // candidates kept per row before falling back to all k
+constexpr int TC_THREADS = 384;
+constexpr int EPI_WARP0 = 4;
+constexpr int EPI_THREADS = 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n.reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1,
+                                            uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// K-major operand tile, 128-byte rows, SWIZZLE_128B: 8-row groups are 1024 bytes apart.
+// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO [16,30), SBO [32,46), version=1 [46,48),
+//  layout_type=2 (SWIZZLE_128B) [61,64))
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;                 // LBO (unused for swizzled K-major) = 1
+    d |= (uint64_t)(1024 >> 4) << 32;       // SBO = 1024 bytes
+    d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---- operand preparation -----------------------------------------------------------------
+// rows: f32 -> two bf16 pieces (full row width, every division at once) + |x|^2 per (problem,row)
+__global__ void __launch_bounds__(256) split_rows_kernel(const float *x, size_t n, size_t ldx,
+                                                         size_t col_off, size_t m, size_t nb,
+                                                         const float *mu, __nv_bfloat16 *x1,
+                                                         __nv_bfloat16 *x2, float *xn2) {
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= n * nb) return;
+    const size_t row = warp / nb, b = warp - row * nb;
+    const float *xr = x + row * ldx + col_off + b * m;
+    const float *mr = mu + col_off + b * m;
+    __nv_bfloat16 *o1 = x1 + row * ldx + col_off + b * m;
+    __nv_bfloat16 *o2 = x2 + row * ldx + col_off + b * m;
+    double acc = 0.0;
+    for (size_t e = lane; e < m; e += 32) {
+        const float v = __fsub_rn(xr[e], mr[e]);
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        const float r = __fsub_rn(v, __bfloat162float(h));
+        o1[e] = h;
+        o2[e] = __float2bfloat16_rn(r);
+        acc += (double)v * (double)v;
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) xn2[b * n + row] = __double2float_ru(acc);
+}
+
+// column means of the rows, deterministic two-level reduction (slices of rows, then slices)
+constexpr int MEAN_SLICES = 64;
+__global__ void __launch_bounds__(128) col_partial_kernel(const float *x, size_t n, size_t ldx, size_t c0,
+                                                          size_t ncols, double *partial) {
+    const size_t col = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= ncols) return;
+    const size_t per = (n + MEAN_SLICES - 1) / MEAN_SLICES;
+    const size_t lo = blockIdx.y * per, hi = lo + per < n ? lo + per : n;
+    double acc = 0.0;
+    for (size_t r = lo; r < hi; ++r) acc += (double)x[r * ldx + c0 + col];
+    partial[(size_t)blockIdx.y * ncols + col] = acc;
+}
+__global__ void col_mean_kernel(const double *partial, size_t n, size_t c0, size_t ncols, float *mu) {
+    const size_t col = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= ncols) return;
+    double acc = 0.0;
+    for (int sl = 0; sl < MEAN_SLICES; ++sl) acc += partial[(size_t)sl * ncols + col];
+    const float v = (float)(acc / (double)n);
+    mu[c0 + col] = (v == v && fabsf(v) < 3.0e38f) ? v : 0.0f;
+}
+
+// centroids: f32 -> two bf16 pieces [nb*k][m], h_j = |c_j|^2/2, cmax_b = max_j |c_j| (rounded up)
+__global__ void __launch_bounds__(128) prep_centroids_kernel(const float *c, size_t k, size_t m, size_t np,
+                                                             const float *mu, size_t col_off,
+                                                             __nv_bfloat16 *c1, __nv_bfloat16 *c2,
+                                                             float *h, unsigned *cmax2_bits,
+                                                             const int *active) {
+    const size_t b = blockIdx.y, j = blockIdx.x;
+    if (active && !active[b]) return;
+    if (j >= k) {  // padded columns never win: s = acc - inf
+        if (threadIdx.x == 0) h[b * np + j] = __int_as_float(0x7f800000);
+        return;
+    }
+    const float *cr = c + (b * k + j) * m;
+    const float *mr = mu + col_off + b * m;
+    double acc = 0.0;
+    for (size_t e = threadIdx.x; e < m; e += blockDim.x) {
+        const float v = __fsub_rn(cr[e], mr[e]);
+        const __nv_bfloat16 hh = __float2bfloat16_rn(v);
+        c1[(b * k + j) * m + e] = hh;
+        c2[(b * k + j) * m + e] = __float2bfloat16_rn(__fsub_rn(v, __bfloat162float(hh)));
+        acc += (double)v * (double)v;
+    }
+    __shared__ double red[128];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int off = 64; off >= 1; off >>= 1) {
+        if ((int)threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        h[b * np + j] = (float)(0.5 * red[0]);
+        atomicMax(&cmax2_bits[b], __float_as_uint(__double2float_ru(red[0])));  // >= 0: bit order == value order
+    }
+}
+
+struct TcParams {
+    size_t n, m, nb, k, col_off;
+    int np;                     // padded N (multiple of 64, <= 256)
+    int row_tiles;              // ceil(n / 128)
+    int stages;
+    const float *h;             // [nb][np]
+    const float *xn2;           // [nb][n]
+    const unsigned *cmax2_bits; // [nb]
+    const int *active;
+    float gamma1, eta;
+    uint32_t *indices;          // [nb][n]
+    unsigned *work_count;       // rows that need the exact re-check
+    uint32_t *work_rows;        // [cap] b * n + row
+    uint16_t *work_cand;        // [cap][CAP]
+    uint8_t *work_cnt;          // [cap] number of candidates (CAP+1 = overflow)
+    unsigned work_cap;
+    unsigned *stats;            // [2]: (unused), rows that overflowed CAP
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_assign_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_constant__ CUtensorMap map_x2,
+                 const __grid_constant__ CUtensorMap map_c1, const __grid_constant__ CUtensorMap map_c2,
+                 TcParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    __shared__ __align__(8) uint64_t full_bar[4], empty_bar[4], tmem_full[2], tmem_empty[2];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float rowmax_s[2][BM];
+    __shared__ unsigned cnt_s[BM];
+    __shared__ uint16_t cand_s[BM][CAP];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int NP = p.np;
+    const uint32_t a_bytes = BM * BK * 2;             // 16 KB per piece
+    const uint32_t b_bytes = (uint32_t)NP * BK * 2;   // NP * 128 B per piece
+    const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+    const int S = p.stages;
+    const int kchunks = (int)(p.m / BK);
+    const int total_tiles = (int)p.nb * p.row_tiles;
+    // contiguous tile ranges per CTA (a CTA mostly stays inside one problem: its centroids stay hot in L2)
+    const int per_cta = (total_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int t_begin = (int)blockIdx.x * per_cta;
+    const int t_end = min(total_tiles, t_begin + per_cta);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tmem_full[s], 1);
+            mbar_init(&tmem_empty[s], EPI_THREADS / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x < BM) cnt_s[threadIdx.x] = 0;
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                     "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = t_begin; t < t_end; ++t) {
+                const int b = t / p.row_tiles, rt = t - b * p.row_tiles;
+                if (p.active && !p.active[b]) continue;
+                const int row0 = rt * BM;
+                const int kcol0 = (int)(p.col_off + (size_t)b * p.m);
+                const int crow0 = (int)((size_t)b * p.k);
+                for (int kc = 0; kc < kchunks; ++kc) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    unsigned char *st = smem + (size_t)stage * stage_bytes;
+                    mbar_expect_tx(&full_bar[stage], stage_bytes);
+                    tma_load_2d(st, &map_x1, kcol0 + kc * BK, row0, &full_bar[stage]);
+                    tma_load_2d(st + a_bytes, &map_x2, kcol0 + kc * BK, row0, &full_bar[stage]);
+                    tma_load_2d(st + 2 * a_bytes, &map_c1, kc * BK, crow0, &full_bar[stage]);
+                    tma_load_2d(st + 2 * a_bytes + b_bytes, &map_c2, kc * BK, crow0, &full_bar[stage]);
+                    if (++stage == S) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            // kind::f16 instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7, 10), K-major A and B,
+            // N>>3 at [17,23), M>>4 at [24,29)   (cute::UMMA::InstrDescriptor)
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NP >> 3) << 17) |
+                                   ((uint32_t)(BM >> 4) << 24);
+            int stage = 0, as = 0;
+            uint32_t phase = 0, aphase = 0;
+            for (int t = t_begin; t < t_end; ++t) {
+                const int b = t / p.row_tiles;
+                if (p.active && !p.active[b]) continue;
+                mbar_wait(&tmem_empty[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * NP);
+                for (int kc = 0; kc < kchunks; ++kc) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+                    const uint64_t a1 = make_smem_desc(sa), a2 = make_smem_desc(sa + a_bytes);
+                    const uint64_t b1 = make_smem_desc(sa + 2 * a_bytes);
+                    const uint64_t b2 = make_smem_desc(sa + 2 * a_bytes + b_bytes);
+#pragma unroll
+                    for (int ks = 0; ks < BK / 16; ++ks) {
+                        const uint64_t off = (uint64_t)(ks * 32 >> 4);  // 16 bf16 = 32 bytes along K
+                        umma_bf16(d_tmem, a2 + off, b1 + off, idesc, (kc | ks) != 0);  // small terms first
+                        umma_bf16(d_tmem, a1 + off, b2 + off, idesc, 1);
+                        umma_bf16(d_tmem, a1 + off, b1 + off, idesc, 1);
+                    }
+                    umma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
+                    if (++stage == S) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit(&tmem_full[as]);
+                if (++as == 2) {
+                    as = 0;
+                    aphase ^= 1;
+                }
+            }
+        }
+    } else if (warp >= EPI_WARP0) {
+        // ===== epilogue: 2 threads per row (column halves) =====
+        const int ew = warp - EPI_WARP0;
+        const int q = ew & 3, hf = ew >> 2;
+        const int row = 32 * q + lane;
+        const int half = NP >> 1;
+        const int et = threadIdx.x - EPI_WARP0 * 32;  // 0..255
+        int as = 0;
+        uint32_t aphase = 0;
+        for (int t = t_begin; t < t_end; ++t) {
+            const int b = t / p.row_tiles, rt = t - b * p.row_tiles;
+            if (p.active && !p.active[b]) continue;
+            const size_t grow = (size_t)rt * BM + row;
+            const bool valid = grow < p.n;
+            const float *hb = p.h + (size_t)b * NP + hf * half;
+            mbar_wait(&tmem_full[as], aphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (uint32_t)(as * NP + hf * half) + ((uint32_t)(32 * q) << 16);
+            // pass 1: row maximum of s = acc - h
+            float smax = -__int_as_float(0x7f800000);
+            for (int c0 = 0; c0 < half; c0 += 32) {
+                float v[32];
+                tmem_ld32(taddr + c0, v);
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    const float4 hv = __ldg(reinterpret_cast<const float4 *>(hb + c0 + i));
+                    smax = fmaxf(smax, v[i] - hv.x);
+                    smax = fmaxf(smax, v[i + 1] - hv.y);
+                    smax = fmaxf(smax, v[i + 2] - hv.z);
+                    smax = fmaxf(smax, v[i + 3] - hv.w);
+                }
+            }
+            rowmax_s[hf][row] = smax;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            smax = fmaxf(rowmax_s[0][row], rowmax_s[1][row]);
+            // band (see the header of this file)
+            const float xn2 = valid ? p.xn2[(size_t)b * p.n + grow] : 0.0f;
+            const float cmax2 = __uint_as_float(p.cmax2_bits[b]);
+            const float E = p.gamma1 * sqrtf(xn2 * cmax2) * 1.0001f + 1.2e-7f * (0.5f * cmax2);
+            const float dmin = fmaxf(0.0f, xn2 - 2.0f * smax + 2.0f * E);
+            // rounding of the shift: |d(x',c') - d(x,c)| <= 2 sqrt(d) 2^-24 (|x'| + |c'|)
+            const float shift = 1.3e-7f * sqrtf(dmin) * (sqrtf(xn2) + sqrtf(cmax2));
+            const float band = 2.0f * (2.0f * E + 1.01f * p.eta * dmin + shift);
+            const float thresh = smax - band;
+            // pass 2: every column inside the band is a candidate
+            for (int c0 = 0; c0 < half; c0 += 32) {
+                float v[32];
+                tmem_ld32(taddr + c0, v);
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    const float4 hv = __ldg(reinterpret_cast<const float4 *>(hb + c0 + i));
+                    const float s0 = v[i] - hv.x, s1 = v[i + 1] - hv.y, s2 = v[i + 2] - hv.z, s3 = v[i + 3] - hv.w;
+                    if (s0 >= thresh || s1 >= thresh || s2 >= thresh || s3 >= thresh) {
+                        const float ss[4] = {s0, s1, s2, s3};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (ss[u] >= thresh) {
+                                const unsigned pos = atomicAdd(&cnt_s[row], 1u);
+                                if (pos < CAP) cand_s[row][pos] = (uint16_t)(hf * half + c0 + i + u);
+                            }
+                    }
+                }
+            }
+            // the accumulator stage is free again
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[as]);
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (hf == 0) {
+                const unsigned c = cnt_s[row];
+                cnt_s[row] = 0;
+                // rows with exactly one candidate are final; the others go to the re-check list
+                // (c == 0: non-finite scores, c > CAP: too many candidates -> all k centroids)
+                const bool need = valid && c != 1;
+                const unsigned bal = __ballot_sync(0xffffffffu, need);
+                unsigned base = 0;
+                if (lane == 0 && bal) base = atomicAdd(p.work_count, (unsigned)__popc(bal));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (valid && c == 1) p.indices[(size_t)b * p.n + grow] = cand_s[row][0];
+                if (need) {
+                    const unsigned slot = base + __popc(bal & ((1u << lane) - 1u));
+                    if (slot < p.work_cap) {
+                        p.work_rows[slot] = (uint32_t)((size_t)b * p.n + grow);
+                        const unsigned cc = (c == 0 || c > CAP) ? CAP + 1 : c;
+                        p.work_cnt[slot] = (uint8_t)cc;
+                        for (unsigned u = 0; u < CAP; ++u)
+                            p.work_cand[(size_t)slot * CAP + u] = u < c ? cand_s[row][u] : 0;
+                        if (cc > CAP) atomicAdd(&p.stats[1], 1u);
+                    }
+                }
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            (void)et;
+            if (++as == 2) {
+                as = 0;
+                aphase ^= 1;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+// ---- exact re-check of the rows with several candidates --------------------------------------
+__device__ __forceinline__ float sq_acc(float acc, float x, float c) {
+    float d = __fsub_rn(x, c);
+    return __fadd_rn(acc, __fmul_rn(d, d));
+}
+
+// one warp per row; each quad evaluates one candidate in the reference's order (m % 16 == 0)
+__global__ void __launch_bounds__(256) recheck_kernel(const float *x, size_t n, size_t ldx, size_t col_off,
+                                                      size_t m, size_t k, const float *cent,
+                                                      const unsigned *work_count, unsigned work_cap,
+                                                      const uint32_t *work_rows, const uint16_t *work_cand,
+                                                      const uint8_t *work_cnt, uint32_t *indices,
+                                                      unsigned *flags) {
+    const unsigned total = min(*work_count, work_cap);
+    const int lane = threadIdx.x & 31, quad = lane >> 2, tq = lane & 3;
+    const int qbase = lane & ~3;
+    for (unsigned w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < total;
+         w += (gridDim.x * blockDim.x) >> 5) {
+        const uint32_t br = work_rows[w];
+        const size_t b = br / n, row = br - b * n;
+        const unsigned cnt = work_cnt[w];
+        const bool all = cnt > CAP;
+        const unsigned ncand = all ? (unsigned)k : cnt;
+        const float *xr = x + row * ldx + col_off + b * m;
+        const float *cb = cent + b * k * m;
+        float bd = __int_as_float(0x7f800000);
+        uint32_t bi = 0xFFFFFFFFu;
+        for (unsigned c0 = 0; c0 < ncand; c0 += 8) {
+            const unsigned ci = c0 + quad;
+            const bool act = ci < ncand;
+            const uint32_t j = act ? (all ? ci : (uint32_t)work_cand[(size_t)w * CAP + ci]) : 0;
+            const float *cr = cb + (size_t)j * m;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            if (act) {
+                for (size_t e = 4 * tq; e < m; e += 16) {
+                    const float4 xv = *reinterpret_cast<const float4 *>(xr + e);
+                    const float4 cv = *reinterpret_cast<const float4 *>(cr + e);
+                    a0 = sq_acc(a0, xv.x, cv.x);
+                    a1 = sq_acc(a1, xv.y, cv.y);
+                    a2 = sq_acc(a2, xv.z, cv.z);
+                    a3 = sq_acc(a3, xv.w, cv.w);
+                }
+            }
+            float s = 0.0f;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                if (tq == t) {
+                    s = __fadd_rn(s, a0);
+                    s = __fadd_rn(s, a1);
+                    s = __fadd_rn(s, a2);
+                    s = __fadd_rn(s, a3);
+                }
+                s = __shfl_sync(0xffffffffu, s, qbase + t);
+            }
+            if (act && (s < bd || (s == bd && j < bi))) {
+                bd = s;
+                bi = j;
+            }
+        }
+        // lexicographic (distance, index) minimum over the 8 quads == first strict minimum in index order
+#pragma unroll
+        for (int off = 4; off <= 16; off <<= 1) {
+            const float od = __shfl_xor_sync(0xffffffffu, bd, off);
+            const uint32_t oi = __shfl_xor_sync(0xffffffffu, bi, off);
+            if (oi != 0xFFFFFFFFu && (bi == 0xFFFFFFFFu || od < bd || (od == bd && oi < bi))) {
+                bd = od;
+                bi = oi;
+            }
+        }
+        if (lane == 0) {
+            if (bi == 0xFFFFFFFFu) atomicOr(flags, FLAG_NO_ARGMIN);
+            else indices[b * n + row] = bi;
+        }
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+int make_map(CUtensorMap *map, void *base, uint64_t inner, uint64_t outer, uint32_t box_outer) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled is not available");
+        return FDB_ERR_CUDA;
+    }
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {inner * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed: %d", (int)r);
+        return FDB_ERR_CUDA;
+    }
+    return FDB_OK;
+}
+
+}  // namespace
+
+struct TcState {
+    DevBuf<__nv_bfloat16> x1, x2, c1, c2;
+    DevBuf<float> xn2, h, mu;
+    DevBuf<double> mean_partial;
+    DevBuf<unsigned> cmax2, work_count, stats;
+    DevBuf<uint32_t> work_rows;
+    DevBuf<uint16_t> work_cand;
+    DevBuf<uint8_t> work_cnt;
+    CUtensorMap map_x1, map_x2, map_c1, map_c2;
+    uint64_t rows_version = ~0ull;
+    int np = 0;
+    unsigned last_stats[3] = {0, 0, 0};
+};
+
+bool tc_eligible(const fdb_km *km) {
+    if (getenv("FDB_DISABLE_TC")) return false;
+    const size_t ld = km->vs->dim;
+    return km->k <= 256 && km->m % BK == 0 && ld % 8 == 0 && km->col_off % 8 == 0 &&
+           km->n >= 1 && km->n < (1ull << 31) && km->nb * km->n < (1ull << 32) &&
+           ((uintptr_t)km->vs->d % 16 == 0);
+}
+
+void tc_free(fdb_km *km) {
+    delete km->tc;
+    km->tc = nullptr;
+}
+
+int tc_last_stats(const fdb_km *km, unsigned out[3]) {
+    if (!km->tc) return FDB_ERR_INVALID_CONTEXT;
+    for (int i = 0; i < 3; ++i) out[i] = km->tc->last_stats[i];
+    return FDB_OK;
+}
+
+int tc_reassign(fdb_km *km, const int *d_active) {
+    fdb_ctx *ctx = km->ctx;
+    const size_t n = km->n, m = km->m, nb = km->nb, k = km->k, ld = km->vs->dim;
+    if (!km->tc) km->tc = new TcState;
+    TcState *tc = km->tc;
+    const int np = (int)((k + 63) / 64 * 64);
+    cudaStream_t st = ctx->stream;
+    if (tc->rows_version != km->vs->version || tc->np != np) {
+        FDB_TRY(tc->x1.ensure(n * ld));
+        FDB_TRY(tc->x2.ensure(n * ld));
+        FDB_TRY(tc->xn2.ensure(nb * n));
+        FDB_TRY(tc->c1.ensure(nb * k * m + 256 * m));  // slack: the last problem's box reads past nb*k rows
+        FDB_TRY(tc->c2.ensure(nb * k * m + 256 * m));
+        FDB_TRY(tc->h.ensure(nb * np));
+        FDB_TRY(tc->cmax2.ensure(nb));
+        FDB_TRY(tc->work_count.ensure(1));
+        FDB_TRY(tc->stats.ensure(2));
+        FDB_TRY(tc->work_rows.ensure(nb * n));
+        FDB_TRY(tc->work_cand.ensure(nb * n * CAP));
+        FDB_TRY(tc->work_cnt.ensure(nb * n));
+        FDB_CUDA(cudaMemsetAsync(tc->c1.p, 0, (nb * k * m + 256 * m) * 2, st));
+        FDB_CUDA(cudaMemsetAsync(tc->c2.p, 0, (nb * k * m + 256 * m) * 2, st));
+        // mu = column means of this problem's columns (any mu is valid; the mean minimises |x'|)
+        const size_t ncols = nb * m;
+        FDB_TRY(tc->mu.ensure(ld));
+        FDB_TRY(tc->mean_partial.ensure((size_t)MEAN_SLICES * ncols));
+        FDB_CUDA(cudaMemsetAsync(tc->mu.p, 0, ld * sizeof(float), st));
+        {
+            dim3 grid((unsigned)((ncols + 127) / 128), MEAN_SLICES);
+            col_partial_kernel<<<grid, 128, 0, st>>>(km->vs->d, n, ld, km->col_off, ncols, tc->mean_partial.p);
+            col_mean_kernel<<<(unsigned)((ncols + 127) / 128), 128, 0, st>>>(tc->mean_partial.p, n, km->col_off,
+                                                                          ncols, tc->mu.p);
+            ctx->launches += 2;
+        }
+        const size_t warps = n * nb;
+        split_rows_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(
+            km->vs->d, n, ld, km->col_off, m, nb, tc->mu.p, tc->x1.p, tc->x2.p, tc->xn2.p);
+        ctx->launches++;
+        FDB_CHECK_LAUNCH();
+        FDB_TRY(make_map(&tc->map_x1, tc->x1.p, ld, n, BM));
+        FDB_TRY(make_map(&tc->map_x2, tc->x2.p, ld, n, BM));
+        FDB_TRY(make_map(&tc->map_c1, tc->c1.p, m, nb * k + 256, (uint32_t)np));
+        FDB_TRY(make_map(&tc->map_c2, tc->c2.p, m, nb * k + 256, (uint32_t)np));
+        tc->rows_version = km->vs->version;
+        tc->np = np;
+    }
+    FDB_CUDA(cudaMemsetAsync(tc->cmax2.p, 0, nb * sizeof(unsigned), st));
+    FDB_CUDA(cudaMemsetAsync(tc->work_count.p, 0, sizeof(unsigned), st));
+    FDB_CUDA(cudaMemsetAsync(tc->stats.p, 0, 2 * sizeof(unsigned), st));
+    {
+        dim3 grid((unsigned)np, (unsigned)nb);
+        prep_centroids_kernel<<<grid, 128, 0, st>>>(km->centroids.p, k, m, (size_t)np, tc->mu.p, km->col_off,
+                                                    tc->c1.p, tc->c2.p,
+                                                    tc->h.p, tc->cmax2.p, d_active);
+        ctx->launches++;
+        FDB_CHECK_LAUNCH();
+    }
+    TcParams p;
+    p.n = n;
+    p.m = m;
+    p.nb = nb;
+    p.k = k;
+    p.col_off = km->col_off;
+    p.np = np;
+    p.row_tiles = (int)((n + BM - 1) / BM);
+    const size_t stage_bytes = 2 * (size_t)BM * BK * 2 + 2 * (size_t)np * BK * 2;
+    p.stages = (int)std::min<size_t>(4, (200 * 1024) / stage_bytes);
+    p.h = tc->h.p;
+    p.xn2 = tc->xn2.p;
+    p.cmax2_bits = tc->cmax2.p;
+    p.active = d_active;
+    // split error 3*2^-18 + fp32 accumulation in the tensor pipe, (3m/16) MMAs at <= 2^-21 each
+    p.gamma1 = 3.0f * 3.8146973e-06f + (3.0f * (float)m / 16.0f) * 4.7683716e-07f;
+    // the reference's own f32 evaluation: (m/16 + 20) roundings in the longest chain
+    p.eta = ((float)m / 16.0f + 20.0f) * 5.9604645e-08f;
+    p.indices = km->indices.p;
+    p.work_count = tc->work_count.p;
+    p.work_rows = tc->work_rows.p;
+    p.work_cand = tc->work_cand.p;
+    p.work_cnt = tc->work_cnt.p;
+    p.work_cap = (unsigned)(nb * n);
+    p.stats = tc->stats.p;
+    const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+    FDB_CUDA(cudaFuncSetAttribute(tc_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int total_tiles = (int)nb * p.row_tiles;
+    const int grid = std::min(total_tiles, ctx->sm_count);
+    tc_assign_kernel<<<grid, TC_THREADS, smem, st>>>(tc->map_x1, tc->map_x2, tc->map_c1, tc->map_c2, p);
+    ctx->launches++;
+    FDB_CHECK_LAUNCH();
+    recheck_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(km->vs->d, n, ld, km->col_off, m, k, km->centroids.p,
+                                                      tc->work_count.p, p.work_cap, tc->work_rows.p,
+                                                      tc->work_cand.p, tc->work_cnt.p, km->indices.p,
+                                                      ctx->d_flags);
+    ctx->launches++;
+    FDB_CHECK_LAUNCH();
+    if (getenv("FDB_TC_STATS")) {
+        unsigned hs[3];
+        FDB_CUDA(cudaMemcpyAsync(hs, tc->stats.p, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        FDB_CUDA(cudaMemcpyAsync(hs + 2, tc->work_count.p, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        FDB_CUDA(cudaStreamSynchronize(st));
+        for (int i = 0; i < 3; ++i) tc->last_stats[i] = hs[i];
+        fprintf(stderr, "[fdb tc] rows=%zu recheck=%u overflow=%u\n", nb * n, hs[2], hs[1]);
+    }
+    return FDB_OK;
+}
+
+}  // namespace fdb

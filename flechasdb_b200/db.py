@@ -73,8 +73,9 @@ class DatabaseBuilder:
     engine.VectorSet already resident in HBM; it is consumed (the residues reuse its
     buffer, src/partitions.rs:17-22,120)."""
 
-    def __init__(self, vs, ctx=None, seeds=None, exact_sampler=False):
+    def __init__(self, vs, ctx=None, seeds=None, exact_sampler=False, profile=None):
         self.vs = vs
+        self.profile = profile   # optional dict: phase name -> seconds (adds a sync per phase)
         self.ctx = ctx
         self.seeds = seeds if seeds is not None else SeedSource()
         self.exact_sampler = exact_sampler
@@ -113,7 +114,18 @@ class DatabaseBuilder:
                 raise _invalid_args(e.message) from e
             raise
 
+    def _tick(self, ctx, name, t0):
+        if self.profile is not None:
+            import time
+            ctx.sync()
+            t1 = time.perf_counter()
+            self.profile[name] = self.profile.get(name, 0.0) + (t1 - t0)
+            return t1
+        return t0
+
     def _build(self, ctx, own_ctx, event):
+        import time
+        t = time.perf_counter()
         P, D, Cn = self.num_partitions, self.num_divisions, self.num_clusters
         vs = self.vs if isinstance(self.vs, VectorSet) else VectorSet.upload(ctx, self.vs)
         M, N = len(vs), vs.vector_size
@@ -123,14 +135,18 @@ class DatabaseBuilder:
         raw[:, 6] = (raw[:, 6] & 0x0F) | 0x40   # version 4
         raw[:, 8] = (raw[:, 8] & 0x3F) | 0x80   # RFC 4122 variant
         event(("FinishedIdAssignment",))
+        t = self._tick(ctx, "upload_and_ids", t)
         # partitions all the data (src/db/build.rs:93-98 -> src/partitions.rs:119-143)
         event(("StartingPartitioning",))
         ckm = KMeans(vs, P)
         ckm.seed_run(self.seeds.first(M, 1), self.seeds.draws(1, P - 1), self.exact_sampler)
+        t = self._tick(ctx, "coarse_seeding", t)
         grads, _, reas = ckm.run()
+        t = self._tick(ctx, "coarse_lloyd", t)
         _replay_cluster_events(event, lambda e: ("ClusterEvent", e), grads[0], int(reas[0]))
         vs.subtract_assigned(ckm)
         event(("FinishedPartitioning",))
+        t = self._tick(ctx, "residues", t)
         # divides residual vectors (src/db/build.rs:100-105): strided views, no copy
         event(("StartingSubvectorDivision",))
         if N % D != 0:
@@ -139,12 +155,15 @@ class DatabaseBuilder:
         # builds codebooks for residues (src/db/build.rs:110-118): all divisions side by side
         pkm = KMeans(vs, Cn, col_off=0, dim=N // D, nb=D)
         pkm.seed_run(self.seeds.first(M, D), self.seeds.draws(D, Cn - 1), self.exact_sampler)
+        t = self._tick(ctx, "pq_seeding", t)
         grads, _, reas = pkm.run()
+        t = self._tick(ctx, "pq_lloyd", t)
         for di in range(D):
             event(("StartingQuantization", di))
             _replay_cluster_events(event, lambda e: ("ClusterEvent", e), grads[di], int(reas[di]))
             event(("FinishedQuantization", di))
         index = Index.from_build(ctx, ckm, pkm)
+        t = self._tick(ctx, "events_and_index", t)
         return Database(ctx, own_ctx, vs, ckm, pkm, index, raw, P, D, Cn)
 
 

@@ -167,6 +167,13 @@ class KMeans:
         check(capi.lib().fdb_kmeans_run(self.h, max_rounds, eps, f32p(g), u32p(rounds), u32p(reas)))
         return [g[b, :rounds[b]].copy() for b in range(self.nb)], rounds, reas
 
+    def last_assign_info(self):
+        a = (C.c_uint32 * 3)()
+        check(capi.lib().fdb_kmeans_last_assign_info(
+            self.h, C.cast(C.byref(a, 0), capi.U32P), C.cast(C.byref(a, 4), capi.U32P),
+            C.cast(C.byref(a, 8), capi.U32P)))
+        return dict(tensor_cores=bool(a[0]), rechecked=int(a[1]), overflow=int(a[2]))
+
     def get(self):
         c = np.zeros((self.nb, self.k, self.dim), np.float32)
         i = np.zeros((self.nb, self.n), np.uint32)

@@ -126,6 +126,11 @@ int fdb_kmeans_reassign(fdb_km *km, const uint8_t *active);
  * rounds[nb] the number of updates, reassigns[nb] the number of reassignments. */
 int fdb_kmeans_run(fdb_km *km, size_t max_rounds, float epsilon, float *gradients,
                    uint32_t *rounds, uint32_t *reassigns);
+/* how the last reassignment ran: on the tensor pipe (GEMM filter + exact re-check of the
+ * rows with several candidates) or on the exact fp32 kernel; the row counts are only
+ * collected when the environment variable FDB_TC_STATS is set. */
+int fdb_kmeans_last_assign_info(fdb_km *km, uint32_t *used_tensor_cores, uint32_t *rechecked_rows,
+                                uint32_t *overflow_rows);
 /* Codebook { centroids, indices }: centroids [nb][k][dim], indices [nb][n] */
 int fdb_kmeans_get(fdb_km *km, float *centroids, uint32_t *indices);
 int fdb_kmeans_get_weights(fdb_km *km, float *weights); /* [nb][n] D^2 weights */

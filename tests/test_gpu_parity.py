@@ -424,3 +424,82 @@ def test_golden_fixture(eng, ctx):
         assert (d == g["q%d_dist" % mode]).all() and (c == g["q%d_cnt" % mode]).all()
     for h in (ix, pkm, ckm, vs):
         h.close()
+
+
+# ---- tensor-core assignment (tcgen05 GEMM filter + exact re-check) ---------------------------
+def _tc_case(eng, ctx, oracle, x, cent, nb=1, dim=None, expect_tc=True):
+    n = x.shape[0]
+    k = cent.shape[-2]
+    vs = eng.VectorSet.upload(ctx, x)
+    km = eng.KMeans(vs, k, dim=dim, nb=nb)
+    km.set_state(cent)
+    km.reassign()
+    info = km.last_assign_info()
+    assert info["tensor_cores"] == expect_tc
+    _, idx = km.get()
+    m = km.dim
+    for b in range(nb):
+        rc, want = oracle.kmeans_reassign(x, k, cent.reshape(nb, k, m)[b], off=b * m, dim=m)
+        assert rc == 0
+        bad = np.nonzero(idx[b] != want)[0]
+        assert bad.size == 0, (b, bad[:10], idx[b][bad[:10]], want[bad[:10]])
+    km.close()
+    vs.close()
+
+
+@pytest.mark.parametrize("n,m,k", [(4000, 128, 256), (3000, 1536, 100), (129, 64, 1), (1000, 192, 64),
+                                   (5000, 64, 200), (127, 128, 17)])
+def test_tc_reassign_uniform(eng, ctx, oracle, n, m, k):
+    _tc_case(eng, ctx, oracle, data(oracle, n, m), data(oracle, k, m, SEED + 7))
+
+
+def test_tc_reassign_batched_divisions(eng, ctx, oracle):
+    n, N, D, k = 3000, 768, 6, 256
+    x = data(oracle, n, N) - np.float32(0.5)
+    cent = (data(oracle, D * k, N // D, SEED + 9) - np.float32(0.5)).reshape(D, k, N // D)
+    _tc_case(eng, ctx, oracle, x, cent, nb=D, dim=N // D)
+
+
+def test_tc_reassign_adversarial(eng, ctx, oracle):
+    rng = np.random.default_rng(0)
+    n, m, k = 2000, 128, 64
+    # 1. centroids that are tiny perturbations of one another: every row is a near tie
+    base = data(oracle, 1, m, SEED + 1)
+    cent = (base + rng.normal(0, 1e-6, (k, m))).astype(np.float32)
+    cent[7] = cent[3]
+    _tc_case(eng, ctx, oracle, data(oracle, n, m), cent)
+    # 2. a large common offset: |x|,|c| >> |x-c| (catastrophic cancellation in the GEMM form)
+    x = (data(oracle, n, m) + np.float32(1000.0)).astype(np.float32)
+    cent = (data(oracle, k, m, SEED + 2) + np.float32(1000.0)).astype(np.float32)
+    _tc_case(eng, ctx, oracle, x, cent)
+    # 3. tiny and huge scales
+    for scale in (1e-18, 1e15):
+        _tc_case(eng, ctx, oracle, (data(oracle, n, m) * np.float32(scale)).astype(np.float32),
+                 (data(oracle, k, m, SEED + 3) * np.float32(scale)).astype(np.float32))
+    # 4. rows that coincide with centroids (distance exactly 0) and duplicated rows
+    x = data(oracle, n, m)
+    cent = x[rng.choice(n, k, replace=False)].copy()
+    _tc_case(eng, ctx, oracle, x, cent)
+    # 5. clustered data, mixed signs
+    centers = rng.normal(0, 5, (k, m)).astype(np.float32)
+    x = (centers[rng.integers(0, k, n)] + rng.normal(0, 0.5, (n, m))).astype(np.float32)
+    _tc_case(eng, ctx, oracle, x, centers)
+
+
+def test_tc_lloyd_trajectory_equals_exact_path(eng, ctx, oracle, monkeypatch):
+    """A whole k-means run on the tensor-core path reproduces the oracle's trajectory."""
+    n, m, k = 6000, 128, 32
+    x = data(oracle, n, m)
+    rng = np.random.default_rng(4)
+    chosen = rng.choice(n, k, replace=False).astype(np.uint32)
+    rc, c0, i0, _, _ = oracle.kmeans_init(x, k, int(chosen[0]), chosen=chosen[1:])
+    rc, wc, wi, wg, wnr = oracle.kmeans_lloyd(x, k, c0, i0, max_rounds=25, nthreads=4)
+    vs = eng.VectorSet.upload(ctx, x)
+    km = eng.KMeans(vs, k)
+    km.seed_chosen(chosen[None, :])
+    grads, rounds, reas = km.run(max_rounds=25)
+    assert km.last_assign_info()["tensor_cores"]
+    cent, idx = km.get()
+    assert (grads[0] == wg).all() and (cent[0] == wc).all() and (idx[0] == wi).all()
+    km.close()
+    vs.close()
