@@ -63,6 +63,8 @@ SIGNATURES = {
     "fdb_kmeans_seed_add": (C.c_int, [VP, SZ, U32P, C.c_int]),
     "fdb_kmeans_seed_run": (C.c_int, [VP, U32P, F32P, C.c_int, U32P]),
     "fdb_kmeans_seed_chosen": (C.c_int, [VP, U32P]),
+    "fdb_kmeans_seed_round_ext": (C.c_int, [VP, SZ, F32P, U32P]),
+    "fdb_kmeans_seed_pick_value": (C.c_int, [VP, F32P, U32P]),
     "fdb_kmeans_set_state": (C.c_int, [VP, F32P, U32P]),
     "fdb_kmeans_update": (C.c_int, [VP, U8P, F32P]),
     "fdb_kmeans_reassign": (C.c_int, [VP, U8P]),

@@ -423,6 +423,43 @@ int fdb_kmeans_seed_add(fdb_km *km, size_t i, const uint32_t *ci, int exact) {
     return km_finish_call(km);
 }
 
+/* ---- sharded rows (multi-GPU build): the chosen vector may live on another rank ------------ */
+int fdb_kmeans_seed_pick_value(fdb_km *km, const float *sample_values, uint32_t *ci_out) {
+    ARG(km && sample_values && ci_out, "null argument");
+    ARG(km->weights.p, "seeding has not started");
+    FDB_TRY(km->ctx->use());
+    FDB_TRY(km->u01.ensure(km->nb));
+    FDB_TRY(upload_small(km->ctx, km->u01.p, sample_values, km->nb * sizeof(float)));
+    FDB_TRY(km_seed_pick(km, km->u01.p, 1, 0, 0, 1));
+    FDB_CUDA(cudaMemcpyAsync(ci_out, km->ci.p, km->nb * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                             km->ctx->stream));
+    unsigned f = 0;
+    FDB_TRY(km->ctx->check_flags(&f));
+    return map_flags(f & ~FLAG_WEIGHTS);  // an empty shard is not an error; the caller sums the totals
+}
+
+int fdb_kmeans_seed_round_ext(fdb_km *km, size_t i, const float *centres, const uint32_t *local_ci) {
+    ARG(km && centres && local_ci, "null argument");
+    ARG(i < km->k, "round %zu out of range", i);
+    for (size_t b = 0; b < km->nb; ++b)
+        ARG(local_ci[b] == 0xFFFFFFFFu || local_ci[b] < km->n, "local index out of range");
+    FDB_TRY(km->ctx->use());
+    if (i == 0) {
+        FDB_TRY(km_seed_alloc(km));
+        FDB_CUDA(cudaMemsetAsync(km->chosen.p, 0, km->nb * km->n, km->ctx->stream));
+    } else {
+        ARG(km->weights.p, "round 0 has not run");
+    }
+    FDB_TRY(km->centre.ensure(km->nb * km->m));
+    FDB_TRY(upload_small(km->ctx, km->centre.p, centres, km->nb * km->m * sizeof(float)));
+    FDB_TRY(upload_small(km->ctx, km->ci.p, local_ci, km->nb * sizeof(uint32_t)));
+    FDB_TRY(km_seed_round(km, (uint32_t)i, 0, km->centre.p));
+    FDB_TRY(km_total_fast(km));
+    unsigned f = 0;
+    FDB_TRY(km->ctx->check_flags(&f));
+    return map_flags(f & ~FLAG_WEIGHTS);  // a shard's own total may legitimately be zero
+}
+
 static int seed_loop(fdb_km *km, const uint32_t *first, const float *u01, const uint32_t *chosen,
                      int exact, uint32_t *picked) {
     const size_t nb = km->nb, k = km->k;

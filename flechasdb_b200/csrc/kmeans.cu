@@ -62,7 +62,8 @@ __device__ float uniform_scale(float high) {
 struct SeedParams {
     const float *x;
     size_t n, ldx, col_off, m, nb, k;
-    const uint32_t *ci;      // [nb] chosen vector of this round
+    const uint32_t *ci;      // [nb] chosen vector of this round (0xFFFFFFFF: not in this shard)
+    const float *centre;     // [nb][m] the chosen vectors when they may live on another rank, else null
     float *centroids;        // [nb][k][m]
     const float *w_old;      // [nb][n]
     float *w_new;            // [nb][n]
@@ -82,7 +83,7 @@ __global__ void __launch_bounds__(256) seed_round_kernel(SeedParams p) {
         for (size_t t = threadIdx.x; t < p.nb * p.m; t += blockDim.x) {
             const size_t b = t / p.m, e = t - b * p.m;
             p.centroids[(b * p.k + p.round) * p.m + e] =
-                p.x[(size_t)p.ci[b] * p.ldx + p.col_off + b * p.m + e];
+                p.centre ? p.centre[b * p.m + e] : p.x[(size_t)p.ci[b] * p.ldx + p.col_off + b * p.m + e];
         }
     }
     const size_t per = VEC ? 4 : 1;
@@ -91,7 +92,7 @@ __global__ void __launch_bounds__(256) seed_round_kernel(SeedParams p) {
     const size_t row = valid ? g / p.nb : 0, b = valid ? g % p.nb : 0;
     const uint32_t ci = p.ci[b];
     const float *x = p.x + row * p.ldx + p.col_off + b * p.m;
-    const float *c = p.x + (size_t)ci * p.ldx + p.col_off + b * p.m;
+    const float *c = p.centre ? p.centre + b * p.m : p.x + (size_t)ci * p.ldx + p.col_off + b * p.m;
     float d;
     bool writer;
     if (VEC) {
@@ -231,7 +232,7 @@ __global__ void __launch_bounds__(PICK_THREADS) pick_fast_kernel(const float *w,
                                                                  const float *u01, size_t u_stride,
                                                                  size_t u_off, uint32_t *ci,
                                                                  float *total_out, unsigned *flags,
-                                                                 int pick) {
+                                                                 int pick, int absolute) {
     const size_t b = blockIdx.x;
     const float *x = w + b * n;
     const int t = threadIdx.x;
@@ -266,7 +267,10 @@ __global__ void __launch_bounds__(PICK_THREADS) pick_fast_kernel(const float *w,
         if (!(total_f > 0.0f)) atomicOr(flags, FLAG_WEIGHTS);
     }
     if (!pick) return;
-    const float sample = __fadd_rn(__fmul_rn(u01[b * u_stride + u_off], uniform_scale(total_f)), 0.0f);
+    // absolute: the caller passes the sample value itself (multi-GPU: the part of the global
+    // draw that falls into this shard); a negative value means "not this shard"
+    const float sample = absolute ? u01[b * u_stride + u_off]
+                                  : __fadd_rn(__fmul_rn(u01[b * u_stride + u_off], uniform_scale(total_f)), 0.0f);
     const double sd = (double)sample;
     if (hi > lo && excl[t] + s > sd) atomicMin(&first_t, t);
     // last positive weight, for the case the scan never exceeds the sample
@@ -694,9 +698,10 @@ int km_reassign(fdb_km *km, const int *d_active) {
     return launch_exact_argmin(km->ctx, q, km->indices.p, km->n);
 }
 
-int km_seed_round(fdb_km *km, uint32_t round, int exact) {
+int km_seed_round(fdb_km *km, uint32_t round, int exact, const float *d_centre) {
     fdb_ctx *ctx = km->ctx;
     SeedParams p;
+    p.centre = d_centre;
     p.x = km->vs->d;
     p.n = km->n;
     p.ldx = km->vs->dim;
@@ -712,7 +717,7 @@ int km_seed_round(fdb_km *km, uint32_t round, int exact) {
     p.chosen = km->chosen.p;
     p.round = round;
     const bool vec = (km->m % 16 == 0) && (p.ldx % 4 == 0) && (p.col_off % 4 == 0) &&
-                     ((uintptr_t)p.x % 16 == 0);
+                     ((uintptr_t)p.x % 16 == 0) && (!d_centre || (uintptr_t)d_centre % 16 == 0);
     const size_t threads = km->n * km->nb * (vec ? 4 : 1);
     const unsigned grid = (unsigned)((threads + 255) / 256);
     if (vec) seed_round_kernel<true><<<grid, 256, 0, ctx->stream>>>(p);
@@ -733,14 +738,15 @@ int km_seed_round(fdb_km *km, uint32_t round, int exact) {
     return FDB_OK;
 }
 
-int km_seed_pick(fdb_km *km, const float *d_u01, size_t u_stride, size_t u_off, int exact) {
+int km_seed_pick(fdb_km *km, const float *d_u01, size_t u_stride, size_t u_off, int exact,
+                 int absolute) {
     fdb_ctx *ctx = km->ctx;
-    if (exact) {
+    if (exact && !absolute) {
         pick_exact_kernel<<<(unsigned)km->nb, 1, 0, ctx->stream>>>(
             km->weights.p, km->n, km->total.p, d_u01, u_stride, u_off, km->ci.p, ctx->d_flags);
     } else {
         pick_fast_kernel<<<(unsigned)km->nb, PICK_THREADS, 0, ctx->stream>>>(
-            km->weights.p, km->n, d_u01, u_stride, u_off, km->ci.p, km->total.p, ctx->d_flags, 1);
+            km->weights.p, km->n, d_u01, u_stride, u_off, km->ci.p, km->total.p, ctx->d_flags, 1, absolute);
     }
     ctx->launches++;
     FDB_CHECK_LAUNCH();
@@ -750,7 +756,7 @@ int km_seed_pick(fdb_km *km, const float *d_u01, size_t u_stride, size_t u_off, 
 int km_total_fast(fdb_km *km) {
     fdb_ctx *ctx = km->ctx;
     pick_fast_kernel<<<(unsigned)km->nb, PICK_THREADS, 0, ctx->stream>>>(
-        km->weights.p, km->n, nullptr, 0, 0, km->ci.p, km->total.p, ctx->d_flags, 0);
+        km->weights.p, km->n, nullptr, 0, 0, km->ci.p, km->total.p, ctx->d_flags, 0, 0);
     ctx->launches++;
     FDB_CHECK_LAUNCH();
     return FDB_OK;

@@ -22,6 +22,7 @@ struct fdb_km {
     fdb::DevBuf<int> active, step_active;           // [nb]
     fdb::DevBuf<float> partial;                     // multi-GPU sums ++ counts
     fdb::DevBuf<float> u01;                         // seeding draws staged on the device
+    fdb::DevBuf<float> centre;                      // [nb][m] externally supplied centres (sharded rows)
     fdb::DevBuf<uint32_t> picked;                   // [k][nb] picks of seed_run
     fdb::TcState *tc = nullptr;                     // tensor-core assignment state (tc_assign.cu)
     int last_assign_tc = 0;                         // 1 if the last reassignment ran on the tensor pipe
@@ -31,8 +32,9 @@ namespace fdb {
 int km_sort_members(fdb_km *km, const int *d_active);
 int km_update(fdb_km *km, const int *d_active, int loop_mode, float eps, size_t max_rounds);
 int km_reassign(fdb_km *km, const int *d_active);
-int km_seed_round(fdb_km *km, uint32_t round, int exact);
-int km_seed_pick(fdb_km *km, const float *d_u01, size_t u_stride, size_t u_off, int exact);
+int km_seed_round(fdb_km *km, uint32_t round, int exact, const float *d_centre = nullptr);
+int km_seed_pick(fdb_km *km, const float *d_u01, size_t u_stride, size_t u_off, int exact,
+                 int absolute = 0);
 int km_total_fast(fdb_km *km);
 int km_fill_int(fdb_ctx *ctx, int *p, size_t n, int v);
 int km_update_partial(fdb_km *km);

@@ -1,0 +1,235 @@
+"""Multi-GPU orchestration: one process per GPU, torch.distributed for the plumbing.
+
+Build: rows are sharded contiguously over the ranks, centroids are
+replicated.  k-means++ needs two tiny exchanges per round (the shards' weight totals; the
+chosen vector), a Lloyd round needs ONE all-reduce of `[nb*k*m sums || nb*k counts]`.
+Assignments stay bit-exact per row; centroids differ from the single-GPU run only by the
+order in which the shards' partial sums are added (step-wise parity).
+
+Query: either the index is replicated and the query batch is sharded (no collective), or the
+partitions (code lists) are sharded, every rank scans the partitions it owns and the
+per-rank top-k lists are all-gathered and merged by the canonical key
+(distance, probe rank, vector index), which makes the result independent of the rank count.
+
+Nothing here computes distances: the local work is done by the engine objects
+(flechasdb_b200.engine.KMeans / Index, i.e. libflechasdb_b200.so).  The same code runs on
+CPU tensors over gloo in the tests, with a stand-in for the engine objects.
+"""
+import numpy as np
+
+NONE = 0xFFFFFFFF
+
+
+class Comm:
+    """The three collectives the path needs, over torch.distributed (nccl or gloo)."""
+
+    def __init__(self, dist=None, device="cpu"):
+        self.dist = dist
+        self.device = device
+        self.rank = dist.get_rank() if dist is not None else 0
+        self.world = dist.get_world_size() if dist is not None else 1
+
+    def _t(self, a):
+        import torch
+        return torch.as_tensor(np.ascontiguousarray(a)).to(self.device)
+
+    def all_gather(self, a):
+        """numpy (…)-> numpy (world, …)"""
+        a = np.ascontiguousarray(a)
+        if self.dist is None:
+            return a[None].copy()
+        import torch
+        view = a.view(np.int32) if a.dtype == np.uint32 else a
+        t = self._t(view)
+        out = [torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t)
+        g = np.stack([o.cpu().numpy() for o in out])
+        return g.view(np.uint32) if a.dtype == np.uint32 else g
+
+    def all_reduce_sum_tensor(self, t):
+        """in place on a torch tensor (device buffer of the engine)"""
+        if self.dist is not None:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return t
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+
+
+def shard_rows(n, world, rank):
+    """contiguous shard [lo, hi) of rank"""
+    return n * rank // world, n * (rank + 1) // world
+
+
+def owner_of(index, n, world):
+    for r in range(world):
+        lo, hi = shard_rows(n, world, r)
+        if lo <= index < hi:
+            return r, index - lo
+    raise ValueError("index out of range")
+
+
+def split_sample(u01, totals):
+    """WeightedIndex::sample over the concatenated shards (src/distribution.rs:104-121):
+    the draw u*total lands in the shard whose cumulative weight range contains it.
+    totals: (world,) shard totals for one problem.  Returns (owner, sample value inside it)."""
+    t = totals.astype(np.float64)
+    total = np.float32(t.sum())
+    sample = np.float64(np.float32(u01) * total)
+    cum = 0.0
+    last = None
+    for r in range(len(t)):
+        if t[r] > 0:
+            last = r
+            if cum + t[r] > sample:
+                return r, np.float32(sample - cum)
+            cum += t[r]
+    if last is None:
+        raise ArithmeticError("total weight is zero")  # WeightedIndex unwrap() in the reference
+    return last, np.float32(t[last])                    # rounding pushed the draw past the end
+
+
+def device_tensor(ptr, nfloats, device):
+    """torch view of an engine-owned device buffer (no copy)."""
+    import torch
+
+    class _Arr:
+        pass
+
+    a = _Arr()
+    a.__cuda_array_interface__ = {"shape": (nfloats,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+    return torch.as_tensor(a, device=device)
+
+
+class ShardedKMeans:
+    """cluster_with_events (src/kmeans.rs:104-139) over row shards.
+
+    km        engine.KMeans over this rank's rows (nb problems)
+    get_rows  f(local_index) -> the full local row as float32 (for the chosen vectors)
+    n_global  total number of rows
+    partial_view f(ptr, nfloats) -> torch tensor aliasing the engine's partial buffer
+    """
+
+    def __init__(self, comm, km, get_rows, n_global, col_off=0, partial_view=None):
+        self.comm, self.km, self.get_rows, self.n = comm, km, get_rows, n_global
+        self.col_off = col_off
+        self.partial_view = partial_view
+        self.lo, self.hi = shard_rows(n_global, comm.world, comm.rank)
+
+    def _centres(self, owners_local):
+        """owners_local: list of (owner rank, local index) per problem -> (nb, m) chosen vectors"""
+        km = self.km
+        mine = np.zeros((km.nb, km.dim), np.float32)
+        for b, (r, li) in enumerate(owners_local):
+            if r == self.comm.rank:
+                row = self.get_rows(li)
+                mine[b] = row[self.col_off + b * km.dim: self.col_off + (b + 1) * km.dim]
+        allc = self.comm.all_gather(mine)                     # (world, nb, m); bit-exact copies
+        return np.stack([allc[r, b] for b, (r, _) in enumerate(owners_local)])
+
+    def seed(self, first_global, u01):
+        """k-means++ (src/kmeans.rs:142-229) with the draws injected: first_global[nb] global
+        indices (gen_range(0..n)), u01[nb][k-1].  Returns the picked global indices [nb][k]."""
+        km, comm = self.km, self.comm
+        nb, k = km.nb, km.k
+        picked = np.zeros((nb, k), np.int64)
+        owners = [owner_of(int(g), self.n, comm.world) for g in first_global]
+        for i in range(k):
+            if i > 0:
+                totals = comm.all_gather(km.seed_total())     # (world, nb)
+                choice = [split_sample(u01[b][i - 1], totals[:, b]) for b in range(nb)]
+                values = np.array([v if r == comm.rank else -1.0 for r, v in choice], np.float32)
+                local_pick = km.seed_pick_value(values)
+                picks = comm.all_gather(local_pick)           # (world, nb)
+                owners = [(r, int(picks[r, b])) for b, (r, _) in enumerate(choice)]
+            for b, (r, li) in enumerate(owners):
+                picked[b, i] = shard_rows(self.n, comm.world, r)[0] + li
+            centres = self._centres(owners)
+            local_ci = np.array([li if r == comm.rank else NONE for r, li in owners], np.uint32)
+            km.seed_round_ext(i, centres, local_ci)
+        return picked
+
+    def run(self, max_rounds=100, eps=1e-6, on_round=None):
+        """the Lloyd loop; returns (gradients[nb] list per round, reassignments)"""
+        km, comm = self.km, self.comm
+        active = np.ones(km.nb, np.uint8)
+        grads, reassigns = [], np.zeros(km.nb, np.int64)
+        for r in range(max_rounds):
+            ptr, nfl = km.update_partial()
+            buf = self.partial_view(ptr, nfl)
+            comm.all_reduce_sum_tensor(buf)                   # sums and counts of every shard
+            self._sync()
+            g = km.update_finish()
+            g = np.where(active.astype(bool), g, np.float32(0))
+            grads.append(g.copy())
+            active &= ~(g < eps)
+            if on_round is not None:
+                on_round(r, g)
+            if not active.any():
+                break
+            km.reassign(active)
+            reassigns += active
+        return grads, reassigns
+
+    def _sync(self):
+        if str(self.comm.device).startswith("cuda"):
+            import torch
+            torch.cuda.synchronize()
+
+
+def owned_partitions(sizes, world):
+    """size-balanced greedy assignment of partitions (code lists) to ranks: (P,) owner ids"""
+    order = np.argsort(-np.asarray(sizes, np.int64), kind="stable")
+    load = np.zeros(world, np.int64)
+    owner = np.zeros(len(sizes), np.int64)
+    for p in order:
+        r = int(np.argmin(load))
+        owner[p] = r
+        load[r] += sizes[p]
+    return owner
+
+
+def shard_index_arrays(offsets, codes, owner, rank):
+    """keep only the code lists this rank owns (the others become empty partitions)"""
+    offsets = np.asarray(offsets, np.int64)
+    sizes = np.diff(offsets)
+    keep = owner == rank
+    new_sizes = np.where(keep, sizes, 0)
+    new_off = np.concatenate([[0], np.cumsum(new_sizes)]).astype(np.uint64)
+    parts = [codes[offsets[p]:offsets[p + 1]] for p in range(len(sizes)) if keep[p]]
+    new_codes = np.concatenate(parts) if parts else np.zeros((0, codes.shape[1]), codes.dtype)
+    return new_off, np.ascontiguousarray(new_codes)
+
+
+def merge_topk(parts, vidxs, dists, counts, probes, k):
+    """Cross-rank top-k merge.  Inputs are stacked per rank: (world, nq, k) and (world, nq);
+    probes (nq, nprobe) is the probe order (identical on every rank).  Canonical key:
+    (distance, probe rank of the partition, vector index) == the order of
+    build::Database::query's stable sort (src/db/build.rs:334-337)."""
+    world, nq, kk = dists.shape
+    out_p = np.zeros((nq, k), np.uint32)
+    out_v = np.zeros((nq, k), np.uint32)
+    out_d = np.zeros((nq, k), np.float32)
+    out_c = np.zeros(nq, np.uint32)
+    for q in range(nq):
+        rank_of = {int(p): i for i, p in enumerate(probes[q])}
+        items = []
+        for r in range(world):
+            for i in range(int(counts[r, q])):
+                p = int(parts[r, q, i])
+                items.append((float(dists[r, q, i]), rank_of[p], int(vidxs[r, q, i]), p))
+        items.sort(key=lambda t: t[:3])
+        items = items[:k]
+        out_c[q] = len(items)
+        for i, (d, _, v, p) in enumerate(items):
+            out_p[q, i], out_v[q, i], out_d[q, i] = p, v, d
+    return out_p, out_v, out_d, out_c
+
+
+def sharded_query(comm, index, queries, k, nprobe, mode=1):
+    """partitions sharded: every rank scans its own code lists, results are merged"""
+    probes, _ = index.probe(queries, nprobe, mode)
+    p, v, d, c = index.query(queries, k, nprobe, mode)
+    gp, gv, gd, gc = (comm.all_gather(a) for a in (p, v, d, c))
+    return merge_topk(gp, gv, gd, gc, probes, k)

@@ -135,6 +135,17 @@ class KMeans:
         check(capi.lib().fdb_kmeans_seed_run(self.h, u32p(first), f32p(u), int(exact), u32p(picked)))
         return picked
 
+    def seed_round_ext(self, i, centres, local_ci):
+        c = as_f32(centres).reshape(self.nb, self.dim)
+        l = as_u32(np.atleast_1d(local_ci))
+        check(capi.lib().fdb_kmeans_seed_round_ext(self.h, i, f32p(c), u32p(l)))
+
+    def seed_pick_value(self, values):
+        v = as_f32(np.atleast_1d(values))
+        out = np.zeros(self.nb, np.uint32)
+        check(capi.lib().fdb_kmeans_seed_pick_value(self.h, f32p(v), u32p(out)))
+        return out
+
     def seed_chosen(self, chosen):
         ch = as_u32(chosen).reshape(self.nb, self.k)
         check(capi.lib().fdb_kmeans_seed_chosen(self.h, u32p(ch)))

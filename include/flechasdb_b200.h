@@ -110,6 +110,14 @@ int fdb_kmeans_seed_run(fdb_km *km, const uint32_t *first, const float *u01, int
                         uint32_t *picked);
 /* the same loop with the picks injected ("k-means++ seeds fixed"): chosen[nb][k] */
 int fdb_kmeans_seed_chosen(fdb_km *km, const uint32_t *chosen);
+/* Rows sharded over several processes (multi-GPU build).  The host combines the shards:
+ *   seed_round_ext : round i with the chosen vectors given by value, centres[nb][dim]
+ *                    (host), local_ci[b] = the vector's index in THIS shard or 0xFFFFFFFF;
+ *                    afterwards seed_total returns this shard's totals
+ *   seed_pick_value: WeightedIndex::sample for an absolute sample value inside this shard's
+ *                    cumulative weights (negative = the draw falls into another shard) */
+int fdb_kmeans_seed_round_ext(fdb_km *km, size_t i, const float *centres, const uint32_t *local_ci);
+int fdb_kmeans_seed_pick_value(fdb_km *km, const float *sample_values, uint32_t *ci_out);
 /* test hook / resume: set centroids [nb][k][dim] and (optionally) indices [nb][n] */
 int fdb_kmeans_set_state(fdb_km *km, const float *centroids, const uint32_t *indices);
 

@@ -503,3 +503,20 @@ def test_tc_lloyd_trajectory_equals_exact_path(eng, ctx, oracle, monkeypatch):
     assert (grads[0] == wg).all() and (cent[0] == wc).all() and (idx[0] == wi).all()
     km.close()
     vs.close()
+
+
+# ---- multi-GPU: sharded build + partition-sharded query over NCCL (needs >= 2 GPUs) -----------
+def test_multi_gpu_sharded_build_and_query():
+    import os
+    import subprocess
+    import sys
+    from flechasdb_b200 import _capi as capi
+    ngpu = capi.lib().fdb_device_count()
+    if ngpu < 2:
+        pytest.skip("needs at least 2 GPUs (run with gpurun --gpus 2)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tools", "dist_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "picks_equal=True update_close=True assign_exact=True query_equal=True" in out.stdout
