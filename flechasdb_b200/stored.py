@@ -1,0 +1,396 @@
+"""The reference's on-disk layout: writer and reader (host-side I/O, no arithmetic).
+
+Mirrors serialize_database (src/db/build/proto.rs:25-267), the content-addressed files of
+src/io.rs:170-300 and load_database / load_partition_centroids / load_codebook /
+load_partition of src/db/stored.rs:659-880:
+
+    <base>/<h>.binpb                 Database header                    (zlib)
+    <base>/partitions/<h>.binpb      one Partition per partition        (zlib)
+    <base>/partitions/<h>.binpb      the partition centroids VectorSet  (plain)
+    <base>/codebooks/<h>.binpb       one VectorSet per division         (plain)
+    <base>/attributes/<h>.binpb      one AttributesLog per partition    (zlib)
+
+<h> = URL-safe base64 (no padding) of the SHA-256 of the bytes ON DISK (the hasher sits under
+the zlib encoder, src/io.rs:97-106,231-235).  Messages follow src/protos/database.proto;
+rust-protobuf 3.2.0 writes repeated scalars UNPACKED (one tag per element), which this writer
+reproduces; the reader accepts packed and unpacked.  Compressed bytes (and therefore file
+names) depend on the zlib implementation; the files verify against their own names.
+"""
+import base64
+import hashlib
+import os
+import struct
+import uuid
+import zlib
+
+import numpy as np
+
+EXT = "binpb"
+
+
+# ---- protobuf wire format ----------------------------------------------------------------------
+def _varint(v):
+    out = bytearray()
+    while True:
+        b = v & 0x7F
+        v >>= 7
+        if v:
+            out.append(b | 0x80)
+        else:
+            out.append(b)
+            return bytes(out)
+
+
+def _tag(field, wire):
+    return _varint((field << 3) | wire)
+
+
+def _uint32_field(field, v):
+    return b"" if v == 0 else _tag(field, 0) + _varint(int(v))   # proto3: zero is not written
+
+
+def _string_field(field, s, always=False):
+    b = s.encode()
+    return b"" if (not b and not always) else _tag(field, 2) + _varint(len(b)) + b
+
+
+def _message_field(field, payload):
+    return _tag(field, 2) + _varint(len(payload)) + payload
+
+
+def _floats_unpacked(field, a):
+    """`for v in data { os.write_float(field, v) }`: tag + 4 little-endian bytes per element"""
+    a = np.ascontiguousarray(a, "<f4").reshape(-1)
+    tag = _tag(field, 5)
+    assert len(tag) == 1
+    out = np.empty((a.size, 5), np.uint8)
+    out[:, 0] = tag[0]
+    out[:, 1:] = a.view(np.uint8).reshape(-1, 4)
+    return out.tobytes()
+
+
+def _uint32s_unpacked(field, a):
+    """`for v in data { os.write_uint32(field, v) }` for values < 2^14 (PQ codes)"""
+    a = np.ascontiguousarray(a, np.uint32).reshape(-1)
+    assert a.size == 0 or int(a.max()) < (1 << 14)
+    tag = _tag(field, 0)
+    assert len(tag) == 1
+    two = a >= 128
+    length = 2 + two.astype(np.int64)
+    pos = np.concatenate([[0], np.cumsum(length)])
+    out = np.empty(int(pos[-1]), np.uint8)
+    start = pos[:-1]
+    out[start] = tag[0]
+    out[start + 1] = np.where(two, (a & 0x7F) | 0x80, a).astype(np.uint8)
+    out[start[two] + 2] = (a[two] >> 7).astype(np.uint8)
+    return out.tobytes()
+
+
+def _uuid_message(u16):
+    """Uuid { fixed64 upper = 1; fixed64 lower = 2 } from 16 big-endian bytes
+    (Uuid::as_u64_pair, src/protos/mod.rs:21-27); zero halves are not written."""
+    upper, lower = struct.unpack(">QQ", bytes(u16))
+    out = b""
+    if upper:
+        out += _tag(1, 1) + struct.pack("<Q", upper)
+    if lower:
+        out += _tag(2, 1) + struct.pack("<Q", lower)
+    return out
+
+
+def parse(buf):
+    """generic wire parser -> {field: [values]} (varint int, 64-bit bytes, length-delimited
+    bytes, 32-bit bytes)"""
+    fields = {}
+    i, n = 0, len(buf)
+    while i < n:
+        key = 0
+        shift = 0
+        while True:
+            b = buf[i]
+            i += 1
+            key |= (b & 0x7F) << shift
+            shift += 7
+            if not b & 0x80:
+                break
+        field, wire = key >> 3, key & 7
+        if wire == 0:
+            v = 0
+            shift = 0
+            while True:
+                b = buf[i]
+                i += 1
+                v |= (b & 0x7F) << shift
+                shift += 7
+                if not b & 0x80:
+                    break
+        elif wire == 1:
+            v = buf[i:i + 8]
+            i += 8
+        elif wire == 5:
+            v = buf[i:i + 4]
+            i += 4
+        elif wire == 2:
+            ln = 0
+            shift = 0
+            while True:
+                b = buf[i]
+                i += 1
+                ln |= (b & 0x7F) << shift
+                shift += 7
+                if not b & 0x80:
+                    break
+            v = buf[i:i + ln]
+            i += ln
+        else:
+            raise ValueError("unsupported wire type %d" % wire)
+        fields.setdefault(field, []).append((wire, v))
+    return fields
+
+
+def _parse_floats(buf, field):
+    """repeated float, unpacked fast path (tag + 4 bytes per element) or generic"""
+    tag = _tag(field, 5)[0]
+    b = np.frombuffer(buf, np.uint8)
+    # find where the run of unpacked elements starts: skip leading other fields generically
+    f = parse_prefix(buf, stop_field=field)
+    rest = b[f:]
+    if rest.size and rest.size % 5 == 0 and (rest.reshape(-1, 5)[:, 0] == tag).all():
+        return np.ascontiguousarray(rest.reshape(-1, 5)[:, 1:]).view("<f4").reshape(-1).copy()
+    out = []
+    for wire, v in parse(buf).get(field, []):
+        if wire == 5:
+            out.append(np.frombuffer(v, "<f4"))
+        else:  # packed
+            out.append(np.frombuffer(v, "<f4"))
+    return np.concatenate(out) if out else np.zeros(0, np.float32)
+
+
+def parse_prefix(buf, stop_field):
+    """offset of the first occurrence of `stop_field` when every earlier field is a varint"""
+    i, n = 0, len(buf)
+    while i < n:
+        j = i
+        key = 0
+        shift = 0
+        while True:
+            b = buf[j]
+            j += 1
+            key |= (b & 0x7F) << shift
+            shift += 7
+            if not b & 0x80:
+                break
+        if key >> 3 == stop_field or key & 7 != 0:
+            return i
+        while buf[j] & 0x80:
+            j += 1
+        i = j + 1
+    return n
+
+
+def _parse_uint32s(buf, field):
+    out = []
+    for wire, v in parse(buf).get(field, []):
+        if wire == 0:
+            out.append(v)
+        else:  # packed varints
+            i = 0
+            while i < len(v):
+                x = 0
+                shift = 0
+                while True:
+                    b = v[i]
+                    i += 1
+                    x |= (b & 0x7F) << shift
+                    shift += 7
+                    if not b & 0x80:
+                        break
+                out.append(x)
+    return np.array(out, np.uint32)
+
+
+# ---- content-addressed files (src/io.rs) -----------------------------------------------------------
+class Error(Exception):
+    def __init__(self, kind, msg):
+        super().__init__(msg)
+        self.kind = kind
+
+
+def _persist(base, sub, payload, compressed):
+    data = zlib.compress(payload, 6) if compressed else payload
+    h = base64.urlsafe_b64encode(hashlib.sha256(data).digest()).rstrip(b"=").decode()
+    d = os.path.join(base, sub) if sub else base
+    os.makedirs(d, exist_ok=True)
+    with open(os.path.join(d, h + "." + EXT), "wb") as f:
+        f.write(data)
+    return h
+
+
+def _open(base, rel, compressed, verify=True):
+    path = os.path.join(base, rel)
+    data = open(path, "rb").read()
+    if verify:
+        h = base64.urlsafe_b64encode(hashlib.sha256(data).digest()).rstrip(b"=").decode()
+        stem = os.path.splitext(os.path.basename(path))[0]
+        if h != stem:
+            raise Error("VerificationFailure", "Expected hash %r, but got %s" % (stem, h))
+    return zlib.decompress(data) if compressed else data
+
+
+# ---- messages ---------------------------------------------------------------------------------------
+def vector_set_message(data2d):
+    data2d = np.ascontiguousarray(data2d, np.float32)
+    return _uint32_field(1, data2d.shape[1]) + _floats_unpacked(10, data2d)
+
+
+def partition_message(centroid, codes, ids16):
+    codes = np.ascontiguousarray(codes, np.uint32)
+    D = codes.shape[1]
+    enc = _uint32_field(1, D) + _uint32s_unpacked(10, codes)
+    out = _uint32_field(1, len(centroid)) + _uint32_field(2, D) + _floats_unpacked(10, centroid)
+    out += _message_field(11, enc)
+    out += b"".join(_message_field(12, _uuid_message(u)) for u in ids16)
+    return out
+
+
+def database_message(N, P, D, C, partition_ids, centroids_id, codebook_ids, attributes_log_ids,
+                     attribute_names=()):
+    out = _uint32_field(1, N) + _uint32_field(2, P) + _uint32_field(3, D) + _uint32_field(4, C)
+    out += b"".join(_string_field(10, s, True) for s in partition_ids)
+    out += _string_field(11, centroids_id)
+    out += b"".join(_string_field(12, s, True) for s in codebook_ids)
+    out += b"".join(_string_field(13, s, True) for s in attributes_log_ids)
+    out += b"".join(_string_field(14, s, True) for s in attribute_names)
+    return out
+
+
+def serialize_arrays(base, coarse, codebooks, offsets, codes_pm, ids16):
+    """serialize_database from plain arrays: coarse [P][N], codebooks [D][C][s], offsets [P+1],
+    codes_pm [M][D] partition-major, ids16 [M][16] uint8 partition-major.  Returns the header id."""
+    coarse = np.ascontiguousarray(coarse, np.float32)
+    codebooks = np.ascontiguousarray(codebooks, np.float32)
+    P, N = coarse.shape
+    D, C, _ = codebooks.shape
+    offsets = np.asarray(offsets, np.int64)
+    partition_ids = []
+    for p in range(P):
+        lo, hi = int(offsets[p]), int(offsets[p + 1])
+        msg = partition_message(coarse[p], np.asarray(codes_pm[lo:hi]).reshape(hi - lo, D), ids16[lo:hi])
+        partition_ids.append(_persist(base, "partitions", msg, True))
+    centroids_id = _persist(base, "partitions", vector_set_message(coarse), False)
+    codebook_ids = [_persist(base, "codebooks", vector_set_message(codebooks[d]), False) for d in range(D)]
+    log_ids = [_persist(base, "attributes", _string_field(1, pid), True) for pid in partition_ids]
+    return _persist(base, "", database_message(N, P, D, C, partition_ids, centroids_id, codebook_ids, log_ids), True)
+
+
+def serialize_database(db, base):
+    """db: flechasdb_b200.db.Database (built on the GPU).  Returns the header id; the database
+    is then loadable with load_database(base, "<id>.binpb") here or by the reference."""
+    coarse, _ = db.ckm.get()
+    cbs, _ = db.pkm.get()
+    off, order, codes = db.index.layout(order=True)
+    return serialize_arrays(base, coarse[0], cbs, off, codes, db._id_bytes[order])
+
+
+class StoredArrays:
+    """what stored::Database holds after all lazy loads"""
+
+    def __init__(self, N, P, D, C, coarse, codebooks, offsets, codes_pm, ids16):
+        self.vector_size, self.num_partitions, self.num_divisions, self.num_codes = N, P, D, C
+        self.coarse, self.codebooks, self.offsets, self.codes_pm, self.ids16 = coarse, codebooks, offsets, codes_pm, ids16
+
+    def vector_id(self, partition_index, vector_index):
+        return uuid.UUID(bytes=bytes(self.ids16[int(self.offsets[partition_index]) + vector_index]))
+
+
+def load_database(base, path):
+    """load_database + every lazy loader, with the reference's validation (src/db/stored.rs:659-880)"""
+    hdr = parse(_open(base, path, True))
+
+    def u(field):
+        v = hdr.get(field)
+        return int(v[0][1]) if v else 0
+
+    def strs(field):
+        return [v.decode() for _, v in hdr.get(field, [])]
+
+    N, P, D, C = u(1), u(2), u(3), u(4)
+    for name, v in (("vector_size", N), ("num_divisions", D), ("num_partitions", P), ("num_codes", C)):
+        if v == 0:
+            raise Error("InvalidData", "%s is zero" % name)
+    if N % D:
+        raise Error("InvalidData", "vector_size %d is not multiple of num_divisions %d" % (N, D))
+    partition_ids, codebook_ids = strs(10), strs(12)
+    if len(partition_ids) != P:
+        raise Error("InvalidData", "num_partitions %d and partition_ids.len() %d do not match" % (P, len(partition_ids)))
+    if len(codebook_ids) != D:
+        raise Error("InvalidData", "num_divisions %d and codebook_ids.len() %d do not match" % (D, len(codebook_ids)))
+    # load_partition_centroids never calls verify() (src/db/stored.rs:729-755)
+    cen = _open(base, "partitions/%s.%s" % (strs(11)[0], EXT), False, verify=False)
+    coarse = _parse_floats(cen, 10)
+    cvs = int(parse(cen[:parse_prefix(cen, 10)]).get(1, [(0, 0)])[0][1])
+    if cvs != N:
+        raise Error("InvalidData", "partition centroids vector size mismatch: expected %d, got %d" % (N, cvs))
+    if coarse.size != P * N:
+        raise Error("InvalidData", "partition centroids data length mismatch: expected %d, got %d" % (P, coarse.size // N))
+    s = N // D
+    cbs = np.zeros((D, C, s), np.float32)
+    for d in range(D):
+        raw = _open(base, "codebooks/%s.%s" % (codebook_ids[d], EXT), False)
+        data = _parse_floats(raw, 10)
+        if data.size != C * s:
+            raise Error("InvalidData", "codebook %d has %d elements, expected %d" % (d, data.size, C * s))
+        cbs[d] = data.reshape(C, s)
+    offsets = [0]
+    codes, ids = [], []
+    for p in range(P):
+        f = parse(_open(base, "partitions/%s.%s" % (partition_ids[p], EXT), True))
+        pv, pd = int(f.get(1, [(0, 0)])[0][1]), int(f.get(2, [(0, 0)])[0][1])
+        if pv != N or pd != D:
+            raise Error("InvalidData", "partition %d shape mismatch" % p)
+        enc = f.get(11)
+        data = _parse_uint32s(enc[0][1], 10) if enc else np.zeros(0, np.uint32)
+        if data.size % D:
+            raise Error("InvalidData", "encoded vectors of partition %d are not a multiple of %d" % (p, D))
+        n_p = data.size // D
+        pid = np.zeros((n_p, 16), np.uint8)
+        msgs = f.get(12, [])
+        if len(msgs) != n_p:
+            raise Error("InvalidData", "partition %d: %d vector ids for %d vectors" % (p, len(msgs), n_p))
+        for i, (_, m) in enumerate(msgs):
+            g = parse(m)
+            upper = struct.unpack("<Q", g[1][0][1])[0] if 1 in g else 0
+            lower = struct.unpack("<Q", g[2][0][1])[0] if 2 in g else 0
+            pid[i] = np.frombuffer(struct.pack(">QQ", upper, lower), np.uint8)
+        codes.append(data.reshape(n_p, D))
+        ids.append(pid)
+        offsets.append(offsets[-1] + n_p)
+    codes_pm = np.concatenate(codes) if codes else np.zeros((0, D), np.uint32)
+    ids16 = np.concatenate(ids) if ids else np.zeros((0, 16), np.uint8)
+    return StoredArrays(N, P, D, C, coarse.reshape(P, N), cbs, np.array(offsets, np.uint64), codes_pm, ids16)
+
+
+class StoredDatabase:
+    """stored::Database<f32, LocalFileSystem> resident on the GPU (src/db/stored.rs:41-57,315-389)."""
+
+    def __init__(self, ctx, arrays):
+        from .engine import Index
+        self.arrays = arrays
+        if arrays.num_codes > 256:
+            raise Error("InvalidData", "num_codes > 256 is not supported by the u8 device layout")
+        self.index = Index.create(ctx, arrays.coarse, arrays.codebooks, arrays.offsets,
+                                  arrays.codes_pm.astype(np.uint8))
+
+    @classmethod
+    def load_database(cls, ctx, base, path):
+        return cls(ctx, load_database(base, path))
+
+    def query(self, v, k, nprobe):
+        from . import _capi as capi
+        from .db import QueryResult
+        p, vi, d, c = self.index.query(np.asarray(v, np.float32).reshape(1, -1), k, nprobe, capi.QUERY_STORED)
+        return [QueryResult(int(p[0, i]), self.arrays.vector_id(int(p[0, i]), int(vi[0, i])), int(vi[0, i]),
+                            float(d[0, i])) for i in range(int(c[0]))]
+
+    def close(self):
+        self.index.close()

@@ -520,3 +520,40 @@ def test_multi_gpu_sharded_build_and_query():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "picks_equal=True update_close=True assign_exact=True query_equal=True" in out.stdout
+
+
+# ---- host mirrors: DatabaseBuilder / Database / stored layout ---------------------------------
+def test_database_builder_events_serialize_and_stored_query(eng, ctx, oracle, tmp_path):
+    from flechasdb_b200.db import DatabaseBuilder, SeedSource, Error
+    from flechasdb_b200 import stored
+    M, N = 3000, 64
+    x = data(oracle, M, N)
+    events = []
+    db = DatabaseBuilder(x, ctx=ctx, seeds=SeedSource(5)).with_partitions(8).with_divisions(4) \
+        .with_clusters(32).build_with_events(events.append)
+    names = [e[0] for e in events]
+    # BuildEvent order of src/db/build.rs:84-118
+    assert names[:3] == ["StartingIdAssignment", "FinishedIdAssignment", "StartingPartitioning"]
+    assert names.index("FinishedPartitioning") < names.index("StartingSubvectorDivision") \
+        < names.index("FinishedSubvectorDivision") < names.index("StartingQuantization")
+    assert [e[1] for e in events if e[0] == "StartingQuantization"] == [0, 1, 2, 3]
+    assert names[-1] == "FinishedQuantization"
+    q = data(oracle, 5, N, SEED + 4)
+    qe = []
+    res = db.query_with_events(q[0], 10, 3, qe.append)
+    assert [e[0] for e in qe][:2] == ["StartingPartitionSelection", "FinishedPartitionSelection"]
+    assert len(res) == 10 and all(res[i].squared_distance <= res[i + 1].squared_distance for i in range(9))
+    with pytest.raises(Error) as e:      # nprobe > P -> Err(InvalidArgs)
+        db.query(q[0], 10, 9)
+    assert e.value.kind == "InvalidArgs"
+    # serialize -> load (reference layout) -> stored query == in-memory stored-mode query
+    base = str(tmp_path / "testdb")
+    h = stored.serialize_database(db, base)
+    sdb = stored.StoredDatabase.load_database(ctx, base, h + ".binpb")
+    for qi in range(5):
+        a = db.query(q[qi], 7, 3, mode="stored")
+        b = sdb.query(q[qi], 7, 3)
+        assert [(r.partition_index, r.vector_index, r.squared_distance, r.vector_id) for r in a] == \
+               [(r.partition_index, r.vector_index, r.squared_distance, r.vector_id) for r in b]
+    sdb.close()
+    db.index.close(); db.pkm.close(); db.ckm.close(); db.vs.close()

