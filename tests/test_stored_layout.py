@@ -53,8 +53,8 @@ def test_round_trip_and_content_addressing(tmp_path):
     base = str(tmp_path / "db")
     h = stored.serialize_arrays(base, coarse, cbs, off, codes, ids)
     # file layout and names: URL-safe base64 (no pad) of the SHA-256 of the bytes on disk
-    assert sorted(os.listdir(base)) == ["attributes", "codebooks", "partitions", h + ".binpb"]
-    assert len(os.listdir(os.path.join(base, "partitions"))) == coarse.shape[0] + 1 - 1 + 1 - 1 + 0 or True
+    assert set(os.listdir(base)) == {"attributes", "codebooks", "partitions", h + ".binpb"}
+    assert len(os.listdir(os.path.join(base, "codebooks"))) == cbs.shape[0]
     for sub in ("", "partitions", "codebooks", "attributes"):
         d = os.path.join(base, sub)
         for f in os.listdir(d):
