@@ -102,6 +102,23 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
     d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
     return d;
 }
+// issue without waiting: the registers are valid only after tmem_ld_wait()
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, float (&v)[32]) {
+    uint32_t *r = reinterpret_cast<uint32_t *>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t va_bits(const float (&v)[32], int i) { return __float_as_uint(v[i]); }
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     uint32_t r[32];
     asm volatile(
@@ -229,7 +246,9 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
     unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     __shared__ __align__(8) uint64_t full_bar[4], empty_bar[4], tmem_full[2], tmem_empty[2];
     __shared__ uint32_t tmem_base_s;
-    __shared__ float rowmax_s[2][BM];
+    __shared__ float rowmax_s[2][BM], rowsec_s[2][BM];
+    __shared__ uint16_t rowarg_s[2][BM];
+    __shared__ __align__(16) float h_s[256];
     __shared__ unsigned cnt_s[BM];
     __shared__ uint16_t cand_s[BM][CAP];
 
@@ -343,34 +362,61 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
         const int row = 32 * q + lane;
         const int half = NP >> 1;
         const int et = threadIdx.x - EPI_WARP0 * 32;  // 0..255
-        int as = 0;
+        int as = 0, h_loaded = -1;
         uint32_t aphase = 0;
         for (int t = t_begin; t < t_end; ++t) {
             const int b = t / p.row_tiles, rt = t - b * p.row_tiles;
             if (p.active && !p.active[b]) continue;
             const size_t grow = (size_t)rt * BM + row;
             const bool valid = grow < p.n;
-            const float *hb = p.h + (size_t)b * NP + hf * half;
+            // h_j = |c'_j|^2/2 of this problem in shared memory (reloaded when the problem changes)
+            if (b != h_loaded) {
+                asm volatile("bar.sync 1, 256;" ::: "memory");  // nobody still reads the old values
+                for (int j = et; j < NP; j += EPI_THREADS) h_s[j] = p.h[(size_t)b * NP + j];
+                h_loaded = b;
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            }
+            const float *hb = h_s + hf * half;
             mbar_wait(&tmem_full[as], aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (uint32_t)(as * NP + hf * half) + ((uint32_t)(32 * q) << 16);
-            // pass 1: row maximum of s = acc - h
-            float smax = -__int_as_float(0x7f800000);
-            for (int c0 = 0; c0 < half; c0 += 32) {
-                float v[32];
-                tmem_ld32(taddr + c0, v);
+            // pass 1 (software pipelined TMEM loads): the two largest s = acc - h and the argmax
+            const float NEG_INF = -__int_as_float(0x7f800000);
+            float m1 = NEG_INF, m2 = NEG_INF;
+            int i1 = 0;
+            {
+                float va[32], vb[32];
+                tmem_ld32_issue(taddr, va);
+                for (int c0 = 0; c0 < half; c0 += 64) {
+                    tmem_ld_wait();
+                    if (c0 + 32 < half) tmem_ld32_issue(taddr + c0 + 32, vb);
 #pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    const float4 hv = __ldg(reinterpret_cast<const float4 *>(hb + c0 + i));
-                    smax = fmaxf(smax, v[i] - hv.x);
-                    smax = fmaxf(smax, v[i + 1] - hv.y);
-                    smax = fmaxf(smax, v[i + 2] - hv.z);
-                    smax = fmaxf(smax, v[i + 3] - hv.w);
+                    for (int i = 0; i < 32; ++i) {
+                        const float sv = __uint_as_float(va_bits(va, i)) - hb[c0 + i];
+                        m2 = fmaxf(m2, fminf(sv, m1));
+                        i1 = sv > m1 ? c0 + i : i1;
+                        m1 = fmaxf(m1, sv);
+                    }
+                    if (c0 + 32 < half) {
+                        tmem_ld_wait();
+                        if (c0 + 64 < half) tmem_ld32_issue(taddr + c0 + 64, va);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const float sv = __uint_as_float(va_bits(vb, i)) - hb[c0 + 32 + i];
+                            m2 = fmaxf(m2, fminf(sv, m1));
+                            i1 = sv > m1 ? c0 + 32 + i : i1;
+                            m1 = fmaxf(m1, sv);
+                        }
+                    }
                 }
             }
-            rowmax_s[hf][row] = smax;
+            rowmax_s[hf][row] = m1;
+            rowsec_s[hf][row] = m2;
+            rowarg_s[hf][row] = (uint16_t)(hf * half + i1);
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            smax = fmaxf(rowmax_s[0][row], rowmax_s[1][row]);
+            const float o1 = rowmax_s[hf ^ 1][row], o2 = rowsec_s[hf ^ 1][row];
+            const float smax = fmaxf(m1, o1);
+            const float second = fmaxf(fminf(m1, o1), fmaxf(m2, o2));
             // band (see the header of this file)
             const float xn2 = valid ? p.xn2[(size_t)b * p.n + grow] : 0.0f;
             const float cmax2 = __uint_as_float(p.cmax2_bits[b]);
@@ -380,22 +426,25 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
             const float shift = 1.3e-7f * sqrtf(dmin) * (sqrtf(xn2) + sqrtf(cmax2));
             const float band = 2.0f * (2.0f * E + 1.01f * p.eta * dmin + shift);
             const float thresh = smax - band;
-            // pass 2: every column inside the band is a candidate
-            for (int c0 = 0; c0 < half; c0 += 32) {
-                float v[32];
-                tmem_ld32(taddr + c0, v);
+            // a single column inside the band <=> the runner-up is below the threshold (the
+            // negation also catches NaN scores, which must go to the exact kernel)
+            const bool single = valid && (second < thresh) && (smax > NEG_INF);
+            const bool need2 = valid && !single;
+            // pass 2 (rare): collect every column inside the band
+            if (__any_sync(0xffffffffu, need2)) {
+                for (int c0 = 0; c0 < half; c0 += 32) {
+                    float v[32];
+                    tmem_ld32_issue(taddr + c0, v);
+                    tmem_ld_wait();
+                    if (need2) {
 #pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    const float4 hv = __ldg(reinterpret_cast<const float4 *>(hb + c0 + i));
-                    const float s0 = v[i] - hv.x, s1 = v[i + 1] - hv.y, s2 = v[i + 2] - hv.z, s3 = v[i + 3] - hv.w;
-                    if (s0 >= thresh || s1 >= thresh || s2 >= thresh || s3 >= thresh) {
-                        const float ss[4] = {s0, s1, s2, s3};
-#pragma unroll
-                        for (int u = 0; u < 4; ++u)
-                            if (ss[u] >= thresh) {
+                        for (int i = 0; i < 32; ++i) {
+                            const float sv = __uint_as_float(va_bits(v, i)) - hb[c0 + i];
+                            if (sv >= thresh) {
                                 const unsigned pos = atomicAdd(&cnt_s[row], 1u);
-                                if (pos < CAP) cand_s[row][pos] = (uint16_t)(hf * half + c0 + i + u);
+                                if (pos < CAP) cand_s[row][pos] = (uint16_t)(hf * half + c0 + i);
                             }
+                        }
                     }
                 }
             }
@@ -407,19 +456,20 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
             if (hf == 0) {
                 const unsigned c = cnt_s[row];
                 cnt_s[row] = 0;
-                // rows with exactly one candidate are final; the others go to the re-check list
-                // (c == 0: non-finite scores, c > CAP: too many candidates -> all k centroids)
-                const bool need = valid && c != 1;
+                // rows with exactly one column inside the band are final; the others go to the
+                // re-check list (c == 0: non-finite scores, c > CAP: too many -> all k centroids)
+                const bool need = need2;
                 const unsigned bal = __ballot_sync(0xffffffffu, need);
                 unsigned base = 0;
                 if (lane == 0 && bal) base = atomicAdd(p.work_count, (unsigned)__popc(bal));
                 base = __shfl_sync(0xffffffffu, base, 0);
-                if (valid && c == 1) p.indices[(size_t)b * p.n + grow] = cand_s[row][0];
+                if (single)
+                    p.indices[(size_t)b * p.n + grow] = m1 >= o1 ? rowarg_s[0][row] : rowarg_s[1][row];
                 if (need) {
                     const unsigned slot = base + __popc(bal & ((1u << lane) - 1u));
                     if (slot < p.work_cap) {
                         p.work_rows[slot] = (uint32_t)((size_t)b * p.n + grow);
-                        const unsigned cc = (c == 0 || c > CAP) ? CAP + 1 : c;
+                        const unsigned cc = (c < 2 || c > CAP) ? CAP + 1 : c;
                         p.work_cnt[slot] = (uint8_t)cc;
                         for (unsigned u = 0; u < CAP; ++u)
                             p.work_cand[(size_t)slot * CAP + u] = u < c ? cand_s[row][u] : 0;
