@@ -1,0 +1,724 @@
+// ADC filter path of the batched query: the reference's result at a fraction of its arithmetic.
+//
+// The reference builds, for every probed (query, partition) pair, a table of D*C exact
+// sub-distances |l_d - codebook[d][c]|^2, l = q - centroid_p (src/db/stored.rs:556-573):
+// N*C sub-mul-adds per pair although a query only ever returns k vectors.  Here:
+//
+//   1. expansion.  |l_d - cb|^2 = |l_d|^2 - 2 q_d.cb + (2 c_pd.cb + |cb|^2).  The middle term
+//      depends on the query only (G[q][d][c], one batched fp32 GEMM for all queries), the last
+//      one on the index only (PC[p][d][c], computed once in double).  Per pair the table is
+//      T = G[q] + PC[p] (D*C adds) and the pair constant K = |l|^2.
+//   2. scan.  One CTA per query keeps G[q] and T in shared memory, streams the code lists of
+//      its probed partitions (cp.async, 16-byte coalesced) and keeps the 32 smallest
+//      approximate distances A(v) = K + sum_d T[d][code(v,d)] (register-resident sorted list
+//      per warp, merged per CTA).
+//   3. band.  |A(v) - D(v)| <= E_q for the real-valued D(v) and |R(v) - D(v)| <= eta D(v) for
+//      the reference's f32 value R(v) (bounds below), so every vector that can be among the
+//      reference's k+1 smallest has A(v) <= tau' = (a_(k+1) + E)(1+eta)/(1-eta) + E; the band
+//      is doubled for safety.  If the 32-entry list does not provably contain all of them the
+//      query goes to the exact pipeline.
+//   4. exact re-check.  The candidates (typically k+1) are evaluated in the reference's order
+//      of operations (fl(fl(q - c_p) - cb), 16-lane dot, sequential sum over divisions); the k
+//      smallest are the reference's result when the k+1 smallest are pairwise distinct.
+//      Exact ties (which NBestByKey, src/nbest.rs:52-64, resolves by push history), NaN and
+//      non-finite tables also go to the exact pipeline, which reproduces them slot by slot.
+//
+// Error bound.  u = 2^-24, gamma = s u / (1 - s u) (an s-term FMA chain).  With
+// cbmax_d = max_c |cb_dc|, cb2 = sum_d cbmax_d^2, pcmax = max_p sum_d max_c |PC[p][d][c]|,
+// Qc = sum_d 2 |q_d| cbmax_d and Kmax = max over the query's probes of K:
+//     |A(v) - D(v)| <= (2 gamma + (D+4) u) (Kmax + Qc + pcmax + cb2) =: E_q
+// (terms: rounding of K, of l = fl(q - c_p) inside l.cb, the FMA chain of G, the roundings of
+// PC, T and of the D+1 adds of A).  The reference's own evaluation: (1+u)^(s/16+19+D) - 1
+// <= eta = (s/16 + 40 + D) u relative, all terms being non-negative.
+#include "index.cuh"
+#include "nbest.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+
+namespace fdb {
+
+struct FilterState {
+    DevBuf<float> pc;            // [P][D][C]
+    DevBuf<float> cbmax;         // [D]
+    DevBuf<unsigned> bounds;     // float bits: [0] cb2, [1] pcmax
+    DevBuf<float> G;             // [chunk_q][D][C]
+    DevBuf<float> Kq, Wq;        // [nq][nprobe], [nq]
+    DevBuf<float> cand_d;        // [nq][32]
+    DevBuf<uint32_t> cand_a, cand_cnt, cand_total;
+    DevBuf<unsigned> qbad;       // [nq]
+    DevBuf<uint32_t> fb_list;    // [nq]
+    DevBuf<unsigned long long> counters;  // [0] fallbacks, [1] exact candidates, [2] scanned vectors
+    unsigned long long *h_counters = nullptr;  // pinned
+    size_t chunk_q = 4096;
+    ~FilterState() {
+        if (h_counters) cudaFreeHost(h_counters);
+    }
+};
+
+namespace {
+
+constexpr int RCAP = 32;        // approximate candidates kept per query
+constexpr int KMAX_FILTER = 24; // k + 1 <= 25 leaves >= 7 slots of head room
+constexpr float U24 = 5.9604645e-08f;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+__device__ __forceinline__ unsigned abs_bits(float v) { return __float_as_uint(fabsf(v)); }
+
+// ---- per-index tables ------------------------------------------------------------------
+// PC[p][d][c] = 2 c_pd . cb_dc + |cb_dc|^2 (double accumulation, rounded once)
+__global__ void __launch_bounds__(256) pc_kernel(const float *coarse, const float *cb, size_t P, size_t D,
+                                                 size_t C, size_t s, float *pc) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= P * D * C) return;
+    const size_t p = t / (D * C), dc = t - p * D * C, d = dc / C;
+    const float *cp = coarse + p * D * s + d * s;
+    const float *cr = cb + dc * s;
+    double acc = 0.0;
+    for (size_t i = 0; i < s; ++i) {
+        const double b = (double)cr[i];
+        acc += b * (2.0 * (double)cp[i] + b);
+    }
+    pc[t] = (float)acc;
+}
+// cbmax[d] = max_c |cb_dc| (rounded up), cb2 += cbmax_d^2; one CTA per division
+__global__ void __launch_bounds__(256) cbmax_kernel(const float *cb, size_t C, size_t s, float *cbmax,
+                                                    unsigned *bounds) {
+    __shared__ unsigned red;
+    if (threadIdx.x == 0) red = 0;
+    __syncthreads();
+    const size_t d = blockIdx.x;
+    unsigned mx = 0;
+    for (size_t c = threadIdx.x; c < C; c += blockDim.x) {
+        const float *cr = cb + (d * C + c) * s;
+        double acc = 0.0;
+        for (size_t i = 0; i < s; ++i) acc += (double)cr[i] * (double)cr[i];
+        mx = max(mx, abs_bits(__double2float_ru(sqrt(acc)) * 1.000001f));
+    }
+    atomicMax(&red, mx);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const float m = __uint_as_float(red);
+        cbmax[d] = m;
+        atomicAdd(reinterpret_cast<float *>(&bounds[0]), m * m * 1.000001f);  // D adds: order-dependent in the
+    }                                                                          // last bits, covered by the slack
+}
+// pcmax = max_p sum_d max_c |PC[p][d][c]|; one warp per partition
+__global__ void __launch_bounds__(128) pcmax_kernel(const float *pc, size_t P, size_t D, size_t C,
+                                                    unsigned *bounds) {
+    const size_t p = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (p >= P) return;
+    float sum = 0.0f;
+    bool nan = false;
+    for (size_t d = 0; d < D; ++d) {
+        unsigned mx = 0;
+        for (size_t c = lane; c < C; c += 32) mx = max(mx, abs_bits(pc[(p * D + d) * C + c]));
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+        const float m = __uint_as_float(mx);
+        nan |= m != m;
+        sum += m * 1.000001f;
+    }
+    if (lane == 0) atomicMax(&bounds[1], nan ? 0x7fc00000u : abs_bits(sum * 1.00001f));
+}
+
+// ---- per-pair constants K = |fl(q - c_p)|^2 and the per-query magnitude W -----------------
+__global__ void __launch_bounds__(128) pair_const_kernel(const float *q, const float *coarse,
+                                                         const uint32_t *probes, const float *cbmax,
+                                                         const unsigned *bounds, size_t nq, size_t N,
+                                                         size_t D, size_t s, int nprobe, float *Kq,
+                                                         float *Wq) {
+    const size_t qi = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (qi >= nq) return;
+    const float *qv = q + qi * N;
+    float kmax = 0.0f;
+    bool nan = false;
+    for (int pr = 0; pr < nprobe; ++pr) {
+        const float *cv = coarse + (size_t)probes[qi * nprobe + pr] * N;
+        double acc = 0.0;
+        for (size_t i = lane; i < N; i += 32) {
+            const double l = (double)__fsub_rn(qv[i], cv[i]);
+            acc += l * l;
+        }
+        acc = warp_sum(acc);
+        const float K = (float)acc;
+        if (lane == 0) Kq[qi * nprobe + pr] = K;
+        nan |= K != K;
+        kmax = fmaxf(kmax, K);
+    }
+    double qc = 0.0;
+    for (size_t d = 0; d < D; ++d) {
+        double acc = 0.0;
+        for (size_t i = lane; i < s; i += 32) acc += (double)qv[d * s + i] * (double)qv[d * s + i];
+        acc = warp_sum(acc);
+        qc += 2.0 * sqrt(acc) * (double)cbmax[d];
+    }
+    const double w = ((double)kmax + qc + (double)__uint_as_float(bounds[1]) +
+                      (double)__uint_as_float(bounds[0])) * 1.00001;
+    if (lane == 0) Wq[qi] = nan ? __int_as_float(0x7fc00000) : __double2float_ru(w);
+}
+
+// ---- G[q][d][c] = -2 q_d . cb_dc : batched fp32 GEMM on the FMA pipe -------------------------
+// 128 x 128 tile per CTA (queries x code vectors of one division), 8 x 8 per thread, K in
+// slices of 8 through double-buffered shared memory.
+constexpr int GM = 128, GN = 128, GK = 8, G_THREADS = 256;
+
+template <bool VEC>
+__global__ void __launch_bounds__(G_THREADS, 2) adc_gemm_kernel(const float *__restrict__ q, size_t nq, size_t N,
+                                                                const float *__restrict__ cb, size_t C,
+                                                                size_t s, size_t D, float *__restrict__ G) {
+    __shared__ __align__(16) float As[2][GK][GM];
+    __shared__ __align__(16) float Bs[2][GK][GN];
+    const int tid = threadIdx.x;
+    const size_t d = blockIdx.z;
+    const size_t row0 = (size_t)blockIdx.x * GM, col0 = (size_t)blockIdx.y * GN;
+    const int lr = tid >> 1, lk = (tid & 1) * 4;
+    size_t ar = row0 + lr, br = col0 + lr;
+    if (ar >= nq) ar = nq - 1;
+    if (br >= C) br = C - 1;
+    const float *ap = q + ar * N + d * s;
+    const float *bp = cb + (d * C + br) * s;
+    const int nk = (int)((s + GK - 1) / GK);
+
+    auto load = [&](int kt, float (&a)[4], float (&b)[4]) {
+        const size_t k0 = (size_t)kt * GK + lk;
+        if (VEC) {
+            if (k0 < s) {
+                const float4 av = *reinterpret_cast<const float4 *>(ap + k0);
+                const float4 bv = *reinterpret_cast<const float4 *>(bp + k0);
+                a[0] = av.x, a[1] = av.y, a[2] = av.z, a[3] = av.w;
+                b[0] = bv.x, b[1] = bv.y, b[2] = bv.z, b[3] = bv.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) a[j] = b[j] = 0.0f;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                a[j] = k0 + j < s ? ap[k0 + j] : 0.0f;
+                b[j] = k0 + j < s ? bp[k0 + j] : 0.0f;
+            }
+        }
+    };
+    auto stage = [&](int buf, const float (&a)[4], const float (&b)[4]) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            As[buf][lk + j][lr] = a[j];
+            Bs[buf][lk + j][lr] = b[j];
+        }
+    };
+
+    const int tx = tid & 15, ty = tid >> 4;
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+
+    float ra[4], rb[4];
+    load(0, ra, rb);
+    stage(0, ra, rb);
+    __syncthreads();
+    for (int kt = 0; kt < nk; ++kt) {
+        const int buf = kt & 1;
+        if (kt + 1 < nk) load(kt + 1, ra, rb);
+#pragma unroll
+        for (int kk = 0; kk < GK; ++kk) {
+            const float4 a0 = *reinterpret_cast<const float4 *>(&As[buf][kk][ty * 4]);
+            const float4 a1 = *reinterpret_cast<const float4 *>(&As[buf][kk][64 + ty * 4]);
+            const float4 b0 = *reinterpret_cast<const float4 *>(&Bs[buf][kk][tx * 4]);
+            const float4 b1 = *reinterpret_cast<const float4 *>(&Bs[buf][kk][64 + tx * 4]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        if (kt + 1 < nk) {
+            stage(buf ^ 1, ra, rb);
+            __syncthreads();
+        }
+    }
+    const bool vec_out = (C & 3) == 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const size_t row = row0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+        if (row >= nq) continue;
+        float *o = G + (row * D + d) * C;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const size_t col = col0 + (h ? 64 : 0) + tx * 4;
+            if (vec_out && col + 3 < C) {
+                *reinterpret_cast<float4 *>(o + col) =
+                    make_float4(-2.0f * acc[i][4 * h], -2.0f * acc[i][4 * h + 1], -2.0f * acc[i][4 * h + 2],
+                                -2.0f * acc[i][4 * h + 3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (col + j < C) o[col + j] = -2.0f * acc[i][4 * h + j];
+            }
+        }
+    }
+}
+
+// ---- scan: the 32 smallest approximate distances of a query --------------------------------
+struct FScanParams {
+    const float *G;             // [queries of this chunk][D*C]
+    const float *pc;            // [P][D*C]
+    const float *Kq;            // [nq][nprobe]
+    const uint8_t *codes;
+    const uint32_t *part_off;
+    const uint64_t *part_cstart;
+    const uint32_t *probes;     // [nq][nprobe]
+    size_t q0;
+    int nprobe, D, C, chunk_vecs;
+    float *cand_d;              // [nq][RCAP] ascending
+    uint32_t *cand_a;           // position in the concatenation of the probed lists
+    uint32_t *cand_cnt, *cand_total;
+    unsigned *qbad;
+    unsigned long long *counters;
+};
+
+constexpr int FS_WARPS = 4;
+
+__device__ __forceinline__ void push_lanes(RegSorted &sel, float dv, uint32_t av, bool valid, int lane) {
+    unsigned bal = __ballot_sync(0xffffffffu, valid && (sel.len < sel.n || dv < sel.last));
+    while (bal) {
+        const int L = __ffs(bal) - 1;
+        bal &= bal - 1;
+        sel.push(__shfl_sync(0xffffffffu, dv, L), __shfl_sync(0xffffffffu, av, L), lane);
+    }
+}
+
+__global__ void __launch_bounds__(FS_WARPS * 32) fscan_kernel(FScanParams p) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int D = p.D, C = p.C;
+    const int DC = D * C;
+    const int DCp = (DC + 3) & ~3;
+    float *Gs = reinterpret_cast<float *>(sm);
+    float *Ts = Gs + DCp;
+    const size_t chunk_bytes = (size_t)p.chunk_vecs * D;  // multiple of 16 (chunk_vecs % 32 == 0)
+    unsigned char *cbuf = reinterpret_cast<unsigned char *>(Ts + DCp) + (size_t)warp * 2 * chunk_bytes;
+    float *md = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(Ts + DCp) +
+                                          (size_t)FS_WARPS * 2 * chunk_bytes);
+    uint32_t *ma = reinterpret_cast<uint32_t *>(md + FS_WARPS * RCAP);
+    int *mlen = reinterpret_cast<int *>(ma + FS_WARPS * RCAP);
+
+    const size_t q = p.q0 + blockIdx.x;
+    const float *gq = p.G + (size_t)blockIdx.x * DC;
+    if ((DC & 3) == 0) {
+        for (int i = tid; i < DC / 4; i += FS_WARPS * 32)
+            reinterpret_cast<float4 *>(Gs)[i] = reinterpret_cast<const float4 *>(gq)[i];
+    } else {
+        for (int i = tid; i < DC; i += FS_WARPS * 32) Gs[i] = gq[i];
+    }
+
+    RegSorted sel;
+    sel.init(RCAP);
+    bool bad = false;
+    uint32_t flat0 = 0;
+    for (int pr = 0; pr < p.nprobe; ++pr) {
+        const uint32_t part = p.probes[q * p.nprobe + pr];
+        const int np = (int)(p.part_off[part + 1] - p.part_off[part]);
+        const float K = p.Kq[q * p.nprobe + pr];
+        bad |= !(fabsf(K) < 1e30f);
+        __syncthreads();  // the previous list is fully scanned (first round: Gs is complete)
+        const float *pcp = p.pc + (size_t)part * DC;
+        if ((DC & 3) == 0) {
+            for (int i = tid; i < DC / 4; i += FS_WARPS * 32) {
+                const float4 g = reinterpret_cast<const float4 *>(Gs)[i];
+                const float4 c = __ldg(reinterpret_cast<const float4 *>(pcp) + i);
+                const float4 t = make_float4(g.x + c.x, g.y + c.y, g.z + c.z, g.w + c.w);
+                bad |= !(fabsf(t.x) < 1e30f) | !(fabsf(t.y) < 1e30f) | !(fabsf(t.z) < 1e30f) | !(fabsf(t.w) < 1e30f);
+                reinterpret_cast<float4 *>(Ts)[i] = t;
+            }
+        } else {
+            for (int i = tid; i < DC; i += FS_WARPS * 32) {
+                const float t = Gs[i] + __ldg(pcp + i);
+                bad |= !(fabsf(t) < 1e30f);
+                Ts[i] = t;
+            }
+        }
+        __syncthreads();
+        const uint8_t *cg = p.codes + p.part_cstart[part];
+        const int nchunks = (np + p.chunk_vecs - 1) / p.chunk_vecs;
+        auto issue = [&](int c, int slot) {
+            if (c < nchunks) {
+                const int c0 = c * p.chunk_vecs;
+                const int cnt = min(p.chunk_vecs, np - c0);
+                const size_t n16 = ((size_t)cnt * D + 15) >> 4;
+                const uint8_t *src = cg + (size_t)c0 * D;
+                unsigned char *dst = cbuf + (size_t)slot * chunk_bytes;
+                for (size_t i = lane; i < n16; i += 32) cp_async16(dst + 16 * i, src + 16 * i);
+            }
+            cp_async_commit();
+        };
+        int slot = 0;
+        issue(warp, 0);
+        for (int c = warp; c < nchunks; c += FS_WARPS) {
+            issue(c + FS_WARPS, slot ^ 1);
+            cp_async_wait<1>();
+            __syncwarp();
+            const int c0 = c * p.chunk_vecs;
+            const int cnt = min(p.chunk_vecs, np - c0);
+            const unsigned char *cs = cbuf + (size_t)slot * chunk_bytes;
+            for (int base = 0; base < cnt; base += 32) {
+                const int v = base + lane;
+                const bool valid = v < cnt;
+                float acc = 0.0f;
+                if (valid) {
+                    if ((D & 3) == 0) {
+                        const uint32_t *cw = reinterpret_cast<const uint32_t *>(cs) + (size_t)v * (D >> 2);
+                        for (int w = 0; w < (D >> 2); ++w) {
+                            const uint32_t x = cw[w];
+                            const float *t = Ts + (size_t)(4 * w) * C;
+                            acc += t[x & 255u];
+                            acc += t[C + ((x >> 8) & 255u)];
+                            acc += t[2 * C + ((x >> 16) & 255u)];
+                            acc += t[3 * C + (x >> 24)];
+                        }
+                    } else {
+                        for (int di = 0; di < D; ++di) acc += Ts[(size_t)di * C + cs[(size_t)v * D + di]];
+                    }
+                }
+                push_lanes(sel, acc + K, flat0 + (uint32_t)(c0 + v), valid, lane);
+            }
+            __syncwarp();
+            slot ^= 1;
+        }
+        cp_async_wait<0>();
+        flat0 += (uint32_t)np;
+    }
+    // merge the warps' lists into warp 0's
+    if (lane < sel.len) {
+        md[warp * RCAP + lane] = sel.d;
+        ma[warp * RCAP + lane] = sel.a;
+    }
+    if (lane == 0) mlen[warp] = sel.len;
+    const int anybad = __syncthreads_or(bad ? 1 : 0);
+    if (warp != 0) return;
+    for (int w = 1; w < FS_WARPS; ++w)
+        push_lanes(sel, md[w * RCAP + lane], ma[w * RCAP + lane], lane < mlen[w], lane);
+    if (lane < sel.len) {
+        p.cand_d[q * RCAP + lane] = sel.d;
+        p.cand_a[q * RCAP + lane] = sel.a;
+    }
+    if (lane == 0) {
+        p.cand_cnt[q] = (uint32_t)sel.len;
+        p.cand_total[q] = flat0;
+        p.qbad[q] = (unsigned)anybad;
+        atomicAdd(&p.counters[2], (unsigned long long)flat0);
+    }
+}
+
+// ---- band, exact re-check of the candidates, final selection; one warp per query ------------
+struct FSelParams {
+    const float *q;
+    const float *coarse, *codebooks;
+    const uint8_t *codes;
+    const uint32_t *part_off;
+    const uint64_t *part_cstart;
+    const uint32_t *probes;
+    const float *Wq;
+    const float *cand_d;
+    const uint32_t *cand_a, *cand_cnt, *cand_total;
+    const unsigned *qbad;
+    size_t q0, q1, N, D, C, s;
+    int nprobe, k;
+    float coef, eta3;
+    uint32_t *out_p, *out_v, *out_c;
+    float *out_d;
+    uint32_t *fb_list;
+    unsigned long long *counters;
+};
+
+__device__ __forceinline__ float sq_diff2(float qv, float cv, float bv) {
+    const float l = __fsub_rn(qv, cv);        // localise, src/db/stored.rs:421
+    const float d = __fsub_rn(l, bv);         // subtract, src/db/stored.rs:565-571
+    return __fmul_rn(d, d);
+}
+
+__global__ void __launch_bounds__(128) fselect_kernel(FSelParams p) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t q = p.q0 + (size_t)blockIdx.x * 4 + warp;
+    if (q >= p.q1) return;
+    const int cnt = (int)p.cand_cnt[q];
+    const uint32_t total = p.cand_total[q];
+    const int k = p.k;
+    bool fb = p.qbad[q] != 0;
+    if (cnt == 0 && !fb) {
+        if (lane == 0) p.out_c[q] = 0;
+        return;
+    }
+    const float a = lane < cnt ? p.cand_d[q * RCAP + lane] : INF;
+    const uint32_t t = lane < cnt ? p.cand_a[q * RCAP + lane] : 0u;
+    int ncand = cnt;
+    if (cnt > k) {
+        const float E = p.coef * p.Wq[q];
+        const float tau = __shfl_sync(0xffffffffu, a, k);  // the (k+1)-th smallest approximation
+        const float hi = (tau + E) * (1.0f + p.eta3) + E;
+        const float thr = tau + 2.0f * (hi - tau);
+        if (!(fabsf(thr) < 1e30f)) fb = true;  // NaN or overflow
+        ncand = __popc(__ballot_sync(0xffffffffu, lane < cnt && a <= thr));
+        if (ncand == RCAP && total > (uint32_t)RCAP) fb = true;  // the list may be incomplete
+    }
+    if (fb) {
+        if (lane == 0) p.fb_list[atomicAdd(&p.counters[0], 1ull)] = (uint32_t)q;
+        return;
+    }
+    // position in the concatenated lists -> (partition, vector_index)
+    uint32_t my_part = 0, my_vidx = 0, start = 0;
+    for (int pr = 0; pr < p.nprobe; ++pr) {
+        const uint32_t part = p.probes[q * p.nprobe + pr];
+        const uint32_t np = p.part_off[part + 1] - p.part_off[part];
+        if (t >= start && t - start < np) {
+            my_part = part;
+            my_vidx = t - start;
+        }
+        start += np;
+    }
+    // exact distances, two candidates at a time (one per half warp); lane j of a half owns
+    // accumulator j of the 16-lane dot (src/linalg.rs:12-40)
+    const int half = lane >> 4, j = lane & 15, hbase = half * 16;
+    const size_t s = p.s, D = p.D;
+    const size_t r = s & 15;
+    const float *qv = p.q + q * p.N;
+    float myR = 0.0f;
+    for (int i = 0; 2 * i < ncand; ++i) {
+        const int c = 2 * i + half;
+        const int src = c < ncand ? c : 0;
+        const uint32_t part = __shfl_sync(0xffffffffu, my_part, src);
+        const uint32_t vidx = __shfl_sync(0xffffffffu, my_vidx, src);
+        const uint8_t *code = p.codes + p.part_cstart[part] + (size_t)vidx * D;
+        const float *cv = p.coarse + (size_t)part * p.N;
+        float R = 0.0f;  // dist = 0; dist += table[..] in division order, src/db/stored.rs:581-587
+        for (size_t d = 0; d < D; ++d) {
+            const float *bv = p.codebooks + (d * p.C + code[d]) * s;
+            const size_t o = d * s;
+            float T;
+            if (s < 16) {  // dot_naive, src/linalg.rs:43-53
+                T = 0.0f;
+                for (size_t e = 0; e < s; ++e) T = __fadd_rn(T, sq_diff2(qv[o + e], cv[o + e], bv[e]));
+            } else {
+                float acc = 0.0f;
+                if ((size_t)j < r) acc = sq_diff2(qv[o + j], cv[o + j], bv[j]);
+                for (size_t base = r; base < s; base += 16) {
+                    const size_t e = base + j;
+                    acc = __fadd_rn(acc, sq_diff2(qv[o + e], cv[o + e], bv[e]));
+                }
+                T = 0.0f;
+#pragma unroll
+                for (int l = 0; l < 16; ++l) T = __fadd_rn(T, __shfl_sync(0xffffffffu, acc, hbase + l));
+            }
+            R = __fadd_rn(R, T);
+        }
+        const float v = __shfl_sync(0xffffffffu, R, (lane & 1) * 16);
+        if ((lane >> 1) == i) myR = v;
+    }
+    const bool mine = lane < ncand;
+    int rank = 0;
+    bool tie = false;
+    for (int jx = 0; jx < ncand; ++jx) {
+        const float Rj = __shfl_sync(0xffffffffu, myR, jx);
+        rank += (Rj < myR) || (Rj == myR && jx < lane);
+        tie |= (Rj == myR) && jx != lane;
+    }
+    // NaN, or an exact tie among the k+1 smallest: the reference's answer depends on push history
+    const bool hard = mine && ((myR != myR) || (tie && rank <= k));
+    if (__any_sync(0xffffffffu, hard)) {
+        if (lane == 0) p.fb_list[atomicAdd(&p.counters[0], 1ull)] = (uint32_t)q;
+        return;
+    }
+    const int keep = min(k, ncand);
+    if (mine && rank < keep) {
+        p.out_p[q * k + rank] = my_part;
+        p.out_v[q * k + rank] = my_vidx;
+        p.out_d[q * k + rank] = myR;
+    }
+    if (lane == 0) {
+        p.out_c[q] = (uint32_t)keep;
+        atomicAdd(&p.counters[1], (unsigned long long)ncand);
+    }
+}
+
+size_t scan_smem_bytes(const fdb_index *ix, int chunk_vecs) {
+    const size_t DCp = (ix->D * ix->C + 3) & ~(size_t)3;
+    return 2 * DCp * 4 + (size_t)FS_WARPS * 2 * chunk_vecs * ix->D + (size_t)FS_WARPS * RCAP * 8 +
+           FS_WARPS * 4 + 16;
+}
+int scan_chunk_vecs(const fdb_index *ix) {
+    return (int)std::max<size_t>(32, (2048 / ix->D) & ~(size_t)31);
+}
+
+}  // namespace
+
+}  // namespace fdb
+
+fdb_index::~fdb_index() { delete filter; }
+
+namespace fdb {
+
+void filter_free(fdb_index *ix) {
+    delete ix->filter;
+    ix->filter = nullptr;
+}
+
+int filter_prepare(fdb_index *ix) {
+    filter_free(ix);
+    if (getenv("FDB_QUERY_EXACT")) return FDB_OK;
+    fdb_ctx *ctx = ix->ctx;
+    const size_t P = ix->P, D = ix->D, C = ix->C, s = ix->s;
+    if (P * D * C * sizeof(float) > (4ull << 30)) return FDB_OK;          // PC tables too large
+    if (scan_smem_bytes(ix, scan_chunk_vecs(ix)) > 200 * 1024) return FDB_OK;
+    if ((double)s * U24 > 1e-3) return FDB_OK;
+    FilterState *fs = new FilterState;
+    ix->filter = fs;
+    cudaStream_t st = ctx->stream;
+    FDB_TRY(fs->pc.alloc(P * D * C));
+    FDB_TRY(fs->cbmax.alloc(D));
+    FDB_TRY(fs->bounds.alloc(2));
+    FDB_TRY(fs->counters.alloc(4));
+    FDB_CUDA(cudaMallocHost((void **)&fs->h_counters, 4 * sizeof(unsigned long long)));
+    FDB_CUDA(cudaMemsetAsync(fs->bounds.p, 0, 2 * sizeof(unsigned), st));
+    pc_kernel<<<(unsigned)((P * D * C + 255) / 256), 256, 0, st>>>(ix->coarse.p, ix->codebooks.p, P, D, C, s,
+                                                                  fs->pc.p);
+    cbmax_kernel<<<(unsigned)D, 256, 0, st>>>(ix->codebooks.p, C, s, fs->cbmax.p, fs->bounds.p);
+    pcmax_kernel<<<(unsigned)((P * 32 + 127) / 128), 128, 0, st>>>(fs->pc.p, P, D, C, fs->bounds.p);
+    ctx->launches += 3;
+    FDB_CHECK_LAUNCH();
+    float hb[2];
+    FDB_CUDA(cudaMemcpyAsync(hb, fs->bounds.p, sizeof(hb), cudaMemcpyDeviceToHost, st));
+    FDB_CUDA(cudaStreamSynchronize(st));
+    if (const char *e = getenv("FDB_FILTER_CHUNK_Q")) fs->chunk_q = (size_t)std::max(1L, atol(e));
+    if (!(std::isfinite(hb[0]) && std::isfinite(hb[1]) && hb[0] < 1e30f && hb[1] < 1e30f))
+        filter_free(ix);  // non-finite centroids or code vectors: exact pipeline only
+    return FDB_OK;
+}
+
+bool filter_eligible(const fdb_index *ix, size_t nq, size_t k, size_t nprobe) {
+    return ix->filter && !getenv("FDB_QUERY_EXACT") && k <= (size_t)KMAX_FILTER && nq > 0 &&
+           nq * RCAP < (1ull << 32) && ix->M < (1ull << 32) && nprobe <= 4096;
+}
+
+int filter_query(fdb_index *ix, const float *d_q, size_t nq, size_t k, size_t nprobe, uint32_t *d_p,
+                 uint32_t *d_v, float *d_d, uint32_t *d_c, EventLog *log, const uint32_t **d_fb_list,
+                 unsigned *h_nfb) {
+    fdb_ctx *ctx = ix->ctx;
+    FilterState *fs = ix->filter;
+    cudaStream_t st = ctx->stream;
+    const size_t N = ix->N, D = ix->D, C = ix->C, s = ix->s, DC = D * C;
+    const size_t chunk = std::min(nq, fs->chunk_q);
+    FDB_TRY(fs->G.ensure(chunk * DC));
+    FDB_TRY(fs->Kq.ensure(nq * nprobe));
+    FDB_TRY(fs->Wq.ensure(nq));
+    FDB_TRY(fs->cand_d.ensure(nq * RCAP));
+    FDB_TRY(fs->cand_a.ensure(nq * RCAP));
+    FDB_TRY(fs->cand_cnt.ensure(nq));
+    FDB_TRY(fs->cand_total.ensure(nq));
+    FDB_TRY(fs->qbad.ensure(nq));
+    FDB_TRY(fs->fb_list.ensure(nq));
+    FDB_CUDA(cudaMemsetAsync(fs->counters.p, 0, 4 * sizeof(unsigned long long), st));
+
+    FDB_TRY(log->mark(2));
+    pair_const_kernel<<<(unsigned)((nq * 32 + 127) / 128), 128, 0, st>>>(
+        d_q, ix->coarse.p, ix->probes.p, fs->cbmax.p, fs->bounds.p, nq, N, D, s, (int)nprobe, fs->Kq.p,
+        fs->Wq.p);
+    ctx->launches++;
+    FDB_CHECK_LAUNCH();
+
+    const int chunk_vecs = scan_chunk_vecs(ix);
+    const size_t smem = scan_smem_bytes(ix, chunk_vecs);
+    FDB_CUDA(cudaFuncSetAttribute(fscan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const bool vec = (s % 4 == 0) && (N % 4 == 0) && ((uintptr_t)d_q % 16 == 0);
+    const double gamma = (double)s * U24 / (1.0 - (double)s * U24);
+    const float coef = (float)((2.0 * gamma + (double)(D + 4) * U24) * 1.01);
+    const float eta3 = (float)(2.1 * ((double)s / 16.0 + 40.0 + (double)D) * U24);
+
+    for (size_t q0 = 0; q0 < nq; q0 += chunk) {
+        const size_t nc = std::min(chunk, nq - q0);
+        FDB_TRY(log->mark(3));
+        dim3 grid((unsigned)((nc + GM - 1) / GM), (unsigned)((C + GN - 1) / GN), (unsigned)D);
+        if (vec) adc_gemm_kernel<true><<<grid, G_THREADS, 0, st>>>(d_q + q0 * N, nc, N, ix->codebooks.p, C, s, D, fs->G.p);
+        else adc_gemm_kernel<false><<<grid, G_THREADS, 0, st>>>(d_q + q0 * N, nc, N, ix->codebooks.p, C, s, D, fs->G.p);
+        ctx->launches++;
+        FDB_CHECK_LAUNCH();
+        FDB_TRY(log->mark(4));
+        FScanParams sp;
+        sp.G = fs->G.p;
+        sp.pc = fs->pc.p;
+        sp.Kq = fs->Kq.p;
+        sp.codes = ix->codes.p;
+        sp.part_off = ix->part_off.p;
+        sp.part_cstart = ix->part_cstart.p;
+        sp.probes = ix->probes.p;
+        sp.q0 = q0;
+        sp.nprobe = (int)nprobe;
+        sp.D = (int)D;
+        sp.C = (int)C;
+        sp.chunk_vecs = chunk_vecs;
+        sp.cand_d = fs->cand_d.p;
+        sp.cand_a = fs->cand_a.p;
+        sp.cand_cnt = fs->cand_cnt.p;
+        sp.cand_total = fs->cand_total.p;
+        sp.qbad = fs->qbad.p;
+        sp.counters = fs->counters.p;
+        fscan_kernel<<<(unsigned)nc, FS_WARPS * 32, smem, st>>>(sp);
+        ctx->launches++;
+        FDB_CHECK_LAUNCH();
+    }
+    FDB_TRY(log->mark(5));
+    FSelParams fp;
+    fp.q = d_q;
+    fp.coarse = ix->coarse.p;
+    fp.codebooks = ix->codebooks.p;
+    fp.codes = ix->codes.p;
+    fp.part_off = ix->part_off.p;
+    fp.part_cstart = ix->part_cstart.p;
+    fp.probes = ix->probes.p;
+    fp.Wq = fs->Wq.p;
+    fp.cand_d = fs->cand_d.p;
+    fp.cand_a = fs->cand_a.p;
+    fp.cand_cnt = fs->cand_cnt.p;
+    fp.cand_total = fs->cand_total.p;
+    fp.qbad = fs->qbad.p;
+    fp.q0 = 0;
+    fp.q1 = nq;
+    fp.N = N;
+    fp.D = D;
+    fp.C = C;
+    fp.s = s;
+    fp.nprobe = (int)nprobe;
+    fp.k = (int)k;
+    fp.coef = coef;
+    fp.eta3 = eta3;
+    fp.out_p = d_p;
+    fp.out_v = d_v;
+    fp.out_c = d_c;
+    fp.out_d = d_d;
+    fp.fb_list = fs->fb_list.p;
+    fp.counters = fs->counters.p;
+    fselect_kernel<<<(unsigned)((nq + 3) / 4), 128, 0, st>>>(fp);
+    ctx->launches++;
+    FDB_CHECK_LAUNCH();
+    FDB_CUDA(cudaMemcpyAsync(fs->h_counters, fs->counters.p, 4 * sizeof(unsigned long long),
+                             cudaMemcpyDeviceToHost, st));
+    FDB_CUDA(cudaStreamSynchronize(st));
+    *h_nfb = (unsigned)fs->h_counters[0];
+    *d_fb_list = fs->fb_list.p;
+    ix->last_stats[0] = nq - fs->h_counters[0];
+    ix->last_stats[1] = fs->h_counters[0];
+    ix->last_stats[2] = fs->h_counters[1];
+    ix->last_stats[3] = fs->h_counters[2];
+    return FDB_OK;
+}
+
+}  // namespace fdb

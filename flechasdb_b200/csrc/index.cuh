@@ -1,0 +1,81 @@
+// Device state of a queryable IVF-PQ index (stored::Database, src/db/stored.rs:41-57).
+#pragma once
+#include "kmeans.cuh"
+
+#include <vector>
+
+namespace fdb { struct FilterState; }
+
+struct fdb_index {
+    fdb_ctx *ctx = nullptr;
+    size_t N = 0, P = 0, D = 0, C = 0, s = 0, M = 0;
+    fdb::DevBuf<float> coarse, codebooks;
+    fdb::DevBuf<uint8_t> codes;
+    fdb::DevBuf<uint32_t> part_off;    // [P+1] vectors before partition p
+    fdb::DevBuf<uint64_t> part_cstart; // [P] byte offset of the partition's code list
+    fdb::DevBuf<uint32_t> order;       // [M] global vector index at each partition-major position
+    std::vector<uint32_t> h_off;
+    std::vector<uint64_t> h_cstart;
+    // scratch
+    fdb::DevBuf<float> q_dev, dist, loc, tables, part_d, out_d, probe_d;
+    fdb::DevBuf<uint32_t> probes, part_v, part_cnt, out_p, out_v, out_c;
+    std::vector<cudaEvent_t> events;
+    float phase_ms[6] = {0, 0, 0, 0, 0, 0};
+    uint64_t scan_bytes = 0;
+    size_t last_npairs = 0;
+    bool timing = false;
+    size_t chunk_pairs = 8192;
+    fdb::DevBuf<float> fb_q, fb_d;        // queries the filter path handed to the exact pipeline
+    fdb::DevBuf<uint32_t> fb_p, fb_v, fb_c;
+    bool last_filter = false;
+    fdb::FilterState *filter = nullptr;   // ADC filter path (adc_filter.cu), null when not usable
+    uint64_t last_stats[4] = {0, 0, 0, 0};  // queries on the filter path, exact fallbacks, exact candidates, scanned vectors
+    ~fdb_index();                         // adc_filter.cu (FilterState is complete there)
+};
+
+namespace fdb {
+
+// CUDA-event log of the query phases (0 coarse, 1 probe, 2 localise / pair constants,
+// 3 ADC tables, 4 code scan, 5 selection / merge); a phase ends where the next mark starts
+struct EventLog {
+    fdb_index *ix;
+    size_t used = 0;
+    std::vector<std::pair<int, size_t>> marks;  // (phase, index of the start event)
+    int mark(int phase) {
+        if (!ix->timing) return FDB_OK;
+        if (used == ix->events.size()) {
+            cudaEvent_t e;
+            FDB_CUDA(cudaEventCreate(&e));
+            ix->events.push_back(e);
+        }
+        FDB_CUDA(cudaEventRecord(ix->events[used], ix->ctx->stream));
+        marks.emplace_back(phase, used);
+        used++;
+        return FDB_OK;
+    }
+    int finish() {
+        for (int i = 0; i < 6; ++i) ix->phase_ms[i] = 0.f;
+        if (!ix->timing) return FDB_OK;
+        for (size_t i = 0; i + 1 < marks.size(); ++i) {
+            if (marks[i].first < 0) continue;
+            float ms = 0.f;
+            FDB_CUDA(cudaEventElapsedTime(&ms, ix->events[marks[i].second], ix->events[marks[i + 1].second]));
+            ix->phase_ms[marks[i].first] += ms;
+        }
+        return FDB_OK;
+    }
+};
+
+// ---- ADC filter path (adc_filter.cu) ---------------------------------------------------
+// filter_prepare: per-index tables and bounds, once the coarse centroids and codebooks are
+// resident.  filter_query: decides every query it can from approximate tables + an exact
+// re-check of the few candidates inside the error band; the others are appended to
+// *d_fb_list (count in *h_nfb) for the exact pipeline.
+int filter_prepare(fdb_index *ix);
+void filter_free(fdb_index *ix);
+bool filter_eligible(const fdb_index *ix, size_t nq, size_t k, size_t nprobe);
+int filter_query(fdb_index *ix, const float *d_q, size_t nq, size_t k, size_t nprobe, uint32_t *d_p,
+                 uint32_t *d_v, float *d_d, uint32_t *d_c, EventLog *log, const uint32_t **d_fb_list,
+                 unsigned *h_nfb);
+
+}  // namespace fdb

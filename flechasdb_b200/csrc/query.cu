@@ -20,208 +20,13 @@
 #include <cstdlib>
 #include <memory>
 
-struct fdb_index {
-    fdb_ctx *ctx = nullptr;
-    size_t N = 0, P = 0, D = 0, C = 0, s = 0, M = 0;
-    fdb::DevBuf<float> coarse, codebooks;
-    fdb::DevBuf<uint8_t> codes;
-    fdb::DevBuf<uint32_t> part_off;    // [P+1] vectors before partition p
-    fdb::DevBuf<uint64_t> part_cstart; // [P] byte offset of the partition's code list
-    fdb::DevBuf<uint32_t> order;       // [M] global vector index at each partition-major position
-    std::vector<uint32_t> h_off;
-    std::vector<uint64_t> h_cstart;
-    // scratch
-    fdb::DevBuf<float> q_dev, dist, loc, tables, part_d, out_d, probe_d;
-    fdb::DevBuf<uint32_t> probes, part_v, part_cnt, out_p, out_v, out_c;
-    std::vector<cudaEvent_t> events;
-    float phase_ms[6] = {0, 0, 0, 0, 0, 0};
-    uint64_t scan_bytes = 0;
-    size_t last_npairs = 0;
-    bool timing = false;
-    size_t chunk_pairs = 8192;
-};
+#include "index.cuh"
+#include "nbest.cuh"
+
 
 namespace fdb {
 namespace {
 
-constexpr float INF = __builtin_huge_valf();
-
-__device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, off));
-    return v;
-}
-
-// ---- NBestByKey::push (src/nbest.rs:52-64), executed by one warp ---------------------
-// slots live in shared memory in the reference's slot order.  `maxd` caches the largest
-// key so that candidates that beat no slot are rejected without touching the slots
-// (exactly the candidates for which the reference's `find` returns None).
-struct WarpNBest {
-    float *d;
-    uint32_t *a;
-    int n, len;
-    float maxd;
-    __device__ void init(float *dd, uint32_t *aa, int nn) {
-        d = dd;
-        a = aa;
-        n = nn;
-        len = 0;
-        maxd = -INF;
-    }
-    __device__ void refresh_max(int lane) {
-        float m = -INF;
-        for (int s = lane; s < len; s += 32) m = fmaxf(m, d[s]);  // fmaxf drops NaN like `<` does
-        maxd = warp_max(m);
-    }
-    // all lanes call with the same candidate
-    __device__ void push(float cd, uint32_t ca, int lane) {
-        if (len < n) {
-            if (lane == 0) {
-                d[len] = cd;
-                a[len] = ca;
-            }
-            len++;
-            __syncwarp();
-            if (len == n) refresh_max(lane);
-            return;
-        }
-        if (!(cd < maxd)) return;
-        for (;;) {
-            int found = -1;
-            for (int base = 0; base < n; base += 32) {
-                const int s = base + lane;
-                const unsigned bal = __ballot_sync(0xffffffffu, s < n && cd < d[s]);
-                if (bal) {
-                    found = base + __ffs(bal) - 1;
-                    break;
-                }
-            }
-            if (found < 0) break;
-            const float od = d[found];
-            const uint32_t oa = a[found];
-            __syncwarp();
-            if (lane == 0) {
-                d[found] = cd;
-                a[found] = ca;
-            }
-            __syncwarp();
-            cd = od;
-            ca = oa;
-        }
-        refresh_max(lane);
-    }
-    // slice::sort_by(partial_cmp) on the slots: stable, so ties keep slot order.
-    // rank sort into (od, oa).
-    __device__ void sorted_out(float *od, uint32_t *oa, int lane) const {
-        // a NaN key makes the reference panic (partial_cmp().unwrap()); the caller raises
-        // FLAG_NAN, here the slots are just copied so that every output entry is defined
-        bool nan = false;
-        for (int i = lane; i < len; i += 32) nan |= d[i] != d[i];
-        if (__any_sync(0xffffffffu, nan)) {
-            for (int i = lane; i < len; i += 32) {
-                od[i] = d[i];
-                oa[i] = a[i];
-            }
-            return;
-        }
-        for (int i = lane; i < len; i += 32) {
-            const float di = d[i];
-            int rank = 0;
-            for (int j = 0; j < len; ++j) {
-                const float dj = d[j];
-                rank += (dj < di) || (dj == di && j < i);
-            }
-            od[rank] = di;
-            oa[rank] = a[i];
-        }
-    }
-};
-
-// ---- "stable sort then truncate" (src/db/build.rs:334-337,370-371), by one warp -------
-// slots stay sorted; a candidate goes after every slot with key <= its key.
-struct WarpSorted {
-    float *d;
-    uint32_t *a;
-    int n, len;
-    __device__ void init(float *dd, uint32_t *aa, int nn) {
-        d = dd;
-        a = aa;
-        n = nn;
-        len = 0;
-    }
-    __device__ void push(float cd, uint32_t ca, int lane) {
-        if (len == n && !(cd < d[n - 1])) return;
-        int pos = len;
-        for (int base = 0; base < len; base += 32) {
-            const int s = base + lane;
-            const unsigned bal = __ballot_sync(0xffffffffu, s < len && cd < d[s]);
-            if (bal) {
-                pos = base + __ffs(bal) - 1;
-                break;
-            }
-        }
-        const int last = len < n ? len : n - 1;  // index that receives the shifted tail end
-        // shift [pos, last) right by one, highest first, 32 at a time
-        for (int hi = last; hi > pos;) {
-            const int lo = max(pos, hi - 32);
-            const int s = lo + lane;  // source index, moves to s+1
-            float td = 0.f;
-            uint32_t ta = 0;
-            const bool act = s < hi;
-            if (act) {
-                td = d[s];
-                ta = a[s];
-            }
-            __syncwarp();
-            if (act) {
-                d[s + 1] = td;
-                a[s + 1] = ta;
-            }
-            __syncwarp();
-            hi = lo;
-        }
-        if (lane == 0) {
-            d[pos] = cd;
-            a[pos] = ca;
-        }
-        if (len < n) len++;
-        __syncwarp();
-    }
-};
-
-// feed `cnt` keys (lane-parallel readable through key(i)) in index order
-template <typename KeyFn>
-__device__ void feed_nbest(WarpNBest &nb, int cnt, uint32_t payload0, KeyFn key, int lane) {
-    int i = 0;
-    for (; i < cnt && nb.len < nb.n; ++i) nb.push(key(i), payload0 + i, lane);  // fill phase
-    for (int base = i; base < cnt; base += 32) {
-        const int v = base + lane;
-        const float dv = v < cnt ? key(v) : INF;
-        unsigned bal = __ballot_sync(0xffffffffu, v < cnt && dv < nb.maxd);
-        while (bal) {
-            const int L = __ffs(bal) - 1;
-            bal &= bal - 1;
-            const float cd = __shfl_sync(0xffffffffu, dv, L);
-            nb.push(cd, payload0 + base + L, lane);
-        }
-    }
-}
-template <typename KeyFn>
-__device__ void feed_sorted(WarpSorted &sl, int cnt, uint32_t payload0, KeyFn key, int lane) {
-    int i = 0;
-    for (; i < cnt && sl.len < sl.n; ++i) sl.push(key(i), payload0 + i, lane);
-    for (int base = i; base < cnt; base += 32) {
-        const int v = base + lane;
-        const float dv = v < cnt ? key(v) : INF;
-        unsigned bal = __ballot_sync(0xffffffffu, v < cnt && dv < sl.d[sl.n - 1]);
-        while (bal) {
-            const int L = __ffs(bal) - 1;
-            bal &= bal - 1;
-            const float cd = __shfl_sync(0xffffffffu, dv, L);
-            sl.push(cd, payload0 + base + L, lane);
-        }
-    }
-}
 
 // ---- 2: probe selection (src/db/stored.rs:411-426 / src/db/build.rs:357-371) -----------
 constexpr int PROBE_WARPS = 4;
@@ -378,129 +183,6 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(ScanParams p) {
     }
 }
 
-// ---- register-resident variants for n <= 32: lane s holds slot s --------------------------
-struct RegNBest {
-    float d;
-    uint32_t a;
-    int n, len;
-    float maxd;
-    __device__ void init(int nn) {
-        d = 0.f;
-        a = 0;
-        n = nn;
-        len = 0;
-        maxd = -INF;
-    }
-    __device__ void refresh_max(int lane) { maxd = warp_max(lane < len ? d : -INF); }
-    __device__ void push(float cd, uint32_t ca, int lane) {
-        if (len < n) {
-            if (lane == len) {
-                d = cd;
-                a = ca;
-            }
-            len++;
-            if (len == n) refresh_max(lane);
-            return;
-        }
-        if (!(cd < maxd)) return;
-        for (;;) {
-            const unsigned bal = __ballot_sync(0xffffffffu, lane < n && cd < d);
-            if (!bal) break;
-            const int f = __ffs(bal) - 1;
-            const float od = __shfl_sync(0xffffffffu, d, f);
-            const uint32_t oa = __shfl_sync(0xffffffffu, a, f);
-            if (lane == f) {
-                d = cd;
-                a = ca;
-            }
-            cd = od;
-            ca = oa;
-        }
-        refresh_max(lane);
-    }
-    // stable sort by key; result in lane order
-    __device__ void sort(int lane) {
-        const bool mine = lane < len;
-        const bool nan = __any_sync(0xffffffffu, mine && d != d);
-        if (nan) return;  // the caller raises FLAG_NAN
-        int rank = 0;
-        for (int j = 0; j < len; ++j) {
-            const float dj = __shfl_sync(0xffffffffu, d, j);
-            rank += (dj < d) || (dj == d && j < lane);
-        }
-        // scatter lane -> rank: every lane r fetches from the lane whose rank is r
-        int src = 0;
-        for (int j = 0; j < len; ++j) {
-            const int rj = __shfl_sync(0xffffffffu, rank, j);
-            if (rj == lane) src = j;
-        }
-        const float nd = __shfl_sync(0xffffffffu, d, src);
-        const uint32_t na = __shfl_sync(0xffffffffu, a, src);
-        if (mine) {
-            d = nd;
-            a = na;
-        }
-    }
-};
-
-struct RegSorted {
-    float d;
-    uint32_t a;
-    int n, len;
-    float last;  // key of slot n-1 once full
-    __device__ void init(int nn) {
-        d = 0.f;
-        a = 0;
-        n = nn;
-        len = 0;
-        last = INF;
-    }
-    __device__ void push(float cd, uint32_t ca, int lane) {
-        if (len == n && !(cd < last)) return;
-        const unsigned bal = __ballot_sync(0xffffffffu, lane < len && cd < d);
-        const int pos = bal ? __ffs(bal) - 1 : len;
-        const float ud = __shfl_up_sync(0xffffffffu, d, 1);
-        const uint32_t ua = __shfl_up_sync(0xffffffffu, a, 1);
-        if (lane > pos && lane < n) {
-            d = ud;
-            a = ua;
-        }
-        if (lane == pos) {
-            d = cd;
-            a = ca;
-        }
-        if (len < n) len++;
-        if (len == n) last = __shfl_sync(0xffffffffu, d, n - 1);
-    }
-};
-
-// feed one group of up to 32 keys (lane-held) in lane order
-__device__ __forceinline__ void feed_group(RegNBest &nb, float dv, bool valid, uint32_t payload0, int lane) {
-    unsigned bal = __ballot_sync(0xffffffffu, valid && (nb.len < nb.n || dv < nb.maxd));
-    while (bal) {
-        const int L = __ffs(bal) - 1;
-        bal &= bal - 1;
-        nb.push(__shfl_sync(0xffffffffu, dv, L), payload0 + L, lane);
-    }
-}
-__device__ __forceinline__ void feed_group(RegSorted &sl, float dv, bool valid, uint32_t payload0, int lane) {
-    unsigned bal = __ballot_sync(0xffffffffu, valid && (sl.len < sl.n || dv < sl.last));
-    while (bal) {
-        const int L = __ffs(bal) - 1;
-        bal &= bal - 1;
-        sl.push(__shfl_sync(0xffffffffu, dv, L), payload0 + L, lane);
-    }
-}
-
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
-    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int NWAIT>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;\n" ::"n"(NWAIT));
-}
 
 // ---- 5 (fast path): one warp per (query, partition) pair, k <= 32 ------------------------
 // The warp keeps the pair's ADC table in shared memory, streams the partition's code list
@@ -640,6 +322,26 @@ __global__ void __launch_bounds__(MERGE_WARPS * 32) merge_kernel(
     if (nan && len > 1) atomicOr(flags, FLAG_NAN);
 }
 
+// ---- hand-over of undecided queries between the filter path and the exact pipeline ------
+__global__ void gather_rows_kernel(const float *q, const uint32_t *list, size_t n, size_t N, float *out) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * N) return;
+    const size_t r = t / N, e = t - r * N;
+    out[t] = q[(size_t)list[r] * N + e];
+}
+__global__ void scatter_results_kernel(const uint32_t *list, size_t n, size_t k, const uint32_t *fp,
+                                       const uint32_t *fv, const float *fd, const uint32_t *fc,
+                                       uint32_t *d_p, uint32_t *d_v, float *d_d, uint32_t *d_c) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * k) return;
+    const size_t r = t / k, e = t - r * k;
+    const size_t q = list[r];
+    d_p[q * k + e] = fp[t];
+    d_v[q * k + e] = fv[t];
+    d_d[q * k + e] = fd[t];
+    if (e == 0) d_c[q] = fc[r];
+}
+
 // ---- Partition::new on the device (src/db/build.rs:459-473) ----------------------------
 __global__ void gather_codes_kernel(const uint32_t *order, const uint32_t *coarse_idx,
                                     const uint32_t *pq_idx, const uint32_t *part_off,
@@ -743,6 +445,7 @@ int fdb_index_create(fdb_ctx *ctx, size_t N, size_t P, size_t D, size_t C, const
                                      cudaMemcpyHostToDevice, st));
     }
     FDB_CUDA(cudaStreamSynchronize(st));
+    FDB_TRY(filter_prepare(ix.get()));
     *out = ix.release();
     return FDB_OK;
 }
@@ -781,6 +484,7 @@ int fdb_index_from_build(fdb_ctx *ctx, const fdb_km *coarse, const fdb_km *pq, f
         FDB_CHECK_LAUNCH();
     }
     FDB_CUDA(cudaStreamSynchronize(st));
+    FDB_TRY(filter_prepare(ix.get()));
     *out = ix.release();
     return FDB_OK;
 }
@@ -813,41 +517,13 @@ void fdb_index_destroy(fdb_index *ix) {
     cudaSetDevice(ix->ctx->device);
     cudaStreamSynchronize(ix->ctx->stream);
     for (cudaEvent_t e : ix->events) cudaEventDestroy(e);
+    filter_free(ix);
     delete ix;
 }
 
 }  // extern "C"
 
 namespace {
-
-struct EventLog {
-    fdb_index *ix;
-    size_t used = 0;
-    std::vector<std::pair<int, size_t>> marks;  // (phase, index of the start event)
-    int mark(int phase) {                        // records start; end = next event
-        if (!ix->timing) return FDB_OK;
-        if (used == ix->events.size()) {
-            cudaEvent_t e;
-            FDB_CUDA(cudaEventCreate(&e));
-            ix->events.push_back(e);
-        }
-        FDB_CUDA(cudaEventRecord(ix->events[used], ix->ctx->stream));
-        marks.emplace_back(phase, used);
-        used++;
-        return FDB_OK;
-    }
-    int finish() {
-        for (int i = 0; i < 6; ++i) ix->phase_ms[i] = 0.f;
-        if (!ix->timing) return FDB_OK;
-        for (size_t i = 0; i + 1 < marks.size(); ++i) {
-            if (marks[i].first < 0) continue;
-            float ms = 0.f;
-            FDB_CUDA(cudaEventElapsedTime(&ms, ix->events[marks[i].second], ix->events[marks[i + 1].second]));
-            ix->phase_ms[marks[i].first] += ms;
-        }
-        return FDB_OK;
-    }
-};
 
 int probe_device(fdb_index *ix, const float *d_q, size_t nq, size_t nprobe, int mode, EventLog *log) {
     fdb_ctx *ctx = ix->ctx;
@@ -888,13 +564,10 @@ int check_query_args(fdb_index *ix, size_t nq, size_t k, size_t nprobe, int mode
     return FDB_OK;
 }
 
-int query_device(fdb_index *ix, const float *d_q, size_t nq, size_t k, size_t nprobe, int mode,
-                 uint32_t *d_p, uint32_t *d_v, float *d_d, uint32_t *d_c) {
+// steps 3-6 of the exact pipeline for queries whose probes are already in ix->probes
+int exact_after_probe(fdb_index *ix, const float *d_q, size_t nq, size_t k, size_t nprobe, int mode,
+                      uint32_t *d_p, uint32_t *d_v, float *d_d, uint32_t *d_c, EventLog &log) {
     fdb_ctx *ctx = ix->ctx;
-    EventLog log{ix};
-    ix->scan_bytes = 0;
-    if (nq == 0) return FDB_OK;
-    FDB_TRY(probe_device(ix, d_q, nq, nprobe, mode, &log));
     const size_t npairs = nq * nprobe;
     const size_t DC = ix->D * ix->C;
     const size_t chunk = std::min(npairs, ix->chunk_pairs);
@@ -979,8 +652,50 @@ int query_device(fdb_index *ix, const float *d_q, size_t nq, size_t k, size_t np
         d_v, d_d, d_c, ctx->d_flags);
     ctx->launches++;
     FDB_CHECK_LAUNCH();
+    return FDB_OK;
+}
+
+// The whole query.  Shapes the ADC filter path accepts go through it (adc_filter.cu); the
+// queries it cannot decide (exact ties, NaN, overfull band) and every other shape take the
+// exact pipeline, which reproduces the reference's selection slot by slot.
+int query_device(fdb_index *ix, const float *d_q, size_t nq, size_t k, size_t nprobe, int mode,
+                 uint32_t *d_p, uint32_t *d_v, float *d_d, uint32_t *d_c) {
+    fdb_ctx *ctx = ix->ctx;
+    EventLog log{ix};
+    ix->scan_bytes = 0;
+    ix->last_filter = false;
+    for (int i = 0; i < 4; ++i) ix->last_stats[i] = 0;
+    if (nq == 0) return FDB_OK;
+    FDB_TRY(probe_device(ix, d_q, nq, nprobe, mode, &log));
+    if (filter_eligible(ix, nq, k, nprobe)) {
+        const uint32_t *d_fb = nullptr;
+        unsigned nfb = 0;
+        FDB_TRY(filter_query(ix, d_q, nq, k, nprobe, d_p, d_v, d_d, d_c, &log, &d_fb, &nfb));
+        ix->last_filter = true;
+        if (nfb) {
+            cudaStream_t st = ctx->stream;
+            FDB_TRY(ix->fb_q.ensure((size_t)nfb * ix->N));
+            FDB_TRY(ix->fb_p.ensure((size_t)nfb * k));
+            FDB_TRY(ix->fb_v.ensure((size_t)nfb * k));
+            FDB_TRY(ix->fb_d.ensure((size_t)nfb * k));
+            FDB_TRY(ix->fb_c.ensure(nfb));
+            gather_rows_kernel<<<(unsigned)(((size_t)nfb * ix->N + 255) / 256), 256, 0, st>>>(d_q, d_fb, nfb, ix->N,
+                                                                                            ix->fb_q.p);
+            ctx->launches++;
+            FDB_TRY(probe_device(ix, ix->fb_q.p, nfb, nprobe, mode, &log));
+            FDB_TRY(exact_after_probe(ix, ix->fb_q.p, nfb, k, nprobe, mode, ix->fb_p.p, ix->fb_v.p, ix->fb_d.p,
+                                      ix->fb_c.p, log));
+            scatter_results_kernel<<<(unsigned)(((size_t)nfb * k + 255) / 256), 256, 0, st>>>(
+                d_fb, nfb, k, ix->fb_p.p, ix->fb_v.p, ix->fb_d.p, ix->fb_c.p, d_p, d_v, d_d, d_c);
+            ctx->launches++;
+            FDB_CHECK_LAUNCH();
+        }
+    } else {
+        FDB_TRY(exact_after_probe(ix, d_q, nq, k, nprobe, mode, d_p, d_v, d_d, d_c, log));
+        ix->last_npairs = nq * nprobe;
+        ix->last_stats[1] = nq;
+    }
     FDB_TRY(log.mark(-1));
-    ix->last_npairs = npairs;
     if (ix->timing) {
         FDB_CUDA(cudaStreamSynchronize(ctx->stream));
         FDB_TRY(log.finish());
@@ -1083,6 +798,12 @@ int fdb_index_table(fdb_index *ix, const float *query, uint32_t partition, float
     return finish_query(ctx);
 }
 
+int fdb_index_last_stats(fdb_index *ix, uint64_t out[4]) {
+    ARG(ix && out, "null argument");
+    for (int i = 0; i < 4; ++i) out[i] = ix->last_stats[i];
+    return FDB_OK;
+}
+
 int fdb_index_set_timing(fdb_index *ix, int enabled) {
     ARG(ix, "ix is null");
     ix->timing = enabled != 0;
@@ -1097,6 +818,11 @@ int fdb_index_last_timing(fdb_index *ix, float ms[6], uint64_t *scan_bytes) {
         // (SURVEY.md section 8d); read back lazily so that the query itself never waits on it
         fdb_ctx *ctx = ix->ctx;
         FDB_TRY(ctx->use());
+        if (ix->last_filter) {  // counted by the scan kernel itself (the fallbacks' lists are not included)
+            ix->scan_bytes = ix->last_stats[3] * ix->D;
+            *scan_bytes = ix->scan_bytes;
+            return FDB_OK;
+        }
         std::vector<uint32_t> hp(ix->last_npairs);
         if (!hp.empty()) {
             FDB_CUDA(cudaMemcpyAsync(hp.data(), ix->probes.p, hp.size() * sizeof(uint32_t),

@@ -289,6 +289,13 @@ class Index:
         check(capi.lib().fdb_index_last_timing(self.h, f32p(ms), C.byref(b)))
         return ms, int(b.value)
 
+    def last_stats(self):
+        """(queries on the ADC filter path, queries on the exact pipeline, candidates evaluated
+        exactly, code vectors scanned) of the last query call."""
+        st = np.zeros(4, np.uint64)
+        check(capi.lib().fdb_index_last_stats(self.h, u64p(st)))
+        return tuple(int(x) for x in st)
+
     def close(self):
         if self.h:
             capi.lib().fdb_index_destroy(self.h)

@@ -191,6 +191,12 @@ int fdb_index_set_timing(fdb_index *ix, int enabled);
  * [0] coarse distances, [1] probe selection, [2] localise, [3] ADC tables,
  * [4] code scan + per-partition n-best, [5] merge; and the algorithmic scan bytes */
 int fdb_index_last_timing(fdb_index *ix, float ms[6], uint64_t *scan_bytes);
+/* how the last fdb_index_query* call was answered: [0] queries decided by the ADC filter
+ * path (approximate tables + exact re-check of the candidates inside the error band),
+ * [1] queries answered by the exact pipeline (ties, NaN, shapes the filter does not take),
+ * [2] candidates the filter path evaluated exactly, [3] code vectors it scanned.
+ * Results are identical on both paths; FDB_QUERY_EXACT=1 in the environment forces [1]. */
+int fdb_index_last_stats(fdb_index *ix, uint64_t out[4]);
 
 /* raw device buffers for benches that keep inputs resident */
 int fdb_device_alloc(fdb_ctx *ctx, size_t bytes, void **out);

@@ -383,6 +383,93 @@ def test_query_errors(eng, ctx, oracle):
     assert e.value.code == capi.ERR_UNSUPPORTED
 
 
+# ---- ADC filter path (adc_filter.cu): same answers as the exact pipeline and the oracle --------
+def _check_query(ix, oix, q, k, nprobe, mode):
+    part, vidx, dist, cnt = ix.query(q, k, nprobe, mode)
+    rc, wp, wv, wd, wc = oix.query(q, k, nprobe, mode)
+    assert rc == 0
+    assert (cnt == wc).all()
+    for qi in range(len(q)):
+        c = cnt[qi]
+        assert (part[qi, :c] == wp[qi, :c]).all(), (mode, qi)
+        assert (vidx[qi, :c] == wv[qi, :c]).all(), (mode, qi)
+        assert (dist[qi, :c] == wd[qi, :c]).all(), (mode, qi)
+    return ix.last_stats()
+
+
+@pytest.mark.parametrize("N,P,D,Cn,M,k,nprobe,nq", [
+    (1536, 100, 12, 256, 20000, 10, 5, 256),   # the README shape: GEMM tables + scan + re-check
+    (96, 64, 12, 256, 30000, 10, 8, 256),      # s = 8: dot_naive order in the re-check
+    (120, 20, 5, 17, 3000, 7, 20, 128),        # odd D and C, s = 24 (remainder rule), nprobe == P
+    (80, 12, 4, 100, 900, 24, 3, 128),         # largest k the filter takes, lists barely above k
+    (64, 9, 4, 256, 60, 5, 9, 64),             # fewer vectors than the candidate list holds
+    (36, 30, 3, 33, 5000, 1, 4, 128),          # k = 1, s = 12 < 16, unaligned C
+])
+def test_filter_path_bit_exact(eng, ctx, oracle, N, P, D, Cn, M, k, nprobe, nq):
+    coarse, cbs, off, codes = random_index(oracle, N, P, D, Cn, M, empty=(1,))
+    ix = eng.Index.create(ctx, coarse, cbs, off, codes.astype(np.uint8))
+    oix = oracle.QueryIndex(coarse, cbs, off, codes)
+    q = data(oracle, nq, N, SEED + 79)
+    for mode in (0, 1):
+        fast, exact, cand, scanned = _check_query(ix, oix, q, k, nprobe, mode)
+        assert fast + exact == nq
+        assert fast >= 0.9 * nq, (fast, exact)     # the filter decides almost every query itself
+        assert cand <= 2 * (k + 1) * fast          # and re-checks about k+1 candidates per query
+    ix.close()
+
+
+def test_filter_path_equals_exact_pipeline_on_a_large_batch(eng, ctx, oracle, monkeypatch):
+    """4096 queries against the README shape: ids, distances and counts of the filter path equal
+    the exact pipeline's bit for bit (the oracle is too slow for this many; it checks a sample)."""
+    N, P, D, Cn, M, k, nprobe, nq = 1536, 100, 12, 256, 50000, 10, 5, 4096
+    coarse, cbs, off, codes = random_index(oracle, N, P, D, Cn, M)
+    ix = eng.Index.create(ctx, coarse, cbs, off, codes.astype(np.uint8))
+    q = data(oracle, nq, N, SEED + 80)
+    got = ix.query(q, k, nprobe)
+    fast, exact, cand, scanned = ix.last_stats()
+    assert fast >= 0.99 * nq
+    monkeypatch.setenv("FDB_QUERY_EXACT", "1")
+    want = ix.query(q, k, nprobe)
+    assert ix.last_stats()[0] == 0 and ix.last_stats()[1] == nq
+    monkeypatch.delenv("FDB_QUERY_EXACT")
+    for g, w in zip(got, want):
+        assert (g == w).all()
+    oix = oracle.QueryIndex(coarse, cbs, off, codes)
+    rc, wp, wv, wd, wc = oix.query(q[:64], k, nprobe, 0)
+    assert (got[0][:64] == wp).all() and (got[1][:64] == wv).all() and (got[2][:64] == wd).all()
+    ix.close()
+
+
+def test_filter_path_hands_ties_and_bad_numbers_to_the_exact_pipeline(eng, ctx, oracle):
+    # (a) duplicated code vectors: every distance is shared by many vectors -> NBestByKey history
+    N, P, D, Cn, M = 64, 8, 4, 64, 3000
+    coarse, cbs, off, codes = random_index(oracle, N, P, D, Cn, M, dup=True)
+    ix = eng.Index.create(ctx, coarse, cbs, off, codes.astype(np.uint8))
+    oix = oracle.QueryIndex(coarse, cbs, off, codes)
+    q = data(oracle, 64, N, SEED + 81)
+    for mode in (0, 1):
+        fast, exact, _, _ = _check_query(ix, oix, q, 6, 4, mode)
+        assert exact == 64 and fast == 0
+    ix.close()
+    # (b) large offsets: |q|, |c| ~ 3000 while distances stay ~ N/6 -> wide band, still exact
+    coarse, cbs, off, codes = random_index(oracle, N, P, D, Cn, M)
+    coarse = (coarse + np.float32(3000.0)).astype(np.float32)
+    ix = eng.Index.create(ctx, coarse, cbs, off, codes.astype(np.uint8))
+    oix = oracle.QueryIndex(coarse, cbs, off, codes)
+    qb = (q + np.float32(3000.0)).astype(np.float32)
+    for mode in (0, 1):
+        fast, exact, _, _ = _check_query(ix, oix, qb, 6, 4, mode)
+        assert fast + exact == 64
+    ix.close()
+    # (c) an infinite code vector disables the filter for the whole index
+    cb2 = cbs.copy()
+    cb2[1, 3, 0] = np.inf
+    ix = eng.Index.create(ctx, coarse, cb2, off, codes.astype(np.uint8))
+    ix.query(q[:4], 3, 2)
+    assert ix.last_stats()[0] == 0
+    ix.close()
+
+
 # ---- the committed golden fixture, without the oracle at run time ---------------------------
 def test_golden_fixture(eng, ctx):
     import os
