@@ -14,12 +14,12 @@
 //      per warp, merged per CTA).
 //   3. band.  |A(v) - D(v)| <= E_q for the real-valued D(v) and |R(v) - D(v)| <= eta D(v) for
 //      the reference's f32 value R(v) (bounds below), so every vector that can be among the
-//      reference's k+1 smallest has A(v) <= tau' = (a_(k+1) + E)(1+eta)/(1-eta) + E; the band
-//      is doubled for safety.  If the 32-entry list does not provably contain all of them the
+//      reference's k smallest (or tied with the k-th) has A(v) <= tau' = (a_(k) + E)(1+eta)/(1-eta) + E; the band
+//      is doubled for safety.  If the (k+6)-entry list does not provably contain all of them the
 //      query goes to the exact pipeline.
-//   4. exact re-check.  The candidates (typically k+1) are evaluated in the reference's order
+//   4. exact re-check.  The candidates (typically k) are evaluated in the reference's order
 //      of operations (fl(fl(q - c_p) - cb), 16-lane dot, sequential sum over divisions); the k
-//      smallest are the reference's result when the k+1 smallest are pairwise distinct.
+//      smallest are the reference's result when none of them is exactly tied with another candidate.
 //      Exact ties (which NBestByKey, src/nbest.rs:52-64, resolves by push history), NaN and
 //      non-finite tables also go to the exact pipeline, which reproduces them slot by slot.
 //
@@ -60,7 +60,7 @@ struct FilterState {
 namespace {
 
 constexpr int RCAP = 32;        // approximate candidates kept per query
-constexpr int KMAX_FILTER = 24; // k + 1 <= 25 leaves >= 7 slots of head room
+constexpr int KMAX_FILTER = 26; // list capacity min(32, k + 6): k plus head room for the band
 constexpr float U24 = 5.9604645e-08f;
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(G_THREADS, 2) adc_gemm_kernel(const float *__r
     }
 }
 
-// ---- scan: the 32 smallest approximate distances of a query --------------------------------
+// ---- scan: the ncap smallest approximate distances of a query -------------------------------
 struct FScanParams {
     const float *G;             // [queries of this chunk][D*C]
     const float *pc;            // [P][D*C]
@@ -279,8 +279,8 @@ struct FScanParams {
     const uint64_t *part_cstart;
     const uint32_t *probes;     // [nq][nprobe]
     size_t q0;
-    int nprobe, D, C, chunk_vecs;
-    float *cand_d;              // [nq][RCAP] ascending
+    int nprobe, D, C, chunk_vecs, ncap, use_gs;
+    float *cand_d;              // [nq][RCAP] ascending, ncap <= RCAP used
     uint32_t *cand_a;           // position in the concatenation of the probed lists
     uint32_t *cand_cnt, *cand_total;
     unsigned *qbad;
@@ -288,9 +288,10 @@ struct FScanParams {
 };
 
 constexpr int FS_WARPS = 4;
+constexpr int TSTRIDE = 256;    // table row stride in shared memory: offsets become immediates
 
-__device__ __forceinline__ void push_lanes(RegSorted &sel, float dv, uint32_t av, bool valid, int lane) {
-    unsigned bal = __ballot_sync(0xffffffffu, valid && (sel.len < sel.n || dv < sel.last));
+__device__ __forceinline__ void push_lanes(RegSorted &sel, float dv, uint32_t av, bool want, int lane) {
+    unsigned bal = __ballot_sync(0xffffffffu, want);
     while (bal) {
         const int L = __ffs(bal) - 1;
         bal &= bal - 1;
@@ -298,32 +299,60 @@ __device__ __forceinline__ void push_lanes(RegSorted &sel, float dv, uint32_t av
     }
 }
 
+// sum of the D table entries of code vector v; W = D / 4 code words (0: any D, byte by byte)
+template <int W>
+__device__ __forceinline__ float adc_sum(const unsigned char *cs, int v, const float *Ts, int D) {
+    if (W > 0) {
+        const uint32_t *cw = reinterpret_cast<const uint32_t *>(cs) + v * W;
+        float a0 = 0.0f, a1 = 0.0f;
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            const uint32_t x = cw[w];
+            const float *t = Ts + w * 4 * TSTRIDE;
+            a0 += t[x & 255u];
+            a1 += t[TSTRIDE + ((x >> 8) & 255u)];
+            a0 += t[2 * TSTRIDE + ((x >> 16) & 255u)];
+            a1 += t[3 * TSTRIDE + (x >> 24)];
+        }
+        return a0 + a1;
+    }
+    float acc = 0.0f;
+    for (int di = 0; di < D; ++di) acc += Ts[di * TSTRIDE + cs[(size_t)v * D + di]];
+    return acc;
+}
+
+template <int W>
 __global__ void __launch_bounds__(FS_WARPS * 32) fscan_kernel(FScanParams p) {
     extern __shared__ __align__(16) unsigned char sm[];
+    __shared__ int thr_s;       // bits of the smallest "worst kept" value over the warps' full lists
+    __shared__ float md[FS_WARPS * RCAP];
+    __shared__ uint32_t ma[FS_WARPS * RCAP];
+    __shared__ int mlen[FS_WARPS];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int D = p.D, C = p.C;
     const int DC = D * C;
-    const int DCp = (DC + 3) & ~3;
-    float *Gs = reinterpret_cast<float *>(sm);
-    float *Ts = Gs + DCp;
-    const size_t chunk_bytes = (size_t)p.chunk_vecs * D;  // multiple of 16 (chunk_vecs % 32 == 0)
-    unsigned char *cbuf = reinterpret_cast<unsigned char *>(Ts + DCp) + (size_t)warp * 2 * chunk_bytes;
-    float *md = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(Ts + DCp) +
-                                          (size_t)FS_WARPS * 2 * chunk_bytes);
-    uint32_t *ma = reinterpret_cast<uint32_t *>(md + FS_WARPS * RCAP);
-    int *mlen = reinterpret_cast<int *>(ma + FS_WARPS * RCAP);
+    float *Ts = reinterpret_cast<float *>(sm);                       // [D][TSTRIDE]
+    const size_t chunk_bytes = (size_t)p.chunk_vecs * D;             // multiple of 16 (chunk_vecs % 32 == 0)
+    unsigned char *cbuf = reinterpret_cast<unsigned char *>(Ts + (size_t)D * TSTRIDE) + (size_t)warp * 2 * chunk_bytes;
+    float *Gs = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(Ts + (size_t)D * TSTRIDE) +
+                                          (size_t)FS_WARPS * 2 * chunk_bytes);  // [D*C] when use_gs
 
     const size_t q = p.q0 + blockIdx.x;
     const float *gq = p.G + (size_t)blockIdx.x * DC;
-    if ((DC & 3) == 0) {
-        for (int i = tid; i < DC / 4; i += FS_WARPS * 32)
-            reinterpret_cast<float4 *>(Gs)[i] = reinterpret_cast<const float4 *>(gq)[i];
-    } else {
-        for (int i = tid; i < DC; i += FS_WARPS * 32) Gs[i] = gq[i];
+    const bool vec4 = (C & 3) == 0;
+    if (p.use_gs) {
+        if (vec4) {
+            for (int i = tid; i < DC / 4; i += FS_WARPS * 32)
+                reinterpret_cast<float4 *>(Gs)[i] = reinterpret_cast<const float4 *>(gq)[i];
+        } else {
+            for (int i = tid; i < DC; i += FS_WARPS * 32) Gs[i] = gq[i];
+        }
+        gq = Gs;
     }
+    if (tid == 0) thr_s = 0x7f800000;
 
     RegSorted sel;
-    sel.init(RCAP);
+    sel.init(p.ncap);
     bool bad = false;
     uint32_t flat0 = 0;
     for (int pr = 0; pr < p.nprobe; ++pr) {
@@ -331,24 +360,6 @@ __global__ void __launch_bounds__(FS_WARPS * 32) fscan_kernel(FScanParams p) {
         const int np = (int)(p.part_off[part + 1] - p.part_off[part]);
         const float K = p.Kq[q * p.nprobe + pr];
         bad |= !(fabsf(K) < 1e30f);
-        __syncthreads();  // the previous list is fully scanned (first round: Gs is complete)
-        const float *pcp = p.pc + (size_t)part * DC;
-        if ((DC & 3) == 0) {
-            for (int i = tid; i < DC / 4; i += FS_WARPS * 32) {
-                const float4 g = reinterpret_cast<const float4 *>(Gs)[i];
-                const float4 c = __ldg(reinterpret_cast<const float4 *>(pcp) + i);
-                const float4 t = make_float4(g.x + c.x, g.y + c.y, g.z + c.z, g.w + c.w);
-                bad |= !(fabsf(t.x) < 1e30f) | !(fabsf(t.y) < 1e30f) | !(fabsf(t.z) < 1e30f) | !(fabsf(t.w) < 1e30f);
-                reinterpret_cast<float4 *>(Ts)[i] = t;
-            }
-        } else {
-            for (int i = tid; i < DC; i += FS_WARPS * 32) {
-                const float t = Gs[i] + __ldg(pcp + i);
-                bad |= !(fabsf(t) < 1e30f);
-                Ts[i] = t;
-            }
-        }
-        __syncthreads();
         const uint8_t *cg = p.codes + p.part_cstart[part];
         const int nchunks = (np + p.chunk_vecs - 1) / p.chunk_vecs;
         auto issue = [&](int c, int slot) {
@@ -362,8 +373,28 @@ __global__ void __launch_bounds__(FS_WARPS * 32) fscan_kernel(FScanParams p) {
             }
             cp_async_commit();
         };
+        issue(warp, 0);  // the warp's first chunk travels while the table is assembled
+        __syncthreads();  // the previous list is fully scanned (first round: Gs and thr_s are set)
+        // T = G[q] + PC[p]
+        const float *pcp = p.pc + (size_t)part * DC;
+        if (C == TSTRIDE) {
+            for (int i = tid; i < DC / 4; i += FS_WARPS * 32) {
+                const float4 g = reinterpret_cast<const float4 *>(gq)[i];
+                const float4 c = __ldg(reinterpret_cast<const float4 *>(pcp) + i);
+                const float4 t = make_float4(g.x + c.x, g.y + c.y, g.z + c.z, g.w + c.w);
+                bad |= !(fabsf(t.x) < 1e30f) | !(fabsf(t.y) < 1e30f) | !(fabsf(t.z) < 1e30f) | !(fabsf(t.w) < 1e30f);
+                reinterpret_cast<float4 *>(Ts)[i] = t;
+            }
+        } else {
+            for (int i = tid; i < DC; i += FS_WARPS * 32) {
+                const float t = gq[i] + __ldg(pcp + i);
+                bad |= !(fabsf(t) < 1e30f);
+                const int d = i / C;
+                Ts[d * TSTRIDE + (i - d * C)] = t;
+            }
+        }
+        __syncthreads();
         int slot = 0;
-        issue(warp, 0);
         for (int c = warp; c < nchunks; c += FS_WARPS) {
             issue(c + FS_WARPS, slot ^ 1);
             cp_async_wait<1>();
@@ -374,23 +405,15 @@ __global__ void __launch_bounds__(FS_WARPS * 32) fscan_kernel(FScanParams p) {
             for (int base = 0; base < cnt; base += 32) {
                 const int v = base + lane;
                 const bool valid = v < cnt;
-                float acc = 0.0f;
-                if (valid) {
-                    if ((D & 3) == 0) {
-                        const uint32_t *cw = reinterpret_cast<const uint32_t *>(cs) + (size_t)v * (D >> 2);
-                        for (int w = 0; w < (D >> 2); ++w) {
-                            const uint32_t x = cw[w];
-                            const float *t = Ts + (size_t)(4 * w) * C;
-                            acc += t[x & 255u];
-                            acc += t[C + ((x >> 8) & 255u)];
-                            acc += t[2 * C + ((x >> 16) & 255u)];
-                            acc += t[3 * C + (x >> 24)];
-                        }
-                    } else {
-                        for (int di = 0; di < D; ++di) acc += Ts[(size_t)di * C + cs[(size_t)v * D + di]];
-                    }
+                const float a = valid ? adc_sum<W>(cs, v, Ts, D) + K : 0.0f;
+                // a vector is kept only below this warp's worst kept value and below every other
+                // warp's (a full list elsewhere already holds ncap values <= its worst)
+                const float lim = fminf(sel.last, __int_as_float(*reinterpret_cast<volatile int *>(&thr_s)));
+                const bool want = valid && (a < lim);
+                if (__any_sync(0xffffffffu, want)) {
+                    push_lanes(sel, a, flat0 + (uint32_t)(c0 + v), want, lane);
+                    if (lane == 0 && sel.len == sel.n && sel.last >= 0.0f) atomicMin(&thr_s, __float_as_int(sel.last));
                 }
-                push_lanes(sel, acc + K, flat0 + (uint32_t)(c0 + v), valid, lane);
             }
             __syncwarp();
             slot ^= 1;
@@ -406,8 +429,10 @@ __global__ void __launch_bounds__(FS_WARPS * 32) fscan_kernel(FScanParams p) {
     if (lane == 0) mlen[warp] = sel.len;
     const int anybad = __syncthreads_or(bad ? 1 : 0);
     if (warp != 0) return;
-    for (int w = 1; w < FS_WARPS; ++w)
-        push_lanes(sel, md[w * RCAP + lane], ma[w * RCAP + lane], lane < mlen[w], lane);
+    for (int w = 1; w < FS_WARPS; ++w) {
+        const float dv = md[w * RCAP + lane];
+        push_lanes(sel, dv, ma[w * RCAP + lane], lane < mlen[w] && (sel.len < sel.n || dv < sel.last), lane);
+    }
     if (lane < sel.len) {
         p.cand_d[q * RCAP + lane] = sel.d;
         p.cand_a[q * RCAP + lane] = sel.a;
@@ -433,7 +458,7 @@ struct FSelParams {
     const uint32_t *cand_a, *cand_cnt, *cand_total;
     const unsigned *qbad;
     size_t q0, q1, N, D, C, s;
-    int nprobe, k;
+    int nprobe, k, ncap, quad;
     float coef, eta3;
     uint32_t *out_p, *out_v, *out_c;
     float *out_d;
@@ -463,13 +488,16 @@ __global__ void __launch_bounds__(128) fselect_kernel(FSelParams p) {
     const uint32_t t = lane < cnt ? p.cand_a[q * RCAP + lane] : 0u;
     int ncand = cnt;
     if (cnt > k) {
+        // S = the k smallest approximations; max_S R <= (a_(k) + E)(1 + eta) =: Rmax >= the k-th smallest R,
+        // and every v with R(v) <= Rmax (the reference's k best and anything tied with the k-th) has
+        // A(v) <= Rmax / (1 - eta) + E
         const float E = p.coef * p.Wq[q];
-        const float tau = __shfl_sync(0xffffffffu, a, k);  // the (k+1)-th smallest approximation
+        const float tau = __shfl_sync(0xffffffffu, a, k - 1);
         const float hi = (tau + E) * (1.0f + p.eta3) + E;
         const float thr = tau + 2.0f * (hi - tau);
         if (!(fabsf(thr) < 1e30f)) fb = true;  // NaN or overflow
         ncand = __popc(__ballot_sync(0xffffffffu, lane < cnt && a <= thr));
-        if (ncand == RCAP && total > (uint32_t)RCAP) fb = true;  // the list may be incomplete
+        if (ncand == p.ncap && total > (uint32_t)p.ncap) fb = true;  // the list may be incomplete
     }
     if (fb) {
         if (lane == 0) p.fb_list[atomicAdd(&p.counters[0], 1ull)] = (uint32_t)q;
@@ -486,13 +514,59 @@ __global__ void __launch_bounds__(128) fselect_kernel(FSelParams p) {
         }
         start += np;
     }
+    const size_t s = p.s, D = p.D;
+    const float *qv = p.q + q * p.N;
+    float myR = 0.0f;
+    if (p.quad) {
+        // s % 16 == 0: a quad of lanes per (candidate, division) item, 8 items per round; lane tq
+        // of the quad owns accumulators 4tq..4tq+3 of the 16-lane dot (src/linalg.rs:12-40) and
+        // loads 128 bits at a time; the lane sums are chained through the quad in lane order
+        extern __shared__ float tbuf_all[];
+        float *tbuf = tbuf_all + (size_t)warp * RCAP * D;   // [candidate][division]
+        const int g = lane >> 2, tq = lane & 3, qbase = lane & ~3;
+        const int nitems = ncand * (int)D;
+        for (int it0 = 0; it0 < nitems; it0 += 8) {
+            const int item = it0 + g;
+            const bool act = item < nitems;
+            const int c = act ? item / (int)D : 0;
+            const size_t d = act ? (size_t)(item - c * (int)D) : 0;
+            const uint32_t part = __shfl_sync(0xffffffffu, my_part, c);
+            const uint32_t vidx = __shfl_sync(0xffffffffu, my_vidx, c);
+            const uint8_t code = p.codes[p.part_cstart[part] + (size_t)vidx * D + d];
+            const float *xq = qv + d * s;
+            const float *xc = p.coarse + (size_t)part * p.N + d * s;
+            const float *xb = p.codebooks + (d * p.C + code) * s;
+            float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+            for (size_t e = 4 * tq; e < s; e += 16) {
+                const float4 x = *reinterpret_cast<const float4 *>(xq + e);
+                const float4 cc = __ldg(reinterpret_cast<const float4 *>(xc + e));
+                const float4 b = __ldg(reinterpret_cast<const float4 *>(xb + e));
+                a0 = __fadd_rn(a0, sq_diff2(x.x, cc.x, b.x));
+                a1 = __fadd_rn(a1, sq_diff2(x.y, cc.y, b.y));
+                a2 = __fadd_rn(a2, sq_diff2(x.z, cc.z, b.z));
+                a3 = __fadd_rn(a3, sq_diff2(x.w, cc.w, b.w));
+            }
+            float T = 0.0f;  // sum_naive over the 16 accumulators, src/linalg.rs:39
+#pragma unroll
+            for (int t4 = 0; t4 < 4; ++t4) {
+                if (tq == t4) {
+                    T = __fadd_rn(T, a0);
+                    T = __fadd_rn(T, a1);
+                    T = __fadd_rn(T, a2);
+                    T = __fadd_rn(T, a3);
+                }
+                T = __shfl_sync(0xffffffffu, T, qbase + t4);
+            }
+            if (act && tq == 0) tbuf[item] = T;
+        }
+        __syncwarp();
+        if (lane < ncand)  // dist = 0; dist += table[..] in division order, src/db/stored.rs:581-587
+            for (size_t d = 0; d < D; ++d) myR = __fadd_rn(myR, tbuf[(size_t)lane * D + d]);
+    } else {
     // exact distances, two candidates at a time (one per half warp); lane j of a half owns
     // accumulator j of the 16-lane dot (src/linalg.rs:12-40)
     const int half = lane >> 4, j = lane & 15, hbase = half * 16;
-    const size_t s = p.s, D = p.D;
     const size_t r = s & 15;
-    const float *qv = p.q + q * p.N;
-    float myR = 0.0f;
     for (int i = 0; 2 * i < ncand; ++i) {
         const int c = 2 * i + half;
         const int src = c < ncand ? c : 0;
@@ -524,6 +598,7 @@ __global__ void __launch_bounds__(128) fselect_kernel(FSelParams p) {
         const float v = __shfl_sync(0xffffffffu, R, (lane & 1) * 16);
         if ((lane >> 1) == i) myR = v;
     }
+    }
     const bool mine = lane < ncand;
     int rank = 0;
     bool tie = false;
@@ -532,8 +607,9 @@ __global__ void __launch_bounds__(128) fselect_kernel(FSelParams p) {
         rank += (Rj < myR) || (Rj == myR && jx < lane);
         tie |= (Rj == myR) && jx != lane;
     }
-    // NaN, or an exact tie among the k+1 smallest: the reference's answer depends on push history
-    const bool hard = mine && ((myR != myR) || (tie && rank <= k));
+    // NaN, or an exact tie that involves one of the k smallest: the reference's answer depends on
+    // push history
+    const bool hard = mine && ((myR != myR) || (tie && rank < k));
     if (__any_sync(0xffffffffu, hard)) {
         if (lane == 0) p.fb_list[atomicAdd(&p.counters[0], 1ull)] = (uint32_t)q;
         return;
@@ -550,13 +626,32 @@ __global__ void __launch_bounds__(128) fselect_kernel(FSelParams p) {
     }
 }
 
+bool scan_use_gs(const fdb_index *ix, int chunk_vecs) {
+    const size_t DCp = (ix->D * ix->C + 3) & ~(size_t)3;
+    return ix->D * TSTRIDE * 4 + (size_t)FS_WARPS * 2 * chunk_vecs * ix->D + DCp * 4 <= 64 * 1024;
+}
 size_t scan_smem_bytes(const fdb_index *ix, int chunk_vecs) {
     const size_t DCp = (ix->D * ix->C + 3) & ~(size_t)3;
-    return 2 * DCp * 4 + (size_t)FS_WARPS * 2 * chunk_vecs * ix->D + (size_t)FS_WARPS * RCAP * 8 +
-           FS_WARPS * 4 + 16;
+    return ix->D * TSTRIDE * 4 + (size_t)FS_WARPS * 2 * chunk_vecs * ix->D +
+           (scan_use_gs(ix, chunk_vecs) ? DCp * 4 : 0) + 16;
 }
 int scan_chunk_vecs(const fdb_index *ix) {
     return (int)std::max<size_t>(32, (2048 / ix->D) & ~(size_t)31);
+}
+
+typedef void (*FScanFn)(FScanParams);
+FScanFn scan_fn(size_t D) {
+    switch (D) {
+        case 4: return fscan_kernel<1>;
+        case 8: return fscan_kernel<2>;
+        case 12: return fscan_kernel<3>;
+        case 16: return fscan_kernel<4>;
+        case 24: return fscan_kernel<6>;
+        case 32: return fscan_kernel<8>;
+        case 48: return fscan_kernel<12>;
+        case 64: return fscan_kernel<16>;
+        default: return fscan_kernel<0>;
+    }
 }
 
 }  // namespace
@@ -637,7 +732,10 @@ int filter_query(fdb_index *ix, const float *d_q, size_t nq, size_t k, size_t np
 
     const int chunk_vecs = scan_chunk_vecs(ix);
     const size_t smem = scan_smem_bytes(ix, chunk_vecs);
-    FDB_CUDA(cudaFuncSetAttribute(fscan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const FScanFn scan = scan_fn(D);
+    FDB_CUDA(cudaFuncSetAttribute(scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // list capacity: k plus head room for the vectors inside the error band
+    const int ncap = (int)std::min<size_t>(RCAP, k + 6);
     const bool vec = (s % 4 == 0) && (N % 4 == 0) && ((uintptr_t)d_q % 16 == 0);
     const double gamma = (double)s * U24 / (1.0 - (double)s * U24);
     const float coef = (float)((2.0 * gamma + (double)(D + 4) * U24) * 1.01);
@@ -665,13 +763,15 @@ int filter_query(fdb_index *ix, const float *d_q, size_t nq, size_t k, size_t np
         sp.D = (int)D;
         sp.C = (int)C;
         sp.chunk_vecs = chunk_vecs;
+        sp.ncap = ncap;
+        sp.use_gs = scan_use_gs(ix, chunk_vecs) ? 1 : 0;
         sp.cand_d = fs->cand_d.p;
         sp.cand_a = fs->cand_a.p;
         sp.cand_cnt = fs->cand_cnt.p;
         sp.cand_total = fs->cand_total.p;
         sp.qbad = fs->qbad.p;
         sp.counters = fs->counters.p;
-        fscan_kernel<<<(unsigned)nc, FS_WARPS * 32, smem, st>>>(sp);
+        scan<<<(unsigned)nc, FS_WARPS * 32, smem, st>>>(sp);
         ctx->launches++;
         FDB_CHECK_LAUNCH();
     }
@@ -698,6 +798,8 @@ int filter_query(fdb_index *ix, const float *d_q, size_t nq, size_t k, size_t np
     fp.s = s;
     fp.nprobe = (int)nprobe;
     fp.k = (int)k;
+    fp.ncap = ncap;
+    fp.quad = (s % 16 == 0) && (N % 4 == 0) && ((uintptr_t)d_q % 16 == 0) && (4 * RCAP * D * sizeof(float) <= 48 * 1024);
     fp.coef = coef;
     fp.eta3 = eta3;
     fp.out_p = d_p;
@@ -706,7 +808,7 @@ int filter_query(fdb_index *ix, const float *d_q, size_t nq, size_t k, size_t np
     fp.out_d = d_d;
     fp.fb_list = fs->fb_list.p;
     fp.counters = fs->counters.p;
-    fselect_kernel<<<(unsigned)((nq + 3) / 4), 128, 0, st>>>(fp);
+    fselect_kernel<<<(unsigned)((nq + 3) / 4), 128, fp.quad ? 4 * RCAP * D * sizeof(float) : 0, st>>>(fp);
     ctx->launches++;
     FDB_CHECK_LAUNCH();
     FDB_CUDA(cudaMemcpyAsync(fs->h_counters, fs->counters.p, 4 * sizeof(unsigned long long),

@@ -26,7 +26,7 @@ struct fdb_index {
     bool timing = false;
     size_t chunk_pairs = 8192;
     fdb::DevBuf<float> fb_q, fb_d;        // queries the filter path handed to the exact pipeline
-    fdb::DevBuf<uint32_t> fb_p, fb_v, fb_c;
+    fdb::DevBuf<uint32_t> fb_p, fb_v, fb_c, fb_probes;
     bool last_filter = false;
     fdb::FilterState *filter = nullptr;   // ADC filter path (adc_filter.cu), null when not usable
     uint64_t last_stats[4] = {0, 0, 0, 0};  // queries on the filter path, exact fallbacks, exact candidates, scanned vectors

@@ -323,11 +323,16 @@ __global__ void __launch_bounds__(MERGE_WARPS * 32) merge_kernel(
 }
 
 // ---- hand-over of undecided queries between the filter path and the exact pipeline ------
-__global__ void gather_rows_kernel(const float *q, const uint32_t *list, size_t n, size_t N, float *out) {
+__global__ void gather_rows_kernel(const float *q, const uint32_t *probes, const uint32_t *list, size_t n,
+                                   size_t N, size_t nprobe, float *out_q, uint32_t *out_probes) {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n * nprobe) {
+        const size_t r = t / nprobe, e = t - r * nprobe;
+        out_probes[t] = probes[(size_t)list[r] * nprobe + e];
+    }
     if (t >= n * N) return;
     const size_t r = t / N, e = t - r * N;
-    out[t] = q[(size_t)list[r] * N + e];
+    out_q[t] = q[(size_t)list[r] * N + e];
 }
 __global__ void scatter_results_kernel(const uint32_t *list, size_t n, size_t k, const uint32_t *fp,
                                        const uint32_t *fv, const float *fd, const uint32_t *fc,
@@ -565,8 +570,9 @@ int check_query_args(fdb_index *ix, size_t nq, size_t k, size_t nprobe, int mode
 }
 
 // steps 3-6 of the exact pipeline for queries whose probes are already in ix->probes
-int exact_after_probe(fdb_index *ix, const float *d_q, size_t nq, size_t k, size_t nprobe, int mode,
-                      uint32_t *d_p, uint32_t *d_v, float *d_d, uint32_t *d_c, EventLog &log) {
+int exact_after_probe(fdb_index *ix, const float *d_q, const uint32_t *d_probes, size_t nq, size_t k,
+                      size_t nprobe, int mode, uint32_t *d_p, uint32_t *d_v, float *d_d, uint32_t *d_c,
+                      EventLog &log) {
     fdb_ctx *ctx = ix->ctx;
     const size_t npairs = nq * nprobe;
     const size_t DC = ix->D * ix->C;
@@ -602,7 +608,7 @@ int exact_after_probe(fdb_index *ix, const float *d_q, size_t nq, size_t k, size
         {
             const size_t work = (ix->N & 3) == 0 ? np * (ix->N >> 2) : np * ix->N;
             localize_kernel<<<(unsigned)((work + 255) / 256), 256, 0, ctx->stream>>>(
-                d_q, ix->coarse.p, ix->probes.p, pair0, np, nprobe, ix->N, ix->loc.p);
+                d_q, ix->coarse.p, d_probes, pair0, np, nprobe, ix->N, ix->loc.p);
         }
         ctx->launches++;
         FDB_TRY(log.mark(3));
@@ -622,7 +628,7 @@ int exact_after_probe(fdb_index *ix, const float *d_q, size_t nq, size_t k, size
         sp.codes = ix->codes.p;
         sp.part_off = ix->part_off.p;
         sp.part_cstart = ix->part_cstart.p;
-        sp.probes = ix->probes.p;
+        sp.probes = d_probes;
         sp.pair0 = pair0;
         sp.D = ix->D;
         sp.C = ix->C;
@@ -648,7 +654,7 @@ int exact_after_probe(fdb_index *ix, const float *d_q, size_t nq, size_t k, size
     FDB_TRY(log.mark(5));
     const size_t msmem = (size_t)MERGE_WARPS * 4 * k * sizeof(float);
     merge_kernel<<<(unsigned)((nq + MERGE_WARPS - 1) / MERGE_WARPS), MERGE_WARPS * 32, msmem, ctx->stream>>>(
-        ix->part_d.p, ix->part_v.p, ix->part_cnt.p, ix->probes.p, nq, (int)nprobe, (int)k, mode, d_p,
+        ix->part_d.p, ix->part_v.p, ix->part_cnt.p, d_probes, nq, (int)nprobe, (int)k, mode, d_p,
         d_v, d_d, d_c, ctx->d_flags);
     ctx->launches++;
     FDB_CHECK_LAUNCH();
@@ -679,19 +685,20 @@ int query_device(fdb_index *ix, const float *d_q, size_t nq, size_t k, size_t np
             FDB_TRY(ix->fb_v.ensure((size_t)nfb * k));
             FDB_TRY(ix->fb_d.ensure((size_t)nfb * k));
             FDB_TRY(ix->fb_c.ensure(nfb));
-            gather_rows_kernel<<<(unsigned)(((size_t)nfb * ix->N + 255) / 256), 256, 0, st>>>(d_q, d_fb, nfb, ix->N,
-                                                                                            ix->fb_q.p);
+            FDB_TRY(ix->fb_probes.ensure((size_t)nfb * nprobe));
+            // their probes are already selected (exactly): only steps 3-6 run again
+            gather_rows_kernel<<<(unsigned)(((size_t)nfb * std::max(ix->N, nprobe) + 255) / 256), 256, 0, st>>>(
+                d_q, ix->probes.p, d_fb, nfb, ix->N, nprobe, ix->fb_q.p, ix->fb_probes.p);
             ctx->launches++;
-            FDB_TRY(probe_device(ix, ix->fb_q.p, nfb, nprobe, mode, &log));
-            FDB_TRY(exact_after_probe(ix, ix->fb_q.p, nfb, k, nprobe, mode, ix->fb_p.p, ix->fb_v.p, ix->fb_d.p,
-                                      ix->fb_c.p, log));
+            FDB_TRY(exact_after_probe(ix, ix->fb_q.p, ix->fb_probes.p, nfb, k, nprobe, mode, ix->fb_p.p,
+                                      ix->fb_v.p, ix->fb_d.p, ix->fb_c.p, log));
             scatter_results_kernel<<<(unsigned)(((size_t)nfb * k + 255) / 256), 256, 0, st>>>(
                 d_fb, nfb, k, ix->fb_p.p, ix->fb_v.p, ix->fb_d.p, ix->fb_c.p, d_p, d_v, d_d, d_c);
             ctx->launches++;
             FDB_CHECK_LAUNCH();
         }
     } else {
-        FDB_TRY(exact_after_probe(ix, d_q, nq, k, nprobe, mode, d_p, d_v, d_d, d_c, log));
+        FDB_TRY(exact_after_probe(ix, d_q, ix->probes.p, nq, k, nprobe, mode, d_p, d_v, d_d, d_c, log));
         ix->last_npairs = nq * nprobe;
         ix->last_stats[1] = nq;
     }

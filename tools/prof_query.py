@@ -23,3 +23,4 @@ for _ in range(steps):
     ix.query_device(d_q, NQ, K, NPROBE, *outs)
     ctx.sync()
 print("phase ms", ix.last_timing())
+print("stats (filter, exact, exact candidates, scanned vectors)", ix.last_stats())
