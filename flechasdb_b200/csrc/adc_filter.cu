@@ -36,6 +36,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 
 namespace fdb {
 
@@ -43,6 +44,9 @@ struct FilterState {
     DevBuf<float> pc;            // [P][D][C]
     DevBuf<float> cbmax;         // [D]
     DevBuf<unsigned> bounds;     // float bits: [0] cb2, [1] pcmax
+    DevBuf<uint8_t> rec;         // records (RECORDS layout), empty when the lists are long
+    DevBuf<uint64_t> rec_start;  // [P] byte offset of the partition's records, 16-byte aligned
+    size_t rb = 0;               // bytes per record
     DevBuf<float> G;             // [chunk_q][D][C]
     DevBuf<float> Kq, Wq;        // [nq][nprobe], [nq]
     DevBuf<float> cand_d;        // [nq][32]
@@ -270,16 +274,21 @@ __global__ void __launch_bounds__(G_THREADS, 2) adc_gemm_kernel(const float *__r
 }
 
 // ---- scan: the ncap smallest approximate distances of a query -------------------------------
+// Two layouts of the same sum.  RECORDS (short lists): the index-only part of every vector,
+// bv(v) = sum_d PC[p][d][code(v,d)], is stored next to its codes (one 16-byte record per vector
+// when D = 12), the table is G[q] for all probed lists and no per-list table is built.  TABLES
+// (long lists, where 4 extra bytes per vector would cost more than D*C adds per list): the
+// table T = G[q] + PC[p] is assembled per list and the compact u8 codes are streamed.
 struct FScanParams {
     const float *G;             // [queries of this chunk][D*C]
     const float *pc;            // [P][D*C]
     const float *Kq;            // [nq][nprobe]
-    const uint8_t *codes;
+    const uint8_t *codes;       // compact codes (TABLES) or records (RECORDS)
     const uint32_t *part_off;
-    const uint64_t *part_cstart;
+    const uint64_t *part_start; // byte offset of the list of partition p in `codes`
     const uint32_t *probes;     // [nq][nprobe]
     size_t q0;
-    int nprobe, D, C, chunk_vecs, ncap, use_gs;
+    int nprobe, D, C, chunk_vecs, ncap, rb;   // rb = bytes per vector in `codes`
     float *cand_d;              // [nq][RCAP] ascending, ncap <= RCAP used
     uint32_t *cand_a;           // position in the concatenation of the probed lists
     uint32_t *cand_cnt, *cand_total;
@@ -290,20 +299,59 @@ struct FScanParams {
 constexpr int FS_WARPS = 4;
 constexpr int TSTRIDE = 256;    // table row stride in shared memory: offsets become immediates
 
-__device__ __forceinline__ void push_lanes(RegSorted &sel, float dv, uint32_t av, bool want, int lane) {
+// order-preserving map float -> u32 (all finite values, -0 < +0 adjacent)
+__device__ __forceinline__ uint32_t fkey(float f) {
+    const uint32_t b = __float_as_uint(f);
+    return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);
+}
+__device__ __forceinline__ float fkey_inv(uint32_t k) {
+    return __uint_as_float(k ^ ((k >> 31) ? 0x80000000u : 0xffffffffu));
+}
+
+// the n <= 32 smallest keys seen so far, unsorted, lane s holds slot s; maxkey = largest kept
+struct RegTopK {
+    uint32_t key, a;
+    int n, len;
+    uint32_t maxkey;  // 0xffffffff until the list is full
+    __device__ void init(int nn) {
+        key = 0;
+        a = 0;
+        n = nn;
+        len = 0;
+        maxkey = 0xffffffffu;
+    }
+    __device__ void push(uint32_t ck, uint32_t ca, int lane) {
+        if (len < n) {
+            if (lane == len) {
+                key = ck;
+                a = ca;
+            }
+            if (++len == n) maxkey = __reduce_max_sync(0xffffffffu, lane < n ? key : 0u);
+            return;
+        }
+        if (!(ck < maxkey)) return;
+        const unsigned bal = __ballot_sync(0xffffffffu, lane < n && key == maxkey);
+        if (lane == __ffs(bal) - 1) {
+            key = ck;
+            a = ca;
+        }
+        maxkey = __reduce_max_sync(0xffffffffu, lane < n ? key : 0u);
+    }
+};
+__device__ __forceinline__ void push_lanes(RegTopK &sel, uint32_t kv, uint32_t av, bool want, int lane) {
     unsigned bal = __ballot_sync(0xffffffffu, want);
     while (bal) {
         const int L = __ffs(bal) - 1;
         bal &= bal - 1;
-        sel.push(__shfl_sync(0xffffffffu, dv, L), __shfl_sync(0xffffffffu, av, L), lane);
+        sel.push(__shfl_sync(0xffffffffu, kv, L), __shfl_sync(0xffffffffu, av, L), lane);
     }
 }
 
-// sum of the D table entries of code vector v; W = D / 4 code words (0: any D, byte by byte)
+// sum of the D table entries of a code vector; W = D / 4 code words (0: any D, byte by byte)
 template <int W>
-__device__ __forceinline__ float adc_sum(const unsigned char *cs, int v, const float *Ts, int D) {
+__device__ __forceinline__ float adc_sum(const unsigned char *rec, const float *Ts, int D) {
     if (W > 0) {
-        const uint32_t *cw = reinterpret_cast<const uint32_t *>(cs) + v * W;
+        const uint32_t *cw = reinterpret_cast<const uint32_t *>(rec);
         float a0 = 0.0f, a1 = 0.0f;
 #pragma unroll
         for (int w = 0; w < W; ++w) {
@@ -317,83 +365,78 @@ __device__ __forceinline__ float adc_sum(const unsigned char *cs, int v, const f
         return a0 + a1;
     }
     float acc = 0.0f;
-    for (int di = 0; di < D; ++di) acc += Ts[di * TSTRIDE + cs[(size_t)v * D + di]];
+    for (int di = 0; di < D; ++di) acc += Ts[di * TSTRIDE + rec[di]];
     return acc;
 }
 
-template <int W>
+template <int W, bool RECORDS>
 __global__ void __launch_bounds__(FS_WARPS * 32) fscan_kernel(FScanParams p) {
     extern __shared__ __align__(16) unsigned char sm[];
-    __shared__ int thr_s;       // bits of the smallest "worst kept" value over the warps' full lists
-    __shared__ float md[FS_WARPS * RCAP];
-    __shared__ uint32_t ma[FS_WARPS * RCAP];
+    __shared__ unsigned thr_s;  // smallest "largest kept key" over the warps' full lists
+    __shared__ uint32_t mk[FS_WARPS * RCAP], ma[FS_WARPS * RCAP];
     __shared__ int mlen[FS_WARPS];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int D = p.D, C = p.C;
+    const int D = p.D, C = p.C, RB = p.rb;
     const int DC = D * C;
     float *Ts = reinterpret_cast<float *>(sm);                       // [D][TSTRIDE]
-    const size_t chunk_bytes = (size_t)p.chunk_vecs * D;             // multiple of 16 (chunk_vecs % 32 == 0)
+    const size_t chunk_bytes = (size_t)p.chunk_vecs * RB;            // multiple of 16 (chunk_vecs % 32 == 0, RB % 4 == 0 or W == 0 && !RECORDS)
     unsigned char *cbuf = reinterpret_cast<unsigned char *>(Ts + (size_t)D * TSTRIDE) + (size_t)warp * 2 * chunk_bytes;
-    float *Gs = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(Ts + (size_t)D * TSTRIDE) +
-                                          (size_t)FS_WARPS * 2 * chunk_bytes);  // [D*C] when use_gs
 
     const size_t q = p.q0 + blockIdx.x;
     const float *gq = p.G + (size_t)blockIdx.x * DC;
-    const bool vec4 = (C & 3) == 0;
-    if (p.use_gs) {
-        if (vec4) {
-            for (int i = tid; i < DC / 4; i += FS_WARPS * 32)
-                reinterpret_cast<float4 *>(Gs)[i] = reinterpret_cast<const float4 *>(gq)[i];
-        } else {
-            for (int i = tid; i < DC; i += FS_WARPS * 32) Gs[i] = gq[i];
-        }
-        gq = Gs;
-    }
-    if (tid == 0) thr_s = 0x7f800000;
-
-    RegSorted sel;
-    sel.init(p.ncap);
     bool bad = false;
+    // table rows: Ts[d][c] = G[q][d][c] (+ PC[p][d][c] per list in TABLES mode)
+    auto build_table = [&](const float *pcp) {
+        if (C == TSTRIDE) {
+            for (int i = tid; i < DC / 4; i += FS_WARPS * 32) {
+                float4 t = __ldg(reinterpret_cast<const float4 *>(gq) + i);
+                if (pcp) {
+                    const float4 c = __ldg(reinterpret_cast<const float4 *>(pcp) + i);
+                    t = make_float4(t.x + c.x, t.y + c.y, t.z + c.z, t.w + c.w);
+                }
+                bad |= !(fabsf(t.x) + fabsf(t.y) + fabsf(t.z) + fabsf(t.w) < 1e30f);
+                reinterpret_cast<float4 *>(Ts)[i] = t;
+            }
+        } else {
+            for (int i = tid; i < DC; i += FS_WARPS * 32) {
+                const float t = __ldg(gq + i) + (pcp ? __ldg(pcp + i) : 0.0f);
+                bad |= !(fabsf(t) < 1e30f);
+                const int d = i / C;
+                Ts[d * TSTRIDE + (i - d * C)] = t;
+            }
+        }
+    };
+    if (tid == 0) thr_s = 0xffffffffu;
+    if (RECORDS) build_table(nullptr);
+
+    RegTopK sel;
+    sel.init(p.ncap);
     uint32_t flat0 = 0;
+    const int dpad = (D + 3) & ~3;   // offset of bv inside a record
     for (int pr = 0; pr < p.nprobe; ++pr) {
         const uint32_t part = p.probes[q * p.nprobe + pr];
         const int np = (int)(p.part_off[part + 1] - p.part_off[part]);
         const float K = p.Kq[q * p.nprobe + pr];
         bad |= !(fabsf(K) < 1e30f);
-        const uint8_t *cg = p.codes + p.part_cstart[part];
+        const uint8_t *cg = p.codes + p.part_start[part];
         const int nchunks = (np + p.chunk_vecs - 1) / p.chunk_vecs;
         auto issue = [&](int c, int slot) {
             if (c < nchunks) {
                 const int c0 = c * p.chunk_vecs;
                 const int cnt = min(p.chunk_vecs, np - c0);
-                const size_t n16 = ((size_t)cnt * D + 15) >> 4;
-                const uint8_t *src = cg + (size_t)c0 * D;
+                const size_t n16 = ((size_t)cnt * RB + 15) >> 4;
+                const uint8_t *src = cg + (size_t)c0 * RB;
                 unsigned char *dst = cbuf + (size_t)slot * chunk_bytes;
                 for (size_t i = lane; i < n16; i += 32) cp_async16(dst + 16 * i, src + 16 * i);
             }
             cp_async_commit();
         };
         issue(warp, 0);  // the warp's first chunk travels while the table is assembled
-        __syncthreads();  // the previous list is fully scanned (first round: Gs and thr_s are set)
-        // T = G[q] + PC[p]
-        const float *pcp = p.pc + (size_t)part * DC;
-        if (C == TSTRIDE) {
-            for (int i = tid; i < DC / 4; i += FS_WARPS * 32) {
-                const float4 g = reinterpret_cast<const float4 *>(gq)[i];
-                const float4 c = __ldg(reinterpret_cast<const float4 *>(pcp) + i);
-                const float4 t = make_float4(g.x + c.x, g.y + c.y, g.z + c.z, g.w + c.w);
-                bad |= !(fabsf(t.x) < 1e30f) | !(fabsf(t.y) < 1e30f) | !(fabsf(t.z) < 1e30f) | !(fabsf(t.w) < 1e30f);
-                reinterpret_cast<float4 *>(Ts)[i] = t;
-            }
-        } else {
-            for (int i = tid; i < DC; i += FS_WARPS * 32) {
-                const float t = gq[i] + __ldg(pcp + i);
-                bad |= !(fabsf(t) < 1e30f);
-                const int d = i / C;
-                Ts[d * TSTRIDE + (i - d * C)] = t;
-            }
+        if (!RECORDS || pr == 0) __syncthreads();  // previous list fully scanned / Ts and thr_s set
+        if (!RECORDS) {
+            build_table(p.pc + (size_t)part * DC);
+            __syncthreads();
         }
-        __syncthreads();
         int slot = 0;
         for (int c = warp; c < nchunks; c += FS_WARPS) {
             issue(c + FS_WARPS, slot ^ 1);
@@ -405,14 +448,21 @@ __global__ void __launch_bounds__(FS_WARPS * 32) fscan_kernel(FScanParams p) {
             for (int base = 0; base < cnt; base += 32) {
                 const int v = base + lane;
                 const bool valid = v < cnt;
-                const float a = valid ? adc_sum<W>(cs, v, Ts, D) + K : 0.0f;
-                // a vector is kept only below this warp's worst kept value and below every other
-                // warp's (a full list elsewhere already holds ncap values <= its worst)
-                const float lim = fminf(sel.last, __int_as_float(*reinterpret_cast<volatile int *>(&thr_s)));
-                const bool want = valid && (a < lim);
+                float a = 0.0f;
+                if (valid) {
+                    const unsigned char *rec = cs + (size_t)v * RB;
+                    a = adc_sum<W>(rec, Ts, D);
+                    if (RECORDS) a += *reinterpret_cast<const float *>(rec + dpad);
+                    a += K;
+                }
+                const uint32_t ka = fkey(a);
+                // a vector is kept only below this warp's largest kept value and below every other
+                // warp's (a full list elsewhere already holds ncap values <= its largest)
+                const uint32_t lim = min(sel.maxkey, *reinterpret_cast<volatile unsigned *>(&thr_s));
+                const bool want = valid && (ka < lim);
                 if (__any_sync(0xffffffffu, want)) {
-                    push_lanes(sel, a, flat0 + (uint32_t)(c0 + v), want, lane);
-                    if (lane == 0 && sel.len == sel.n && sel.last >= 0.0f) atomicMin(&thr_s, __float_as_int(sel.last));
+                    push_lanes(sel, ka, flat0 + (uint32_t)(c0 + v), want, lane);
+                    if (lane == 0 && sel.len == sel.n) atomicMin(&thr_s, sel.maxkey);
                 }
             }
             __syncwarp();
@@ -423,25 +473,53 @@ __global__ void __launch_bounds__(FS_WARPS * 32) fscan_kernel(FScanParams p) {
     }
     // merge the warps' lists into warp 0's
     if (lane < sel.len) {
-        md[warp * RCAP + lane] = sel.d;
+        mk[warp * RCAP + lane] = sel.key;
         ma[warp * RCAP + lane] = sel.a;
     }
     if (lane == 0) mlen[warp] = sel.len;
     const int anybad = __syncthreads_or(bad ? 1 : 0);
     if (warp != 0) return;
     for (int w = 1; w < FS_WARPS; ++w) {
-        const float dv = md[w * RCAP + lane];
-        push_lanes(sel, dv, ma[w * RCAP + lane], lane < mlen[w] && (sel.len < sel.n || dv < sel.last), lane);
+        const uint32_t kv = mk[w * RCAP + lane];
+        push_lanes(sel, kv, ma[w * RCAP + lane], lane < mlen[w] && kv < sel.maxkey, lane);
+    }
+    // ascending order (rank sort; equal keys in slot order)
+    int rank = 0;
+    for (int j = 0; j < sel.len; ++j) {
+        const uint32_t kj = __shfl_sync(0xffffffffu, sel.key, j);
+        rank += (kj < sel.key) || (kj == sel.key && j < lane);
     }
     if (lane < sel.len) {
-        p.cand_d[q * RCAP + lane] = sel.d;
-        p.cand_a[q * RCAP + lane] = sel.a;
+        p.cand_d[q * RCAP + rank] = fkey_inv(sel.key);
+        p.cand_a[q * RCAP + rank] = sel.a;
     }
     if (lane == 0) {
         p.cand_cnt[q] = (uint32_t)sel.len;
         p.cand_total[q] = flat0;
         p.qbad[q] = (unsigned)anybad;
         atomicAdd(&p.counters[2], (unsigned long long)flat0);
+    }
+}
+
+// ---- records: D code bytes (padded to a multiple of 4) + bv(v) per vector ---------------------
+__global__ void __launch_bounds__(256) records_kernel(const uint8_t *codes, const float *pc,
+                                                      const uint32_t *part_off, const uint64_t *part_cstart,
+                                                      const uint64_t *rec_start, size_t P, size_t D, size_t C,
+                                                      size_t rb, uint8_t *rec) {
+    const size_t p = blockIdx.y;
+    const size_t np = part_off[p + 1] - part_off[p];
+    const size_t dpad = (D + 3) & ~(size_t)3;
+    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < np; v += (size_t)gridDim.x * blockDim.x) {
+        const uint8_t *src = codes + part_cstart[p] + v * D;
+        uint8_t *dst = rec + rec_start[p] + v * rb;
+        double acc = 0.0;
+        for (size_t d = 0; d < D; ++d) {
+            const uint8_t c = src[d];
+            dst[d] = c;
+            acc += (double)pc[(p * D + d) * C + c];
+        }
+        for (size_t d = D; d < dpad; ++d) dst[d] = 0;
+        *reinterpret_cast<float *>(dst + dpad) = (float)acc;
     }
 }
 
@@ -626,33 +704,28 @@ __global__ void __launch_bounds__(128) fselect_kernel(FSelParams p) {
     }
 }
 
-bool scan_use_gs(const fdb_index *ix, int chunk_vecs) {
-    const size_t DCp = (ix->D * ix->C + 3) & ~(size_t)3;
-    return ix->D * TSTRIDE * 4 + (size_t)FS_WARPS * 2 * chunk_vecs * ix->D + DCp * 4 <= 64 * 1024;
+size_t scan_smem_bytes(const fdb_index *ix, int chunk_vecs, size_t rb) {
+    return ix->D * TSTRIDE * 4 + (size_t)FS_WARPS * 2 * chunk_vecs * rb + 16;
 }
-size_t scan_smem_bytes(const fdb_index *ix, int chunk_vecs) {
-    const size_t DCp = (ix->D * ix->C + 3) & ~(size_t)3;
-    return ix->D * TSTRIDE * 4 + (size_t)FS_WARPS * 2 * chunk_vecs * ix->D +
-           (scan_use_gs(ix, chunk_vecs) ? DCp * 4 : 0) + 16;
-}
-int scan_chunk_vecs(const fdb_index *ix) {
-    return (int)std::max<size_t>(32, (2048 / ix->D) & ~(size_t)31);
-}
+int scan_chunk_vecs(size_t rb) { return (int)std::max<size_t>(32, (2048 / rb) & ~(size_t)31); }
+size_t record_bytes(size_t D) { return ((D + 3) & ~(size_t)3) + 4; }
 
 typedef void (*FScanFn)(FScanParams);
-FScanFn scan_fn(size_t D) {
+template <bool R>
+FScanFn scan_fn_w(size_t D) {
     switch (D) {
-        case 4: return fscan_kernel<1>;
-        case 8: return fscan_kernel<2>;
-        case 12: return fscan_kernel<3>;
-        case 16: return fscan_kernel<4>;
-        case 24: return fscan_kernel<6>;
-        case 32: return fscan_kernel<8>;
-        case 48: return fscan_kernel<12>;
-        case 64: return fscan_kernel<16>;
-        default: return fscan_kernel<0>;
+        case 4: return fscan_kernel<1, R>;
+        case 8: return fscan_kernel<2, R>;
+        case 12: return fscan_kernel<3, R>;
+        case 16: return fscan_kernel<4, R>;
+        case 24: return fscan_kernel<6, R>;
+        case 32: return fscan_kernel<8, R>;
+        case 48: return fscan_kernel<12, R>;
+        case 64: return fscan_kernel<16, R>;
+        default: return fscan_kernel<0, R>;
     }
 }
+FScanFn scan_fn(size_t D, bool records) { return records ? scan_fn_w<true>(D) : scan_fn_w<false>(D); }
 
 }  // namespace
 
@@ -673,7 +746,7 @@ int filter_prepare(fdb_index *ix) {
     fdb_ctx *ctx = ix->ctx;
     const size_t P = ix->P, D = ix->D, C = ix->C, s = ix->s;
     if (P * D * C * sizeof(float) > (4ull << 30)) return FDB_OK;          // PC tables too large
-    if (scan_smem_bytes(ix, scan_chunk_vecs(ix)) > 200 * 1024) return FDB_OK;
+    if (scan_smem_bytes(ix, scan_chunk_vecs(record_bytes(D)), record_bytes(D)) > 200 * 1024) return FDB_OK;
     if ((double)s * U24 > 1e-3) return FDB_OK;
     FilterState *fs = new FilterState;
     ix->filter = fs;
@@ -694,6 +767,36 @@ int filter_prepare(fdb_index *ix) {
     FDB_CUDA(cudaMemcpyAsync(hb, fs->bounds.p, sizeof(hb), cudaMemcpyDeviceToHost, st));
     FDB_CUDA(cudaStreamSynchronize(st));
     if (const char *e = getenv("FDB_FILTER_CHUNK_Q")) fs->chunk_q = (size_t)std::max(1L, atol(e));
+    // short lists: records (codes + bv) instead of a table per probed list
+    const char *layout = getenv("FDB_FILTER_LAYOUT");  // "records" / "tables" override the heuristic
+    bool records = ix->M < (size_t)1.5 * D * C * P;
+    if (layout && !strcmp(layout, "records")) records = true;
+    if (layout && !strcmp(layout, "tables")) records = false;
+    if (records && ix->M > 0) {
+        const size_t rb = record_bytes(D);
+        std::vector<uint64_t> rs(P);
+        uint64_t cur = 0;
+        for (size_t p = 0; p < P; ++p) {
+            rs[p] = cur;
+            cur += ((uint64_t)(ix->h_off[p + 1] - ix->h_off[p]) * rb + 15) & ~(uint64_t)15;
+        }
+        fs->rb = rb;
+        FDB_TRY(fs->rec.alloc(cur + 16));
+        FDB_TRY(fs->rec_start.alloc(P));
+        FDB_CUDA(cudaMemsetAsync(fs->rec.p, 0, cur + 16, st));
+        FDB_CUDA(cudaMemcpyAsync(fs->rec_start.p, rs.data(), P * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        dim3 grid((unsigned)std::min<size_t>(64, (ix->M / P + 255) / 256 + 1), (unsigned)std::min<size_t>(P, 65535));
+        if (P <= 65535) {
+            records_kernel<<<grid, 256, 0, st>>>(ix->codes.p, fs->pc.p, ix->part_off.p, ix->part_cstart.p,
+                                                 fs->rec_start.p, P, D, C, rb, fs->rec.p);
+            ctx->launches++;
+            FDB_CHECK_LAUNCH();
+            FDB_CUDA(cudaStreamSynchronize(st));
+        } else {
+            fs->rec.release();
+            fs->rb = 0;
+        }
+    }
     if (!(std::isfinite(hb[0]) && std::isfinite(hb[1]) && hb[0] < 1e30f && hb[1] < 1e30f))
         filter_free(ix);  // non-finite centroids or code vectors: exact pipeline only
     return FDB_OK;
@@ -730,9 +833,11 @@ int filter_query(fdb_index *ix, const float *d_q, size_t nq, size_t k, size_t np
     ctx->launches++;
     FDB_CHECK_LAUNCH();
 
-    const int chunk_vecs = scan_chunk_vecs(ix);
-    const size_t smem = scan_smem_bytes(ix, chunk_vecs);
-    const FScanFn scan = scan_fn(D);
+    const bool records = fs->rb != 0;
+    const size_t rb = records ? fs->rb : D;
+    const int chunk_vecs = scan_chunk_vecs(rb);
+    const size_t smem = scan_smem_bytes(ix, chunk_vecs, rb);
+    const FScanFn scan = scan_fn(D, records);
     FDB_CUDA(cudaFuncSetAttribute(scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // list capacity: k plus head room for the vectors inside the error band
     const int ncap = (int)std::min<size_t>(RCAP, k + 6);
@@ -754,17 +859,17 @@ int filter_query(fdb_index *ix, const float *d_q, size_t nq, size_t k, size_t np
         sp.G = fs->G.p;
         sp.pc = fs->pc.p;
         sp.Kq = fs->Kq.p;
-        sp.codes = ix->codes.p;
+        sp.codes = records ? fs->rec.p : ix->codes.p;
         sp.part_off = ix->part_off.p;
-        sp.part_cstart = ix->part_cstart.p;
+        sp.part_start = records ? fs->rec_start.p : ix->part_cstart.p;
         sp.probes = ix->probes.p;
+        sp.rb = (int)rb;
         sp.q0 = q0;
         sp.nprobe = (int)nprobe;
         sp.D = (int)D;
         sp.C = (int)C;
         sp.chunk_vecs = chunk_vecs;
         sp.ncap = ncap;
-        sp.use_gs = scan_use_gs(ix, chunk_vecs) ? 1 : 0;
         sp.cand_d = fs->cand_d.p;
         sp.cand_a = fs->cand_a.p;
         sp.cand_cnt = fs->cand_cnt.p;
