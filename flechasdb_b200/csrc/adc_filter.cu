@@ -32,6 +32,7 @@
 // <= eta = (s/16 + 40 + D) u relative, all terms being non-negative.
 #include "index.cuh"
 #include "nbest.cuh"
+#include "tc_gemm.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -47,6 +48,18 @@ struct FilterState {
     DevBuf<uint8_t> rec;         // records (RECORDS layout), empty when the lists are long
     DevBuf<uint64_t> rec_start;  // [P] byte offset of the partition's records, 16-byte aligned
     size_t rb = 0;               // bytes per record
+    DevBuf<float> mu;            // [N] centre of the coarse centroids (zeros when no GEMM runs on the tensor pipe)
+    DevBuf<float> zeros;         // [N]
+    // undecided queries of the whole batch (appended slice by slice, no host round trip in between)
+    DevBuf<uint32_t> bfb_q, bfb_probes;       // global query index, its probe list
+    DevBuf<unsigned long long> bcounters;     // [0] undecided, [1] exact candidates, [2] scanned vectors, [3] undecided with foreign probes
+    size_t bfb_cap = 0;
+    bool tc_g = false, tc_coarse = false;
+    TcCentroids cb_tc, coarse_tc;   // bf16 pieces of the centred code vectors / coarse centroids
+    TcRows rows;                    // bf16 pieces of the centred queries of the current batch
+    DevBuf<float> S;                // [nq][ldS] approximate coarse scores x'.c' - |c'|^2/2
+    DevBuf<unsigned> hard;          // [nq] the probe filter could not decide: exact pipeline
+    bool rows_ready = false, probes_from_filter = false;
     DevBuf<float> G;             // [chunk_q][D][C]
     DevBuf<float> Kq, Wq;        // [nq][nprobe], [nq]
     DevBuf<float> cand_d;        // [nq][32]
@@ -75,18 +88,28 @@ __device__ __forceinline__ double warp_sum(double v) {
 __device__ __forceinline__ unsigned abs_bits(float v) { return __float_as_uint(fabsf(v)); }
 
 // ---- per-index tables ------------------------------------------------------------------
-// PC[p][d][c] = 2 c_pd . cb_dc + |cb_dc|^2 (double accumulation, rounded once)
-__global__ void __launch_bounds__(256) pc_kernel(const float *coarse, const float *cb, size_t P, size_t D,
-                                                 size_t C, size_t s, float *pc) {
+// PC[p][d][c] = 2 (c_pd - mu_d) . cb_dc + |cb_dc|^2 (double accumulation, rounded once); G uses q - mu
+// column means of the coarse centroids
+__global__ void mu_kernel(const float *coarse, size_t P, size_t N, float *mu) {
+    const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= N) return;
+    double acc = 0.0;
+    for (size_t p = 0; p < P; ++p) acc += (double)coarse[p * N + c];
+    const float v = (float)(acc / (double)P);
+    mu[c] = (v == v && fabsf(v) < 3.0e38f) ? v : 0.0f;
+}
+__global__ void __launch_bounds__(256) pc_kernel(const float *coarse, const float *mu, const float *cb, size_t P,
+                                                 size_t D, size_t C, size_t s, float *pc) {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= P * D * C) return;
     const size_t p = t / (D * C), dc = t - p * D * C, d = dc / C;
     const float *cp = coarse + p * D * s + d * s;
+    const float *mp = mu + d * s;
     const float *cr = cb + dc * s;
     double acc = 0.0;
     for (size_t i = 0; i < s; ++i) {
         const double b = (double)cr[i];
-        acc += b * (2.0 * (double)cp[i] + b);
+        acc += b * (2.0 * ((double)cp[i] - (double)mp[i]) + b);
     }
     pc[t] = (float)acc;
 }
@@ -133,7 +156,7 @@ __global__ void __launch_bounds__(128) pcmax_kernel(const float *pc, size_t P, s
 }
 
 // ---- per-pair constants K = |fl(q - c_p)|^2 and the per-query magnitude W -----------------
-__global__ void __launch_bounds__(128) pair_const_kernel(const float *q, const float *coarse,
+__global__ void __launch_bounds__(128) pair_const_kernel(const float *q, const float *coarse, const float *mu,
                                                          const uint32_t *probes, const float *cbmax,
                                                          const unsigned *bounds, size_t nq, size_t N,
                                                          size_t D, size_t s, int nprobe, float *Kq,
@@ -160,7 +183,10 @@ __global__ void __launch_bounds__(128) pair_const_kernel(const float *q, const f
     double qc = 0.0;
     for (size_t d = 0; d < D; ++d) {
         double acc = 0.0;
-        for (size_t i = lane; i < s; i += 32) acc += (double)qv[d * s + i] * (double)qv[d * s + i];
+        for (size_t i = lane; i < s; i += 32) {
+            const double x = (double)__fsub_rn(qv[d * s + i], mu[d * s + i]);
+            acc += x * x;
+        }
         acc = warp_sum(acc);
         qc += 2.0 * sqrt(acc) * (double)cbmax[d];
     }
@@ -176,6 +202,7 @@ constexpr int GM = 128, GN = 128, GK = 8, G_THREADS = 256;
 
 template <bool VEC>
 __global__ void __launch_bounds__(G_THREADS, 2) adc_gemm_kernel(const float *__restrict__ q, size_t nq, size_t N,
+                                                                const float *__restrict__ mu,
                                                                 const float *__restrict__ cb, size_t C,
                                                                 size_t s, size_t D, float *__restrict__ G) {
     __shared__ __align__(16) float As[2][GK][GM];
@@ -188,6 +215,7 @@ __global__ void __launch_bounds__(G_THREADS, 2) adc_gemm_kernel(const float *__r
     if (ar >= nq) ar = nq - 1;
     if (br >= C) br = C - 1;
     const float *ap = q + ar * N + d * s;
+    const float *mp = mu + d * s;
     const float *bp = cb + (d * C + br) * s;
     const int nk = (int)((s + GK - 1) / GK);
 
@@ -196,8 +224,10 @@ __global__ void __launch_bounds__(G_THREADS, 2) adc_gemm_kernel(const float *__r
         if (VEC) {
             if (k0 < s) {
                 const float4 av = *reinterpret_cast<const float4 *>(ap + k0);
+                const float4 mv = *reinterpret_cast<const float4 *>(mp + k0);
                 const float4 bv = *reinterpret_cast<const float4 *>(bp + k0);
-                a[0] = av.x, a[1] = av.y, a[2] = av.z, a[3] = av.w;
+                a[0] = __fsub_rn(av.x, mv.x), a[1] = __fsub_rn(av.y, mv.y);
+                a[2] = __fsub_rn(av.z, mv.z), a[3] = __fsub_rn(av.w, mv.w);
                 b[0] = bv.x, b[1] = bv.y, b[2] = bv.z, b[3] = bv.w;
             } else {
 #pragma unroll
@@ -206,7 +236,7 @@ __global__ void __launch_bounds__(G_THREADS, 2) adc_gemm_kernel(const float *__r
         } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                a[j] = k0 + j < s ? ap[k0 + j] : 0.0f;
+                a[j] = k0 + j < s ? __fsub_rn(ap[k0 + j], mp[k0 + j]) : 0.0f;
                 b[j] = k0 + j < s ? bp[k0 + j] : 0.0f;
             }
         }
@@ -293,6 +323,7 @@ struct FScanParams {
     uint32_t *cand_a;           // position in the concatenation of the probed lists
     uint32_t *cand_cnt, *cand_total;
     unsigned *qbad;
+    const unsigned *hard;       // [nq] set by the probe filter
     unsigned long long *counters;
 };
 
@@ -496,7 +527,7 @@ __global__ void __launch_bounds__(FS_WARPS * 32) fscan_kernel(FScanParams p) {
     if (lane == 0) {
         p.cand_cnt[q] = (uint32_t)sel.len;
         p.cand_total[q] = flat0;
-        p.qbad[q] = (unsigned)anybad;
+        p.qbad[q] = (unsigned)anybad | (p.hard[q] ? 2u : 0u);
         atomicAdd(&p.counters[2], (unsigned long long)flat0);
     }
 }
@@ -520,6 +551,139 @@ __global__ void __launch_bounds__(256) records_kernel(const uint8_t *codes, cons
         }
         for (size_t d = D; d < dpad; ++d) dst[d] = 0;
         *reinterpret_cast<float *>(dst + dpad) = (float)acc;
+    }
+}
+
+// ---- probe filter: the nprobe nearest partitions from approximate scores ----------------------
+// S[q][p] ~ x'.c'_p - |c'_p|^2/2 from the tensor pipe (error <= E, see tc_assign.cu).  The
+// nprobe best scores plus everything inside the band are evaluated exactly (reference order,
+// src/db/stored.rs:413-424) and sorted; the result is the reference's probe list when the
+// exact distances around the boundary are distinct.  Otherwise (ties, NaN, overfull band) the
+// query is marked hard and answered by the exact pipeline.
+struct ProbeParams {
+    const float *S;
+    size_t ldS;
+    const float *xn2;           // [D][nq] |x'_d|^2
+    size_t D;
+    const unsigned *cmax2;      // [ntiles] bits of max |c'|^2
+    size_t ntiles;
+    const float *q, *coarse;
+    size_t nq, P, N;
+    int nprobe, ncap;
+    float gamma1, eta;
+    uint32_t *probes;
+    float *probe_d;
+    unsigned *hard;
+};
+
+template <typename F>
+__device__ __forceinline__ float halfwarp_dot16(size_t m, int j, int hbase, F term) {
+    if (m < 16) {  // dot_naive, src/linalg.rs:43-53
+        float T = 0.0f;
+        for (size_t e = 0; e < m; ++e) T = __fadd_rn(T, term(e));
+        return T;
+    }
+    const size_t r = m & 15;
+    float acc = 0.0f;
+    if ((size_t)j < r) acc = term((size_t)j);
+    for (size_t base = r; base < m; base += 16) acc = __fadd_rn(acc, term(base + j));
+    float T = 0.0f;  // sum_naive over the 16 accumulators, src/linalg.rs:39
+#pragma unroll
+    for (int l = 0; l < 16; ++l) T = __fadd_rn(T, __shfl_sync(0xffffffffu, acc, hbase + l));
+    return T;
+}
+
+__global__ void __launch_bounds__(128) probe_filter_kernel(ProbeParams p) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t q = (size_t)blockIdx.x * 4 + warp;
+    if (q >= p.nq) return;
+    float xn2 = 0.0f;
+    for (size_t d = 0; d < p.D; ++d) xn2 += p.xn2[d * p.nq + q];
+    xn2 *= 1.0001f;
+    unsigned cb = 0;
+    for (size_t t = 0; t < p.ntiles; ++t) cb = max(cb, p.cmax2[t]);
+    const float cmax2 = __uint_as_float(cb);
+    const float E = p.gamma1 * sqrtf(xn2 * cmax2) * 1.0001f + 1.2e-7f * (0.5f * cmax2);
+    // the ncap largest scores (key = -s ascending)
+    RegTopK sel;
+    sel.init(p.ncap);
+    bool bad = !(xn2 < 1e30f);
+    const float *Sq = p.S + q * p.ldS;
+    for (size_t base = 0; base < p.P; base += 32) {
+        const size_t pi = base + lane;
+        const bool valid = pi < p.P;
+        const float sv = valid ? Sq[pi] : 0.0f;
+        bad |= valid && !(fabsf(sv) < 1e30f);
+        const uint32_t key = fkey(-sv);
+        const bool want = valid && key < sel.maxkey;
+        if (__any_sync(0xffffffffu, want)) push_lanes(sel, key, (uint32_t)pi, want, lane);
+    }
+    const int cnt = sel.len;
+    // sort: lane r receives the entry of rank r
+    int rank = 0;
+    for (int j = 0; j < cnt; ++j) {
+        const uint32_t kj = __shfl_sync(0xffffffffu, sel.key, j);
+        rank += (kj < sel.key) || (kj == sel.key && j < lane);
+    }
+    int src = 0;
+    for (int j = 0; j < cnt; ++j) {
+        const int rj = __shfl_sync(0xffffffffu, rank, j);
+        if (rj == lane) src = j;
+    }
+    const float ss = -fkey_inv(__shfl_sync(0xffffffffu, sel.key, src));   // descending scores
+    const uint32_t part = __shfl_sync(0xffffffffu, sel.a, src);
+    bool hard = __any_sync(0xffffffffu, bad);
+    int ncand = cnt;
+    if (cnt > p.nprobe) {
+        const float s_tau = __shfl_sync(0xffffffffu, ss, p.nprobe - 1);
+        const float dtau = fmaxf(0.0f, xn2 - 2.0f * s_tau + 2.0f * E);
+        const float shift = 1.3e-7f * sqrtf(dtau) * (sqrtf(xn2) + sqrtf(cmax2));
+        const float band = 2.0f * (2.0f * E + 1.01f * p.eta * dtau + shift);
+        const float thr = s_tau - band;
+        if (!(fabsf(thr) < 1e30f)) hard = true;
+        ncand = __popc(__ballot_sync(0xffffffffu, lane < cnt && ss >= thr));
+        if (ncand == p.ncap && p.P > (size_t)p.ncap) hard = true;
+    }
+    float myD = 0.0f;
+    if (!hard) {
+        const int half = lane >> 4, j = lane & 15, hbase = half * 16;
+        const float *qv = p.q + q * p.N;
+        for (int i = 0; 2 * i < ncand; ++i) {
+            const int c = 2 * i + half;
+            const uint32_t pc = __shfl_sync(0xffffffffu, part, c < ncand ? c : 0);
+            const float *cv = p.coarse + (size_t)pc * p.N;
+            const float T = halfwarp_dot16(p.N, j, hbase, [&](size_t e) {
+                const float d = __fsub_rn(qv[e], cv[e]);
+                return __fmul_rn(d, d);
+            });
+            const float v = __shfl_sync(0xffffffffu, T, (lane & 1) * 16);
+            if ((lane >> 1) == i) myD = v;
+        }
+        const bool mine = lane < ncand;
+        rank = 0;
+        bool tie = false;
+        for (int jx = 0; jx < ncand; ++jx) {
+            const float Dj = __shfl_sync(0xffffffffu, myD, jx);
+            const uint32_t pj = __shfl_sync(0xffffffffu, part, jx);
+            rank += (Dj < myD) || (Dj == myD && pj < part);
+            tie |= (Dj == myD) && jx != lane;
+        }
+        // NaN, or a tie that involves one of the nprobe nearest (which survives / in which order
+        // depends on NBestByKey's push history)
+        if (__any_sync(0xffffffffu, mine && ((myD != myD) || (tie && rank < p.nprobe)))) hard = true;
+    }
+    if (hard) {
+        // placeholders that keep the later kernels in bounds; the query is redone exactly
+        if (lane < p.nprobe) {
+            p.probes[q * p.nprobe + lane] = part;
+            p.probe_d[q * p.nprobe + lane] = xn2 - 2.0f * ss;
+        }
+        if (lane == 0) p.hard[q] = 1u;
+        return;
+    }
+    if (lane < ncand && rank < p.nprobe) {
+        p.probes[q * p.nprobe + rank] = part;
+        p.probe_d[q * p.nprobe + rank] = myD;
     }
 }
 
@@ -578,7 +742,10 @@ __global__ void __launch_bounds__(128) fselect_kernel(FSelParams p) {
         if (ncand == p.ncap && total > (uint32_t)p.ncap) fb = true;  // the list may be incomplete
     }
     if (fb) {
-        if (lane == 0) p.fb_list[atomicAdd(&p.counters[0], 1ull)] = (uint32_t)q;
+        if (lane == 0) {
+            p.fb_list[atomicAdd(&p.counters[0], 1ull)] = (uint32_t)q;
+            if (p.qbad[q] & 2u) atomicAdd(&p.counters[3], 1ull);  // its probes are not the reference's
+        }
         return;
     }
     // position in the concatenated lists -> (partition, vector_index)
@@ -704,6 +871,27 @@ __global__ void __launch_bounds__(128) fselect_kernel(FSelParams p) {
     }
 }
 
+// ---- slice -> batch: undecided queries with their probe lists, statistics -----------------------
+__global__ void __launch_bounds__(256) stash_undecided_kernel(const unsigned long long *counters, const uint32_t *fb_list,
+                                                              const uint32_t *probes, size_t q_base, int nprobe,
+                                                              unsigned long long *bcounters, uint32_t *bfb_q,
+                                                              uint32_t *bfb_probes) {
+    const unsigned n = (unsigned)counters[0];
+    const unsigned long long base = bcounters[0];   // one CTA, slices run in stream order
+    for (unsigned i = threadIdx.x; i < n * (unsigned)nprobe; i += blockDim.x) {
+        const unsigned r = i / nprobe, e = i - r * nprobe;
+        bfb_probes[(base + r) * nprobe + e] = probes[(size_t)fb_list[r] * nprobe + e];
+        if (e == 0) bfb_q[base + r] = (uint32_t)(q_base + fb_list[r]);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        bcounters[0] = base + n;
+        bcounters[1] += counters[1];
+        bcounters[2] += counters[2];
+        bcounters[3] += counters[3];
+    }
+}
+
 size_t scan_smem_bytes(const fdb_index *ix, int chunk_vecs, size_t rb) {
     return ix->D * TSTRIDE * 4 + (size_t)FS_WARPS * 2 * chunk_vecs * rb + 16;
 }
@@ -755,10 +943,28 @@ int filter_prepare(fdb_index *ix) {
     FDB_TRY(fs->cbmax.alloc(D));
     FDB_TRY(fs->bounds.alloc(2));
     FDB_TRY(fs->counters.alloc(4));
+    FDB_TRY(fs->bcounters.alloc(4));
     FDB_CUDA(cudaMallocHost((void **)&fs->h_counters, 4 * sizeof(unsigned long long)));
     FDB_CUDA(cudaMemsetAsync(fs->bounds.p, 0, 2 * sizeof(unsigned), st));
-    pc_kernel<<<(unsigned)((P * D * C + 255) / 256), 256, 0, st>>>(ix->coarse.p, ix->codebooks.p, P, D, C, s,
-                                                                  fs->pc.p);
+    // which GEMMs run on the tensor pipe (tcgen05, bf16 3-term split); both operands are then
+    // centred by the mean of the coarse centroids, which shrinks |x'| |c'| and with it the band
+    const size_t N = ix->N;
+    const size_t kc = std::min<size_t>(P, 256), ntiles = (P + kc - 1) / kc;
+    fs->tc_coarse = tc_shape_ok(kc, N, N) && !getenv("FDB_FILTER_NO_TC_COARSE");
+    fs->tc_g = tc_shape_ok(C, s, N) && C % 64 == 0 && !getenv("FDB_FILTER_NO_TC_TABLES");
+    FDB_TRY(fs->mu.alloc(N));
+    FDB_CUDA(cudaMemsetAsync(fs->mu.p, 0, N * sizeof(float), st));
+    if (fs->tc_coarse || fs->tc_g) {
+        mu_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(ix->coarse.p, P, N, fs->mu.p);
+        ctx->launches++;
+    }
+    if (fs->tc_coarse) FDB_TRY(tc_prepare_centroids(ctx, ix->coarse.p, ntiles, kc, N, fs->mu.p, 0, P, &fs->coarse_tc));
+    // the code vectors are not shifted: G = -2 (q - mu) . cb, the mu . cb part lives in PC
+    FDB_TRY(fs->zeros.alloc(N));
+    FDB_CUDA(cudaMemsetAsync(fs->zeros.p, 0, N * sizeof(float), st));
+    if (fs->tc_g) FDB_TRY(tc_prepare_centroids(ctx, ix->codebooks.p, D, C, s, fs->zeros.p, 0, D * C, &fs->cb_tc));
+    pc_kernel<<<(unsigned)((P * D * C + 255) / 256), 256, 0, st>>>(ix->coarse.p, fs->mu.p, ix->codebooks.p, P, D, C,
+                                                                  s, fs->pc.p);
     cbmax_kernel<<<(unsigned)D, 256, 0, st>>>(ix->codebooks.p, C, s, fs->cbmax.p, fs->bounds.p);
     pcmax_kernel<<<(unsigned)((P * 32 + 127) / 128), 128, 0, st>>>(fs->pc.p, P, D, C, fs->bounds.p);
     ctx->launches += 3;
@@ -807,14 +1013,90 @@ bool filter_eligible(const fdb_index *ix, size_t nq, size_t k, size_t nprobe) {
            nq * RCAP < (1ull << 32) && ix->M < (1ull << 32) && nprobe <= 4096;
 }
 
-int filter_query(fdb_index *ix, const float *d_q, size_t nq, size_t k, size_t nprobe, uint32_t *d_p,
-                 uint32_t *d_v, float *d_d, uint32_t *d_c, EventLog *log, const uint32_t **d_fb_list,
-                 unsigned *h_nfb) {
+// probes through the tensor pipe + the probe filter; *done = false when the shape is not taken
+int filter_probe(fdb_index *ix, const float *d_q, size_t nq, size_t nprobe, EventLog *log, bool *done) {
+    fdb_ctx *ctx = ix->ctx;
+    FilterState *fs = ix->filter;
+    cudaStream_t st = ctx->stream;
+    const size_t N = ix->N, P = ix->P, D = ix->D, s = ix->s;
+    *done = false;
+    fs->rows_ready = false;
+    fs->probes_from_filter = false;
+    FDB_TRY(fs->hard.ensure(nq));
+    FDB_CUDA(cudaMemsetAsync(fs->hard.p, 0, nq * sizeof(unsigned), st));
+    if (!fs->tc_coarse || nprobe > 24 || (uintptr_t)d_q % 16 != 0) return FDB_OK;
+    FDB_TRY(log->mark(0));
+    FDB_TRY(tc_prepare_rows(ctx, d_q, nq, N, s, D, fs->mu.p, &fs->rows));
+    fs->rows_ready = true;
+    const size_t ldS = fs->coarse_tc.nb * fs->coarse_tc.np;
+    FDB_TRY(fs->S.ensure(nq * ldS));
+    FDB_TRY(tc_gemm_raw(ctx, fs->rows, fs->coarse_tc, 0, 1.0f, 1, fs->S.p, ldS, fs->coarse_tc.np));
+    FDB_TRY(log->mark(1));
+    FDB_TRY(ix->probes.ensure(nq * nprobe));
+    FDB_TRY(ix->probe_d.ensure(nq * nprobe));
+    ProbeParams pp;
+    pp.S = fs->S.p;
+    pp.ldS = ldS;
+    pp.xn2 = fs->rows.xn2.p;
+    pp.D = D;
+    pp.cmax2 = fs->coarse_tc.cmax2.p;
+    pp.ntiles = fs->coarse_tc.nb;
+    pp.q = d_q;
+    pp.coarse = ix->coarse.p;
+    pp.nq = nq;
+    pp.P = P;
+    pp.N = N;
+    pp.nprobe = (int)nprobe;
+    pp.ncap = (int)std::min<size_t>(RCAP, nprobe + 8);
+    pp.gamma1 = tc_gamma(N);
+    pp.eta = ((float)N / 16.0f + 20.0f) * U24;   // the reference's own f32 evaluation of one distance
+    pp.probes = ix->probes.p;
+    pp.probe_d = ix->probe_d.p;
+    pp.hard = fs->hard.p;
+    probe_filter_kernel<<<(unsigned)((nq + 3) / 4), 128, 0, st>>>(pp);
+    ctx->launches++;
+    FDB_CHECK_LAUNCH();
+    fs->probes_from_filter = true;
+    *done = true;
+    return FDB_OK;
+}
+
+int filter_batch_begin(fdb_index *ix, size_t nq_total, size_t nprobe) {
+    FilterState *fs = ix->filter;
+    FDB_TRY(fs->bfb_q.ensure(nq_total));
+    FDB_TRY(fs->bfb_probes.ensure(nq_total * nprobe));
+    fs->bfb_cap = nq_total;
+    FDB_CUDA(cudaMemsetAsync(fs->bcounters.p, 0, 4 * sizeof(unsigned long long), ix->ctx->stream));
+    return FDB_OK;
+}
+
+int filter_batch_end(fdb_index *ix, size_t nq_total, const uint32_t **d_fb_q, const uint32_t **d_fb_probes,
+                     unsigned *h_nfb, unsigned *h_nhard) {
+    FilterState *fs = ix->filter;
+    cudaStream_t st = ix->ctx->stream;
+    FDB_CUDA(cudaMemcpyAsync(fs->h_counters, fs->bcounters.p, 4 * sizeof(unsigned long long),
+                             cudaMemcpyDeviceToHost, st));
+    FDB_CUDA(cudaStreamSynchronize(st));
+    *h_nfb = (unsigned)fs->h_counters[0];
+    *h_nhard = (unsigned)fs->h_counters[3];
+    *d_fb_q = fs->bfb_q.p;
+    *d_fb_probes = fs->bfb_probes.p;
+    ix->last_stats[0] = nq_total - fs->h_counters[0];
+    ix->last_stats[1] = fs->h_counters[0];
+    ix->last_stats[2] = fs->h_counters[1];
+    ix->last_stats[3] = fs->h_counters[2];
+    return FDB_OK;
+}
+
+int filter_query(fdb_index *ix, const float *d_q, size_t q_base, size_t nq, size_t k, size_t nprobe, uint32_t *d_p,
+                 uint32_t *d_v, float *d_d, uint32_t *d_c, EventLog *log) {
     fdb_ctx *ctx = ix->ctx;
     FilterState *fs = ix->filter;
     cudaStream_t st = ctx->stream;
     const size_t N = ix->N, D = ix->D, C = ix->C, s = ix->s, DC = D * C;
-    const size_t chunk = std::min(nq, fs->chunk_q);
+    const bool tc_g = fs->tc_g && (uintptr_t)d_q % 16 == 0;
+    // the tensor-pipe GEMM writes whole 128-row tiles of the batch: no chunking of G then
+    const size_t chunk = tc_g ? nq : std::min(nq, fs->chunk_q);
     FDB_TRY(fs->G.ensure(chunk * DC));
     FDB_TRY(fs->Kq.ensure(nq * nprobe));
     FDB_TRY(fs->Wq.ensure(nq));
@@ -824,11 +1106,12 @@ int filter_query(fdb_index *ix, const float *d_q, size_t nq, size_t k, size_t np
     FDB_TRY(fs->cand_total.ensure(nq));
     FDB_TRY(fs->qbad.ensure(nq));
     FDB_TRY(fs->fb_list.ensure(nq));
+    FDB_TRY(fs->hard.ensure(nq));
     FDB_CUDA(cudaMemsetAsync(fs->counters.p, 0, 4 * sizeof(unsigned long long), st));
 
     FDB_TRY(log->mark(2));
     pair_const_kernel<<<(unsigned)((nq * 32 + 127) / 128), 128, 0, st>>>(
-        d_q, ix->coarse.p, ix->probes.p, fs->cbmax.p, fs->bounds.p, nq, N, D, s, (int)nprobe, fs->Kq.p,
+        d_q, ix->coarse.p, fs->mu.p, ix->probes.p, fs->cbmax.p, fs->bounds.p, nq, N, D, s, (int)nprobe, fs->Kq.p,
         fs->Wq.p);
     ctx->launches++;
     FDB_CHECK_LAUNCH();
@@ -842,18 +1125,27 @@ int filter_query(fdb_index *ix, const float *d_q, size_t nq, size_t k, size_t np
     // list capacity: k plus head room for the vectors inside the error band
     const int ncap = (int)std::min<size_t>(RCAP, k + 6);
     const bool vec = (s % 4 == 0) && (N % 4 == 0) && ((uintptr_t)d_q % 16 == 0);
-    const double gamma = (double)s * U24 / (1.0 - (double)s * U24);
+    const double gamma = tc_g ? (double)tc_gamma(s) : (double)s * U24 / (1.0 - (double)s * U24);
     const float coef = (float)((2.0 * gamma + (double)(D + 4) * U24) * 1.01);
     const float eta3 = (float)(2.1 * ((double)s / 16.0 + 40.0 + (double)D) * U24);
 
     for (size_t q0 = 0; q0 < nq; q0 += chunk) {
         const size_t nc = std::min(chunk, nq - q0);
         FDB_TRY(log->mark(3));
-        dim3 grid((unsigned)((nc + GM - 1) / GM), (unsigned)((C + GN - 1) / GN), (unsigned)D);
-        if (vec) adc_gemm_kernel<true><<<grid, G_THREADS, 0, st>>>(d_q + q0 * N, nc, N, ix->codebooks.p, C, s, D, fs->G.p);
-        else adc_gemm_kernel<false><<<grid, G_THREADS, 0, st>>>(d_q + q0 * N, nc, N, ix->codebooks.p, C, s, D, fs->G.p);
-        ctx->launches++;
-        FDB_CHECK_LAUNCH();
+        if (tc_g) {
+            // G[q][d][c] = -2 x'_d . cb_dc on the tensor pipe (problem d = division d)
+            if (!fs->rows_ready) {
+                FDB_TRY(tc_prepare_rows(ctx, d_q, nq, N, s, D, fs->mu.p, &fs->rows));
+                fs->rows_ready = true;
+            }
+            FDB_TRY(tc_gemm_raw(ctx, fs->rows, fs->cb_tc, s, -2.0f, 0, fs->G.p, DC, C));
+        } else {
+            dim3 grid((unsigned)((nc + GM - 1) / GM), (unsigned)((C + GN - 1) / GN), (unsigned)D);
+            if (vec) adc_gemm_kernel<true><<<grid, G_THREADS, 0, st>>>(d_q + q0 * N, nc, N, fs->mu.p, ix->codebooks.p, C, s, D, fs->G.p);
+            else adc_gemm_kernel<false><<<grid, G_THREADS, 0, st>>>(d_q + q0 * N, nc, N, fs->mu.p, ix->codebooks.p, C, s, D, fs->G.p);
+            ctx->launches++;
+            FDB_CHECK_LAUNCH();
+        }
         FDB_TRY(log->mark(4));
         FScanParams sp;
         sp.G = fs->G.p;
@@ -875,6 +1167,7 @@ int filter_query(fdb_index *ix, const float *d_q, size_t nq, size_t k, size_t np
         sp.cand_cnt = fs->cand_cnt.p;
         sp.cand_total = fs->cand_total.p;
         sp.qbad = fs->qbad.p;
+        sp.hard = fs->hard.p;
         sp.counters = fs->counters.p;
         scan<<<(unsigned)nc, FS_WARPS * 32, smem, st>>>(sp);
         ctx->launches++;
@@ -916,15 +1209,10 @@ int filter_query(fdb_index *ix, const float *d_q, size_t nq, size_t k, size_t np
     fselect_kernel<<<(unsigned)((nq + 3) / 4), 128, fp.quad ? 4 * RCAP * D * sizeof(float) : 0, st>>>(fp);
     ctx->launches++;
     FDB_CHECK_LAUNCH();
-    FDB_CUDA(cudaMemcpyAsync(fs->h_counters, fs->counters.p, 4 * sizeof(unsigned long long),
-                             cudaMemcpyDeviceToHost, st));
-    FDB_CUDA(cudaStreamSynchronize(st));
-    *h_nfb = (unsigned)fs->h_counters[0];
-    *d_fb_list = fs->fb_list.p;
-    ix->last_stats[0] = nq - fs->h_counters[0];
-    ix->last_stats[1] = fs->h_counters[0];
-    ix->last_stats[2] = fs->h_counters[1];
-    ix->last_stats[3] = fs->h_counters[2];
+    stash_undecided_kernel<<<1, 256, 0, st>>>(fs->counters.p, fs->fb_list.p, ix->probes.p, q_base, (int)nprobe,
+                                              fs->bcounters.p, fs->bfb_q.p, fs->bfb_probes.p);
+    ctx->launches++;
+    FDB_CHECK_LAUNCH();
     return FDB_OK;
 }
 

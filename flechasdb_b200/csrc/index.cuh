@@ -20,6 +20,8 @@ struct fdb_index {
     fdb::DevBuf<float> q_dev, dist, loc, tables, part_d, out_d, probe_d;
     fdb::DevBuf<uint32_t> probes, part_v, part_cnt, out_p, out_v, out_c;
     std::vector<cudaEvent_t> events;
+    cudaStream_t copy_stream = nullptr;   // host->device copies of fdb_index_query, overlapped with the kernels
+    std::vector<cudaEvent_t> copy_events;
     float phase_ms[6] = {0, 0, 0, 0, 0, 0};
     uint64_t scan_bytes = 0;
     size_t last_npairs = 0;
@@ -74,8 +76,18 @@ struct EventLog {
 int filter_prepare(fdb_index *ix);
 void filter_free(fdb_index *ix);
 bool filter_eligible(const fdb_index *ix, size_t nq, size_t k, size_t nprobe);
-int filter_query(fdb_index *ix, const float *d_q, size_t nq, size_t k, size_t nprobe, uint32_t *d_p,
-                 uint32_t *d_v, float *d_d, uint32_t *d_c, EventLog *log, const uint32_t **d_fb_list,
-                 unsigned *h_nfb);
+// filter_probe: probe lists from approximate coarse scores (tensor pipe) + exact re-check;
+// *done = false when the shape is not taken (the caller then runs the exact probe kernels).
+// *h_nhard = queries among the *h_nfb handed back whose probe list is not the reference's.
+int filter_probe(fdb_index *ix, const float *d_q, size_t nq, size_t nprobe, EventLog *log, bool *done);
+// A batch is answered slice by slice (filter_probe + filter_query per slice, nothing waits on the
+// host); the queries a slice could not decide are appended, with their probe lists, to a batch
+// list that filter_batch_end hands to the exact pipeline.  *h_nhard = those among the *h_nfb
+// whose probe list is not the reference's.
+int filter_batch_begin(fdb_index *ix, size_t nq_total, size_t nprobe);
+int filter_query(fdb_index *ix, const float *d_q, size_t q_base, size_t nq, size_t k, size_t nprobe, uint32_t *d_p,
+                 uint32_t *d_v, float *d_d, uint32_t *d_c, EventLog *log);
+int filter_batch_end(fdb_index *ix, size_t nq_total, const uint32_t **d_fb_q, const uint32_t **d_fb_probes,
+                     unsigned *h_nfb, unsigned *h_nhard);
 
 }  // namespace fdb

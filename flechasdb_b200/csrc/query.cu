@@ -323,16 +323,11 @@ __global__ void __launch_bounds__(MERGE_WARPS * 32) merge_kernel(
 }
 
 // ---- hand-over of undecided queries between the filter path and the exact pipeline ------
-__global__ void gather_rows_kernel(const float *q, const uint32_t *probes, const uint32_t *list, size_t n,
-                                   size_t N, size_t nprobe, float *out_q, uint32_t *out_probes) {
+__global__ void gather_rows_kernel(const float *q, const uint32_t *list, size_t n, size_t N, float *out) {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < n * nprobe) {
-        const size_t r = t / nprobe, e = t - r * nprobe;
-        out_probes[t] = probes[(size_t)list[r] * nprobe + e];
-    }
     if (t >= n * N) return;
     const size_t r = t / N, e = t - r * N;
-    out_q[t] = q[(size_t)list[r] * N + e];
+    out[t] = q[(size_t)list[r] * N + e];
 }
 __global__ void scatter_results_kernel(const uint32_t *list, size_t n, size_t k, const uint32_t *fp,
                                        const uint32_t *fv, const float *fd, const uint32_t *fc,
@@ -522,6 +517,11 @@ void fdb_index_destroy(fdb_index *ix) {
     cudaSetDevice(ix->ctx->device);
     cudaStreamSynchronize(ix->ctx->stream);
     for (cudaEvent_t e : ix->events) cudaEventDestroy(e);
+    for (cudaEvent_t e : ix->copy_events) cudaEventDestroy(e);
+    if (ix->copy_stream) {
+        cudaStreamSynchronize(ix->copy_stream);
+        cudaStreamDestroy(ix->copy_stream);
+    }
     filter_free(ix);
     delete ix;
 }
@@ -664,19 +664,52 @@ int exact_after_probe(fdb_index *ix, const float *d_q, const uint32_t *d_probes,
 // The whole query.  Shapes the ADC filter path accepts go through it (adc_filter.cu); the
 // queries it cannot decide (exact ties, NaN, overfull band) and every other shape take the
 // exact pipeline, which reproduces the reference's selection slot by slot.
-int query_device(fdb_index *ix, const float *d_q, size_t nq, size_t k, size_t nprobe, int mode,
-                 uint32_t *d_p, uint32_t *d_v, float *d_d, uint32_t *d_c) {
-    fdb_ctx *ctx = ix->ctx;
-    EventLog log{ix};
+// A batch = begin, one or more slices (kernels only, nothing waits on the host), end.
+struct QueryBatch {
+    fdb_index *ix;
+    size_t nq_total, k, nprobe;
+    int mode;
+    bool filter;
+    EventLog log;
+};
+
+int batch_begin(QueryBatch &b) {
+    fdb_index *ix = b.ix;
     ix->scan_bytes = 0;
     ix->last_filter = false;
     for (int i = 0; i < 4; ++i) ix->last_stats[i] = 0;
+    b.filter = b.nq_total > 0 && filter_eligible(ix, b.nq_total, b.k, b.nprobe);
+    if (b.filter) FDB_TRY(filter_batch_begin(ix, b.nq_total, b.nprobe));
+    return FDB_OK;
+}
+
+// queries [q_base, q_base + nq) of the batch; d_q and the outputs point at the slice
+int batch_slice(QueryBatch &b, const float *d_q, size_t q_base, size_t nq, uint32_t *d_p, uint32_t *d_v,
+                float *d_d, uint32_t *d_c) {
+    fdb_index *ix = b.ix;
     if (nq == 0) return FDB_OK;
-    FDB_TRY(probe_device(ix, d_q, nq, nprobe, mode, &log));
-    if (filter_eligible(ix, nq, k, nprobe)) {
-        const uint32_t *d_fb = nullptr;
-        unsigned nfb = 0;
-        FDB_TRY(filter_query(ix, d_q, nq, k, nprobe, d_p, d_v, d_d, d_c, &log, &d_fb, &nfb));
+    bool probed = false;
+    if (b.filter) FDB_TRY(filter_probe(ix, d_q, nq, b.nprobe, &b.log, &probed));
+    if (!probed) FDB_TRY(probe_device(ix, d_q, nq, b.nprobe, b.mode, &b.log));
+    if (b.filter) {
+        FDB_TRY(filter_query(ix, d_q, q_base, nq, b.k, b.nprobe, d_p, d_v, d_d, d_c, &b.log));
+    } else {
+        FDB_TRY(exact_after_probe(ix, d_q, ix->probes.p, nq, b.k, b.nprobe, b.mode, d_p, d_v, d_d, d_c, b.log));
+        ix->last_npairs = nq * b.nprobe;
+        ix->last_stats[1] += nq;
+    }
+    return FDB_OK;
+}
+
+// d_q and the outputs point at the whole batch
+int batch_end(QueryBatch &b, const float *d_q, uint32_t *d_p, uint32_t *d_v, float *d_d, uint32_t *d_c) {
+    fdb_index *ix = b.ix;
+    fdb_ctx *ctx = ix->ctx;
+    const size_t k = b.k, nprobe = b.nprobe;
+    if (b.filter) {
+        const uint32_t *d_fb = nullptr, *d_fbp = nullptr;
+        unsigned nfb = 0, nhard = 0;
+        FDB_TRY(filter_batch_end(ix, b.nq_total, &d_fb, &d_fbp, &nfb, &nhard));
         ix->last_filter = true;
         if (nfb) {
             cudaStream_t st = ctx->stream;
@@ -685,29 +718,39 @@ int query_device(fdb_index *ix, const float *d_q, size_t nq, size_t k, size_t np
             FDB_TRY(ix->fb_v.ensure((size_t)nfb * k));
             FDB_TRY(ix->fb_d.ensure((size_t)nfb * k));
             FDB_TRY(ix->fb_c.ensure(nfb));
-            FDB_TRY(ix->fb_probes.ensure((size_t)nfb * nprobe));
-            // their probes are already selected (exactly): only steps 3-6 run again
-            gather_rows_kernel<<<(unsigned)(((size_t)nfb * std::max(ix->N, nprobe) + 255) / 256), 256, 0, st>>>(
-                d_q, ix->probes.p, d_fb, nfb, ix->N, nprobe, ix->fb_q.p, ix->fb_probes.p);
+            gather_rows_kernel<<<(unsigned)(((size_t)nfb * ix->N + 255) / 256), 256, 0, st>>>(d_q, d_fb, nfb, ix->N,
+                                                                                            ix->fb_q.p);
             ctx->launches++;
-            FDB_TRY(exact_after_probe(ix, ix->fb_q.p, ix->fb_probes.p, nfb, k, nprobe, mode, ix->fb_p.p,
-                                      ix->fb_v.p, ix->fb_d.p, ix->fb_c.p, log));
+            // their probes are already selected (exactly) unless the probe filter gave up on one
+            // of them: then steps 1-2 run again for the handed-back queries, else only steps 3-6
+            const uint32_t *fb_probes = d_fbp;
+            if (nhard) {
+                FDB_TRY(probe_device(ix, ix->fb_q.p, nfb, nprobe, b.mode, &b.log));
+                fb_probes = ix->probes.p;
+            }
+            FDB_TRY(exact_after_probe(ix, ix->fb_q.p, fb_probes, nfb, k, nprobe, b.mode, ix->fb_p.p, ix->fb_v.p,
+                                      ix->fb_d.p, ix->fb_c.p, b.log));
             scatter_results_kernel<<<(unsigned)(((size_t)nfb * k + 255) / 256), 256, 0, st>>>(
                 d_fb, nfb, k, ix->fb_p.p, ix->fb_v.p, ix->fb_d.p, ix->fb_c.p, d_p, d_v, d_d, d_c);
             ctx->launches++;
             FDB_CHECK_LAUNCH();
         }
-    } else {
-        FDB_TRY(exact_after_probe(ix, d_q, ix->probes.p, nq, k, nprobe, mode, d_p, d_v, d_d, d_c, log));
-        ix->last_npairs = nq * nprobe;
-        ix->last_stats[1] = nq;
     }
-    FDB_TRY(log.mark(-1));
+    FDB_TRY(b.log.mark(-1));
     if (ix->timing) {
         FDB_CUDA(cudaStreamSynchronize(ctx->stream));
-        FDB_TRY(log.finish());
+        FDB_TRY(b.log.finish());
     }
     return FDB_OK;
+}
+
+int query_device(fdb_index *ix, const float *d_q, size_t nq, size_t k, size_t nprobe, int mode,
+                 uint32_t *d_p, uint32_t *d_v, float *d_d, uint32_t *d_c) {
+    if (nq == 0) return FDB_OK;
+    QueryBatch b{ix, nq, k, nprobe, mode, false, EventLog{ix}};
+    FDB_TRY(batch_begin(b));
+    FDB_TRY(batch_slice(b, d_q, 0, nq, d_p, d_v, d_d, d_c));
+    return batch_end(b, d_q, d_p, d_v, d_d, d_c);
 }
 
 int finish_query(fdb_ctx *ctx) {
@@ -745,9 +788,38 @@ int fdb_index_query(fdb_index *ix, const float *queries, size_t nq, size_t k, si
     FDB_TRY(ix->out_v.ensure(nq * k));
     FDB_TRY(ix->out_d.ensure(nq * k));
     FDB_TRY(ix->out_c.ensure(nq));
-    FDB_CUDA(cudaMemcpyAsync(ix->q_dev.p, queries, nq * ix->N * sizeof(float), cudaMemcpyHostToDevice, st));
-    FDB_TRY(query_device(ix, ix->q_dev.p, nq, k, nprobe, mode, ix->out_p.p, ix->out_v.p, ix->out_d.p,
-                         ix->out_c.p));
+    // The batch is cut into slices: every slice's host->device copy is queued up front on a
+    // copy stream, the kernels of slice i wait only for copy i, so the copies of the later
+    // slices travel while the earlier ones are being answered.
+    // (two slices already hide half of the copy; more slices only add per-slice kernel tails)
+    size_t nslices = nq >= 4096 ? std::max<size_t>(2, (nq + 6143) / 6144) : 1;
+    size_t slice = (nq + nslices - 1) / nslices;
+    if (const char *e = getenv("FDB_QUERY_HOST_SLICE")) slice = (size_t)std::max(1L, atol(e));
+    nslices = (nq + slice - 1) / slice;
+    if (!ix->copy_stream) FDB_CUDA(cudaStreamCreateWithFlags(&ix->copy_stream, cudaStreamNonBlocking));
+    while (ix->copy_events.size() < nslices + 1) {
+        cudaEvent_t e;
+        FDB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ix->copy_events.push_back(e);
+    }
+    // the copy stream must not overwrite q_dev while an earlier call's kernels still read it
+    FDB_CUDA(cudaEventRecord(ix->copy_events[nslices], st));
+    FDB_CUDA(cudaStreamWaitEvent(ix->copy_stream, ix->copy_events[nslices], 0));
+    for (size_t i = 0; i < nslices; ++i) {
+        const size_t q0 = i * slice, nc = std::min(slice, nq - q0);
+        FDB_CUDA(cudaMemcpyAsync(ix->q_dev.p + q0 * ix->N, queries + q0 * ix->N, nc * ix->N * sizeof(float),
+                                 cudaMemcpyHostToDevice, ix->copy_stream));
+        FDB_CUDA(cudaEventRecord(ix->copy_events[i], ix->copy_stream));
+    }
+    QueryBatch b{ix, nq, k, nprobe, mode, false, EventLog{ix}};
+    FDB_TRY(batch_begin(b));
+    for (size_t i = 0; i < nslices; ++i) {
+        const size_t q0 = i * slice, nc = std::min(slice, nq - q0);
+        FDB_CUDA(cudaStreamWaitEvent(st, ix->copy_events[i], 0));
+        FDB_TRY(batch_slice(b, ix->q_dev.p + q0 * ix->N, q0, nc, ix->out_p.p + q0 * k, ix->out_v.p + q0 * k,
+                            ix->out_d.p + q0 * k, ix->out_c.p + q0));
+    }
+    FDB_TRY(batch_end(b, ix->q_dev.p, ix->out_p.p, ix->out_v.p, ix->out_d.p, ix->out_c.p));
     FDB_CUDA(cudaMemcpyAsync(out_partition, ix->out_p.p, nq * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     FDB_CUDA(cudaMemcpyAsync(out_vector_index, ix->out_v.p, nq * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     FDB_CUDA(cudaMemcpyAsync(out_sqdist, ix->out_d.p, nq * k * sizeof(float), cudaMemcpyDeviceToHost, st));

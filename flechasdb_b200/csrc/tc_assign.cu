@@ -27,9 +27,7 @@
 //   warp 2   TMEM allocator 512 columns = two accumulator stages of up to 256 columns
 //   warps 4-11 epilogue     tcgen05.ld 32x32b.x32, two passes (row max, band collection)
 #include "kmeans.cuh"
-
-#include <cuda.h>
-#include <cuda_bf16.h>
+#include "tc_gemm.cuh"
 
 #include <cstdlib>
 
@@ -186,18 +184,19 @@ __global__ void col_mean_kernel(const double *partial, size_t n, size_t c0, size
 
 // centroids: f32 -> two bf16 pieces [nb*k][m], h_j = |c_j|^2/2, cmax_b = max_j |c_j| (rounded up)
 __global__ void __launch_bounds__(128) prep_centroids_kernel(const float *c, size_t k, size_t m, size_t np,
-                                                             const float *mu, size_t col_off,
+                                                             const float *mu, size_t col_off, size_t mu_stride,
+                                                             size_t ktotal,
                                                              __nv_bfloat16 *c1, __nv_bfloat16 *c2,
                                                              float *h, unsigned *cmax2_bits,
                                                              const int *active) {
     const size_t b = blockIdx.y, j = blockIdx.x;
     if (active && !active[b]) return;
-    if (j >= k) {  // padded columns never win: s = acc - inf
+    if (j >= k || b * k + j >= ktotal) {  // padded columns never win: s = acc - inf
         if (threadIdx.x == 0) h[b * np + j] = __int_as_float(0x7f800000);
         return;
     }
     const float *cr = c + (b * k + j) * m;
-    const float *mr = mu + col_off + b * m;
+    const float *mr = mu + col_off + b * mu_stride;
     double acc = 0.0;
     for (size_t e = threadIdx.x; e < m; e += blockDim.x) {
         const float v = __fsub_rn(cr[e], mr[e]);
@@ -221,6 +220,13 @@ __global__ void __launch_bounds__(128) prep_centroids_kernel(const float *c, siz
 
 struct TcParams {
     size_t n, m, nb, k, col_off;
+    size_t xcol_stride;         // operand columns of problem b start at col_off + b * xcol_stride
+    size_t crow_stride;         // centroid rows of problem b start at b * crow_stride
+    int mode;                   // 0: assignment epilogue, 1: raw scores out = alpha * acc - (sub_h ? h : 0)
+    float *out;                 // mode 1: out[row * out_row_stride + b * out_b_stride + col]
+    size_t out_row_stride, out_b_stride;
+    float alpha;
+    int sub_h;
     int np;                     // padded N (multiple of 64, <= 256)
     int row_tiles;              // ceil(n / 128)
     int stages;
@@ -296,8 +302,8 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
                 const int b = t / p.row_tiles, rt = t - b * p.row_tiles;
                 if (p.active && !p.active[b]) continue;
                 const int row0 = rt * BM;
-                const int kcol0 = (int)(p.col_off + (size_t)b * p.m);
-                const int crow0 = (int)((size_t)b * p.k);
+                const int kcol0 = (int)(p.col_off + (size_t)b * p.xcol_stride);
+                const int crow0 = (int)((size_t)b * p.crow_stride);
                 for (int kc = 0; kc < kchunks; ++kc) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     unsigned char *st = smem + (size_t)stage * stage_bytes;
@@ -372,7 +378,7 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
             // h_j = |c'_j|^2/2 of this problem in shared memory (reloaded when the problem changes)
             if (b != h_loaded) {
                 asm volatile("bar.sync 1, 256;" ::: "memory");  // nobody still reads the old values
-                for (int j = et; j < NP; j += EPI_THREADS) h_s[j] = p.h[(size_t)b * NP + j];
+                for (int j = et; j < NP; j += EPI_THREADS) h_s[j] = p.h ? p.h[(size_t)b * NP + j] : 0.0f;
                 h_loaded = b;
                 asm volatile("bar.sync 1, 256;" ::: "memory");
             }
@@ -380,6 +386,34 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
             mbar_wait(&tmem_full[as], aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (uint32_t)(as * NP + hf * half) + ((uint32_t)(32 * q) << 16);
+            if (p.mode == 1) {
+                // raw scores: every thread streams its half row out of TMEM, 32 columns at a time
+                float *orow = p.out + grow * p.out_row_stride + (size_t)b * p.out_b_stride + hf * half;
+                float va[32];
+                for (int c0 = 0; c0 < half; c0 += 32) {
+                    tmem_ld32_issue(taddr + c0, va);
+                    tmem_ld_wait();
+                    if (valid) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            float4 o;
+                            o.x = p.alpha * va[i] - (p.sub_h ? hb[c0 + i] : 0.0f);
+                            o.y = p.alpha * va[i + 1] - (p.sub_h ? hb[c0 + i + 1] : 0.0f);
+                            o.z = p.alpha * va[i + 2] - (p.sub_h ? hb[c0 + i + 2] : 0.0f);
+                            o.w = p.alpha * va[i + 3] - (p.sub_h ? hb[c0 + i + 3] : 0.0f);
+                            *reinterpret_cast<float4 *>(orow + c0 + i) = o;
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[as]);
+                if (++as == 2) {
+                    as = 0;
+                    aphase ^= 1;
+                }
+                continue;
+            }
             // pass 1 (software pipelined TMEM loads): the two largest s = acc - h and the argmax
             const float NEG_INF = -__int_as_float(0x7f800000);
             float m1 = NEG_INF, m2 = NEG_INF;
@@ -691,8 +725,8 @@ int tc_reassign(fdb_km *km, const int *d_active) {
     FDB_CUDA(cudaMemsetAsync(tc->stats.p, 0, 2 * sizeof(unsigned), st));
     {
         dim3 grid((unsigned)np, (unsigned)nb);
-        prep_centroids_kernel<<<grid, 128, 0, st>>>(km->centroids.p, k, m, (size_t)np, tc->mu.p, km->col_off,
-                                                    tc->c1.p, tc->c2.p,
+        prep_centroids_kernel<<<grid, 128, 0, st>>>(km->centroids.p, k, m, (size_t)np, tc->mu.p, km->col_off, m,
+                                                    nb * k, tc->c1.p, tc->c2.p,
                                                     tc->h.p, tc->cmax2.p, d_active);
         ctx->launches++;
         FDB_CHECK_LAUNCH();
@@ -703,6 +737,13 @@ int tc_reassign(fdb_km *km, const int *d_active) {
     p.nb = nb;
     p.k = k;
     p.col_off = km->col_off;
+    p.xcol_stride = m;
+    p.crow_stride = k;
+    p.mode = 0;
+    p.out = nullptr;
+    p.out_row_stride = p.out_b_stride = 0;
+    p.alpha = 1.0f;
+    p.sub_h = 1;
     p.np = np;
     p.row_tiles = (int)((n + BM - 1) / BM);
     const size_t stage_bytes = 2 * (size_t)BM * BK * 2 + 2 * (size_t)np * BK * 2;
@@ -743,6 +784,96 @@ int tc_reassign(fdb_km *km, const int *d_active) {
         for (int i = 0; i < 3; ++i) tc->last_stats[i] = hs[i];
         fprintf(stderr, "[fdb tc] rows=%zu recheck=%u overflow=%u\n", nb * n, hs[2], hs[1]);
     }
+    return FDB_OK;
+}
+
+// ---- query-side GEMMs (tc_gemm.cuh) ---------------------------------------------------------
+bool tc_shape_ok(size_t k, size_t m, size_t ld) {
+    return !getenv("FDB_DISABLE_TC") && k >= 1 && k <= 256 && m % BK == 0 && ld % 8 == 0;
+}
+
+float tc_gamma(size_t m) {
+    // split error 3*2^-18 + fp32 accumulation in the tensor pipe, (3m/16) MMAs at <= 2^-21 each
+    return 3.0f * 3.8146973e-06f + (3.0f * (float)m / 16.0f) * 4.7683716e-07f;
+}
+
+int tc_prepare_centroids(fdb_ctx *ctx, const float *c, size_t nb, size_t k, size_t m, const float *mu,
+                         size_t mu_stride, size_t ktotal, TcCentroids *out) {
+    cudaStream_t st = ctx->stream;
+    const int np = (int)((k + 63) / 64 * 64);
+    out->nb = nb;
+    out->k = k;
+    out->m = m;
+    out->np = np;
+    const size_t rows = nb * k + 256;  // slack: the last problem's box reads past its rows
+    FDB_TRY(out->c1.alloc(rows * m));
+    FDB_TRY(out->c2.alloc(rows * m));
+    FDB_TRY(out->h.alloc(nb * np));
+    FDB_TRY(out->cmax2.alloc(nb));
+    FDB_CUDA(cudaMemsetAsync(out->c1.p, 0, rows * m * 2, st));
+    FDB_CUDA(cudaMemsetAsync(out->c2.p, 0, rows * m * 2, st));
+    FDB_CUDA(cudaMemsetAsync(out->cmax2.p, 0, nb * sizeof(unsigned), st));
+    dim3 grid((unsigned)np, (unsigned)nb);
+    prep_centroids_kernel<<<grid, 128, 0, st>>>(c, k, m, (size_t)np, mu, 0, mu_stride, ktotal, out->c1.p,
+                                                out->c2.p, out->h.p, out->cmax2.p, nullptr);
+    ctx->launches++;
+    FDB_CHECK_LAUNCH();
+    FDB_TRY(make_map(&out->map1, out->c1.p, m, rows, (uint32_t)np));
+    FDB_TRY(make_map(&out->map2, out->c2.p, m, rows, (uint32_t)np));
+    return FDB_OK;
+}
+
+int tc_prepare_rows(fdb_ctx *ctx, const float *x, size_t n, size_t ld, size_t m, size_t nb, const float *mu,
+                    TcRows *out) {
+    cudaStream_t st = ctx->stream;
+    const bool grown = out->x1.n < n * ld;
+    FDB_TRY(out->x1.ensure(n * ld));
+    FDB_TRY(out->x2.ensure(n * ld));
+    FDB_TRY(out->xn2.ensure(nb * n));
+    const size_t warps = n * nb;
+    split_rows_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(x, n, ld, 0, m, nb, mu, out->x1.p,
+                                                                          out->x2.p, out->xn2.p);
+    ctx->launches++;
+    FDB_CHECK_LAUNCH();
+    if (grown || out->n != n || out->ld != ld) {
+        FDB_TRY(make_map(&out->map1, out->x1.p, ld, n, BM));
+        FDB_TRY(make_map(&out->map2, out->x2.p, ld, n, BM));
+        out->n = n;
+        out->ld = ld;
+    }
+    return FDB_OK;
+}
+
+int tc_gemm_raw(fdb_ctx *ctx, const TcRows &rows, const TcCentroids &cent, size_t xcol_stride, float alpha,
+                int sub_h, float *out, size_t out_row_stride, size_t out_b_stride) {
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    p.n = rows.n;
+    p.m = cent.m;
+    p.nb = cent.nb;
+    p.k = cent.k;
+    p.col_off = 0;
+    p.xcol_stride = xcol_stride;
+    p.crow_stride = cent.k;
+    p.mode = 1;
+    p.out = out;
+    p.out_row_stride = out_row_stride;
+    p.out_b_stride = out_b_stride;
+    p.alpha = alpha;
+    p.sub_h = sub_h;
+    p.np = cent.np;
+    p.row_tiles = (int)((rows.n + BM - 1) / BM);
+    const size_t stage_bytes = 2 * (size_t)BM * BK * 2 + 2 * (size_t)cent.np * BK * 2;
+    p.stages = (int)std::min<size_t>(4, (200 * 1024) / stage_bytes);
+    p.h = cent.h.p;
+    const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+    FDB_CUDA(cudaFuncSetAttribute(tc_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int total_tiles = (int)p.nb * p.row_tiles;
+    if (total_tiles == 0) return FDB_OK;
+    const int grid = std::min(total_tiles, ctx->sm_count);
+    tc_assign_kernel<<<grid, TC_THREADS, smem, ctx->stream>>>(rows.map1, rows.map2, cent.map1, cent.map2, p);
+    ctx->launches++;
+    FDB_CHECK_LAUNCH();
     return FDB_OK;
 }
 

@@ -420,6 +420,53 @@ def test_filter_path_bit_exact(eng, ctx, oracle, monkeypatch, layout, N, P, D, C
     ix.close()
 
 
+@pytest.mark.parametrize("N,P,D,Cn,M,k,nprobe", [
+    (128, 300, 2, 256, 30000, 10, 8),    # two column tiles of coarse centroids, s = 64, C = 256
+    (256, 40, 4, 64, 6000, 5, 40),       # nprobe == P > 24: exact probe kernels + tensor-pipe tables
+    (192, 500, 3, 128, 20000, 12, 24),   # largest nprobe the probe filter takes
+    (64, 7, 2, 256, 2000, 3, 2),         # tiny P, s = 32 (tables on the FMA pipe, coarse on the tensor pipe)
+])
+def test_filter_path_tensor_pipe_gemms(eng, ctx, oracle, N, P, D, Cn, M, k, nprobe):
+    """Shapes whose coarse scores and/or ADC tables come from the tcgen05 GEMM (m % 64 == 0)."""
+    coarse, cbs, off, codes = random_index(oracle, N, P, D, Cn, M, empty=(1,))
+    ix = eng.Index.create(ctx, coarse, cbs, off, codes.astype(np.uint8))
+    oix = oracle.QueryIndex(coarse, cbs, off, codes)
+    q = data(oracle, 200, N, SEED + 83)
+    for mode in (0, 1):
+        fast, exact, cand, scanned = _check_query(ix, oix, q, k, nprobe, mode)
+        assert fast >= 0.9 * len(q), (fast, exact)
+    ix.close()
+
+
+def test_probe_filter_ties_and_far_offsets(eng, ctx, oracle):
+    """Duplicated coarse centroids (exactly tied coarse distances -> NBestByKey history decides the
+    probe list) and data far from the origin (wide band): both must still equal the oracle."""
+    N, P, D, Cn, M, k, nprobe = 128, 24, 2, 256, 5000, 6, 5
+    coarse, cbs, off, codes = random_index(oracle, N, P, D, Cn, M)
+    coarse[7] = coarse[3]
+    coarse[11] = coarse[3]
+    ix = eng.Index.create(ctx, coarse, cbs, off, codes.astype(np.uint8))
+    oix = oracle.QueryIndex(coarse, cbs, off, codes)
+    q = data(oracle, 128, N, SEED + 84)
+    q[:40] = coarse[3] + (q[:40] - np.float32(0.5)) * np.float32(0.05)   # partition 3/7/11 is the nearest
+    for mode in (0, 1):
+        fast, exact, _, _ = _check_query(ix, oix, q, k, nprobe, mode)
+        assert exact >= 40          # the tied queries are answered by the exact pipeline
+        pp, pd = ix.probe(q, nprobe, mode)
+        rc, wp, wd = oix.probe(q[5], nprobe, mode)
+        assert (pp[5] == wp).all() and (pd[5] == wd).all()
+    ix.close()
+    coarse, cbs, off, codes = random_index(oracle, N, P, D, Cn, M)
+    coarse = (coarse + np.float32(500.0)).astype(np.float32)
+    ix = eng.Index.create(ctx, coarse, cbs, off, codes.astype(np.uint8))
+    oix = oracle.QueryIndex(coarse, cbs, off, codes)
+    qb = (q + np.float32(500.0)).astype(np.float32)
+    for mode in (0, 1):
+        fast, exact, _, _ = _check_query(ix, oix, qb, k, nprobe, mode)
+        assert fast >= 100
+    ix.close()
+
+
 def test_filter_path_equals_exact_pipeline_on_a_large_batch(eng, ctx, oracle, monkeypatch):
     """4096 queries against the README shape: ids, distances and counts of the filter path equal
     the exact pipeline's bit for bit (the oracle is too slow for this many; it checks a sample)."""
