@@ -378,11 +378,36 @@ __device__ __forceinline__ void push_lanes(RegTopK &sel, uint32_t kv, uint32_t a
     }
 }
 
-// sum of the D table entries of a code vector; W = D / 4 code words (0: any D, byte by byte)
-template <int W>
-__device__ __forceinline__ float adc_sum(const unsigned char *rec, const float *Ts, int D) {
-    if (W > 0) {
-        const uint32_t *cw = reinterpret_cast<const uint32_t *>(rec);
+// the RW 32-bit words of a record / code vector, with the widest loads its stride allows (a
+// 16-byte stride read word by word would be a 4-way bank conflict)
+template <int RW>
+__device__ __forceinline__ void load_words(const unsigned char *rec, uint32_t (&w)[RW]) {
+    if (RW % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < RW / 4; ++i) {
+            const uint4 v = reinterpret_cast<const uint4 *>(rec)[i];
+            w[4 * i] = v.x, w[4 * i + 1] = v.y, w[4 * i + 2] = v.z, w[4 * i + 3] = v.w;
+        }
+    } else if (RW % 2 == 0) {
+#pragma unroll
+        for (int i = 0; i < RW / 2; ++i) {
+            const uint2 v = reinterpret_cast<const uint2 *>(rec)[i];
+            w[2 * i] = v.x, w[2 * i + 1] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < RW; ++i) w[i] = reinterpret_cast<const uint32_t *>(rec)[i];
+    }
+}
+
+// approximate distance of one vector without K: sum of its D table entries (+ bv in RECORDS
+// layout); W = D / 4 code words (0: any D, byte by byte)
+template <int W, bool RECORDS>
+__device__ __forceinline__ float adc_sum(const unsigned char *rec, const float *Ts, int D, int dpad) {
+    if constexpr (W > 0) {
+        constexpr int RW = RECORDS ? W + 1 : W;
+        uint32_t cw[RW];
+        load_words<RW>(rec, cw);
         float a0 = 0.0f, a1 = 0.0f;
 #pragma unroll
         for (int w = 0; w < W; ++w) {
@@ -393,11 +418,15 @@ __device__ __forceinline__ float adc_sum(const unsigned char *rec, const float *
             a0 += t[2 * TSTRIDE + ((x >> 16) & 255u)];
             a1 += t[3 * TSTRIDE + (x >> 24)];
         }
-        return a0 + a1;
+        float a = a0 + a1;
+        if constexpr (RECORDS) a += __uint_as_float(cw[W]);
+        return a;
+    } else {
+        float acc = 0.0f;
+        for (int di = 0; di < D; ++di) acc += Ts[di * TSTRIDE + rec[di]];
+        if (RECORDS) acc += *reinterpret_cast<const float *>(rec + dpad);
+        return acc;
     }
-    float acc = 0.0f;
-    for (int di = 0; di < D; ++di) acc += Ts[di * TSTRIDE + rec[di]];
-    return acc;
 }
 
 template <int W, bool RECORDS>
@@ -481,10 +510,7 @@ __global__ void __launch_bounds__(FS_WARPS * 32) fscan_kernel(FScanParams p) {
                 const bool valid = v < cnt;
                 float a = 0.0f;
                 if (valid) {
-                    const unsigned char *rec = cs + (size_t)v * RB;
-                    a = adc_sum<W>(rec, Ts, D);
-                    if (RECORDS) a += *reinterpret_cast<const float *>(rec + dpad);
-                    a += K;
+                    a = adc_sum<W, RECORDS>(cs + (size_t)v * RB, Ts, D, dpad) + K;
                 }
                 const uint32_t ka = fkey(a);
                 // a vector is kept only below this warp's largest kept value and below every other
@@ -574,6 +600,11 @@ struct ProbeParams {
     uint32_t *probes;
     float *probe_d;
     unsigned *hard;
+    const float *cbmax;         // [D]
+    const unsigned *bounds;     // cb2, pcmax
+    float *Kq, *Wq;             // pair constants and magnitude for the ADC band (pair_const_kernel's outputs)
+    float kfac;                 // eta / coef: turns the rounding of K into the units of W
+    int quad, use_smem;
 };
 
 template <typename F>
@@ -604,60 +635,160 @@ __global__ void __launch_bounds__(128) probe_filter_kernel(ProbeParams p) {
     for (size_t t = 0; t < p.ntiles; ++t) cb = max(cb, p.cmax2[t]);
     const float cmax2 = __uint_as_float(cb);
     const float E = p.gamma1 * sqrtf(xn2 * cmax2) * 1.0001f + 1.2e-7f * (0.5f * cmax2);
-    // the ncap largest scores (key = -s ascending)
-    RegTopK sel;
-    sel.init(p.ncap);
     bool bad = !(xn2 < 1e30f);
     const float *Sq = p.S + q * p.ldS;
-    for (size_t base = 0; base < p.P; base += 32) {
-        const size_t pi = base + lane;
-        const bool valid = pi < p.P;
-        const float sv = valid ? Sq[pi] : 0.0f;
-        bad |= valid && !(fabsf(sv) < 1e30f);
-        const uint32_t key = fkey(-sv);
-        const bool want = valid && key < sel.maxkey;
-        if (__any_sync(0xffffffffu, want)) push_lanes(sel, key, (uint32_t)pi, want, lane);
+    float ss = 0.0f;        // lane c: score of candidate c (the first nprobe in descending order)
+    uint32_t part = 0;      //         and its partition
+    bool hard = false;
+    int ncand = 0;
+    if (p.use_smem) {
+        // scores in shared memory; the nprobe largest by repeated extraction of the maximum, then
+        // one pass collects what else lies inside the band
+        extern __shared__ float sbuf_all[];
+        float *sbuf = sbuf_all + (size_t)warp * (p.P + 32);
+        uint32_t *cidx = reinterpret_cast<uint32_t *>(sbuf + p.P);   // [32] candidates beyond the nprobe best
+        for (size_t pi = lane; pi < p.P; pi += 32) {
+            const float sv = Sq[pi];
+            bad |= !(fabsf(sv) < 1e30f);
+            sbuf[pi] = sv;
+        }
+        __syncwarp();
+        hard = __any_sync(0xffffffffu, bad);
+        if (!hard) {
+            for (int it = 0; it < p.nprobe; ++it) {
+                uint32_t bk = 0, bi = 0;
+                for (size_t pi = lane; pi < p.P; pi += 32) {
+                    const uint32_t kk = fkey(sbuf[pi]);
+                    if (kk > bk) {
+                        bk = kk;
+                        bi = (uint32_t)pi;
+                    }
+                }
+                const uint32_t m = __reduce_max_sync(0xffffffffu, bk);
+                const int owner = __ffs(__ballot_sync(0xffffffffu, bk == m)) - 1;
+                const uint32_t widx = __shfl_sync(0xffffffffu, bi, owner);
+                if (lane == it) {
+                    ss = fkey_inv(m);
+                    part = widx;
+                }
+                if (lane == owner) sbuf[widx] = -INF;
+                __syncwarp();
+            }
+            ncand = p.nprobe;
+            if (p.P > (size_t)p.nprobe) {
+                const float s_tau = __shfl_sync(0xffffffffu, ss, p.nprobe - 1);
+                const float dtau = fmaxf(0.0f, xn2 - 2.0f * s_tau + 2.0f * E);
+                const float shift = 1.3e-7f * sqrtf(dtau) * (sqrtf(xn2) + sqrtf(cmax2));
+                const float band = 2.0f * (2.0f * E + 1.01f * p.eta * dtau + shift);
+                const float thr = s_tau - band;
+                if (!(fabsf(thr) < 1e30f)) hard = true;
+                for (size_t base = 0; base < p.P && !hard; base += 32) {
+                    const size_t pi = base + lane;
+                    const float sv = pi < p.P ? sbuf[pi] : -INF;   // the nprobe best are -inf by now
+                    const unsigned bal = __ballot_sync(0xffffffffu, sv >= thr);
+                    if (bal) {
+                        const int pos = ncand + __popc(bal & ((1u << lane) - 1u));
+                        if (sv >= thr && pos < 32) cidx[pos - p.nprobe] = (uint32_t)pi;
+                        ncand += __popc(bal);
+                        if (ncand > 32) hard = true;   // more partitions inside the band than lanes
+                    }
+                }
+                __syncwarp();
+                if (!hard && lane >= p.nprobe && lane < ncand) part = cidx[lane - p.nprobe];
+            }
+        }
+    } else {
+        // the ncap largest scores (key = -s ascending) in registers, any P
+        RegTopK sel;
+        sel.init(p.ncap);
+        for (size_t base = 0; base < p.P; base += 32) {
+            const size_t pi = base + lane;
+            const bool valid = pi < p.P;
+            const float sv = valid ? Sq[pi] : 0.0f;
+            bad |= valid && !(fabsf(sv) < 1e30f);
+            const uint32_t key = fkey(-sv);
+            const bool want = valid && key < sel.maxkey;
+            if (__any_sync(0xffffffffu, want)) push_lanes(sel, key, (uint32_t)pi, want, lane);
+        }
+        const int cnt = sel.len;
+        // sort: lane r receives the entry of rank r
+        int rk = 0;
+        for (int j = 0; j < cnt; ++j) {
+            const uint32_t kj = __shfl_sync(0xffffffffu, sel.key, j);
+            rk += (kj < sel.key) || (kj == sel.key && j < lane);
+        }
+        int src = 0;
+        for (int j = 0; j < cnt; ++j) {
+            const int rj = __shfl_sync(0xffffffffu, rk, j);
+            if (rj == lane) src = j;
+        }
+        ss = -fkey_inv(__shfl_sync(0xffffffffu, sel.key, src));   // descending scores
+        part = __shfl_sync(0xffffffffu, sel.a, src);
+        hard = __any_sync(0xffffffffu, bad);
+        ncand = cnt;
+        if (cnt > p.nprobe) {
+            const float s_tau = __shfl_sync(0xffffffffu, ss, p.nprobe - 1);
+            const float dtau = fmaxf(0.0f, xn2 - 2.0f * s_tau + 2.0f * E);
+            const float shift = 1.3e-7f * sqrtf(dtau) * (sqrtf(xn2) + sqrtf(cmax2));
+            const float band = 2.0f * (2.0f * E + 1.01f * p.eta * dtau + shift);
+            const float thr = s_tau - band;
+            if (!(fabsf(thr) < 1e30f)) hard = true;
+            ncand = __popc(__ballot_sync(0xffffffffu, lane < cnt && ss >= thr));
+            if (ncand == p.ncap && p.P > (size_t)p.ncap) hard = true;
+        }
     }
-    const int cnt = sel.len;
-    // sort: lane r receives the entry of rank r
     int rank = 0;
-    for (int j = 0; j < cnt; ++j) {
-        const uint32_t kj = __shfl_sync(0xffffffffu, sel.key, j);
-        rank += (kj < sel.key) || (kj == sel.key && j < lane);
-    }
-    int src = 0;
-    for (int j = 0; j < cnt; ++j) {
-        const int rj = __shfl_sync(0xffffffffu, rank, j);
-        if (rj == lane) src = j;
-    }
-    const float ss = -fkey_inv(__shfl_sync(0xffffffffu, sel.key, src));   // descending scores
-    const uint32_t part = __shfl_sync(0xffffffffu, sel.a, src);
-    bool hard = __any_sync(0xffffffffu, bad);
-    int ncand = cnt;
-    if (cnt > p.nprobe) {
-        const float s_tau = __shfl_sync(0xffffffffu, ss, p.nprobe - 1);
-        const float dtau = fmaxf(0.0f, xn2 - 2.0f * s_tau + 2.0f * E);
-        const float shift = 1.3e-7f * sqrtf(dtau) * (sqrtf(xn2) + sqrtf(cmax2));
-        const float band = 2.0f * (2.0f * E + 1.01f * p.eta * dtau + shift);
-        const float thr = s_tau - band;
-        if (!(fabsf(thr) < 1e30f)) hard = true;
-        ncand = __popc(__ballot_sync(0xffffffffu, lane < cnt && ss >= thr));
-        if (ncand == p.ncap && p.P > (size_t)p.ncap) hard = true;
-    }
     float myD = 0.0f;
     if (!hard) {
-        const int half = lane >> 4, j = lane & 15, hbase = half * 16;
         const float *qv = p.q + q * p.N;
-        for (int i = 0; 2 * i < ncand; ++i) {
-            const int c = 2 * i + half;
-            const uint32_t pc = __shfl_sync(0xffffffffu, part, c < ncand ? c : 0);
-            const float *cv = p.coarse + (size_t)pc * p.N;
-            const float T = halfwarp_dot16(p.N, j, hbase, [&](size_t e) {
-                const float d = __fsub_rn(qv[e], cv[e]);
-                return __fmul_rn(d, d);
-            });
-            const float v = __shfl_sync(0xffffffffu, T, (lane & 1) * 16);
-            if ((lane >> 1) == i) myD = v;
+        if (p.quad) {
+            // N % 16 == 0: a quad of lanes per candidate (8 at a time), lane tq owns accumulators
+            // 4tq..4tq+3 of the 16-lane dot and loads 128 bits at a time
+            const int g = lane >> 2, tq = lane & 3, qbase = lane & ~3;
+            for (int c0 = 0; c0 < ncand; c0 += 8) {
+                const int c = c0 + g;
+                const uint32_t pc = __shfl_sync(0xffffffffu, part, c < ncand ? c : 0);
+                const float *cv = p.coarse + (size_t)pc * p.N;
+                float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+                for (size_t e = 4 * tq; e < p.N; e += 16) {
+                    const float4 x = *reinterpret_cast<const float4 *>(qv + e);
+                    const float4 cc = __ldg(reinterpret_cast<const float4 *>(cv + e));
+                    float d = __fsub_rn(x.x, cc.x);
+                    a0 = __fadd_rn(a0, __fmul_rn(d, d));
+                    d = __fsub_rn(x.y, cc.y);
+                    a1 = __fadd_rn(a1, __fmul_rn(d, d));
+                    d = __fsub_rn(x.z, cc.z);
+                    a2 = __fadd_rn(a2, __fmul_rn(d, d));
+                    d = __fsub_rn(x.w, cc.w);
+                    a3 = __fadd_rn(a3, __fmul_rn(d, d));
+                }
+                float T = 0.0f;  // sum_naive over the 16 accumulators, src/linalg.rs:39
+#pragma unroll
+                for (int t4 = 0; t4 < 4; ++t4) {
+                    if (tq == t4) {
+                        T = __fadd_rn(T, a0);
+                        T = __fadd_rn(T, a1);
+                        T = __fadd_rn(T, a2);
+                        T = __fadd_rn(T, a3);
+                    }
+                    T = __shfl_sync(0xffffffffu, T, qbase + t4);
+                }
+                const float v = __shfl_sync(0xffffffffu, T, ((lane - c0) & 7) * 4);
+                if (lane >= c0 && lane < c0 + 8) myD = v;
+            }
+        } else {
+            const int half = lane >> 4, j = lane & 15, hbase = half * 16;
+            for (int i = 0; 2 * i < ncand; ++i) {
+                const int c = 2 * i + half;
+                const uint32_t pc = __shfl_sync(0xffffffffu, part, c < ncand ? c : 0);
+                const float *cv = p.coarse + (size_t)pc * p.N;
+                const float T = halfwarp_dot16(p.N, j, hbase, [&](size_t e) {
+                    const float d = __fsub_rn(qv[e], cv[e]);
+                    return __fmul_rn(d, d);
+                });
+                const float v = __shfl_sync(0xffffffffu, T, (lane & 1) * 16);
+                if ((lane >> 1) == i) myD = v;
+            }
         }
         const bool mine = lane < ncand;
         rank = 0;
@@ -678,13 +809,32 @@ __global__ void __launch_bounds__(128) probe_filter_kernel(ProbeParams p) {
             p.probes[q * p.nprobe + lane] = part;
             p.probe_d[q * p.nprobe + lane] = xn2 - 2.0f * ss;
         }
-        if (lane == 0) p.hard[q] = 1u;
+        if (lane == 0) {
+            p.hard[q] = 1u;
+            p.Wq[q] = __int_as_float(0x7fc00000);
+        }
+        if (lane < p.nprobe) p.Kq[q * p.nprobe + lane] = 0.0f;
         return;
     }
-    if (lane < ncand && rank < p.nprobe) {
+    const bool sel_me = lane < ncand && rank < p.nprobe;
+    if (sel_me) {
         p.probes[q * p.nprobe + rank] = part;
         p.probe_d[q * p.nprobe + rank] = myD;
+        // the pair constant K = |l|^2 of the ADC expansion: the reference's own f32 value of it,
+        // |myD - |l|^2| <= eta |l|^2 goes into the band through kfac
+        p.Kq[q * p.nprobe + rank] = myD;
     }
+    // W = Kmax (1 + kfac) + sum_d 2 |x'_d| cbmax_d + pcmax + cb2 (see the header), rounded up
+    float kmax = sel_me ? myD * (1.0f + p.kfac) : 0.0f;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) kmax = fmaxf(kmax, __shfl_xor_sync(0xffffffffu, kmax, off));
+    double qc = 0.0;
+    for (size_t d = lane; d < p.D; d += 32) qc += 2.0 * sqrt((double)p.xn2[d * p.nq + q]) * (double)p.cbmax[d];
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) qc += __shfl_xor_sync(0xffffffffu, qc, off);
+    if (lane == 0)
+        p.Wq[q] = __double2float_ru(((double)kmax * 1.000001 + qc + (double)__uint_as_float(p.bounds[1]) +
+                                     (double)__uint_as_float(p.bounds[0])) * 1.00001);
 }
 
 // ---- band, exact re-check of the candidates, final selection; one warp per query ------------
@@ -1013,6 +1163,12 @@ bool filter_eligible(const fdb_index *ix, size_t nq, size_t k, size_t nprobe) {
            nq * RCAP < (1ull << 32) && ix->M < (1ull << 32) && nprobe <= 4096;
 }
 
+// E_q = coef * W_q (header): gamma of the GEMM that produces G (tensor pipe or FMA chain)
+static float adc_coef(size_t s, size_t D, bool tc_g) {
+    const double gamma = tc_g ? (double)tc_gamma(s) : (double)s * U24 / (1.0 - (double)s * U24);
+    return (float)((2.0 * gamma + (double)(D + 4) * U24) * 1.01);
+}
+
 // probes through the tensor pipe + the probe filter; *done = false when the shape is not taken
 int filter_probe(fdb_index *ix, const float *d_q, size_t nq, size_t nprobe, EventLog *log, bool *done) {
     fdb_ctx *ctx = ix->ctx;
@@ -1047,13 +1203,24 @@ int filter_probe(fdb_index *ix, const float *d_q, size_t nq, size_t nprobe, Even
     pp.P = P;
     pp.N = N;
     pp.nprobe = (int)nprobe;
-    pp.ncap = (int)std::min<size_t>(RCAP, nprobe + 8);
+    pp.ncap = RCAP;   // the band may hold many partitions when the centroids are about equally far
     pp.gamma1 = tc_gamma(N);
     pp.eta = ((float)N / 16.0f + 20.0f) * U24;   // the reference's own f32 evaluation of one distance
     pp.probes = ix->probes.p;
     pp.probe_d = ix->probe_d.p;
     pp.hard = fs->hard.p;
-    probe_filter_kernel<<<(unsigned)((nq + 3) / 4), 128, 0, st>>>(pp);
+    pp.cbmax = fs->cbmax.p;
+    pp.bounds = fs->bounds.p;
+    FDB_TRY(fs->Kq.ensure(nq * nprobe));
+    FDB_TRY(fs->Wq.ensure(nq));
+    pp.Kq = fs->Kq.p;
+    pp.Wq = fs->Wq.p;
+    pp.kfac = 1.01f * pp.eta / adc_coef(s, D, fs->tc_g);
+    pp.quad = (N % 16 == 0) ? 1 : 0;   // d_q is 16-byte aligned here, the centroid rows always are
+    pp.use_smem = P <= 4096 ? 1 : 0;
+    const size_t psmem = pp.use_smem ? 4 * (P + 32) * sizeof(float) : 0;
+    FDB_CUDA(cudaFuncSetAttribute(probe_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(psmem, 1024)));
+    probe_filter_kernel<<<(unsigned)((nq + 3) / 4), 128, psmem, st>>>(pp);
     ctx->launches++;
     FDB_CHECK_LAUNCH();
     fs->probes_from_filter = true;
@@ -1110,11 +1277,13 @@ int filter_query(fdb_index *ix, const float *d_q, size_t q_base, size_t nq, size
     FDB_CUDA(cudaMemsetAsync(fs->counters.p, 0, 4 * sizeof(unsigned long long), st));
 
     FDB_TRY(log->mark(2));
-    pair_const_kernel<<<(unsigned)((nq * 32 + 127) / 128), 128, 0, st>>>(
-        d_q, ix->coarse.p, fs->mu.p, ix->probes.p, fs->cbmax.p, fs->bounds.p, nq, N, D, s, (int)nprobe, fs->Kq.p,
-        fs->Wq.p);
-    ctx->launches++;
-    FDB_CHECK_LAUNCH();
+    if (!fs->probes_from_filter) {  // the probe filter already left K and W behind
+        pair_const_kernel<<<(unsigned)((nq * 32 + 127) / 128), 128, 0, st>>>(
+            d_q, ix->coarse.p, fs->mu.p, ix->probes.p, fs->cbmax.p, fs->bounds.p, nq, N, D, s, (int)nprobe, fs->Kq.p,
+            fs->Wq.p);
+        ctx->launches++;
+        FDB_CHECK_LAUNCH();
+    }
 
     const bool records = fs->rb != 0;
     const size_t rb = records ? fs->rb : D;
@@ -1125,8 +1294,7 @@ int filter_query(fdb_index *ix, const float *d_q, size_t q_base, size_t nq, size
     // list capacity: k plus head room for the vectors inside the error band
     const int ncap = (int)std::min<size_t>(RCAP, k + 6);
     const bool vec = (s % 4 == 0) && (N % 4 == 0) && ((uintptr_t)d_q % 16 == 0);
-    const double gamma = tc_g ? (double)tc_gamma(s) : (double)s * U24 / (1.0 - (double)s * U24);
-    const float coef = (float)((2.0 * gamma + (double)(D + 4) * U24) * 1.01);
+    const float coef = adc_coef(s, D, tc_g);
     const float eta3 = (float)(2.1 * ((double)s / 16.0 + 40.0 + (double)D) * U24);
 
     for (size_t q0 = 0; q0 < nq; q0 += chunk) {
