@@ -59,6 +59,9 @@ struct FilterState {
     TcRows rows;                    // bf16 pieces of the centred queries of the current batch
     DevBuf<float> S;                // [nq][ldS] approximate coarse scores x'.c' - |c'|^2/2
     DevBuf<unsigned> hard;          // [nq] the probe filter could not decide: exact pipeline
+    DevBuf<uint32_t> ps_part, ps_meta, ps_items;   // state of the probe filter's three kernels
+    DevBuf<float> ps_ss, ps_dist;
+    DevBuf<unsigned> ps_count;
     bool rows_ready = false, probes_from_filter = false;
     DevBuf<float> G;             // [chunk_q][D][C]
     DevBuf<float> Kq, Wq;        // [nq][nprobe], [nq]
@@ -582,10 +585,13 @@ __global__ void __launch_bounds__(256) records_kernel(const uint8_t *codes, cons
 
 // ---- probe filter: the nprobe nearest partitions from approximate scores ----------------------
 // S[q][p] ~ x'.c'_p - |c'_p|^2/2 from the tensor pipe (error <= E, see tc_assign.cu).  The
-// nprobe best scores plus everything inside the band are evaluated exactly (reference order,
-// src/db/stored.rs:413-424) and sorted; the result is the reference's probe list when the
-// exact distances around the boundary are distinct.  Otherwise (ties, NaN, overfull band) the
-// query is marked hard and answered by the exact pipeline.
+// partitions whose score is clear of the nprobe-th by more than the band are certainly probed
+// (or certainly not); only those inside the band around the boundary are evaluated exactly
+// (reference order, src/db/stored.rs:413-424) and the nearest of them fill the list.  Exact ties
+// at the cut, NaN and an overfull band mark the query hard: the exact pipeline answers it.
+// The list is the reference's probe SET (its order only matters for ties, which never stay on
+// this path); the pair constants K = |q - c_p|^2 of the ADC expansion are taken from the
+// scores, their error (2E + shift) is added to the ADC band through W.
 struct ProbeParams {
     const float *S;
     size_t ldS;
@@ -598,13 +604,20 @@ struct ProbeParams {
     int nprobe, ncap;
     float gamma1, eta;
     uint32_t *probes;
-    float *probe_d;
     unsigned *hard;
     const float *cbmax;         // [D]
     const unsigned *bounds;     // cb2, pcmax
     float *Kq, *Wq;             // pair constants and magnitude for the ADC band (pair_const_kernel's outputs)
-    float kfac;                 // eta / coef: turns the rounding of K into the units of W
+    float inv_coef;             // 1 / coef: turns the error of K into the units of W
     int quad, use_smem;
+    unsigned long long *nexact; // statistics: partitions evaluated exactly
+    // state between the three kernels of the probe filter (select -> exact distances -> finalize)
+    uint32_t *st_part;          // [nq][32] candidate partitions, lane order
+    float *st_ss;               // [nq][32] their scores
+    uint32_t *st_meta;          // [nq][8] hard, ncand, ambmask, need, cheap, item base, qcf bits, kerr bits
+    uint32_t *items;            // [cap][2] (query, partition) pairs to evaluate exactly
+    float *item_d;              // [cap] their exact distances
+    unsigned *item_count;
 };
 
 template <typename F>
@@ -624,23 +637,30 @@ __device__ __forceinline__ float halfwarp_dot16(size_t m, int j, int hbase, F te
     return T;
 }
 
-__global__ void __launch_bounds__(128) probe_filter_kernel(ProbeParams p) {
+__global__ void __launch_bounds__(128) probe_select_kernel(ProbeParams p) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t q = (size_t)blockIdx.x * 4 + warp;
     if (q >= p.nq) return;
     float xn2 = 0.0f;
     for (size_t d = 0; d < p.D; ++d) xn2 += p.xn2[d * p.nq + q];
-    xn2 *= 1.0001f;
+    const float xn2k = xn2;   // as accurate as it gets: used for K
+    xn2 *= 1.0001f;           // rounded up: used for the bounds
     unsigned cb = 0;
     for (size_t t = 0; t < p.ntiles; ++t) cb = max(cb, p.cmax2[t]);
     const float cmax2 = __uint_as_float(cb);
     const float E = p.gamma1 * sqrtf(xn2 * cmax2) * 1.0001f + 1.2e-7f * (0.5f * cmax2);
     bool bad = !(xn2 < 1e30f);
     const float *Sq = p.S + q * p.ldS;
-    float ss = 0.0f;        // lane c: score of candidate c (the first nprobe in descending order)
-    uint32_t part = 0;      //         and its partition
+    float ss = 0.0f;        // lane c < ncand: score of candidate c (the first nprobe in descending order)
+    uint32_t part = 0;      //                 and its partition
     bool hard = false;
     int ncand = 0;
+    float band = 0.0f, s_tau = 0.0f;
+    auto band_of = [&](float st) {
+        const float dtau = fmaxf(0.0f, xn2 - 2.0f * st + 2.0f * E);
+        const float shift = 1.3e-7f * sqrtf(dtau) * (sqrtf(xn2) + sqrtf(cmax2));
+        return 2.0f * (2.0f * E + 1.01f * p.eta * dtau + shift);
+    };
     if (p.use_smem) {
         // scores in shared memory; the nprobe largest by repeated extraction of the maximum, then
         // one pass collects what else lies inside the band
@@ -675,11 +695,9 @@ __global__ void __launch_bounds__(128) probe_filter_kernel(ProbeParams p) {
                 __syncwarp();
             }
             ncand = p.nprobe;
+            s_tau = __shfl_sync(0xffffffffu, ss, p.nprobe - 1);
+            band = band_of(s_tau);
             if (p.P > (size_t)p.nprobe) {
-                const float s_tau = __shfl_sync(0xffffffffu, ss, p.nprobe - 1);
-                const float dtau = fmaxf(0.0f, xn2 - 2.0f * s_tau + 2.0f * E);
-                const float shift = 1.3e-7f * sqrtf(dtau) * (sqrtf(xn2) + sqrtf(cmax2));
-                const float band = 2.0f * (2.0f * E + 1.01f * p.eta * dtau + shift);
                 const float thr = s_tau - band;
                 if (!(fabsf(thr) < 1e30f)) hard = true;
                 for (size_t base = 0; base < p.P && !hard; base += 32) {
@@ -694,7 +712,10 @@ __global__ void __launch_bounds__(128) probe_filter_kernel(ProbeParams p) {
                     }
                 }
                 __syncwarp();
-                if (!hard && lane >= p.nprobe && lane < ncand) part = cidx[lane - p.nprobe];
+                if (!hard && lane >= p.nprobe && lane < ncand) {
+                    part = cidx[lane - p.nprobe];
+                    ss = sbuf[part];
+                }
             }
         }
     } else {
@@ -725,116 +746,210 @@ __global__ void __launch_bounds__(128) probe_filter_kernel(ProbeParams p) {
         ss = -fkey_inv(__shfl_sync(0xffffffffu, sel.key, src));   // descending scores
         part = __shfl_sync(0xffffffffu, sel.a, src);
         hard = __any_sync(0xffffffffu, bad);
-        ncand = cnt;
+        ncand = min(cnt, p.nprobe);
+        s_tau = __shfl_sync(0xffffffffu, ss, p.nprobe - 1);
+        band = band_of(s_tau);
         if (cnt > p.nprobe) {
-            const float s_tau = __shfl_sync(0xffffffffu, ss, p.nprobe - 1);
-            const float dtau = fmaxf(0.0f, xn2 - 2.0f * s_tau + 2.0f * E);
-            const float shift = 1.3e-7f * sqrtf(dtau) * (sqrtf(xn2) + sqrtf(cmax2));
-            const float band = 2.0f * (2.0f * E + 1.01f * p.eta * dtau + shift);
             const float thr = s_tau - band;
             if (!(fabsf(thr) < 1e30f)) hard = true;
             ncand = __popc(__ballot_sync(0xffffffffu, lane < cnt && ss >= thr));
             if (ncand == p.ncap && p.P > (size_t)p.ncap) hard = true;
         }
     }
-    int rank = 0;
-    float myD = 0.0f;
-    if (!hard) {
-        const float *qv = p.q + q * p.N;
-        if (p.quad) {
-            // N % 16 == 0: a quad of lanes per candidate (8 at a time), lane tq owns accumulators
-            // 4tq..4tq+3 of the 16-lane dot and loads 128 bits at a time
-            const int g = lane >> 2, tq = lane & 3, qbase = lane & ~3;
-            for (int c0 = 0; c0 < ncand; c0 += 8) {
-                const int c = c0 + g;
-                const uint32_t pc = __shfl_sync(0xffffffffu, part, c < ncand ? c : 0);
-                const float *cv = p.coarse + (size_t)pc * p.N;
-                float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
-                for (size_t e = 4 * tq; e < p.N; e += 16) {
-                    const float4 x = *reinterpret_cast<const float4 *>(qv + e);
-                    const float4 cc = __ldg(reinterpret_cast<const float4 *>(cv + e));
-                    float d = __fsub_rn(x.x, cc.x);
-                    a0 = __fadd_rn(a0, __fmul_rn(d, d));
-                    d = __fsub_rn(x.y, cc.y);
-                    a1 = __fadd_rn(a1, __fmul_rn(d, d));
-                    d = __fsub_rn(x.z, cc.z);
-                    a2 = __fadd_rn(a2, __fmul_rn(d, d));
-                    d = __fsub_rn(x.w, cc.w);
-                    a3 = __fadd_rn(a3, __fmul_rn(d, d));
-                }
-                float T = 0.0f;  // sum_naive over the 16 accumulators, src/linalg.rs:39
+    // Pair constants K = |q - c_p|^2 of the ADC expansion: taken from the scores when their error
+    // (GEMM error 2E, centring roundings, roundings of xn2 and of xn2 - 2 s) is small next to the
+    // other terms of the ADC band, else from the exact distances of all candidates.
+    float qcf;
+    {
+        double qc = 0.0;
+        for (size_t d = lane; d < p.D; d += 32) qc += 2.0 * sqrt((double)p.xn2[d * p.nq + q]) * (double)p.cbmax[d];
 #pragma unroll
-                for (int t4 = 0; t4 < 4; ++t4) {
-                    if (tq == t4) {
-                        T = __fadd_rn(T, a0);
-                        T = __fadd_rn(T, a1);
-                        T = __fadd_rn(T, a2);
-                        T = __fadd_rn(T, a3);
-                    }
-                    T = __shfl_sync(0xffffffffu, T, qbase + t4);
+        for (int off = 16; off >= 1; off >>= 1) qc += __shfl_xor_sync(0xffffffffu, qc, off);
+        qcf = __double2float_ru(qc);
+    }
+    const float kapx = fmaxf(0.0f, xn2k - 2.0f * ss);   // |x' - c'|^2 from the score
+    float kmax0 = (lane < ncand && lane < p.nprobe) ? kapx : 0.0f;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) kmax0 = fmaxf(kmax0, __shfl_xor_sync(0xffffffffu, kmax0, off));
+    const float w0 = kmax0 + qcf + __uint_as_float(p.bounds[1]) + __uint_as_float(p.bounds[0]);
+    const float kerr = 2.0f * E + 1.3e-7f * sqrtf(kmax0 + 2.0f * E) * (sqrtf(xn2) + sqrtf(cmax2)) +
+                       (6e-8f * (float)(p.D + 8)) * xn2 + 4e-7f * (xn2 + cmax2);
+    const bool cheap = kerr * p.inv_coef <= 0.25f * w0;
+    // certain: clear of the boundary by more than the band; ambiguous: the rest of the candidates
+    const bool isc = lane < ncand;
+    const bool amb = isc && (!cheap || (ncand > p.nprobe && !(ss > s_tau + band)));
+    const unsigned ambmask = __ballot_sync(0xffffffffu, amb);
+    const int namb = __popc(ambmask);
+    const int ncert = __popc(__ballot_sync(0xffffffffu, isc && !amb && lane < p.nprobe));
+    const int need = p.nprobe - ncert;   // how many of the ambiguous ones are probed
+    // hand the ambiguous candidates to the exact-distance kernel, keep the rest for the finalizer
+    unsigned base = 0;
+    if (!hard && namb > 0) {
+        if (lane == 0) base = atomicAdd(p.item_count, (unsigned)namb);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (amb) {
+            const unsigned slot = base + __popc(ambmask & ((1u << lane) - 1u));
+            p.items[2 * (size_t)slot] = (uint32_t)q;
+            p.items[2 * (size_t)slot + 1] = part;
+        }
+    }
+    p.st_part[q * 32 + lane] = part;
+    p.st_ss[q * 32 + lane] = ss;
+    if (lane < 8) {
+        uint32_t m = 0;
+        switch (lane) {
+            case 0: m = hard ? 1u : 0u; break;
+            case 1: m = (uint32_t)ncand; break;
+            case 2: m = ambmask; break;
+            case 3: m = (uint32_t)need; break;
+            case 4: m = cheap ? 1u : 0u; break;
+            case 5: m = base; break;
+            case 6: m = __float_as_uint(qcf); break;
+            default: m = __float_as_uint(kerr); break;
+        }
+        p.st_meta[q * 8 + lane] = m;
+    }
+}
+
+// exact distances |q - c_p|^2 of the listed (query, partition) pairs in the reference's order of
+// operations (src/db/stored.rs:413-424); a grid-stride loop over a device-side count
+__global__ void __launch_bounds__(256) probe_exact_kernel(ProbeParams p) {
+    const unsigned total = *p.item_count;
+    const int lane = threadIdx.x & 31;
+    if (p.quad) {
+        // N % 16 == 0: a quad of lanes per pair, lane tq owns accumulators 4tq..4tq+3 of the 16-lane dot
+        const int tq = lane & 3, qbase = lane & ~3;
+        const unsigned nquads = (gridDim.x * blockDim.x) >> 2;
+        const unsigned rounds = (total + nquads - 1) / nquads;
+        for (unsigned r = 0; r < rounds; ++r) {
+            const unsigned item = r * nquads + ((blockIdx.x * blockDim.x + threadIdx.x) >> 2);
+            const bool act = item < total;
+            const uint32_t qi = act ? p.items[2 * (size_t)item] : 0, pc = act ? p.items[2 * (size_t)item + 1] : 0;
+            const float *qv = p.q + (size_t)qi * p.N;
+            const float *cv = p.coarse + (size_t)pc * p.N;
+            float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+            for (size_t e = 4 * tq; e < p.N; e += 16) {
+                const float4 x = __ldg(reinterpret_cast<const float4 *>(qv + e));
+                const float4 cc = __ldg(reinterpret_cast<const float4 *>(cv + e));
+                float d = __fsub_rn(x.x, cc.x);
+                a0 = __fadd_rn(a0, __fmul_rn(d, d));
+                d = __fsub_rn(x.y, cc.y);
+                a1 = __fadd_rn(a1, __fmul_rn(d, d));
+                d = __fsub_rn(x.z, cc.z);
+                a2 = __fadd_rn(a2, __fmul_rn(d, d));
+                d = __fsub_rn(x.w, cc.w);
+                a3 = __fadd_rn(a3, __fmul_rn(d, d));
+            }
+            float T = 0.0f;  // sum_naive over the 16 accumulators, src/linalg.rs:39
+#pragma unroll
+            for (int t4 = 0; t4 < 4; ++t4) {
+                if (tq == t4) {
+                    T = __fadd_rn(T, a0);
+                    T = __fadd_rn(T, a1);
+                    T = __fadd_rn(T, a2);
+                    T = __fadd_rn(T, a3);
                 }
-                const float v = __shfl_sync(0xffffffffu, T, ((lane - c0) & 7) * 4);
-                if (lane >= c0 && lane < c0 + 8) myD = v;
+                T = __shfl_sync(0xffffffffu, T, qbase + t4);
             }
-        } else {
-            const int half = lane >> 4, j = lane & 15, hbase = half * 16;
-            for (int i = 0; 2 * i < ncand; ++i) {
-                const int c = 2 * i + half;
-                const uint32_t pc = __shfl_sync(0xffffffffu, part, c < ncand ? c : 0);
-                const float *cv = p.coarse + (size_t)pc * p.N;
-                const float T = halfwarp_dot16(p.N, j, hbase, [&](size_t e) {
-                    const float d = __fsub_rn(qv[e], cv[e]);
-                    return __fmul_rn(d, d);
-                });
-                const float v = __shfl_sync(0xffffffffu, T, (lane & 1) * 16);
-                if ((lane >> 1) == i) myD = v;
-            }
+            if (act && tq == 0) p.item_d[item] = T;
         }
-        const bool mine = lane < ncand;
-        rank = 0;
+    } else {
+        const int half = lane >> 4, j = lane & 15, hbase = half * 16;
+        const unsigned nhalves = (gridDim.x * blockDim.x) >> 4;
+        const unsigned rounds = (total + nhalves - 1) / nhalves;
+        for (unsigned r = 0; r < rounds; ++r) {
+            const unsigned item = r * nhalves + ((blockIdx.x * blockDim.x + threadIdx.x) >> 4);
+            const bool act = item < total;
+            const uint32_t qi = act ? p.items[2 * (size_t)item] : 0, pc = act ? p.items[2 * (size_t)item + 1] : 0;
+            const float *qv = p.q + (size_t)qi * p.N;
+            const float *cv = p.coarse + (size_t)pc * p.N;
+            const float T = halfwarp_dot16(p.N, j, hbase, [&](size_t e) {
+                const float d = __fsub_rn(qv[e], cv[e]);
+                return __fmul_rn(d, d);
+            });
+            if (act && j == 0) p.item_d[item] = T;
+        }
+    }
+}
+
+// the probe list, the pair constants K and the magnitude W of every query; one warp per query
+__global__ void __launch_bounds__(128) probe_finalize_kernel(ProbeParams p) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t q = (size_t)blockIdx.x * 4 + warp;
+    if (q >= p.nq) return;
+    const uint32_t mt = lane < 8 ? p.st_meta[q * 8 + lane] : 0u;
+    bool hard = __shfl_sync(0xffffffffu, mt, 0) != 0;
+    const int ncand = (int)__shfl_sync(0xffffffffu, mt, 1);
+    const unsigned ambmask = __shfl_sync(0xffffffffu, mt, 2);
+    const int need = (int)__shfl_sync(0xffffffffu, mt, 3);
+    const bool cheap = __shfl_sync(0xffffffffu, mt, 4) != 0;
+    const unsigned base = __shfl_sync(0xffffffffu, mt, 5);
+    const float qcf = __uint_as_float(__shfl_sync(0xffffffffu, mt, 6));
+    const float kerr = __uint_as_float(__shfl_sync(0xffffffffu, mt, 7));
+    const uint32_t part = p.st_part[q * 32 + lane];
+    const float ss = p.st_ss[q * 32 + lane];
+    const bool isc = lane < ncand;
+    const bool amb = (ambmask >> lane) & 1u;
+    const int namb = __popc(ambmask);
+    bool chosen = isc && !amb && lane < p.nprobe;
+    float myD = 0.0f;
+    if (!hard && namb > 0) {
+        const int myamb = __popc(ambmask & ((1u << lane) - 1u));
+        if (amb) myD = p.item_d[base + myamb];
+        // rank among the ambiguous ones by (distance, partition); the `need` nearest are probed
+        int rank = 0;
         bool tie = false;
-        for (int jx = 0; jx < ncand; ++jx) {
-            const float Dj = __shfl_sync(0xffffffffu, myD, jx);
-            const uint32_t pj = __shfl_sync(0xffffffffu, part, jx);
+        for (int a = 0; a < namb; ++a) {
+            const int al = __fns(ambmask, 0, a + 1);
+            const float Dj = __shfl_sync(0xffffffffu, myD, al);
+            const uint32_t pj = __shfl_sync(0xffffffffu, part, al);
             rank += (Dj < myD) || (Dj == myD && pj < part);
-            tie |= (Dj == myD) && jx != lane;
+            tie |= (Dj == myD) && al != lane;
         }
-        // NaN, or a tie that involves one of the nprobe nearest (which survives / in which order
-        // depends on NBestByKey's push history)
-        if (__any_sync(0xffffffffu, mine && ((myD != myD) || (tie && rank < p.nprobe)))) hard = true;
+        // NaN, or an exact tie that involves one of the probed partitions (which one survives, and
+        // the order of the list, then depend on NBestByKey's push history)
+        if (__any_sync(0xffffffffu, amb && ((myD != myD) || (tie && rank < need)))) hard = true;
+        chosen |= amb && rank < need;
+        if (lane == 0) atomicAdd(p.nexact, (unsigned long long)namb);
     }
     if (hard) {
         // placeholders that keep the later kernels in bounds; the query is redone exactly
         if (lane < p.nprobe) {
             p.probes[q * p.nprobe + lane] = part;
-            p.probe_d[q * p.nprobe + lane] = xn2 - 2.0f * ss;
+            p.Kq[q * p.nprobe + lane] = 0.0f;
         }
         if (lane == 0) {
             p.hard[q] = 1u;
             p.Wq[q] = __int_as_float(0x7fc00000);
         }
-        if (lane < p.nprobe) p.Kq[q * p.nprobe + lane] = 0.0f;
         return;
     }
-    const bool sel_me = lane < ncand && rank < p.nprobe;
-    if (sel_me) {
-        p.probes[q * p.nprobe + rank] = part;
-        p.probe_d[q * p.nprobe + rank] = myD;
-        // the pair constant K = |l|^2 of the ADC expansion: the reference's own f32 value of it,
-        // |myD - |l|^2| <= eta |l|^2 goes into the band through kfac
-        p.Kq[q * p.nprobe + rank] = myD;
+    float xn2 = 0.0f;
+    for (size_t d = 0; d < p.D; ++d) xn2 += p.xn2[d * p.nq + q];
+    const float xn2k = xn2;
+    xn2 *= 1.0001f;
+    unsigned cb = 0;
+    for (size_t t = 0; t < p.ntiles; ++t) cb = max(cb, p.cmax2[t]);
+    const float cmax2 = __uint_as_float(cb);
+    // the probe list: the chosen candidates, compacted
+    const unsigned cm = __ballot_sync(0xffffffffu, chosen);
+    // K from the score, or (!cheap) the reference's own f32 distance, relative error eta
+    const float K = cheap ? fmaxf(0.0f, xn2k - 2.0f * ss) : myD;
+    if (chosen) {
+        const int pos = __popc(cm & ((1u << lane) - 1u));
+        p.probes[q * p.nprobe + pos] = part;
+        p.Kq[q * p.nprobe + pos] = K;
     }
-    // W = Kmax (1 + kfac) + sum_d 2 |x'_d| cbmax_d + pcmax + cb2 (see the header), rounded up
-    float kmax = sel_me ? myD * (1.0f + p.kfac) : 0.0f;
+    // W = Kmax + sum_d 2 |x'_d| cbmax_d + pcmax + cb2 (see the header) + the error of K in W's units
+    float kmax = chosen ? K : 0.0f;
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) kmax = fmaxf(kmax, __shfl_xor_sync(0xffffffffu, kmax, off));
-    double qc = 0.0;
-    for (size_t d = lane; d < p.D; d += 32) qc += 2.0 * sqrt((double)p.xn2[d * p.nq + q]) * (double)p.cbmax[d];
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) qc += __shfl_xor_sync(0xffffffffu, qc, off);
-    if (lane == 0)
-        p.Wq[q] = __double2float_ru(((double)kmax * 1.000001 + qc + (double)__uint_as_float(p.bounds[1]) +
-                                     (double)__uint_as_float(p.bounds[0])) * 1.00001);
+    if (lane == 0) {
+        const float ke = cheap ? kerr + 1.3e-7f * sqrtf(kmax) * (sqrtf(xn2) + sqrtf(cmax2)) : 1.01f * p.eta * kmax;
+        p.Wq[q] = __double2float_ru(((double)kmax + (double)qcf + (double)__uint_as_float(p.bounds[1]) +
+                                     (double)__uint_as_float(p.bounds[0])) * 1.00001 +
+                                    1.01 * (double)ke * (double)p.inv_coef);
+    }
 }
 
 // ---- band, exact re-check of the candidates, final selection; one warp per query ------------
@@ -864,6 +979,77 @@ __device__ __forceinline__ float sq_diff2(float qv, float cv, float bv) {
     return __fmul_rn(d, d);
 }
 
+// exact sub-distances of a query's candidates, grouped by partition: a quad of lanes owns one
+// (partition group, division) at a time, keeps l_d = fl(q_d - c_pd) in registers (ITERS float4 per
+// lane, s = 16 ITERS) and walks the group's candidates, so q_d and c_pd are read once per group
+// instead of once per candidate.  Lane tq of the quad owns accumulators 4tq..4tq+3 of the 16-lane
+// dot (src/linalg.rs:12-40).  Candidates are in lanes 0..ncand-1, sorted by partition.
+template <int ITERS>
+__device__ __forceinline__ void quad_groups(const FSelParams &p, const float *qv, uint32_t my_part,
+                                            uint32_t my_vidx, int ncand, unsigned gmask, float *tbuf, int lane) {
+    const int g = lane >> 2, tq = lane & 3, qbase = lane & ~3;
+    const int D = (int)p.D;
+    const size_t s = p.s;
+    const int ngroups = __popc(gmask);
+    const int nitems = ngroups * D;
+    for (int it0 = 0; it0 < nitems; it0 += 8) {
+        const int item = it0 + g;
+        const bool act = item < nitems;
+        const int gi = act ? item / D : 0;
+        const size_t d = act ? (size_t)(item - gi * D) : 0;
+        int gs = (int)__fns(gmask, 0, gi + 1);                                   // first lane of the group
+        int ge = gi + 1 < ngroups ? (int)__fns(gmask, 0, gi + 2) : ncand;        // one past its last
+        if (!act) gs = ge = 0;
+        const uint32_t part = __shfl_sync(0xffffffffu, my_part, gs);
+        const float *xq = qv + d * s;
+        const float *xc = p.coarse + (size_t)part * p.N + d * s;
+        float4 l[ITERS];
+#pragma unroll
+        for (int it = 0; it < ITERS; ++it) {
+            const size_t e = 4 * tq + 16 * it;
+            const float4 x = *reinterpret_cast<const float4 *>(xq + e);
+            const float4 cc = __ldg(reinterpret_cast<const float4 *>(xc + e));
+            l[it] = make_float4(__fsub_rn(x.x, cc.x), __fsub_rn(x.y, cc.y), __fsub_rn(x.z, cc.z),
+                                __fsub_rn(x.w, cc.w));   // localise, src/db/stored.rs:421
+        }
+        int tmax = ge - gs;
+#pragma unroll
+        for (int off = 16; off >= 4; off >>= 1) tmax = max(tmax, __shfl_xor_sync(0xffffffffu, tmax, off));
+        for (int t = 0; t < tmax; ++t) {
+            const int c = gs + t;
+            const bool cact = c < ge;
+            const uint32_t vidx = __shfl_sync(0xffffffffu, my_vidx, cact ? c : 0);
+            const uint8_t code = cact ? p.codes[p.part_cstart[part] + (size_t)vidx * D + d] : (uint8_t)0;
+            const float *xb = p.codebooks + (d * p.C + code) * s;
+            float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+#pragma unroll
+            for (int it = 0; it < ITERS; ++it) {
+                const float4 b = __ldg(reinterpret_cast<const float4 *>(xb + 4 * tq + 16 * it));
+                float dd = __fsub_rn(l[it].x, b.x);   // subtract, src/db/stored.rs:565-571
+                a0 = __fadd_rn(a0, __fmul_rn(dd, dd));
+                dd = __fsub_rn(l[it].y, b.y);
+                a1 = __fadd_rn(a1, __fmul_rn(dd, dd));
+                dd = __fsub_rn(l[it].z, b.z);
+                a2 = __fadd_rn(a2, __fmul_rn(dd, dd));
+                dd = __fsub_rn(l[it].w, b.w);
+                a3 = __fadd_rn(a3, __fmul_rn(dd, dd));
+            }
+            float T = 0.0f;  // sum_naive over the 16 accumulators, src/linalg.rs:39
+#pragma unroll
+            for (int t4 = 0; t4 < 4; ++t4) {
+                if (tq == t4) {
+                    T = __fadd_rn(T, a0);
+                    T = __fadd_rn(T, a1);
+                    T = __fadd_rn(T, a2);
+                    T = __fadd_rn(T, a3);
+                }
+                T = __shfl_sync(0xffffffffu, T, qbase + t4);
+            }
+            if (cact && tq == 0) tbuf[(size_t)c * D + d] = T;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(128) fselect_kernel(FSelParams p) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t q = p.q0 + (size_t)blockIdx.x * 4 + warp;
@@ -887,14 +1073,17 @@ __global__ void __launch_bounds__(128) fselect_kernel(FSelParams p) {
         const float tau = __shfl_sync(0xffffffffu, a, k - 1);
         const float hi = (tau + E) * (1.0f + p.eta3) + E;
         const float thr = tau + 2.0f * (hi - tau);
-        if (!(fabsf(thr) < 1e30f)) fb = true;  // NaN or overflow
+        int why = 0;
+        if (!(fabsf(thr) < 1e30f)) fb = true, why = 6;  // NaN or overflow
         ncand = __popc(__ballot_sync(0xffffffffu, lane < cnt && a <= thr));
-        if (ncand == p.ncap && total > (uint32_t)p.ncap) fb = true;  // the list may be incomplete
+        if (ncand == p.ncap && total > (uint32_t)p.ncap) fb = true, why = why ? why : 7;  // the list may be incomplete
+        if (fb && lane == 0 && !p.qbad[q]) atomicAdd(&p.counters[why], 1ull);
     }
     if (fb) {
         if (lane == 0) {
             p.fb_list[atomicAdd(&p.counters[0], 1ull)] = (uint32_t)q;
-            if (p.qbad[q] & 2u) atomicAdd(&p.counters[3], 1ull);  // its probes are not the reference's
+            if (p.qbad[q] & 1u) atomicAdd(&p.counters[4], 1ull);  // non-finite table or pair constant
+            if (p.qbad[q] & 2u) atomicAdd(&p.counters[5], 1ull);  // the probe filter gave up
         }
         return;
     }
@@ -918,41 +1107,61 @@ __global__ void __launch_bounds__(128) fselect_kernel(FSelParams p) {
         // loads 128 bits at a time; the lane sums are chained through the quad in lane order
         extern __shared__ float tbuf_all[];
         float *tbuf = tbuf_all + (size_t)warp * RCAP * D;   // [candidate][division]
+        const int iters = (int)(s >> 4);
+        if (iters == 8 || iters == 4 || iters == 2 || iters == 1) {
+            // candidates ordered by partition; a group = the candidates of one partition
+            int prank = 0, psrc = 0;
+            for (int jx = 0; jx < ncand; ++jx) {
+                const uint32_t pj = __shfl_sync(0xffffffffu, my_part, jx);
+                prank += (pj < my_part) || (pj == my_part && jx < lane);
+            }
+            for (int jx = 0; jx < ncand; ++jx)
+                if (__shfl_sync(0xffffffffu, prank, jx) == lane) psrc = jx;
+            my_part = __shfl_sync(0xffffffffu, my_part, psrc);
+            my_vidx = __shfl_sync(0xffffffffu, my_vidx, psrc);
+            const uint32_t prevp = __shfl_up_sync(0xffffffffu, my_part, 1);
+            const unsigned gmask = __ballot_sync(0xffffffffu, lane < ncand && (lane == 0 || prevp != my_part));
+            if (iters == 8) quad_groups<8>(p, qv, my_part, my_vidx, ncand, gmask, tbuf, lane);
+            else if (iters == 4) quad_groups<4>(p, qv, my_part, my_vidx, ncand, gmask, tbuf, lane);
+            else if (iters == 2) quad_groups<2>(p, qv, my_part, my_vidx, ncand, gmask, tbuf, lane);
+            else quad_groups<1>(p, qv, my_part, my_vidx, ncand, gmask, tbuf, lane);
+        } else {
         const int g = lane >> 2, tq = lane & 3, qbase = lane & ~3;
-        const int nitems = ncand * (int)D;
-        for (int it0 = 0; it0 < nitems; it0 += 8) {
-            const int item = it0 + g;
-            const bool act = item < nitems;
-            const int c = act ? item / (int)D : 0;
-            const size_t d = act ? (size_t)(item - c * (int)D) : 0;
-            const uint32_t part = __shfl_sync(0xffffffffu, my_part, c);
-            const uint32_t vidx = __shfl_sync(0xffffffffu, my_vidx, c);
-            const uint8_t code = p.codes[p.part_cstart[part] + (size_t)vidx * D + d];
-            const float *xq = qv + d * s;
-            const float *xc = p.coarse + (size_t)part * p.N + d * s;
-            const float *xb = p.codebooks + (d * p.C + code) * s;
-            float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
-            for (size_t e = 4 * tq; e < s; e += 16) {
-                const float4 x = *reinterpret_cast<const float4 *>(xq + e);
-                const float4 cc = __ldg(reinterpret_cast<const float4 *>(xc + e));
-                const float4 b = __ldg(reinterpret_cast<const float4 *>(xb + e));
-                a0 = __fadd_rn(a0, sq_diff2(x.x, cc.x, b.x));
-                a1 = __fadd_rn(a1, sq_diff2(x.y, cc.y, b.y));
-                a2 = __fadd_rn(a2, sq_diff2(x.z, cc.z, b.z));
-                a3 = __fadd_rn(a3, sq_diff2(x.w, cc.w, b.w));
-            }
-            float T = 0.0f;  // sum_naive over the 16 accumulators, src/linalg.rs:39
-#pragma unroll
-            for (int t4 = 0; t4 < 4; ++t4) {
-                if (tq == t4) {
-                    T = __fadd_rn(T, a0);
-                    T = __fadd_rn(T, a1);
-                    T = __fadd_rn(T, a2);
-                    T = __fadd_rn(T, a3);
+            const int nitems = ncand * (int)D;
+            for (int it0 = 0; it0 < nitems; it0 += 8) {
+                const int item = it0 + g;
+                const bool act = item < nitems;
+                const int c = act ? item / (int)D : 0;
+                const size_t d = act ? (size_t)(item - c * (int)D) : 0;
+                const uint32_t part = __shfl_sync(0xffffffffu, my_part, c);
+                const uint32_t vidx = __shfl_sync(0xffffffffu, my_vidx, c);
+                const uint8_t code = p.codes[p.part_cstart[part] + (size_t)vidx * D + d];
+                const float *xq = qv + d * s;
+                const float *xc = p.coarse + (size_t)part * p.N + d * s;
+                const float *xb = p.codebooks + (d * p.C + code) * s;
+                float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+                for (size_t e = 4 * tq; e < s; e += 16) {
+                    const float4 x = *reinterpret_cast<const float4 *>(xq + e);
+                    const float4 cc = __ldg(reinterpret_cast<const float4 *>(xc + e));
+                    const float4 b = __ldg(reinterpret_cast<const float4 *>(xb + e));
+                    a0 = __fadd_rn(a0, sq_diff2(x.x, cc.x, b.x));
+                    a1 = __fadd_rn(a1, sq_diff2(x.y, cc.y, b.y));
+                    a2 = __fadd_rn(a2, sq_diff2(x.z, cc.z, b.z));
+                    a3 = __fadd_rn(a3, sq_diff2(x.w, cc.w, b.w));
                 }
-                T = __shfl_sync(0xffffffffu, T, qbase + t4);
+                float T = 0.0f;  // sum_naive over the 16 accumulators, src/linalg.rs:39
+#pragma unroll
+                for (int t4 = 0; t4 < 4; ++t4) {
+                    if (tq == t4) {
+                        T = __fadd_rn(T, a0);
+                        T = __fadd_rn(T, a1);
+                        T = __fadd_rn(T, a2);
+                        T = __fadd_rn(T, a3);
+                    }
+                    T = __shfl_sync(0xffffffffu, T, qbase + t4);
+                }
+                if (act && tq == 0) tbuf[item] = T;
             }
-            if (act && tq == 0) tbuf[item] = T;
         }
         __syncwarp();
         if (lane < ncand)  // dist = 0; dist += table[..] in division order, src/db/stored.rs:581-587
@@ -1006,7 +1215,10 @@ __global__ void __launch_bounds__(128) fselect_kernel(FSelParams p) {
     // push history
     const bool hard = mine && ((myR != myR) || (tie && rank < k));
     if (__any_sync(0xffffffffu, hard)) {
-        if (lane == 0) p.fb_list[atomicAdd(&p.counters[0], 1ull)] = (uint32_t)q;
+        if (lane == 0) {
+            p.fb_list[atomicAdd(&p.counters[0], 1ull)] = (uint32_t)q;
+            atomicAdd(&p.counters[8], 1ull);  // exact tie (or NaN) among the k best
+        }
         return;
     }
     const int keep = min(k, ncand);
@@ -1039,6 +1251,7 @@ __global__ void __launch_bounds__(256) stash_undecided_kernel(const unsigned lon
         bcounters[1] += counters[1];
         bcounters[2] += counters[2];
         bcounters[3] += counters[3];
+        for (int i = 4; i < 12; ++i) bcounters[i] += counters[i];   // why queries were handed back
     }
 }
 
@@ -1092,9 +1305,9 @@ int filter_prepare(fdb_index *ix) {
     FDB_TRY(fs->pc.alloc(P * D * C));
     FDB_TRY(fs->cbmax.alloc(D));
     FDB_TRY(fs->bounds.alloc(2));
-    FDB_TRY(fs->counters.alloc(4));
-    FDB_TRY(fs->bcounters.alloc(4));
-    FDB_CUDA(cudaMallocHost((void **)&fs->h_counters, 4 * sizeof(unsigned long long)));
+    FDB_TRY(fs->counters.alloc(12));
+    FDB_TRY(fs->bcounters.alloc(12));
+    FDB_CUDA(cudaMallocHost((void **)&fs->h_counters, 12 * sizeof(unsigned long long)));
     FDB_CUDA(cudaMemsetAsync(fs->bounds.p, 0, 2 * sizeof(unsigned), st));
     // which GEMMs run on the tensor pipe (tcgen05, bf16 3-term split); both operands are then
     // centred by the mean of the coarse centroids, which shrinks |x'| |c'| and with it the band
@@ -1207,21 +1420,38 @@ int filter_probe(fdb_index *ix, const float *d_q, size_t nq, size_t nprobe, Even
     pp.gamma1 = tc_gamma(N);
     pp.eta = ((float)N / 16.0f + 20.0f) * U24;   // the reference's own f32 evaluation of one distance
     pp.probes = ix->probes.p;
-    pp.probe_d = ix->probe_d.p;
     pp.hard = fs->hard.p;
+    pp.nexact = fs->bcounters.p + 3;
     pp.cbmax = fs->cbmax.p;
     pp.bounds = fs->bounds.p;
     FDB_TRY(fs->Kq.ensure(nq * nprobe));
     FDB_TRY(fs->Wq.ensure(nq));
     pp.Kq = fs->Kq.p;
     pp.Wq = fs->Wq.p;
-    pp.kfac = 1.01f * pp.eta / adc_coef(s, D, fs->tc_g);
+    pp.inv_coef = 1.0f / adc_coef(s, D, fs->tc_g);
     pp.quad = (N % 16 == 0) ? 1 : 0;   // d_q is 16-byte aligned here, the centroid rows always are
     pp.use_smem = P <= 4096 ? 1 : 0;
+    FDB_TRY(fs->ps_part.ensure(nq * 32));
+    FDB_TRY(fs->ps_ss.ensure(nq * 32));
+    FDB_TRY(fs->ps_meta.ensure(nq * 8));
+    FDB_TRY(fs->ps_items.ensure(nq * 64));
+    FDB_TRY(fs->ps_dist.ensure(nq * 32));
+    FDB_TRY(fs->ps_count.ensure(1));
+    FDB_CUDA(cudaMemsetAsync(fs->ps_count.p, 0, sizeof(unsigned), st));
+    pp.st_part = fs->ps_part.p;
+    pp.st_ss = fs->ps_ss.p;
+    pp.st_meta = fs->ps_meta.p;
+    pp.items = fs->ps_items.p;
+    pp.item_d = fs->ps_dist.p;
+    pp.item_count = fs->ps_count.p;
     const size_t psmem = pp.use_smem ? 4 * (P + 32) * sizeof(float) : 0;
-    FDB_CUDA(cudaFuncSetAttribute(probe_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(psmem, 1024)));
-    probe_filter_kernel<<<(unsigned)((nq + 3) / 4), 128, psmem, st>>>(pp);
-    ctx->launches++;
+    FDB_CUDA(cudaFuncSetAttribute(probe_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(psmem, 1024)));
+    // select (scores -> candidates, band) -> exact distances of the ambiguous pairs, spread over the
+    // whole GPU -> finalize (probe list, K, W)
+    probe_select_kernel<<<(unsigned)((nq + 3) / 4), 128, psmem, st>>>(pp);
+    probe_exact_kernel<<<(unsigned)std::min<size_t>((nq * 32 * 4 + 255) / 256, (size_t)ctx->sm_count * 8), 256, 0, st>>>(pp);
+    probe_finalize_kernel<<<(unsigned)((nq + 3) / 4), 128, 0, st>>>(pp);
+    ctx->launches += 3;
     FDB_CHECK_LAUNCH();
     fs->probes_from_filter = true;
     *done = true;
@@ -1233,7 +1463,7 @@ int filter_batch_begin(fdb_index *ix, size_t nq_total, size_t nprobe) {
     FDB_TRY(fs->bfb_q.ensure(nq_total));
     FDB_TRY(fs->bfb_probes.ensure(nq_total * nprobe));
     fs->bfb_cap = nq_total;
-    FDB_CUDA(cudaMemsetAsync(fs->bcounters.p, 0, 4 * sizeof(unsigned long long), ix->ctx->stream));
+    FDB_CUDA(cudaMemsetAsync(fs->bcounters.p, 0, 12 * sizeof(unsigned long long), ix->ctx->stream));
     return FDB_OK;
 }
 
@@ -1241,17 +1471,24 @@ int filter_batch_end(fdb_index *ix, size_t nq_total, const uint32_t **d_fb_q, co
                      unsigned *h_nfb, unsigned *h_nhard) {
     FilterState *fs = ix->filter;
     cudaStream_t st = ix->ctx->stream;
-    FDB_CUDA(cudaMemcpyAsync(fs->h_counters, fs->bcounters.p, 4 * sizeof(unsigned long long),
+    FDB_CUDA(cudaMemcpyAsync(fs->h_counters, fs->bcounters.p, 12 * sizeof(unsigned long long),
                              cudaMemcpyDeviceToHost, st));
     FDB_CUDA(cudaStreamSynchronize(st));
     *h_nfb = (unsigned)fs->h_counters[0];
-    *h_nhard = (unsigned)fs->h_counters[3];
+    // lists made by the probe filter are the reference's probe set in no particular order: the
+    // exact pipeline selects its own (the order matters for the ties it is there to resolve)
+    *h_nhard = fs->probes_from_filter ? *h_nfb : 0;
     *d_fb_q = fs->bfb_q.p;
     *d_fb_probes = fs->bfb_probes.p;
     ix->last_stats[0] = nq_total - fs->h_counters[0];
     ix->last_stats[1] = fs->h_counters[0];
     ix->last_stats[2] = fs->h_counters[1];
     ix->last_stats[3] = fs->h_counters[2];
+    if (getenv("FDB_FILTER_STATS"))
+        fprintf(stderr, "[fdb filter] queries=%zu handed back=%llu: non-finite=%llu probe filter=%llu band=%llu "
+                        "list overflow=%llu exact tie=%llu; partitions evaluated exactly=%llu\n",
+                nq_total, fs->h_counters[0], fs->h_counters[4], fs->h_counters[5], fs->h_counters[6],
+                fs->h_counters[7], fs->h_counters[8], fs->h_counters[3]);
     return FDB_OK;
 }
 
@@ -1274,7 +1511,7 @@ int filter_query(fdb_index *ix, const float *d_q, size_t q_base, size_t nq, size
     FDB_TRY(fs->qbad.ensure(nq));
     FDB_TRY(fs->fb_list.ensure(nq));
     FDB_TRY(fs->hard.ensure(nq));
-    FDB_CUDA(cudaMemsetAsync(fs->counters.p, 0, 4 * sizeof(unsigned long long), st));
+    FDB_CUDA(cudaMemsetAsync(fs->counters.p, 0, 12 * sizeof(unsigned long long), st));
 
     FDB_TRY(log->mark(2));
     if (!fs->probes_from_filter) {  // the probe filter already left K and W behind

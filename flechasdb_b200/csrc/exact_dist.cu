@@ -279,6 +279,42 @@ __global__ void exact_generic_kernel(TileParams p) {
     }
 }
 
+// few rows (the queries the filter path hands back): one quad of lanes per (row, problem,
+// centroid) item instead of a 32-row tile per CTA, so that even a single row spreads over the
+// whole GPU.  m % 16 == 0; lane tq of the quad owns accumulators 4tq..4tq+3.
+__global__ void __launch_bounds__(256) exact_pairs_kernel(TileParams p) {
+    const size_t item = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    const int lane = threadIdx.x & 31, tq = lane & 3, qbase = lane & ~3;
+    const size_t total = p.n * p.nb * p.k;
+    const bool act = item < total;
+    const size_t it = act ? item : 0;
+    const size_t row = it / (p.nb * p.k), rem = it - row * p.nb * p.k;
+    const size_t b = rem / p.k, j = rem - b * p.k;
+    const float *x = p.x + row * p.ldx + p.col_off + b * p.m;
+    const float *c = p.c + (b * p.k + j) * p.m;
+    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+    for (size_t e = 4 * tq; e < p.m; e += 16) {
+        const float4 xv = *reinterpret_cast<const float4 *>(x + e);
+        const float4 cv = *reinterpret_cast<const float4 *>(c + e);
+        a0 = sq_acc(a0, xv.x, cv.x);
+        a1 = sq_acc(a1, xv.y, cv.y);
+        a2 = sq_acc(a2, xv.z, cv.z);
+        a3 = sq_acc(a3, xv.w, cv.w);
+    }
+    float sum = 0.0f;  // sum_naive over the 16 lanes (src/linalg.rs:39), chained through the quad
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        if (tq == t) {
+            sum = __fadd_rn(sum, a0);
+            sum = __fadd_rn(sum, a1);
+            sum = __fadd_rn(sum, a2);
+            sum = __fadd_rn(sum, a3);
+        }
+        sum = __shfl_sync(0xffffffffu, sum, qbase + t);
+    }
+    if (act && tq == 0) p.out_mat[(row * p.nb + b) * p.k + j] = sum;
+}
+
 template <int MODE>
 int launch(fdb_ctx *ctx, const DistProblem &q, uint32_t *d_idx, size_t idx_stride, float *d_out) {
     if (q.n == 0 || q.k == 0 || q.nb == 0) return FDB_OK;
@@ -302,7 +338,10 @@ int launch(fdb_ctx *ctx, const DistProblem &q, uint32_t *d_idx, size_t idx_strid
     }
     const bool aligned = (q.m % 16 == 0) && (q.ldx % 4 == 0) && (q.col_off % 4 == 0) &&
                          ((uintptr_t)q.x % 16 == 0) && ((uintptr_t)q.c % 16 == 0);
-    if (aligned) {
+    const size_t tile_ctas = ((q.n + TM - 1) / TM) * q.nb, items = q.n * q.nb * q.k;
+    if (MODE == 1 && aligned && !q.active && tile_ctas * 2 < (size_t)ctx->sm_count && items <= (1u << 22)) {
+        exact_pairs_kernel<<<(unsigned)((items * 4 + 255) / 256), 256, 0, ctx->stream>>>(p);
+    } else if (aligned) {
         dim3 grid((unsigned)((q.n + TM - 1) / TM), (unsigned)q.nb);
         if (q.m % 64 == 0) exact_tile_kernel<MODE, 64><<<grid, TILE_THREADS, 0, ctx->stream>>>(p);
         else if (q.m % 32 == 0) exact_tile_kernel<MODE, 32><<<grid, TILE_THREADS, 0, ctx->stream>>>(p);

@@ -9,7 +9,8 @@ M, N, P, D, CN, NQ, K, NPROBE = 100000, 1536, 100, 12, 256, 10000, 10, 5
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 rng = np.random.default_rng(0)
 ctx = engine.Context(0)
-coarse = rng.random((P, N), dtype=np.float32)
+# centroids like k-means leaves them on uniform data: means of ~M/P vectors
+coarse = (0.5 + rng.normal(0.0, (1.0 / (12.0 * M / P)) ** 0.5, (P, N))).astype(np.float32)
 cbs = rng.random((D, CN, N // D), dtype=np.float32) - np.float32(0.5)
 sizes = rng.multinomial(M, np.ones(P) / P)
 off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)

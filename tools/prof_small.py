@@ -7,7 +7,7 @@ from flechasdb_b200 import engine
 M, N, P, D, CN, K, NPROBE = 100000, 1536, 100, 12, 256, 10, 5
 rng = np.random.default_rng(0)
 ctx = engine.Context(0)
-coarse = rng.random((P, N), dtype=np.float32)
+coarse = (0.5 + rng.normal(0.0, (1.0 / (12.0 * M / P)) ** 0.5, (P, N))).astype(np.float32)
 cbs = rng.random((D, CN, N // D), dtype=np.float32) - np.float32(0.5)
 sizes = rng.multinomial(M, np.ones(P) / P)
 off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
