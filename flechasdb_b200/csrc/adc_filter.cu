@@ -828,17 +828,41 @@ __global__ void __launch_bounds__(256) probe_exact_kernel(ProbeParams p) {
             const float *qv = p.q + (size_t)qi * p.N;
             const float *cv = p.coarse + (size_t)pc * p.N;
             float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
-            for (size_t e = 4 * tq; e < p.N; e += 16) {
-                const float4 x = __ldg(reinterpret_cast<const float4 *>(qv + e));
-                const float4 cc = __ldg(reinterpret_cast<const float4 *>(cv + e));
-                float d = __fsub_rn(x.x, cc.x);
-                a0 = __fadd_rn(a0, __fmul_rn(d, d));
-                d = __fsub_rn(x.y, cc.y);
-                a1 = __fadd_rn(a1, __fmul_rn(d, d));
-                d = __fsub_rn(x.z, cc.z);
-                a2 = __fadd_rn(a2, __fmul_rn(d, d));
-                d = __fsub_rn(x.w, cc.w);
-                a3 = __fadd_rn(a3, __fmul_rn(d, d));
+            // software pipeline: the next PF float4 pairs are in flight while the current ones are summed
+            constexpr int PF = 4;
+            float4 xb[PF], cb[PF];
+            const size_t iters = p.N / 16;
+#pragma unroll
+            for (int u = 0; u < PF; ++u)
+                if ((size_t)u < iters) {
+                    xb[u] = __ldg(reinterpret_cast<const float4 *>(qv + 4 * tq + 16 * u));
+                    cb[u] = __ldg(reinterpret_cast<const float4 *>(cv + 4 * tq + 16 * u));
+                }
+            for (size_t i0 = 0; i0 < iters; i0 += PF) {
+                float4 xn[PF], cn[PF];
+#pragma unroll
+                for (int u = 0; u < PF; ++u)
+                    if (i0 + PF + u < iters) {
+                        xn[u] = __ldg(reinterpret_cast<const float4 *>(qv + 4 * tq + 16 * (i0 + PF + u)));
+                        cn[u] = __ldg(reinterpret_cast<const float4 *>(cv + 4 * tq + 16 * (i0 + PF + u)));
+                    }
+#pragma unroll
+                for (int u = 0; u < PF; ++u)
+                    if (i0 + u < iters) {
+                        float d = __fsub_rn(xb[u].x, cb[u].x);
+                        a0 = __fadd_rn(a0, __fmul_rn(d, d));
+                        d = __fsub_rn(xb[u].y, cb[u].y);
+                        a1 = __fadd_rn(a1, __fmul_rn(d, d));
+                        d = __fsub_rn(xb[u].z, cb[u].z);
+                        a2 = __fadd_rn(a2, __fmul_rn(d, d));
+                        d = __fsub_rn(xb[u].w, cb[u].w);
+                        a3 = __fadd_rn(a3, __fmul_rn(d, d));
+                    }
+#pragma unroll
+                for (int u = 0; u < PF; ++u) {
+                    xb[u] = xn[u];
+                    cb[u] = cn[u];
+                }
             }
             float T = 0.0f;  // sum_naive over the 16 accumulators, src/linalg.rs:39
 #pragma unroll

@@ -282,6 +282,7 @@ __global__ void exact_generic_kernel(TileParams p) {
 // few rows (the queries the filter path hands back): one quad of lanes per (row, problem,
 // centroid) item instead of a 32-row tile per CTA, so that even a single row spreads over the
 // whole GPU.  m % 16 == 0; lane tq of the quad owns accumulators 4tq..4tq+3.
+template <bool PIPE>
 __global__ void __launch_bounds__(256) exact_pairs_kernel(TileParams p) {
     const size_t item = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
     const int lane = threadIdx.x & 31, tq = lane & 3, qbase = lane & ~3;
@@ -293,13 +294,49 @@ __global__ void __launch_bounds__(256) exact_pairs_kernel(TileParams p) {
     const float *x = p.x + row * p.ldx + p.col_off + b * p.m;
     const float *c = p.c + (b * p.k + j) * p.m;
     float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
-    for (size_t e = 4 * tq; e < p.m; e += 16) {
-        const float4 xv = *reinterpret_cast<const float4 *>(x + e);
-        const float4 cv = *reinterpret_cast<const float4 *>(c + e);
-        a0 = sq_acc(a0, xv.x, cv.x);
-        a1 = sq_acc(a1, xv.y, cv.y);
-        a2 = sq_acc(a2, xv.z, cv.z);
-        a3 = sq_acc(a3, xv.w, cv.w);
+    if (PIPE) {
+        // long rows: software pipeline, the next PF float4 pairs are in flight while the current
+        // ones are summed (the sums are sequential per accumulator, the loads are not)
+        constexpr int PF = 8;
+        float4 xb[PF], cb[PF];
+        const size_t iters = p.m / 16;
+#pragma unroll
+        for (int u = 0; u < PF; ++u)
+            if ((size_t)u < iters) {
+                xb[u] = __ldg(reinterpret_cast<const float4 *>(x + 4 * tq + 16 * u));
+                cb[u] = __ldg(reinterpret_cast<const float4 *>(c + 4 * tq + 16 * u));
+            }
+        for (size_t i0 = 0; i0 < iters; i0 += PF) {
+            float4 xn[PF], cn[PF];
+#pragma unroll
+            for (int u = 0; u < PF; ++u)
+                if (i0 + PF + u < iters) {
+                    xn[u] = __ldg(reinterpret_cast<const float4 *>(x + 4 * tq + 16 * (i0 + PF + u)));
+                    cn[u] = __ldg(reinterpret_cast<const float4 *>(c + 4 * tq + 16 * (i0 + PF + u)));
+                }
+#pragma unroll
+            for (int u = 0; u < PF; ++u)
+                if (i0 + u < iters) {
+                    a0 = sq_acc(a0, xb[u].x, cb[u].x);
+                    a1 = sq_acc(a1, xb[u].y, cb[u].y);
+                    a2 = sq_acc(a2, xb[u].z, cb[u].z);
+                    a3 = sq_acc(a3, xb[u].w, cb[u].w);
+                }
+#pragma unroll
+            for (int u = 0; u < PF; ++u) {
+                xb[u] = xn[u];
+                cb[u] = cn[u];
+            }
+        }
+    } else {
+        for (size_t e = 4 * tq; e < p.m; e += 16) {
+            const float4 xv = *reinterpret_cast<const float4 *>(x + e);
+            const float4 cv = *reinterpret_cast<const float4 *>(c + e);
+            a0 = sq_acc(a0, xv.x, cv.x);
+            a1 = sq_acc(a1, xv.y, cv.y);
+            a2 = sq_acc(a2, xv.z, cv.z);
+            a3 = sq_acc(a3, xv.w, cv.w);
+        }
     }
     float sum = 0.0f;  // sum_naive over the 16 lanes (src/linalg.rs:39), chained through the quad
 #pragma unroll
@@ -340,7 +377,8 @@ int launch(fdb_ctx *ctx, const DistProblem &q, uint32_t *d_idx, size_t idx_strid
                          ((uintptr_t)q.x % 16 == 0) && ((uintptr_t)q.c % 16 == 0);
     const size_t tile_ctas = ((q.n + TM - 1) / TM) * q.nb, items = q.n * q.nb * q.k;
     if (MODE == 1 && aligned && !q.active && tile_ctas * 2 < (size_t)ctx->sm_count && items <= (1u << 22)) {
-        exact_pairs_kernel<<<(unsigned)((items * 4 + 255) / 256), 256, 0, ctx->stream>>>(p);
+        if (q.m >= 512) exact_pairs_kernel<true><<<(unsigned)((items * 4 + 255) / 256), 256, 0, ctx->stream>>>(p);
+        else exact_pairs_kernel<false><<<(unsigned)((items * 4 + 255) / 256), 256, 0, ctx->stream>>>(p);
     } else if (aligned) {
         dim3 grid((unsigned)((q.n + TM - 1) / TM), (unsigned)q.nb);
         if (q.m % 64 == 0) exact_tile_kernel<MODE, 64><<<grid, TILE_THREADS, 0, ctx->stream>>>(p);

@@ -593,8 +593,11 @@ int exact_after_probe(fdb_index *ix, const float *d_q, const uint32_t *d_probes,
     // fast path: one warp per pair with register-resident selection
     const int w_chunk_vecs = (int)std::max<size_t>(32, (2048 / ix->D) & ~(size_t)31);
     const size_t w_per_warp = DC * 4 + 2 * (size_t)w_chunk_vecs * ix->D;
+    // (a handful of pairs, as handed back by the filter path: a CTA per pair evaluates the list with
+    // all its warps, only the selection itself is sequential)
+    const bool few_pairs = getenv("FDB_SCAN_FEW_BLOCK") && npairs < (size_t)ctx->sm_count * 4;  // (measured slower)
     const bool warp_path = k <= 32 && (DC & 3) == 0 && w_per_warp * SCANW_WARPS <= 96 * 1024 &&
-                           !getenv("FDB_SCAN_BLOCK");
+                           !getenv("FDB_SCAN_BLOCK") && !few_pairs;
     if (warp_path) {
         FDB_CUDA(cudaFuncSetAttribute(scan_warp_kernel<RegNBest>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)(w_per_warp * SCANW_WARPS)));
