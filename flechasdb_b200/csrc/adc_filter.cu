@@ -56,24 +56,38 @@ struct FilterState {
     size_t bfb_cap = 0;
     bool tc_g = false, tc_coarse = false;
     TcCentroids cb_tc, coarse_tc;   // bf16 pieces of the centred code vectors / coarse centroids
-    TcRows rows;                    // bf16 pieces of the centred queries of the current batch
-    DevBuf<float> S;                // [nq][ldS] approximate coarse scores x'.c' - |c'|^2/2
-    DevBuf<unsigned> hard;          // [nq] the probe filter could not decide: exact pipeline
-    DevBuf<uint32_t> ps_part, ps_meta, ps_items;   // state of the probe filter's three kernels
-    DevBuf<float> ps_ss, ps_dist;
-    DevBuf<unsigned> ps_count;
-    bool rows_ready = false, probes_from_filter = false;
-    DevBuf<float> G;             // [chunk_q][D][C]
-    DevBuf<float> Kq, Wq;        // [nq][nprobe], [nq]
-    DevBuf<float> cand_d;        // [nq][32]
-    DevBuf<uint32_t> cand_a, cand_cnt, cand_total;
-    DevBuf<unsigned> qbad;       // [nq]
-    DevBuf<uint32_t> fb_list;    // [nq]
-    DevBuf<unsigned long long> counters;  // [0] fallbacks, [1] exact candidates, [2] scanned vectors
+    // per-slice scratch; two slots so that consecutive slices of a host batch can run on two streams
+    struct Slot {
+        TcRows rows;                    // bf16 pieces of the centred queries of the slice
+        DevBuf<float> S;                // [nq][ldS] approximate coarse scores x'.c' - |c'|^2/2
+        DevBuf<unsigned> hard;          // [nq] the probe filter could not decide: exact pipeline
+        DevBuf<uint32_t> probes;        // [nq][nprobe] probe lists made by the probe filter
+        DevBuf<uint32_t> ps_part, ps_meta, ps_items;   // state of the probe filter's three kernels
+        DevBuf<float> ps_ss, ps_dist;
+        DevBuf<unsigned> ps_count;
+        bool rows_ready = false, probes_from_filter = false;
+        DevBuf<float> G;             // [chunk_q][D][C]
+        DevBuf<float> Kq, Wq;        // [nq][nprobe], [nq]
+        DevBuf<float> cand_d;        // [nq][32]
+        DevBuf<uint32_t> cand_a, cand_cnt, cand_total;
+        DevBuf<unsigned> qbad;       // [nq]
+        DevBuf<uint32_t> fb_list;    // [nq]
+        DevBuf<unsigned long long> counters;  // [0] fallbacks, [1] exact candidates, [2] scanned vectors, [4..] reasons
+        cudaStream_t stream = nullptr;
+        cudaEvent_t done = nullptr;
+    } slot[2];
+    Slot *cur = &slot[0];
+    bool batch_reprobe = false;      // some slice of the batch took its probe lists from the probe filter
+    cudaEvent_t begun = nullptr;     // batch_begin's resets, the slot streams wait for it
     unsigned long long *h_counters = nullptr;  // pinned
     size_t chunk_q = 4096;
     ~FilterState() {
         if (h_counters) cudaFreeHost(h_counters);
+        for (Slot &sl : slot) {
+            if (sl.stream) cudaStreamDestroy(sl.stream);
+            if (sl.done) cudaEventDestroy(sl.done);
+        }
+        if (begun) cudaEventDestroy(begun);
     }
 };
 
@@ -1263,20 +1277,18 @@ __global__ void __launch_bounds__(256) stash_undecided_kernel(const unsigned lon
                                                               unsigned long long *bcounters, uint32_t *bfb_q,
                                                               uint32_t *bfb_probes) {
     const unsigned n = (unsigned)counters[0];
-    const unsigned long long base = bcounters[0];   // one CTA, slices run in stream order
+    __shared__ unsigned long long base_s;   // slices may run concurrently on two streams: reserve atomically
+    if (threadIdx.x == 0) base_s = atomicAdd(&bcounters[0], (unsigned long long)n);
+    __syncthreads();
+    const unsigned long long base = base_s;
     for (unsigned i = threadIdx.x; i < n * (unsigned)nprobe; i += blockDim.x) {
         const unsigned r = i / nprobe, e = i - r * nprobe;
         bfb_probes[(base + r) * nprobe + e] = probes[(size_t)fb_list[r] * nprobe + e];
         if (e == 0) bfb_q[base + r] = (uint32_t)(q_base + fb_list[r]);
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        bcounters[0] = base + n;
-        bcounters[1] += counters[1];
-        bcounters[2] += counters[2];
-        bcounters[3] += counters[3];
-        for (int i = 4; i < 12; ++i) bcounters[i] += counters[i];   // why queries were handed back
-    }
+    if (threadIdx.x == 0)
+        for (int i = 1; i < 12; ++i) atomicAdd(&bcounters[i], counters[i]);   // statistics, why queries were handed back
 }
 
 size_t scan_smem_bytes(const fdb_index *ix, int chunk_vecs, size_t rb) {
@@ -1329,7 +1341,7 @@ int filter_prepare(fdb_index *ix) {
     FDB_TRY(fs->pc.alloc(P * D * C));
     FDB_TRY(fs->cbmax.alloc(D));
     FDB_TRY(fs->bounds.alloc(2));
-    FDB_TRY(fs->counters.alloc(12));
+    for (FilterState::Slot &sl : fs->slot) FDB_TRY(sl.counters.alloc(12));
     FDB_TRY(fs->bcounters.alloc(12));
     FDB_CUDA(cudaMallocHost((void **)&fs->h_counters, 12 * sizeof(unsigned long long)));
     FDB_CUDA(cudaMemsetAsync(fs->bounds.p, 0, 2 * sizeof(unsigned), st));
@@ -1410,27 +1422,27 @@ static float adc_coef(size_t s, size_t D, bool tc_g) {
 int filter_probe(fdb_index *ix, const float *d_q, size_t nq, size_t nprobe, EventLog *log, bool *done) {
     fdb_ctx *ctx = ix->ctx;
     FilterState *fs = ix->filter;
+    FilterState::Slot *sl = fs->cur;
     cudaStream_t st = ctx->stream;
     const size_t N = ix->N, P = ix->P, D = ix->D, s = ix->s;
     *done = false;
-    fs->rows_ready = false;
-    fs->probes_from_filter = false;
-    FDB_TRY(fs->hard.ensure(nq));
-    FDB_CUDA(cudaMemsetAsync(fs->hard.p, 0, nq * sizeof(unsigned), st));
+    sl->rows_ready = false;
+    sl->probes_from_filter = false;
+    FDB_TRY(sl->hard.ensure(nq));
+    FDB_CUDA(cudaMemsetAsync(sl->hard.p, 0, nq * sizeof(unsigned), st));
     if (!fs->tc_coarse || nprobe > 24 || (uintptr_t)d_q % 16 != 0) return FDB_OK;
     FDB_TRY(log->mark(0));
-    FDB_TRY(tc_prepare_rows(ctx, d_q, nq, N, s, D, fs->mu.p, &fs->rows));
-    fs->rows_ready = true;
+    FDB_TRY(tc_prepare_rows(ctx, d_q, nq, N, s, D, fs->mu.p, &sl->rows));
+    sl->rows_ready = true;
     const size_t ldS = fs->coarse_tc.nb * fs->coarse_tc.np;
-    FDB_TRY(fs->S.ensure(nq * ldS));
-    FDB_TRY(tc_gemm_raw(ctx, fs->rows, fs->coarse_tc, 0, 1.0f, 1, fs->S.p, ldS, fs->coarse_tc.np));
+    FDB_TRY(sl->S.ensure(nq * ldS));
+    FDB_TRY(tc_gemm_raw(ctx, sl->rows, fs->coarse_tc, 0, 1.0f, 1, sl->S.p, ldS, fs->coarse_tc.np));
     FDB_TRY(log->mark(1));
-    FDB_TRY(ix->probes.ensure(nq * nprobe));
-    FDB_TRY(ix->probe_d.ensure(nq * nprobe));
+    FDB_TRY(sl->probes.ensure(nq * nprobe));
     ProbeParams pp;
-    pp.S = fs->S.p;
+    pp.S = sl->S.p;
     pp.ldS = ldS;
-    pp.xn2 = fs->rows.xn2.p;
+    pp.xn2 = sl->rows.xn2.p;
     pp.D = D;
     pp.cmax2 = fs->coarse_tc.cmax2.p;
     pp.ntiles = fs->coarse_tc.nb;
@@ -1443,31 +1455,31 @@ int filter_probe(fdb_index *ix, const float *d_q, size_t nq, size_t nprobe, Even
     pp.ncap = RCAP;   // the band may hold many partitions when the centroids are about equally far
     pp.gamma1 = tc_gamma(N);
     pp.eta = ((float)N / 16.0f + 20.0f) * U24;   // the reference's own f32 evaluation of one distance
-    pp.probes = ix->probes.p;
-    pp.hard = fs->hard.p;
+    pp.probes = sl->probes.p;
+    pp.hard = sl->hard.p;
     pp.nexact = fs->bcounters.p + 3;
     pp.cbmax = fs->cbmax.p;
     pp.bounds = fs->bounds.p;
-    FDB_TRY(fs->Kq.ensure(nq * nprobe));
-    FDB_TRY(fs->Wq.ensure(nq));
-    pp.Kq = fs->Kq.p;
-    pp.Wq = fs->Wq.p;
+    FDB_TRY(sl->Kq.ensure(nq * nprobe));
+    FDB_TRY(sl->Wq.ensure(nq));
+    pp.Kq = sl->Kq.p;
+    pp.Wq = sl->Wq.p;
     pp.inv_coef = 1.0f / adc_coef(s, D, fs->tc_g);
     pp.quad = (N % 16 == 0) ? 1 : 0;   // d_q is 16-byte aligned here, the centroid rows always are
     pp.use_smem = P <= 4096 ? 1 : 0;
-    FDB_TRY(fs->ps_part.ensure(nq * 32));
-    FDB_TRY(fs->ps_ss.ensure(nq * 32));
-    FDB_TRY(fs->ps_meta.ensure(nq * 8));
-    FDB_TRY(fs->ps_items.ensure(nq * 64));
-    FDB_TRY(fs->ps_dist.ensure(nq * 32));
-    FDB_TRY(fs->ps_count.ensure(1));
-    FDB_CUDA(cudaMemsetAsync(fs->ps_count.p, 0, sizeof(unsigned), st));
-    pp.st_part = fs->ps_part.p;
-    pp.st_ss = fs->ps_ss.p;
-    pp.st_meta = fs->ps_meta.p;
-    pp.items = fs->ps_items.p;
-    pp.item_d = fs->ps_dist.p;
-    pp.item_count = fs->ps_count.p;
+    FDB_TRY(sl->ps_part.ensure(nq * 32));
+    FDB_TRY(sl->ps_ss.ensure(nq * 32));
+    FDB_TRY(sl->ps_meta.ensure(nq * 8));
+    FDB_TRY(sl->ps_items.ensure(nq * 64));
+    FDB_TRY(sl->ps_dist.ensure(nq * 32));
+    FDB_TRY(sl->ps_count.ensure(1));
+    FDB_CUDA(cudaMemsetAsync(sl->ps_count.p, 0, sizeof(unsigned), st));
+    pp.st_part = sl->ps_part.p;
+    pp.st_ss = sl->ps_ss.p;
+    pp.st_meta = sl->ps_meta.p;
+    pp.items = sl->ps_items.p;
+    pp.item_d = sl->ps_dist.p;
+    pp.item_count = sl->ps_count.p;
     const size_t psmem = pp.use_smem ? 4 * (P + 32) * sizeof(float) : 0;
     FDB_CUDA(cudaFuncSetAttribute(probe_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(psmem, 1024)));
     // select (scores -> candidates, band) -> exact distances of the ambiguous pairs, spread over the
@@ -1477,8 +1489,58 @@ int filter_probe(fdb_index *ix, const float *d_q, size_t nq, size_t nprobe, Even
     probe_finalize_kernel<<<(unsigned)((nq + 3) / 4), 128, 0, st>>>(pp);
     ctx->launches += 3;
     FDB_CHECK_LAUNCH();
-    fs->probes_from_filter = true;
+    sl->probes_from_filter = true;
+    fs->batch_reprobe = true;
     *done = true;
+    return FDB_OK;
+}
+
+// slices are independent of each other (and may run on two streams) when the probe filter makes
+// their probe lists: everything a slice touches then lives in its slot
+bool filter_can_overlap(const fdb_index *ix, size_t nprobe) {
+    return ix->filter && ix->filter->tc_coarse && nprobe <= 24 && !getenv("FDB_QUERY_NO_OVERLAP");
+}
+
+// makes `slot` the current one; *stream = its stream (created on first use), which waits for the
+// batch's resets
+int filter_use_slot(fdb_index *ix, int slot, bool own_stream, cudaStream_t *stream) {
+    FilterState *fs = ix->filter;
+    FilterState::Slot *sl = &fs->slot[slot];
+    fs->cur = sl;
+    if (!own_stream) {
+        *stream = ix->ctx->stream;
+        return FDB_OK;
+    }
+    if (!sl->stream) {
+        FDB_CUDA(cudaStreamCreateWithFlags(&sl->stream, cudaStreamNonBlocking));
+        FDB_CUDA(cudaEventCreateWithFlags(&sl->done, cudaEventDisableTiming));
+    }
+    if (!fs->begun) FDB_CUDA(cudaEventCreateWithFlags(&fs->begun, cudaEventDisableTiming));
+    *stream = sl->stream;
+    return FDB_OK;
+}
+
+// batch_begin's resets are visible to the slot streams / the slots' work is visible to the main stream
+int filter_fork(fdb_index *ix) {
+    FilterState *fs = ix->filter;
+    if (!fs->begun) FDB_CUDA(cudaEventCreateWithFlags(&fs->begun, cudaEventDisableTiming));
+    FDB_CUDA(cudaEventRecord(fs->begun, ix->ctx->stream));
+    return FDB_OK;
+}
+int filter_slot_wait_fork(fdb_index *ix, int slot) {
+    FilterState *fs = ix->filter;
+    FDB_CUDA(cudaStreamWaitEvent(fs->slot[slot].stream, fs->begun, 0));
+    return FDB_OK;
+}
+int filter_slot_done(fdb_index *ix, int slot) {
+    FilterState::Slot *sl = &ix->filter->slot[slot];
+    FDB_CUDA(cudaEventRecord(sl->done, sl->stream));
+    return FDB_OK;
+}
+int filter_join(fdb_index *ix) {
+    FilterState *fs = ix->filter;
+    for (FilterState::Slot &sl : fs->slot)
+        if (sl.stream && sl.done) FDB_CUDA(cudaStreamWaitEvent(ix->ctx->stream, sl.done, 0));
     return FDB_OK;
 }
 
@@ -1487,6 +1549,8 @@ int filter_batch_begin(fdb_index *ix, size_t nq_total, size_t nprobe) {
     FDB_TRY(fs->bfb_q.ensure(nq_total));
     FDB_TRY(fs->bfb_probes.ensure(nq_total * nprobe));
     fs->bfb_cap = nq_total;
+    fs->batch_reprobe = false;
+    fs->cur = &fs->slot[0];
     FDB_CUDA(cudaMemsetAsync(fs->bcounters.p, 0, 12 * sizeof(unsigned long long), ix->ctx->stream));
     return FDB_OK;
 }
@@ -1501,7 +1565,7 @@ int filter_batch_end(fdb_index *ix, size_t nq_total, const uint32_t **d_fb_q, co
     *h_nfb = (unsigned)fs->h_counters[0];
     // lists made by the probe filter are the reference's probe set in no particular order: the
     // exact pipeline selects its own (the order matters for the ties it is there to resolve)
-    *h_nhard = fs->probes_from_filter ? *h_nfb : 0;
+    *h_nhard = fs->batch_reprobe ? *h_nfb : 0;
     *d_fb_q = fs->bfb_q.p;
     *d_fb_probes = fs->bfb_probes.p;
     ix->last_stats[0] = nq_total - fs->h_counters[0];
@@ -1520,28 +1584,30 @@ int filter_query(fdb_index *ix, const float *d_q, size_t q_base, size_t nq, size
                  uint32_t *d_v, float *d_d, uint32_t *d_c, EventLog *log) {
     fdb_ctx *ctx = ix->ctx;
     FilterState *fs = ix->filter;
+    FilterState::Slot *sl = fs->cur;
     cudaStream_t st = ctx->stream;
     const size_t N = ix->N, D = ix->D, C = ix->C, s = ix->s, DC = D * C;
+    const uint32_t *d_probes = sl->probes_from_filter ? sl->probes.p : ix->probes.p;
     const bool tc_g = fs->tc_g && (uintptr_t)d_q % 16 == 0;
     // the tensor-pipe GEMM writes whole 128-row tiles of the batch: no chunking of G then
     const size_t chunk = tc_g ? nq : std::min(nq, fs->chunk_q);
-    FDB_TRY(fs->G.ensure(chunk * DC));
-    FDB_TRY(fs->Kq.ensure(nq * nprobe));
-    FDB_TRY(fs->Wq.ensure(nq));
-    FDB_TRY(fs->cand_d.ensure(nq * RCAP));
-    FDB_TRY(fs->cand_a.ensure(nq * RCAP));
-    FDB_TRY(fs->cand_cnt.ensure(nq));
-    FDB_TRY(fs->cand_total.ensure(nq));
-    FDB_TRY(fs->qbad.ensure(nq));
-    FDB_TRY(fs->fb_list.ensure(nq));
-    FDB_TRY(fs->hard.ensure(nq));
-    FDB_CUDA(cudaMemsetAsync(fs->counters.p, 0, 12 * sizeof(unsigned long long), st));
+    FDB_TRY(sl->G.ensure(chunk * DC));
+    FDB_TRY(sl->Kq.ensure(nq * nprobe));
+    FDB_TRY(sl->Wq.ensure(nq));
+    FDB_TRY(sl->cand_d.ensure(nq * RCAP));
+    FDB_TRY(sl->cand_a.ensure(nq * RCAP));
+    FDB_TRY(sl->cand_cnt.ensure(nq));
+    FDB_TRY(sl->cand_total.ensure(nq));
+    FDB_TRY(sl->qbad.ensure(nq));
+    FDB_TRY(sl->fb_list.ensure(nq));
+    FDB_TRY(sl->hard.ensure(nq));
+    FDB_CUDA(cudaMemsetAsync(sl->counters.p, 0, 12 * sizeof(unsigned long long), st));
 
     FDB_TRY(log->mark(2));
-    if (!fs->probes_from_filter) {  // the probe filter already left K and W behind
+    if (!sl->probes_from_filter) {  // the probe filter already left K and W behind
         pair_const_kernel<<<(unsigned)((nq * 32 + 127) / 128), 128, 0, st>>>(
-            d_q, ix->coarse.p, fs->mu.p, ix->probes.p, fs->cbmax.p, fs->bounds.p, nq, N, D, s, (int)nprobe, fs->Kq.p,
-            fs->Wq.p);
+            d_q, ix->coarse.p, fs->mu.p, d_probes, fs->cbmax.p, fs->bounds.p, nq, N, D, s, (int)nprobe, sl->Kq.p,
+            sl->Wq.p);
         ctx->launches++;
         FDB_CHECK_LAUNCH();
     }
@@ -1563,27 +1629,27 @@ int filter_query(fdb_index *ix, const float *d_q, size_t q_base, size_t nq, size
         FDB_TRY(log->mark(3));
         if (tc_g) {
             // G[q][d][c] = -2 x'_d . cb_dc on the tensor pipe (problem d = division d)
-            if (!fs->rows_ready) {
-                FDB_TRY(tc_prepare_rows(ctx, d_q, nq, N, s, D, fs->mu.p, &fs->rows));
-                fs->rows_ready = true;
+            if (!sl->rows_ready) {
+                FDB_TRY(tc_prepare_rows(ctx, d_q, nq, N, s, D, fs->mu.p, &sl->rows));
+                sl->rows_ready = true;
             }
-            FDB_TRY(tc_gemm_raw(ctx, fs->rows, fs->cb_tc, s, -2.0f, 0, fs->G.p, DC, C));
+            FDB_TRY(tc_gemm_raw(ctx, sl->rows, fs->cb_tc, s, -2.0f, 0, sl->G.p, DC, C));
         } else {
             dim3 grid((unsigned)((nc + GM - 1) / GM), (unsigned)((C + GN - 1) / GN), (unsigned)D);
-            if (vec) adc_gemm_kernel<true><<<grid, G_THREADS, 0, st>>>(d_q + q0 * N, nc, N, fs->mu.p, ix->codebooks.p, C, s, D, fs->G.p);
-            else adc_gemm_kernel<false><<<grid, G_THREADS, 0, st>>>(d_q + q0 * N, nc, N, fs->mu.p, ix->codebooks.p, C, s, D, fs->G.p);
+            if (vec) adc_gemm_kernel<true><<<grid, G_THREADS, 0, st>>>(d_q + q0 * N, nc, N, fs->mu.p, ix->codebooks.p, C, s, D, sl->G.p);
+            else adc_gemm_kernel<false><<<grid, G_THREADS, 0, st>>>(d_q + q0 * N, nc, N, fs->mu.p, ix->codebooks.p, C, s, D, sl->G.p);
             ctx->launches++;
             FDB_CHECK_LAUNCH();
         }
         FDB_TRY(log->mark(4));
         FScanParams sp;
-        sp.G = fs->G.p;
+        sp.G = sl->G.p;
         sp.pc = fs->pc.p;
-        sp.Kq = fs->Kq.p;
+        sp.Kq = sl->Kq.p;
         sp.codes = records ? fs->rec.p : ix->codes.p;
         sp.part_off = ix->part_off.p;
         sp.part_start = records ? fs->rec_start.p : ix->part_cstart.p;
-        sp.probes = ix->probes.p;
+        sp.probes = d_probes;
         sp.rb = (int)rb;
         sp.q0 = q0;
         sp.nprobe = (int)nprobe;
@@ -1591,13 +1657,13 @@ int filter_query(fdb_index *ix, const float *d_q, size_t q_base, size_t nq, size
         sp.C = (int)C;
         sp.chunk_vecs = chunk_vecs;
         sp.ncap = ncap;
-        sp.cand_d = fs->cand_d.p;
-        sp.cand_a = fs->cand_a.p;
-        sp.cand_cnt = fs->cand_cnt.p;
-        sp.cand_total = fs->cand_total.p;
-        sp.qbad = fs->qbad.p;
-        sp.hard = fs->hard.p;
-        sp.counters = fs->counters.p;
+        sp.cand_d = sl->cand_d.p;
+        sp.cand_a = sl->cand_a.p;
+        sp.cand_cnt = sl->cand_cnt.p;
+        sp.cand_total = sl->cand_total.p;
+        sp.qbad = sl->qbad.p;
+        sp.hard = sl->hard.p;
+        sp.counters = sl->counters.p;
         scan<<<(unsigned)nc, FS_WARPS * 32, smem, st>>>(sp);
         ctx->launches++;
         FDB_CHECK_LAUNCH();
@@ -1610,13 +1676,13 @@ int filter_query(fdb_index *ix, const float *d_q, size_t q_base, size_t nq, size
     fp.codes = ix->codes.p;
     fp.part_off = ix->part_off.p;
     fp.part_cstart = ix->part_cstart.p;
-    fp.probes = ix->probes.p;
-    fp.Wq = fs->Wq.p;
-    fp.cand_d = fs->cand_d.p;
-    fp.cand_a = fs->cand_a.p;
-    fp.cand_cnt = fs->cand_cnt.p;
-    fp.cand_total = fs->cand_total.p;
-    fp.qbad = fs->qbad.p;
+    fp.probes = d_probes;
+    fp.Wq = sl->Wq.p;
+    fp.cand_d = sl->cand_d.p;
+    fp.cand_a = sl->cand_a.p;
+    fp.cand_cnt = sl->cand_cnt.p;
+    fp.cand_total = sl->cand_total.p;
+    fp.qbad = sl->qbad.p;
     fp.q0 = 0;
     fp.q1 = nq;
     fp.N = N;
@@ -1633,12 +1699,12 @@ int filter_query(fdb_index *ix, const float *d_q, size_t q_base, size_t nq, size
     fp.out_v = d_v;
     fp.out_c = d_c;
     fp.out_d = d_d;
-    fp.fb_list = fs->fb_list.p;
-    fp.counters = fs->counters.p;
+    fp.fb_list = sl->fb_list.p;
+    fp.counters = sl->counters.p;
     fselect_kernel<<<(unsigned)((nq + 3) / 4), 128, fp.quad ? 4 * RCAP * D * sizeof(float) : 0, st>>>(fp);
     ctx->launches++;
     FDB_CHECK_LAUNCH();
-    stash_undecided_kernel<<<1, 256, 0, st>>>(fs->counters.p, fs->fb_list.p, ix->probes.p, q_base, (int)nprobe,
+    stash_undecided_kernel<<<1, 256, 0, st>>>(sl->counters.p, sl->fb_list.p, d_probes, q_base, (int)nprobe,
                                               fs->bcounters.p, fs->bfb_q.p, fs->bfb_probes.p);
     ctx->launches++;
     FDB_CHECK_LAUNCH();

@@ -85,6 +85,14 @@ int filter_probe(fdb_index *ix, const float *d_q, size_t nq, size_t nprobe, Even
 // list that filter_batch_end hands to the exact pipeline.  *h_nhard = those among the *h_nfb
 // whose probe list is not the reference's.
 int filter_batch_begin(fdb_index *ix, size_t nq_total, size_t nprobe);
+// two scratch slots: consecutive slices of a host batch run on two streams when
+// filter_can_overlap (fork after batch_begin, join before batch_end)
+bool filter_can_overlap(const fdb_index *ix, size_t nprobe);
+int filter_use_slot(fdb_index *ix, int slot, bool own_stream, cudaStream_t *stream);
+int filter_fork(fdb_index *ix);
+int filter_slot_wait_fork(fdb_index *ix, int slot);
+int filter_slot_done(fdb_index *ix, int slot);
+int filter_join(fdb_index *ix);
 int filter_query(fdb_index *ix, const float *d_q, size_t q_base, size_t nq, size_t k, size_t nprobe, uint32_t *d_p,
                  uint32_t *d_v, float *d_d, uint32_t *d_c, EventLog *log);
 int filter_batch_end(fdb_index *ix, size_t nq_total, const uint32_t **d_fb_q, const uint32_t **d_fb_probes,
