@@ -73,10 +73,6 @@ struct FilterState {
         DevBuf<unsigned> qbad;       // [nq]
         DevBuf<uint32_t> fb_list;    // [nq]
         DevBuf<unsigned long long> counters;  // [0] fallbacks, [1] exact candidates, [2] scanned vectors, [4..] reasons
-        // partition-major scan: pairs grouped by partition, work items, per-pair candidate lists
-        DevBuf<unsigned> pcount, pfill, poff, nitems, pbad;
-        DevBuf<uint32_t> sorted_pairs, item_part, item_first, item_cnt, pl_a, pl_cnt;
-        DevBuf<float> pl_d;
         cudaStream_t stream = nullptr;
         cudaEvent_t done = nullptr;
     } slot[2];
@@ -576,307 +572,6 @@ __global__ void __launch_bounds__(FS_WARPS * 32) fscan_kernel(FScanParams p) {
         p.cand_total[q] = flat0;
         p.qbad[q] = (unsigned)anybad | (p.hard[q] ? 2u : 0u);
         atomicAdd(&p.counters[2], (unsigned long long)flat0);
-    }
-}
-
-// ---- partition-major scan: one CTA per (partition, group of GQ queries probing it) ----------------
-// The tables of the GQ queries are interleaved, T[d][c][g] = G[q_g][d][c] + PC[p][d][c], so one
-// 128-bit shared-memory load answers a look-up for all GQ queries at once: the code bytes are
-// unpacked once per vector instead of once per (query, vector), a warp-wide look-up costs ~9
-// wavefronts for 128 results instead of ~3.1 for 32, and the code list is read once per group.
-// Approximate distances of a chunk go through shared memory to the warp that owns the query
-// (warp g <-> query g), which keeps its ncap smallest in registers.
-constexpr int GQ = 4;
-
-// pairs (query, probe) grouped by partition: histogram -> offsets + work items -> scatter
-__global__ void pair_hist_kernel(const uint32_t *probes, size_t npairs, unsigned *pcount) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < npairs) atomicAdd(&pcount[probes[i]], 1u);
-}
-__global__ void __launch_bounds__(1024) pair_layout_kernel(const unsigned *pcount, size_t P, unsigned *poff,
-                                                           unsigned *pfill, uint32_t *item_part, uint32_t *item_first,
-                                                           uint32_t *item_cnt, unsigned *nitems) {
-    __shared__ unsigned spairs[1024], sitems[1024];
-    const int t = threadIdx.x;
-    const size_t per = (P + 1023) / 1024, lo = min(P, t * per), hi = min(P, lo + per);
-    unsigned np = 0, ni = 0;
-    for (size_t p = lo; p < hi; ++p) {
-        np += pcount[p];
-        ni += (pcount[p] + GQ - 1) / GQ;
-    }
-    spairs[t] = np;
-    sitems[t] = ni;
-    __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) {   // inclusive scans
-        const unsigned a = t >= off ? spairs[t - off] : 0u, b = t >= off ? sitems[t - off] : 0u;
-        __syncthreads();
-        spairs[t] += a;
-        sitems[t] += b;
-        __syncthreads();
-    }
-    unsigned pb = spairs[t] - np, ib = sitems[t] - ni;
-    for (size_t p = lo; p < hi; ++p) {
-        const unsigned c = pcount[p];
-        poff[p] = pb;
-        pfill[p] = 0;
-        for (unsigned j = 0; j * GQ < c; ++j) {
-            item_part[ib] = (uint32_t)p;
-            item_first[ib] = pb + j * GQ;
-            item_cnt[ib] = min((unsigned)GQ, c - j * GQ);
-            ++ib;
-        }
-        pb += c;
-    }
-    if (t == 1023) *nitems = sitems[1023];
-}
-__global__ void pair_scatter_kernel(const uint32_t *probes, size_t npairs, const unsigned *poff, unsigned *pfill,
-                                    uint32_t *sorted_pairs) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= npairs) return;
-    const uint32_t p = probes[i];
-    sorted_pairs[poff[p] + atomicAdd(&pfill[p], 1u)] = (uint32_t)i;
-}
-
-struct GScanParams {
-    const float *G;              // [queries of the slice][D*C]
-    const float *pc;             // [P][D*C]
-    const float *Kq;             // [nq][nprobe] pair constants
-    const uint8_t *codes;
-    const uint32_t *part_off;
-    const uint64_t *part_cstart;
-    const uint32_t *sorted_pairs, *item_part, *item_first, *item_cnt;
-    const unsigned *nitems;
-    int nprobe, D, C, chunk_vecs, ncap;
-    float *pl_d;                 // [npairs][RCAP] the ncap smallest approximate distances of the pair, unsorted
-    uint32_t *pl_a;              //                their vector indices
-    uint32_t *pl_cnt;            // [npairs]
-    unsigned *pbad;              // [npairs] non-finite table entry or pair constant
-    unsigned long long *counters;
-};
-
-constexpr int GS_WARPS = 8;
-
-template <int W>
-__global__ void __launch_bounds__(GS_WARPS * 32) gscan_kernel(GScanParams p) {
-    extern __shared__ __align__(16) unsigned char sm[];
-    const unsigned item = blockIdx.x;
-    if (item >= *p.nitems) return;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int D = p.D, C = p.C, DC = D * C;
-    const int CV = p.chunk_vecs, CH = GS_WARPS * CV;     // vectors per warp / per CTA and round
-    float4 *T = reinterpret_cast<float4 *>(sm);          // [D][TSTRIDE] x GQ queries
-    uint32_t *ckey = reinterpret_cast<uint32_t *>(T + (size_t)D * TSTRIDE);   // [GQ][CH] candidates of the round
-    uint32_t *cidx = ckey + GQ * CH;                                          // [GQ][CH]
-    const size_t chunk_bytes = (size_t)CV * D;           // multiple of 16 (CV % 32 == 0)
-    unsigned char *cbuf = reinterpret_cast<unsigned char *>(cidx + GQ * CH) + (size_t)warp * 2 * chunk_bytes;
-    __shared__ uint32_t pid_s[GQ];
-    __shared__ float K_s[GQ];
-    __shared__ __align__(16) unsigned thr_s[GQ];   // key of the largest distance query g still keeps
-    __shared__ unsigned cn_s[GQ];                  // candidates of the round
-
-    const uint32_t part = p.item_part[item];
-    const int gq = (int)p.item_cnt[item];
-    if (tid < GQ) {
-        const uint32_t pid = p.sorted_pairs[p.item_first[item] + (tid < gq ? tid : 0)];
-        pid_s[tid] = pid;
-        K_s[tid] = p.Kq[pid];
-        thr_s[tid] = tid < gq ? 0xffffffffu : 0u;   // unused slots of the group take nothing
-        cn_s[tid] = 0;
-    }
-    __syncthreads();
-    const int np = (int)(p.part_off[part + 1] - p.part_off[part]);
-    const uint8_t *cg = p.codes + p.part_cstart[part];
-    const int nrounds = (np + CH - 1) / CH;
-    auto issue = [&](int r, int slot) {   // this warp's CV vectors of round r
-        const int c0 = r * CH + warp * CV;
-        if (r < nrounds && c0 < np) {
-            const int cnt = min(CV, np - c0);
-            const size_t n16 = ((size_t)cnt * D + 15) >> 4;
-            const uint8_t *src = cg + (size_t)c0 * D;
-            unsigned char *dst = cbuf + (size_t)slot * chunk_bytes;
-            for (size_t i = lane; i < n16; i += 32) cp_async16(dst + 16 * i, src + 16 * i);
-        }
-        cp_async_commit();
-    };
-    issue(0, 0);
-    // the interleaved table, four entries (one float4 per query and for PC) at a time
-    bool bad = false;
-    {
-        const float *g0 = p.G + (size_t)(pid_s[0] / p.nprobe) * DC, *g1 = p.G + (size_t)(pid_s[1] / p.nprobe) * DC;
-        const float *g2 = p.G + (size_t)(pid_s[2] / p.nprobe) * DC, *g3 = p.G + (size_t)(pid_s[3] / p.nprobe) * DC;
-        const float *pcp = p.pc + (size_t)part * DC;
-        if (C == TSTRIDE) {
-            for (int i = tid; i < DC / 4; i += GS_WARPS * 32) {
-                const float4 c = __ldg(reinterpret_cast<const float4 *>(pcp) + i);
-                const float4 x0 = __ldg(reinterpret_cast<const float4 *>(g0) + i);
-                const float4 x1 = __ldg(reinterpret_cast<const float4 *>(g1) + i);
-                const float4 x2 = __ldg(reinterpret_cast<const float4 *>(g2) + i);
-                const float4 x3 = __ldg(reinterpret_cast<const float4 *>(g3) + i);
-                const float4 t0 = make_float4(x0.x + c.x, x1.x + c.x, x2.x + c.x, x3.x + c.x);
-                const float4 t1 = make_float4(x0.y + c.y, x1.y + c.y, x2.y + c.y, x3.y + c.y);
-                const float4 t2 = make_float4(x0.z + c.z, x1.z + c.z, x2.z + c.z, x3.z + c.z);
-                const float4 t3 = make_float4(x0.w + c.w, x1.w + c.w, x2.w + c.w, x3.w + c.w);
-                bad |= !(fabsf(t0.x) + fabsf(t0.y) + fabsf(t0.z) + fabsf(t0.w) + fabsf(t1.x) + fabsf(t1.y) +
-                         fabsf(t1.z) + fabsf(t1.w) + fabsf(t2.x) + fabsf(t2.y) + fabsf(t2.z) + fabsf(t2.w) +
-                         fabsf(t3.x) + fabsf(t3.y) + fabsf(t3.z) + fabsf(t3.w) < 1e30f);
-                T[4 * i] = t0;
-                T[4 * i + 1] = t1;
-                T[4 * i + 2] = t2;
-                T[4 * i + 3] = t3;
-            }
-        } else {
-            for (int i = tid; i < DC; i += GS_WARPS * 32) {
-                const float c = __ldg(pcp + i);
-                const float4 t = make_float4(__ldg(g0 + i) + c, __ldg(g1 + i) + c, __ldg(g2 + i) + c, __ldg(g3 + i) + c);
-                bad |= !(fabsf(t.x) + fabsf(t.y) + fabsf(t.z) + fabsf(t.w) < 1e30f);
-                const int d = i / C;
-                T[d * TSTRIDE + (i - d * C)] = t;
-            }
-        }
-    }
-    const float K0 = K_s[0], K1 = K_s[1], K2 = K_s[2], K3 = K_s[3];
-    bad |= !(fabsf(K0) + fabsf(K1) + fabsf(K2) + fabsf(K3) < 1e30f);
-    RegTopK sel;   // warp g < GQ keeps the list of query g
-    sel.init(p.ncap);
-    __syncthreads();   // the table is complete
-    const unsigned char *Tb = reinterpret_cast<const unsigned char *>(T);
-    int slot = 0;
-    for (int r = 0; r < nrounds; ++r) {
-        issue(r + 1, slot ^ 1);
-        cp_async_wait<1>();
-        __syncwarp();
-        const int c0 = r * CH + warp * CV;
-        const int cnt = max(0, min(CV, np - c0));
-        const unsigned char *cs = cbuf + (size_t)slot * chunk_bytes;
-        for (int base = 0; base < cnt; base += 32) {
-            const int v = base + lane;
-            const bool valid = v < cnt;
-            float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
-            if (valid) {
-                if constexpr (W > 0) {
-                    uint32_t cw[W];
-                    load_words<W>(cs + (size_t)v * D, cw);
-#pragma unroll
-                    for (int w = 0; w < W; ++w) {
-#pragma unroll
-                        for (int b = 0; b < 4; ++b) {
-                            const uint32_t off = ((cw[w] >> (8 * b)) & 255u) * 16u + (uint32_t)(4 * w + b) * (TSTRIDE * 16u);
-                            const float4 t = *reinterpret_cast<const float4 *>(Tb + off);
-                            a0 += t.x, a1 += t.y, a2 += t.z, a3 += t.w;
-                        }
-                    }
-                } else {
-                    for (int di = 0; di < D; ++di) {
-                        const float4 t = T[di * TSTRIDE + cs[(size_t)v * D + di]];
-                        a0 += t.x, a1 += t.y, a2 += t.z, a3 += t.w;
-                    }
-                }
-            }
-            // candidates: below the largest distance the query's list still keeps
-            const volatile unsigned *tv = thr_s;
-            const unsigned l0 = tv[0], l1 = tv[1], l2 = tv[2], l3 = tv[3];
-            const uint32_t k0 = fkey(a0 + K0), k1 = fkey(a1 + K1), k2 = fkey(a2 + K2), k3 = fkey(a3 + K3);
-            const bool w0 = valid && k0 < l0, w1 = valid && k1 < l1, w2 = valid && k2 < l2, w3 = valid && k3 < l3;
-            if (__any_sync(0xffffffffu, w0 | w1 | w2 | w3)) {
-                const uint32_t vi = (uint32_t)(c0 + v);
-                auto emit = [&](bool want, uint32_t key, int g) {
-                    const unsigned bal = __ballot_sync(0xffffffffu, want);
-                    if (bal) {
-                        unsigned pos = 0;
-                        if (lane == 0) pos = atomicAdd(&cn_s[g], (unsigned)__popc(bal));
-                        pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(bal & ((1u << lane) - 1u));
-                        if (want) {
-                            ckey[g * CH + pos] = key;
-                            cidx[g * CH + pos] = vi;
-                        }
-                    }
-                };
-                emit(w0, k0, 0);
-                emit(w1, k1, 1);
-                emit(w2, k2, 2);
-                emit(w3, k3, 3);
-            }
-        }
-        __syncthreads();
-        // warp g drains the round's candidates of query g into its list and tightens the threshold
-        if (warp < gq) {
-            const int n = (int)cn_s[warp];
-            for (int base = 0; base < n; base += 32) {
-                const bool valid = base + lane < n;
-                const uint32_t ka = valid ? ckey[warp * CH + base + lane] : 0u;
-                const uint32_t vi = valid ? cidx[warp * CH + base + lane] : 0u;
-                const bool want = valid && ka < sel.maxkey;
-                if (__any_sync(0xffffffffu, want)) push_lanes(sel, ka, vi, want, lane);
-            }
-            if (lane == 0) {
-                cn_s[warp] = 0;
-                thr_s[warp] = sel.maxkey;
-            }
-        }
-        __syncthreads();
-        slot ^= 1;
-    }
-    cp_async_wait<0>();
-    const int anybad = __syncthreads_or(bad ? 1 : 0);
-    if (warp < gq) {
-        const uint32_t pid = pid_s[warp];
-        if (lane < sel.len) {
-            p.pl_d[(size_t)pid * RCAP + lane] = fkey_inv(sel.key);
-            p.pl_a[(size_t)pid * RCAP + lane] = sel.a;
-        }
-        if (lane == 0) {
-            p.pl_cnt[pid] = (uint32_t)sel.len;
-            p.pbad[pid] = (unsigned)anybad;
-            atomicAdd(&p.counters[2], (unsigned long long)np);
-        }
-    }
-}
-
-// per-pair lists -> the per-query candidate list fselect reads (ascending, flat positions)
-struct GMergeParams {
-    const float *pl_d;
-    const uint32_t *pl_a, *pl_cnt;
-    const unsigned *pbad, *hard;
-    const uint32_t *probes, *part_off;
-    size_t nq;
-    int nprobe, ncap;
-    float *cand_d;
-    uint32_t *cand_a, *cand_cnt, *cand_total;
-    unsigned *qbad;
-};
-__global__ void __launch_bounds__(128) gmerge_kernel(GMergeParams p) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const size_t q = (size_t)blockIdx.x * 4 + warp;
-    if (q >= p.nq) return;
-    RegTopK sel;
-    sel.init(p.ncap);
-    uint32_t start = 0;
-    unsigned bad = 0;
-    for (int pr = 0; pr < p.nprobe; ++pr) {
-        const size_t pid = q * p.nprobe + pr;
-        const uint32_t part = p.probes[pid];
-        const int cnt = (int)p.pl_cnt[pid];
-        bad |= p.pbad[pid];
-        const bool valid = lane < cnt;
-        const uint32_t ka = fkey(valid ? p.pl_d[pid * RCAP + lane] : 0.0f);
-        const uint32_t av = valid ? start + p.pl_a[pid * RCAP + lane] : 0u;
-        const bool want = valid && ka < sel.maxkey;
-        if (__any_sync(0xffffffffu, want)) push_lanes(sel, ka, av, want, lane);
-        start += p.part_off[part + 1] - p.part_off[part];
-    }
-    int rank = 0;
-    for (int j = 0; j < sel.len; ++j) {
-        const uint32_t kj = __shfl_sync(0xffffffffu, sel.key, j);
-        rank += (kj < sel.key) || (kj == sel.key && j < lane);
-    }
-    if (lane < sel.len) {
-        p.cand_d[q * RCAP + rank] = fkey_inv(sel.key);
-        p.cand_a[q * RCAP + rank] = sel.a;
-    }
-    if (lane == 0) {
-        p.cand_cnt[q] = (uint32_t)sel.len;
-        p.cand_total[q] = start;
-        p.qbad[q] = (bad ? 1u : 0u) | (p.hard[q] ? 2u : 0u);
     }
 }
 
@@ -1602,19 +1297,6 @@ size_t scan_smem_bytes(const fdb_index *ix, int chunk_vecs, size_t rb) {
 int scan_chunk_vecs(size_t rb) { return (int)std::max<size_t>(32, (2048 / rb) & ~(size_t)31); }
 size_t record_bytes(size_t D) { return ((D + 3) & ~(size_t)3) + 4; }
 
-typedef void (*GScanFn)(GScanParams);
-GScanFn gscan_fn(size_t D) {
-    switch (D) {
-        case 4: return gscan_kernel<1>;
-        case 8: return gscan_kernel<2>;
-        case 12: return gscan_kernel<3>;
-        case 16: return gscan_kernel<4>;
-        case 20: return gscan_kernel<5>;
-        default: return gscan_kernel<0>;
-    }
-}
-int scan_chunk_vecs(size_t rb);
-
 typedef void (*FScanFn)(FScanParams);
 template <bool R>
 FScanFn scan_fn_w(size_t D) {
@@ -1907,14 +1589,8 @@ int filter_query(fdb_index *ix, const float *d_q, size_t q_base, size_t nq, size
     const size_t N = ix->N, D = ix->D, C = ix->C, s = ix->s, DC = D * C;
     const uint32_t *d_probes = sl->probes_from_filter ? sl->probes.p : ix->probes.p;
     const bool tc_g = fs->tc_g && (uintptr_t)d_q % 16 == 0;
-    // partition-major scan (one CTA per partition and group of 4 queries) when the interleaved
-    // tables fit in shared memory; else query-major (one CTA per query)
-    const int gcv = 64;
-    const size_t gsmem = D * TSTRIDE * 16 + (size_t)GQ * GS_WARPS * gcv * 8 + (size_t)GS_WARPS * 2 * gcv * D + 16;
-    const bool gscan = gsmem <= 100 * 1024 && !getenv("FDB_FILTER_QUERY_MAJOR");
-    // the tensor-pipe GEMM writes whole 128-row tiles of the batch, the partition-major scan needs
-    // every query's table: no chunking of G then
-    const size_t chunk = (tc_g || gscan) ? nq : std::min(nq, fs->chunk_q);
+    // the tensor-pipe GEMM writes whole 128-row tiles of the batch: no chunking of G then
+    const size_t chunk = tc_g ? nq : std::min(nq, fs->chunk_q);
     FDB_TRY(sl->G.ensure(chunk * DC));
     FDB_TRY(sl->Kq.ensure(nq * nprobe));
     FDB_TRY(sl->Wq.ensure(nq));
@@ -1965,7 +1641,6 @@ int filter_query(fdb_index *ix, const float *d_q, size_t q_base, size_t nq, size
             ctx->launches++;
             FDB_CHECK_LAUNCH();
         }
-        if (gscan) break;   // one chunk: scanned below
         FDB_TRY(log->mark(4));
         FScanParams sp;
         sp.G = sl->G.p;
@@ -1991,73 +1666,6 @@ int filter_query(fdb_index *ix, const float *d_q, size_t q_base, size_t nq, size
         sp.counters = sl->counters.p;
         scan<<<(unsigned)nc, FS_WARPS * 32, smem, st>>>(sp);
         ctx->launches++;
-        FDB_CHECK_LAUNCH();
-    }
-    if (gscan) {
-        FDB_TRY(log->mark(4));
-        const size_t npairs = nq * nprobe, P = ix->P;
-        const size_t max_items = (npairs + GQ - 1) / GQ + P;
-        FDB_TRY(sl->pcount.ensure(P));
-        FDB_TRY(sl->pfill.ensure(P));
-        FDB_TRY(sl->poff.ensure(P + 1));
-        FDB_TRY(sl->nitems.ensure(1));
-        FDB_TRY(sl->pbad.ensure(npairs));
-        FDB_TRY(sl->sorted_pairs.ensure(npairs));
-        FDB_TRY(sl->item_part.ensure(max_items));
-        FDB_TRY(sl->item_first.ensure(max_items));
-        FDB_TRY(sl->item_cnt.ensure(max_items));
-        FDB_TRY(sl->pl_d.ensure(npairs * RCAP));
-        FDB_TRY(sl->pl_a.ensure(npairs * RCAP));
-        FDB_TRY(sl->pl_cnt.ensure(npairs));
-        FDB_CUDA(cudaMemsetAsync(sl->pcount.p, 0, P * sizeof(unsigned), st));
-        pair_hist_kernel<<<(unsigned)((npairs + 255) / 256), 256, 0, st>>>(d_probes, npairs, sl->pcount.p);
-        pair_layout_kernel<<<1, 1024, 0, st>>>(sl->pcount.p, P, sl->poff.p, sl->pfill.p, sl->item_part.p,
-                                               sl->item_first.p, sl->item_cnt.p, sl->nitems.p);
-        pair_scatter_kernel<<<(unsigned)((npairs + 255) / 256), 256, 0, st>>>(d_probes, npairs, sl->poff.p,
-                                                                             sl->pfill.p, sl->sorted_pairs.p);
-        GScanParams gp;
-        gp.G = sl->G.p;
-        gp.pc = fs->pc.p;
-        gp.Kq = sl->Kq.p;
-        gp.codes = ix->codes.p;
-        gp.part_off = ix->part_off.p;
-        gp.part_cstart = ix->part_cstart.p;
-        gp.sorted_pairs = sl->sorted_pairs.p;
-        gp.item_part = sl->item_part.p;
-        gp.item_first = sl->item_first.p;
-        gp.item_cnt = sl->item_cnt.p;
-        gp.nitems = sl->nitems.p;
-        gp.nprobe = (int)nprobe;
-        gp.D = (int)D;
-        gp.C = (int)C;
-        gp.chunk_vecs = gcv;
-        gp.ncap = ncap;
-        gp.pl_d = sl->pl_d.p;
-        gp.pl_a = sl->pl_a.p;
-        gp.pl_cnt = sl->pl_cnt.p;
-        gp.pbad = sl->pbad.p;
-        gp.counters = sl->counters.p;
-        const GScanFn gfn = gscan_fn(D);
-        FDB_CUDA(cudaFuncSetAttribute(gfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
-        gfn<<<(unsigned)max_items, GS_WARPS * 32, gsmem, st>>>(gp);
-        GMergeParams mp;
-        mp.pl_d = sl->pl_d.p;
-        mp.pl_a = sl->pl_a.p;
-        mp.pl_cnt = sl->pl_cnt.p;
-        mp.pbad = sl->pbad.p;
-        mp.hard = sl->hard.p;
-        mp.probes = d_probes;
-        mp.part_off = ix->part_off.p;
-        mp.nq = nq;
-        mp.nprobe = (int)nprobe;
-        mp.ncap = ncap;
-        mp.cand_d = sl->cand_d.p;
-        mp.cand_a = sl->cand_a.p;
-        mp.cand_cnt = sl->cand_cnt.p;
-        mp.cand_total = sl->cand_total.p;
-        mp.qbad = sl->qbad.p;
-        gmerge_kernel<<<(unsigned)((nq + 3) / 4), 128, 0, st>>>(mp);
-        ctx->launches += 5;
         FDB_CHECK_LAUNCH();
     }
     FDB_TRY(log->mark(5));

@@ -405,13 +405,9 @@ def _check_query(ix, oix, q, k, nprobe, mode):
     (64, 9, 4, 256, 60, 5, 9, 64),             # fewer vectors than the candidate list holds
     (36, 30, 3, 33, 5000, 1, 4, 128),          # k = 1, s = 12 < 16, unaligned C
 ])
-@pytest.mark.parametrize("layout", ["records", "tables", "partition-major"])
+@pytest.mark.parametrize("layout", ["records", "tables"])
 def test_filter_path_bit_exact(eng, ctx, oracle, monkeypatch, layout, N, P, D, Cn, M, k, nprobe, nq):
-    if layout == "partition-major":   # the default scan when D <= 20; the other two are query-major
-        monkeypatch.delenv("FDB_FILTER_QUERY_MAJOR", raising=False)
-    else:
-        monkeypatch.setenv("FDB_FILTER_QUERY_MAJOR", "1")
-        monkeypatch.setenv("FDB_FILTER_LAYOUT", layout)   # read when the index is created
+    monkeypatch.setenv("FDB_FILTER_LAYOUT", layout)   # read when the index is created
     coarse, cbs, off, codes = random_index(oracle, N, P, D, Cn, M, empty=(1,))
     ix = eng.Index.create(ctx, coarse, cbs, off, codes.astype(np.uint8))
     oix = oracle.QueryIndex(coarse, cbs, off, codes)
