@@ -467,6 +467,39 @@ def test_probe_filter_ties_and_far_offsets(eng, ctx, oracle):
     ix.close()
 
 
+def _clustered_index(oracle, N, P, D, Cn, M, seed):
+    """An index with real cluster structure (Gaussian blobs with very different scales, far from the
+    origin), built the cheap way: partition centres = blob centres, code vectors = a sample of the
+    residues.  Distances span orders of magnitude, unlike the uniform data of the other tests."""
+    rng = np.random.default_rng(seed)
+    s = N // D
+    centres = (rng.normal(0.0, 8.0, (P, N)) + 20.0).astype(np.float32)
+    scale = rng.uniform(0.05, 2.0, P).astype(np.float32)
+    sizes = rng.multinomial(M, np.ones(P) / P)
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+    cbs = (rng.normal(0.0, 1.0, (D, Cn, s)) * rng.uniform(0.05, 2.0, (D, Cn, 1))).astype(np.float32)
+    codes = rng.integers(0, Cn, (M, D)).astype(np.uint32)
+    part_of = np.repeat(np.arange(P), sizes)
+    q = (centres[rng.integers(0, P, 96)] + rng.normal(0.0, 1.0, (96, N)) * scale[rng.integers(0, P, 96), None])
+    return centres, cbs, off, codes, q.astype(np.float32)
+
+
+@pytest.mark.parametrize("N,P,D,Cn,M,k,nprobe", [
+    (128, 64, 16, 256, 20000, 10, 8),     # SIFT-like shape: s = 8, tables on the FMA pipe, coarse on tcgen05
+    (256, 300, 4, 256, 30000, 10, 16),    # s = 64: both GEMMs on tcgen05, two column tiles
+    (96, 50, 12, 64, 8000, 5, 5),         # no tensor-pipe GEMM at all
+])
+def test_filter_path_on_clustered_data(eng, ctx, oracle, N, P, D, Cn, M, k, nprobe):
+    coarse, cbs, off, codes, q = _clustered_index(oracle, N, P, D, Cn, M, 11)
+    ix = eng.Index.create(ctx, coarse, cbs, off, codes.astype(np.uint8))
+    oix = oracle.QueryIndex(coarse, cbs, off, codes)
+    for mode in (0, 1):
+        fast, exact, cand, scanned = _check_query(ix, oix, q, k, nprobe, mode)
+        assert fast + exact == len(q)
+        assert fast >= 0.5 * len(q), (fast, exact)   # wide bands are allowed to hand back more, not most
+    ix.close()
+
+
 def test_filter_path_equals_exact_pipeline_on_a_large_batch(eng, ctx, oracle, monkeypatch):
     """4096 queries against the README shape: ids, distances and counts of the filter path equal
     the exact pipeline's bit for bit (the oracle is too slow for this many; it checks a sample)."""
