@@ -75,7 +75,7 @@ struct FilterState {
         DevBuf<unsigned long long> counters;  // [0] fallbacks, [1] exact candidates, [2] scanned vectors, [4..] reasons
         cudaStream_t stream = nullptr;
         cudaEvent_t done = nullptr;
-    } slot[2];
+    } slot[FDB_FILTER_SLOTS];
     Slot *cur = &slot[0];
     bool batch_reprobe = false;      // some slice of the batch took its probe lists from the probe filter
     cudaEvent_t begun = nullptr;     // batch_begin's resets, the slot streams wait for it

@@ -5,6 +5,9 @@
 #include <vector>
 
 namespace fdb { struct FilterState; }
+#ifndef FDB_FILTER_SLOTS
+#define FDB_FILTER_SLOTS 2   // scratch slots = compute streams that slices of a host batch rotate through
+#endif
 
 struct fdb_index {
     fdb_ctx *ctx = nullptr;

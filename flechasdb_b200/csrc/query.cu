@@ -17,6 +17,7 @@
 #include "kmeans.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <memory>
 
@@ -696,7 +697,7 @@ int batch_slice(QueryBatch &b, const float *d_q, size_t q_base, size_t nq, uint3
                 float *d_d, uint32_t *d_c, cudaEvent_t ready) {
     fdb_index *ix = b.ix;
     fdb_ctx *ctx = ix->ctx;
-    const int slot = b.overlap ? (int)(b.islice & 1) : 0;
+    const int slot = b.overlap ? (int)(b.islice % FDB_FILTER_SLOTS) : 0;
     b.islice++;
     cudaStream_t main_stream = ctx->stream, st = ctx->stream;
     if (b.filter) FDB_TRY(filter_use_slot(ix, slot, b.overlap, &st));
@@ -816,10 +817,21 @@ int fdb_index_query(fdb_index *ix, const float *queries, size_t nq, size_t k, si
     // slices travel while the earlier ones are being answered.
     // (slices of ~2500 queries, alternating between two streams: measured best on the 10 000 x 1536
     // batch; smaller slices lose more to kernel tails than they gain in overlap)
-    size_t nslices = nq >= 4096 ? std::max<size_t>(2, (nq + 1250) / 2500) : 1;
-    size_t slice = (nq + nslices - 1) / nslices;
-    if (const char *e = getenv("FDB_QUERY_HOST_SLICE")) slice = (size_t)std::max(1L, atol(e));
-    nslices = (nq + slice - 1) / slice;
+    // (equal slices: a shorter last slice was measured slower, the compute of the sliced batch,
+    // not the tail after the last copy, is what limits the pipeline)
+    std::vector<size_t> bounds;   // slice i = [bounds[i], bounds[i + 1])
+    {
+        size_t nslices = nq >= 4096 ? std::max<size_t>(2, (nq + 1250) / 2500) : 1;
+        size_t slice = (nq + nslices - 1) / nslices;
+        if (const char *e = getenv("FDB_QUERY_HOST_SLICE")) {
+            slice = (size_t)std::max(1L, atol(e));
+            nslices = (nq + slice - 1) / slice;
+        }
+        bounds.push_back(0);
+        for (size_t i = 0; i + 1 < nslices && bounds.back() + slice < nq; ++i) bounds.push_back(bounds.back() + slice);
+        bounds.push_back(nq);
+    }
+    const size_t nslices = bounds.size() - 1;
     if (!ix->copy_stream) FDB_CUDA(cudaStreamCreateWithFlags(&ix->copy_stream, cudaStreamNonBlocking));
     while (ix->copy_events.size() < nslices + 1) {
         cudaEvent_t e;
@@ -830,25 +842,38 @@ int fdb_index_query(fdb_index *ix, const float *queries, size_t nq, size_t k, si
     FDB_CUDA(cudaEventRecord(ix->copy_events[nslices], st));
     FDB_CUDA(cudaStreamWaitEvent(ix->copy_stream, ix->copy_events[nslices], 0));
     for (size_t i = 0; i < nslices; ++i) {
-        const size_t q0 = i * slice, nc = std::min(slice, nq - q0);
+        const size_t q0 = bounds[i], nc = bounds[i + 1] - q0;
         FDB_CUDA(cudaMemcpyAsync(ix->q_dev.p + q0 * ix->N, queries + q0 * ix->N, nc * ix->N * sizeof(float),
                                  cudaMemcpyHostToDevice, ix->copy_stream));
         FDB_CUDA(cudaEventRecord(ix->copy_events[i], ix->copy_stream));
     }
+    const bool trace = getenv("FDB_QUERY_TRACE") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = trace ? now() : 0.0;
     QueryBatch b{ix, nq, k, nprobe, mode, false, EventLog{ix}};
     b.nslices = nslices;
     FDB_TRY(batch_begin(b));
     for (size_t i = 0; i < nslices; ++i) {
-        const size_t q0 = i * slice, nc = std::min(slice, nq - q0);
+        const size_t q0 = bounds[i], nc = bounds[i + 1] - q0;
         FDB_TRY(batch_slice(b, ix->q_dev.p + q0 * ix->N, q0, nc, ix->out_p.p + q0 * k, ix->out_v.p + q0 * k,
                             ix->out_d.p + q0 * k, ix->out_c.p + q0, ix->copy_events[i]));
     }
+    const double t1 = trace ? now() : 0.0;
+    if (trace) {
+        FDB_CUDA(cudaStreamSynchronize(ix->copy_stream));
+    }
+    const double t1c = trace ? now() : 0.0;
     FDB_TRY(batch_end(b, ix->q_dev.p, ix->out_p.p, ix->out_v.p, ix->out_d.p, ix->out_c.p));
+    const double t2 = trace ? now() : 0.0;
     FDB_CUDA(cudaMemcpyAsync(out_partition, ix->out_p.p, nq * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     FDB_CUDA(cudaMemcpyAsync(out_vector_index, ix->out_v.p, nq * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     FDB_CUDA(cudaMemcpyAsync(out_sqdist, ix->out_d.p, nq * k * sizeof(float), cudaMemcpyDeviceToHost, st));
     FDB_CUDA(cudaMemcpyAsync(out_count, ix->out_c.p, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    return finish_query(ctx);
+    const int rc = finish_query(ctx);
+    if (trace)
+        fprintf(stderr, "[fdb query] nq=%zu slices=%zu: enqueue %.3f ms, copies done +%.3f, batch end (sync + hand-back) +%.3f, "
+                        "results +%.3f, total %.3f ms\n", nq, nslices, t1 - t0, t1c - t1, t2 - t1c, now() - t2, now() - t0);
+    return rc;
 }
 
 int fdb_index_probe(fdb_index *ix, const float *queries, size_t nq, size_t nprobe, int mode,
