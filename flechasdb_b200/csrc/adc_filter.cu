@@ -79,10 +79,9 @@ struct FilterState {
     Slot *cur = &slot[0];
     bool batch_reprobe = false;      // some slice of the batch took its probe lists from the probe filter
     cudaEvent_t begun = nullptr;     // batch_begin's resets, the slot streams wait for it
-    unsigned long long *h_counters = nullptr;  // pinned
+    unsigned long long *h_counters = nullptr;  // the last 128 bytes of the context's pinned staging area
     size_t chunk_q = 4096;
     ~FilterState() {
-        if (h_counters) cudaFreeHost(h_counters);
         for (Slot &sl : slot) {
             if (sl.stream) cudaStreamDestroy(sl.stream);
             if (sl.done) cudaEventDestroy(sl.done);
@@ -1343,7 +1342,7 @@ int filter_prepare(fdb_index *ix) {
     FDB_TRY(fs->bounds.alloc(2));
     for (FilterState::Slot &sl : fs->slot) FDB_TRY(sl.counters.alloc(12));
     FDB_TRY(fs->bcounters.alloc(12));
-    FDB_CUDA(cudaMallocHost((void **)&fs->h_counters, 12 * sizeof(unsigned long long)));
+    fs->h_counters = reinterpret_cast<unsigned long long *>(static_cast<char *>(ctx->h_pinned) + ctx->h_pinned_bytes - 128);
     FDB_CUDA(cudaMemsetAsync(fs->bounds.p, 0, 2 * sizeof(unsigned), st));
     // which GEMMs run on the tensor pipe (tcgen05, bf16 3-term split); both operands are then
     // centred by the mean of the coarse centroids, which shrinks |x'| |c'| and with it the band

@@ -585,18 +585,68 @@ int fdb_kmeans_run(fdb_km *km, size_t max_rounds, float epsilon, float *gradient
         set_error("too many problems for the staging buffer");
         return FDB_ERR_UNSUPPORTED;
     }
-    for (size_t r = 0; r < max_rounds; ++r) {
+    // One round = update + reassignment + the read-back of the active flags: ~16 stream operations,
+    // several of them shorter than a launch.  Round 0 runs eagerly (it allocates), round 1 is
+    // captured into a CUDA graph, the later rounds replay it: one launch per round instead of 16.
+    cudaGraphExec_t round_graph = nullptr;
+    uint64_t graph_launches = 0;
+    const bool use_graph = !getenv("FDB_NO_GRAPH") && !getenv("FDB_TC_STATS");
+    auto one_round = [&]() -> int {
         // update; a problem whose gradient < epsilon clears its own active flag on the device,
         // so the reassignment that follows skips it (src/kmeans.rs:130-132)
         FDB_TRY(km_update(km, km->active.p, 1, epsilon, km->max_rounds));
         FDB_TRY(km_reassign(km, km->active.p));
         FDB_CUDA(cudaMemcpyAsync(h_active, km->active.p, nb * sizeof(int), cudaMemcpyDeviceToHost,
                                  ctx->stream));
-        FDB_CUDA(cudaStreamSynchronize(ctx->stream));
+        return FDB_OK;
+    };
+    int rc_loop = FDB_OK;
+    for (size_t r = 0; r < max_rounds; ++r) {
+        if (round_graph) {
+            if (cudaGraphLaunch(round_graph, ctx->stream) != cudaSuccess) {
+                set_error("cudaGraphLaunch failed: %s", cudaGetErrorString(cudaGetLastError()));
+                rc_loop = FDB_ERR_CUDA;
+                break;
+            }
+            ctx->launches += graph_launches;
+        } else if (use_graph && r == 1) {
+            const uint64_t l0 = ctx->launches;
+            cudaGraph_t g = nullptr;
+            bool ok = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+            if (ok) {
+                const int rc = one_round();
+                const cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
+                ok = rc == FDB_OK && e == cudaSuccess && g != nullptr;
+            }
+            if (ok) ok = cudaGraphInstantiate(&round_graph, g, 0) == cudaSuccess;
+            if (g) cudaGraphDestroy(g);
+            if (!ok) {  // not capturable here: run the round the ordinary way
+                cudaGetLastError();
+                round_graph = nullptr;
+                ctx->launches = l0;
+                if ((rc_loop = one_round()) != FDB_OK) break;
+            } else {
+                graph_launches = ctx->launches - l0;
+                if (cudaGraphLaunch(round_graph, ctx->stream) != cudaSuccess) {
+                    set_error("cudaGraphLaunch failed: %s", cudaGetErrorString(cudaGetLastError()));
+                    rc_loop = FDB_ERR_CUDA;
+                    break;
+                }
+            }
+        } else {
+            if ((rc_loop = one_round()) != FDB_OK) break;
+        }
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+            set_error("cudaStreamSynchronize failed: %s", cudaGetErrorString(cudaGetLastError()));
+            rc_loop = FDB_ERR_CUDA;
+            break;
+        }
         bool any = false;
         for (size_t b = 0; b < nb; ++b) any |= h_active[b] != 0;
         if (!any) break;
     }
+    if (round_graph) cudaGraphExecDestroy(round_graph);
+    FDB_TRY(rc_loop);
     std::vector<float> gh(nb * km->max_rounds);
     if (gradients) {
         FDB_CUDA(cudaMemcpyAsync(gh.data(), km->grad_hist.p, gh.size() * sizeof(float),
