@@ -173,20 +173,28 @@ def run_ours(args, rank, world, local_rank, dist):
     capi.check(capi.lib().fdb_vs_download(gen.h, capi.f32p(host_x)))
     gen.close()
 
-    t0 = time.perf_counter()
-    vs = engine.VectorSet.upload(ctx, host_x)
-    t_upload = time.perf_counter() - t0
-    launches0 = ctx.launches
-    ctx.timer_start()
-    t1 = time.perf_counter()
-    events = []
-    build_profile = {} if os.environ.get("FDB_BENCH_BUILD_PROFILE") else None
-    db = DatabaseBuilder(vs, ctx=ctx, seeds=BenchSeeds(SEED_KMEANS), profile=build_profile) \
-        .with_partitions(P).with_divisions(D).with_clusters(CN) \
-        .build_with_events(events.append)
-    build_dev_ms = ctx.timer_stop()
-    t_build = time.perf_counter() - t1
-    build_launches = ctx.launches - launches0
+    # the build runs twice: the first one pays the one-off costs (module load, first cudaMalloc of
+    # 2 GB of scratch, clock ramp) and is reported as sec_cold, the second one is the number
+    builds = []
+    db = None
+    for attempt in range(2):
+        if db is not None:
+            db.close()
+        t0 = time.perf_counter()
+        vs = engine.VectorSet.upload(ctx, host_x)
+        t_upload = time.perf_counter() - t0
+        launches0 = ctx.launches
+        ctx.timer_start()
+        t1 = time.perf_counter()
+        events = []
+        build_profile = {} if os.environ.get("FDB_BENCH_BUILD_PROFILE") else None
+        db = DatabaseBuilder(vs, ctx=ctx, seeds=BenchSeeds(SEED_KMEANS), profile=build_profile) \
+            .with_partitions(P).with_divisions(D).with_clusters(CN) \
+            .build_with_events(events.append)
+        build_dev_ms = ctx.timer_stop()
+        t_build = time.perf_counter() - t1
+        build_launches = ctx.launches - launches0
+        builds.append(build_dev_ms * 1e-3)
     rounds_coarse = sum(1 for e in events if e[0] == "ClusterEvent" and e[1][0] == "FinishedCentroidUpdate")
     ix = db.index
     ix.set_timing(True)
@@ -397,7 +405,7 @@ def run_ours(args, rank, world, local_rank, dist):
         "scan_large": scan_large,
         "cpu_baseline": cpu_baseline,
         "parity": {"queries_checked": ns, "id_mismatches": mism, "distances_bit_equal": dist_bits},
-        "build": {"metric": "ivfpq_build_sec_100kx1536", "sec": build_dev_ms * 1e-3,
+        "build": {"metric": "ivfpq_build_sec_100kx1536", "sec": build_dev_ms * 1e-3, "sec_cold": builds[0],
                   "e2e_sec": t_upload + t_build, "h2d_sec": t_upload, "gpu_launches": int(build_launches),
                   "lloyd_updates": len(upd), "lloyd_reassignments": len(rea),
                   "reassignments_coarse": n_rea_coarse, "reassignments_pq_all_divisions": n_rea_pq,
