@@ -86,6 +86,7 @@ SIGNATURES = {
     "fdb_index_set_timing": (C.c_int, [VP, C.c_int]),
     "fdb_index_last_timing": (C.c_int, [VP, F32P, U64P]),
     "fdb_index_last_stats": (C.c_int, [VP, U64P]),
+    "fdb_index_debug_band": (C.c_int, [VP, SZ, SZ, F32P, F32P, U32P, U32P, U32P]),
     "fdb_device_alloc": (C.c_int, [VP, SZ, C.POINTER(VP)]),
     "fdb_device_free": (C.c_int, [VP, VP]),
     "fdb_device_fill_uniform": (C.c_int, [VP, VP, SZ, C.c_uint64, C.c_uint64]),

@@ -96,6 +96,8 @@ int filter_fork(fdb_index *ix);
 int filter_slot_wait_fork(fdb_index *ix, int slot);
 int filter_slot_done(fdb_index *ix, int slot);
 int filter_join(fdb_index *ix);
+int filter_debug_band(fdb_index *ix, size_t nq, size_t nprobe, float *E, float *cand_approx, uint32_t *cand_flat,
+                      uint32_t *cand_cnt, uint32_t *probes);
 int filter_query(fdb_index *ix, const float *d_q, size_t q_base, size_t nq, size_t k, size_t nprobe, uint32_t *d_p,
                  uint32_t *d_v, float *d_d, uint32_t *d_c, EventLog *log);
 int filter_batch_end(fdb_index *ix, size_t nq_total, const uint32_t **d_fb_q, const uint32_t **d_fb_probes,

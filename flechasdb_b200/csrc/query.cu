@@ -932,6 +932,13 @@ int fdb_index_last_stats(fdb_index *ix, uint64_t out[4]) {
     return FDB_OK;
 }
 
+int fdb_index_debug_band(fdb_index *ix, size_t nq, size_t nprobe, float *E, float *cand_approx,
+                         uint32_t *cand_flat, uint32_t *cand_cnt, uint32_t *probes) {
+    ARG(ix && E && cand_approx && cand_flat && cand_cnt && probes, "null argument");
+    FDB_TRY(ix->ctx->use());
+    return filter_debug_band(ix, nq, nprobe, E, cand_approx, cand_flat, cand_cnt, probes);
+}
+
 int fdb_index_set_timing(fdb_index *ix, int enabled) {
     ARG(ix, "ix is null");
     ix->timing = enabled != 0;

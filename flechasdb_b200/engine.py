@@ -78,6 +78,10 @@ class VectorSet:
         check(capi.lib().fdb_vs_generate(ctx.h, n, dim, seed, start, C.byref(h)))
         return cls(ctx, h)
 
+    def device_ptr(self):
+        """Device address of the rows (for the *_device entry points)."""
+        return capi.lib().fdb_vs_device_ptr(self.h)
+
     def __len__(self):
         return int(capi.lib().fdb_vs_len(self.h))
 
@@ -295,6 +299,18 @@ class Index:
         st = np.zeros(4, np.uint64)
         check(capi.lib().fdb_index_last_stats(self.h, u64p(st)))
         return tuple(int(x) for x in st)
+
+    def debug_band(self, nq, nprobe):
+        """Test hook (after query_device): error bound E[q], the candidates' approximate distances and
+        flat positions, their count, and the probe lists the filter path scanned."""
+        E = np.zeros(nq, np.float32)
+        approx = np.zeros((nq, 32), np.float32)
+        flat = np.zeros((nq, 32), np.uint32)
+        cnt = np.zeros(nq, np.uint32)
+        probes = np.zeros((nq, nprobe), np.uint32)
+        check(capi.lib().fdb_index_debug_band(self.h, nq, nprobe, f32p(E), f32p(approx), u32p(flat),
+                                              u32p(cnt), u32p(probes)))
+        return E, approx, flat, cnt, probes
 
     def close(self):
         if self.h:

@@ -197,6 +197,13 @@ int fdb_index_last_timing(fdb_index *ix, float ms[6], uint64_t *scan_bytes);
  * [2] candidates the filter path evaluated exactly, [3] code vectors it scanned.
  * Results are identical on both paths; FDB_QUERY_EXACT=1 in the environment forces [1]. */
 int fdb_index_last_stats(fdb_index *ix, uint64_t out[4]);
+/* test hook: the filter path's view of the nq queries of the last fdb_index_query_device call
+ * (one slice): E[q] = its bound on |approximate - true| distance, the up to 32 smallest approximate
+ * distances per query (ascending) with their positions in the concatenation of the probed lists,
+ * and the probe lists it scanned (the reference's probe set, in no particular order). */
+int fdb_index_debug_band(fdb_index *ix, size_t nq, size_t nprobe, float *E /*[nq]*/,
+                         float *cand_approx /*[nq][32]*/, uint32_t *cand_flat /*[nq][32]*/,
+                         uint32_t *cand_cnt /*[nq]*/, uint32_t *probes /*[nq][nprobe]*/);
 
 /* raw device buffers for benches that keep inputs resident */
 int fdb_device_alloc(fdb_ctx *ctx, size_t bytes, void **out);

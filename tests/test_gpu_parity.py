@@ -500,6 +500,57 @@ def test_filter_path_on_clustered_data(eng, ctx, oracle, N, P, D, Cn, M, k, npro
     ix.close()
 
 
+@pytest.mark.parametrize("N,P,D,Cn,M,nprobe,clustered", [
+    (1536, 100, 12, 256, 20000, 5, False),   # both GEMMs on the tensor pipe (3-term bf16 split)
+    (128, 64, 16, 256, 20000, 8, False),     # tables from the fp32 FMA GEMM
+    (256, 300, 4, 256, 30000, 16, True),     # clustered data far from the origin
+])
+def test_filter_error_bound_holds(eng, ctx, oracle, N, P, D, Cn, M, nprobe, clustered):
+    """The band is only as good as the bound behind it: |approximate - reference| distance of every
+    candidate the scan kept must stay below E_q + eta * reference (adc_filter.cu header), and by a wide
+    margin, because the band adds a factor of 2 on top."""
+    k, nq = 10, 64
+    if clustered:
+        coarse, cbs, off, codes, _ = _clustered_index(oracle, N, P, D, Cn, M, 5)
+    else:
+        coarse, cbs, off, codes = random_index(oracle, N, P, D, Cn, M)
+    ix = eng.Index.create(ctx, coarse, cbs, off, codes.astype(np.uint8))
+    oix = oracle.QueryIndex(coarse, cbs, off, codes)
+    d_q = ctx.alloc(nq * N * 4)
+    ctx.fill_uniform(d_q, nq * N, SEED + 90)          # the same counter-based generator as the oracle's
+    q = data(oracle, nq, N, SEED + 90)
+    if clustered:                                      # move the queries to where the data is
+        q = (q + coarse[:nq] - np.float32(0.5)).astype(np.float32)
+        vs = eng.VectorSet.upload(ctx, q)
+        d_q = vs.device_ptr()
+    outs = [ctx.alloc(nq * k * 4) for _ in range(3)] + [ctx.alloc(nq * 4)]
+    ix.query_device(d_q, nq, k, nprobe, *outs)
+    E, approx, flat, cnt, probes = ix.debug_band(nq, nprobe)
+    s = N // D
+    eta = (s / 16.0 + 40.0 + D) * 2.0 ** -24
+    sizes = np.diff(off.astype(np.int64))
+    worst = 0.0
+    for qi in range(0, nq, 4):
+        if not np.isfinite(E[qi]):
+            continue                                   # a query the probe filter handed back
+        starts = np.concatenate([[0], np.cumsum(sizes[probes[qi]])])
+        tables = {}
+        for c in range(int(cnt[qi])):
+            pr = int(np.searchsorted(starts, flat[qi, c], side="right") - 1)
+            part, vidx = int(probes[qi, pr]), int(flat[qi, c] - starts[pr])
+            if part not in tables:
+                tables[part] = oix.table(q[qi], part)
+            code = codes[int(off[part]) + vidx]
+            r = np.float32(0.0)
+            for d in range(D):
+                r = np.float32(r + tables[part][d, code[d]])
+            err = abs(float(approx[qi, c]) - float(r))
+            worst = max(worst, err / (float(E[qi]) + eta * float(r)))
+    print("worst |approx - reference| / (E + eta R) = %.4f" % worst)
+    assert 0.0 < worst < 0.5, worst                   # observed: 0.2 % .. 2 % of the bound
+    ix.close()
+
+
 def test_filter_path_equals_exact_pipeline_on_a_large_batch(eng, ctx, oracle, monkeypatch):
     """4096 queries against the README shape: ids, distances and counts of the filter path equal
     the exact pipeline's bit for bit (the oracle is too slow for this many; it checks a sample)."""
