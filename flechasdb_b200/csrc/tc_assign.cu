@@ -222,7 +222,10 @@ struct TcParams {
     size_t n, m, nb, k, col_off;
     size_t xcol_stride;         // operand columns of problem b start at col_off + b * xcol_stride
     size_t crow_stride;         // centroid rows of problem b start at b * crow_stride
-    int mode;                   // 0: assignment epilogue, 1: raw scores out = alpha * acc - (sub_h ? h : 0)
+    int mode;                   // 0: assignment epilogue, 1: raw scores out = alpha * acc - (sub_h ? h : 0),
+                                // 2: the three largest scores of every (row, column tile) for tc_combine_kernel
+    float *tile_v;              // mode 2: [n][nb][4] scores v1 >= v2 >= v3 of the tile (problem b = column tile)
+    uint16_t *tile_i;           //         [n][nb][2] columns of v1, v2 inside the tile
     float *out;                 // mode 1: out[row * out_row_stride + b * out_b_stride + col]
     size_t out_row_stride, out_b_stride;
     float alpha;
@@ -300,7 +303,7 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
             uint32_t phase = 0;
             for (int t = t_begin; t < t_end; ++t) {
                 const int b = t / p.row_tiles, rt = t - b * p.row_tiles;
-                if (p.active && !p.active[b]) continue;
+                if (p.active && !p.active[p.mode == 2 ? 0 : b]) continue;
                 const int row0 = rt * BM;
                 const int kcol0 = (int)(p.col_off + (size_t)b * p.xcol_stride);
                 const int crow0 = (int)((size_t)b * p.crow_stride);
@@ -330,7 +333,7 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
             uint32_t phase = 0, aphase = 0;
             for (int t = t_begin; t < t_end; ++t) {
                 const int b = t / p.row_tiles;
-                if (p.active && !p.active[b]) continue;
+                if (p.active && !p.active[p.mode == 2 ? 0 : b]) continue;
                 mbar_wait(&tmem_empty[as], aphase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * NP);
@@ -372,7 +375,7 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
         uint32_t aphase = 0;
         for (int t = t_begin; t < t_end; ++t) {
             const int b = t / p.row_tiles, rt = t - b * p.row_tiles;
-            if (p.active && !p.active[b]) continue;
+            if (p.active && !p.active[p.mode == 2 ? 0 : b]) continue;
             const size_t grow = (size_t)rt * BM + row;
             const bool valid = grow < p.n;
             // h_j = |c'_j|^2/2 of this problem in shared memory (reloaded when the problem changes)
@@ -408,6 +411,65 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tmem_empty[as]);
+                if (++as == 2) {
+                    as = 0;
+                    aphase ^= 1;
+                }
+                continue;
+            }
+            if (p.mode == 2) {
+                // the three largest scores of this thread's half of the tile's columns, with the
+                // columns of the first two (strict >: the lower column wins ties)
+                const float NI = -__int_as_float(0x7f800000);
+                float v1 = NI, v2 = NI, v3 = NI;
+                int i1 = 0, i2 = 0;
+                float va[32];
+                for (int c0 = 0; c0 < half; c0 += 32) {
+                    tmem_ld32_issue(taddr + c0, va);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float sv = va[i] - hb[c0 + i];
+                        const int c = hf * half + c0 + i;
+                        const bool g1 = sv > v1, g2 = sv > v2, g3 = sv > v3;
+                        v3 = g2 ? v2 : (g3 ? sv : v3);
+                        i2 = g1 ? i1 : (g2 ? c : i2);
+                        v2 = g1 ? v1 : (g2 ? sv : v2);
+                        i1 = g1 ? c : i1;
+                        v1 = g1 ? sv : v1;
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[as]);
+                // merge the two halves of the row (half 1 hands its triple to half 0)
+                if (hf == 1) {
+                    rowmax_s[1][row] = v1;
+                    rowsec_s[1][row] = v2;
+                    rowmax_s[0][row] = v3;
+                    rowarg_s[1][row] = (uint16_t)i1;
+                    rowarg_s[0][row] = (uint16_t)i2;
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (hf == 0 && valid) {
+                    const float w[3] = {rowmax_s[1][row], rowsec_s[1][row], rowmax_s[0][row]};
+                    const int wi[2] = {rowarg_s[1][row], rowarg_s[0][row]};
+#pragma unroll
+                    for (int u = 0; u < 3; ++u) {   // columns of half 1 are higher: strict > keeps ties low
+                        const float sv = w[u];
+                        const int c = u < 2 ? wi[u] : 0;
+                        const bool g1 = sv > v1, g2 = sv > v2, g3 = sv > v3;
+                        v3 = g2 ? v2 : (g3 ? sv : v3);
+                        i2 = g1 ? i1 : (g2 ? c : i2);
+                        v2 = g1 ? v1 : (g2 ? sv : v2);
+                        i1 = g1 ? c : i1;
+                        v1 = g1 ? sv : v1;
+                    }
+                    const size_t o = grow * p.nb + b;
+                    *reinterpret_cast<float4 *>(p.tile_v + 4 * o) = make_float4(v1, v2, v3, 0.0f);
+                    *reinterpret_cast<uint32_t *>(p.tile_i + 2 * o) = (uint32_t)i1 | ((uint32_t)i2 << 16);
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
                 if (++as == 2) {
                     as = 0;
                     aphase ^= 1;
@@ -602,6 +664,59 @@ __global__ void __launch_bounds__(256) recheck_kernel(const float *x, size_t n, 
     }
 }
 
+// ---- k > 256: column tiles of 256 centroids ------------------------------------------------------
+// tc_assign_kernel (mode 2) leaves the three largest scores of every (row, tile); one thread per row
+// puts them together: the global maximum, the band, and the columns that can be inside it.  A tile
+// whose third score is inside the band may hold more: the row is then decided over all k centroids.
+__global__ void __launch_bounds__(256) tc_combine_kernel(TcParams p, size_t ktotal) {
+    const size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p.active && !p.active[0]) return;
+    if (row >= p.n) return;
+    const float NI = -__int_as_float(0x7f800000);
+    const int nct = (int)p.nb;
+    float smax = NI;
+    for (int ct = 0; ct < nct; ++ct) smax = fmaxf(smax, p.tile_v[4 * (row * nct + ct)]);
+    unsigned cb = 0;
+    for (int ct = 0; ct < nct; ++ct) cb = max(cb, p.cmax2_bits[ct]);
+    const float cmax2 = __uint_as_float(cb);
+    const float xn2 = p.xn2[row];
+    const float E = p.gamma1 * sqrtf(xn2 * cmax2) * 1.0001f + 1.2e-7f * (0.5f * cmax2);
+    const float dmin = fmaxf(0.0f, xn2 - 2.0f * smax + 2.0f * E);
+    const float shift = 1.3e-7f * sqrtf(dmin) * (sqrtf(xn2) + sqrtf(cmax2));
+    const float band = 2.0f * (2.0f * E + 1.01f * p.eta * dmin + shift);
+    const float thresh = smax - band;
+    // every column inside the band (the negated comparisons also catch NaN scores)
+    uint32_t cand[CAP];
+    unsigned c = 0;
+    bool all = !(smax > NI) || !(thresh == thresh);
+    for (int ct = 0; ct < nct && !all; ++ct) {
+        const float4 v = *reinterpret_cast<const float4 *>(p.tile_v + 4 * (row * nct + ct));
+        const uint32_t ii = *reinterpret_cast<const uint32_t *>(p.tile_i + 2 * (row * nct + ct));
+        if (v.z >= thresh) all = true;   // a third (and maybe more) inside the band
+        if (v.x >= thresh) {
+            if (c < CAP) cand[c] = (uint32_t)ct * 256u + (ii & 0xffffu);
+            ++c;
+        }
+        if (v.y >= thresh) {
+            if (c < CAP) cand[c] = (uint32_t)ct * 256u + (ii >> 16);
+            ++c;
+        }
+    }
+    if (c > CAP) all = true;
+    if (!all && c == 1) {
+        p.indices[row] = cand[0];
+        return;
+    }
+    const unsigned slot = atomicAdd(p.work_count, 1u);
+    if (slot < p.work_cap) {
+        p.work_rows[slot] = (uint32_t)row;
+        p.work_cnt[slot] = (uint8_t)((all || c < 2) ? CAP + 1 : c);
+        for (unsigned u = 0; u < CAP; ++u) p.work_cand[(size_t)slot * CAP + u] = (uint16_t)(u < c && !all ? cand[u] : 0);
+        if (all || c < 2) atomicAdd(&p.stats[1], 1u);
+    }
+    (void)ktotal;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
@@ -646,6 +761,9 @@ struct TcState {
     DevBuf<float> xn2, h, mu;
     DevBuf<double> mean_partial;
     DevBuf<unsigned> cmax2, work_count, stats;
+    DevBuf<float> tile_v;       // k > 256: [n][tiles][4] largest scores per (row, column tile)
+    DevBuf<uint16_t> tile_i;    //          [n][tiles][2] their columns
+    size_t pnb = 0;
     DevBuf<uint32_t> work_rows;
     DevBuf<uint16_t> work_cand;
     DevBuf<uint8_t> work_cnt;
@@ -658,7 +776,7 @@ struct TcState {
 bool tc_eligible(const fdb_km *km) {
     if (getenv("FDB_DISABLE_TC")) return false;
     const size_t ld = km->vs->dim;
-    return km->k <= 256 && km->m % BK == 0 && ld % 8 == 0 && km->col_off % 8 == 0 &&
+    return (km->k <= 256 || (km->nb == 1 && km->k <= 65535)) && km->m % BK == 0 && ld % 8 == 0 && km->col_off % 8 == 0 &&
            km->n >= 1 && km->n < (1ull << 31) && km->nb * km->n < (1ull << 32) &&
            ((uintptr_t)km->vs->d % 16 == 0);
 }
@@ -679,23 +797,31 @@ int tc_reassign(fdb_km *km, const int *d_active) {
     const size_t n = km->n, m = km->m, nb = km->nb, k = km->k, ld = km->vs->dim;
     if (!km->tc) km->tc = new TcState;
     TcState *tc = km->tc;
-    const int np = (int)((k + 63) / 64 * 64);
+    // k > 256 (one problem): column tiles of 256 centroids are the kernel's "problems"; they share the
+    // operand columns, every tile leaves its three largest scores per row, tc_combine_kernel decides
+    const bool tiled = k > 256;
+    const size_t pk = tiled ? 256 : k, pnb = tiled ? (k + 255) / 256 : nb;
+    const int np = tiled ? 256 : (int)((k + 63) / 64 * 64);
     cudaStream_t st = ctx->stream;
-    if (tc->rows_version != km->vs->version || tc->np != np) {
+    if (tc->rows_version != km->vs->version || tc->np != np || tc->pnb != pnb) {
         FDB_TRY(tc->x1.ensure(n * ld));
         FDB_TRY(tc->x2.ensure(n * ld));
         FDB_TRY(tc->xn2.ensure(nb * n));
-        FDB_TRY(tc->c1.ensure(nb * k * m + 256 * m));  // slack: the last problem's box reads past nb*k rows
-        FDB_TRY(tc->c2.ensure(nb * k * m + 256 * m));
-        FDB_TRY(tc->h.ensure(nb * np));
-        FDB_TRY(tc->cmax2.ensure(nb));
+        FDB_TRY(tc->c1.ensure(pnb * pk * m + 256 * m));  // slack: the last problem's box reads past its rows
+        FDB_TRY(tc->c2.ensure(pnb * pk * m + 256 * m));
+        FDB_TRY(tc->h.ensure(pnb * np));
+        FDB_TRY(tc->cmax2.ensure(pnb));
+        if (tiled) {
+            FDB_TRY(tc->tile_v.ensure(n * pnb * 4));
+            FDB_TRY(tc->tile_i.ensure(n * pnb * 2));
+        }
         FDB_TRY(tc->work_count.ensure(1));
         FDB_TRY(tc->stats.ensure(2));
         FDB_TRY(tc->work_rows.ensure(nb * n));
         FDB_TRY(tc->work_cand.ensure(nb * n * CAP));
         FDB_TRY(tc->work_cnt.ensure(nb * n));
-        FDB_CUDA(cudaMemsetAsync(tc->c1.p, 0, (nb * k * m + 256 * m) * 2, st));
-        FDB_CUDA(cudaMemsetAsync(tc->c2.p, 0, (nb * k * m + 256 * m) * 2, st));
+        FDB_CUDA(cudaMemsetAsync(tc->c1.p, 0, (pnb * pk * m + 256 * m) * 2, st));
+        FDB_CUDA(cudaMemsetAsync(tc->c2.p, 0, (pnb * pk * m + 256 * m) * 2, st));
         // mu = column means of this problem's columns (any mu is valid; the mean minimises |x'|)
         const size_t ncols = nb * m;
         FDB_TRY(tc->mu.ensure(ld));
@@ -715,31 +841,36 @@ int tc_reassign(fdb_km *km, const int *d_active) {
         FDB_CHECK_LAUNCH();
         FDB_TRY(make_map(&tc->map_x1, tc->x1.p, ld, n, BM));
         FDB_TRY(make_map(&tc->map_x2, tc->x2.p, ld, n, BM));
-        FDB_TRY(make_map(&tc->map_c1, tc->c1.p, m, nb * k + 256, (uint32_t)np));
-        FDB_TRY(make_map(&tc->map_c2, tc->c2.p, m, nb * k + 256, (uint32_t)np));
+        FDB_TRY(make_map(&tc->map_c1, tc->c1.p, m, pnb * pk + 256, (uint32_t)np));
+        FDB_TRY(make_map(&tc->map_c2, tc->c2.p, m, pnb * pk + 256, (uint32_t)np));
         tc->rows_version = km->vs->version;
         tc->np = np;
+        tc->pnb = pnb;
     }
-    FDB_CUDA(cudaMemsetAsync(tc->cmax2.p, 0, nb * sizeof(unsigned), st));
+    FDB_CUDA(cudaMemsetAsync(tc->cmax2.p, 0, pnb * sizeof(unsigned), st));
     FDB_CUDA(cudaMemsetAsync(tc->work_count.p, 0, sizeof(unsigned), st));
     FDB_CUDA(cudaMemsetAsync(tc->stats.p, 0, 2 * sizeof(unsigned), st));
     {
-        dim3 grid((unsigned)np, (unsigned)nb);
-        prep_centroids_kernel<<<grid, 128, 0, st>>>(km->centroids.p, k, m, (size_t)np, tc->mu.p, km->col_off, m,
-                                                    nb * k, tc->c1.p, tc->c2.p,
-                                                    tc->h.p, tc->cmax2.p, d_active);
+        dim3 grid((unsigned)np, (unsigned)pnb);
+        // (tiled: every tile is centred by the same columns, rows past k are padding; the active flag of
+        // the one problem is checked by the kernels that follow)
+        prep_centroids_kernel<<<grid, 128, 0, st>>>(km->centroids.p, pk, m, (size_t)np, tc->mu.p, km->col_off,
+                                                    tiled ? 0 : m, nb * k, tc->c1.p, tc->c2.p, tc->h.p,
+                                                    tc->cmax2.p, tiled ? nullptr : d_active);
         ctx->launches++;
         FDB_CHECK_LAUNCH();
     }
     TcParams p;
     p.n = n;
     p.m = m;
-    p.nb = nb;
-    p.k = k;
+    p.nb = pnb;
+    p.k = pk;
     p.col_off = km->col_off;
-    p.xcol_stride = m;
-    p.crow_stride = k;
-    p.mode = 0;
+    p.xcol_stride = tiled ? 0 : m;
+    p.crow_stride = pk;
+    p.mode = tiled ? 2 : 0;
+    p.tile_v = tc->tile_v.p;
+    p.tile_i = tc->tile_i.p;
     p.out = nullptr;
     p.out_row_stride = p.out_b_stride = 0;
     p.alpha = 1.0f;
@@ -765,11 +896,16 @@ int tc_reassign(fdb_km *km, const int *d_active) {
     p.stats = tc->stats.p;
     const size_t smem = (size_t)p.stages * stage_bytes + 1024;
     FDB_CUDA(cudaFuncSetAttribute(tc_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int total_tiles = (int)nb * p.row_tiles;
+    const int total_tiles = (int)pnb * p.row_tiles;
     const int grid = std::min(total_tiles, ctx->sm_count);
     tc_assign_kernel<<<grid, TC_THREADS, smem, st>>>(tc->map_x1, tc->map_x2, tc->map_c1, tc->map_c2, p);
     ctx->launches++;
     FDB_CHECK_LAUNCH();
+    if (tiled) {
+        tc_combine_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, k);
+        ctx->launches++;
+        FDB_CHECK_LAUNCH();
+    }
     recheck_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(km->vs->d, n, ld, km->col_off, m, k, km->centroids.p,
                                                       tc->work_count.p, p.work_cap, tc->work_rows.p,
                                                       tc->work_cand.p, tc->work_cnt.p, km->indices.p,

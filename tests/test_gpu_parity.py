@@ -706,6 +706,31 @@ def test_tc_reassign_adversarial(eng, ctx, oracle):
     _tc_case(eng, ctx, oracle, x, centers)
 
 
+@pytest.mark.parametrize("n,m,k", [(4000, 128, 300), (3000, 256, 1024), (2500, 64, 257), (1500, 768, 600)])
+def test_tc_reassign_more_than_256_centroids(eng, ctx, oracle, n, m, k):
+    """k > 256: column tiles of 256 centroids, three largest scores per (row, tile), combine kernel."""
+    _tc_case(eng, ctx, oracle, data(oracle, n, m), data(oracle, k, m, SEED + 7))
+
+
+def test_tc_reassign_tiled_adversarial(eng, ctx, oracle):
+    rng = np.random.default_rng(1)
+    n, m, k = 1500, 128, 700
+    # near ties spread over tiles, exact duplicates in different tiles (lowest index must win)
+    base = data(oracle, 1, m, SEED + 1)
+    cent = (base + rng.normal(0, 1e-6, (k, m))).astype(np.float32)
+    cent[650] = cent[3]
+    cent[300] = cent[3]
+    _tc_case(eng, ctx, oracle, data(oracle, n, m), cent)
+    # rows that coincide with centroids, and a common offset
+    x = (data(oracle, n, m) + np.float32(100.0)).astype(np.float32)
+    cent = x[rng.choice(n, k, replace=False)].copy()
+    _tc_case(eng, ctx, oracle, x, cent)
+    # clustered data: one clear winner per row
+    centers = rng.normal(0, 5, (k, m)).astype(np.float32)
+    x = (centers[rng.integers(0, k, n)] + rng.normal(0, 0.5, (n, m))).astype(np.float32)
+    _tc_case(eng, ctx, oracle, x, centers)
+
+
 def test_tc_lloyd_trajectory_equals_exact_path(eng, ctx, oracle, monkeypatch):
     """A whole k-means run on the tensor-core path reproduces the oracle's trajectory."""
     n, m, k = 6000, 128, 32
