@@ -91,13 +91,15 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 // K-major operand tile, 128-byte rows, SWIZZLE_128B: 8-row groups are 1024 bytes apart.
 // (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO [16,30), SBO [32,46), version=1 [46,48),
 //  layout_type=2 (SWIZZLE_128B) [61,64))
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, int bk) {
+    // bk = 64: 128-byte rows, SWIZZLE_128B (layout 2), 8-row groups 1024 bytes apart;
+    // bk = 16:  32-byte rows, SWIZZLE_32B  (layout 6), 8-row groups  256 bytes apart
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-    d |= (uint64_t)1 << 16;                 // LBO (unused for swizzled K-major) = 1
-    d |= (uint64_t)(1024 >> 4) << 32;       // SBO = 1024 bytes
-    d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+    d |= (uint64_t)1 << 16;                                   // LBO (unused for swizzled K-major) = 1
+    d |= (uint64_t)((bk == 64 ? 1024 : 256) >> 4) << 32;      // SBO
+    d |= (uint64_t)1 << 46;                                   // descriptor version (Blackwell)
+    d |= (uint64_t)(bk == 64 ? 2 : 6) << 61;                  // layout type
     return d;
 }
 // issue without waiting: the registers are valid only after tmem_ld_wait()
@@ -231,6 +233,7 @@ struct TcParams {
     float alpha;
     int sub_h;
     int np;                     // padded N (multiple of 64, <= 256)
+    int bk;                     // bf16 elements per K chunk: 64 (m % 64 == 0) or 16
     int row_tiles;              // ceil(n / 128)
     int stages;
     const float *h;             // [nb][np]
@@ -263,11 +266,12 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int NP = p.np;
-    const uint32_t a_bytes = BM * BK * 2;             // 16 KB per piece
-    const uint32_t b_bytes = (uint32_t)NP * BK * 2;   // NP * 128 B per piece
+    const int BKr = p.bk;                             // 64, or 16 when m is not a multiple of 64
+    const uint32_t a_bytes = BM * BKr * 2;            // 16 KB per piece (bk = 64)
+    const uint32_t b_bytes = (uint32_t)NP * BKr * 2;  // NP * 128 B per piece
     const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
     const int S = p.stages;
-    const int kchunks = (int)(p.m / BK);
+    const int kchunks = (int)(p.m / BKr);
     const int total_tiles = (int)p.nb * p.row_tiles;
     // contiguous tile ranges per CTA (a CTA mostly stays inside one problem: its centroids stay hot in L2)
     const int per_cta = (total_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -311,10 +315,10 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     unsigned char *st = smem + (size_t)stage * stage_bytes;
                     mbar_expect_tx(&full_bar[stage], stage_bytes);
-                    tma_load_2d(st, &map_x1, kcol0 + kc * BK, row0, &full_bar[stage]);
-                    tma_load_2d(st + a_bytes, &map_x2, kcol0 + kc * BK, row0, &full_bar[stage]);
-                    tma_load_2d(st + 2 * a_bytes, &map_c1, kc * BK, crow0, &full_bar[stage]);
-                    tma_load_2d(st + 2 * a_bytes + b_bytes, &map_c2, kc * BK, crow0, &full_bar[stage]);
+                    tma_load_2d(st, &map_x1, kcol0 + kc * BKr, row0, &full_bar[stage]);
+                    tma_load_2d(st + a_bytes, &map_x2, kcol0 + kc * BKr, row0, &full_bar[stage]);
+                    tma_load_2d(st + 2 * a_bytes, &map_c1, kc * BKr, crow0, &full_bar[stage]);
+                    tma_load_2d(st + 2 * a_bytes + b_bytes, &map_c2, kc * BKr, crow0, &full_bar[stage]);
                     if (++stage == S) {
                         stage = 0;
                         phase ^= 1;
@@ -341,11 +345,10 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-                    const uint64_t a1 = make_smem_desc(sa), a2 = make_smem_desc(sa + a_bytes);
-                    const uint64_t b1 = make_smem_desc(sa + 2 * a_bytes);
-                    const uint64_t b2 = make_smem_desc(sa + 2 * a_bytes + b_bytes);
-#pragma unroll
-                    for (int ks = 0; ks < BK / 16; ++ks) {
+                    const uint64_t a1 = make_smem_desc(sa, BKr), a2 = make_smem_desc(sa + a_bytes, BKr);
+                    const uint64_t b1 = make_smem_desc(sa + 2 * a_bytes, BKr);
+                    const uint64_t b2 = make_smem_desc(sa + 2 * a_bytes + b_bytes, BKr);
+                    for (int ks = 0; ks < BKr / 16; ++ks) {
                         const uint64_t off = (uint64_t)(ks * 32 >> 4);  // 16 bf16 = 32 bytes along K
                         umma_bf16(d_tmem, a2 + off, b1 + off, idesc, (kc | ks) != 0);  // small terms first
                         umma_bf16(d_tmem, a1 + off, b2 + off, idesc, 1);
@@ -734,7 +737,7 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-int make_map(CUtensorMap *map, void *base, uint64_t inner, uint64_t outer, uint32_t box_outer) {
+int make_map(CUtensorMap *map, void *base, uint64_t inner, uint64_t outer, uint32_t box_outer, int bk = BK) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) {
         set_error("cuTensorMapEncodeTiled is not available");
@@ -742,10 +745,10 @@ int make_map(CUtensorMap *map, void *base, uint64_t inner, uint64_t outer, uint3
     }
     cuuint64_t dims[2] = {inner, outer};
     cuuint64_t strides[1] = {inner * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BK, box_outer};
+    cuuint32_t box[2] = {(cuuint32_t)bk, box_outer};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed: %d", (int)r);
@@ -776,7 +779,7 @@ struct TcState {
 bool tc_eligible(const fdb_km *km) {
     if (getenv("FDB_DISABLE_TC")) return false;
     const size_t ld = km->vs->dim;
-    return (km->k <= 256 || (km->nb == 1 && km->k <= 65535)) && km->m % BK == 0 && ld % 8 == 0 && km->col_off % 8 == 0 &&
+    return (km->k <= 256 || (km->nb == 1 && km->k <= 65535)) && km->m % 16 == 0 && ld % 8 == 0 && km->col_off % 8 == 0 &&
            km->n >= 1 && km->n < (1ull << 31) && km->nb * km->n < (1ull << 32) &&
            ((uintptr_t)km->vs->d % 16 == 0);
 }
@@ -802,6 +805,7 @@ int tc_reassign(fdb_km *km, const int *d_active) {
     const bool tiled = k > 256;
     const size_t pk = tiled ? 256 : k, pnb = tiled ? (k + 255) / 256 : nb;
     const int np = tiled ? 256 : (int)((k + 63) / 64 * 64);
+    const int bk = m % BK == 0 ? BK : 16;
     cudaStream_t st = ctx->stream;
     if (tc->rows_version != km->vs->version || tc->np != np || tc->pnb != pnb) {
         FDB_TRY(tc->x1.ensure(n * ld));
@@ -839,10 +843,10 @@ int tc_reassign(fdb_km *km, const int *d_active) {
             km->vs->d, n, ld, km->col_off, m, nb, tc->mu.p, tc->x1.p, tc->x2.p, tc->xn2.p);
         ctx->launches++;
         FDB_CHECK_LAUNCH();
-        FDB_TRY(make_map(&tc->map_x1, tc->x1.p, ld, n, BM));
-        FDB_TRY(make_map(&tc->map_x2, tc->x2.p, ld, n, BM));
-        FDB_TRY(make_map(&tc->map_c1, tc->c1.p, m, pnb * pk + 256, (uint32_t)np));
-        FDB_TRY(make_map(&tc->map_c2, tc->c2.p, m, pnb * pk + 256, (uint32_t)np));
+        FDB_TRY(make_map(&tc->map_x1, tc->x1.p, ld, n, BM, bk));
+        FDB_TRY(make_map(&tc->map_x2, tc->x2.p, ld, n, BM, bk));
+        FDB_TRY(make_map(&tc->map_c1, tc->c1.p, m, pnb * pk + 256, (uint32_t)np, bk));
+        FDB_TRY(make_map(&tc->map_c2, tc->c2.p, m, pnb * pk + 256, (uint32_t)np, bk));
         tc->rows_version = km->vs->version;
         tc->np = np;
         tc->pnb = pnb;
@@ -877,7 +881,8 @@ int tc_reassign(fdb_km *km, const int *d_active) {
     p.sub_h = 1;
     p.np = np;
     p.row_tiles = (int)((n + BM - 1) / BM);
-    const size_t stage_bytes = 2 * (size_t)BM * BK * 2 + 2 * (size_t)np * BK * 2;
+    p.bk = bk;
+    const size_t stage_bytes = 2 * (size_t)BM * bk * 2 + 2 * (size_t)np * bk * 2;
     p.stages = (int)std::min<size_t>(4, (200 * 1024) / stage_bytes);
     p.h = tc->h.p;
     p.xn2 = tc->xn2.p;
@@ -999,6 +1004,7 @@ int tc_gemm_raw(fdb_ctx *ctx, const TcRows &rows, const TcCentroids &cent, size_
     p.sub_h = sub_h;
     p.np = cent.np;
     p.row_tiles = (int)((rows.n + BM - 1) / BM);
+    p.bk = BK;
     const size_t stage_bytes = 2 * (size_t)BM * BK * 2 + 2 * (size_t)cent.np * BK * 2;
     p.stages = (int)std::min<size_t>(4, (200 * 1024) / stage_bytes);
     p.h = cent.h.p;
