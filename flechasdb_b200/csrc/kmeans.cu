@@ -405,12 +405,26 @@ __global__ void __launch_bounds__(32) sort_scatter_kernel(SortParams p) {
     }
 }
 
-__global__ void cluster_count_kernel(const uint32_t *keys, size_t n, size_t k, uint32_t *cnt,
-                                     const int *active) {
+// cluster sizes: a shared-memory histogram per CTA (k <= 4096), flushed with one global atomic per
+// non-empty bin (one atomic per row on 256 hot counters is an order of magnitude slower)
+constexpr int COUNT_ROWS_PER_CTA = 4096;
+__global__ void __launch_bounds__(256) cluster_count_kernel(const uint32_t *keys, size_t n, size_t k, uint32_t *cnt,
+                                                            const int *active) {
+    extern __shared__ unsigned hist_s[];
     const size_t b = blockIdx.y;
     if (active && !active[b]) return;
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) atomicAdd(&cnt[b * (k + 1) + keys[b * n + i]], 1u);
+    const size_t lo = (size_t)blockIdx.x * COUNT_ROWS_PER_CTA;
+    const size_t hi = lo + COUNT_ROWS_PER_CTA < n ? lo + COUNT_ROWS_PER_CTA : n;
+    if (k <= 4096) {
+        for (size_t j = threadIdx.x; j < k; j += blockDim.x) hist_s[j] = 0;
+        __syncthreads();
+        for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) atomicAdd(&hist_s[keys[b * n + i]], 1u);
+        __syncthreads();
+        for (size_t j = threadIdx.x; j < k; j += blockDim.x)
+            if (hist_s[j]) atomicAdd(&cnt[b * (k + 1) + j], hist_s[j]);
+    } else {
+        for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) atomicAdd(&cnt[b * (k + 1) + keys[b * n + i]], 1u);
+    }
 }
 
 // ---- update_centroids (src/kmeans.rs:232-276) -----------------------------------------
@@ -426,10 +440,21 @@ struct UpdateParams {
     unsigned *flags;
 };
 
-__global__ void __launch_bounds__(128) accumulate_kernel(UpdateParams p) {
-    const size_t b = blockIdx.z, i = blockIdx.y;
+// One thread per (cluster, dimension): the members are added in ascending row order, so the chain is
+// sequential by construction.  m >= 128: blockIdx.x tiles the dimensions of one cluster; smaller m: a
+// CTA takes 128 / mpad clusters (mpad = m rounded up to a power of two) so that all its lanes work.
+__global__ void __launch_bounds__(128) accumulate_kernel(UpdateParams p, unsigned mpad) {
+    const size_t b = blockIdx.z;
     if (p.active && !p.active[b]) return;
-    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t i, e;
+    if (mpad >= 128) {
+        i = blockIdx.y;
+        e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    } else {
+        i = (size_t)blockIdx.y * (128 / mpad) + threadIdx.x / mpad;
+        e = threadIdx.x % mpad;
+        if (i >= p.k) return;
+    }
     if (e >= p.m) return;
     const uint32_t *mem = p.members + b * p.n;
     const size_t start = p.cl_off[b * (p.k + 1) + i], end = p.cl_off[b * (p.k + 1) + i + 1];
@@ -601,8 +626,9 @@ int km_sort_members(fdb_km *km, const int *d_active) {
     // cluster offsets = exclusive scan of the per-cluster counts
     FDB_CUDA(cudaMemsetAsync(km->cl_off.p, 0, nb * (k + 1) * sizeof(uint32_t), ctx->stream));
     {
-        dim3 grid((unsigned)((n + 255) / 256), (unsigned)nb);
-        cluster_count_kernel<<<grid, 256, 0, ctx->stream>>>(km->indices.p, n, k, km->cl_off.p, d_active);
+        dim3 grid((unsigned)((n + COUNT_ROWS_PER_CTA - 1) / COUNT_ROWS_PER_CTA), (unsigned)nb);
+        cluster_count_kernel<<<grid, 256, k <= 4096 ? k * sizeof(unsigned) : 0, ctx->stream>>>(
+            km->indices.p, n, k, km->cl_off.p, d_active);
         ctx->launches++;
         sort_scan_kernel<<<(unsigned)nb, 1024, 0, ctx->stream>>>(km->cl_off.p, k + 1, d_active);
         ctx->launches++;
@@ -631,6 +657,25 @@ int km_sort_members(fdb_km *km, const int *d_active) {
     }
     FDB_CHECK_LAUNCH();
     return FDB_OK;
+}
+
+struct AccGrid {
+    dim3 grid;
+    unsigned mpad;
+};
+static AccGrid acc_grid(const fdb_km *km) {
+    AccGrid a;
+    if (km->m >= 128) {
+        a.mpad = 128;
+        a.grid = dim3((unsigned)((km->m + 127) / 128), (unsigned)km->k, (unsigned)km->nb);
+    } else {
+        unsigned mp = 1;
+        while (mp < km->m) mp <<= 1;
+        a.mpad = mp;
+        const unsigned cpb = 128 / mp;
+        a.grid = dim3(1, (unsigned)((km->k + cpb - 1) / cpb), (unsigned)km->nb);
+    }
+    return a;
 }
 
 static UpdateParams make_update_params(fdb_km *km, const int *d_active, float *partial) {
@@ -671,8 +716,8 @@ int km_update(fdb_km *km, const int *d_active, int loop_mode, float eps, size_t 
     fdb_ctx *ctx = km->ctx;
     FDB_TRY(km_sort_members(km, d_active));
     UpdateParams p = make_update_params(km, d_active, nullptr);
-    dim3 grid((unsigned)((km->m + 127) / 128), (unsigned)km->k, (unsigned)km->nb);
-    accumulate_kernel<<<grid, 128, 0, ctx->stream>>>(p);
+    const AccGrid ag = acc_grid(km);
+    accumulate_kernel<<<ag.grid, 128, 0, ctx->stream>>>(p, ag.mpad);
     ctx->launches++;
     FDB_CHECK_LAUNCH();
     return km_norms_and_gradient(km, d_active, loop_mode, eps, max_rounds);
@@ -775,8 +820,8 @@ int km_update_partial(fdb_km *km) {
     FDB_TRY(km->partial.ensure(km->nb * km->k * km->m + km->nb * km->k));
     FDB_TRY(km_sort_members(km, nullptr));
     UpdateParams p = make_update_params(km, nullptr, km->partial.p);
-    dim3 grid((unsigned)((km->m + 127) / 128), (unsigned)km->k, (unsigned)km->nb);
-    accumulate_kernel<<<grid, 128, 0, ctx->stream>>>(p);
+    const AccGrid ag = acc_grid(km);
+    accumulate_kernel<<<ag.grid, 128, 0, ctx->stream>>>(p, ag.mpad);
     ctx->launches++;
     FDB_CHECK_LAUNCH();
     return FDB_OK;
