@@ -137,18 +137,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 
 // ---- operand preparation -----------------------------------------------------------------
 // rows: f32 -> two bf16 pieces (full row width, every division at once) + |x|^2 per (problem,row)
+// (the pieces of problem b start at column out_off + b * out_m of rows out_ld wide: the layout of the
+//  rows themselves, or a compact one padded with zeros when m is not a multiple of 16)
 __global__ void __launch_bounds__(256) split_rows_kernel(const float *x, size_t n, size_t ldx,
                                                          size_t col_off, size_t m, size_t nb,
                                                          const float *mu, __nv_bfloat16 *x1,
-                                                         __nv_bfloat16 *x2, float *xn2) {
+                                                         __nv_bfloat16 *x2, float *xn2, size_t out_ld,
+                                                         size_t out_off, size_t out_m) {
     const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= n * nb) return;
     const size_t row = warp / nb, b = warp - row * nb;
     const float *xr = x + row * ldx + col_off + b * m;
     const float *mr = mu + col_off + b * m;
-    __nv_bfloat16 *o1 = x1 + row * ldx + col_off + b * m;
-    __nv_bfloat16 *o2 = x2 + row * ldx + col_off + b * m;
+    __nv_bfloat16 *o1 = x1 + row * out_ld + out_off + b * out_m;
+    __nv_bfloat16 *o2 = x2 + row * out_ld + out_off + b * out_m;
     double acc = 0.0;
     for (size_t e = lane; e < m; e += 32) {
         const float v = __fsub_rn(xr[e], mr[e]);
@@ -187,7 +190,7 @@ __global__ void col_mean_kernel(const double *partial, size_t n, size_t c0, size
 // centroids: f32 -> two bf16 pieces [nb*k][m], h_j = |c_j|^2/2, cmax_b = max_j |c_j| (rounded up)
 __global__ void __launch_bounds__(128) prep_centroids_kernel(const float *c, size_t k, size_t m, size_t np,
                                                              const float *mu, size_t col_off, size_t mu_stride,
-                                                             size_t ktotal,
+                                                             size_t ktotal, size_t out_m,
                                                              __nv_bfloat16 *c1, __nv_bfloat16 *c2,
                                                              float *h, unsigned *cmax2_bits,
                                                              const int *active) {
@@ -203,8 +206,8 @@ __global__ void __launch_bounds__(128) prep_centroids_kernel(const float *c, siz
     for (size_t e = threadIdx.x; e < m; e += blockDim.x) {
         const float v = __fsub_rn(cr[e], mr[e]);
         const __nv_bfloat16 hh = __float2bfloat16_rn(v);
-        c1[(b * k + j) * m + e] = hh;
-        c2[(b * k + j) * m + e] = __float2bfloat16_rn(__fsub_rn(v, __bfloat162float(hh)));
+        c1[(b * k + j) * out_m + e] = hh;
+        c2[(b * k + j) * out_m + e] = __float2bfloat16_rn(__fsub_rn(v, __bfloat162float(hh)));
         acc += (double)v * (double)v;
     }
     __shared__ double red[128];
@@ -667,6 +670,78 @@ __global__ void __launch_bounds__(256) recheck_kernel(const float *x, size_t n, 
     }
 }
 
+// any m / alignment: one warp per row, one lane per candidate, the reference's summation order
+// (16 accumulators, the first m % 16 elements seed them; fewer than 16 elements: one running sum)
+__device__ float sqdist_generic(const float *__restrict__ x, const float *__restrict__ c, size_t m) {
+    if (m < 16) {
+        float a = 0.0f;
+        for (size_t e = 0; e < m; ++e) a = sq_acc(a, x[e], c[e]);
+        return a;
+    }
+    float acc[16];
+#pragma unroll
+    for (int l = 0; l < 16; ++l) acc[l] = 0.0f;
+    const size_t r = m & 15;
+#pragma unroll
+    for (int l = 0; l < 16; ++l)
+        if ((size_t)l < r) {
+            const float d = __fsub_rn(x[l], c[l]);
+            acc[l] = __fmul_rn(d, d);
+        }
+    for (size_t base = r; base < m; base += 16) {
+#pragma unroll
+        for (int l = 0; l < 16; ++l) acc[l] = sq_acc(acc[l], x[base + l], c[base + l]);
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int l = 0; l < 16; ++l) s = __fadd_rn(s, acc[l]);
+    return s;
+}
+
+__global__ void __launch_bounds__(256) recheck_generic_kernel(const float *x, size_t n, size_t ldx, size_t col_off,
+                                                              size_t m, size_t k, const float *cent,
+                                                              const unsigned *work_count, unsigned work_cap,
+                                                              const uint32_t *work_rows, const uint16_t *work_cand,
+                                                              const uint8_t *work_cnt, uint32_t *indices,
+                                                              unsigned *flags) {
+    const unsigned total = min(*work_count, work_cap);
+    const int lane = threadIdx.x & 31;
+    for (unsigned w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < total;
+         w += (gridDim.x * blockDim.x) >> 5) {
+        const uint32_t br = work_rows[w];
+        const size_t b = br / n, row = br - b * n;
+        const unsigned cnt = work_cnt[w];
+        const bool all = cnt > CAP;
+        const unsigned ncand = all ? (unsigned)k : cnt;
+        const float *xr = x + row * ldx + col_off + b * m;
+        const float *cb = cent + b * k * m;
+        float bd = __int_as_float(0x7f800000);
+        uint32_t bi = 0xFFFFFFFFu;
+        for (unsigned ci = lane; ci < ncand; ci += 32) {
+            const uint32_t j = all ? ci : (uint32_t)work_cand[(size_t)w * CAP + ci];
+            const float d = sqdist_generic(xr, cb + (size_t)j * m, m);
+            if (d < bd || (d == bd && j < bi)) {
+                bd = d;
+                bi = j;
+            }
+        }
+        // lexicographic (distance, index) minimum == first strict minimum in index order
+#pragma unroll
+        for (int off = 1; off <= 16; off <<= 1) {
+            const float od = __shfl_xor_sync(0xffffffffu, bd, off);
+            const uint32_t oi = __shfl_xor_sync(0xffffffffu, bi, off);
+            if (oi != 0xFFFFFFFFu && (bi == 0xFFFFFFFFu || od < bd || (od == bd && oi < bi))) {
+                bd = od;
+                bi = oi;
+            }
+        }
+        if (lane == 0) {
+            if (bi == 0xFFFFFFFFu) atomicOr(flags, FLAG_NO_ARGMIN);
+            else indices[b * n + row] = bi;
+        }
+    }
+}
+
 // ---- k > 256: column tiles of 256 centroids ------------------------------------------------------
 // tc_assign_kernel (mode 2) leaves the three largest scores of every (row, tile); one thread per row
 // puts them together: the global maximum, the band, and the columns that can be inside it.  A tile
@@ -779,9 +854,9 @@ struct TcState {
 bool tc_eligible(const fdb_km *km) {
     if (getenv("FDB_DISABLE_TC")) return false;
     const size_t ld = km->vs->dim;
-    return (km->k <= 256 || (km->nb == 1 && km->k <= 65535)) && km->m % 16 == 0 && ld % 8 == 0 && km->col_off % 8 == 0 &&
-           km->n >= 1 && km->n < (1ull << 31) && km->nb * km->n < (1ull << 32) &&
-           ((uintptr_t)km->vs->d % 16 == 0);
+    (void)ld;
+    return (km->k <= 256 || (km->nb == 1 && km->k <= 65535)) && km->m >= 1 &&
+           km->n >= 1 && km->n < (1ull << 31) && km->nb * km->n < (1ull << 32);
 }
 
 void tc_free(fdb_km *km) {
@@ -805,14 +880,19 @@ int tc_reassign(fdb_km *km, const int *d_active) {
     const bool tiled = k > 256;
     const size_t pk = tiled ? 256 : k, pnb = tiled ? (k + 255) / 256 : nb;
     const int np = tiled ? 256 : (int)((k + 63) / 64 * 64);
-    const int bk = m % BK == 0 ? BK : 16;
+    // Piece layout: the rows' own layout when every problem's columns start on a 16-byte boundary and
+    // m is a multiple of 16; else a compact copy, every problem padded with zeros to mp columns
+    const bool own_layout = m % 16 == 0 && ld % 8 == 0 && km->col_off % 8 == 0;
+    const size_t mp = (m + 15) / 16 * 16;
+    const size_t ldp = own_layout ? ld : nb * mp, coff = own_layout ? km->col_off : 0;
+    const int bk = mp % BK == 0 ? BK : 16;
     cudaStream_t st = ctx->stream;
     if (tc->rows_version != km->vs->version || tc->np != np || tc->pnb != pnb) {
-        FDB_TRY(tc->x1.ensure(n * ld));
-        FDB_TRY(tc->x2.ensure(n * ld));
+        FDB_TRY(tc->x1.ensure(n * ldp));
+        FDB_TRY(tc->x2.ensure(n * ldp));
         FDB_TRY(tc->xn2.ensure(nb * n));
-        FDB_TRY(tc->c1.ensure(pnb * pk * m + 256 * m));  // slack: the last problem's box reads past its rows
-        FDB_TRY(tc->c2.ensure(pnb * pk * m + 256 * m));
+        FDB_TRY(tc->c1.ensure(pnb * pk * mp + 256 * mp));  // slack: the last problem's box reads past its rows
+        FDB_TRY(tc->c2.ensure(pnb * pk * mp + 256 * mp));
         FDB_TRY(tc->h.ensure(pnb * np));
         FDB_TRY(tc->cmax2.ensure(pnb));
         if (tiled) {
@@ -824,8 +904,12 @@ int tc_reassign(fdb_km *km, const int *d_active) {
         FDB_TRY(tc->work_rows.ensure(nb * n));
         FDB_TRY(tc->work_cand.ensure(nb * n * CAP));
         FDB_TRY(tc->work_cnt.ensure(nb * n));
-        FDB_CUDA(cudaMemsetAsync(tc->c1.p, 0, (pnb * pk * m + 256 * m) * 2, st));
-        FDB_CUDA(cudaMemsetAsync(tc->c2.p, 0, (pnb * pk * m + 256 * m) * 2, st));
+        FDB_CUDA(cudaMemsetAsync(tc->c1.p, 0, (pnb * pk * mp + 256 * mp) * 2, st));
+        FDB_CUDA(cudaMemsetAsync(tc->c2.p, 0, (pnb * pk * mp + 256 * mp) * 2, st));
+        if (!own_layout) {
+            FDB_CUDA(cudaMemsetAsync(tc->x1.p, 0, n * ldp * 2, st));
+            FDB_CUDA(cudaMemsetAsync(tc->x2.p, 0, n * ldp * 2, st));
+        }
         // mu = column means of this problem's columns (any mu is valid; the mean minimises |x'|)
         const size_t ncols = nb * m;
         FDB_TRY(tc->mu.ensure(ld));
@@ -840,13 +924,14 @@ int tc_reassign(fdb_km *km, const int *d_active) {
         }
         const size_t warps = n * nb;
         split_rows_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(
-            km->vs->d, n, ld, km->col_off, m, nb, tc->mu.p, tc->x1.p, tc->x2.p, tc->xn2.p);
+            km->vs->d, n, ld, km->col_off, m, nb, tc->mu.p, tc->x1.p, tc->x2.p, tc->xn2.p, ldp, coff,
+            own_layout ? m : mp);
         ctx->launches++;
         FDB_CHECK_LAUNCH();
-        FDB_TRY(make_map(&tc->map_x1, tc->x1.p, ld, n, BM, bk));
-        FDB_TRY(make_map(&tc->map_x2, tc->x2.p, ld, n, BM, bk));
-        FDB_TRY(make_map(&tc->map_c1, tc->c1.p, m, pnb * pk + 256, (uint32_t)np, bk));
-        FDB_TRY(make_map(&tc->map_c2, tc->c2.p, m, pnb * pk + 256, (uint32_t)np, bk));
+        FDB_TRY(make_map(&tc->map_x1, tc->x1.p, ldp, n, BM, bk));
+        FDB_TRY(make_map(&tc->map_x2, tc->x2.p, ldp, n, BM, bk));
+        FDB_TRY(make_map(&tc->map_c1, tc->c1.p, mp, pnb * pk + 256, (uint32_t)np, bk));
+        FDB_TRY(make_map(&tc->map_c2, tc->c2.p, mp, pnb * pk + 256, (uint32_t)np, bk));
         tc->rows_version = km->vs->version;
         tc->np = np;
         tc->pnb = pnb;
@@ -859,18 +944,18 @@ int tc_reassign(fdb_km *km, const int *d_active) {
         // (tiled: every tile is centred by the same columns, rows past k are padding; the active flag of
         // the one problem is checked by the kernels that follow)
         prep_centroids_kernel<<<grid, 128, 0, st>>>(km->centroids.p, pk, m, (size_t)np, tc->mu.p, km->col_off,
-                                                    tiled ? 0 : m, nb * k, tc->c1.p, tc->c2.p, tc->h.p,
+                                                    tiled ? 0 : m, nb * k, mp, tc->c1.p, tc->c2.p, tc->h.p,
                                                     tc->cmax2.p, tiled ? nullptr : d_active);
         ctx->launches++;
         FDB_CHECK_LAUNCH();
     }
     TcParams p;
     p.n = n;
-    p.m = m;
+    p.m = mp;                   // K extent of the GEMM (zero padded); the bounds below use the true m
     p.nb = pnb;
     p.k = pk;
-    p.col_off = km->col_off;
-    p.xcol_stride = tiled ? 0 : m;
+    p.col_off = coff;
+    p.xcol_stride = tiled ? 0 : (own_layout ? m : mp);
     p.crow_stride = pk;
     p.mode = tiled ? 2 : 0;
     p.tile_v = tc->tile_v.p;
@@ -911,10 +996,16 @@ int tc_reassign(fdb_km *km, const int *d_active) {
         ctx->launches++;
         FDB_CHECK_LAUNCH();
     }
-    recheck_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(km->vs->d, n, ld, km->col_off, m, k, km->centroids.p,
-                                                      tc->work_count.p, p.work_cap, tc->work_rows.p,
-                                                      tc->work_cand.p, tc->work_cnt.p, km->indices.p,
-                                                      ctx->d_flags);
+    if (own_layout && (uintptr_t)km->vs->d % 16 == 0 && ld % 4 == 0)
+        recheck_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(km->vs->d, n, ld, km->col_off, m, k, km->centroids.p,
+                                                          tc->work_count.p, p.work_cap, tc->work_rows.p,
+                                                          tc->work_cand.p, tc->work_cnt.p, km->indices.p,
+                                                          ctx->d_flags);
+    else
+        recheck_generic_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(km->vs->d, n, ld, km->col_off, m, k,
+                                                                  km->centroids.p, tc->work_count.p, p.work_cap,
+                                                                  tc->work_rows.p, tc->work_cand.p, tc->work_cnt.p,
+                                                                  km->indices.p, ctx->d_flags);
     ctx->launches++;
     FDB_CHECK_LAUNCH();
     if (getenv("FDB_TC_STATS")) {
@@ -955,7 +1046,7 @@ int tc_prepare_centroids(fdb_ctx *ctx, const float *c, size_t nb, size_t k, size
     FDB_CUDA(cudaMemsetAsync(out->c2.p, 0, rows * m * 2, st));
     FDB_CUDA(cudaMemsetAsync(out->cmax2.p, 0, nb * sizeof(unsigned), st));
     dim3 grid((unsigned)np, (unsigned)nb);
-    prep_centroids_kernel<<<grid, 128, 0, st>>>(c, k, m, (size_t)np, mu, 0, mu_stride, ktotal, out->c1.p,
+    prep_centroids_kernel<<<grid, 128, 0, st>>>(c, k, m, (size_t)np, mu, 0, mu_stride, ktotal, m, out->c1.p,
                                                 out->c2.p, out->h.p, out->cmax2.p, nullptr);
     ctx->launches++;
     FDB_CHECK_LAUNCH();
@@ -973,7 +1064,7 @@ int tc_prepare_rows(fdb_ctx *ctx, const float *x, size_t n, size_t ld, size_t m,
     FDB_TRY(out->xn2.ensure(nb * n));
     const size_t warps = n * nb;
     split_rows_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(x, n, ld, 0, m, nb, mu, out->x1.p,
-                                                                          out->x2.p, out->xn2.p);
+                                                                          out->x2.p, out->xn2.p, ld, 0, m);
     ctx->launches++;
     FDB_CHECK_LAUNCH();
     if (grown || out->n != n || out->ld != ld) {

@@ -669,7 +669,8 @@ def _tc_case(eng, ctx, oracle, x, cent, nb=1, dim=None, expect_tc=True):
 
 @pytest.mark.parametrize("n,m,k", [(4000, 128, 256), (3000, 1536, 100), (129, 64, 1), (1000, 192, 64),
                                    (5000, 64, 200), (127, 128, 17),
-                                   (5000, 16, 256), (3000, 48, 100), (2000, 32, 64), (900, 80, 300)])  # K chunks of 16
+                                   (5000, 16, 256), (3000, 48, 100), (2000, 32, 64), (900, 80, 300),  # K chunks of 16
+                                   (6000, 8, 256), (2000, 20, 7), (1500, 100, 33), (700, 5, 3)])      # zero-padded pieces
 def test_tc_reassign_uniform(eng, ctx, oracle, n, m, k):
     _tc_case(eng, ctx, oracle, data(oracle, n, m), data(oracle, k, m, SEED + 7))
 
@@ -683,6 +684,17 @@ def test_tc_reassign_batched_divisions(eng, ctx, oracle):
 
 def test_tc_reassign_batched_small_divisions(eng, ctx, oracle):
     n, N, D, k = 4000, 768, 48, 256          # BASELINE.json configs[2]: s = 16
+    x = data(oracle, n, N) - np.float32(0.5)
+    cent = (data(oracle, D * k, N // D, SEED + 9) - np.float32(0.5)).reshape(D, k, N // D)
+    _tc_case(eng, ctx, oracle, x, cent, nb=D, dim=N // D)
+
+
+def test_tc_reassign_batched_padded_divisions(eng, ctx, oracle):
+    n, N, D, k = 5000, 128, 16, 256          # BASELINE.json configs[3]: s = 8, padded to 16
+    x = data(oracle, n, N) - np.float32(0.5)
+    cent = (data(oracle, D * k, N // D, SEED + 9) - np.float32(0.5)).reshape(D, k, N // D)
+    _tc_case(eng, ctx, oracle, x, cent, nb=D, dim=N // D)
+    n, N, D, k = 3000, 60, 3, 40             # s = 20, rows not 16-byte aligned per problem
     x = data(oracle, n, N) - np.float32(0.5)
     cent = (data(oracle, D * k, N // D, SEED + 9) - np.float32(0.5)).reshape(D, k, N // D)
     _tc_case(eng, ctx, oracle, x, cent, nb=D, dim=N // D)
