@@ -307,6 +307,153 @@ __global__ void __launch_bounds__(PICK_THREADS) pick_fast_kernel(const float *w,
     }
 }
 
+// Large n: the same sampler in two levels, so that the pass over the weights uses the whole GPU.
+// weight_blocks_kernel: sum (double, fixed order) and last positive index of every block of
+// PICK_BLOCK weights.  pick_blocks_kernel (one CTA per problem): scan of the block sums -> total and
+// the block in which the running sum first exceeds the sample -> the element inside that block.
+constexpr int PICK_BLOCK = 4096;
+__global__ void __launch_bounds__(256) weight_blocks_kernel(const float *w, size_t n, size_t nblk, double *bsum,
+                                                            unsigned *blast) {
+    const size_t b = blockIdx.y, blk = blockIdx.x;
+    const float *x = w + b * n;
+    const size_t lo = blk * PICK_BLOCK, hi = minz(lo + PICK_BLOCK, n);
+    double s = 0.0;
+    unsigned last = 0xFFFFFFFFu;
+    for (size_t i = lo + threadIdx.x; i < hi; i += 256) {
+        const float v = x[i];
+        s += (double)v;
+        if (v > 0.0f) last = (unsigned)i;
+    }
+    __shared__ double red[256];
+    __shared__ int lastmax;
+    red[threadIdx.x] = s;
+    if (threadIdx.x == 0) lastmax = -1;
+    __syncthreads();
+    if (last != 0xFFFFFFFFu) atomicMax(&lastmax, (int)last);  // indices < 2^31
+    for (int off = 128; off >= 1; off >>= 1) {
+        if ((int)threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        bsum[b * nblk + blk] = red[0];
+        blast[b * nblk + blk] = lastmax < 0 ? 0xFFFFFFFFu : (unsigned)lastmax;
+    }
+}
+
+__global__ void __launch_bounds__(PICK_THREADS) pick_blocks_kernel(const float *w, size_t n, size_t nblk,
+                                                                   const double *bsum, const unsigned *blast,
+                                                                   const float *u01, size_t u_stride, size_t u_off,
+                                                                   uint32_t *ci, float *total_out, unsigned *flags,
+                                                                   int pick, int absolute) {
+    const size_t b = blockIdx.x;
+    const float *x = w + b * n;
+    const double *bs = bsum + b * nblk;
+    const unsigned *bl = blast + b * nblk;
+    const int t = threadIdx.x;
+    const size_t seg = (nblk + PICK_THREADS - 1) / PICK_THREADS;
+    const size_t lo = minz((size_t)t * seg, nblk), hi = minz(lo + seg, nblk);
+    double s = 0.0;
+    unsigned ln = 0xFFFFFFFFu;
+    for (size_t i = lo; i < hi; ++i) {
+        s += bs[i];
+        if (bl[i] != 0xFFFFFFFFu) ln = bl[i];
+    }
+    __shared__ double part[PICK_THREADS];
+    __shared__ int first_t;
+    __shared__ unsigned last_nz, pick_s, blk_s;
+    __shared__ double cum_s;
+    part[t] = s;
+    if (t == 0) {
+        first_t = PICK_THREADS;
+        last_nz = 0xFFFFFFFFu;
+        pick_s = 0xFFFFFFFFu;
+        blk_s = 0xFFFFFFFFu;
+        cum_s = 0.0;
+    }
+    __syncthreads();
+    for (int off = 1; off < PICK_THREADS; off <<= 1) {   // inclusive Hillis-Steele scan, fixed order
+        double v = part[t];
+        if (t >= off) v += part[t - off];
+        __syncthreads();
+        part[t] = v;
+        __syncthreads();
+    }
+    const double excl = part[t] - s;
+    const double total = part[PICK_THREADS - 1];
+    const float total_f = (float)total;
+    if (t == 0) {
+        total_out[b] = total_f;
+        if (!(total_f > 0.0f)) atomicOr(flags, FLAG_WEIGHTS);
+    }
+    if (!pick) return;
+    const float sample = absolute ? u01[b * u_stride + u_off]
+                                  : __fadd_rn(__fmul_rn(u01[b * u_stride + u_off], uniform_scale(total_f)), 0.0f);
+    const double sd = (double)sample;
+    if (hi > lo && excl + s > sd) atomicMin(&first_t, t);
+    if (ln != 0xFFFFFFFFu) atomicMax((int *)&last_nz, (int)ln);
+    __syncthreads();
+    if (t == first_t) {   // the block in which the running sum first exceeds the sample
+        double cum = excl;
+        for (size_t i = lo; i < hi; ++i) {
+            if (cum + bs[i] > sd) {
+                blk_s = (unsigned)i;
+                cum_s = cum;
+                break;
+            }
+            cum += bs[i];
+        }
+    }
+    __syncthreads();
+    if (blk_s != 0xFFFFFFFFu) {
+        // inside the block: 4 consecutive weights per thread, scan, then the sequential rule
+        const size_t e0 = (size_t)blk_s * PICK_BLOCK + (size_t)t * (PICK_BLOCK / PICK_THREADS);
+        const size_t e1 = minz(e0 + PICK_BLOCK / PICK_THREADS, n);
+        double ls = 0.0;
+        for (size_t i = e0; i < e1; ++i) ls += (double)x[i];
+        __syncthreads();
+        part[t] = ls;
+        if (t == 0) first_t = PICK_THREADS;
+        __syncthreads();
+        for (int off = 1; off < PICK_THREADS; off <<= 1) {
+            double v = part[t];
+            if (t >= off) v += part[t - off];
+            __syncthreads();
+            part[t] = v;
+            __syncthreads();
+        }
+        const double ex2 = cum_s + part[t] - ls;
+        if (e1 > e0 && ex2 + ls > sd) atomicMin(&first_t, t);
+        __syncthreads();
+        if (t == first_t) {
+            double cum = ex2;
+            uint32_t pickd = 0xFFFFFFFFu;
+            for (size_t i = e0; i < e1; ++i) {
+                const float v = x[i];
+                if (v > 0.0f) {
+                    pickd = (uint32_t)i;
+                    cum += (double)v;
+                    if (cum > sd) break;
+                }
+            }
+            pick_s = pickd;
+        }
+        __syncthreads();
+        // (the element-wise sums may stay a hair below the block-wise ones: then the block's last
+        //  positive weight is the one that crosses)
+        if (t == 0 && pick_s == 0xFFFFFFFFu) pick_s = bl[blk_s];
+    }
+    __syncthreads();
+    if (t == 0) {
+        unsigned r = pick_s;
+        if (r == 0xFFFFFFFFu) r = last_nz;  // the scan never exceeded the sample: last positive weight
+        if (r == 0xFFFFFFFFu) {
+            atomicOr(flags, FLAG_WEIGHTS);
+            r = 0;
+        }
+        ci[b] = r;
+    }
+}
+
 // ---- stable grouping of rows by cluster (LSD radix, 8-bit digits) -------------------
 constexpr int SORT_CHUNK = 1024;
 
@@ -783,26 +930,43 @@ int km_seed_round(fdb_km *km, uint32_t round, int exact, const float *d_centre) 
     return FDB_OK;
 }
 
+// the parallel sampler / total: one CTA per problem for small n, two levels for large n
+static int launch_pick_fast(fdb_km *km, const float *d_u01, size_t u_stride, size_t u_off, int pick, int absolute) {
+    fdb_ctx *ctx = km->ctx;
+    if (km->n < 65536) {
+        pick_fast_kernel<<<(unsigned)km->nb, PICK_THREADS, 0, ctx->stream>>>(
+            km->weights.p, km->n, d_u01, u_stride, u_off, km->ci.p, km->total.p, ctx->d_flags, pick, absolute);
+        ctx->launches++;
+        return FDB_OK;
+    }
+    const size_t nblk = (km->n + PICK_BLOCK - 1) / PICK_BLOCK;
+    FDB_TRY(km->pick_bsum.ensure(km->nb * nblk));
+    FDB_TRY(km->pick_blast.ensure(km->nb * nblk));
+    dim3 grid((unsigned)nblk, (unsigned)km->nb);
+    weight_blocks_kernel<<<grid, 256, 0, ctx->stream>>>(km->weights.p, km->n, nblk, km->pick_bsum.p, km->pick_blast.p);
+    pick_blocks_kernel<<<(unsigned)km->nb, PICK_THREADS, 0, ctx->stream>>>(
+        km->weights.p, km->n, nblk, km->pick_bsum.p, km->pick_blast.p, d_u01, u_stride, u_off, km->ci.p, km->total.p,
+        ctx->d_flags, pick, absolute);
+    ctx->launches += 2;
+    return FDB_OK;
+}
+
 int km_seed_pick(fdb_km *km, const float *d_u01, size_t u_stride, size_t u_off, int exact,
                  int absolute) {
     fdb_ctx *ctx = km->ctx;
     if (exact && !absolute) {
         pick_exact_kernel<<<(unsigned)km->nb, 1, 0, ctx->stream>>>(
             km->weights.p, km->n, km->total.p, d_u01, u_stride, u_off, km->ci.p, ctx->d_flags);
+        ctx->launches++;
     } else {
-        pick_fast_kernel<<<(unsigned)km->nb, PICK_THREADS, 0, ctx->stream>>>(
-            km->weights.p, km->n, d_u01, u_stride, u_off, km->ci.p, km->total.p, ctx->d_flags, 1, absolute);
+        FDB_TRY(launch_pick_fast(km, d_u01, u_stride, u_off, 1, absolute));
     }
-    ctx->launches++;
     FDB_CHECK_LAUNCH();
     return FDB_OK;
 }
 
 int km_total_fast(fdb_km *km) {
-    fdb_ctx *ctx = km->ctx;
-    pick_fast_kernel<<<(unsigned)km->nb, PICK_THREADS, 0, ctx->stream>>>(
-        km->weights.p, km->n, nullptr, 0, 0, km->ci.p, km->total.p, ctx->d_flags, 0, 0);
-    ctx->launches++;
+    FDB_TRY(launch_pick_fast(km, nullptr, 0, 0, 0, 0));
     FDB_CHECK_LAUNCH();
     return FDB_OK;
 }

@@ -24,6 +24,8 @@ struct fdb_km {
     fdb::DevBuf<float> u01;                         // seeding draws staged on the device
     fdb::DevBuf<float> centre;                      // [nb][m] externally supplied centres (sharded rows)
     fdb::DevBuf<uint32_t> picked;                   // [k][nb] picks of seed_run
+    fdb::DevBuf<double> pick_bsum;                  // [nb][blocks] block sums of the weights (two-level sampler)
+    fdb::DevBuf<unsigned> pick_blast;               // [nb][blocks] last positive weight of every block
     fdb::TcState *tc = nullptr;                     // tensor-core assignment state (tc_assign.cu)
     int last_assign_tc = 0;                         // 1 if the last reassignment ran on the tensor pipe
 };

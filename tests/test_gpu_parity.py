@@ -165,6 +165,34 @@ def test_seeding_exact_sampler_follows_the_same_draws(eng, ctx, oracle, n, m, k)
     vs.close()
 
 
+@pytest.mark.parametrize("n,m,nb", [(70000, 16, 1), (150001, 8, 3), (3000, 32, 2)])
+def test_parallel_sampler_picks_where_the_running_sum_crosses(eng, ctx, oracle, n, m, nb):
+    """The default (parallel, double precision) sampler, one level for small n and two levels for large
+    n: the pick is the first positive weight at which the running sum exceeds the sample
+    (src/distribution.rs:104-121), the total is the sum of the weights."""
+    x = data(oracle, n, m * nb)
+    vs = eng.VectorSet.upload(ctx, x)
+    km = eng.KMeans(vs, 4, dim=m, nb=nb)
+    km.seed_first(np.arange(nb) * 7 + 3)
+    w = km.weights()
+    for u in (0.0, 0.123456, 0.5, 0.999, 0.99999994):
+        got = km.seed_pick(np.full(nb, u, np.float32))
+        tot = km.seed_total()
+        for b in range(nb):
+            cum = np.cumsum(w[b].astype(np.float64))
+            assert abs(float(tot[b]) - cum[-1]) <= 1e-6 * cum[-1]
+            sample = float(np.float32(np.float32(u) * tot[b]))     # scale == total except at the very top
+            i = int(got[b])
+            assert w[b, i] > 0
+            before = cum[i] - float(w[b, i])
+            # the running sum crosses the sample at i (tolerance: association of the double sums,
+            # and the one-ulp smaller scale the reference uses when u * total would round up to total)
+            tol = 1e-9 * cum[-1] + 2e-7 * float(tot[b])
+            assert before <= sample + tol and cum[i] >= sample - tol, (u, b, i, before, sample, cum[i])
+    km.close()
+    vs.close()
+
+
 def test_seeding_special_cases(eng, ctx, oracle):
     x = data(oracle, 50, 24)
     vs = eng.VectorSet.upload(ctx, x)
