@@ -65,6 +65,14 @@ SIGNATURES = {
     "fdb_kmeans_seed_chosen": (C.c_int, [VP, U32P]),
     "fdb_kmeans_seed_round_ext": (C.c_int, [VP, SZ, F32P, U32P]),
     "fdb_kmeans_seed_pick_value": (C.c_int, [VP, F32P, U32P]),
+    "fdb_ctx_stream": (VP, [VP]),
+    "fdb_kmeans_seed_sharded_begin": (C.c_int, [VP, C.POINTER(VP), C.POINTER(VP), C.POINTER(VP), C.POINTER(VP),
+                                                C.POINTER(VP)]),
+    "fdb_kmeans_seed_sharded_first": (C.c_int, [VP, U32P]),
+    "fdb_kmeans_seed_sharded_total": (C.c_int, [VP]),
+    "fdb_kmeans_seed_sharded_pick": (C.c_int, [VP, VP, C.c_int, C.c_int]),
+    "fdb_kmeans_seed_sharded_round": (C.c_int, [VP, SZ, VP, VP, C.c_int, C.c_int, SZ]),
+    "fdb_kmeans_seed_sharded_finish": (C.c_int, [VP, U32P]),
     "fdb_kmeans_set_state": (C.c_int, [VP, F32P, U32P]),
     "fdb_kmeans_update": (C.c_int, [VP, U8P, F32P]),
     "fdb_kmeans_reassign": (C.c_int, [VP, U8P]),

@@ -460,6 +460,90 @@ int fdb_kmeans_seed_round_ext(fdb_km *km, size_t i, const float *centres, const 
     return map_flags(f & ~FLAG_WEIGHTS);  // a shard's own total may legitimately be zero
 }
 
+// ---- sharded k-means++ without host round trips (rows sharded over `world` ranks) -------------
+// One round = local totals -> all-gather -> split of the global draw + local pick -> all-gather of
+// the picks and of the picked rows -> D^2 pass.  The three stage functions below only enqueue work
+// on the context's stream; the caller runs the all-gathers (NCCL through torch.distributed) on the
+// same stream in between.
+namespace fdb_shard {
+using namespace fdb;
+
+// WeightedIndex::sample over the concatenated shards (src/distribution.rs:104-121): the draw lands in
+// the shard whose cumulative range of totals contains it.  values[b] = the part of the draw inside
+// this shard (absolute sample for the local pick), or -1 when another shard owns it.
+__global__ void shard_split_kernel(const float *all_totals, int world, int rank, size_t nb, const float *u01,
+                                   float *values, int *owner) {
+    const size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    double tsum = 0.0;
+    for (int r = 0; r < world; ++r) tsum += (double)all_totals[(size_t)r * nb + b];
+    const float total = (float)tsum;
+    const double sample = (double)__fmul_rn(u01[b], total);
+    double cum = 0.0;
+    int last = -1, own = -1;
+    float val = 0.0f;
+    for (int r = 0; r < world; ++r) {
+        const double t = (double)all_totals[(size_t)r * nb + b];
+        if (t > 0.0) {
+            last = r;
+            if (cum + t > sample) {
+                own = r;
+                val = (float)(sample - cum);
+                break;
+            }
+            cum += t;
+        }
+    }
+    if (own < 0 && last >= 0) {   // rounding pushed the draw past the end: the last shard with weight
+        own = last;
+        val = all_totals[(size_t)last * nb + b];
+    }
+    owner[b] = own;               // -1: the total weight is zero (WeightedIndex fails in the reference)
+    values[b] = own == rank ? val : -1.0f;
+}
+
+// after the local pick: ranks that do not own the draw publish NONE, the owner its row
+__global__ void shard_publish_kernel(const int *owner, int rank, size_t nb, size_t m, const float *x, size_t ldx,
+                                     size_t col_off, uint32_t *ci, float *centre_send) {
+    const size_t b = blockIdx.x;
+    const bool mine = owner[b] == rank;
+    if (!mine && threadIdx.x == 0) ci[b] = 0xFFFFFFFFu;
+    __syncthreads();
+    const uint32_t c = mine ? ci[b] : 0u;
+    for (size_t e = threadIdx.x; e < m; e += blockDim.x)
+        centre_send[b * m + e] = mine ? x[(size_t)c * ldx + col_off + b * m + e] : 0.0f;
+}
+
+// after the all-gathers: the owner's row becomes the round's centre on every rank
+__global__ void shard_adopt_kernel(const uint32_t *all_picks, const float *all_centres, int world, int rank,
+                                   size_t nb, size_t m, size_t n_global, uint32_t *ci, float *centre,
+                                   uint32_t *picked_global, unsigned *flags) {
+    const size_t b = blockIdx.x;
+    int own = -1;
+    for (int r = 0; r < world; ++r)
+        if (all_picks[(size_t)r * nb + b] != 0xFFFFFFFFu) {
+            own = r;
+            break;
+        }
+    if (own < 0) {
+        if (threadIdx.x == 0) {
+            atomicOr(flags, FLAG_WEIGHTS);
+            ci[b] = 0xFFFFFFFFu;
+            picked_global[b] = 0;
+        }
+        return;
+    }
+    const uint32_t li = all_picks[(size_t)own * nb + b];
+    if (threadIdx.x == 0) {
+        ci[b] = own == rank ? li : 0xFFFFFFFFu;
+        picked_global[b] = (uint32_t)(n_global * (size_t)own / (size_t)world) + li;   // shard_rows().lo + local
+    }
+    for (size_t e = threadIdx.x; e < m; e += blockDim.x)
+        centre[b * m + e] = all_centres[((size_t)own * nb + b) * m + e];
+}
+
+}  // namespace fdb_shard
+
 static int seed_loop(fdb_km *km, const uint32_t *first, const float *u01, const uint32_t *chosen,
                      int exact, uint32_t *picked) {
     const size_t nb = km->nb, k = km->k;
@@ -515,6 +599,101 @@ static int seed_loop(fdb_km *km, const uint32_t *first, const float *u01, const 
     FDB_TRY(km->ctx->check_flags(&f));
     if (k == 1) f &= ~FLAG_WEIGHTS;
     return map_flags(f);
+}
+
+void *fdb_ctx_stream(fdb_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+int fdb_kmeans_seed_sharded_begin(fdb_km *km, float **d_totals, uint32_t **d_pick, float **d_centre_send,
+                                  float **d_u01, uint32_t **d_picked_global) {
+    ARG(km && d_totals && d_pick && d_centre_send && d_u01 && d_picked_global, "null argument");
+    FDB_TRY(km->ctx->use());
+    FDB_TRY(km_seed_alloc(km));
+    FDB_CUDA(cudaMemsetAsync(km->chosen.p, 0, km->nb * km->n, km->ctx->stream));
+    FDB_TRY(km->centre.ensure(km->nb * km->m));
+    FDB_TRY(km->centre_send.ensure(km->nb * km->m));
+    FDB_TRY(km->u01.ensure(km->nb));
+    FDB_TRY(km->shard_values.ensure(km->nb));
+    FDB_TRY(km->shard_owner.ensure(km->nb));
+    FDB_TRY(km->picked.ensure(km->nb * km->k));
+    *d_totals = km->total.p;
+    *d_pick = km->ci.p;
+    *d_centre_send = km->centre_send.p;
+    *d_u01 = km->u01.p;
+    *d_picked_global = km->picked.p;
+    return FDB_OK;
+}
+
+int fdb_kmeans_seed_sharded_total(fdb_km *km) {
+    ARG(km, "km is null");
+    FDB_TRY(km->ctx->use());
+    return km_total_fast(km);
+}
+
+int fdb_kmeans_seed_sharded_pick(fdb_km *km, const float *d_all_totals, int world, int rank) {
+    ARG(km && d_all_totals && world >= 1 && rank >= 0 && rank < world, "invalid argument");
+    fdb_ctx *ctx = km->ctx;
+    FDB_TRY(ctx->use());
+    const size_t nb = km->nb;
+    fdb_shard::shard_split_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, ctx->stream>>>(
+        d_all_totals, world, rank, nb, km->u01.p, km->shard_values.p, km->shard_owner.p);
+    ctx->launches++;
+    FDB_TRY(km_seed_pick(km, km->shard_values.p, 1, 0, 0, 1));
+    fdb_shard::shard_publish_kernel<<<(unsigned)nb, 128, 0, ctx->stream>>>(km->shard_owner.p, rank, nb, km->m, km->vs->d,
+                                                               km->vs->dim, km->col_off, km->ci.p,
+                                                               km->centre_send.p);
+    ctx->launches++;
+    FDB_CHECK_LAUNCH();
+    return FDB_OK;
+}
+
+int fdb_kmeans_seed_sharded_first(fdb_km *km, const uint32_t *local_first) {
+    ARG(km && local_first, "null argument");
+    fdb_ctx *ctx = km->ctx;
+    FDB_TRY(ctx->use());
+    const size_t nb = km->nb;
+    std::vector<int> own(nb);
+    for (size_t b = 0; b < nb; ++b) {
+        ARG(local_first[b] == 0xFFFFFFFFu || local_first[b] < km->n, "local index out of range");
+        own[b] = local_first[b] == 0xFFFFFFFFu ? -1 : 0;
+    }
+    FDB_TRY(upload_small(ctx, km->ci.p, local_first, nb * sizeof(uint32_t)));
+    FDB_TRY(upload_small(ctx, km->shard_owner.p, own.data(), nb * sizeof(int)));
+    fdb_shard::shard_publish_kernel<<<(unsigned)nb, 128, 0, ctx->stream>>>(km->shard_owner.p, 0, nb, km->m, km->vs->d,
+                                                               km->vs->dim, km->col_off, km->ci.p,
+                                                               km->centre_send.p);
+    ctx->launches++;
+    FDB_CHECK_LAUNCH();
+    return FDB_OK;
+}
+
+int fdb_kmeans_seed_sharded_round(fdb_km *km, size_t i, const uint32_t *d_all_picks, const float *d_all_centres,
+                                  int world, int rank, size_t n_global) {
+    ARG(km && d_all_picks && d_all_centres && world >= 1 && rank >= 0 && rank < world, "invalid argument");
+    ARG(i < km->k, "round %zu out of range", i);
+    fdb_ctx *ctx = km->ctx;
+    FDB_TRY(ctx->use());
+    fdb_shard::shard_adopt_kernel<<<(unsigned)km->nb, 128, 0, ctx->stream>>>(d_all_picks, d_all_centres, world, rank, km->nb,
+                                                                 km->m, n_global, km->ci.p, km->centre.p,
+                                                                 km->picked.p + i * km->nb, ctx->d_flags);
+    ctx->launches++;
+    FDB_CHECK_LAUNCH();
+    return km_seed_round(km, (uint32_t)i, 0, km->centre.p);
+}
+
+int fdb_kmeans_seed_sharded_finish(fdb_km *km, uint32_t *picked_global) {
+    ARG(km && picked_global, "null argument");
+    fdb_ctx *ctx = km->ctx;
+    FDB_TRY(ctx->use());
+    const size_t nb = km->nb, k = km->k;
+    std::vector<uint32_t> stage(nb * k);
+    FDB_CUDA(cudaMemcpyAsync(stage.data(), km->picked.p, stage.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                             ctx->stream));
+    FDB_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (size_t b = 0; b < nb; ++b)
+        for (size_t i = 0; i < k; ++i) picked_global[b * k + i] = stage[i * nb + b];
+    unsigned f = 0;
+    FDB_TRY(ctx->check_flags(&f));
+    return map_flags(f & ~FLAG_WEIGHTS);  // a shard's own total may legitimately be zero
 }
 
 int fdb_kmeans_seed_run(fdb_km *km, const uint32_t *first, const float *u01, int exact,

@@ -23,6 +23,8 @@ struct fdb_km {
     fdb::DevBuf<float> partial;                     // multi-GPU sums ++ counts
     fdb::DevBuf<float> u01;                         // seeding draws staged on the device
     fdb::DevBuf<float> centre;                      // [nb][m] externally supplied centres (sharded rows)
+    fdb::DevBuf<float> centre_send, shard_values;   // sharded seeding: this rank's picked rows, split draw
+    fdb::DevBuf<int> shard_owner;                   // [nb] rank that owns the round's draw
     fdb::DevBuf<uint32_t> picked;                   // [k][nb] picks of seed_run
     fdb::DevBuf<double> pick_bsum;                  // [nb][blocks] block sums of the weights (two-level sampler)
     fdb::DevBuf<unsigned> pick_blast;               // [nb][blocks] last positive weight of every block

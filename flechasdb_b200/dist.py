@@ -90,15 +90,15 @@ def split_sample(u01, totals):
     return last, np.float32(t[last])                    # rounding pushed the draw past the end
 
 
-def device_tensor(ptr, nfloats, device):
-    """torch view of an engine-owned device buffer (no copy)."""
+def device_tensor(ptr, nelems, device, typestr="<f4"):
+    """torch view of an engine-owned device buffer (no copy); typestr "<f4" or "<i4"."""
     import torch
 
     class _Arr:
         pass
 
     a = _Arr()
-    a.__cuda_array_interface__ = {"shape": (nfloats,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+    a.__cuda_array_interface__ = {"shape": (nelems,), "typestr": typestr, "data": (ptr, False), "version": 2}
     return torch.as_tensor(a, device=device)
 
 
@@ -149,6 +149,48 @@ class ShardedKMeans:
             local_ci = np.array([li if r == comm.rank else NONE for r, li in owners], np.uint32)
             km.seed_round_ext(i, centres, local_ci)
         return picked
+
+    def seed_device(self, first_global, u01):
+        """The same seeding with nothing but kernels and NCCL all-gathers on the engine's stream: three
+        small collectives per round, no host synchronisation until the picks are read back.  CUDA only."""
+        import ctypes as C
+        import torch
+        from . import _capi as capi
+        km, comm = self.km, self.comm
+        nb, k, m, world, rank = km.nb, km.k, km.dim, comm.world, comm.rank
+        lib, dev, dist = capi.lib(), comm.device, comm.dist
+        ptrs = [capi.VP() for _ in range(5)]
+        capi.check(lib.fdb_kmeans_seed_sharded_begin(km.h, *[C.byref(p) for p in ptrs]))
+        d_tot = device_tensor(ptrs[0].value, nb, dev)
+        d_pick = device_tensor(ptrs[1].value, nb, dev, "<i4")
+        d_send = device_tensor(ptrs[2].value, nb * m, dev)
+        d_u = device_tensor(ptrs[3].value, nb, dev)
+        all_tot = torch.empty((world, nb), dtype=torch.float32, device=dev)
+        all_pick = torch.empty((world, nb), dtype=torch.int32, device=dev)
+        all_cen = torch.empty((world, nb * m), dtype=torch.float32, device=dev)
+        u_dev = torch.as_tensor(np.ascontiguousarray(u01, np.float32).reshape(nb, max(k - 1, 0))).to(dev)
+        local_first = np.full(nb, NONE, np.uint32)
+        for b, g in enumerate(first_global):
+            r, li = owner_of(int(g), self.n, world)
+            if r == rank:
+                local_first[b] = li
+        stream = torch.cuda.ExternalStream(lib.fdb_ctx_stream(km.vs.ctx.h), device=dev)
+        torch.cuda.current_stream(dev).synchronize()          # u_dev is ready
+        with torch.cuda.stream(stream):
+            capi.check(lib.fdb_kmeans_seed_sharded_first(km.h, capi.u32p(local_first)))
+            for i in range(k):
+                if i > 0:
+                    capi.check(lib.fdb_kmeans_seed_sharded_total(km.h))
+                    dist.all_gather_into_tensor(all_tot, d_tot)
+                    d_u.copy_(u_dev[:, i - 1])
+                    capi.check(lib.fdb_kmeans_seed_sharded_pick(km.h, all_tot.data_ptr(), world, rank))
+                dist.all_gather_into_tensor(all_pick, d_pick)
+                dist.all_gather_into_tensor(all_cen, d_send)
+                capi.check(lib.fdb_kmeans_seed_sharded_round(km.h, i, all_pick.data_ptr(), all_cen.data_ptr(),
+                                                             world, rank, self.n))
+            picked = np.zeros((nb, k), np.uint32)
+            capi.check(lib.fdb_kmeans_seed_sharded_finish(km.h, capi.u32p(picked)))
+        return picked.astype(np.int64)
 
     def run(self, max_rounds=100, eps=1e-6, on_round=None):
         """the Lloyd loop; returns (gradients[nb] list per round, reassignments)"""

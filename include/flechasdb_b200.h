@@ -118,6 +118,23 @@ int fdb_kmeans_seed_chosen(fdb_km *km, const uint32_t *chosen);
  *                    cumulative weights (negative = the draw falls into another shard) */
 int fdb_kmeans_seed_round_ext(fdb_km *km, size_t i, const float *centres, const uint32_t *local_ci);
 int fdb_kmeans_seed_pick_value(fdb_km *km, const float *sample_values, uint32_t *ci_out);
+/* The same sharded k-means++ without host round trips: every call only enqueues kernels on the
+ * context's stream (fdb_ctx_stream), the caller runs the all-gathers (NCCL) on that stream in between.
+ *   begin  -> device addresses of: totals [nb], pick [nb], centre_send [nb][dim], u01 [nb] (the caller
+ *             copies this round's draws there), picked_global [k][nb]
+ *   round 0: first(local index of the first centre or 0xFFFFFFFF) -> all-gather pick, centre_send -> round(0, ..)
+ *   round i: total -> all-gather totals [world][nb] -> pick(all_totals) -> all-gather pick [world][nb] and
+ *            centre_send [world][nb][dim] -> round(i, all_picks, all_centres)
+ *   finish -> the picked global indices [nb][k] (the only host synchronisation) */
+void *fdb_ctx_stream(fdb_ctx *ctx);
+int fdb_kmeans_seed_sharded_begin(fdb_km *km, float **d_totals, uint32_t **d_pick, float **d_centre_send,
+                                  float **d_u01, uint32_t **d_picked_global);
+int fdb_kmeans_seed_sharded_first(fdb_km *km, const uint32_t *local_first);
+int fdb_kmeans_seed_sharded_total(fdb_km *km);
+int fdb_kmeans_seed_sharded_pick(fdb_km *km, const float *d_all_totals, int world, int rank);
+int fdb_kmeans_seed_sharded_round(fdb_km *km, size_t i, const uint32_t *d_all_picks, const float *d_all_centres,
+                                  int world, int rank, size_t n_global);
+int fdb_kmeans_seed_sharded_finish(fdb_km *km, uint32_t *picked_global);
 /* test hook / resume: set centroids [nb][k][dim] and (optionally) indices [nb][n] */
 int fdb_kmeans_set_state(fdb_km *km, const float *centroids, const uint32_t *indices);
 

@@ -30,11 +30,16 @@ u = rng.random((1, P - 1)).astype(np.float32)
 
 ckm = engine.KMeans(vs, P)
 sk = fd.ShardedKMeans(comm, ckm, lambda li: vs.download(li, 1)[0], M, partial_view=view)
-t0 = time.perf_counter()
-picked = sk.seed(first, u)
-t_seed = time.perf_counter() - t0
+# host-driven seeding (three host round trips per round) and the device-driven one: same picks
+torch.cuda.synchronize(); comm.barrier(); t0 = time.perf_counter()
+picked_host = sk.seed(first, u)
+torch.cuda.synchronize(); t_seed_host = time.perf_counter() - t0
+comm.barrier(); t0 = time.perf_counter()
+picked = sk.seed_device(first, u)
+torch.cuda.synchronize(); t_seed = time.perf_counter() - t0
+ok_same = bool((picked == picked_host).all())
 allp = comm.all_gather(picked.astype(np.int32))
-ok_picks = all((allp[r] == allp[0]).all() for r in range(world))
+ok_picks = all((allp[r] == allp[0]).all() for r in range(world)) and ok_same
 # one update step, compared with a single-GPU engine over all rows (rank 0 only)
 ptr, nfl = ckm.update_partial()
 comm.all_reduce_sum_tensor(view(ptr, nfl)); torch.cuda.synchronize()
@@ -83,8 +88,9 @@ if True:
         ok_query = bool((mc == wc).all() and (mp_ == wp).all() and (mv == wv).all() and (md == wd).all())
 if rank == 0:
     print("dist_check world=%d M=%d N=%d P=%d: picks_equal=%s update_close=%s assign_exact=%s query_equal=%s "
-          "seed_s=%.3f lloyd_s=%.3f rounds=%d" % (world, M, N, P, ok_picks, ok_update, ok_assign, ok_query,
-                                                  t_seed, t_lloyd, len(grads)), flush=True)
+          "seed_s=%.3f (host-driven %.3f) lloyd_s=%.3f rounds=%d" % (world, M, N, P, ok_picks, ok_update, ok_assign,
+                                                                     ok_query, t_seed, t_seed_host, t_lloyd,
+                                                                     len(grads)), flush=True)
     assert ok_picks and ok_update and ok_assign and ok_query
 dist.barrier()
 dist.destroy_process_group()
