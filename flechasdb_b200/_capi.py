@@ -81,6 +81,11 @@ SIGNATURES = {
     "fdb_kmeans_get": (C.c_int, [VP, F32P, U32P]),
     "fdb_kmeans_get_weights": (C.c_int, [VP, F32P]),
     "fdb_kmeans_update_partial": (C.c_int, [VP, C.POINTER(VP), C.POINTER(SZ)]),
+    "fdb_kmeans_sharded_loop_begin": (C.c_int, [VP]),
+    "fdb_kmeans_sharded_partial_async": (C.c_int, [VP, C.POINTER(VP), C.POINTER(SZ)]),
+    "fdb_kmeans_sharded_finish_async": (C.c_int, [VP, C.c_float]),
+    "fdb_kmeans_sharded_poll": (C.c_int, [VP, U8P]),
+    "fdb_kmeans_sharded_loop_end": (C.c_int, [VP, F32P, U32P, U32P]),
     "fdb_kmeans_update_finish": (C.c_int, [VP, F32P]),
     "fdb_index_create": (C.c_int, [VP, SZ, SZ, SZ, SZ, F32P, F32P, U64P, U8P, C.POINTER(VP)]),
     "fdb_index_from_build": (C.c_int, [VP, VP, VP, C.POINTER(VP)]),

@@ -898,4 +898,61 @@ int fdb_kmeans_update_finish(fdb_km *km, float *gradients) {
     return km_finish_call(km);
 }
 
+/* ---- sharded Lloyd loop without host round trips -------------------------------------------------
+ * begin; per round: partial (enqueue) -> all-reduce of the buffer on the context's stream -> finish
+ * (divide, gradient, device-side convergence flags, reassignment of the still active problems);
+ * poll reads the flags back (the only synchronisation, the caller chooses how often); end returns the
+ * gradient history like fdb_kmeans_run. */
+int fdb_kmeans_sharded_loop_begin(fdb_km *km) {
+    ARG(km, "km is null");
+    fdb_ctx *ctx = km->ctx;
+    FDB_TRY(ctx->use());
+    const size_t nb = km->nb;
+    FDB_TRY(km_fill_int(ctx, km->active.p, nb, 1));
+    FDB_CUDA(cudaMemsetAsync(km->rounds.p, 0, nb * sizeof(uint32_t), ctx->stream));
+    FDB_CUDA(cudaMemsetAsync(km->reassigns.p, 0, nb * sizeof(uint32_t), ctx->stream));
+    FDB_CUDA(cudaMemsetAsync(km->grad_hist.p, 0, nb * km->max_rounds * sizeof(float), ctx->stream));
+    return FDB_OK;
+}
+
+int fdb_kmeans_sharded_partial_async(fdb_km *km, float **device_buf, size_t *nfloats) {
+    ARG(km && device_buf && nfloats, "null argument");
+    FDB_TRY(km->ctx->use());
+    FDB_TRY(km_update_partial(km));
+    *device_buf = km->partial.p;
+    *nfloats = km->nb * km->k * km->m + km->nb * km->k;
+    return FDB_OK;
+}
+
+int fdb_kmeans_sharded_finish_async(fdb_km *km, float epsilon) {
+    ARG(km, "km is null");
+    ARG(km->partial.p, "partial has not been called");
+    FDB_TRY(km->ctx->use());
+    FDB_TRY(km_update_finish_loop(km, km->active.p, 1, epsilon));
+    return km_reassign(km, km->active.p);
+}
+
+int fdb_kmeans_sharded_poll(fdb_km *km, uint8_t *active) {
+    ARG(km && active, "null argument");
+    fdb_ctx *ctx = km->ctx;
+    FDB_TRY(ctx->use());
+    std::vector<int> a(km->nb);
+    FDB_CUDA(cudaMemcpyAsync(a.data(), km->active.p, km->nb * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    FDB_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (size_t b = 0; b < km->nb; ++b) active[b] = a[b] ? 1 : 0;
+    return FDB_OK;
+}
+
+int fdb_kmeans_sharded_loop_end(fdb_km *km, float *gradients, uint32_t *rounds, uint32_t *reassigns) {
+    ARG(km && gradients && rounds && reassigns, "null argument");
+    fdb_ctx *ctx = km->ctx;
+    FDB_TRY(ctx->use());
+    const size_t nb = km->nb;
+    FDB_CUDA(cudaMemcpyAsync(gradients, km->grad_hist.p, nb * km->max_rounds * sizeof(float), cudaMemcpyDeviceToHost,
+                             ctx->stream));
+    FDB_CUDA(cudaMemcpyAsync(rounds, km->rounds.p, nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    FDB_CUDA(cudaMemcpyAsync(reassigns, km->reassigns.p, nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    return km_finish_call(km);
+}
+
 }  // extern "C"

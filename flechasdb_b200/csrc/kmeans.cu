@@ -635,6 +635,7 @@ __global__ void __launch_bounds__(128) accumulate_kernel(UpdateParams p, unsigne
 // multi-GPU: after the all-reduce of sums/counts
 __global__ void finish_partial_kernel(UpdateParams p) {
     const size_t b = blockIdx.z, i = blockIdx.y;
+    if (p.active && !p.active[b]) return;
     const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= p.m) return;
     const size_t o = (b * p.k + i) * p.m + e;
@@ -991,14 +992,18 @@ int km_update_partial(fdb_km *km) {
     return FDB_OK;
 }
 
-int km_update_finish(fdb_km *km) {
+int km_update_finish(fdb_km *km) { return km_update_finish_loop(km, nullptr, 0, -1.0f); }
+
+// loop_mode: the gradient kernel keeps the per-problem active flags, round counters and gradient
+// history on the device (problems that converged are frozen: their flag is already 0)
+int km_update_finish_loop(fdb_km *km, const int *d_active, int loop_mode, float eps) {
     fdb_ctx *ctx = km->ctx;
-    UpdateParams p = make_update_params(km, nullptr, km->partial.p);
+    UpdateParams p = make_update_params(km, d_active, km->partial.p);
     dim3 grid((unsigned)((km->m + 127) / 128), (unsigned)km->k, (unsigned)km->nb);
     finish_partial_kernel<<<grid, 128, 0, ctx->stream>>>(p);
     ctx->launches++;
     FDB_CHECK_LAUNCH();
-    return km_norms_and_gradient(km, nullptr, 0, -1.0f, 1);
+    return km_norms_and_gradient(km, d_active, loop_mode, eps, loop_mode ? km->max_rounds : 1);
 }
 
 int km_residuals(fdb_vs *vs, const fdb_km *km) {

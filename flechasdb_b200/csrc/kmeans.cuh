@@ -43,6 +43,7 @@ int km_total_fast(fdb_km *km);
 int km_fill_int(fdb_ctx *ctx, int *p, size_t n, int v);
 int km_update_partial(fdb_km *km);
 int km_update_finish(fdb_km *km);
+int km_update_finish_loop(fdb_km *km, const int *d_active, int loop_mode, float eps);
 int km_residuals(fdb_vs *vs, const fdb_km *km);
 bool tc_eligible(const fdb_km *km);
 int tc_reassign(fdb_km *km, const int *d_active);

@@ -214,6 +214,42 @@ class ShardedKMeans:
             reassigns += active
         return grads, reassigns
 
+    def run_device(self, max_rounds=100, eps=1e-6, poll_every=4):
+        """The same loop with every round enqueued on the engine's stream: partial sums -> NCCL all-reduce
+        -> divide / gradient / convergence flags / reassignment, all on the device.  The host reads the
+        flags every `poll_every` rounds only (a converged problem is frozen on the device, so the rounds
+        enqueued past its convergence change nothing).  Returns what run() returns.  CUDA only."""
+        import ctypes as C
+        import torch
+        from . import _capi as capi
+        km, comm = self.km, self.comm
+        lib, dev, dist = capi.lib(), comm.device, comm.dist
+        assert max_rounds <= capi.KMEANS_MAX_ROUNDS
+        stream = torch.cuda.ExternalStream(lib.fdb_ctx_stream(km.vs.ctx.h), device=dev)
+        active = np.ones(km.nb, np.uint8)
+        with torch.cuda.stream(stream):
+            capi.check(lib.fdb_kmeans_sharded_loop_begin(km.h))
+            buf = None
+            for r in range(max_rounds):
+                p, n = capi.VP(), C.c_size_t()
+                capi.check(lib.fdb_kmeans_sharded_partial_async(km.h, C.byref(p), C.byref(n)))
+                if buf is None or buf.data_ptr() != p.value:
+                    buf = device_tensor(p.value, n.value, dev)
+                if dist is not None:
+                    dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+                capi.check(lib.fdb_kmeans_sharded_finish_async(km.h, eps))
+                if (r + 1) % poll_every == 0 or r + 1 == max_rounds:
+                    capi.check(lib.fdb_kmeans_sharded_poll(km.h, capi.u8p(active)))
+                    if not active.any():
+                        break
+            g = np.zeros((km.nb, capi.KMEANS_MAX_ROUNDS), np.float32)
+            rounds = np.zeros(km.nb, np.uint32)
+            reas = np.zeros(km.nb, np.uint32)
+            capi.check(lib.fdb_kmeans_sharded_loop_end(km.h, capi.f32p(g), capi.u32p(rounds), capi.u32p(reas)))
+        nr = int(rounds.max()) if km.nb else 0
+        grads = [np.where(np.arange(km.nb) * 0 + i < rounds, g[:, i], np.float32(0)) for i in range(nr)]
+        return grads, reas.astype(np.int64)
+
     def _sync(self):
         if str(self.comm.device).startswith("cuda"):
             import torch

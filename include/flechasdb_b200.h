@@ -166,6 +166,16 @@ int fdb_kmeans_get_weights(fdb_km *km, float *weights); /* [nb][n] D^2 weights *
  * all-reduces (NCCL sum) in place; update_finish divides and computes the gradient. */
 int fdb_kmeans_update_partial(fdb_km *km, float **device_buf, size_t *nfloats);
 int fdb_kmeans_update_finish(fdb_km *km, float *gradients);
+/* The same loop without host round trips (everything is enqueued on fdb_ctx_stream): begin; per round
+ * partial_async -> all-reduce of the buffer on that stream -> finish_async (divide, gradient, device-side
+ * convergence flags, reassignment of the active problems); poll reads the flags (the caller chooses how
+ * often: converged problems are frozen on the device, extra rounds do nothing); end returns what
+ * fdb_kmeans_run returns, gradients [nb][FDB_KMEANS_MAX_ROUNDS]. */
+int fdb_kmeans_sharded_loop_begin(fdb_km *km);
+int fdb_kmeans_sharded_partial_async(fdb_km *km, float **device_buf, size_t *nfloats);
+int fdb_kmeans_sharded_finish_async(fdb_km *km, float epsilon);
+int fdb_kmeans_sharded_poll(fdb_km *km, uint8_t *active /*[nb]*/);
+int fdb_kmeans_sharded_loop_end(fdb_km *km, float *gradients, uint32_t *rounds, uint32_t *reassigns);
 
 /* ---- index + query: src/db/build.rs:446-482, src/db/stored.rs:331-442,549-597 ---- */
 /* Host-side constructor (what load_database/load_partition feed):

@@ -64,9 +64,19 @@ if rank == 0:
     stitched = np.concatenate([gi[r][:fd.shard_rows(M, world, r)[1] - fd.shard_rows(M, world, r)[0]] for r in range(world)])
     ok_assign = bool((stitched == full_idx).all())
 # full sharded Lloyd loop, timed
+c_start, i_start = ckm.get()
 comm.barrier(); torch.cuda.synchronize(); t0 = time.perf_counter()
 grads, reas = sk.run(max_rounds=100)
+torch.cuda.synchronize(); t_lloyd_host = time.perf_counter() - t0
+c_host, i_host = ckm.get()
+# the same loop without host round trips (kernels + NCCL on the engine's stream): identical trajectory
+ckm.set_state(c_start, i_start)
+comm.barrier(); torch.cuda.synchronize(); t0 = time.perf_counter()
+grads_d, reas_d = sk.run_device(max_rounds=100)
 torch.cuda.synchronize(); t_lloyd = time.perf_counter() - t0
+c_dev, i_dev = ckm.get()
+ok_loop = bool((c_dev == c_host).all() and (i_dev == i_host).all() and len(grads) == len(grads_d)
+               and all((a == b).all() for a, b in zip(grads, grads_d)) and (reas == reas_d).all())
 # partition-sharded query against an index built on rank 0's single-GPU path
 ok_query = True
 if True:
@@ -88,9 +98,9 @@ if True:
         ok_query = bool((mc == wc).all() and (mp_ == wp).all() and (mv == wv).all() and (md == wd).all())
 if rank == 0:
     print("dist_check world=%d M=%d N=%d P=%d: picks_equal=%s update_close=%s assign_exact=%s query_equal=%s "
-          "seed_s=%.3f (host-driven %.3f) lloyd_s=%.3f rounds=%d" % (world, M, N, P, ok_picks, ok_update, ok_assign,
-                                                                     ok_query, t_seed, t_seed_host, t_lloyd,
-                                                                     len(grads)), flush=True)
-    assert ok_picks and ok_update and ok_assign and ok_query
+          "loop_equal=%s seed_s=%.3f (host-driven %.3f) lloyd_s=%.3f (host-driven %.3f) rounds=%d" % (
+              world, M, N, P, ok_picks, ok_update, ok_assign, ok_query, ok_loop, t_seed, t_seed_host, t_lloyd,
+              t_lloyd_host, len(grads)), flush=True)
+    assert ok_picks and ok_update and ok_assign and ok_query and ok_loop
 dist.barrier()
 dist.destroy_process_group()
