@@ -72,6 +72,11 @@ struct FilterState {
         DevBuf<uint32_t> cand_a, cand_cnt, cand_total;
         DevBuf<unsigned> qbad;       // [nq]
         DevBuf<uint32_t> fb_list;    // [nq]
+        // partition-major scan (adc_pscan.cuh): grouping of the (query, probe) pairs, shared thresholds, item lists
+        DevBuf<uint32_t> pg_ctl;     // [2P] pairs per bucket, then the item counter
+        DevBuf<uint32_t> pg_pstart, pg_istart, pg_slot, pg_pairs, pg_desc;
+        DevBuf<unsigned> pg_thr;     // [nq]
+        DevBuf<uint32_t> it_keys, it_pos, it_cnt;
         DevBuf<unsigned long long> counters;  // [0] fallbacks, [1] exact candidates, [2] scanned vectors, [4..] reasons
         cudaStream_t stream = nullptr;
         cudaEvent_t done = nullptr;
@@ -402,6 +407,67 @@ __device__ __forceinline__ void push_lanes(RegTopK &sel, uint32_t kv, uint32_t a
     }
 }
 
+// (key, pos) ascending bitonic sort over the 32 lanes of a warp
+__device__ __forceinline__ void warp_sort32(uint32_t &key, uint32_t &pos, int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j >= 1; j >>= 1) {
+            const uint32_t ok = __shfl_xor_sync(0xffffffffu, key, j), op = __shfl_xor_sync(0xffffffffu, pos, j);
+            // ascending block and lower lane of the pair (or descending block and upper lane): keep the smaller
+            const bool keep_min = ((lane & j) == 0) == ((lane & k) == 0);
+            const bool other_less = (ok < key) || (ok == key && op < pos);
+            const bool other_more = (ok > key) || (ok == key && op > pos);
+            const bool take = keep_min ? other_less : other_more;
+            if (take) key = ok, pos = op;
+        }
+    }
+}
+
+// cuts the append buffer of query j back to its ncap smallest entries; one warp.  Returns the new
+// count; *thr = the largest kept key when the list is full (unchanged otherwise).
+__device__ __forceinline__ int cut_to_smallest(uint32_t *bk, uint32_t *bp, int n, int ncap, unsigned *thr, int lane) {
+    if (n <= 0) return 0;
+    uint32_t key = 0xffffffffu, pos = 0xffffffffu;
+    int kept;
+    if (ncap <= 16) {
+        // lanes 0..15 carry the best so far, lanes 16..31 take the next 16 entries
+        int done = min(n, 32);
+        if (lane < done) key = bk[lane], pos = bp[lane];
+        warp_sort32(key, pos, lane);
+        while (done < n) {
+            const int i = done + lane - 16;
+            if (lane >= 16) {
+                key = 0xffffffffu, pos = 0xffffffffu;
+                if (i < n) key = bk[i], pos = bp[i];
+            }
+            done = min(n, done + 16);
+            warp_sort32(key, pos, lane);
+        }
+        kept = min(n, ncap);
+    } else {
+        RegTopK sel;
+        sel.init(ncap);
+        for (int base = 0; base < n; base += 32) {
+            const int i = base + lane;
+            const uint32_t kv = i < n ? bk[i] : 0xffffffffu, pv = i < n ? bp[i] : 0u;
+            push_lanes(sel, kv, pv, i < n && kv < sel.maxkey, lane);
+        }
+        key = lane < sel.len ? sel.key : 0xffffffffu;
+        pos = lane < sel.len ? sel.a : 0xffffffffu;
+        warp_sort32(key, pos, lane);
+        kept = sel.len;
+    }
+    __syncwarp();
+    if (lane < kept) bk[lane] = key, bp[lane] = pos;
+    if (kept == ncap) {
+        const uint32_t last = __shfl_sync(0xffffffffu, key, ncap - 1);
+        if (lane == 0) *thr = min(*thr, last);
+    }
+    __syncwarp();
+    return kept;
+}
+
 // the RW 32-bit words of a record / code vector, with the widest loads its stride allows (a
 // 16-byte stride read word by word would be a 4-way bank conflict)
 template <int RW>
@@ -453,12 +519,20 @@ __device__ __forceinline__ float adc_sum(const unsigned char *rec, const float *
     }
 }
 
+// Selection: one append buffer per query (CTA) in shared memory and a threshold held in a register;
+// a lane appends (atomicAdd on the counter) when its value is below the threshold -- no votes, no
+// shuffles in the steady state.  After every iteration (one 128-vector chunk per warp) the CTA meets,
+// warp 0 cuts the buffer back to the ncap smallest entries and the threshold becomes the largest kept.
+// While no threshold exists yet the first chunks are taken in pieces of 16, 16, 32 and 64 vectors per
+// warp, so the buffer (FSB entries) cannot overflow before a threshold exists; an overflow later on
+// (the lists would have to be sorted by decreasing distance) flags the query for the exact pipeline.
+constexpr int FSB = 96;
 template <int W, bool RECORDS>
 __global__ void __launch_bounds__(FS_WARPS * 32) fscan_kernel(FScanParams p) {
     extern __shared__ __align__(16) unsigned char sm[];
-    __shared__ unsigned thr_s;  // smallest "largest kept key" over the warps' full lists
-    __shared__ uint32_t mk[FS_WARPS * RCAP], ma[FS_WARPS * RCAP];
-    __shared__ int mlen[FS_WARPS];
+    __shared__ unsigned thr_s, flag_s;
+    __shared__ int cnt_s;
+    __shared__ uint32_t bk[FSB], bp[FSB];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int D = p.D, C = p.C, RB = p.rb;
     const int DC = D * C;
@@ -490,60 +564,104 @@ __global__ void __launch_bounds__(FS_WARPS * 32) fscan_kernel(FScanParams p) {
             }
         }
     };
-    if (tid == 0) thr_s = 0xffffffffu;
+    if (tid == 0) {
+        thr_s = 0xffffffffu;
+        flag_s = 0u;
+        cnt_s = 0;
+    }
     if (RECORDS) build_table(nullptr);
 
-    RegTopK sel;
-    sel.init(p.ncap);
+    unsigned thr = 0xffffffffu;
+    // the CTA meets: buffer cut back to the ncap smallest, new threshold
+    auto round_end = [&]() {
+        __syncthreads();
+        if (warp == 0) {
+            const int n = min(cnt_s, FSB);
+            if (n > p.ncap) {
+                const int kept = cut_to_smallest(bk, bp, n, p.ncap, &thr_s, lane);
+                if (lane == 0) cnt_s = kept;
+            }
+        }
+        __syncthreads();
+        thr = thr_s;
+    };
     uint32_t flat0 = 0;
+    int seen = 0, target = 64;       // vectors the CTA has scanned so far; the CTA meets when seen reaches target
     const int dpad = (D + 3) & ~3;   // offset of bv inside a record
+    const int CV = p.chunk_vecs;
     for (int pr = 0; pr < p.nprobe; ++pr) {
         const uint32_t part = p.probes[q * p.nprobe + pr];
         const int np = (int)(p.part_off[part + 1] - p.part_off[part]);
         const float K = p.Kq[q * p.nprobe + pr];
         bad |= !(fabsf(K) < 1e30f);
         const uint8_t *cg = p.codes + p.part_start[part];
-        const int nchunks = (np + p.chunk_vecs - 1) / p.chunk_vecs;
+        const int nchunks = (np + CV - 1) / CV;
         auto issue = [&](int c, int slot) {
             if (c < nchunks) {
-                const int c0 = c * p.chunk_vecs;
-                const int cnt = min(p.chunk_vecs, np - c0);
-                const size_t n16 = ((size_t)cnt * RB + 15) >> 4;
+                const int c0 = c * CV;
+                const int n16 = (min(CV, np - c0) * RB + 15) >> 4;
                 const uint8_t *src = cg + (size_t)c0 * RB;
                 unsigned char *dst = cbuf + (size_t)slot * chunk_bytes;
-                for (size_t i = lane; i < n16; i += 32) cp_async16(dst + 16 * i, src + 16 * i);
+                for (int i = lane; i < n16; i += 32) cp_async16(dst + 16 * i, src + 16 * i);
             }
             cp_async_commit();
         };
         issue(warp, 0);  // the warp's first chunk travels while the table is assembled
-        if (!RECORDS || pr == 0) __syncthreads();  // previous list fully scanned / Ts and thr_s set
+        if (!RECORDS || pr == 0) __syncthreads();  // previous list fully scanned / Ts and the selection state set
         if (!RECORDS) {
             build_table(p.pc + (size_t)part * DC);
             __syncthreads();
         }
         int slot = 0;
-        for (int c = warp; c < nchunks; c += FS_WARPS) {
+        const int niter = (nchunks + FS_WARPS - 1) / FS_WARPS;   // the same number of iterations in every warp
+        for (int it = 0; it < niter; ++it) {
+            const int c = it * FS_WARPS + warp;
             issue(c + FS_WARPS, slot ^ 1);
             cp_async_wait<1>();
             __syncwarp();
-            const int c0 = c * p.chunk_vecs;
-            const int cnt = min(p.chunk_vecs, np - c0);
+            const int c0 = c * CV;
+            const int cnt = max(0, min(CV, np - c0));
             const unsigned char *cs = cbuf + (size_t)slot * chunk_bytes;
-            for (int base = 0; base < cnt; base += 32) {
-                const int v = base + lane;
-                const bool valid = v < cnt;
-                float a = 0.0f;
-                if (valid) {
-                    a = adc_sum<W, RECORDS>(cs + (size_t)v * RB, Ts, D, dpad) + K;
+            auto scan_range = [&](int lo, int top) {
+                for (int base = lo & ~31; base < top; base += 32) {
+                    const int v = base + lane;
+                    if (v >= lo && v < top) {
+                        const float a = adc_sum<W, RECORDS>(cs + (size_t)v * RB, Ts, D, dpad) + K;
+                        const uint32_t ka = fkey(a);
+                        if (ka < thr) {
+                            const int i = atomicAdd(&cnt_s, 1);
+                            if (i < FSB) {
+                                bk[i] = ka;
+                                bp[i] = flat0 + (uint32_t)(c0 + v);
+                            } else {
+                                flag_s = 1u;
+                            }
+                        }
+                    }
                 }
-                const uint32_t ka = fkey(a);
-                // a vector is kept only below this warp's largest kept value and below every other
-                // warp's (a full list elsewhere already holds ncap values <= its largest)
-                const uint32_t lim = min(sel.maxkey, *reinterpret_cast<volatile unsigned *>(&thr_s));
-                const bool want = valid && (ka < lim);
-                if (__any_sync(0xffffffffu, want)) {
-                    push_lanes(sel, ka, flat0 + (uint32_t)(c0 + v), want, lane);
-                    if (lane == 0 && sel.len == sel.n) atomicMin(&thr_s, sel.maxkey);
+            };
+            const int it0 = it * FS_WARPS * CV;   // first vector of the iteration (uniform)
+            if (seen >= FS_WARPS * CV) {
+                // steady state: the whole chunk; the CTA meets when the number of vectors seen has doubled
+                scan_range(0, cnt);
+                seen += min(np, it0 + FS_WARPS * CV) - it0;
+                if (seen >= target) {
+                    round_end();
+                    while (target <= seen) target <<= 1;
+                }
+            } else {
+                // the first vectors: pieces of 16, 16, 32, 64, ... per warp with a meeting after each, so that a
+                // piece never holds more vectors than the CTA has seen (about ncap new entries per piece)
+                int lo = 0;
+                while (lo < CV && it0 + lo < np) {
+                    const int piece = min(CV - lo, max(16, (seen / FS_WARPS) & ~15));
+                    const int hi = lo + piece;
+                    scan_range(lo, min(hi, cnt));
+#pragma unroll
+                    for (int w = 0; w < FS_WARPS; ++w) seen += max(0, min(np - it0 - w * CV, hi) - lo);
+                    lo = hi;
+                    round_end();
+                    while (target <= seen) target <<= 1;
                 }
             }
             __syncwarp();
@@ -552,32 +670,21 @@ __global__ void __launch_bounds__(FS_WARPS * 32) fscan_kernel(FScanParams p) {
         cp_async_wait<0>();
         flat0 += (uint32_t)np;
     }
-    // merge the warps' lists into warp 0's
-    if (lane < sel.len) {
-        mk[warp * RCAP + lane] = sel.key;
-        ma[warp * RCAP + lane] = sel.a;
-    }
-    if (lane == 0) mlen[warp] = sel.len;
+    round_end();   // at most ncap entries are left
+    // ascending order (bitonic sort; equal keys by position)
     const int anybad = __syncthreads_or(bad ? 1 : 0);
     if (warp != 0) return;
-    for (int w = 1; w < FS_WARPS; ++w) {
-        const uint32_t kv = mk[w * RCAP + lane];
-        push_lanes(sel, kv, ma[w * RCAP + lane], lane < mlen[w] && kv < sel.maxkey, lane);
-    }
-    // ascending order (rank sort; equal keys in slot order)
-    int rank = 0;
-    for (int j = 0; j < sel.len; ++j) {
-        const uint32_t kj = __shfl_sync(0xffffffffu, sel.key, j);
-        rank += (kj < sel.key) || (kj == sel.key && j < lane);
-    }
-    if (lane < sel.len) {
-        p.cand_d[q * RCAP + rank] = fkey_inv(sel.key);
-        p.cand_a[q * RCAP + rank] = sel.a;
+    const int n = min(cnt_s, p.ncap);   // round_end left at most ncap entries
+    uint32_t key = lane < n ? bk[lane] : 0xffffffffu, pos = lane < n ? bp[lane] : 0xffffffffu;
+    warp_sort32(key, pos, lane);
+    if (lane < n) {
+        p.cand_d[q * RCAP + lane] = fkey_inv(key);
+        p.cand_a[q * RCAP + lane] = pos;
     }
     if (lane == 0) {
-        p.cand_cnt[q] = (uint32_t)sel.len;
+        p.cand_cnt[q] = (uint32_t)n;
         p.cand_total[q] = flat0;
-        p.qbad[q] = (unsigned)anybad | (p.hard[q] ? 2u : 0u);
+        p.qbad[q] = (unsigned)(anybad | (flag_s ? 1 : 0)) | (p.hard[q] ? 2u : 0u);
         atomicAdd(&p.counters[2], (unsigned long long)flat0);
     }
 }
@@ -1321,6 +1428,40 @@ FScanFn scan_fn_w(size_t D) {
 }
 FScanFn scan_fn(size_t D, bool records) { return records ? scan_fn_w<true>(D) : scan_fn_w<false>(D); }
 
+#include "adc_pscan.cuh"
+
+typedef void (*PScanFn)(PScanParams);
+// W = D / 4 code words per vector, RW = words per vector in the list (records carry one more)
+PScanFn pscan_fn(size_t D, bool records) {
+    switch (D) {
+        case 4: return records ? pscan_kernel<1, 2> : pscan_kernel<1, 1>;
+        case 8: return records ? pscan_kernel<2, 3> : pscan_kernel<2, 2>;
+        case 12: return records ? pscan_kernel<3, 4> : pscan_kernel<3, 3>;
+        default: return nullptr;
+    }
+}
+// dynamic shared memory: the tables end at the absolute shared address PT_BASE + D * 16 KB; the dynamic
+// window starts after the 1 KB the system reserves and the kernel's static variables
+size_t pscan_smem_bytes(size_t D, size_t rb) {
+    (void)rb;
+    return PT_BASE + D * PT_STRIDE * PJ * sizeof(float) - 1024;
+}
+bool pscan_smem_ok(size_t D, size_t rb) {
+    return 2 * PJ * PB * sizeof(uint32_t) + (size_t)PW * 2 * 32 * rb + 2048 <= PT_BASE &&
+           pscan_smem_bytes(D, rb) + 1024 <= 227 * 1024;
+}
+constexpr int PSCAN_VCH = 16384;   // vectors per item (a multiple of 4)
+// upper bound of the number of items: sum_p ceil(count_p / PJ) * nv_p <= sum_p nv_p + (npairs / PJ) * max nv
+size_t pscan_items_bound(const fdb_index *ix, size_t npairs) {
+    size_t sum_nv = 0, max_nv = 0;
+    for (size_t p = 0; p < ix->P; ++p) {
+        const size_t nv = ((size_t)(ix->h_off[p + 1] - ix->h_off[p]) + PSCAN_VCH - 1) / PSCAN_VCH;
+        sum_nv += nv;
+        max_nv = std::max(max_nv, nv);
+    }
+    return 2 * sum_nv + (npairs / PJ + 1) * max_nv;   // two buckets per partition
+}
+
 }  // namespace
 
 }  // namespace fdb
@@ -1631,6 +1772,38 @@ int filter_query(fdb_index *ix, const float *d_q, size_t q_base, size_t nq, size
     const float coef = adc_coef(s, D, tc_g);
     const float eta3 = (float)(2.1 * ((double)s / 16.0 + 40.0 + (double)D) * U24);
 
+    // partition-major scan when the groups of 16 queries per partition fill up (adc_pscan.cuh)
+    const PScanFn pscan = pscan_fn(D, records);
+    const size_t psmem = pscan_smem_bytes(D, rb);
+    // (long lists only: a short list costs as much to scan as its 16 tables cost to load, and the
+    // query-major kernel loads a query's table once for all its lists)
+    const bool pscan_ok = pscan && C % 8 == 0 && C <= (size_t)PT_STRIDE && pscan_smem_ok(D, rb);
+    const size_t pscan_min_list = getenv("FDB_PSCAN_MIN_LIST") ? (size_t)atol(getenv("FDB_PSCAN_MIN_LIST")) : 3000;
+    bool use_pscan = pscan_ok && (double)std::min(chunk, nq) * (double)nprobe >= 8.0 * (double)ix->P &&
+                     ix->M >= pscan_min_list * ix->P;
+    if (const char *e = getenv("FDB_FILTER_SCAN")) use_pscan = pscan_ok && !strcmp(e, "partition");
+    // probe rank 0 first (two buckets per partition) only when both buckets fill their groups
+    const bool pscan_split = (double)std::min(chunk, nq) * (double)nprobe >= 64.0 * (double)ix->P && nprobe > 1 &&
+                             !getenv("FDB_PSCAN_NO_SPLIT");
+    if (use_pscan) {
+        const size_t bound = pscan_items_bound(ix, std::min(chunk, nq) * nprobe);
+        if (bound * PJ * PLK * 8 > (2ull << 30)) use_pscan = false;
+        else {
+            FDB_CUDA(cudaFuncSetAttribute(pscan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+            FDB_TRY(sl->pg_ctl.ensure(2 * ix->P + 1));
+            FDB_TRY(sl->pg_pstart.ensure(2 * ix->P + 1));
+            FDB_TRY(sl->pg_istart.ensure(2 * ix->P + 1));
+            FDB_TRY(sl->pg_desc.ensure(bound * PDESC));
+            FDB_TRY(sl->pg_slot.ensure(std::min(chunk, nq) * nprobe));
+            FDB_TRY(sl->pg_pairs.ensure(std::min(chunk, nq) * nprobe));
+            FDB_TRY(sl->pg_thr.ensure(nq));
+            FDB_TRY(sl->it_keys.ensure(bound * PJ * PLK));
+            FDB_TRY(sl->it_pos.ensure(bound * PJ * PLK));
+            FDB_TRY(sl->it_cnt.ensure(bound * PJ));
+            FDB_CUDA(cudaMemsetAsync(sl->pg_thr.p, 0xff, nq * sizeof(unsigned), st));
+        }
+    }
+
     for (size_t q0 = 0; q0 < nq; q0 += chunk) {
         const size_t nc = std::min(chunk, nq - q0);
         FDB_TRY(log->mark(3));
@@ -1671,8 +1844,68 @@ int filter_query(fdb_index *ix, const float *d_q, size_t q_base, size_t nq, size
         sp.qbad = sl->qbad.p;
         sp.hard = sl->hard.p;
         sp.counters = sl->counters.p;
-        scan<<<(unsigned)nc, FS_WARPS * 32, smem, st>>>(sp);
-        ctx->launches++;
+        if (!use_pscan) {
+            scan<<<(unsigned)nc, FS_WARPS * 32, smem, st>>>(sp);
+            ctx->launches++;
+            FDB_CHECK_LAUNCH();
+            continue;
+        }
+        // partition-major: group the chunk's pairs by partition, scan item by item, merge per query
+        const size_t P = ix->P, npairs = nc * nprobe;
+        FDB_CUDA(cudaMemsetAsync(sl->pg_ctl.p, 0, (2 * P + 1) * sizeof(uint32_t), st));
+        const uint32_t *chunk_probes = d_probes + q0 * nprobe;
+        pg_count_kernel<<<(unsigned)((npairs + 255) / 256), 256, 0, st>>>(chunk_probes, npairs, pscan_split ? (int)nprobe : 0, (int)P,
+                                                                          sl->pg_ctl.p, sl->pg_slot.p);
+        pg_scan_kernel<<<1, 1024, 0, st>>>(sl->pg_ctl.p, ix->part_off.p, (int)P, PSCAN_VCH, sl->pg_pstart.p, sl->pg_istart.p);
+        pg_scatter_kernel<<<(unsigned)((npairs + 255) / 256), 256, 0, st>>>(chunk_probes, sl->pg_slot.p, sl->pg_pstart.p, npairs,
+                                                                            pscan_split ? (int)nprobe : 0, (int)P, sl->pg_pairs.p);
+        pg_items_kernel<<<(unsigned)((2 * P + 3) / 4), 128, 0, st>>>(sl->pg_ctl.p, sl->pg_pstart.p, sl->pg_istart.p,
+                                                                     sl->pg_pairs.p, ix->part_off.p, (int)P, PSCAN_VCH,
+                                                                     sl->pg_desc.p);
+        PScanParams pp;
+        pp.G = sl->G.p;
+        pp.pc = fs->pc.p;
+        pp.Kq = sl->Kq.p;
+        pp.codes = sp.codes;
+        pp.part_start = sp.part_start;
+        pp.q0 = q0;
+        pp.nprobe = (int)nprobe;
+        pp.D = (int)D;
+        pp.C = (int)C;
+        pp.rb = (int)rb;
+        pp.ncap = ncap;
+        pp.desc = sl->pg_desc.p;
+        pp.nitems = sl->pg_istart.p + 2 * P;
+        pp.work = sl->pg_ctl.p + 2 * P;
+        pp.thrg = sl->pg_thr.p;
+        pp.item_keys = sl->it_keys.p;
+        pp.item_pos = sl->it_pos.p;
+        pp.item_cnt = sl->it_cnt.p;
+        const unsigned pgrid = (unsigned)std::min<size_t>(pscan_items_bound(ix, npairs), (size_t)ctx->sm_count);
+        pscan<<<pgrid, PW * 32, psmem, st>>>(pp);
+        PMergeParams mp;
+        mp.probes = d_probes;
+        mp.part_off = ix->part_off.p;
+        mp.pair_slot = sl->pg_slot.p;
+        mp.istart = sl->pg_istart.p;
+        mp.item_keys = sl->it_keys.p;
+        mp.item_pos = sl->it_pos.p;
+        mp.item_cnt = sl->it_cnt.p;
+        mp.q0 = q0;
+        mp.nc = nc;
+        mp.nprobe = (int)nprobe;
+        mp.ncap = ncap;
+        mp.vch = PSCAN_VCH;
+        mp.P = pscan_split ? (int)P : 0;
+        mp.cand_d = sl->cand_d.p;
+        mp.cand_a = sl->cand_a.p;
+        mp.cand_cnt = sl->cand_cnt.p;
+        mp.cand_total = sl->cand_total.p;
+        mp.qbad = sl->qbad.p;
+        mp.hard = sl->hard.p;
+        mp.counters = sl->counters.p;
+        pmerge_kernel<<<(unsigned)((nc + 3) / 4), 128, 0, st>>>(mp);
+        ctx->launches += 6;
         FDB_CHECK_LAUNCH();
     }
     FDB_TRY(log->mark(5));

@@ -601,6 +601,56 @@ def test_filter_path_equals_exact_pipeline_on_a_large_batch(eng, ctx, oracle, mo
     ix.close()
 
 
+@pytest.mark.parametrize("N,P,D,Cn,M,k,nprobe,nq", [
+    (1536, 100, 12, 256, 20000, 10, 5, 512),   # the README shape: ~26 queries per partition, two groups
+    (96, 64, 12, 256, 30000, 10, 8, 256),      # s = 8
+    (64, 9, 4, 256, 60, 5, 9, 64),             # fewer vectors than a candidate list holds, nprobe == P
+    (80, 12, 4, 104, 900, 24, 3, 128),         # largest k (candidate lists of 30: the RegTopK compaction), C < 256
+    (64, 3, 8, 64, 60000, 10, 2, 300),         # lists longer than one item's chunk of vectors, 200 queries per list
+    (48, 40, 12, 32, 9000, 3, 40, 100),        # every query probes every partition
+])
+@pytest.mark.parametrize("layout", ["records", "tables"])
+def test_partition_major_scan_bit_exact(eng, ctx, oracle, monkeypatch, layout, N, P, D, Cn, M, k, nprobe, nq):
+    """adc_pscan.cuh: the scan grouped by partition (16 queries per item) gives the reference's results."""
+    monkeypatch.setenv("FDB_FILTER_LAYOUT", layout)
+    monkeypatch.setenv("FDB_FILTER_SCAN", "partition")
+    coarse, cbs, off, codes = random_index(oracle, N, P, D, Cn, M, empty=(1,))
+    ix = eng.Index.create(ctx, coarse, cbs, off, codes.astype(np.uint8))
+    oix = oracle.QueryIndex(coarse, cbs, off, codes)
+    q = data(oracle, nq, N, SEED + 85)
+    for mode in (0, 1):
+        fast, exact, cand, scanned = _check_query(ix, oix, q, k, nprobe, mode)
+        assert fast + exact == nq
+        assert fast >= 0.9 * nq, (fast, exact)
+        assert cand <= 2 * (k + 1) * fast
+    ix.close()
+
+
+def test_partition_major_scan_on_clustered_data_and_large_batch(eng, ctx, oracle, monkeypatch):
+    monkeypatch.setenv("FDB_FILTER_SCAN", "partition")
+    N, P, D, Cn, M, k, nprobe = 96, 50, 12, 64, 8000, 5, 5
+    coarse, cbs, off, codes, q = _clustered_index(oracle, N, P, D, Cn, M, 11)
+    ix = eng.Index.create(ctx, coarse, cbs, off, codes.astype(np.uint8))
+    oix = oracle.QueryIndex(coarse, cbs, off, codes)
+    for mode in (0, 1):
+        fast, exact, cand, scanned = _check_query(ix, oix, q, k, nprobe, mode)
+        assert fast + exact == len(q) and fast >= 0.5 * len(q), (fast, exact)
+    ix.close()
+    # 4096 queries against the README shape: equal to the exact pipeline bit for bit
+    N, P, D, Cn, M, k, nprobe, nq = 1536, 100, 12, 256, 50000, 10, 5, 4096
+    coarse, cbs, off, codes = random_index(oracle, N, P, D, Cn, M)
+    ix = eng.Index.create(ctx, coarse, cbs, off, codes.astype(np.uint8))
+    q = data(oracle, nq, N, SEED + 80)
+    got = ix.query(q, k, nprobe)
+    assert ix.last_stats()[0] >= 0.99 * nq
+    monkeypatch.setenv("FDB_QUERY_EXACT", "1")
+    want = ix.query(q, k, nprobe)
+    monkeypatch.delenv("FDB_QUERY_EXACT")
+    for g, w in zip(got, want):
+        assert (g == w).all()
+    ix.close()
+
+
 def test_filter_path_hands_ties_and_bad_numbers_to_the_exact_pipeline(eng, ctx, oracle):
     # (a) duplicated code vectors: every distance is shared by many vectors -> NBestByKey history
     N, P, D, Cn, M = 64, 8, 4, 64, 3000
