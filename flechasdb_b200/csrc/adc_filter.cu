@@ -43,6 +43,7 @@ namespace fdb {
 
 struct FilterState {
     DevBuf<float> pc;            // [P][D][C]
+    DevBuf<float> pcmm;          // [P][D][2] min and max of every PC row (16-bit tables of adc_pscan.cuh)
     DevBuf<float> cbmax;         // [D]
     DevBuf<unsigned> bounds;     // float bits: [0] cb2, [1] pcmax
     DevBuf<uint8_t> rec;         // records (RECORDS layout), empty when the lists are long
@@ -77,6 +78,8 @@ struct FilterState {
         DevBuf<uint32_t> pg_pstart, pg_istart, pg_slot, pg_pairs, pg_desc;
         DevBuf<unsigned> pg_thr;     // [nq]
         DevBuf<uint32_t> it_keys, it_pos, it_cnt;
+        DevBuf<float> gmm;           // [chunk_q][D][2] min and max of every G row
+        DevBuf<unsigned> eadd;       // [nq] extra error of the 16-bit tables (float bits)
         DevBuf<unsigned long long> counters;  // [0] fallbacks, [1] exact candidates, [2] scanned vectors, [4..] reasons
         cudaStream_t stream = nullptr;
         cudaEvent_t done = nullptr;
@@ -1113,6 +1116,7 @@ struct FSelParams {
     const uint64_t *part_cstart;
     const uint32_t *probes;
     const float *Wq;
+    const unsigned *eadd;        // extra error per query (float bits) or null
     const float *cand_d;
     const uint32_t *cand_a, *cand_cnt, *cand_total;
     const unsigned *qbad;
@@ -1221,7 +1225,7 @@ __global__ void __launch_bounds__(128) fselect_kernel(FSelParams p) {
         // S = the k smallest approximations; max_S R <= (a_(k) + E)(1 + eta) =: Rmax >= the k-th smallest R,
         // and every v with R(v) <= Rmax (the reference's k best and anything tied with the k-th) has
         // A(v) <= Rmax / (1 - eta) + E
-        const float E = p.coef * p.Wq[q];
+        const float E = p.coef * p.Wq[q] + (p.eadd ? __uint_as_float(p.eadd[q]) : 0.0f);
         const float tau = __shfl_sync(0xffffffffu, a, k - 1);
         const float hi = (tau + E) * (1.0f + p.eta3) + E;
         const float thr = tau + BAND_SAFETY * (hi - tau);
@@ -1447,19 +1451,30 @@ size_t pscan_smem_bytes(size_t D, size_t rb) {
     return PT_BASE + D * PT_STRIDE * PJ * sizeof(float) - 1024;
 }
 bool pscan_smem_ok(size_t D, size_t rb) {
-    return 2 * PJ * PB * sizeof(uint32_t) + (size_t)PW * 2 * 32 * rb + 2048 <= PT_BASE &&
+    return 2 * PJ * PB * sizeof(uint32_t) + (size_t)PW * 2 * PCV * rb + 2048 <= PT_BASE &&
            pscan_smem_bytes(D, rb) + 1024 <= 227 * 1024;
 }
 constexpr int PSCAN_VCH = 16384;   // vectors per item (a multiple of 4)
 // upper bound of the number of items: sum_p ceil(count_p / PJ) * nv_p <= sum_p nv_p + (npairs / PJ) * max nv
-size_t pscan_items_bound(const fdb_index *ix, size_t npairs) {
+PScanFn pscan16_fn(size_t D) {
+    switch (D) {
+        case 4: return pscan16_kernel<1>;
+        case 8: return pscan16_kernel<2>;
+        case 12: return pscan16_kernel<3>;
+        default: return nullptr;
+    }
+}
+bool pscan16_smem_ok(size_t D) {
+    return 2 * QJ * QB * sizeof(uint32_t) + (size_t)PW * 2 * PCV * D + 6144 <= PT_BASE && pscan_smem_bytes(D, D) + 4096 <= 227 * 1024;
+}
+size_t pscan_items_bound(const fdb_index *ix, size_t npairs, size_t pj) {
     size_t sum_nv = 0, max_nv = 0;
     for (size_t p = 0; p < ix->P; ++p) {
         const size_t nv = ((size_t)(ix->h_off[p + 1] - ix->h_off[p]) + PSCAN_VCH - 1) / PSCAN_VCH;
         sum_nv += nv;
         max_nv = std::max(max_nv, nv);
     }
-    return 2 * sum_nv + (npairs / PJ + 1) * max_nv;   // two buckets per partition
+    return 2 * sum_nv + (npairs / pj + 1) * max_nv;   // two buckets per partition
 }
 
 }  // namespace
@@ -1515,6 +1530,10 @@ int filter_prepare(fdb_index *ix) {
     cbmax_kernel<<<(unsigned)D, 256, 0, st>>>(ix->codebooks.p, C, s, fs->cbmax.p, fs->bounds.p);
     pcmax_kernel<<<(unsigned)((P * 32 + 127) / 128), 128, 0, st>>>(fs->pc.p, P, D, C, fs->bounds.p);
     ctx->launches += 3;
+    FDB_CHECK_LAUNCH();
+    FDB_TRY(fs->pcmm.alloc(P * D * 2));
+    g_minmax_kernel<<<(unsigned)((P * D + 7) / 8), 256, 0, st>>>(fs->pc.p, P * D, (int)C, fs->pcmm.p);
+    ctx->launches++;
     FDB_CHECK_LAUNCH();
     float hb[2];
     FDB_CUDA(cudaMemcpyAsync(hb, fs->bounds.p, sizeof(hb), cudaMemcpyDeviceToHost, st));
@@ -1722,9 +1741,9 @@ int filter_batch_end(fdb_index *ix, size_t nq_total, const uint32_t **d_fb_q, co
     ix->last_stats[3] = fs->h_counters[2];
     if (getenv("FDB_FILTER_STATS"))
         fprintf(stderr, "[fdb filter] queries=%zu handed back=%llu: non-finite=%llu probe filter=%llu band=%llu "
-                        "list overflow=%llu exact tie=%llu; partitions evaluated exactly=%llu\n",
+                        "list overflow=%llu exact tie=%llu append overflow=%llu; partitions evaluated exactly=%llu\n",
                 nq_total, fs->h_counters[0], fs->h_counters[4], fs->h_counters[5], fs->h_counters[6],
-                fs->h_counters[7], fs->h_counters[8], fs->h_counters[3]);
+                fs->h_counters[7], fs->h_counters[8], fs->h_counters[9], fs->h_counters[3]);
     return FDB_OK;
 }
 
@@ -1772,34 +1791,52 @@ int filter_query(fdb_index *ix, const float *d_q, size_t q_base, size_t nq, size
     const float coef = adc_coef(s, D, tc_g);
     const float eta3 = (float)(2.1 * ((double)s / 16.0 + 40.0 + (double)D) * U24);
 
-    // partition-major scan when the groups of 16 queries per partition fill up (adc_pscan.cuh)
-    const PScanFn pscan = pscan_fn(D, records);
-    const size_t psmem = pscan_smem_bytes(D, rb);
-    // (long lists only: a short list costs as much to scan as its 16 tables cost to load, and the
-    // query-major kernel loads a query's table once for all its lists)
-    const bool pscan_ok = pscan && C % 8 == 0 && C <= (size_t)PT_STRIDE && pscan_smem_ok(D, rb);
+    // partition-major scan (adc_pscan.cuh) for long lists probed by many queries: a short list costs as
+    // much to scan as its tables cost to load, and the query-major kernel loads a query's table once for
+    // all its lists.  16-bit tables (32 queries per item) when the lists are compact codes and the candidate
+    // lists are short; f32 tables (16 queries per item) otherwise.
+    const size_t cq = std::min(chunk, nq);
+    const double pairs_per_list = (double)cq * (double)nprobe / (double)ix->P;
+    const bool p32_ok = pscan_fn(D, records) && C % 8 == 0 && C <= (size_t)PT_STRIDE && pscan_smem_ok(D, rb);
+    const bool p16_ok = !records && pscan16_fn(D) && C % 8 == 0 && C <= (size_t)PT_STRIDE && ncap <= 16 && pscan16_smem_ok(D);
     const size_t pscan_min_list = getenv("FDB_PSCAN_MIN_LIST") ? (size_t)atol(getenv("FDB_PSCAN_MIN_LIST")) : 3000;
-    bool use_pscan = pscan_ok && (double)std::min(chunk, nq) * (double)nprobe >= 8.0 * (double)ix->P &&
-                     ix->M >= pscan_min_list * ix->P;
-    if (const char *e = getenv("FDB_FILTER_SCAN")) use_pscan = pscan_ok && !strcmp(e, "partition");
+    const bool long_lists = ix->M >= pscan_min_list * ix->P;
+    // measured (DESIGN.md 4b, 10k-vector lists): from about 64 pairs per list on the partition-major kernels
+    // win: 16-bit tables 2.67 ms, f32 tables 3.19 ms, query-major 3.26 ms at 64; 19.1 / 23.0 / 26.4 ms at 128
+    bool use_p16 = p16_ok && long_lists && pairs_per_list >= 64.0;
+    bool use_pscan = use_p16 || (p32_ok && long_lists && pairs_per_list >= 64.0);
+    if (const char *e = getenv("FDB_FILTER_SCAN")) {   // "query" / "partition" / "partition16": forced (tests, profiling)
+        use_p16 = !strcmp(e, "partition16");
+        use_pscan = use_p16 || !strcmp(e, "partition");
+        if ((use_p16 && !p16_ok) || (use_pscan && !use_p16 && !p32_ok)) {
+            set_error("FDB_FILTER_SCAN=%s: this shape is not taken by that scan (D %zu, C %zu, k %zu, %s lists)", e, D, C, k,
+                      records ? "record" : "compact");
+            return FDB_ERR_UNSUPPORTED;
+        }
+    }
+    const size_t pj = use_p16 ? QJ : PJ;
+    const PScanFn pscan = use_p16 ? pscan16_fn(D) : pscan_fn(D, records);
+    const size_t psmem = pscan_smem_bytes(D, rb);
     // probe rank 0 first (two buckets per partition) only when both buckets fill their groups
-    const bool pscan_split = (double)std::min(chunk, nq) * (double)nprobe >= 64.0 * (double)ix->P && nprobe > 1 &&
-                             !getenv("FDB_PSCAN_NO_SPLIT");
+    const bool pscan_split = pairs_per_list >= 4.0 * (double)pj && nprobe > 1 && !getenv("FDB_PSCAN_NO_SPLIT");
+    FDB_TRY(sl->eadd.ensure(nq));
+    FDB_CUDA(cudaMemsetAsync(sl->eadd.p, 0, nq * sizeof(unsigned), st));
     if (use_pscan) {
-        const size_t bound = pscan_items_bound(ix, std::min(chunk, nq) * nprobe);
-        if (bound * PJ * PLK * 8 > (2ull << 30)) use_pscan = false;
+        const size_t bound = pscan_items_bound(ix, cq * nprobe, pj);
+        if (bound * pj * PLK * 8 > (2ull << 30)) use_pscan = false;
         else {
             FDB_CUDA(cudaFuncSetAttribute(pscan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
             FDB_TRY(sl->pg_ctl.ensure(2 * ix->P + 1));
             FDB_TRY(sl->pg_pstart.ensure(2 * ix->P + 1));
             FDB_TRY(sl->pg_istart.ensure(2 * ix->P + 1));
-            FDB_TRY(sl->pg_desc.ensure(bound * PDESC));
-            FDB_TRY(sl->pg_slot.ensure(std::min(chunk, nq) * nprobe));
-            FDB_TRY(sl->pg_pairs.ensure(std::min(chunk, nq) * nprobe));
+            FDB_TRY(sl->pg_desc.ensure(bound * (4 + pj)));
+            FDB_TRY(sl->pg_slot.ensure(cq * nprobe));
+            FDB_TRY(sl->pg_pairs.ensure(cq * nprobe));
             FDB_TRY(sl->pg_thr.ensure(nq));
-            FDB_TRY(sl->it_keys.ensure(bound * PJ * PLK));
-            FDB_TRY(sl->it_pos.ensure(bound * PJ * PLK));
-            FDB_TRY(sl->it_cnt.ensure(bound * PJ));
+            FDB_TRY(sl->it_keys.ensure(bound * pj * PLK));
+            FDB_TRY(sl->it_pos.ensure(bound * pj * PLK));
+            FDB_TRY(sl->it_cnt.ensure(bound * pj));
+            if (use_p16) FDB_TRY(sl->gmm.ensure(cq * D * 2));
             FDB_CUDA(cudaMemsetAsync(sl->pg_thr.p, 0xff, nq * sizeof(unsigned), st));
         }
     }
@@ -1856,12 +1893,12 @@ int filter_query(fdb_index *ix, const float *d_q, size_t q_base, size_t nq, size
         const uint32_t *chunk_probes = d_probes + q0 * nprobe;
         pg_count_kernel<<<(unsigned)((npairs + 255) / 256), 256, 0, st>>>(chunk_probes, npairs, pscan_split ? (int)nprobe : 0, (int)P,
                                                                           sl->pg_ctl.p, sl->pg_slot.p);
-        pg_scan_kernel<<<1, 1024, 0, st>>>(sl->pg_ctl.p, ix->part_off.p, (int)P, PSCAN_VCH, sl->pg_pstart.p, sl->pg_istart.p);
+        pg_scan_kernel<<<1, 1024, 0, st>>>(sl->pg_ctl.p, ix->part_off.p, (int)P, PSCAN_VCH, (int)pj, sl->pg_pstart.p, sl->pg_istart.p);
         pg_scatter_kernel<<<(unsigned)((npairs + 255) / 256), 256, 0, st>>>(chunk_probes, sl->pg_slot.p, sl->pg_pstart.p, npairs,
                                                                             pscan_split ? (int)nprobe : 0, (int)P, sl->pg_pairs.p);
         pg_items_kernel<<<(unsigned)((2 * P + 3) / 4), 128, 0, st>>>(sl->pg_ctl.p, sl->pg_pstart.p, sl->pg_istart.p,
                                                                      sl->pg_pairs.p, ix->part_off.p, (int)P, PSCAN_VCH,
-                                                                     sl->pg_desc.p);
+                                                                     (int)pj, sl->pg_desc.p);
         PScanParams pp;
         pp.G = sl->G.p;
         pp.pc = fs->pc.p;
@@ -1881,7 +1918,14 @@ int filter_query(fdb_index *ix, const float *d_q, size_t q_base, size_t nq, size
         pp.item_keys = sl->it_keys.p;
         pp.item_pos = sl->it_pos.p;
         pp.item_cnt = sl->it_cnt.p;
-        const unsigned pgrid = (unsigned)std::min<size_t>(pscan_items_bound(ix, npairs), (size_t)ctx->sm_count);
+        pp.gmm = sl->gmm.p;
+        pp.pcmm = fs->pcmm.p;
+        pp.eadd = sl->eadd.p;
+        if (use_p16) {
+            g_minmax_kernel<<<(unsigned)((nc * D + 7) / 8), 256, 0, st>>>(sl->G.p, nc * D, (int)C, sl->gmm.p);
+            ctx->launches++;
+        }
+        const unsigned pgrid = (unsigned)std::min<size_t>(pscan_items_bound(ix, npairs, pj), (size_t)ctx->sm_count);
         pscan<<<pgrid, PW * 32, psmem, st>>>(pp);
         PMergeParams mp;
         mp.probes = d_probes;
@@ -1897,6 +1941,7 @@ int filter_query(fdb_index *ix, const float *d_q, size_t q_base, size_t nq, size
         mp.ncap = ncap;
         mp.vch = PSCAN_VCH;
         mp.P = pscan_split ? (int)P : 0;
+        mp.pj = (int)pj;
         mp.cand_d = sl->cand_d.p;
         mp.cand_a = sl->cand_a.p;
         mp.cand_cnt = sl->cand_cnt.p;
@@ -1918,6 +1963,7 @@ int filter_query(fdb_index *ix, const float *d_q, size_t q_base, size_t nq, size
     fp.part_cstart = ix->part_cstart.p;
     fp.probes = d_probes;
     fp.Wq = sl->Wq.p;
+    fp.eadd = sl->eadd.p;
     fp.cand_d = sl->cand_d.p;
     fp.cand_a = sl->cand_a.p;
     fp.cand_cnt = sl->cand_cnt.p;
@@ -1976,7 +2022,16 @@ int filter_debug_band(fdb_index *ix, size_t nq, size_t nprobe, float *E, float *
     FDB_CUDA(cudaMemcpyAsync(cand_cnt, sl->cand_cnt.p, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     FDB_CUDA(cudaMemcpyAsync(probes, sl->last_probes, nq * nprobe * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     FDB_CUDA(cudaStreamSynchronize(st));
-    for (size_t i = 0; i < nq; ++i) E[i] = sl->last_coef * w[i];
+    std::vector<unsigned> ea(nq, 0u);
+    if (sl->eadd.p && sl->eadd.n >= nq) {
+        FDB_CUDA(cudaMemcpyAsync(ea.data(), sl->eadd.p, nq * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        FDB_CUDA(cudaStreamSynchronize(st));
+    }
+    for (size_t i = 0; i < nq; ++i) {
+        float e;
+        memcpy(&e, &ea[i], sizeof(e));
+        E[i] = sl->last_coef * w[i] + e;
+    }
     return FDB_OK;
 }
 

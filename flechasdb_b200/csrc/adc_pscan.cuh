@@ -23,7 +23,9 @@
 constexpr int PJ = 16;          // queries per group
 constexpr int PB = 96;          // append buffer entries per query
 constexpr int PLK = 32;         // entries kept per (item, query) in global memory (>= ncap)
-constexpr int PW = 16;          // warps per CTA
+constexpr int PW = 32;          // warps per CTA
+constexpr int PCV = 16;         // vectors per warp and round (staging chunk)
+constexpr int PFB = 4;          // float4 table loads in flight per lane during the fill
 constexpr int PT_STRIDE = 256;  // codes per table row in shared memory
 constexpr uint32_t PT_BASE = 0x8000;   // absolute shared address of the tables
 constexpr int PDESC = 4 + PJ;   // words of an item descriptor: partition, first vector, one past the last, members, pairs
@@ -45,6 +47,10 @@ struct PScanParams {
     unsigned *thrg;              // [nq] shared thresholds (order-preserving keys)
     uint32_t *item_keys, *item_pos;   // [item][PJ][PLK]
     uint32_t *item_cnt;               // [item][PJ]: count | bad << 31
+    // 16-bit tables (pscan16_kernel): min / max of every table row and the extra error bound per query
+    const float *gmm;            // [queries of this chunk][D][2]
+    const float *pcmm;           // [P][D][2]
+    unsigned *eadd;              // [nq] float bits, atomicMax
 };
 
 // ---- grouping: pairs by bucket -------------------------------------------------------------------
@@ -61,7 +67,7 @@ __global__ void __launch_bounds__(256) pg_count_kernel(const uint32_t *probes, s
 
 // exclusive scans over the buckets: pairs (pstart) and items (istart); one CTA
 __global__ void __launch_bounds__(1024) pg_scan_kernel(const uint32_t *count, const uint32_t *part_off, int P, int vch,
-                                                       uint32_t *pstart, uint32_t *istart) {
+                                                       int pj, uint32_t *pstart, uint32_t *istart) {
     __shared__ uint32_t wsum[2][32];
     __shared__ uint32_t carry[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -75,7 +81,7 @@ __global__ void __launch_bounds__(1024) pg_scan_kernel(const uint32_t *count, co
             c = count[b];
             const int p = b >= P ? b - P : b;
             const uint32_t np = part_off[p + 1] - part_off[p];
-            it = ((c + PJ - 1) / PJ) * ((np + (uint32_t)vch - 1) / (uint32_t)vch);
+            it = ((c + (uint32_t)pj - 1) / (uint32_t)pj) * ((np + (uint32_t)vch - 1) / (uint32_t)vch);
         }
         uint32_t sc = c, si = it;
 #pragma unroll
@@ -117,25 +123,24 @@ __global__ void __launch_bounds__(256) pg_scatter_kernel(const uint32_t *probes,
 // item descriptors: one warp per bucket walks the bucket's (group, chunk of vectors) items
 __global__ void __launch_bounds__(128) pg_items_kernel(const uint32_t *count, const uint32_t *pstart,
                                                        const uint32_t *istart, const uint32_t *pairs_of,
-                                                       const uint32_t *part_off, int P, int vch, uint32_t *desc) {
+                                                       const uint32_t *part_off, int P, int vch, int pj, uint32_t *desc) {
     const int b = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (b >= 2 * P) return;
     const int p = b >= P ? b - P : b;
     const uint32_t cnt = count[b], np = part_off[p + 1] - part_off[p];
-    const uint32_t nv = (np + (uint32_t)vch - 1) / (uint32_t)vch, ng = (cnt + PJ - 1) / PJ;
+    const uint32_t nv = (np + (uint32_t)vch - 1) / (uint32_t)vch, ng = (cnt + (uint32_t)pj - 1) / (uint32_t)pj;
     for (uint32_t it = 0; it < ng * nv; ++it) {
         const uint32_t g = it / nv, c = it - g * nv;
-        const uint32_t members = min((uint32_t)PJ, cnt - g * PJ);
-        uint32_t *d = desc + (size_t)(istart[b] + it) * PDESC;
+        const uint32_t members = min((uint32_t)pj, cnt - g * (uint32_t)pj);
+        uint32_t *d = desc + (size_t)(istart[b] + it) * (4 + pj);
         if (lane == 0) d[0] = (uint32_t)p;
         if (lane == 1) d[1] = c * (uint32_t)vch;
         if (lane == 2) d[2] = min(np, (c + 1) * (uint32_t)vch);
         if (lane == 3) d[3] = members;
-        if (lane >= 4 && lane < 4 + PJ) d[lane] = (uint32_t)(lane - 4) < members ? pairs_of[pstart[b] + g * PJ + lane - 4] : 0u;
+        for (uint32_t m = lane; m < (uint32_t)pj; m += 32) d[4 + m] = m < members ? pairs_of[pstart[b] + g * pj + m] : 0u;
     }
 }
 
-// ---- the scan -----------------------------------------------------------------------------------
 // shared-space loads with explicit 32-bit addresses (the generic-pointer path recomputes the shared window
 // base and adds it per access)
 template <int IMM>
@@ -180,24 +185,24 @@ __global__ void __launch_bounds__(PW * 32, 1) pscan_kernel(PScanParams p) {
     // 16 KB of one division), so a look-up address is (code << 6) | (lane's 4 j) plus an immediate: no add
     uint32_t *bkeys = reinterpret_cast<uint32_t *>(psm);                         // [PJ][PB]
     uint32_t *bpos = bkeys + PJ * PB;
-    unsigned char *stage = reinterpret_cast<unsigned char *>(bpos + PJ * PB);    // [PW][2][32 * RB]
+    unsigned char *stage = reinterpret_cast<unsigned char *>(bpos + PJ * PB);    // [PW][2][PCV * RB]
     const uint32_t psm_addr = (uint32_t)__cvta_generic_to_shared(psm);
     float *T = reinterpret_cast<float *>(psm + (PT_BASE - psm_addr));           // [D][256][PJ]
     uint32_t dyn_size;
     asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn_size));
-    if (psm_addr + 2 * PJ * PB * 4 + PW * 2 * 32 * RB > PT_BASE || PT_BASE + (uint32_t)D * PT_STRIDE * PJ * 4 > psm_addr + dyn_size)
+    if (psm_addr + 2 * PJ * PB * 4 + PW * 2 * PCV * RB > PT_BASE || PT_BASE + (uint32_t)D * PT_STRIDE * PJ * 4 > psm_addr + dyn_size)
         __trap();
     __shared__ int bcnt[PJ];
     __shared__ unsigned bthr[PJ], bflag[PJ];
     __shared__ uint32_t bq[PJ];      // query (index into Kq / thrg) of member j
-    __shared__ unsigned s_next, s_fast;
+    __shared__ unsigned s_next;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int j = lane & (PJ - 1), h = lane >> 4;
     const int DC = D * C;
     const bool cpow2 = (C & (C - 1)) == 0;
     const int cshift = 31 - __clz(C);
     const unsigned nitems = *p.nitems;
-    unsigned char *mystage = stage + (size_t)warp * 2 * 32 * RB;
+    unsigned char *mystage = stage + (size_t)warp * 2 * PCV * RB;
     uint32_t tlane = (uint32_t)j * 4u;
     asm volatile("" : "+r"(tlane));   // opaque: keeps (code << 6 & mask) | tlane one LOP3 per look-up
 
@@ -234,14 +239,11 @@ __global__ void __launch_bounds__(PW * 32, 1) pscan_kernel(PScanParams p) {
             bq[tid] = (uint32_t)qg;
             bthr[tid] = t0;
             if (active && !(fabsf(K) < 1e30f)) bflag[tid] = 1u;
-            // every member already has a threshold from another of its lists: no need to start with small rounds
-            const unsigned inf = __ballot_sync(0x0000ffffu, active && t0 == 0xffffffffu);
-            if (tid == 0) s_fast = inf == 0u;
         }
         // ---- tables: T[d][c][j] = G[q_j][d][c] (+ PC[part][d][c]); lane (j, h) moves the float4 2u + h of
         //      query j, a warp the 32 float4 of one u; FB of them in flight per lane
         {
-            constexpr int FB = 12;
+            constexpr int FB = PFB;
             // inactive lanes copy row 0 of the chunk (never looked at): no predicates in the loop
             const float4 *gq = reinterpret_cast<const float4 *>(p.G + (size_t)(active ? ql : 0u) * DC);
             const float4 *pcp = reinterpret_cast<const float4 *>(p.pc + (size_t)part * DC);
@@ -292,7 +294,7 @@ __global__ void __launch_bounds__(PW * 32, 1) pscan_kernel(PScanParams p) {
         const Desc nxt = load_desc(next_item);   // consumed at the top of the next iteration
         // ---- rounds
         unsigned mythr = bthr[j];
-        int rs = v0, rsize = s_fast ? PW * 32 : PB - PLK, slot = 0;
+        int rs = v0, rsize = PB - PLK, slot = 0;   // doubling rounds always: a threshold inherited from another list may be loose
         auto warp_range = [&](int rs_, int re_, int &b, int &e) {
             const int cnt_r = re_ - rs_;
             const int per = ((cnt_r + PW * 4 - 1) / (PW * 4)) * 4;
@@ -305,7 +307,7 @@ __global__ void __launch_bounds__(PW * 32, 1) pscan_kernel(PScanParams p) {
             if (e > b) {
                 const size_t n16 = ((size_t)(e - b) * RB + 15) >> 4;
                 const unsigned char *src = lst + (size_t)b * RB;
-                unsigned char *dst = mystage + (size_t)sl * 32 * RB;
+                unsigned char *dst = mystage + (size_t)sl * PCV * RB;
                 for (size_t i = lane; i < n16; i += 32) cp_async16(dst + 16 * i, src + 16 * i);
             }
             cp_async_commit();
@@ -314,13 +316,13 @@ __global__ void __launch_bounds__(PW * 32, 1) pscan_kernel(PScanParams p) {
         int total_seen = 0;
         while (rs < v1) {
             const int re = min(v1, rs + rsize);
-            const int nrs = re, nrsize = min(PW * 32, max(rsize, total_seen + (re - rs)));
+            const int nrs = re, nrsize = min(PW * PCV, max(rsize, total_seen + (re - rs)));
             issue(nrs, min(v1, nrs + nrsize), slot ^ 1);   // next round's codes travel during this one
             cp_async_wait<1>();
             __syncwarp();
             int b, e;
             warp_range(rs, re, b, e);
-            const uint32_t cs_addr = (uint32_t)__cvta_generic_to_shared(mystage) + (uint32_t)(slot * 32 * RB);
+            const uint32_t cs_addr = (uint32_t)__cvta_generic_to_shared(mystage) + (uint32_t)(slot * PCV * RB);
             const int nvec = e - b;
 #pragma unroll 2
             for (int vi = h; vi < nvec; vi += 2) {
@@ -339,7 +341,7 @@ __global__ void __launch_bounds__(PW * 32, 1) pscan_kernel(PScanParams p) {
                         bkeys[j * PB + i] = key;
                         bpos[j * PB + i] = (uint32_t)(b + vi);
                     } else {
-                        bflag[j] = 1u;
+                        bflag[j] = 2u;   // overflow
                     }
                 }
             }
@@ -377,12 +379,307 @@ __global__ void __launch_bounds__(PW * 32, 1) pscan_kernel(PScanParams p) {
             }
             const uint32_t mx = __reduce_max_sync(0xffffffffu, kv);
             if (lane == 0) {
-                p.item_cnt[(size_t)item * PJ + jj] = (uint32_t)n | (bflag[jj] ? 0x80000000u : 0u);
+                p.item_cnt[(size_t)item * PJ + jj] = (uint32_t)n | (bflag[jj] << 30);   // bit 30: non-finite, bit 31: overflow
                 if (n == p.ncap) atomicMin(&p.thrg[bq[jj]], mx);   // ncap vectors of the query are <= mx
                 bflag[jj] = 0u;
             }
         }
         __syncthreads();   // T, the buffers and s_next are reused by the next item
+        item = next_item;
+        cur = nxt;
+    }
+}
+
+// ---- 16-bit tables: 32 queries per item, one vector per warp step ---------------------------------
+// The f32 kernel above is bound by shared-memory wavefronts (1.5 per look-up of 2 vectors x 16 queries).
+// Here the table entries are 16-bit fixed point,
+//     u[d][c][j] = round((T[d][c] - m_jd) / delta_j),   m_jd <= min_c T,   delta_j = max_d range_jd / 65535,
+// so the 32 queries' entries of one (d, c) are 64 contiguous bytes: a warp step is ONE vector for 32 queries,
+// a look-up is one conflict-free wavefront and the sum over the divisions is exact (integers):
+//     A'(v) = base_j + delta_j * sum_d u,    base_j = K_j + sum_d m_jd,    |A' - A| <= D delta_j / 2 (+ roundings).
+// m and the ranges come from the min / max of G[q][d][.] (g_minmax_kernel, once per batch) and of PC[p][d][.]
+// (once per index): bounds, not the exact extremes of the sum, so delta is at most twice the optimum.  The
+// extra error is handed to fselect_kernel per query (eadd), which adds it to the band.
+constexpr int QJ = 32;          // queries per group
+constexpr int QB = 48;          // append buffer entries per query (candidate lists of at most 16)
+
+// min and max of every row of `nrows` rows of C floats; one warp per row
+__global__ void __launch_bounds__(256) g_minmax_kernel(const float *a, size_t nrows, int C, float *mm) {
+    const size_t row = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= nrows) return;
+    float mn = INFINITY, mx = -INFINITY;
+    for (int c = lane; c < C; c += 32) {
+        const float v = a[row * C + c];
+        mn = fminf(mn, v);
+        mx = fmaxf(mx, v);
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, off));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    }
+    if (lane == 0) mm[2 * row] = mn, mm[2 * row + 1] = mx;
+}
+
+template <int IMM>
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+    uint32_t v;
+    asm("ld.shared.u16 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(IMM));
+    return v;
+}
+template <int WI>
+__device__ __forceinline__ uint32_t lookup4_u16(uint32_t x, uint32_t tlane) {
+    constexpr int DV = PT_STRIDE * QJ * 2;
+    const uint32_t s0 = lds_u16<PT_BASE + (4 * WI) * DV>(and_or(x << 6, tlane));
+    const uint32_t s1 = lds_u16<PT_BASE + (4 * WI + 1) * DV>(and_or(x >> 2, tlane));
+    const uint32_t s2 = lds_u16<PT_BASE + (4 * WI + 2) * DV>(and_or(x >> 10, tlane));
+    const uint32_t s3 = lds_u16<PT_BASE + (4 * WI + 3) * DV>(and_or(x >> 18, tlane));
+    return (s0 + s1) + (s2 + s3);
+}
+
+template <int W>
+__global__ void __launch_bounds__(PW * 32, 1) pscan16_kernel(PScanParams p) {
+    constexpr int QD = 4 + QJ;
+    extern __shared__ __align__(16) unsigned char psm[];
+    const int D = p.D, C = p.C, RB = p.rb;   // compact codes: RB == D == 4 W
+    uint32_t *bkeys = reinterpret_cast<uint32_t *>(psm);                         // [QJ][QB]
+    uint32_t *bpos = bkeys + QJ * QB;
+    unsigned char *stage = reinterpret_cast<unsigned char *>(bpos + QJ * QB);    // [PW][2][PCV * RB]
+    const uint32_t psm_addr = (uint32_t)__cvta_generic_to_shared(psm);
+    unsigned short *T = reinterpret_cast<unsigned short *>(psm + (PT_BASE - psm_addr));   // [D][256][QJ]
+    uint32_t dyn_size;
+    asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn_size));
+    if (psm_addr + 2 * QJ * QB * 4 + PW * 2 * PCV * RB > PT_BASE || PT_BASE + (uint32_t)D * PT_STRIDE * QJ * 2 > psm_addr + dyn_size)
+        __trap();
+    __shared__ int bcnt[QJ];
+    __shared__ unsigned bthr[QJ], bflag[QJ];
+    __shared__ uint32_t bq[QJ];
+    __shared__ float qm[QJ][4 * W], qr[QJ][4 * W];   // lower bound m_jd (later m_jd / delta_j) and range of every table row
+    __shared__ float qinv[QJ], qdelta[QJ], qbase[QJ];
+    __shared__ unsigned s_next;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int DC = D * C;
+    const bool cpow2 = (C & (C - 1)) == 0;
+    const int cshift = 31 - __clz(C);
+    const unsigned nitems = *p.nitems;
+    unsigned char *mystage = stage + (size_t)warp * 2 * PCV * RB;
+    uint32_t tlane = (uint32_t)lane * 2u;
+    asm volatile("" : "+r"(tlane));
+
+    struct Desc {
+        uint32_t part, v0, v1, members, pair;
+    };
+    auto load_desc = [&](unsigned item) {
+        Desc d = {0u, 0u, 0u, 0u, 0u};
+        if (item < nitems) {
+            const uint32_t *g = p.desc + (size_t)item * QD;
+            d.part = __ldg(g), d.v0 = __ldg(g + 1), d.v1 = __ldg(g + 2), d.members = __ldg(g + 3), d.pair = __ldg(g + 4 + lane);
+        }
+        return d;
+    };
+    if (tid == 0) s_next = atomicAdd(p.work, 1u);
+    if (tid < QJ) bflag[tid] = 0u;
+    __syncthreads();
+    unsigned item = s_next;
+    Desc cur = load_desc(item);
+
+    while (item < nitems) {
+        unsigned grabbed = 0;
+        if (tid == 0) grabbed = atomicAdd(p.work, 1u);
+        const int part = (int)cur.part, v0 = (int)cur.v0, v1 = (int)cur.v1, members = (int)cur.members;
+        const bool active = lane < members;                                  // lane = member j
+        const uint32_t ql = cur.pair / (uint32_t)p.nprobe;
+        const size_t qg = p.q0 + ql;
+        const float K = active ? __ldg(&p.Kq[qg * p.nprobe + (cur.pair - ql * p.nprobe)]) : 0.0f;
+        const unsigned char *lst = p.codes + p.part_start[part];
+        // ---- quantisation: warp d takes division d of the 32 members
+        for (int d = warp; d < D; d += PW) {
+            float m = 0.0f, r = 0.0f;
+            if (active) {
+                const float2 g = __ldg(reinterpret_cast<const float2 *>(p.gmm) + (size_t)ql * D + d);
+                const float2 c = __ldg(reinterpret_cast<const float2 *>(p.pcmm) + (size_t)part * D + d);
+                m = g.x + c.x;
+                r = (g.y - g.x) + (c.y - c.x);
+            }
+            qm[lane][d] = m;
+            qr[lane][d] = r;
+        }
+        if (tid < QJ) {
+            const unsigned t0 = active ? __ldcg(&p.thrg[qg]) : 0u;
+            bcnt[tid] = 0;
+            bq[tid] = (uint32_t)qg;
+            bthr[tid] = t0;
+        }
+        __syncthreads();
+        if (tid < QJ) {
+            float rmax = 0.0f, rsum = 0.0f, msum = 0.0f, mabs = 0.0f;
+            for (int d = 0; d < D; ++d) {
+                rmax = fmaxf(rmax, qr[tid][d]);
+                rsum += qr[tid][d];
+                msum += qm[tid][d];
+                mabs += fabsf(qm[tid][d]);
+            }
+            const float delta = fmaxf(rmax * (1.0001f / 65535.0f), 1e-30f);
+            const float inv = 1.0f / delta;
+            qdelta[tid] = delta;
+            qinv[tid] = active ? inv : 0.0f;
+            qbase[tid] = K + msum;
+            for (int d = 0; d < D; ++d) qm[tid][d] = active ? qm[tid][d] * inv : 0.0f;
+            if (active) {
+                // per entry |m + delta u - t| <= delta / 2 + 3 ulp(|m| + range) (the scaled difference is formed
+                // from rounded 1 / delta and m / delta); then the roundings of base and of the final fma
+                const float qerr = (float)D * delta * 0.5001f +
+                                   (float)(D + 8) * 5.9604645e-08f * (fabsf(K) + mabs + rsum + delta * 65535.0f * (float)D);
+                if (!(fabsf(K) < 1e30f) || !(qerr < 1e30f) || !(fabsf(msum) < 1e30f)) bflag[tid] = 1u;
+                else atomicMax(&p.eadd[qg], __float_as_uint(qerr));
+            }
+        }
+        __syncthreads();
+        // ---- tables: lane (j16, h) moves the float4 2u + h of the rows j16 and j16 + 16
+        {
+            constexpr int FB = PFB;
+            const int j16 = lane & 15, h = lane >> 4;
+            const int units = DC >> 3;
+            const float4 *pcp = reinterpret_cast<const float4 *>(p.pc + (size_t)part * DC);
+            bool bad = false;
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                const int row = j16 + 16 * half;
+                const uint32_t rpair = __shfl_sync(0xffffffffu, cur.pair, row);
+                const bool ract = row < members;
+                const float4 *gq = reinterpret_cast<const float4 *>(p.G + (size_t)(ract ? rpair / (uint32_t)p.nprobe : 0u) * DC);
+                const float inv = qinv[row];
+                auto put = [&](int u, const float4 &t) {
+                    const int e0 = 4 * (2 * u + h);
+                    const int d = cpow2 ? e0 >> cshift : e0 / C;
+                    const int c0 = e0 - d * C;
+                    bad |= ract && !(fabsf(t.x) + fabsf(t.y) + fabsf(t.z) + fabsf(t.w) < 1e30f);
+                    const float mi = qm[row][d];
+                    // (T - m) / delta in [0, 65535.x]; saturating conversion
+                    const unsigned ux = __float2uint_rn(fminf(fmaxf(fmaf(t.x, inv, -mi), 0.0f), 65535.0f));
+                    const unsigned uy = __float2uint_rn(fminf(fmaxf(fmaf(t.y, inv, -mi), 0.0f), 65535.0f));
+                    const unsigned uz = __float2uint_rn(fminf(fmaxf(fmaf(t.z, inv, -mi), 0.0f), 65535.0f));
+                    const unsigned uw = __float2uint_rn(fminf(fmaxf(fmaf(t.w, inv, -mi), 0.0f), 65535.0f));
+                    unsigned short *dst = T + ((size_t)d * PT_STRIDE + c0) * QJ + row;
+                    unsigned short *de = dst + h * QJ, *dod = dst - h * QJ;   // the halves store different parities
+                    de[0] = (unsigned short)(h ? uy : ux);
+                    dod[QJ] = (unsigned short)(h ? ux : uy);
+                    de[2 * QJ] = (unsigned short)(h ? uw : uz);
+                    dod[3 * QJ] = (unsigned short)(h ? uz : uw);
+                };
+                int u0 = warp;
+                for (; u0 + (FB - 1) * PW < units; u0 += PW * FB) {
+                    float4 t[FB];
+#pragma unroll
+                    for (int i = 0; i < FB; ++i) t[i] = __ldg(gq + 2 * (u0 + i * PW) + h);
+#pragma unroll
+                    for (int i = 0; i < FB; ++i) {
+                        const float4 x = __ldg(pcp + 2 * (u0 + i * PW) + h);
+                        t[i] = make_float4(t[i].x + x.x, t[i].y + x.y, t[i].z + x.z, t[i].w + x.w);
+                    }
+#pragma unroll
+                    for (int i = 0; i < FB; ++i) put(u0 + i * PW, t[i]);
+                }
+                for (; u0 < units; u0 += PW) {
+                    float4 t = __ldg(gq + 2 * u0 + h);
+                    const float4 x = __ldg(pcp + 2 * u0 + h);
+                    t = make_float4(t.x + x.x, t.y + x.y, t.z + x.z, t.w + x.w);
+                    put(u0, t);
+                }
+                if (bad) bflag[row] = 1u;
+                bad = false;
+            }
+        }
+        if (tid == 0) s_next = grabbed;
+        __syncthreads();
+        const unsigned next_item = s_next;
+        const Desc nxt = load_desc(next_item);
+        // ---- rounds
+        unsigned mythr = bthr[lane];
+        const float mydelta = qdelta[lane], mybase = qbase[lane];
+        int rs = v0, rsize = QB - 16, slot = 0;   // doubling rounds always: a threshold inherited from another list may be loose
+        auto warp_range = [&](int rs_, int re_, int &b, int &e) {
+            const int cnt_r = re_ - rs_;
+            const int per = ((cnt_r + PW * 4 - 1) / (PW * 4)) * 4;
+            b = min(re_, rs_ + warp * per);
+            e = min(re_, b + per);
+        };
+        auto issue = [&](int rs_, int re_, int sl) {
+            int b, e;
+            warp_range(rs_, re_, b, e);
+            if (e > b) {
+                const int n16 = ((e - b) * RB + 15) >> 4;
+                const unsigned char *src = lst + (size_t)b * RB;
+                unsigned char *dst = mystage + (size_t)sl * PCV * RB;
+                for (int i = lane; i < n16; i += 32) cp_async16(dst + 16 * i, src + 16 * i);
+            }
+            cp_async_commit();
+        };
+        issue(rs, min(v1, rs + rsize), 0);
+        int total_seen = 0;
+        while (rs < v1) {
+            const int re = min(v1, rs + rsize);
+            // a round holds at most half of what has been seen: ~ncap / 2 new entries expected (the count is
+            // over-dispersed: the threshold is itself an order statistic), QB - ncap = 32 slots of head room
+            const int nrs = re, nrsize = min(PW * PCV, max(QB - 16, ((total_seen + (re - rs)) >> 1) & ~3));
+            issue(nrs, min(v1, nrs + nrsize), slot ^ 1);
+            cp_async_wait<1>();
+            __syncwarp();
+            int b, e;
+            warp_range(rs, re, b, e);
+            const uint32_t cs_addr = (uint32_t)__cvta_generic_to_shared(mystage) + (uint32_t)(slot * PCV * RB);
+            const int nvec = e - b;
+#pragma unroll 4
+            for (int vi = 0; vi < nvec; ++vi) {
+                uint32_t cw[W];
+                lds_words<W>(cs_addr + (uint32_t)(vi * RB), cw);   // the same address in every lane: a broadcast
+                uint32_t S = lookup4_u16<0>(cw[0], tlane);
+                if (W > 1) S += lookup4_u16<1>(cw[W > 1 ? 1 : 0], tlane);
+                if (W > 2) S += lookup4_u16<2>(cw[W > 2 ? 2 : 0], tlane);
+                const uint32_t key = fkey(fmaf(mydelta, (float)S, mybase));
+                if (key < mythr) {
+                    const int i = atomicAdd(&bcnt[lane], 1);
+                    if (i < QB) {
+                        bkeys[lane * QB + i] = key;
+                        bpos[lane * QB + i] = (uint32_t)(b + vi);
+                    } else {
+                        bflag[lane] = 2u;   // overflow
+                    }
+                }
+            }
+            total_seen += re - rs;
+            rs = re;
+            rsize = nrsize;
+            slot ^= 1;
+            __syncthreads();
+            for (int jj = warp; jj < members; jj += PW) {
+                const int n = min(bcnt[jj], QB);
+                if (n > p.ncap) {
+                    const int kept = cut_to_smallest(bkeys + jj * QB, bpos + jj * QB, n, p.ncap, &bthr[jj], lane);
+                    if (lane == 0) bcnt[jj] = kept;
+                }
+            }
+            __syncthreads();
+            mythr = bthr[lane];
+        }
+        cp_async_wait<0>();
+        for (int jj = warp; jj < members; jj += PW) {
+            const int n = bcnt[jj];
+            const size_t o = ((size_t)item * QJ + jj) * PLK;
+            const uint32_t kv = lane < n ? bkeys[jj * QB + lane] : 0u;
+            if (lane < n) {
+                p.item_keys[o + lane] = kv;
+                p.item_pos[o + lane] = bpos[jj * QB + lane];
+            }
+            const uint32_t mx = __reduce_max_sync(0xffffffffu, kv);
+            if (lane == 0) {
+                p.item_cnt[(size_t)item * QJ + jj] = (uint32_t)n | (bflag[jj] << 30);
+                if (n == p.ncap) atomicMin(&p.thrg[bq[jj]], mx);
+                bflag[jj] = 0u;
+            }
+        }
+        __syncthreads();
         item = next_item;
         cur = nxt;
     }
@@ -396,7 +693,7 @@ struct PMergeParams {
     const uint32_t *istart;      // [2P + 1]
     const uint32_t *item_keys, *item_pos, *item_cnt;
     size_t q0, nc;
-    int nprobe, ncap, vch, P;
+    int nprobe, ncap, vch, P, pj;
     float *cand_d;
     uint32_t *cand_a, *cand_cnt, *cand_total;
     unsigned *qbad;
@@ -417,15 +714,15 @@ __global__ void __launch_bounds__(128) pmerge_kernel(PMergeParams p) {
         const uint32_t part = p.probes[q * p.nprobe + pr];
         const uint32_t np = p.part_off[part + 1] - p.part_off[part];
         const uint32_t slot = p.pair_slot[ql * p.nprobe + pr];
-        const uint32_t g = slot / PJ, jj = slot % PJ;
+        const uint32_t g = slot / (uint32_t)p.pj, jj = slot % (uint32_t)p.pj;
         const uint32_t nv = (np + (uint32_t)p.vch - 1) / (uint32_t)p.vch;
         const size_t first = p.istart[part + (pr ? (uint32_t)p.P : 0u)];
         for (uint32_t c = 0; c < nv; ++c) {
             const size_t item = first + (size_t)g * nv + c;
-            const uint32_t cf = p.item_cnt[item * PJ + jj];
+            const uint32_t cf = p.item_cnt[item * p.pj + jj];
             const int cnt = (int)(cf & 0xffffu);
-            bad |= cf >> 31;
-            const size_t o = (item * PJ + jj) * PLK;
+            bad |= cf >> 30;
+            const size_t o = (item * p.pj + jj) * PLK;
             const uint32_t kv = lane < cnt ? p.item_keys[o + lane] : 0xffffffffu;
             const uint32_t pv = lane < cnt ? p.item_pos[o + lane] : 0u;
             push_lanes(sel, kv, flat0 + pv, lane < cnt && kv < sel.maxkey, lane);
@@ -446,5 +743,6 @@ __global__ void __launch_bounds__(128) pmerge_kernel(PMergeParams p) {
         p.cand_total[q] = flat0;
         p.qbad[q] = (bad ? 1u : 0u) | (p.hard[q] ? 2u : 0u);
         atomicAdd(&p.counters[2], (unsigned long long)flat0);
+        if (bad & 2u) atomicAdd(&p.counters[9], 1ull);   // append buffer overflow
     }
 }

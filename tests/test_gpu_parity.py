@@ -626,6 +626,36 @@ def test_partition_major_scan_bit_exact(eng, ctx, oracle, monkeypatch, layout, N
     ix.close()
 
 
+@pytest.mark.parametrize("N,P,D,Cn,M,k,nprobe,nq", [
+    (1536, 100, 12, 256, 20000, 10, 5, 512),   # the README shape
+    (96, 64, 12, 256, 30000, 10, 8, 256),      # s = 8
+    (64, 9, 4, 256, 60, 5, 9, 64),             # fewer vectors than a candidate list holds, nprobe == P
+    (64, 3, 8, 64, 60000, 10, 2, 300),         # lists longer than one item's chunk of vectors, 200 queries per list
+    (48, 40, 12, 32, 9000, 3, 40, 100),        # every query probes every partition
+])
+def test_partition_major_scan_16_bit_tables(eng, ctx, oracle, monkeypatch, N, P, D, Cn, M, k, nprobe, nq):
+    """pscan16_kernel: 16-bit fixed-point tables, 32 queries per item; the quantisation error widens the band."""
+    monkeypatch.setenv("FDB_FILTER_LAYOUT", "tables")
+    monkeypatch.setenv("FDB_FILTER_SCAN", "partition16")
+    coarse, cbs, off, codes = random_index(oracle, N, P, D, Cn, M, empty=(1,))
+    ix = eng.Index.create(ctx, coarse, cbs, off, codes.astype(np.uint8))
+    oix = oracle.QueryIndex(coarse, cbs, off, codes)
+    q = data(oracle, nq, N, SEED + 86)
+    for mode in (0, 1):
+        fast, exact, cand, scanned = _check_query(ix, oix, q, k, nprobe, mode)
+        assert fast + exact == nq
+        assert fast >= 0.9 * nq, (fast, exact)
+        assert cand <= 2 * (k + 1) * fast
+    ix.close()
+    # clustered data far from the origin: distances span orders of magnitude
+    coarse, cbs, off, codes, q = _clustered_index(oracle, 96, 50, 12, 64, 8000, 11)
+    ix = eng.Index.create(ctx, coarse, cbs, off, codes.astype(np.uint8))
+    oix = oracle.QueryIndex(coarse, cbs, off, codes)
+    fast, exact, cand, scanned = _check_query(ix, oix, q, 5, 5, 0)
+    assert fast + exact == len(q) and fast >= 0.5 * len(q), (fast, exact)
+    ix.close()
+
+
 def test_partition_major_scan_on_clustered_data_and_large_batch(eng, ctx, oracle, monkeypatch):
     monkeypatch.setenv("FDB_FILTER_SCAN", "partition")
     N, P, D, Cn, M, k, nprobe = 96, 50, 12, 64, 8000, 5, 5
