@@ -1513,7 +1513,8 @@ int filter_prepare(fdb_index *ix) {
     const size_t N = ix->N;
     const size_t kc = std::min<size_t>(P, 256), ntiles = (P + kc - 1) / kc;
     fs->tc_coarse = tc_shape_ok(kc, N, N) && !getenv("FDB_FILTER_NO_TC_COARSE");
-    fs->tc_g = tc_shape_ok(C, s, N) && C % 64 == 0 && !getenv("FDB_FILTER_NO_TC_TABLES");
+    // (tables: s % 64 == 0 only, so that the rows' tensor map -- chunk size by N -- serves both GEMMs)
+    fs->tc_g = tc_shape_ok(C, s, N) && s % 64 == 0 && C % 64 == 0 && !getenv("FDB_FILTER_NO_TC_TABLES");
     FDB_TRY(fs->mu.alloc(N));
     FDB_CUDA(cudaMemsetAsync(fs->mu.p, 0, N * sizeof(float), st));
     if (fs->tc_coarse || fs->tc_g) {

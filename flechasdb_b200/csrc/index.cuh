@@ -34,6 +34,8 @@ struct fdb_index {
     fdb::DevBuf<uint32_t> fb_p, fb_v, fb_c, fb_probes;
     bool last_filter = false;
     fdb::FilterState *filter = nullptr;   // ADC filter path (adc_filter.cu), null when not usable
+    bool last_probes_exact = false;       // `probes` holds the last device batch's lists in the reference's order
+    size_t last_probes_nq = 0, last_probes_nprobe = 0;
     uint64_t last_stats[4] = {0, 0, 0, 0};  // queries on the filter path, exact fallbacks, exact candidates, scanned vectors
     ~fdb_index();                         // adc_filter.cu (FilterState is complete there)
 };

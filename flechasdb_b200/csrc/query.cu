@@ -710,6 +710,10 @@ int batch_slice(QueryBatch &b, const float *d_q, size_t q_base, size_t nq, uint3
         bool probed = false;
         if (b.filter && (rc = filter_probe(ix, d_q, nq, b.nprobe, &b.log, &probed)) != FDB_OK) break;
         if (!probed && (rc = probe_device(ix, d_q, nq, b.nprobe, b.mode, &b.log)) != FDB_OK) break;
+        // (fdb_index_last_probes_device: ix->probes holds the whole batch's lists in the reference's order)
+        ix->last_probes_exact = !probed && nq == b.nq_total;
+        ix->last_probes_nq = nq;
+        ix->last_probes_nprobe = b.nprobe;
         if (b.filter) {
             rc = filter_query(ix, d_q, q_base, nq, b.k, b.nprobe, d_p, d_v, d_d, d_c, &b.log);
         } else {
@@ -784,6 +788,63 @@ int finish_query(fdb_ctx *ctx) {
 }
 
 }  // namespace
+
+namespace fdb {
+namespace {
+// Cross-rank merge of per-rank top-k lists (code lists sharded over the GPUs): one
+// warp per query takes the world * k candidates and keeps the k smallest by the canonical key of
+// build::Database::query's stable sort (src/db/build.rs:334-337): (distance, probe rank of the partition,
+// vector index).  Every (partition, vector index) occurs once, so the ranks are a permutation.
+__global__ void __launch_bounds__(128) merge_ranks_kernel(int world, size_t nq, int k, int nprobe,
+                                                          const uint32_t *part, const uint32_t *vidx,
+                                                          const float *dist, const uint32_t *cnt,
+                                                          const uint32_t *probes, uint32_t *o_part,
+                                                          uint32_t *o_vidx, float *o_dist, uint32_t *o_cnt) {
+    extern __shared__ unsigned char msm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t q = (size_t)blockIdx.x * 4 + warp;
+    if (q >= nq) return;
+    const int cap = world * k;
+    float *sd = reinterpret_cast<float *>(msm) + (size_t)warp * cap * 4;
+    uint32_t *sp = reinterpret_cast<uint32_t *>(sd + cap), *sv = sp + cap, *sr = sv + cap;
+    int n = 0;
+    for (int r = 0; r < world; ++r) {
+        const int c = (int)min(cnt[(size_t)r * nq + q], (uint32_t)k);
+        const size_t o = ((size_t)r * nq + q) * k;
+        for (int i = lane; i < c; i += 32) {
+            const uint32_t p = part[o + i];
+            int pr = nprobe;   // rank of the partition in the query's probe order
+            for (int e = 0; e < nprobe; ++e)
+                if (probes[q * nprobe + e] == p) {
+                    pr = e;
+                    break;
+                }
+            sd[n + i] = dist[o + i];
+            sp[n + i] = p;
+            sv[n + i] = vidx[o + i];
+            sr[n + i] = (uint32_t)pr;
+        }
+        n += c;
+    }
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) {
+        const float d = sd[i];
+        const uint32_t pr = sr[i], v = sv[i];
+        int rank = 0;
+        for (int j = 0; j < n; ++j) {
+            const float dj = sd[j];
+            rank += (dj < d) || (dj == d && (sr[j] < pr || (sr[j] == pr && sv[j] < v)));
+        }
+        if (rank < k) {
+            o_part[q * k + rank] = sp[i];
+            o_vidx[q * k + rank] = v;
+            o_dist[q * k + rank] = d;
+        }
+    }
+    if (lane == 0) o_cnt[q] = (uint32_t)min(n, k);
+}
+}  // namespace
+}  // namespace fdb
 
 extern "C" {
 
@@ -970,6 +1031,52 @@ int fdb_index_last_timing(fdb_index *ix, float ms[6], uint64_t *scan_bytes) {
         *scan_bytes = bytes;
     }
     return FDB_OK;
+}
+
+int fdb_index_probe_device(fdb_index *ix, const float *d_queries, size_t nq, size_t nprobe, int mode,
+                           uint32_t *d_partition) {
+    FDB_TRY(check_query_args(ix, nq, 1, nprobe, mode));
+    ARG(nq == 0 || (d_queries && d_partition), "null argument");
+    if (nq == 0) return FDB_OK;
+    fdb_ctx *ctx = ix->ctx;
+    FDB_TRY(ctx->use());
+    FDB_TRY(probe_device(ix, d_queries, nq, nprobe, mode, nullptr));
+    FDB_CUDA(cudaMemcpyAsync(d_partition, ix->probes.p, nq * nprobe * sizeof(uint32_t), cudaMemcpyDeviceToDevice,
+                             ctx->stream));
+    return FDB_OK;   // enqueued on the context's stream
+}
+
+int fdb_index_last_probes_device(fdb_index *ix, size_t nq, size_t nprobe, uint32_t *d_partition) {
+    ARG(ix && d_partition, "null argument");
+    if (!ix->last_probes_exact || ix->last_probes_nq != nq || ix->last_probes_nprobe != nprobe) {
+        set_error("the last query did not leave its probe lists in the reference's order (probe filter) or had another shape");
+        return FDB_ERR_INVALID_CONTEXT;
+    }
+    FDB_TRY(ix->ctx->use());
+    FDB_CUDA(cudaMemcpyAsync(d_partition, ix->probes.p, nq * nprobe * sizeof(uint32_t), cudaMemcpyDeviceToDevice,
+                             ix->ctx->stream));
+    return FDB_OK;
+}
+
+int fdb_merge_topk_device(fdb_ctx *ctx, int world, size_t nq, size_t k, size_t nprobe, const uint32_t *d_partition,
+                          const uint32_t *d_vector_index, const float *d_sqdist, const uint32_t *d_count,
+                          const uint32_t *d_probes, uint32_t *d_out_partition, uint32_t *d_out_vector_index,
+                          float *d_out_sqdist, uint32_t *d_out_count) {
+    ARG(ctx, "ctx is null");
+    ARG(world >= 1 && k >= 1 && nprobe >= 1, "world, k and nprobe must be positive");
+    if (nq == 0) return FDB_OK;
+    ARG(d_partition && d_vector_index && d_sqdist && d_count && d_probes && d_out_partition && d_out_vector_index &&
+            d_out_sqdist && d_out_count,
+        "null argument");
+    const size_t smem = 4 * (size_t)world * k * 16;
+    ARG(smem <= 48 * 1024, "world * k = %zu candidates per query exceed the merge buffer", (size_t)world * k);
+    FDB_TRY(ctx->use());
+    fdb::merge_ranks_kernel<<<(unsigned)((nq + 3) / 4), 128, smem, ctx->stream>>>(
+        world, nq, (int)k, (int)nprobe, d_partition, d_vector_index, d_sqdist, d_count, d_probes, d_out_partition,
+        d_out_vector_index, d_out_sqdist, d_out_count);
+    ctx->launches++;
+    FDB_CHECK_LAUNCH();
+    return FDB_OK;   // enqueued on the context's stream
 }
 
 }  // extern "C"

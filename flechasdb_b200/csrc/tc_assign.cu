@@ -1021,7 +1021,7 @@ int tc_reassign(fdb_km *km, const int *d_active) {
 
 // ---- query-side GEMMs (tc_gemm.cuh) ---------------------------------------------------------
 bool tc_shape_ok(size_t k, size_t m, size_t ld) {
-    return !getenv("FDB_DISABLE_TC") && k >= 1 && k <= 256 && m % BK == 0 && ld % 8 == 0;
+    return !getenv("FDB_DISABLE_TC") && k >= 1 && k <= 256 && m % 16 == 0 && ld % 8 == 0;
 }
 
 float tc_gamma(size_t m) {
@@ -1050,8 +1050,9 @@ int tc_prepare_centroids(fdb_ctx *ctx, const float *c, size_t nb, size_t k, size
                                                 out->c2.p, out->h.p, out->cmax2.p, nullptr);
     ctx->launches++;
     FDB_CHECK_LAUNCH();
-    FDB_TRY(make_map(&out->map1, out->c1.p, m, rows, (uint32_t)np));
-    FDB_TRY(make_map(&out->map2, out->c2.p, m, rows, (uint32_t)np));
+    // K chunks of 64 bf16 (128-byte swizzle) when m allows, else of 16 (32-byte swizzle)
+    FDB_TRY(make_map(&out->map1, out->c1.p, m, rows, (uint32_t)np, m % BK == 0 ? BK : 16));
+    FDB_TRY(make_map(&out->map2, out->c2.p, m, rows, (uint32_t)np, m % BK == 0 ? BK : 16));
     return FDB_OK;
 }
 
@@ -1068,8 +1069,10 @@ int tc_prepare_rows(fdb_ctx *ctx, const float *x, size_t n, size_t ld, size_t m,
     ctx->launches++;
     FDB_CHECK_LAUNCH();
     if (grown || out->n != n || out->ld != ld) {
-        FDB_TRY(make_map(&out->map1, out->x1.p, ld, n, BM));
-        FDB_TRY(make_map(&out->map2, out->x2.p, ld, n, BM));
+        // (the chunk size follows the row length: every GEMM that uses these rows has m % 64 == 0 iff ld % 64 == 0,
+        //  see the gates in filter_prepare)
+        FDB_TRY(make_map(&out->map1, out->x1.p, ld, n, BM, ld % BK == 0 ? BK : 16));
+        FDB_TRY(make_map(&out->map2, out->x2.p, ld, n, BM, ld % BK == 0 ? BK : 16));
         out->n = n;
         out->ld = ld;
     }
@@ -1095,8 +1098,9 @@ int tc_gemm_raw(fdb_ctx *ctx, const TcRows &rows, const TcCentroids &cent, size_
     p.sub_h = sub_h;
     p.np = cent.np;
     p.row_tiles = (int)((rows.n + BM - 1) / BM);
-    p.bk = BK;
-    const size_t stage_bytes = 2 * (size_t)BM * BK * 2 + 2 * (size_t)cent.np * BK * 2;
+    const int bk = cent.m % BK == 0 ? BK : 16;
+    p.bk = bk;
+    const size_t stage_bytes = 2 * (size_t)BM * bk * 2 + 2 * (size_t)cent.np * bk * 2;
     p.stages = (int)std::min<size_t>(4, (200 * 1024) / stage_bytes);
     p.h = cent.h.p;
     const size_t smem = (size_t)p.stages * stage_bytes + 1024;

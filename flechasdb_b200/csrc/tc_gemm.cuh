@@ -26,7 +26,8 @@ struct TcRows {
     size_t n = 0, ld = 0;
 };
 
-// shapes the kernel takes: m % 64 == 0, k <= 256 per problem, 16-byte aligned rows
+// shapes the kernel takes: m % 16 == 0 (K chunks of 64, or of 16 when m % 64 != 0), k <= 256 per problem,
+// 16-byte aligned rows
 bool tc_shape_ok(size_t k, size_t m, size_t ld);
 // centroid rows c[nb*k][m]; problem b is centred by mu[b * mu_stride .. + m); rows at or
 // beyond ktotal (column tiling of one long list of centroids) are padding

@@ -311,3 +311,38 @@ def sharded_query(comm, index, queries, k, nprobe, mode=1):
     p, v, d, c = index.query(queries, k, nprobe, mode)
     gp, gv, gd, gc = (comm.all_gather(a) for a in (p, v, d, c))
     return merge_topk(gp, gv, gd, gc, probes, k)
+
+
+def sharded_query_device(comm, index, d_q, nq, k, nprobe):
+    """The same on the device: this rank's lists are scanned by fdb_index_query_device (mode build: the
+    canonical order), the per-rank results are all-gathered with NCCL on the engine's stream and merged by
+    fdb_merge_topk_device; nothing synchronises with the host.  d_q: device pointer of the (replicated)
+    query batch.  Returns torch tensors (part, vidx, dist, cnt) on the device.  CUDA only."""
+    import torch
+    from . import _capi as capi
+    lib, dev, dist, world = capi.lib(), comm.device, comm.dist, comm.world
+    ctx = index.ctx
+    stream = torch.cuda.ExternalStream(lib.fdb_ctx_stream(ctx.h), device=dev)
+    i32, f32 = torch.int32, torch.float32
+    with torch.cuda.stream(stream):
+        lp, lv = torch.empty((nq, k), dtype=i32, device=dev), torch.empty((nq, k), dtype=i32, device=dev)
+        ld, lc = torch.empty((nq, k), dtype=f32, device=dev), torch.empty((nq,), dtype=i32, device=dev)
+        probes = torch.empty((nq, nprobe), dtype=i32, device=dev)
+        capi.check(lib.fdb_index_query_device(index.h, d_q, nq, k, nprobe, capi.QUERY_BUILD, lp.data_ptr(), lv.data_ptr(),
+                                              ld.data_ptr(), lc.data_ptr()))
+        # the probe order (ties between partitions): reuse the lists the query selected when they are exact
+        if lib.fdb_index_last_probes_device(index.h, nq, nprobe, probes.data_ptr()) != 0:
+            capi.check(lib.fdb_index_probe_device(index.h, d_q, nq, nprobe, capi.QUERY_BUILD, probes.data_ptr()))
+        gp, gv = torch.empty((world, nq, k), dtype=i32, device=dev), torch.empty((world, nq, k), dtype=i32, device=dev)
+        gd, gc = torch.empty((world, nq, k), dtype=f32, device=dev), torch.empty((world, nq), dtype=i32, device=dev)
+        if dist is not None and world > 1:
+            for g, l in ((gp, lp), (gv, lv), (gd, ld), (gc, lc)):
+                dist.all_gather_into_tensor(g, l)
+        else:
+            gp[0], gv[0], gd[0], gc[0] = lp, lv, ld, lc
+        op, ov = torch.empty((nq, k), dtype=i32, device=dev), torch.empty((nq, k), dtype=i32, device=dev)
+        od, oc = torch.empty((nq, k), dtype=f32, device=dev), torch.empty((nq,), dtype=i32, device=dev)
+        capi.check(lib.fdb_merge_topk_device(ctx.h, world, nq, k, nprobe, gp.data_ptr(), gv.data_ptr(), gd.data_ptr(),
+                                             gc.data_ptr(), probes.data_ptr(), op.data_ptr(), ov.data_ptr(),
+                                             od.data_ptr(), oc.data_ptr()))
+    return op, ov, od, oc

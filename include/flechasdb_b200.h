@@ -212,6 +212,21 @@ int fdb_index_query_device(fdb_index *ix, const float *d_queries, size_t nq, siz
 int fdb_index_probe(fdb_index *ix, const float *queries, size_t nq, size_t nprobe, int mode,
                     uint32_t *out_partition /*[nq][nprobe]*/, float *out_sqdist /*[nq][nprobe]*/);
 int fdb_index_table(fdb_index *ix, const float *query, uint32_t partition, float *table /*[D][C]*/);
+/* Code lists sharded over several GPUs (one process each; no reference analogue, the result is what
+ * build::Database::query src/db/build.rs:307-340 returns for the whole database): every rank holds the
+ * coarse centroids and codebooks and the lists of the partitions it owns (the others are empty), answers
+ * the batch with fdb_index_query_device(..., FDB_QUERY_BUILD, ...), the per-rank lists are all-gathered
+ * ([world][nq][k] / [world][nq]) and merged by the canonical key (distance, probe rank, vector index).
+ * All pointers are device pointers; both calls are enqueued on fdb_ctx_stream and do not synchronise. */
+int fdb_index_probe_device(fdb_index *ix, const float *d_queries, size_t nq, size_t nprobe, int mode,
+                           uint32_t *d_partition /*[nq][nprobe]*/);
+/* the probe lists the last fdb_index_query_device call used, when it selected them exactly (reference order);
+ * FDB_ERR_INVALID_CONTEXT when it did not (probe filter: a set in no particular order) -> fdb_index_probe_device */
+int fdb_index_last_probes_device(fdb_index *ix, size_t nq, size_t nprobe, uint32_t *d_partition /*[nq][nprobe]*/);
+int fdb_merge_topk_device(fdb_ctx *ctx, int world, size_t nq, size_t k, size_t nprobe, const uint32_t *d_partition,
+                          const uint32_t *d_vector_index, const float *d_sqdist, const uint32_t *d_count,
+                          const uint32_t *d_probes, uint32_t *d_out_partition, uint32_t *d_out_vector_index,
+                          float *d_out_sqdist, uint32_t *d_out_count);
 /* per-phase timing is off by default (it adds events and one probe read-back per call) */
 int fdb_index_set_timing(fdb_index *ix, int enabled);
 /* per-phase device milliseconds of the last fdb_index_query* call (timing enabled):

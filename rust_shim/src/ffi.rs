@@ -47,6 +47,18 @@ extern "C" {
     pub fn fdb_index_probe(ix: *mut fdb_index, queries: *const c_float, nq: usize, nprobe: usize, mode: c_int,
                            out_partition: *mut u32, out_sqdist: *mut c_float) -> c_int;
     pub fn fdb_index_destroy(ix: *mut fdb_index);
+
+    // rows sharded over several GPUs (one process each): stage functions enqueued on fdb_ctx_stream, the
+    // caller enqueues ncclAllGather / ncclAllReduce on the same stream in between
+    pub fn fdb_kmeans_seed_sharded_first(km: *mut fdb_km, local_first: *const u32) -> c_int;
+    pub fn fdb_kmeans_seed_sharded_total(km: *mut fdb_km) -> c_int;
+    pub fn fdb_kmeans_seed_sharded_pick(km: *mut fdb_km, d_all_totals: *const c_float, world: c_int, rank: c_int) -> c_int;
+    pub fn fdb_kmeans_seed_sharded_finish(km: *mut fdb_km, picked_global: *mut u32) -> c_int;
+    pub fn fdb_kmeans_sharded_loop_begin(km: *mut fdb_km) -> c_int;
+    pub fn fdb_kmeans_sharded_partial_async(km: *mut fdb_km, device_buf: *mut *mut c_float, nfloats: *mut usize) -> c_int;
+    pub fn fdb_kmeans_sharded_finish_async(km: *mut fdb_km, epsilon: c_float) -> c_int;
+    pub fn fdb_kmeans_sharded_poll(km: *mut fdb_km, active: *mut u8) -> c_int;
+    pub fn fdb_kmeans_sharded_loop_end(km: *mut fdb_km, gradients: *mut c_float, rounds: *mut u32, reassigns: *mut u32) -> c_int;
 }
 
 /// Maps a status of the C ABI onto the reference's error convention: `Err(Error::…)` for

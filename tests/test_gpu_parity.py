@@ -879,6 +879,50 @@ def test_tc_lloyd_trajectory_equals_exact_path(eng, ctx, oracle, monkeypatch):
 
 
 # ---- multi-GPU: sharded build + partition-sharded query over NCCL (needs >= 2 GPUs) -----------
+def test_cross_rank_merge_kernel_equals_the_host_merge(eng, ctx, oracle):
+    """fdb_merge_topk_device on one GPU: three simulated ranks each own a third of the partitions, their
+    top-k lists are stacked as an all-gather would and merged on the device; equal to the unsharded query
+    (build semantic: canonical order) and to dist.merge_topk."""
+    from flechasdb_b200 import _capi as capi, dist as fd
+    N, P, D, Cn, M, k, nprobe, nq, world = 64, 30, 4, 64, 9000, 10, 12, 200, 3
+    coarse, cbs, off, codes = random_index(oracle, N, P, D, Cn, M, dup=False, empty=(2,))
+    codes8 = codes.astype(np.uint8)
+    q = data(oracle, nq, N, SEED + 91)
+    full = eng.Index.create(ctx, coarse, cbs, off, codes8)
+    want = full.query(q, k, nprobe, 1)
+    probes, _ = full.probe(q, nprobe, 1)
+    sizes = np.diff(off.astype(np.int64))
+    owner = fd.owned_partitions(sizes, world)
+    parts, vidxs, dists, cnts = [], [], [], []
+    for r in range(world):
+        so, sc = fd.shard_index_arrays(off, codes8, owner, r)
+        six = eng.Index.create(ctx, coarse, cbs, so, sc)
+        p_, v_, d_, c_ = six.query(q, k, nprobe, 1)
+        parts.append(p_), vidxs.append(v_), dists.append(d_), cnts.append(c_)
+        six.close()
+    gp, gv, gd, gc = (np.stack(a) for a in (parts, vidxs, dists, cnts))
+    host = fd.merge_topk(gp, gv, gd, gc, probes, k)
+    import torch
+    lib = capi.lib()
+    dev = "cuda:0"
+    ins = [torch.as_tensor(np.ascontiguousarray(a).view(np.int32) if a.dtype == np.uint32 else a).to(dev)
+           for a in (gp, gv, gd, gc, probes)]
+    outs = [torch.zeros((nq, k), dtype=torch.int32, device=dev), torch.zeros((nq, k), dtype=torch.int32, device=dev),
+            torch.zeros((nq, k), dtype=torch.float32, device=dev), torch.zeros((nq,), dtype=torch.int32, device=dev)]
+    torch.cuda.synchronize()
+    capi.check(lib.fdb_merge_topk_device(ctx.h, world, nq, k, nprobe, *[t.data_ptr() for t in ins],
+                                         *[t.data_ptr() for t in outs]))
+    ctx.sync()
+    got = [t.cpu().numpy().view(np.uint32) if t.dtype == torch.int32 else t.cpu().numpy() for t in outs]
+    for qi in range(nq):
+        c = int(want[3][qi])
+        assert got[3][qi] == c == host[3][qi]
+        for i in range(3):
+            assert (got[i][qi, :c] == want[i][qi, :c]).all(), (i, qi)
+            assert (host[i][qi, :c] == want[i][qi, :c]).all(), (i, qi)
+    full.close()
+
+
 def test_multi_gpu_sharded_build_and_query():
     import os
     import subprocess
@@ -892,7 +936,7 @@ def test_multi_gpu_sharded_build_and_query():
            "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tools", "dist_check.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
-    assert "picks_equal=True update_close=True assign_exact=True query_equal=True" in out.stdout
+    assert "picks_equal=True update_close=True assign_exact=True query_equal=True loop_equal=True" in out.stdout
 
 
 # ---- host mirrors: DatabaseBuilder / Database / stored layout ---------------------------------
