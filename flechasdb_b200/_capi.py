@@ -89,7 +89,7 @@ SIGNATURES = {
     "fdb_kmeans_update_finish": (C.c_int, [VP, F32P]),
     "fdb_index_probe_device": (C.c_int, [VP, VP, SZ, SZ, C.c_int, VP]),
     "fdb_index_last_probes_device": (C.c_int, [VP, SZ, SZ, VP]),
-    "fdb_merge_topk_device": (C.c_int, [VP, C.c_int, SZ, SZ, SZ, VP, VP, VP, VP, VP, VP, VP, VP, VP]),
+    "fdb_merge_topk_device": (C.c_int, [VP, C.c_int, SZ, SZ, SZ, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP]),
     "fdb_index_create": (C.c_int, [VP, SZ, SZ, SZ, SZ, F32P, F32P, U64P, U8P, C.POINTER(VP)]),
     "fdb_index_from_build": (C.c_int, [VP, VP, VP, C.POINTER(VP)]),
     "fdb_index_get_layout": (C.c_int, [VP, U64P, U32P, U8P]),

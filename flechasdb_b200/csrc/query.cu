@@ -799,7 +799,8 @@ __global__ void __launch_bounds__(128) merge_ranks_kernel(int world, size_t nq, 
                                                           const uint32_t *part, const uint32_t *vidx,
                                                           const float *dist, const uint32_t *cnt,
                                                           const uint32_t *probes, uint32_t *o_part,
-                                                          uint32_t *o_vidx, float *o_dist, uint32_t *o_cnt) {
+                                                          uint32_t *o_vidx, float *o_dist, uint32_t *o_cnt,
+                                                          uint32_t *tie_flag) {
     extern __shared__ unsigned char msm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t q = (size_t)blockIdx.x * 4 + warp;
@@ -813,12 +814,13 @@ __global__ void __launch_bounds__(128) merge_ranks_kernel(int world, size_t nq, 
         const size_t o = ((size_t)r * nq + q) * k;
         for (int i = lane; i < c; i += 32) {
             const uint32_t p = part[o + i];
-            int pr = nprobe;   // rank of the partition in the query's probe order
-            for (int e = 0; e < nprobe; ++e)
-                if (probes[q * nprobe + e] == p) {
-                    pr = e;
-                    break;
-                }
+            int pr = probes ? nprobe : (int)p;   // rank of the partition in the query's probe order (or its id)
+            if (probes)
+                for (int e = 0; e < nprobe; ++e)
+                    if (probes[q * nprobe + e] == p) {
+                        pr = e;
+                        break;
+                    }
             sd[n + i] = dist[o + i];
             sp[n + i] = p;
             sv[n + i] = vidx[o + i];
@@ -831,10 +833,13 @@ __global__ void __launch_bounds__(128) merge_ranks_kernel(int world, size_t nq, 
         const float d = sd[i];
         const uint32_t pr = sr[i], v = sv[i];
         int rank = 0;
+        bool tied = false;   // equal distance in another partition: the order depends on the probe ranks
         for (int j = 0; j < n; ++j) {
             const float dj = sd[j];
             rank += (dj < d) || (dj == d && (sr[j] < pr || (sr[j] == pr && sv[j] < v)));
+            tied |= dj == d && sr[j] != pr;
         }
+        if (!probes && tied && rank <= k && tie_flag) atomicOr(tie_flag, 1u);
         if (rank < k) {
             o_part[q * k + rank] = sp[i];
             o_vidx[q * k + rank] = v;
@@ -1061,19 +1066,19 @@ int fdb_index_last_probes_device(fdb_index *ix, size_t nq, size_t nprobe, uint32
 int fdb_merge_topk_device(fdb_ctx *ctx, int world, size_t nq, size_t k, size_t nprobe, const uint32_t *d_partition,
                           const uint32_t *d_vector_index, const float *d_sqdist, const uint32_t *d_count,
                           const uint32_t *d_probes, uint32_t *d_out_partition, uint32_t *d_out_vector_index,
-                          float *d_out_sqdist, uint32_t *d_out_count) {
+                          float *d_out_sqdist, uint32_t *d_out_count, uint32_t *d_tie_flag) {
     ARG(ctx, "ctx is null");
     ARG(world >= 1 && k >= 1 && nprobe >= 1, "world, k and nprobe must be positive");
     if (nq == 0) return FDB_OK;
-    ARG(d_partition && d_vector_index && d_sqdist && d_count && d_probes && d_out_partition && d_out_vector_index &&
-            d_out_sqdist && d_out_count,
+    ARG(d_partition && d_vector_index && d_sqdist && d_count && d_out_partition && d_out_vector_index && d_out_sqdist &&
+            d_out_count && (d_probes || d_tie_flag),
         "null argument");
     const size_t smem = 4 * (size_t)world * k * 16;
     ARG(smem <= 48 * 1024, "world * k = %zu candidates per query exceed the merge buffer", (size_t)world * k);
     FDB_TRY(ctx->use());
     fdb::merge_ranks_kernel<<<(unsigned)((nq + 3) / 4), 128, smem, ctx->stream>>>(
         world, nq, (int)k, (int)nprobe, d_partition, d_vector_index, d_sqdist, d_count, d_probes, d_out_partition,
-        d_out_vector_index, d_out_sqdist, d_out_count);
+        d_out_vector_index, d_out_sqdist, d_out_count, d_tie_flag);
     ctx->launches++;
     FDB_CHECK_LAUNCH();
     return FDB_OK;   // enqueued on the context's stream

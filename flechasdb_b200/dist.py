@@ -330,9 +330,6 @@ def sharded_query_device(comm, index, d_q, nq, k, nprobe):
         probes = torch.empty((nq, nprobe), dtype=i32, device=dev)
         capi.check(lib.fdb_index_query_device(index.h, d_q, nq, k, nprobe, capi.QUERY_BUILD, lp.data_ptr(), lv.data_ptr(),
                                               ld.data_ptr(), lc.data_ptr()))
-        # the probe order (ties between partitions): reuse the lists the query selected when they are exact
-        if lib.fdb_index_last_probes_device(index.h, nq, nprobe, probes.data_ptr()) != 0:
-            capi.check(lib.fdb_index_probe_device(index.h, d_q, nq, nprobe, capi.QUERY_BUILD, probes.data_ptr()))
         gp, gv = torch.empty((world, nq, k), dtype=i32, device=dev), torch.empty((world, nq, k), dtype=i32, device=dev)
         gd, gc = torch.empty((world, nq, k), dtype=f32, device=dev), torch.empty((world, nq), dtype=i32, device=dev)
         if dist is not None and world > 1:
@@ -342,7 +339,21 @@ def sharded_query_device(comm, index, d_q, nq, k, nprobe):
             gp[0], gv[0], gd[0], gc[0] = lp, lv, ld, lc
         op, ov = torch.empty((nq, k), dtype=i32, device=dev), torch.empty((nq, k), dtype=i32, device=dev)
         od, oc = torch.empty((nq, k), dtype=f32, device=dev), torch.empty((nq,), dtype=i32, device=dev)
-        capi.check(lib.fdb_merge_topk_device(ctx.h, world, nq, k, nprobe, gp.data_ptr(), gv.data_ptr(), gd.data_ptr(),
-                                             gc.data_ptr(), probes.data_ptr(), op.data_ptr(), ov.data_ptr(),
-                                             od.data_ptr(), oc.data_ptr()))
+
+        def merge(probes_ptr, flag_ptr):
+            capi.check(lib.fdb_merge_topk_device(ctx.h, world, nq, k, nprobe, gp.data_ptr(), gv.data_ptr(), gd.data_ptr(),
+                                                 gc.data_ptr(), probes_ptr, op.data_ptr(), ov.data_ptr(), od.data_ptr(),
+                                                 oc.data_ptr(), flag_ptr))
+
+        # the probe order only matters when candidates of different partitions are exactly tied: reuse the
+        # lists the query selected when they are in the reference's order, else merge by partition id and
+        # look at the tie flag (one 4-byte read-back); exact probes are computed only if it is set
+        if lib.fdb_index_last_probes_device(index.h, nq, nprobe, probes.data_ptr()) == 0:
+            merge(probes.data_ptr(), None)
+        else:
+            flag = torch.zeros((1,), dtype=i32, device=dev)
+            merge(None, flag.data_ptr())
+            if int(flag.item()) != 0:
+                capi.check(lib.fdb_index_probe_device(index.h, d_q, nq, nprobe, capi.QUERY_BUILD, probes.data_ptr()))
+                merge(probes.data_ptr(), None)
     return op, ov, od, oc

@@ -226,7 +226,11 @@ int fdb_index_last_probes_device(fdb_index *ix, size_t nq, size_t nprobe, uint32
 int fdb_merge_topk_device(fdb_ctx *ctx, int world, size_t nq, size_t k, size_t nprobe, const uint32_t *d_partition,
                           const uint32_t *d_vector_index, const float *d_sqdist, const uint32_t *d_count,
                           const uint32_t *d_probes, uint32_t *d_out_partition, uint32_t *d_out_vector_index,
-                          float *d_out_sqdist, uint32_t *d_out_count);
+                          float *d_out_sqdist, uint32_t *d_out_count, uint32_t *d_tie_flag);
+/* d_probes may be NULL when the probe order is not at hand (fdb_index_last_probes_device failed): the
+ * partition id then stands in for the probe rank and *d_tie_flag (device, zeroed by the caller) is set when
+ * two candidates of different partitions with exactly equal distances sit at or above the k-th place -- the
+ * only case in which the order matters; the caller then merges again with fdb_index_probe_device's lists. */
 /* per-phase timing is off by default (it adds events and one probe read-back per call) */
 int fdb_index_set_timing(fdb_index *ix, int enabled);
 /* per-phase device milliseconds of the last fdb_index_query* call (timing enabled):
