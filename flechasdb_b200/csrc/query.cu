@@ -839,7 +839,7 @@ __global__ void __launch_bounds__(128) merge_ranks_kernel(int world, size_t nq, 
             rank += (dj < d) || (dj == d && (sr[j] < pr || (sr[j] == pr && sv[j] < v)));
             tied |= dj == d && sr[j] != pr;
         }
-        if (!probes && tied && rank <= k && tie_flag) atomicOr(tie_flag, 1u);
+        if (!probes && tied && rank <= k && tie_flag) tie_flag[q] = 1u;
         if (rank < k) {
             o_part[q * k + rank] = sp[i];
             o_vidx[q * k + rank] = v;

@@ -340,20 +340,29 @@ def sharded_query_device(comm, index, d_q, nq, k, nprobe):
         op, ov = torch.empty((nq, k), dtype=i32, device=dev), torch.empty((nq, k), dtype=i32, device=dev)
         od, oc = torch.empty((nq, k), dtype=f32, device=dev), torch.empty((nq,), dtype=i32, device=dev)
 
-        def merge(probes_ptr, flag_ptr):
-            capi.check(lib.fdb_merge_topk_device(ctx.h, world, nq, k, nprobe, gp.data_ptr(), gv.data_ptr(), gd.data_ptr(),
-                                                 gc.data_ptr(), probes_ptr, op.data_ptr(), ov.data_ptr(), od.data_ptr(),
-                                                 oc.data_ptr(), flag_ptr))
+        def merge(n, g, probes_ptr, flag_ptr, o):
+            capi.check(lib.fdb_merge_topk_device(ctx.h, world, n, k, nprobe, g[0].data_ptr(), g[1].data_ptr(), g[2].data_ptr(),
+                                                 g[3].data_ptr(), probes_ptr, o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(),
+                                                 o[3].data_ptr(), flag_ptr))
 
-        # the probe order only matters when candidates of different partitions are exactly tied: reuse the
-        # lists the query selected when they are in the reference's order, else merge by partition id and
-        # look at the tie flag (one 4-byte read-back); exact probes are computed only if it is set
+        # The probe order only matters when candidates of different partitions have exactly equal f32
+        # distances.  Reuse the lists the query selected when they are in the reference's order; else merge by
+        # partition id, read back which queries had such a tie (a few per 10 000) and merge only those again
+        # with exactly selected probes.
         if lib.fdb_index_last_probes_device(index.h, nq, nprobe, probes.data_ptr()) == 0:
-            merge(probes.data_ptr(), None)
+            merge(nq, (gp, gv, gd, gc), probes.data_ptr(), None, (op, ov, od, oc))
         else:
-            flag = torch.zeros((1,), dtype=i32, device=dev)
-            merge(None, flag.data_ptr())
-            if int(flag.item()) != 0:
-                capi.check(lib.fdb_index_probe_device(index.h, d_q, nq, nprobe, capi.QUERY_BUILD, probes.data_ptr()))
-                merge(probes.data_ptr(), None)
+            flags = torch.zeros((nq,), dtype=i32, device=dev)
+            merge(nq, (gp, gv, gd, gc), None, flags.data_ptr(), (op, ov, od, oc))
+            tied = torch.nonzero(flags).flatten()
+            nt = int(tied.numel())
+            if nt:
+                qt = device_tensor(getattr(d_q, "value", d_q), nq * index.N, dev).view(nq, index.N)[tied].contiguous()
+                pt = torch.empty((nt, nprobe), dtype=i32, device=dev)
+                capi.check(lib.fdb_index_probe_device(index.h, qt.data_ptr(), nt, nprobe, capi.QUERY_BUILD, pt.data_ptr()))
+                sub = tuple(x[:, tied].contiguous() for x in (gp, gv, gd, gc))
+                o2 = (torch.empty((nt, k), dtype=i32, device=dev), torch.empty((nt, k), dtype=i32, device=dev),
+                      torch.empty((nt, k), dtype=f32, device=dev), torch.empty((nt,), dtype=i32, device=dev))
+                merge(nt, sub, pt.data_ptr(), None, o2)
+                op[tied], ov[tied], od[tied], oc[tied] = o2
     return op, ov, od, oc

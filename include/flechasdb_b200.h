@@ -228,9 +228,10 @@ int fdb_merge_topk_device(fdb_ctx *ctx, int world, size_t nq, size_t k, size_t n
                           const uint32_t *d_probes, uint32_t *d_out_partition, uint32_t *d_out_vector_index,
                           float *d_out_sqdist, uint32_t *d_out_count, uint32_t *d_tie_flag);
 /* d_probes may be NULL when the probe order is not at hand (fdb_index_last_probes_device failed): the
- * partition id then stands in for the probe rank and *d_tie_flag (device, zeroed by the caller) is set when
- * two candidates of different partitions with exactly equal distances sit at or above the k-th place -- the
- * only case in which the order matters; the caller then merges again with fdb_index_probe_device's lists. */
+ * partition id then stands in for the probe rank and d_tie_flag[q] (device, [nq], zeroed by the caller) is
+ * set for the queries in which two candidates of different partitions with exactly equal f32 distances sit
+ * at or above the k-th place -- the only case in which the order matters (a few per 10 000 queries on
+ * 100M vectors); the caller merges those queries again with fdb_index_probe_device's lists. */
 /* per-phase timing is off by default (it adds events and one probe read-back per call) */
 int fdb_index_set_timing(fdb_index *ix, int enabled);
 /* per-phase device milliseconds of the last fdb_index_query* call (timing enabled):

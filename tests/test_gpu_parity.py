@@ -916,12 +916,12 @@ def test_cross_rank_merge_kernel_equals_the_host_merge(eng, ctx, oracle):
     got = [t.cpu().numpy().view(np.uint32) if t.dtype == torch.int32 else t.cpu().numpy() for t in outs]
     # without the probe lists: partition ids break ties, the flag says whether that mattered (here: no exact ties)
     outs2 = [torch.zeros_like(t) for t in outs]
-    flag = torch.zeros((1,), dtype=torch.int32, device=dev)
+    flag = torch.zeros((nq,), dtype=torch.int32, device=dev)
     torch.cuda.synchronize()
     capi.check(lib.fdb_merge_topk_device(ctx.h, world, nq, k, nprobe, *[t.data_ptr() for t in ins[:4]], None,
                                          *[t.data_ptr() for t in outs2], flag.data_ptr()))
     ctx.sync()
-    assert int(flag.item()) == 0
+    assert int(flag.sum().item()) == 0
     for a, b in zip(outs, outs2):
         assert bool((a == b).all())
     for qi in range(nq):
