@@ -1,24 +1,28 @@
 // Partition-major code scan of the ADC filter path (included by adc_filter.cu, inside its namespace).
 //
 // fscan_kernel (query-major) does D shared-memory look-ups per (query, vector) at 32 random bank
-// positions: ~3.1 wavefronts per warp look-up, which caps it at ~0.45 of the HBM roofline, and it reads a
-// list once per query that probes it.  Here the (query, probe) pairs of a slice are grouped by partition
-// (counting sort, three small kernels); one work item = (partition, group of PJ = 16 queries that probe
-// it, chunk of <= vch vectors).  The item's CTA keeps the 16 queries' tables interleaved in shared memory,
-//     T[d][c][j] = G[q_j][d][c] + PC[p][d][c]            (D * 256 * 16 floats = 192 KB at D = 12),
-// and a warp step handles 2 vectors x 16 queries: the 16 lanes of a half warp read 16 consecutive words
-// (one vector's code, 16 queries), so a look-up costs 1 wavefront (2 when the two vectors' codes fall in
-// the same half of the banks: 1.5 on average), and the list is read once per 16 queries.
+// positions: ~3.1 wavefronts per warp look-up, and it reads a list once per query that probes it.  Here
+// the (query, probe) pairs of a slice are grouped by partition (counting sort: pg_count / pg_scan /
+// pg_scatter / pg_items_kernel); one work item = (partition, group of queries that probe it, chunk of
+// <= vch vectors), handed to persistent CTAs (one per SM) through an atomic counter.  Two kernels:
 //
-// Selection.  Every query of the item has a small append buffer in shared memory (PB entries) and a
-// threshold; a lane appends (atomicAdd on the buffer's counter) when its value is below the threshold,
-// nothing else happens in the steady state.  The vectors are handled in rounds (64, 64, 128, 256, ... per
-// CTA); between rounds the buffers that grew are cut back to the ncap smallest (bitonic sort in one warp)
-// and the thresholds tightened.  A query's threshold is shared between its partitions through global
-// memory (thrg[q] = the smallest "ncap-th smallest" any of its finished items saw: an upper bound of the
-// final one), so only the first item of a query starts from +inf.  An overfull buffer flags the query
+//   pscan_kernel    f32 tables, PJ = 16 queries per item: T[d][c][j] = G[q_j][d][c] + PC[p][d][c], 16 KB per
+//                   division; a warp step is 2 vectors x 16 queries, the 16 lanes of a half warp read 16
+//                   consecutive words (1 wavefront per look-up, 2 when both vectors' codes fall into the
+//                   same half of the banks: 1.5 on average);
+//   pscan16_kernel  16-bit fixed-point tables, QJ = 32 queries per item (further down): a warp step is ONE
+//                   vector x 32 queries, every look-up is 64 contiguous bytes, integer sums.
+//
+// Selection.  Every query of the item has a small append buffer in shared memory and a threshold; a lane
+// appends (atomicAdd on the buffer's counter) when its value is below the threshold, nothing else happens
+// in the steady state.  The vectors are handled in rounds that grow with the number of vectors seen (a
+// round never brings more than about ncap new entries); between rounds the buffers that outgrew the list
+// are cut back to the ncap smallest (bitonic sort in one warp) and the thresholds tightened.  A query's
+// threshold is shared between its items through global memory (thrg[q] = the smallest "ncap-th smallest"
+// any of its finished items saw: an upper bound of the final one).  An overfull buffer flags the query
 // (exact pipeline), so the kept set is always exactly the ncap smallest of the pair -- or the query is
 // handed back.  pmerge_kernel then merges the items of a query into the candidate list fselect_kernel reads.
+// Measurements and the reasons it is the default only for long lists probed by many queries: DESIGN.md 4b.
 
 constexpr int PJ = 16;          // queries per group
 constexpr int PB = 96;          // append buffer entries per query
