@@ -536,6 +536,10 @@ __global__ void __launch_bounds__(FS_WARPS * 32) fscan_kernel(FScanParams p) {
     __shared__ unsigned thr_s, flag_s;
     __shared__ int cnt_s;
     __shared__ uint32_t bk[FSB], bp[FSB];
+    // records (short lists, L2 resident): every lane loads its own 16-byte record straight from global memory,
+    // 512 contiguous bytes per warp step -- no staging, 12 KB of shared memory per CTA; compact codes (long
+    // lists, streamed from HBM): staged through shared memory with cp.async, double buffered per warp
+    constexpr bool DIRECT = RECORDS;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int D = p.D, C = p.C, RB = p.rb;
     const int DC = D * C;
@@ -600,6 +604,7 @@ __global__ void __launch_bounds__(FS_WARPS * 32) fscan_kernel(FScanParams p) {
         const uint8_t *cg = p.codes + p.part_start[part];
         const int nchunks = (np + CV - 1) / CV;
         auto issue = [&](int c, int slot) {
+            if (DIRECT) return;
             if (c < nchunks) {
                 const int c0 = c * CV;
                 const int n16 = (min(CV, np - c0) * RB + 15) >> 4;
@@ -620,11 +625,13 @@ __global__ void __launch_bounds__(FS_WARPS * 32) fscan_kernel(FScanParams p) {
         for (int it = 0; it < niter; ++it) {
             const int c = it * FS_WARPS + warp;
             issue(c + FS_WARPS, slot ^ 1);
-            cp_async_wait<1>();
-            __syncwarp();
+            if (!DIRECT) {
+                cp_async_wait<1>();
+                __syncwarp();
+            }
             const int c0 = c * CV;
             const int cnt = max(0, min(CV, np - c0));
-            const unsigned char *cs = cbuf + (size_t)slot * chunk_bytes;
+            const unsigned char *cs = DIRECT ? cg + (size_t)c0 * RB : cbuf + (size_t)slot * chunk_bytes;
             auto scan_range = [&](int lo, int top) {
                 for (int base = lo & ~31; base < top; base += 32) {
                     const int v = base + lane;
@@ -670,7 +677,7 @@ __global__ void __launch_bounds__(FS_WARPS * 32) fscan_kernel(FScanParams p) {
             __syncwarp();
             slot ^= 1;
         }
-        cp_async_wait<0>();
+        if (!DIRECT) cp_async_wait<0>();
         flat0 += (uint32_t)np;
     }
     round_end();   // at most ncap entries are left
@@ -1409,8 +1416,8 @@ __global__ void __launch_bounds__(256) stash_undecided_kernel(const unsigned lon
         for (int i = 1; i < 12; ++i) atomicAdd(&bcounters[i], counters[i]);   // statistics, why queries were handed back
 }
 
-size_t scan_smem_bytes(const fdb_index *ix, int chunk_vecs, size_t rb) {
-    return ix->D * TSTRIDE * 4 + (size_t)FS_WARPS * 2 * chunk_vecs * rb + 16;
+size_t scan_smem_bytes(const fdb_index *ix, int chunk_vecs, size_t rb, bool records = false) {
+    return ix->D * TSTRIDE * 4 + (records ? 0 : (size_t)FS_WARPS * 2 * chunk_vecs * rb) + 16;   // records are not staged
 }
 // vectors per staging chunk (per warp, double buffered).  Short lists (records): 1 KB chunks, 10 CTAs per SM
 // instead of 7 (README shape 0.449 -> 0.425 ms); long lists (compact codes): 2 KB (1.67 vs 1.74 ms on 40M vectors)
@@ -1789,7 +1796,7 @@ int filter_query(fdb_index *ix, const float *d_q, size_t q_base, size_t nq, size
     const bool records = fs->rb != 0;
     const size_t rb = records ? fs->rb : D;
     const int chunk_vecs = scan_chunk_vecs(rb, records);
-    const size_t smem = scan_smem_bytes(ix, chunk_vecs, rb);
+    const size_t smem = scan_smem_bytes(ix, chunk_vecs, rb, records);
     const FScanFn scan = scan_fn(D, records);
     FDB_CUDA(cudaFuncSetAttribute(scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // list capacity: k plus head room for the vectors inside the error band
