@@ -30,6 +30,7 @@ constexpr int PLK = 32;         // entries kept per (item, query) in global memo
 constexpr int PW = 32;          // warps per CTA
 constexpr int PCV = 16;         // vectors per warp and round (staging chunk)
 constexpr int PFB = 4;          // float4 table loads in flight per lane during the fill
+constexpr int PSUB = 4;         // staging chunks per warp and round (pscan16_kernel)
 constexpr int PT_STRIDE = 256;  // codes per table row in shared memory
 constexpr uint32_t PT_BASE = 0x8000;   // absolute shared address of the tables
 constexpr int PDESC = 4 + PJ;   // words of an item descriptor: partition, first vector, one past the last, members, pairs
@@ -603,59 +604,73 @@ __global__ void __launch_bounds__(PW * 32, 1) pscan16_kernel(PScanParams p) {
         unsigned mythr = bthr[lane];
         const float mydelta = qdelta[lane], mybase = qbase[lane];
         int rs = v0, rsize = QB - 16, slot = 0;   // doubling rounds always: a threshold inherited from another list may be loose
+        // a round (the vectors between two meetings of the CTA) is up to PSUB staging chunks of PCV vectors per
+        // warp; the chunks are double buffered per warp across chunk and round boundaries
         auto warp_range = [&](int rs_, int re_, int &b, int &e) {
             const int cnt_r = re_ - rs_;
             const int per = ((cnt_r + PW * 4 - 1) / (PW * 4)) * 4;
             b = min(re_, rs_ + warp * per);
             e = min(re_, b + per);
         };
-        auto issue = [&](int rs_, int re_, int sl) {
-            int b, e;
-            warp_range(rs_, re_, b, e);
-            if (e > b) {
-                const int n16 = ((e - b) * RB + 15) >> 4;
-                const unsigned char *src = lst + (size_t)b * RB;
+        auto issue_sub = [&](int sb, int se, int sl) {   // vectors [sb, se) of the list into staging slot sl
+            if (se > sb) {
+                const int n16 = ((se - sb) * RB + 15) >> 4;
+                const unsigned char *src = lst + (size_t)sb * RB;
                 unsigned char *dst = mystage + (size_t)sl * PCV * RB;
                 for (int i = lane; i < n16; i += 32) cp_async16(dst + 16 * i, src + 16 * i);
             }
             cp_async_commit();
         };
-        issue(rs, min(v1, rs + rsize), 0);
+        {
+            int b0, e0;
+            warp_range(rs, min(v1, rs + rsize), b0, e0);
+            issue_sub(b0, min(e0, b0 + PCV), 0);
+        }
         int total_seen = 0;
         while (rs < v1) {
             const int re = min(v1, rs + rsize);
             // a round holds at most half of what has been seen: ~ncap / 2 new entries expected (the count is
             // over-dispersed: the threshold is itself an order statistic), QB - ncap = 32 slots of head room
-            const int nrs = re, nrsize = min(PW * PCV, max(QB - 16, ((total_seen + (re - rs)) >> 1) & ~3));
-            issue(nrs, min(v1, nrs + nrsize), slot ^ 1);
-            cp_async_wait<1>();
-            __syncwarp();
-            int b, e;
+            const int nrs = re, nrsize = min(PW * PCV * PSUB, max(QB - 16, ((total_seen + (re - rs)) >> 1) & ~3));
+            int b, e, nb, ne;
             warp_range(rs, re, b, e);
-            const uint32_t cs_addr = (uint32_t)__cvta_generic_to_shared(mystage) + (uint32_t)(slot * PCV * RB);
-            const int nvec = e - b;
+            warp_range(nrs, min(v1, nrs + nrsize), nb, ne);
+            if (e <= b) {
+                // nothing for this warp in this round: the next round's first chunk goes where the next chunk is expected
+                issue_sub(nb, min(ne, nb + PCV), slot);
+            }
+            for (int sb = b; sb < e; sb += PCV) {
+                const int se = min(e, sb + PCV);
+                if (se < e) issue_sub(se, min(e, se + PCV), slot ^ 1);          // the next chunk of this round
+                else issue_sub(nb, min(ne, nb + PCV), slot ^ 1);                  // or the first one of the next round
+                cp_async_wait<1>();
+                __syncwarp();
+                const uint32_t cs_addr = (uint32_t)__cvta_generic_to_shared(mystage) + (uint32_t)(slot * PCV * RB);
+                const int nvec = se - sb;
 #pragma unroll 4
-            for (int vi = 0; vi < nvec; ++vi) {
-                uint32_t cw[W];
-                lds_words<W>(cs_addr + (uint32_t)(vi * RB), cw);   // the same address in every lane: a broadcast
-                uint32_t S = lookup4_u16<0>(cw[0], tlane);
-                if (W > 1) S += lookup4_u16<1>(cw[W > 1 ? 1 : 0], tlane);
-                if (W > 2) S += lookup4_u16<2>(cw[W > 2 ? 2 : 0], tlane);
-                const uint32_t key = fkey(fmaf(mydelta, (float)S, mybase));
-                if (key < mythr) {
-                    const int i = atomicAdd(&bcnt[lane], 1);
-                    if (i < QB) {
-                        bkeys[lane * QB + i] = key;
-                        bpos[lane * QB + i] = (uint32_t)(b + vi);
-                    } else {
-                        bflag[lane] = 2u;   // overflow
+                for (int vi = 0; vi < nvec; ++vi) {
+                    uint32_t cw[W];
+                    lds_words<W>(cs_addr + (uint32_t)(vi * RB), cw);   // the same address in every lane: a broadcast
+                    uint32_t S = lookup4_u16<0>(cw[0], tlane);
+                    if (W > 1) S += lookup4_u16<1>(cw[W > 1 ? 1 : 0], tlane);
+                    if (W > 2) S += lookup4_u16<2>(cw[W > 2 ? 2 : 0], tlane);
+                    const uint32_t key = fkey(fmaf(mydelta, (float)S, mybase));
+                    if (key < mythr) {
+                        const int i = atomicAdd(&bcnt[lane], 1);
+                        if (i < QB) {
+                            bkeys[lane * QB + i] = key;
+                            bpos[lane * QB + i] = (uint32_t)(sb + vi);
+                        } else {
+                            bflag[lane] = 2u;   // overflow
+                        }
                     }
                 }
+                __syncwarp();
+                slot ^= 1;
             }
             total_seen += re - rs;
             rs = re;
             rsize = nrsize;
-            slot ^= 1;
             __syncthreads();
             for (int jj = warp; jj < members; jj += PW) {
                 const int n = min(bcnt[jj], QB);
