@@ -59,6 +59,16 @@ extern "C" {
     pub fn fdb_kmeans_sharded_finish_async(km: *mut fdb_km, epsilon: c_float) -> c_int;
     pub fn fdb_kmeans_sharded_poll(km: *mut fdb_km, active: *mut u8) -> c_int;
     pub fn fdb_kmeans_sharded_loop_end(km: *mut fdb_km, gradients: *mut c_float, rounds: *mut u32, reassigns: *mut u32) -> c_int;
+
+    // code lists sharded over several GPUs: per-rank query on device buffers, all-gather, merge on the device
+    pub fn fdb_index_query_device(ix: *mut fdb_index, d_queries: *const c_float, nq: usize, k: usize, nprobe: usize, mode: c_int,
+                                  d_partition: *mut u32, d_vector_index: *mut u32, d_sqdist: *mut c_float, d_count: *mut u32) -> c_int;
+    pub fn fdb_index_probe_device(ix: *mut fdb_index, d_queries: *const c_float, nq: usize, nprobe: usize, mode: c_int, d_partition: *mut u32) -> c_int;
+    pub fn fdb_index_last_probes_device(ix: *mut fdb_index, nq: usize, nprobe: usize, d_partition: *mut u32) -> c_int;
+    pub fn fdb_merge_topk_device(ctx: *mut fdb_ctx, world: c_int, nq: usize, k: usize, nprobe: usize, d_partition: *const u32,
+                                 d_vector_index: *const u32, d_sqdist: *const c_float, d_count: *const u32, d_probes: *const u32,
+                                 d_out_partition: *mut u32, d_out_vector_index: *mut u32, d_out_sqdist: *mut c_float,
+                                 d_out_count: *mut u32, d_tie_flag: *mut u32) -> c_int;
 }
 
 /// Maps a status of the C ABI onto the reference's error convention: `Err(Error::…)` for
