@@ -153,13 +153,34 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const float *x, size_t 
     __nv_bfloat16 *o1 = x1 + row * out_ld + out_off + b * out_m;
     __nv_bfloat16 *o2 = x2 + row * out_ld + out_off + b * out_m;
     double acc = 0.0;
-    for (size_t e = lane; e < m; e += 32) {
-        const float v = __fsub_rn(xr[e], mr[e]);
-        const __nv_bfloat16 h = __float2bfloat16_rn(v);
-        const float r = __fsub_rn(v, __bfloat162float(h));
-        o1[e] = h;
-        o2[e] = __float2bfloat16_rn(r);
-        acc += (double)v * (double)v;
+    // four elements per lane (one 16-byte load, two 8-byte stores) when everything is aligned
+    const bool vec = m % 4 == 0 && ((uintptr_t)xr % 16 == 0) && ((uintptr_t)mr % 16 == 0) && ((uintptr_t)o1 % 8 == 0) &&
+                     ((uintptr_t)o2 % 8 == 0);
+    if (vec) {
+        for (size_t e = 4 * (size_t)lane; e < m; e += 128) {
+            const float4 xv = *reinterpret_cast<const float4 *>(xr + e);
+            const float4 mv = __ldg(reinterpret_cast<const float4 *>(mr + e));
+            const float v[4] = {__fsub_rn(xv.x, mv.x), __fsub_rn(xv.y, mv.y), __fsub_rn(xv.z, mv.z), __fsub_rn(xv.w, mv.w)};
+            __align__(8) __nv_bfloat16 h[4];
+            __align__(8) __nv_bfloat16 l[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                h[i] = __float2bfloat16_rn(v[i]);
+                l[i] = __float2bfloat16_rn(__fsub_rn(v[i], __bfloat162float(h[i])));
+                acc += (double)v[i] * (double)v[i];
+            }
+            *reinterpret_cast<uint2 *>(o1 + e) = *reinterpret_cast<const uint2 *>(h);
+            *reinterpret_cast<uint2 *>(o2 + e) = *reinterpret_cast<const uint2 *>(l);
+        }
+    } else {
+        for (size_t e = lane; e < m; e += 32) {
+            const float v = __fsub_rn(xr[e], mr[e]);
+            const __nv_bfloat16 h = __float2bfloat16_rn(v);
+            const float r = __fsub_rn(v, __bfloat162float(h));
+            o1[e] = h;
+            o2[e] = __float2bfloat16_rn(r);
+            acc += (double)v * (double)v;
+        }
     }
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
