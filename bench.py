@@ -173,11 +173,12 @@ def run_ours(args, rank, world, local_rank, dist):
     capi.check(capi.lib().fdb_vs_download(gen.h, capi.f32p(host_x)))
     gen.close()
 
-    # the build runs twice: the first one pays the one-off costs (module load, first cudaMalloc of
-    # 2 GB of scratch, clock ramp) and is reported as sec_cold, the second one is the number
-    builds = []
+    # the build runs three times: the first one pays the one-off costs (module load, first cudaMalloc of
+    # 2 GB of scratch, clock ramp) and is reported as sec_cold; sec is the faster of the two warm ones (a
+    # warm build occasionally waits ~1 s on the driver freeing the previous database's buffers)
+    builds, build_e2e = [], []
     db = None
-    for attempt in range(2):
+    for attempt in range(3):
         if db is not None:
             db.close()
         t0 = time.perf_counter()
@@ -195,6 +196,7 @@ def run_ours(args, rank, world, local_rank, dist):
         t_build = time.perf_counter() - t1
         build_launches = ctx.launches - launches0
         builds.append(build_dev_ms * 1e-3)
+        build_e2e.append((t_upload + t_build, t_upload))
     rounds_coarse = sum(1 for e in events if e[0] == "ClusterEvent" and e[1][0] == "FinishedCentroidUpdate")
     ix = db.index
     ix.set_timing(True)
@@ -409,8 +411,10 @@ def run_ours(args, rank, world, local_rank, dist):
         "scan_large_partition_major": scan_large_pm,
         "cpu_baseline": cpu_baseline,
         "parity": {"queries_checked": ns, "id_mismatches": mism, "distances_bit_equal": dist_bits},
-        "build": {"metric": "ivfpq_build_sec_100kx1536", "sec": build_dev_ms * 1e-3, "sec_cold": builds[0],
-                  "e2e_sec": t_upload + t_build, "h2d_sec": t_upload, "gpu_launches": int(build_launches),
+        "build": {"metric": "ivfpq_build_sec_100kx1536", "sec": min(builds[1:]), "sec_cold": builds[0],
+                  "sec_all": builds,
+                  "e2e_sec": build_e2e[1 + int(np.argmin(builds[1:]))][0], "h2d_sec": build_e2e[1 + int(np.argmin(builds[1:]))][1],
+                  "gpu_launches": int(build_launches),
                   "lloyd_updates": len(upd), "lloyd_reassignments": len(rea),
                   "reassignments_coarse": n_rea_coarse, "reassignments_pq_all_divisions": n_rea_pq,
                   "cpu_port_extrapolated_sec": cpu_build,
