@@ -656,6 +656,24 @@ def test_partition_major_scan_16_bit_tables(eng, ctx, oracle, monkeypatch, N, P,
     ix.close()
 
 
+def test_forced_scan_mode_fails_loudly_when_the_shape_is_not_taken(eng, ctx, oracle, monkeypatch):
+    """FDB_FILTER_SCAN forces a scan kernel; a shape that kernel does not take is an error, not a silent fallback."""
+    from flechasdb_b200.db import Error
+    N, P, D, Cn, M = 120, 20, 5, 17, 3000          # D = 5: no partition-major kernel
+    coarse, cbs, off, codes = random_index(oracle, N, P, D, Cn, M)
+    ix = eng.Index.create(ctx, coarse, cbs, off, codes.astype(np.uint8))
+    q = data(oracle, 16, N, SEED + 87)
+    for mode in ("partition", "partition16"):
+        monkeypatch.setenv("FDB_FILTER_SCAN", mode)
+        with pytest.raises(Exception) as ei:
+            ix.query(q, 5, 4)
+        assert "FDB_FILTER_SCAN" in str(ei.value)
+    monkeypatch.setenv("FDB_FILTER_SCAN", "query")
+    oix = oracle.QueryIndex(coarse, cbs, off, codes)
+    _check_query(ix, oix, q, 5, 4, 0)
+    ix.close()
+
+
 def test_partition_major_scan_on_clustered_data_and_large_batch(eng, ctx, oracle, monkeypatch):
     monkeypatch.setenv("FDB_FILTER_SCAN", "partition")
     N, P, D, Cn, M, k, nprobe = 96, 50, 12, 64, 8000, 5, 5
