@@ -92,6 +92,7 @@ struct FilterState {
     cudaEvent_t begun = nullptr;     // batch_begin's resets, the slot streams wait for it
     unsigned long long *h_counters = nullptr;  // the last 128 bytes of the context's pinned staging area
     size_t chunk_q = 4096;
+    unsigned bcounters_dense = 0;   // partitions evaluated exactly by the last filter_probe_dense
     ~FilterState() {
         for (Slot &sl : slot) {
             if (sl.stream) cudaStreamDestroy(sl.stream);
@@ -1034,6 +1035,96 @@ __global__ void __launch_bounds__(256) probe_exact_kernel(ProbeParams p) {
     }
 }
 
+// ---- probes for nprobe beyond the probe filter's 24 (build semantic): dense distance rows with the exact
+// value only where it can matter.  The reference evaluates all P distances and keeps the nprobe smallest; here
+// the tensor-pipe scores pick the partitions that can be among them: a lower bound t0 of the nprobe-th largest
+// score (every lane keeps its own 8 largest; the nprobe-th largest of those 256 real scores cannot exceed the
+// nprobe-th largest of all) minus the band.  Those partitions get their exact distance
+// (probe_exact_kernel), all others +inf, and the exact selection kernel runs on the rows unchanged.
+constexpr int PC_MAXM = 8;   // nprobe <= 256
+__global__ void __launch_bounds__(128) probe_cand_kernel(const float *S, size_t ldS, const float *xn2d, size_t D,
+                                                         const unsigned *cmax2t, size_t ntiles, size_t nq, size_t P,
+                                                         int nprobe, float gamma1, float eta, float *dist, uint32_t *items,
+                                                         unsigned *item_count, unsigned cap, unsigned *bad_flag) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t q = (size_t)blockIdx.x * 4 + warp;
+    if (q >= nq) return;
+    float xn2 = 0.0f;
+    for (size_t d = 0; d < D; ++d) xn2 += xn2d[d * nq + q];
+    xn2 *= 1.0001f;
+    unsigned cb = 0;
+    for (size_t t = 0; t < ntiles; ++t) cb = max(cb, cmax2t[t]);
+    const float cmax2 = __uint_as_float(cb);
+    const float E = gamma1 * sqrtf(xn2 * cmax2) * 1.0001f + 1.2e-7f * (0.5f * cmax2);
+    bool bad = !(xn2 < 1e30f);
+    const float *Sq = S + q * ldS;
+    float top[PC_MAXM];
+#pragma unroll
+    for (int i = 0; i < PC_MAXM; ++i) top[i] = -INF;
+    for (size_t pi = lane; pi < P; pi += 32) {
+        float sv = Sq[pi];
+        bad |= !(fabsf(sv) < 1e30f);
+#pragma unroll
+        for (int i = 0; i < PC_MAXM; ++i) {   // descending insertion
+            const float hi = fmaxf(top[i], sv);
+            sv = fminf(top[i], sv);
+            top[i] = hi;
+        }
+    }
+    // the nprobe-th largest of the 32 * PC_MAXM scores the lanes kept (bit descent on the ordered keys): a lower
+    // bound of the nprobe-th largest of all P, close to it when 32 * PC_MAXM >= 2 nprobe
+    uint32_t tk[PC_MAXM];
+#pragma unroll
+    for (int i = 0; i < PC_MAXM; ++i) tk[i] = fkey(top[i]);
+    uint32_t K = 0;
+    for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t c = K | (1u << bit);
+        int n = 0;
+#pragma unroll
+        for (int i = 0; i < PC_MAXM; ++i) n += tk[i] >= c;
+        if (__reduce_add_sync(0xffffffffu, n) >= nprobe) K = c;
+    }
+    const float am = fkey_inv(K);
+    float thr = -INF;
+    if (am > -INF) {
+        const float dtau = fmaxf(0.0f, xn2 - 2.0f * am + 2.0f * E);
+        const float shift = 1.3e-7f * sqrtf(dtau) * (sqrtf(xn2) + sqrtf(cmax2));
+        thr = am - BAND_SAFETY * (2.0f * E + 1.01f * eta * dtau + shift);
+        bad |= !(fabsf(thr) < 1e30f);
+    }
+    if (__any_sync(0xffffffffu, bad)) {
+        if (lane == 0) atomicOr(bad_flag, 1u);
+        return;
+    }
+    for (size_t base = 0; base < P; base += 32) {
+        const size_t pi = base + lane;
+        const bool cand = pi < P && Sq[pi] >= thr;
+        const unsigned bal = __ballot_sync(0xffffffffu, cand);
+        unsigned first = 0;
+        if (bal && lane == 0) first = atomicAdd(item_count, (unsigned)__popc(bal));
+        first = __shfl_sync(0xffffffffu, first, 0);
+        if (cand) {
+            const unsigned i = first + __popc(bal & ((1u << lane) - 1u));
+            if (i < cap) {
+                items[2 * (size_t)i] = (uint32_t)q;
+                items[2 * (size_t)i + 1] = (uint32_t)pi;
+            } else {
+                atomicOr(bad_flag, 2u);
+            }
+        } else if (pi < P) {
+            dist[q * P + pi] = INF;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) probe_scatter_kernel(const uint32_t *items, const float *item_d,
+                                                            const unsigned *item_count, unsigned cap, size_t P,
+                                                            float *dist) {
+    const unsigned n = min(*item_count, cap);
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        dist[(size_t)items[2 * (size_t)i] * P + items[2 * (size_t)i + 1]] = item_d[i];
+}
+
 // the probe list, the pair constants K and the magnitude W of every query; one warp per query
 __global__ void __launch_bounds__(128) probe_finalize_kernel(ProbeParams p) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1672,6 +1763,56 @@ int filter_probe(fdb_index *ix, const float *d_q, size_t nq, size_t nprobe, Even
     FDB_CHECK_LAUNCH();
     sl->probes_from_filter = true;
     fs->batch_reprobe = true;
+    *done = true;
+    return FDB_OK;
+}
+
+// dense distance rows for the exact selection kernel, exact where it can matter (probe_cand_kernel); *done =
+// false when the shape is not taken or the scores were not usable (the caller then evaluates all P distances)
+int filter_probe_dense(fdb_index *ix, const float *d_q, size_t nq, size_t nprobe, float *d_dist, bool *done) {
+    *done = false;
+    FilterState *fs = ix->filter;
+    if (!fs || !fs->tc_coarse || nprobe > 32 * PC_MAXM || (uintptr_t)d_q % 16 != 0 || getenv("FDB_PROBE_DENSE_OFF") ||
+        ix->P < 4 * nprobe)
+        return FDB_OK;
+    fdb_ctx *ctx = ix->ctx;
+    FilterState::Slot *sl = fs->cur;
+    cudaStream_t st = ctx->stream;
+    const size_t N = ix->N, P = ix->P, D = ix->D, s = ix->s;
+    const size_t cap = nq * std::min<size_t>(P, 6 * nprobe + 64);
+    if (cap >= (1ull << 31)) return FDB_OK;
+    FDB_TRY(tc_prepare_rows(ctx, d_q, nq, N, s, D, fs->mu.p, &sl->rows));
+    sl->rows_ready = true;
+    const size_t ldS = fs->coarse_tc.nb * fs->coarse_tc.np;
+    FDB_TRY(sl->S.ensure(nq * ldS));
+    FDB_TRY(tc_gemm_raw(ctx, sl->rows, fs->coarse_tc, 0, 1.0f, 1, sl->S.p, ldS, fs->coarse_tc.np));
+    FDB_TRY(sl->ps_items.ensure(2 * cap));
+    FDB_TRY(sl->ps_dist.ensure(cap));
+    FDB_TRY(sl->ps_count.ensure(2));
+    FDB_CUDA(cudaMemsetAsync(sl->ps_count.p, 0, 2 * sizeof(unsigned), st));
+    probe_cand_kernel<<<(unsigned)((nq + 3) / 4), 128, 0, st>>>(sl->S.p, ldS, sl->rows.xn2.p, D, fs->coarse_tc.cmax2.p,
+                                                               fs->coarse_tc.nb, nq, P, (int)nprobe, tc_gamma(N),
+                                                               ((float)N / 16.0f + 20.0f) * U24, d_dist, sl->ps_items.p,
+                                                               sl->ps_count.p, (unsigned)cap, sl->ps_count.p + 1);
+    ProbeParams pp;
+    memset(&pp, 0, sizeof(pp));
+    pp.q = d_q;
+    pp.coarse = ix->coarse.p;
+    pp.N = N;
+    pp.quad = (N % 16 == 0) ? 1 : 0;
+    pp.items = sl->ps_items.p;
+    pp.item_d = sl->ps_dist.p;
+    pp.item_count = sl->ps_count.p;
+    probe_exact_kernel<<<(unsigned)std::min<size_t>((cap * 4 + 255) / 256, (size_t)ctx->sm_count * 8), 256, 0, st>>>(pp);
+    probe_scatter_kernel<<<(unsigned)ctx->sm_count * 4, 256, 0, st>>>(sl->ps_items.p, sl->ps_dist.p, sl->ps_count.p,
+                                                                    (unsigned)cap, P, d_dist);
+    ctx->launches += 3;
+    FDB_CHECK_LAUNCH();
+    unsigned h[2] = {0, 0};
+    FDB_CUDA(cudaMemcpyAsync(h, sl->ps_count.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+    FDB_CUDA(cudaStreamSynchronize(st));
+    if (h[1] != 0) return FDB_OK;   // non-finite scores or more candidates than room: all P distances instead
+    fs->bcounters_dense = h[0];
     *done = true;
     return FDB_OK;
 }

@@ -85,6 +85,9 @@ bool filter_eligible(const fdb_index *ix, size_t nq, size_t k, size_t nprobe);
 // *done = false when the shape is not taken (the caller then runs the exact probe kernels).
 // *h_nhard = queries among the *h_nfb handed back whose probe list is not the reference's.
 int filter_probe(fdb_index *ix, const float *d_q, size_t nq, size_t nprobe, EventLog *log, bool *done);
+// nprobe beyond the probe filter, build semantic: dense rows of coarse distances for the exact selection kernel,
+// exact for the partitions the tensor-pipe scores cannot rule out and +inf elsewhere
+int filter_probe_dense(fdb_index *ix, const float *d_q, size_t nq, size_t nprobe, float *d_dist, bool *done);
 // A batch is answered slice by slice (filter_probe + filter_query per slice, nothing waits on the
 // host); the queries a slice could not decide are appended, with their probe lists, to a batch
 // list that filter_batch_end hands to the exact pipeline.  *h_nhard = those among the *h_nfb

@@ -546,7 +546,11 @@ int probe_device(fdb_index *ix, const float *d_q, size_t nq, size_t nprobe, int 
     dp.nb = 1;
     dp.c = ix->coarse.p;
     dp.k = ix->P;
-    FDB_TRY(launch_exact_matrix(ctx, dp, ix->dist.p));
+    // build semantic (canonical order, no push history): only the partitions the tensor-pipe scores cannot rule
+    // out need their exact distance (adc_filter.cu, filter_probe_dense)
+    bool dense = false;
+    if (mode == FDB_QUERY_BUILD && nprobe > 24) FDB_TRY(filter_probe_dense(ix, d_q, nq, nprobe, ix->dist.p, &dense));
+    if (!dense) FDB_TRY(launch_exact_matrix(ctx, dp, ix->dist.p));
     if (log) FDB_TRY(log->mark(1));
     const size_t smem = (size_t)PROBE_WARPS * 2 * nprobe * sizeof(float);
     probe_select_kernel<<<(unsigned)((nq + PROBE_WARPS - 1) / PROBE_WARPS), PROBE_WARPS * 32, smem,

@@ -466,6 +466,27 @@ def test_filter_path_tensor_pipe_gemms(eng, ctx, oracle, N, P, D, Cn, M, k, npro
     ix.close()
 
 
+@pytest.mark.parametrize("N,P,D,Cn,M,k,nprobe", [
+    (96, 600, 12, 64, 20000, 10, 64),     # N % 64 != 0: 16-wide K chunks; two column tiles and a bit
+    (128, 1100, 4, 64, 30000, 5, 128),    # five column tiles, four scores per lane
+    (64, 300, 4, 256, 9000, 10, 33),      # just beyond the probe filter's 24
+])
+def test_probes_beyond_the_probe_filter_use_dense_rows(eng, ctx, oracle, monkeypatch, N, P, D, Cn, M, k, nprobe):
+    """nprobe > 24, build semantic: exact coarse distances only for the partitions the tensor-pipe scores
+    cannot rule out (filter_probe_dense); probe lists and results equal the oracle's, and the full matrix."""
+    coarse, cbs, off, codes = random_index(oracle, N, P, D, Cn, M, empty=(1,))
+    ix = eng.Index.create(ctx, coarse, cbs, off, codes.astype(np.uint8))
+    oix = oracle.QueryIndex(coarse, cbs, off, codes)
+    q = data(oracle, 150, N, SEED + 88)
+    for mode in (1, 0):
+        _check_query(ix, oix, q, k, nprobe, mode)
+    got_p, got_d = ix.probe(q, nprobe, 1)
+    monkeypatch.setenv("FDB_PROBE_DENSE_OFF", "1")
+    want_p, want_d = ix.probe(q, nprobe, 1)
+    assert (got_p == want_p).all() and (got_d == want_d).all()
+    ix.close()
+
+
 def test_probe_filter_ties_and_far_offsets(eng, ctx, oracle):
     """Duplicated coarse centroids (exactly tied coarse distances -> NBestByKey history decides the
     probe list) and data far from the origin (wide band): both must still equal the oracle."""
