@@ -45,6 +45,35 @@ __global__ void __launch_bounds__(PROBE_WARPS * 32) probe_select_kernel(
     uint32_t *op = probes + q * nprobe;
     float *od = probe_d + q * nprobe;
     bool nan = false;
+    if (mode == FDB_QUERY_STORED && nprobe > 24) {
+        // Many slots: NBestByKey's push history only matters when distances tie.  When the nprobe smallest are
+        // pairwise distinct and nothing outside equals the largest of them, the kept set is unique and the
+        // stable sort puts it in ascending order: the plain sorted selection is the answer.  Otherwise (a few
+        // per cent of the queries at nprobe = 128: f32 distances do collide) the slots are emulated below.
+        WarpSorted sl;
+        sl.init(sd, sa, nprobe);
+        feed_sorted(sl, (int)P, 0u, key, lane);
+        __syncwarp();
+        bool tie = false;
+        for (int i = lane; i + 1 < sl.len; i += 32) tie |= sd[i] == sd[i + 1];
+        const float mx = sd[sl.len - 1];
+        int eq = 0;
+        for (int i = lane; i < (int)P; i += 32) {
+            const float v = dq[i];
+            eq += v == mx;
+            tie |= v != v;
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) eq += __shfl_xor_sync(0xffffffffu, eq, off);
+        if (!__any_sync(0xffffffffu, tie) && eq == 1) {
+            for (int i = lane; i < sl.len; i += 32) {
+                od[i] = sd[i];
+                op[i] = sa[i];
+            }
+            return;
+        }
+        __syncwarp();
+    }
     if (mode == FDB_QUERY_STORED) {
         WarpNBest nb;
         nb.init(sd, sa, nprobe);

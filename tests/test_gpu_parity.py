@@ -487,6 +487,25 @@ def test_probes_beyond_the_probe_filter_use_dense_rows(eng, ctx, oracle, monkeyp
     ix.close()
 
 
+def test_stored_probe_selection_with_many_slots_and_ties(eng, ctx, oracle):
+    """nprobe > 24 in the stored semantic: the sorted selection when the distances are distinct, the slot
+    emulation when they tie (duplicated centroids: every distance occurs several times)."""
+    N, P, D, Cn, M = 32, 400, 4, 32, 6000
+    coarse, cbs, off, codes = random_index(oracle, N, P, D, Cn, M)
+    coarse[200:] = coarse[:200]                    # every centroid twice: ties everywhere
+    coarse[37] = coarse[5]
+    q = data(oracle, 40, N, SEED + 89)
+    for c in (coarse, random_index(oracle, N, P, D, Cn, M)[0]):
+        ix = eng.Index.create(ctx, c, cbs, off, codes.astype(np.uint8))
+        oix = oracle.QueryIndex(c, cbs, off, codes)
+        for nprobe in (25, 64, 130):
+            got_p, got_d = ix.probe(q, nprobe, 0)
+            for qi in range(len(q)):
+                rc, want_p, want_d = oix.probe(q[qi], nprobe, 0)
+                assert rc == 0 and (got_p[qi] == want_p).all() and (got_d[qi] == want_d).all(), (nprobe, qi)
+        ix.close()
+
+
 def test_probe_filter_ties_and_far_offsets(eng, ctx, oracle):
     """Duplicated coarse centroids (exactly tied coarse distances -> NBestByKey history decides the
     probe list) and data far from the origin (wide band): both must still equal the oracle."""
