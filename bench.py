@@ -7,9 +7,17 @@ A "step" is one pass of the query hot path over one batch of 10 000 synthetic qu
 (BASELINE.json configs[1]: 10k queries vs the 100k x 1536 DB, P=100 D=12 C=256, K=10,
 NPROBE=5).  `value` = queries/s with queries resident in HBM (device-timed with CUDA
 events); `e2e` = the same through the host-buffer C-ABI call (H2D of the queries and D2H of
-the results inside the timed region).  N > 1: every rank holds a replica of the index and
-runs its own query batch (queries are the sharded unit; no data-path collective) -> weak
-scaling.  `--impl reference` times the CPU restatement of the reference (oracle/) instead.
+the results inside the timed region).
+
+N > 1 (torchrun, one rank per GPU): the SHARDED design north_star names, with the collectives in the timed
+region.  A step = one build of BASELINE.json configs[2] (1M x 768, P=1024 D=48 C=256) with the rows sharded
+over the ranks: k-means++ with one packed NCCL all-gather per round, Lloyd with one all-reduce of
+[sums || counts] per round, all issued by libflechasdb_b200.so on its own stream (fdb_comm).  `value` =
+rows/s of the whole job (strong scaling: the work is fixed).  The same run carries configs[4] (100M x 12 B
+code lists sharded by partition, 10k queries, nprobe 8..128, one packed all-gather + merge per batch) under
+`sharded_query`, and checks a sample of both against the CPU oracle.  The N = 1 line carries both sharded
+workloads at world = 1 under `sharded` (the base of the 1 -> 8 curve).
+`--impl reference` times the CPU restatement of the reference (oracle/) instead.
 """
 import argparse
 import json
@@ -426,6 +434,333 @@ def run_ours(args, rank, world, local_rank, dist):
 
 
 # ------------------------------------------------------------------------------------------
+# Sharded workloads (BASELINE.json configs[2] and configs[4]): rows / code lists sharded over the ranks,
+# collectives issued by the library (fdb_comm) on its stream.
+M2, N2, P2, D2, C2 = 1_000_000, 768, 1024, 48, 256
+M4, N4, P4, D4, C4, NQ4 = 100_000_000, 96, 16384, 12, 256, 10_000
+NPROBES4 = (8, 16, 32, 64, 128)
+METRIC_SHARDED = "ivfpq_sharded_build_rows_per_s_1Mx768"
+WORKLOAD_SHARDED = ("configs[2]: build M=1M N=768 D=48 P=1024 C=256, rows sharded over the ranks, NCCL all-gather per "
+                    "k-means++ round and all-reduce per Lloyd round inside the library")
+
+
+class FixedSeeds:
+    """the same injected draws on every rank (stand-in for thread_rng)"""
+
+    def __init__(self, seed):
+        self.rng = np.random.default_rng(seed)
+
+    def first(self, n, nb):
+        return self.rng.integers(0, n, nb).astype(np.uint32)
+
+    def draws(self, nb, count):
+        return (self.rng.integers(0, 1 << 23, (nb, count), dtype=np.uint32).astype(np.float32)
+                * np.float32(2.0 ** -23))
+
+
+def make_comm(engine, ctx, rank, world, dist):
+    def exchange(ident):
+        box = [ident]
+        dist.broadcast_object_list(box, src=0)
+        return box[0]
+    return engine.Comm(ctx, world, rank, exchange if world > 1 else None)
+
+
+def gather_objects(dist, obj, world):
+    if dist is None or world == 1:
+        return [obj]
+    out = [None] * world
+    dist.all_gather_object(out, obj)
+    return out
+
+
+def sharded_build_parity(engine, sharded, ctx, comm, dist, rank, world):
+    """A small sharded k-means (real NCCL) against the CPU oracle: seeding state bit-exact for the picked rows,
+    3 Lloyd rounds: centroids to 1e-4 relative (the shards' partial sums are added in another order),
+    assignments exact given the centroids."""
+    from oracle import pyoracle as oracle
+    n, m, k, rounds = 16384, 768, 64, 3
+    lo, hi = engine.shard_rows(n, world, rank)
+    vs = engine.VectorSet.generate(ctx, hi - lo, m, SEED_DATA + 41, start=lo * m)
+    km = engine.KMeans(vs, k)
+    seeds = FixedSeeds(99)
+    picked = km.seed_run_sharded(comm, n, seeds.first(n, 1), seeds.draws(1, k - 1))
+    cent0, idx0 = km.get()
+    grads, nrounds, _ = km.run_sharded(comm, rounds)
+    cent, idx = km.get()
+    parts = gather_objects(dist, (idx0[0], idx[0]), world)
+    km.close()
+    vs.close()
+    if rank != 0:
+        return None
+    x = oracle.fill_uniform(n * m, SEED_DATA + 41).reshape(n, m)
+    gi0 = np.concatenate([p[0] for p in parts])
+    gi = np.concatenate([p[1] for p in parts])
+    rc, oc0, oi0, _, _ = oracle.kmeans_init(x, k, int(picked[0, 0]), chosen=picked[0, 1:])
+    rc2, oc, oi, og, _ = oracle.kmeans_lloyd(x, k, oc0, oi0, max_rounds=rounds)
+    rel = float(np.max(np.abs(cent[0] - oc)) / max(float(np.max(np.abs(oc))), 1e-30))
+    rc3, want_idx = oracle.kmeans_reassign(x, k, cent[0])
+    return {"workload": "%d x %d rows sharded x%d, k=%d, %d Lloyd rounds, vs the CPU oracle" % (n, m, world, k, rounds),
+            "seeding_centroids_bit_equal": bool(rc == 0 and (cent0[0] == oc0).all()),
+            "seeding_assignments_equal": bool((gi0 == oi0).all()),
+            "centroids_max_rel_err": rel, "centroids_within_1e-4": bool(rc2 == 0 and rel <= 1e-4),
+            "assignments_exact_given_centroids": bool(rc3 == 0 and (gi == want_idx).all()),
+            "gradient_rel_err": float(abs(float(grads[0][-1]) - float(og[-1])) / max(abs(float(og[-1])), 1e-30))}
+
+
+def run_sharded_build(args, engine, sharded, ctx, comm, rank, world, steps, warmup):
+    """configs[2] with the rows sharded.  Device-timed (events on the library's stream, which carries the
+    collectives), max over ranks."""
+    lo, hi = engine.shard_rows(M2, world, rank)
+    phase_names = ("coarse_seeding", "coarse_lloyd", "residues", "pq_seeding", "pq_lloyd")
+    secs, phases, launches, colls, stats = [], [], 0, 0, None
+    for it in range(warmup + steps):
+        vs = engine.VectorSet.generate(ctx, hi - lo, N2, SEED_DATA + 2, start=lo * N2)
+        comm.barrier()
+        marks = []
+
+        def tick(name):
+            marks.append(ctx.timer_stop())      # device ms since timer_start (synchronises)
+        l0, c0 = ctx.launches, comm.collectives
+        ctx.timer_start()
+        b = sharded.ShardedDatabaseBuilder(vs, comm, M2, FixedSeeds(SEED_KMEANS)) \
+            .with_partitions(P2).with_divisions(D2).with_clusters(C2).build(tick=tick)
+        total_ms = marks[-1]
+        t = comm.max_f64([total_ms] + marks)
+        if it >= warmup:
+            secs.append(t[0] * 1e-3)
+            ph = np.diff(np.concatenate([[0.0], t[1:]])) * 1e-3
+            phases.append(ph)
+            launches, colls = ctx.launches - l0, comm.collectives - c0
+        stats = b.stats
+        if it == warmup + steps - 1:
+            coarse, cbs, part, codes = b.quantisers()
+            sizes = np.bincount(part, minlength=P2)
+        b.close()
+        vs.close()
+    ph = np.mean(phases, axis=0)
+    sec = float(np.mean(secs))
+    return {"sec": sec, "sec_all": secs, "rows_per_s": M2 / sec,
+            "phase_sec": {n_: float(v) for n_, v in zip(phase_names, ph)},
+            "gpu_launches": int(launches), "collectives": int(colls),
+            "lloyd_rounds": {"coarse": stats["rounds_coarse"], "pq_max": max(stats["rounds_pq"])},
+            "reassignments": stats["reassignments"],
+            "local_partition_sizes": sizes, "coarse_sum": float(coarse.astype(np.float64).sum()),
+            "codebook_sum": float(cbs.astype(np.float64).sum())}
+
+
+def run_sharded_build_e2e(args, engine, sharded, ctx, comm, rank, world, steps):
+    """the same build from HOST rows: every rank uploads its shard from pinned memory, builds, and reads the
+    quantisers and its rows' partition ids / PQ codes back -- all inside the timed region"""
+    lo, hi = engine.shard_rows(M2, world, rank)
+    gen = engine.VectorSet.generate(ctx, hi - lo, N2, SEED_DATA + 2, start=lo * N2)
+    keep, host = pinned_empty((hi - lo, N2), np.float32)
+    from flechasdb_b200 import _capi as capi_
+    capi_.check(capi_.lib().fdb_vs_download(gen.h, capi_.f32p(host)))
+    gen.close()
+    secs = []
+    d2h = 0
+    for it in range(1 + steps):
+        comm.barrier()
+        t0 = time.perf_counter()
+        vs = engine.VectorSet.upload(ctx, host)
+        b = sharded.ShardedDatabaseBuilder(vs, comm, M2, FixedSeeds(SEED_KMEANS)) \
+            .with_partitions(P2).with_divisions(D2).with_clusters(C2).build()
+        coarse, cbs, part, codes = b.quantisers()
+        dt = time.perf_counter() - t0
+        d2h = coarse.nbytes + cbs.nbytes + part.nbytes + codes.nbytes
+        t = comm.max_f64([dt])
+        if it >= 1:
+            secs.append(float(t[0]))
+        b.close()
+        vs.close()
+    sec = float(np.mean(secs))
+    return {"value": M2 / sec, "unit": "rows/s", "sec": sec,
+            "h2d_bytes_per_step": int(M2) * N2 * 4, "d2h_bytes_per_step": int(d2h) * 1 if world == 1 else None,
+            "d2h_bytes_per_step_rank0": int(d2h),
+            "note": "wall clock around upload (pinned host rows) + build + read-back of the quantisers and of this "
+                    "rank's partition ids / PQ codes, max over ranks; h2d bytes are the whole job's"}
+
+
+def synth_lists(rank, world, sharded):
+    """configs[4]: partition sizes multinomial(M, 1/P); the codes of partition p come from a generator seeded
+    by p, so any rank (and the oracle check) can reproduce any list"""
+    rng = np.random.default_rng(4)
+    sizes = rng.multinomial(M4, np.ones(P4) / P4)
+    owner = sharded.owned_partitions(sizes, world)
+    return sizes, owner
+
+
+def list_codes(p, n):
+    return np.random.default_rng([0xC0DE, int(p)]).integers(0, C4, (int(n), D4), dtype=np.uint8)
+
+
+def run_sharded_query(args, engine, sharded, ctx, comm, dist, rank, world, steps, warmup, hbm_peak):
+    """configs[4]: code lists sharded by partition, the query batch replicated, one packed all-gather + merge"""
+    from flechasdb_b200 import _capi as capi
+    sizes, owner = synth_lists(rank, world, sharded)
+    rng = np.random.default_rng(5)
+    coarse = rng.random((P4, N4), dtype=np.float32)
+    cbs = rng.random((D4, C4, N4 // D4), dtype=np.float32) - np.float32(0.5)
+    off = sharded.shard_offsets(sizes, owner, rank)
+    mine = np.nonzero(owner == rank)[0]
+    codes = np.empty((int(off[-1]), D4), np.uint8)
+    for p in mine:
+        codes[int(off[p]):int(off[p + 1])] = list_codes(p, sizes[p])
+    ix = engine.Index.create(ctx, coarse, cbs, off, codes)
+    del codes
+    d_q = ctx.alloc(NQ4 * N4 * 4)
+    ctx.fill_uniform(d_q, NQ4 * N4, SEED_QUERY + 7)
+    k = K
+    outs = [ctx.alloc(NQ4 * k * 4) for _ in range(3)] + [ctx.alloc(NQ4 * 4)]
+    rows = {}
+    for nprobe in NPROBES4:
+        ms = []
+        c0 = comm.collectives
+        for it in range(warmup + steps):
+            ctx.flush_l2()
+            comm.barrier()
+            ctx.timer_start()
+            ix.query_sharded(comm, d_q, NQ4, k, nprobe, *outs, mode=capi.QUERY_STORED)
+            t = comm.max_f64([ctx.timer_stop()])
+            if it >= warmup:
+                ms.append(float(t[0]))
+        st = ix.last_stats()
+        scanned = comm_sum(comm, float(st[3]))
+        m = float(np.mean(ms))
+        gbs = scanned * D4 / (m * 1e-3) / 1e9
+        rows["nprobe_%d" % nprobe] = {
+            "ms_per_batch": m, "queries_per_s": NQ4 / (m * 1e-3), "scanned_vectors_all_ranks": int(scanned),
+            "algorithmic_scan_GBps_all_ranks": gbs, "frac_of_hbm_per_gpu": gbs / world / hbm_peak,
+            "collectives_per_batch": (comm.collectives - c0) // (warmup + steps) - 1,   # minus the timing all-reduce
+            "tied_queries_remerged": ix.last_sharded_ties(),
+            "note": "whole call (probe + tables + scan + all-gather + merge), device-timed, max over ranks; the "
+                    "fraction divides the whole call, not the scan kernel, by the HBM peak"}
+    # ---- parity: the first queries against the CPU oracle on the lists they probe
+    from oracle import pyoracle as oracle
+    ns, nprobe = 200, 8
+    ix.query_sharded(comm, d_q, NQ4, k, nprobe, *outs, mode=capi.QUERY_STORED)
+    got = [ctx.download(outs[0], (NQ4, k), np.uint32)[:ns], ctx.download(outs[1], (NQ4, k), np.uint32)[:ns],
+           ctx.download(outs[2], (NQ4, k), np.float32)[:ns], ctx.download(outs[3], (NQ4,), np.uint32)[:ns]]
+    parity = None
+    if rank == 0:
+        q = oracle.fill_uniform(ns * N4, SEED_QUERY + 7).reshape(ns, N4)
+        probed = set()
+        for qi in range(ns):
+            d = ((coarse - q[qi]) ** 2).sum(axis=1)
+            probed.update(np.argsort(d)[:nprobe + 4].tolist())     # a superset of every query's probe list
+        osz = np.zeros(P4, np.int64)
+        for p in probed:
+            osz[p] = sizes[p]
+        ooff = np.concatenate([[0], np.cumsum(osz)]).astype(np.uint64)
+        ocodes = np.zeros((int(ooff[-1]), D4), np.uint32)
+        for p in probed:
+            ocodes[int(ooff[p]):int(ooff[p + 1])] = list_codes(p, sizes[p])
+        oix = oracle.QueryIndex(coarse, cbs, ooff, ocodes)
+        rc, wp, wv, wd, wc = oix.query(q, k, nprobe, 0, nthreads=os.cpu_count() or 1)
+        covered = all(int(p) in probed for p in wp.ravel())
+        parity = {"queries_checked": ns, "nprobe": nprobe, "semantic": "stored::Database::query",
+                  "oracle_lists_cover_the_probes": bool(covered),
+                  "id_mismatches": int((wp != got[0]).any(axis=1).sum() + (wv != got[1]).any(axis=1).sum()),
+                  "distances_bit_equal": bool(rc == 0 and (wd == got[2]).all() and (wc == got[3]).all())}
+    ix.close()
+    for h in [d_q] + outs:
+        ctx.free(h)
+    return {"workload": "configs[4]: M=100M N=96 D=12 P=16384 C=256 (1.2 GB of codes), lists sharded x%d by partition "
+                        "(size-balanced), %d replicated queries, k=%d, stored semantic" % (world, NQ4, k),
+            "sweep": rows, "parity": parity}
+
+
+def comm_sum(comm, v):
+    """sum over ranks of one host double through the library's communicator (max of one-hot slots)"""
+    slots = np.zeros(comm.world)
+    slots[comm.rank] = v
+    out = np.zeros(comm.world)
+    for i in range(0, comm.world, 64):
+        out[i:i + 64] = comm.max_f64(slots[i:i + 64])
+    return float(out.sum())
+
+
+def cpu_baselines_sharded(oracle, native=None):
+    """CPU port on a bounded sample, extrapolated (a full run would take days)."""
+    if native is None:
+        try:
+            oracle.build(native=True)
+            native = True
+        except Exception:
+            native = False
+    cores = os.cpu_count() or 1
+    ns = 2000
+    x = oracle.fill_uniform(ns * N2, SEED_DATA + 2).reshape(ns, N2)
+    cc = oracle.fill_uniform(P2 * N2, 5).reshape(P2, N2)
+    t0 = time.perf_counter()
+    oracle.kmeans_reassign(x, P2, cc, nthreads=cores, native=native)
+    t_coarse = (time.perf_counter() - t0) * M2 / ns
+    cb = oracle.fill_uniform(C2 * (N2 // D2), 6).reshape(C2, N2 // D2)
+    t0 = time.perf_counter()
+    oracle.kmeans_reassign(x, C2, cb, off=0, dim=N2 // D2, nthreads=cores, native=native)
+    t_pq = (time.perf_counter() - t0) * M2 / ns * D2
+    return {"configs2_build": {"sec_per_coarse_pass": t_coarse, "sec_per_pq_pass_all_divisions": t_pq,
+                               "extrapolated_build_sec_100_rounds_each": (1 + 100) * t_coarse + (1 + 100) * t_pq,
+                               "cores": cores, "kind": "port",
+                               "sample": "one reassignment pass over %d of the %d rows (coarse; PQ division 0 x %d), "
+                                         "x rows x (k-means++ counted as one pass + 100 Lloyd rounds)" % (ns, M2, D2)}}
+
+
+def run_sharded(args, rank, world, local_rank, dist):
+    from flechasdb_b200 import _capi as capi
+    from flechasdb_b200 import engine, sharded
+    capi.lib()
+    ctx = engine.Context(local_rank)
+    comm = make_comm(engine, ctx, rank, world, dist)
+    hbm_peak, peak_src = measured_peaks()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    build = run_sharded_build(args, engine, sharded, ctx, comm, rank, world, args.steps, args.warmup)
+    clocks = sampler.stop()
+    e2e = run_sharded_build_e2e(args, engine, sharded, ctx, comm, rank, world, max(1, min(args.steps, 2)))
+    parity_build = sharded_build_parity(engine, sharded, ctx, comm, dist, rank, world)
+    query = None if args.no_sharded_query else run_sharded_query(args, engine, sharded, ctx, comm, dist, rank, world,
+                                                                max(2, min(args.steps, 3)), 2, hbm_peak)
+    sizes = gather_objects(dist, build.pop("local_partition_sizes"), world)
+    comm.close()
+    ctx.close()
+    if rank != 0:
+        return None
+    tot = np.sum(sizes, axis=0)
+    bf16_peak = measured_bf16()
+    pq_flops = 2.0 * 3 * M2 * C2 * N2 * build["lloyd_rounds"]["pq_max"]
+    pq_sec = build["phase_sec"]["pq_lloyd"]
+    seed_bytes = (P2 + C2) * float(M2) * N2 * 4
+    seed_sec = build["phase_sec"]["coarse_seeding"] + build["phase_sec"]["pq_seeding"]
+    return {
+        "metric": METRIC_SHARDED, "value": build["rows_per_s"], "unit": "rows/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": build["sec"] * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD_SHARDED, "M": M2, "N": N2, "P": P2, "D": D2, "C": C2,
+                   "l2": "inputs (3 GB of rows) exceed L2", "parallelism": "rows sharded x%d" % world},
+        "e2e": e2e, "gpu_launches": build["gpu_launches"], "collectives_per_step": build["collectives"],
+        "build": {k_: v for k_, v in build.items() if k_ != "rows_per_s"},
+        "partition_sizes_sum": int(tot.sum()), "partition_sizes_min_max": [int(tot.min()), int(tot.max())],
+        "roofline": {"kernel": "tc_assign_kernel (PQ Lloyd reassignment, all %d divisions, %d rounds; phase time incl. "
+                               "update, all-reduce and re-check)" % (D2, build["lloyd_rounds"]["pq_max"]),
+                     "bound": "tensor", "achieved": pq_flops / pq_sec / 1e12 / world, "peak": bf16_peak, "unit": "TFLOP/s",
+                     "frac": pq_flops / pq_sec / 1e12 / world / bf16_peak, "traffic": None,
+                     "note": "per GPU: issued bf16 MMA flops (3 per fp32-accurate product) of the whole job / ranks / phase "
+                             "seconds, against the sustained cuBLAS bf16 peak of MEASURED_PEAKS.json"},
+        "roofline_other_kernels": [
+            {"kernel": "seed_round_kernel (k-means++ D^2 pass, one per round)", "bound": "hbm",
+             "achieved": seed_bytes / seed_sec / 1e9 / world, "peak": hbm_peak, "unit": "GB/s",
+             "frac": seed_bytes / seed_sec / 1e9 / world / hbm_peak,
+             "note": "per GPU; phase time includes the pick, the packed all-gather and the launch gaps of every round"}],
+        "parity": parity_build, "sharded_query": query, "clocks": clocks,
+        "limiter": "see phase_sec: the k-means++ rounds are latency (kernel launches + one small all-gather each), "
+                   "the Lloyd rounds one all-reduce of %.1f MB (coarse) / %.1f MB (PQ) each"
+                   % ((P2 * N2 + P2) * 4 / 1e6, (D2 * C2 * (N2 // D2) + D2 * C2) * 4 / 1e6),
+    }
+
+
+# ------------------------------------------------------------------------------------------
 def run_scan_large(ctx, engine, hbm_peak, peak_src, m=40_000_000, p=4096, nq=2048, nprobe=16,
                    kernel="fscan_kernel (query-major, compact code lists)"):
     """The code scan where its bytes really come from HBM (BASELINE.json configs[4] scaled to one
@@ -495,6 +830,23 @@ def run_reference(args, rank, world):
     except Exception:
         native = False
     cores = os.cpu_count() or 1
+    if world > 1:
+        # the arm's workload at N > 1 is the configs[2] build: one reassignment pass of the CPU port over a row
+        # sample per step, all host threads, extrapolated to the build (1 seeding pass + 100 Lloyd rounds each)
+        vals = []
+        for _ in range(max(1, args.steps)):
+            b = cpu_baselines_sharded(oracle, native)["configs2_build"]
+            vals.append(M2 / b["extrapolated_build_sec_100_rounds_each"])
+        value = float(np.mean(vals))
+        return {
+            "impl": "reference", "metric": METRIC_SHARDED, "value": value, "unit": "rows/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": M2 / value * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD_SHARDED, "M": M2, "N": N2, "P": P2, "D": D2, "C": C2},
+            "cpu_baseline": {"value": value, "unit": "rows/s", "cores": cores, "kind": "port", "sample": b["sample"]},
+            "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
     oix = synth_index(oracle, args.m)
     ns = min(args.nq, max(cores * 8, args.cpu_queries))
     q = oracle.fill_uniform(ns * N, SEED_QUERY).reshape(ns, N)
@@ -531,6 +883,9 @@ def main():
     ap.add_argument("--m", type=int, default=M)
     ap.add_argument("--nq", type=int, default=NQ)
     ap.add_argument("--cpu-queries", type=int, default=2000)
+    ap.add_argument("--no-sharded", action="store_true",
+                    help="N = 1: skip the sharded workloads (configs[2] build, configs[4] query) at world = 1")
+    ap.add_argument("--no-sharded-query", action="store_true", help="skip configs[4] (100M codes) in the sharded run")
     ap.add_argument("--no-scan-large", action="store_true",
                     help="skip the secondary measurement of the code scan on lists that exceed L2")
     args = ap.parse_args()
@@ -545,13 +900,30 @@ def main():
     if world > 1:
         import torch
         import torch.distributed as dist_mod
+        # torch.distributed is bootstrap plumbing only (the NCCL id, gathering parity samples): gloo.  The
+        # collectives of the data path are issued by libflechasdb_b200.so on its own NCCL communicator.
         torch.cuda.set_device(local_rank)
-        dist_mod.init_process_group("nccl", device_id=torch.device("cuda:%d" % local_rank))
+        dist_mod.init_process_group("gloo")
         dist = dist_mod
     try:
-        out = run_ours(args, rank, world, local_rank, dist)
+        if world > 1:
+            out = run_sharded(args, rank, world, local_rank, dist)
+        else:
+            out = run_ours(args, rank, world, local_rank, dist)
+            if not args.no_sharded:
+                try:
+                    sh = run_sharded(args, 0, 1, local_rank, None)
+                    out["sharded"] = {"note": "the N > 1 workloads at world = 1 (base of the 1 -> 8 curve)",
+                                      "metric": sh["metric"], "value": sh["value"], "unit": sh["unit"],
+                                      "ms_per_step": sh["ms_per_step"], "e2e": sh["e2e"], "build": sh["build"],
+                                      "parity": sh["parity"], "sharded_query": sh["sharded_query"],
+                                      "roofline": sh["roofline"]}
+                    from oracle import pyoracle as oracle
+                    out["sharded"]["cpu_baselines"] = cpu_baselines_sharded(oracle)
+                except Exception as exc:   # the headline line does not depend on it
+                    out["sharded"] = {"error": repr(exc)}
         if out is not None:
-            print(json.dumps(out), flush=True)
+            print(json.dumps(out, default=lambda o: o.tolist() if hasattr(o, "tolist") else str(o)), flush=True)
     finally:
         if dist is not None:
             dist.barrier()

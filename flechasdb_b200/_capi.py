@@ -21,6 +21,8 @@ ERR_WEIGHTS = -5
 ERR_NAN = -6
 ERR_CUDA = -7
 ERR_UNSUPPORTED = -8
+ERR_NCCL = -9
+COMM_ID_BYTES = 128
 
 QUERY_STORED = 0
 QUERY_BUILD = 1
@@ -103,8 +105,23 @@ SIGNATURES = {
     "fdb_index_last_timing": (C.c_int, [VP, F32P, U64P]),
     "fdb_index_last_stats": (C.c_int, [VP, U64P]),
     "fdb_index_debug_band": (C.c_int, [VP, SZ, SZ, F32P, F32P, U32P, U32P, U32P]),
+    "fdb_comm_unique_id": (C.c_int, [U8P]),
+    "fdb_comm_create": (C.c_int, [VP, C.c_int, C.c_int, U8P, C.POINTER(VP)]),
+    "fdb_comm_destroy": (None, [VP]),
+    "fdb_comm_world": (C.c_int, [VP]),
+    "fdb_comm_rank": (C.c_int, [VP]),
+    "fdb_comm_collective_count": (C.c_uint64, [VP]),
+    "fdb_comm_allreduce_device": (C.c_int, [VP, VP, SZ]),
+    "fdb_comm_allgather_device": (C.c_int, [VP, VP, VP, SZ]),
+    "fdb_comm_max_f64": (C.c_int, [VP, C.POINTER(C.c_double), SZ]),
+    "fdb_kmeans_seed_run_sharded": (C.c_int, [VP, VP, SZ, U32P, F32P, U32P]),
+    "fdb_kmeans_run_sharded": (C.c_int, [VP, VP, SZ, C.c_float, F32P, U32P, U32P]),
+    "fdb_index_query_sharded": (C.c_int, [VP, VP, VP, SZ, SZ, SZ, C.c_int, VP, VP, VP, VP]),
+    "fdb_index_last_sharded_ties": (C.c_int, [VP, U32P]),
     "fdb_device_alloc": (C.c_int, [VP, SZ, C.POINTER(VP)]),
     "fdb_device_free": (C.c_int, [VP, VP]),
+    "fdb_device_upload": (C.c_int, [VP, VP, VP, SZ]),
+    "fdb_device_download": (C.c_int, [VP, VP, VP, SZ]),
     "fdb_device_fill_uniform": (C.c_int, [VP, VP, SZ, C.c_uint64, C.c_uint64]),
     "fdb_device_flush_l2": (C.c_int, [VP]),
 }

@@ -1571,6 +1571,20 @@ PScanFn pscan16_fn(size_t D) {
 bool pscan16_smem_ok(size_t D) {
     return 2 * QJ * QB * sizeof(uint32_t) + (size_t)PW * 2 * PCV * D + 6144 <= PT_BASE && pscan_smem_bytes(D, D) + 4096 <= 227 * 1024;
 }
+#include "adc_vscan.cuh"
+
+PScanFn vscan_fn(size_t D) {
+    switch (D) {
+        case 4: return vscan_kernel<1>;
+        case 8: return vscan_kernel<2>;
+        case 12: return vscan_kernel<3>;
+        case 16: return vscan_kernel<4>;
+        default: return nullptr;
+    }
+}
+size_t vscan_smem_bytes(size_t D) { return D * PT_STRIDE * 16 + 2 * VJ * VB * sizeof(uint32_t); }
+int vscan_ctas_per_sm(size_t D) { return D <= 12 ? 4 : 3; }
+
 size_t pscan_items_bound(const fdb_index *ix, size_t npairs, size_t pj) {
     size_t sum_nv = 0, max_nv = 0;
     for (size_t p = 0; p < ix->P; ++p) {
@@ -1682,6 +1696,12 @@ int filter_prepare(fdb_index *ix) {
 bool filter_eligible(const fdb_index *ix, size_t nq, size_t k, size_t nprobe) {
     return ix->filter && !getenv("FDB_QUERY_EXACT") && k <= (size_t)KMAX_FILTER && nq > 0 &&
            nq * RCAP < (1ull << 32) && ix->M < (1ull << 32) && nprobe <= 4096;
+}
+
+// when the vector-lane scan (adc_vscan.cuh) is the default
+static bool vscan_default(const fdb_index *ix, size_t nq, size_t nprobe) {
+    (void)ix, (void)nq, (void)nprobe;
+    return getenv("FDB_VSCAN_DEFAULT") != nullptr;
 }
 
 // E_q = coef * W_q (header): gamma of the GEMM that produces G (tensor pipe or FMA chain)
@@ -1911,8 +1931,19 @@ int filter_query(fdb_index *ix, const float *d_q, size_t q_base, size_t nq, size
     const size_t N = ix->N, D = ix->D, C = ix->C, s = ix->s, DC = D * C;
     const uint32_t *d_probes = sl->probes_from_filter ? sl->probes.p : ix->probes.p;
     const bool tc_g = fs->tc_g && (uintptr_t)d_q % 16 == 0;
-    // the tensor-pipe GEMM writes whole 128-row tiles of the batch: no chunking of G then
-    const size_t chunk = tc_g ? nq : std::min(nq, fs->chunk_q);
+    // scan kernel: FDB_FILTER_SCAN = "query" / "partition" / "partition16" / "vector" forces one (tests, profiling)
+    const char *scan_env = getenv("FDB_FILTER_SCAN");
+    // vector-lane scan with packed 16-bit tables (adc_vscan.cuh): D = 4, 8, 12, 16, compact codes
+    const bool v_ok = vscan_fn(D) && C <= (size_t)PT_STRIDE && ix->M > 0;
+    bool use_vscan = v_ok && vscan_default(ix, nq, nprobe);
+    if (scan_env) use_vscan = !strcmp(scan_env, "vector");
+    if (use_vscan && !v_ok) {
+        set_error("FDB_FILTER_SCAN=vector: this shape is not taken by that scan (D %zu, C %zu)", D, C);
+        return FDB_ERR_UNSUPPORTED;
+    }
+    // the tensor-pipe GEMM writes whole 128-row tiles of the batch: no chunking of G then; the vector-lane scan
+    // groups the pairs of a chunk by partition, so its chunks are as large as memory reasonably allows
+    const size_t chunk = tc_g ? nq : std::min(nq, use_vscan ? std::max<size_t>(fs->chunk_q, 32768) : fs->chunk_q);
     FDB_TRY(sl->G.ensure(chunk * DC));
     FDB_TRY(sl->Kq.ensure(nq * nprobe));
     FDB_TRY(sl->Wq.ensure(nq));
@@ -1934,7 +1965,7 @@ int filter_query(fdb_index *ix, const float *d_q, size_t q_base, size_t nq, size
         FDB_CHECK_LAUNCH();
     }
 
-    const bool records = fs->rb != 0;
+    const bool records = fs->rb != 0 && !use_vscan;   // the vector-lane scan reads the compact codes
     const size_t rb = records ? fs->rb : D;
     const int chunk_vecs = scan_chunk_vecs(rb, records);
     const size_t smem = scan_smem_bytes(ix, chunk_vecs, rb, records);
@@ -1958,20 +1989,20 @@ int filter_query(fdb_index *ix, const float *d_q, size_t q_base, size_t nq, size
     const bool long_lists = ix->M >= pscan_min_list * ix->P;
     // measured (DESIGN.md 4b, 10k-vector lists): from about 64 pairs per list on the partition-major kernels
     // win: 16-bit tables 2.67 ms, f32 tables 3.19 ms, query-major 3.26 ms at 64; 19.1 / 23.0 / 26.4 ms at 128
-    bool use_p16 = p16_ok && long_lists && pairs_per_list >= 64.0;
-    bool use_pscan = use_p16 || (p32_ok && long_lists && pairs_per_list >= 64.0);
-    if (const char *e = getenv("FDB_FILTER_SCAN")) {   // "query" / "partition" / "partition16": forced (tests, profiling)
+    bool use_p16 = !use_vscan && p16_ok && long_lists && pairs_per_list >= 64.0;
+    bool use_pscan = use_vscan || use_p16 || (p32_ok && long_lists && pairs_per_list >= 64.0);
+    if (const char *e = scan_env) {
         use_p16 = !strcmp(e, "partition16");
-        use_pscan = use_p16 || !strcmp(e, "partition");
-        if ((use_p16 && !p16_ok) || (use_pscan && !use_p16 && !p32_ok)) {
+        use_pscan = use_vscan || use_p16 || !strcmp(e, "partition");
+        if ((use_p16 && !p16_ok) || (use_pscan && !use_p16 && !use_vscan && !p32_ok)) {
             set_error("FDB_FILTER_SCAN=%s: this shape is not taken by that scan (D %zu, C %zu, k %zu, %s lists)", e, D, C, k,
                       records ? "record" : "compact");
             return FDB_ERR_UNSUPPORTED;
         }
     }
-    const size_t pj = use_p16 ? QJ : PJ;
-    const PScanFn pscan = use_p16 ? pscan16_fn(D) : pscan_fn(D, records);
-    const size_t psmem = pscan_smem_bytes(D, rb);
+    const size_t pj = use_vscan ? VJ : use_p16 ? QJ : PJ;
+    const PScanFn pscan = use_vscan ? vscan_fn(D) : use_p16 ? pscan16_fn(D) : pscan_fn(D, records);
+    const size_t psmem = use_vscan ? vscan_smem_bytes(D) : pscan_smem_bytes(D, rb);
     // probe rank 0 first (two buckets per partition) only when both buckets fill their groups
     const bool pscan_split = pairs_per_list >= 4.0 * (double)pj && nprobe > 1 && !getenv("FDB_PSCAN_NO_SPLIT");
     FDB_TRY(sl->eadd.ensure(nq));
@@ -1991,7 +2022,7 @@ int filter_query(fdb_index *ix, const float *d_q, size_t q_base, size_t nq, size
             FDB_TRY(sl->it_keys.ensure(bound * pj * PLK));
             FDB_TRY(sl->it_pos.ensure(bound * pj * PLK));
             FDB_TRY(sl->it_cnt.ensure(bound * pj));
-            if (use_p16) FDB_TRY(sl->gmm.ensure(cq * D * 2));
+            if (use_p16 || use_vscan) FDB_TRY(sl->gmm.ensure(cq * D * 2));
             FDB_CUDA(cudaMemsetAsync(sl->pg_thr.p, 0xff, nq * sizeof(unsigned), st));
         }
     }
@@ -2076,12 +2107,16 @@ int filter_query(fdb_index *ix, const float *d_q, size_t q_base, size_t nq, size
         pp.gmm = sl->gmm.p;
         pp.pcmm = fs->pcmm.p;
         pp.eadd = sl->eadd.p;
-        if (use_p16) {
+        if (use_vscan) {
+            vq_minmax_kernel<<<(unsigned)((nc * D + 7) / 8), 256, 0, st>>>(sl->G.p, nc * D, (int)C, sl->gmm.p);
+            ctx->launches++;
+        } else if (use_p16) {
             g_minmax_kernel<<<(unsigned)((nc * D + 7) / 8), 256, 0, st>>>(sl->G.p, nc * D, (int)C, sl->gmm.p);
             ctx->launches++;
         }
-        const unsigned pgrid = (unsigned)std::min<size_t>(pscan_items_bound(ix, npairs, pj), (size_t)ctx->sm_count);
-        pscan<<<pgrid, PW * 32, psmem, st>>>(pp);
+        const size_t ctas = use_vscan ? (size_t)ctx->sm_count * vscan_ctas_per_sm(D) : (size_t)ctx->sm_count;
+        const unsigned pgrid = (unsigned)std::min<size_t>(pscan_items_bound(ix, npairs, pj), ctas);
+        pscan<<<pgrid, use_vscan ? VWARPS * 32 : PW * 32, psmem, st>>>(pp);
         PMergeParams mp;
         mp.probes = d_probes;
         mp.part_off = ix->part_off.p;

@@ -182,6 +182,22 @@ int fdb_device_free(fdb_ctx *ctx, void *p) {
     return FDB_OK;
 }
 
+int fdb_device_upload(fdb_ctx *ctx, void *d_dst, const void *src, size_t bytes) {
+    ARG(ctx && (bytes == 0 || (d_dst && src)), "null argument");
+    FDB_TRY(ctx->use());
+    FDB_CUDA(cudaMemcpyAsync(d_dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    FDB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return FDB_OK;
+}
+
+int fdb_device_download(fdb_ctx *ctx, void *dst, const void *d_src, size_t bytes) {
+    ARG(ctx && (bytes == 0 || (dst && d_src)), "null argument");
+    FDB_TRY(ctx->use());
+    FDB_CUDA(cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    FDB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return FDB_OK;
+}
+
 int fdb_device_fill_uniform(fdb_ctx *ctx, float *d, size_t count, uint64_t seed, uint64_t start) {
     ARG(ctx && (d || !count), "null argument");
     FDB_TRY(ctx->use());

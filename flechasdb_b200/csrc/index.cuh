@@ -36,6 +36,8 @@ struct fdb_index {
     fdb::FilterState *filter = nullptr;   // ADC filter path (adc_filter.cu), null when not usable
     bool last_probes_exact = false;       // `probes` holds the last device batch's lists in the reference's order
     size_t last_probes_nq = 0, last_probes_nprobe = 0;
+    fdb::DevBuf<uint32_t> sh_flags, sh_list;   // sharded query: tie flags (+ a counter), list of the flagged queries
+    uint32_t last_sharded_ties = 0;
     uint64_t last_stats[4] = {0, 0, 0, 0};  // queries on the filter path, exact fallbacks, exact candidates, scanned vectors
     ~fdb_index();                         // adc_filter.cu (FilterState is complete there)
 };

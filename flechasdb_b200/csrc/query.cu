@@ -22,6 +22,7 @@
 #include <memory>
 
 #include "index.cuh"
+#include "comm.cuh"
 #include "nbest.cuh"
 
 
@@ -372,6 +373,19 @@ __global__ void scatter_results_kernel(const uint32_t *list, size_t n, size_t k,
     if (e == 0) d_c[q] = fc[r];
 }
 
+// a code >= C would index past the ADC tables and the codebooks (the reference panics on such a file)
+__global__ void __launch_bounds__(256) check_codes_kernel(const uint8_t *codes, size_t bytes, unsigned C, unsigned *bad) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x * 16;
+    unsigned worst = 0;
+    for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 16; i + 16 <= bytes; i += stride) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(codes + i);
+        const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) worst = max(worst, max(max(w[j] & 255u, (w[j] >> 8) & 255u), max((w[j] >> 16) & 255u, w[j] >> 24)));
+    }
+    if (worst >= C) atomicMax(bad, worst);
+}
+
 // ---- Partition::new on the device (src/db/build.rs:459-473) ----------------------------
 __global__ void gather_codes_kernel(const uint32_t *order, const uint32_t *coarse_idx,
                                     const uint32_t *pq_idx, const uint32_t *part_off,
@@ -473,6 +487,24 @@ int fdb_index_create(fdb_ctx *ctx, size_t N, size_t P, size_t D, size_t C, const
         if (bytes)
             FDB_CUDA(cudaMemcpyAsync(ix->codes.p + ix->h_cstart[p], codes + (size_t)off[p] * D, bytes,
                                      cudaMemcpyHostToDevice, st));
+    }
+    if (C < 256 && ix->M) {
+        // codes come from a file: the reference's table[di * C + code] panics on a code >= C (src/db/stored.rs:585)
+        unsigned *d_bad = nullptr;
+        FDB_CUDA(cudaMalloc((void **)&d_bad, sizeof(unsigned)));
+        FDB_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(unsigned), st));
+        const size_t bytes = ix->codes.n & ~(size_t)15;
+        check_codes_kernel<<<(unsigned)std::min<size_t>(4096, bytes / 4096 + 1), 256, 0, st>>>(ix->codes.p, bytes, (unsigned)C, d_bad);
+        ctx->launches++;
+        unsigned bad = 0;
+        cudaError_t e = cudaMemcpyAsync(&bad, d_bad, sizeof(unsigned), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        cudaFree(d_bad);
+        FDB_CUDA(e);
+        if (bad) {
+            set_error("a code (%u) is not below the number of codes C = %zu", bad, C);
+            return FDB_ERR_INVALID_DATA;
+        }
     }
     FDB_CUDA(cudaStreamSynchronize(st));
     FDB_TRY(filter_prepare(ix.get()));
@@ -604,9 +636,10 @@ int check_query_args(fdb_index *ix, size_t nq, size_t k, size_t nprobe, int mode
 }
 
 // steps 3-6 of the exact pipeline for queries whose probes are already in ix->probes
+// (do_merge == false: stops after step 5, the per-pair lists stay in ix->part_d / part_v / part_cnt)
 int exact_after_probe(fdb_index *ix, const float *d_q, const uint32_t *d_probes, size_t nq, size_t k,
                       size_t nprobe, int mode, uint32_t *d_p, uint32_t *d_v, float *d_d, uint32_t *d_c,
-                      EventLog &log) {
+                      EventLog &log, bool do_merge = true) {
     fdb_ctx *ctx = ix->ctx;
     const size_t npairs = nq * nprobe;
     const size_t DC = ix->D * ix->C;
@@ -689,7 +722,9 @@ int exact_after_probe(fdb_index *ix, const float *d_q, const uint32_t *d_probes,
         FDB_CHECK_LAUNCH();
     }
     FDB_TRY(log.mark(5));
+    if (!do_merge) return FDB_OK;
     const size_t msmem = (size_t)MERGE_WARPS * 4 * k * sizeof(float);
+    if (msmem > 48 * 1024) FDB_CUDA(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
     merge_kernel<<<(unsigned)((nq + MERGE_WARPS - 1) / MERGE_WARPS), MERGE_WARPS * 32, msmem, ctx->stream>>>(
         ix->part_d.p, ix->part_v.p, ix->part_cnt.p, d_probes, nq, (int)nprobe, (int)k, mode, d_p,
         d_v, d_d, d_c, ctx->d_flags);
@@ -828,29 +863,34 @@ namespace {
 // warp per query takes the world * k candidates and keeps the k smallest by the canonical key of
 // build::Database::query's stable sort (src/db/build.rs:334-337): (distance, probe rank of the partition,
 // vector index).  Every (partition, vector index) occurs once, so the ranks are a permutation.
-__global__ void __launch_bounds__(128) merge_ranks_kernel(int world, size_t nq, int k, int nprobe,
+__global__ void __launch_bounds__(128) merge_ranks_kernel(int world, size_t nq, int kin, int k, int nprobe,
                                                           const uint32_t *part, const uint32_t *vidx,
-                                                          const float *dist, const uint32_t *cnt,
-                                                          const uint32_t *probes, uint32_t *o_part,
-                                                          uint32_t *o_vidx, float *o_dist, uint32_t *o_cnt,
-                                                          uint32_t *tie_flag) {
+                                                          const float *dist, size_t rs_list, const uint32_t *cnt,
+                                                          size_t rs_cnt, const uint32_t *probes, const uint32_t *qlist,
+                                                          int flag_any_tie, uint32_t *o_part, uint32_t *o_vidx,
+                                                          float *o_dist, uint32_t *o_cnt, uint32_t *tie_flag) {
+    // inputs: rank r's list of query q = part / vidx / dist [r * rs_list + q * kin + i], count cnt[r * rs_cnt + q],
+    // kin entries per list; outputs [q][k], k <= kin.  qlist (may be null): the queries to merge, probes is then
+    // indexed by the position in the list.  flag_any_tie: flag the query when two of its k + 1 best candidates have
+    // equal distances (stored semantic: NBestByKey's push history decides such cases)
     extern __shared__ unsigned char msm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const size_t q = (size_t)blockIdx.x * 4 + warp;
-    if (q >= nq) return;
-    const int cap = world * k;
+    const size_t qi = (size_t)blockIdx.x * 4 + warp;
+    if (qi >= nq) return;
+    const size_t q = qlist ? qlist[qi] : qi;
+    const int cap = world * kin;
     float *sd = reinterpret_cast<float *>(msm) + (size_t)warp * cap * 4;
     uint32_t *sp = reinterpret_cast<uint32_t *>(sd + cap), *sv = sp + cap, *sr = sv + cap;
     int n = 0;
     for (int r = 0; r < world; ++r) {
-        const int c = (int)min(cnt[(size_t)r * nq + q], (uint32_t)k);
-        const size_t o = ((size_t)r * nq + q) * k;
+        const int c = (int)min(cnt[(size_t)r * rs_cnt + q], (uint32_t)kin);
+        const size_t o = (size_t)r * rs_list + q * kin;
         for (int i = lane; i < c; i += 32) {
             const uint32_t p = part[o + i];
             int pr = probes ? nprobe : (int)p;   // rank of the partition in the query's probe order (or its id)
             if (probes)
                 for (int e = 0; e < nprobe; ++e)
-                    if (probes[q * nprobe + e] == p) {
+                    if (probes[qi * nprobe + e] == p) {
                         pr = e;
                         break;
                     }
@@ -866,13 +906,14 @@ __global__ void __launch_bounds__(128) merge_ranks_kernel(int world, size_t nq, 
         const float d = sd[i];
         const uint32_t pr = sr[i], v = sv[i];
         int rank = 0;
-        bool tied = false;   // equal distance in another partition: the order depends on the probe ranks
+        bool tied = false, tied_any = false;   // equal distance in another partition / anywhere
         for (int j = 0; j < n; ++j) {
             const float dj = sd[j];
             rank += (dj < d) || (dj == d && (sr[j] < pr || (sr[j] == pr && sv[j] < v)));
             tied |= dj == d && sr[j] != pr;
+            tied_any |= dj == d && j != i;
         }
-        if (!probes && tied && rank <= k && tie_flag) tie_flag[q] = 1u;
+        if (tie_flag && rank <= k && ((!probes && tied) || (flag_any_tie && (tied_any || d != d)))) tie_flag[q] = 1u;
         if (rank < k) {
             o_part[q * k + rank] = sp[i];
             o_vidx[q * k + rank] = v;
@@ -880,6 +921,39 @@ __global__ void __launch_bounds__(128) merge_ranks_kernel(int world, size_t nq, 
         }
     }
     if (lane == 0) o_cnt[q] = (uint32_t)min(n, k);
+}
+
+// stored semantic, tied queries: the owner's per-partition slot lists.  in: [world] x ([np*k dist][np*k vidx][np cnt]);
+// a partition is a non-empty list on at most one rank
+__global__ void combine_pairs_kernel(const uint32_t *all, size_t words, int world, size_t np, size_t k, float *pd,
+                                     uint32_t *pv, uint32_t *pc) {
+    const size_t pair = blockIdx.x;
+    __shared__ int own_s;
+    if (threadIdx.x == 0) {
+        int own = 0;
+        for (int r = 0; r < world; ++r)
+            if (all[(size_t)r * words + 2 * np * k + pair]) own = r;
+        own_s = own;
+        pc[pair] = all[(size_t)own * words + 2 * np * k + pair];
+    }
+    __syncthreads();
+    const uint32_t *src = all + (size_t)own_s * words;
+    for (size_t i = threadIdx.x; i < k; i += blockDim.x) {
+        pd[pair * k + i] = __uint_as_float(src[pair * k + i]);
+        pv[pair * k + i] = src[np * k + pair * k + i];
+    }
+}
+__global__ void pack_pairs_kernel(const float *pd, const uint32_t *pv, const uint32_t *pc, size_t np, size_t k, uint32_t *out) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < np * k) {
+        out[t] = __float_as_uint(pd[t]);
+        out[np * k + t] = pv[t];
+    }
+    if (t < np) out[2 * np * k + t] = pc[t];
+}
+__global__ void compact_flags_kernel(const uint32_t *flags, size_t nq, uint32_t *list, uint32_t *count) {
+    const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < nq && flags[q]) list[atomicAdd(count, 1u)] = (uint32_t)q;
 }
 }  // namespace
 }  // namespace fdb
@@ -1110,11 +1184,106 @@ int fdb_merge_topk_device(fdb_ctx *ctx, int world, size_t nq, size_t k, size_t n
     ARG(smem <= 48 * 1024, "world * k = %zu candidates per query exceed the merge buffer", (size_t)world * k);
     FDB_TRY(ctx->use());
     fdb::merge_ranks_kernel<<<(unsigned)((nq + 3) / 4), 128, smem, ctx->stream>>>(
-        world, nq, (int)k, (int)nprobe, d_partition, d_vector_index, d_sqdist, d_count, d_probes, d_out_partition,
-        d_out_vector_index, d_out_sqdist, d_out_count, d_tie_flag);
+        world, nq, (int)k, (int)k, (int)nprobe, d_partition, d_vector_index, d_sqdist, nq * k, d_count, nq, d_probes, nullptr, 0,
+        d_out_partition, d_out_vector_index, d_out_sqdist, d_out_count, d_tie_flag);
     ctx->launches++;
     FDB_CHECK_LAUNCH();
     return FDB_OK;   // enqueued on the context's stream
 }
 
+/* Database::query with the code lists sharded over the ranks of `comm` (header). */
+int fdb_index_query_sharded(fdb_index *ix, fdb_comm *comm, const float *d_queries, size_t nq, size_t k, size_t nprobe,
+                            int mode, uint32_t *d_partition, uint32_t *d_vector_index, float *d_sqdist,
+                            uint32_t *d_count) {
+    FDB_TRY(check_query_args(ix, nq, k, nprobe, mode));
+    ARG(comm && comm->ctx == ix->ctx, "the communicator belongs to another context");
+    ARG(nq == 0 || (d_queries && d_partition && d_vector_index && d_sqdist && d_count), "null argument");
+    if (nq == 0) return FDB_OK;
+    fdb_ctx *ctx = ix->ctx;
+    FDB_TRY(ctx->use());
+    cudaStream_t st = ctx->stream;
+    const int world = comm->world;
+    // stored semantic: one candidate more per rank shows whether the k-th place is contested
+    const size_t kin = mode == FDB_QUERY_STORED ? k + 1 : k;
+    const size_t msmem = 4 * (size_t)world * kin * 16;
+    ARG(msmem <= 96 * 1024, "world * k = %zu candidates per query exceed the merge buffer", (size_t)world * kin);
+    // ---- this rank's lists, straight into the send buffer: [nq*kin part][nq*kin vidx][nq*kin dist][nq count]
+    const size_t words = nq * (3 * kin + 1);
+    FDB_TRY(comm->send.ensure(words * 4 + 16));
+    FDB_TRY(comm->recv.ensure((size_t)world * words * 4 + 16));
+    uint32_t *snd = reinterpret_cast<uint32_t *>(comm->send.p), *all = reinterpret_cast<uint32_t *>(comm->recv.p);
+    FDB_TRY(query_device(ix, d_queries, nq, kin, nprobe, mode, snd, snd + nq * kin, reinterpret_cast<float *>(snd + 2 * nq * kin),
+                         snd + 3 * nq * kin));
+    FDB_TRY(comm_allgather(comm, snd, all, words * 4));
+    // ---- merge on every rank.  The probe order breaks distance ties between partitions: it is at hand when the
+    //      query selected its probes exactly; else the partition id stands in and the (few) queries where that
+    //      matters are merged again with exactly selected probes
+    FDB_TRY(ix->sh_flags.ensure(nq + 1));
+    FDB_TRY(ix->sh_list.ensure(nq));
+    FDB_CUDA(cudaMemsetAsync(ix->sh_flags.p, 0, (nq + 1) * sizeof(uint32_t), st));
+    const bool have_probes = ix->last_probes_exact && ix->last_probes_nq == nq && ix->last_probes_nprobe == nprobe;
+    FDB_CUDA(cudaFuncSetAttribute(merge_ranks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
+    auto merge = [&](size_t n, const uint32_t *probes, const uint32_t *qlist, int any_tie, uint32_t *flags) {
+        merge_ranks_kernel<<<(unsigned)((n + 3) / 4), 128, msmem, st>>>(
+            world, n, (int)kin, (int)k, (int)nprobe, all, all + nq * kin, reinterpret_cast<const float *>(all + 2 * nq * kin), words,
+            all + 3 * nq * kin, words, probes, qlist, any_tie, d_partition, d_vector_index, d_sqdist, d_count, flags);
+        ctx->launches++;
+    };
+    merge(nq, have_probes ? ix->probes.p : nullptr, nullptr, mode == FDB_QUERY_STORED, ix->sh_flags.p);
+    compact_flags_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(ix->sh_flags.p, nq, ix->sh_list.p, ix->sh_flags.p + nq);
+    ctx->launches++;
+    FDB_CHECK_LAUNCH();
+    uint32_t nt = 0;
+    FDB_CUDA(cudaMemcpyAsync(&nt, ix->sh_flags.p + nq, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    FDB_CUDA(cudaStreamSynchronize(st));   // (the flags are the same on every rank: the merged lists are)
+    ix->last_sharded_ties = nt;
+    if (nt) {
+        // the flagged queries again, with their probe lists selected exactly (reference order, both semantics)
+        FDB_TRY(ix->fb_q.ensure((size_t)nt * ix->N));
+        gather_rows_kernel<<<(unsigned)(((size_t)nt * ix->N + 255) / 256), 256, 0, st>>>(d_queries, ix->sh_list.p, nt, ix->N, ix->fb_q.p);
+        ctx->launches++;
+        FDB_TRY(probe_device(ix, ix->fb_q.p, nt, nprobe, mode, nullptr));
+        if (mode == FDB_QUERY_BUILD) {
+            merge(nt, ix->probes.p, ix->sh_list.p, 0, nullptr);
+        } else {
+            // stored semantic: flatten() of the per-partition NBestByKey lists in probe order, n_best_by_key(k), stable
+            // sort (src/db/stored.rs:379-386).  A partition's slot list depends on that partition alone: its owner
+            // computes it, the lists travel in one more all-gather, every rank replays the second level.
+            EventLog log{ix};
+            const size_t np = (size_t)nt * nprobe;
+            FDB_TRY(ix->fb_p.ensure((size_t)nt * k));
+            FDB_TRY(ix->fb_v.ensure((size_t)nt * k));
+            FDB_TRY(ix->fb_d.ensure((size_t)nt * k));
+            FDB_TRY(ix->fb_c.ensure(nt));
+            FDB_TRY(exact_after_probe(ix, ix->fb_q.p, ix->probes.p, nt, k, nprobe, mode, nullptr, nullptr, nullptr, nullptr, log, false));
+            const size_t pw = np * (2 * k + 1);
+            FDB_TRY(comm->send.ensure(std::max(words, pw) * 4 + 16));
+            FDB_TRY(comm->recv.ensure((size_t)world * std::max(words, pw) * 4 + 16));
+            uint32_t *psnd = reinterpret_cast<uint32_t *>(comm->send.p), *pall = reinterpret_cast<uint32_t *>(comm->recv.p);
+            pack_pairs_kernel<<<(unsigned)((np * k + 255) / 256), 256, 0, st>>>(ix->part_d.p, ix->part_v.p, ix->part_cnt.p, np, k, psnd);
+            FDB_TRY(comm_allgather(comm, psnd, pall, pw * 4));
+            combine_pairs_kernel<<<(unsigned)np, 32, 0, st>>>(pall, pw, world, np, k, ix->part_d.p, ix->part_v.p, ix->part_cnt.p);
+            const size_t m2 = (size_t)MERGE_WARPS * 4 * k * sizeof(float);
+            if (m2 > 48 * 1024) FDB_CUDA(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m2));
+            merge_kernel<<<(unsigned)((nt + MERGE_WARPS - 1) / MERGE_WARPS), MERGE_WARPS * 32, m2, st>>>(
+                ix->part_d.p, ix->part_v.p, ix->part_cnt.p, ix->probes.p, nt, (int)nprobe, (int)k, mode, ix->fb_p.p, ix->fb_v.p,
+                ix->fb_d.p, ix->fb_c.p, ctx->d_flags);
+            scatter_results_kernel<<<(unsigned)(((size_t)nt * k + 255) / 256), 256, 0, st>>>(
+                ix->sh_list.p, nt, k, ix->fb_p.p, ix->fb_v.p, ix->fb_d.p, ix->fb_c.p, d_partition, d_vector_index, d_sqdist, d_count);
+            ctx->launches += 4;
+        }
+        FDB_CHECK_LAUNCH();
+    }
+    FDB_TRY(comm_check(comm));
+    return finish_query(ctx);
+}
+
+/* how many queries of the last fdb_index_query_sharded call were merged a second time (distance ties) */
+int fdb_index_last_sharded_ties(fdb_index *ix, uint32_t *ties) {
+    ARG(ix && ties, "null argument");
+    *ties = ix->last_sharded_ties;
+    return FDB_OK;
+}
+
 }  // extern "C"
+

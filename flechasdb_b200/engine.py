@@ -42,6 +42,15 @@ class Context:
     def free(self, p):
         check(capi.lib().fdb_device_free(self.h, p))
 
+    def upload(self, dptr, array):
+        a = np.ascontiguousarray(array)
+        check(capi.lib().fdb_device_upload(self.h, dptr, a.ctypes.data_as(VP), a.nbytes))
+
+    def download(self, dptr, shape, dtype):
+        out = np.empty(shape, dtype)
+        check(capi.lib().fdb_device_download(self.h, out.ctypes.data_as(VP), dptr, out.nbytes))
+        return out
+
     def fill_uniform(self, dptr, count, seed, start=0):
         check(capi.lib().fdb_device_fill_uniform(self.h, dptr, count, seed, start))
 
@@ -55,6 +64,47 @@ class Context:
 
     def __exit__(self, *a):
         self.close()
+
+
+class Comm:
+    """One rank of the library's NCCL communicator (fdb_comm), bound to a Context.
+
+    `exchange(id_bytes_or_None) -> id_bytes` hands rank 0's id to the other ranks; any transport
+    will do (bench.py uses a torch.distributed broadcast, the tests a file)."""
+
+    def __init__(self, ctx, world, rank, exchange=None):
+        self.ctx, self.world, self.rank = ctx, world, rank
+        self.h = VP()
+        ident = None
+        if world > 1:
+            ident = np.zeros(capi.COMM_ID_BYTES, np.uint8)
+            if rank == 0:
+                check(capi.lib().fdb_comm_unique_id(u8p(ident)))
+            ident = np.frombuffer(exchange(ident.tobytes() if rank == 0 else None), np.uint8).copy()
+        check(capi.lib().fdb_comm_create(ctx.h, world, rank, None if ident is None else u8p(ident), C.byref(self.h)))
+
+    @property
+    def collectives(self):
+        return int(capi.lib().fdb_comm_collective_count(self.h))
+
+    def max_f64(self, values):
+        """max over the ranks of a few host doubles (device timings); also a barrier"""
+        v = np.ascontiguousarray(np.atleast_1d(values), np.float64).copy()
+        check(capi.lib().fdb_comm_max_f64(self.h, v.ctypes.data_as(C.POINTER(C.c_double)), len(v)))
+        return v
+
+    def barrier(self):
+        self.max_f64([0.0])
+
+    def close(self):
+        if self.h:
+            capi.lib().fdb_comm_destroy(self.h)
+            self.h = VP()
+
+
+def shard_rows(n, world, rank):
+    """contiguous row shard [lo, hi) of `rank` (the convention of fdb_kmeans_*_sharded)"""
+    return n * rank // world, n * (rank + 1) // world
 
 
 class VectorSet:
@@ -182,6 +232,22 @@ class KMeans:
         check(capi.lib().fdb_kmeans_run(self.h, max_rounds, eps, f32p(g), u32p(rounds), u32p(reas)))
         return [g[b, :rounds[b]].copy() for b in range(self.nb)], rounds, reas
 
+    def seed_run_sharded(self, comm, n_global, first_global, u01):
+        """k-means++ over row shards, one packed all-gather per round; returns the picked global rows [nb][k]"""
+        first = as_u32(np.atleast_1d(first_global))
+        u = as_f32(u01).reshape(self.nb, max(self.k - 1, 0))
+        picked = np.zeros((self.nb, self.k), np.uint32)
+        check(capi.lib().fdb_kmeans_seed_run_sharded(self.h, comm.h, n_global, u32p(first), f32p(u), u32p(picked)))
+        return picked
+
+    def run_sharded(self, comm, max_rounds=capi.KMEANS_MAX_ROUNDS, eps=capi.KMEANS_EPSILON):
+        """the Lloyd loop over row shards, one all-reduce per round; returns what run() returns"""
+        g = np.zeros((self.nb, max_rounds), np.float32)
+        rounds = np.zeros(self.nb, np.uint32)
+        reas = np.zeros(self.nb, np.uint32)
+        check(capi.lib().fdb_kmeans_run_sharded(self.h, comm.h, max_rounds, eps, f32p(g), u32p(rounds), u32p(reas)))
+        return [g[b, :rounds[b]].copy() for b in range(self.nb)], rounds, reas
+
     def last_assign_info(self):
         a = (C.c_uint32 * 3)()
         check(capi.lib().fdb_kmeans_last_assign_info(
@@ -269,6 +335,16 @@ class Index:
                      mode=capi.QUERY_STORED):
         check(capi.lib().fdb_index_query_device(self.h, d_q, nq, k, nprobe, mode, d_part, d_vidx,
                                                 d_dist, d_cnt))
+
+    def query_sharded(self, comm, d_q, nq, k, nprobe, d_part, d_vidx, d_dist, d_cnt, mode=capi.QUERY_STORED):
+        """code lists sharded over the ranks of comm: same batch on every rank, one packed all-gather, merged
+        result (identical on every rank) left in the device buffers"""
+        check(capi.lib().fdb_index_query_sharded(self.h, comm.h, d_q, nq, k, nprobe, mode, d_part, d_vidx, d_dist, d_cnt))
+
+    def last_sharded_ties(self):
+        t = C.c_uint32()
+        check(capi.lib().fdb_index_last_sharded_ties(self.h, C.byref(t)))
+        return int(t.value)
 
     def probe(self, q, nprobe, mode=capi.QUERY_STORED):
         q = as_f32(q).reshape(-1, self.N)

@@ -38,6 +38,7 @@ extern "C" {
 #define FDB_ERR_NAN (-6)             /* panic: min_index.unwrap() src/kmeans.rs:304; partial_cmp().unwrap() src/db/stored.rs:385,426 */
 #define FDB_ERR_CUDA (-7)            /* CUDA runtime failure (no reference analogue) */
 #define FDB_ERR_UNSUPPORTED (-8)     /* shape outside what the device layout supports (e.g. C > 256 with u8 codes) */
+#define FDB_ERR_NCCL (-9)            /* NCCL failure or libnccl missing (multi-GPU entry points only) */
 
 #define FDB_KMEANS_MAX_ROUNDS 100    /* const R: usize = 100;   src/kmeans.rs:114 */
 #define FDB_KMEANS_EPSILON 1e-6f     /* f32 default_epsilon     src/kmeans.rs:24-28 */
@@ -49,6 +50,7 @@ typedef struct fdb_ctx fdb_ctx;     /* one CUDA device + stream                 
 typedef struct fdb_vs fdb_vs;       /* BlockVectorSet<f32> resident in HBM   src/vector.rs:28-100 */
 typedef struct fdb_km fdb_km;       /* nb k-means problems (Codebook<f32> each) src/kmeans.rs:62-68 */
 typedef struct fdb_index fdb_index; /* queryable IVF-PQ index: stored::Database src/db/stored.rs:41-57 */
+typedef struct fdb_comm fdb_comm;   /* one rank of an NCCL communicator, bound to a context (no reference analogue) */
 
 /* ---- library / context ------------------------------------------------------ */
 const char *fdb_last_error(void);
@@ -252,9 +254,59 @@ int fdb_index_debug_band(fdb_index *ix, size_t nq, size_t nprobe, float *E /*[nq
                          float *cand_approx /*[nq][32]*/, uint32_t *cand_flat /*[nq][32]*/,
                          uint32_t *cand_cnt /*[nq]*/, uint32_t *probes /*[nq][nprobe]*/);
 
+/* ---- multi-GPU: one rank (thread or process) per GPU, NCCL owned by the library --------------------
+ * No reference analogue (the reference is single-threaded); this is how the build
+ * (DatabaseBuilder::build, src/db/build.rs:73-129) and the query (Database::query,
+ * src/db/stored.rs:315-389, src/db/build.rs:294-340) shard over the GPUs of one box.
+ * Rank 0 makes an id with fdb_comm_unique_id and hands it to the other ranks (any way it likes);
+ * every rank then calls fdb_comm_create with its own context.  All collectives run on the
+ * context's stream.  libnccl.so.2 is opened at run time (FDB_NCCL_LIB overrides the name);
+ * world == 1 needs no NCCL at all. */
+#define FDB_COMM_ID_BYTES 128
+int fdb_comm_unique_id(uint8_t *id /*[FDB_COMM_ID_BYTES]*/);
+int fdb_comm_create(fdb_ctx *ctx, int world, int rank, const uint8_t *id, fdb_comm **out);
+void fdb_comm_destroy(fdb_comm *comm);
+int fdb_comm_world(const fdb_comm *comm);
+int fdb_comm_rank(const fdb_comm *comm);
+uint64_t fdb_comm_collective_count(const fdb_comm *comm); /* collectives enqueued so far */
+/* building blocks (device pointers, enqueued on the context's stream): in-place sum, all-gather of bytes */
+int fdb_comm_allreduce_device(fdb_comm *comm, float *d_buf, size_t n);
+int fdb_comm_allgather_device(fdb_comm *comm, const void *d_send, void *d_recv, size_t bytes_per_rank);
+/* max over the ranks of n <= 64 host doubles (device timings); synchronises: also the barrier */
+int fdb_comm_max_f64(fdb_comm *comm, double *values, size_t n);
+/* cluster_with_events (src/kmeans.rs:104-139) over row shards: rank r holds the rows
+ * [n_global*r/world, n_global*(r+1)/world) of the vector set behind km; centroids are replicated.
+ *   seed_run_sharded: initialize_centroids (:142-229); first_global[nb] = gen_range(0..n) per problem,
+ *     u01[nb][k-1] the draws (identical on every rank); ONE packed all-gather per round (shard total,
+ *     local pick, picked row); picked_global[nb][k] (may be NULL) = the chosen global row indices.
+ *     Two-stage sampling (shard by total, row inside the shard by weight): the reference's distribution.
+ *   run_sharded: the loop of :125-137; ONE all-reduce of [nb*k*dim sums || nb*k counts] per round;
+ *     outputs as fdb_kmeans_run.  Assignments are bit-exact per row given the centroids; centroids
+ *     differ from one GPU only by the order in which the shards' partial sums are added. */
+int fdb_kmeans_seed_run_sharded(fdb_km *km, fdb_comm *comm, size_t n_global, const uint32_t *first_global,
+                                const float *u01, uint32_t *picked_global);
+int fdb_kmeans_run_sharded(fdb_km *km, fdb_comm *comm, size_t max_rounds, float epsilon, float *gradients,
+                           uint32_t *rounds, uint32_t *reassigns);
+/* Database::query with the code lists sharded: every rank holds the coarse centroids, the codebooks and
+ * the lists of the partitions it owns (the other partitions are empty on it) and is given the SAME batch
+ * (device pointer); the per-rank candidates travel in ONE packed all-gather and are merged on every rank.
+ * mode FDB_QUERY_BUILD: canonical order (distance, probe rank, vector index) == build::Database::query on
+ * the whole database.  mode FDB_QUERY_STORED: the same result whenever no two of the k+1 best candidates
+ * have equal distances; the queries where they do (NBestByKey push history decides, src/nbest.rs:52-64)
+ * are answered again from the per-partition slot lists of the owning ranks.  Outputs: device pointers,
+ * [nq][k] / [nq], identical on every rank.  Synchronises once at the end. */
+int fdb_index_query_sharded(fdb_index *ix, fdb_comm *comm, const float *d_queries, size_t nq, size_t k,
+                            size_t nprobe, int mode, uint32_t *d_partition, uint32_t *d_vector_index,
+                            float *d_sqdist, uint32_t *d_count);
+
+/* how many queries of the last fdb_index_query_sharded call were merged a second time (distance ties) */
+int fdb_index_last_sharded_ties(fdb_index *ix, uint32_t *ties);
+
 /* raw device buffers for benches that keep inputs resident */
 int fdb_device_alloc(fdb_ctx *ctx, size_t bytes, void **out);
 int fdb_device_free(fdb_ctx *ctx, void *p);
+int fdb_device_upload(fdb_ctx *ctx, void *d_dst, const void *src, size_t bytes);     /* synchronous */
+int fdb_device_download(fdb_ctx *ctx, void *dst, const void *d_src, size_t bytes);   /* synchronous */
 int fdb_device_fill_uniform(fdb_ctx *ctx, float *d, size_t count, uint64_t seed, uint64_t start);
 int fdb_device_flush_l2(fdb_ctx *ctx);
 

@@ -696,6 +696,56 @@ def test_partition_major_scan_16_bit_tables(eng, ctx, oracle, monkeypatch, N, P,
     ix.close()
 
 
+@pytest.mark.parametrize("N,P,D,Cn,M,k,nprobe,nq", [
+    (1536, 100, 12, 256, 20000, 10, 5, 512),   # the README shape
+    (96, 64, 12, 256, 30000, 10, 8, 256),      # s = 8
+    (64, 9, 4, 256, 60, 5, 9, 64),             # fewer vectors than a candidate list holds, nprobe == P
+    (64, 3, 8, 64, 60000, 10, 2, 300),         # lists longer than one item's chunk of vectors, 200 queries per list
+    (48, 40, 12, 32, 9000, 3, 40, 100),        # every query probes every partition
+    (128, 64, 16, 256, 20000, 10, 8, 200),     # D = 16 (SIFT shape): 64 KB of tables
+    (80, 12, 4, 104, 900, 24, 3, 128),         # largest k (candidate lists of 30), C < 256
+    (64, 500, 4, 16, 20000, 10, 3, 40),        # most lists probed by one or two queries: nearly empty groups
+])
+def test_vector_lane_scan_packed_tables(eng, ctx, oracle, monkeypatch, N, P, D, Cn, M, k, nprobe, nq):
+    """vscan_kernel (adc_vscan.cuh): a lane owns a vector, one 128-bit look-up serves 8 queries' 16-bit entries;
+    the quantisation error widens the band, the results stay the oracle's bit for bit."""
+    monkeypatch.setenv("FDB_FILTER_SCAN", "vector")
+    coarse, cbs, off, codes = random_index(oracle, N, P, D, Cn, M, empty=(1,))
+    ix = eng.Index.create(ctx, coarse, cbs, off, codes.astype(np.uint8))
+    oix = oracle.QueryIndex(coarse, cbs, off, codes)
+    q = data(oracle, nq, N, SEED + 91)
+    for mode in (0, 1):
+        fast, exact, cand, scanned = _check_query(ix, oix, q, k, nprobe, mode)
+        assert fast + exact == nq
+        assert fast >= 0.9 * nq, (fast, exact)
+        assert cand <= 2 * (k + 1) * fast
+    ix.close()
+    # clustered data far from the origin: distances span orders of magnitude, wide bands
+    coarse, cbs, off, codes, q = _clustered_index(oracle, 96, 50, 12, 64, 8000, 11)
+    ix = eng.Index.create(ctx, coarse, cbs, off, codes.astype(np.uint8))
+    oix = oracle.QueryIndex(coarse, cbs, off, codes)
+    fast, exact, cand, scanned = _check_query(ix, oix, q, 5, 5, 0)
+    assert fast + exact == len(q) and fast >= 0.5 * len(q), (fast, exact)
+    ix.close()
+
+
+def test_vector_lane_scan_equals_exact_pipeline_on_a_large_batch(eng, ctx, oracle, monkeypatch):
+    """4096 queries against the README shape and 2048 against long lists: equal to the exact pipeline bit for bit."""
+    monkeypatch.setenv("FDB_FILTER_SCAN", "vector")
+    for (N, P, D, Cn, M, k, nprobe, nq) in [(1536, 100, 12, 256, 50000, 10, 5, 4096), (96, 256, 12, 256, 1500000, 10, 16, 2048)]:
+        coarse, cbs, off, codes = random_index(oracle, N, P, D, Cn, M)
+        ix = eng.Index.create(ctx, coarse, cbs, off, codes.astype(np.uint8))
+        q = data(oracle, nq, N, SEED + 80)
+        got = ix.query(q, k, nprobe)
+        assert ix.last_stats()[0] >= 0.99 * nq, ix.last_stats()
+        monkeypatch.setenv("FDB_QUERY_EXACT", "1")
+        want = ix.query(q, k, nprobe)
+        monkeypatch.delenv("FDB_QUERY_EXACT")
+        for g, w in zip(got, want):
+            assert (g == w).all()
+        ix.close()
+
+
 def test_forced_scan_mode_fails_loudly_when_the_shape_is_not_taken(eng, ctx, oracle, monkeypatch):
     """FDB_FILTER_SCAN forces a scan kernel; a shape that kernel does not take is an error, not a silent fallback."""
     from flechasdb_b200.db import Error
@@ -703,7 +753,7 @@ def test_forced_scan_mode_fails_loudly_when_the_shape_is_not_taken(eng, ctx, ora
     coarse, cbs, off, codes = random_index(oracle, N, P, D, Cn, M)
     ix = eng.Index.create(ctx, coarse, cbs, off, codes.astype(np.uint8))
     q = data(oracle, 16, N, SEED + 87)
-    for mode in ("partition", "partition16"):
+    for mode in ("partition", "partition16", "vector"):
         monkeypatch.setenv("FDB_FILTER_SCAN", mode)
         with pytest.raises(Exception) as ei:
             ix.query(q, 5, 4)
