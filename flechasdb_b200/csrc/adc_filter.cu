@@ -2082,7 +2082,7 @@ int filter_query(fdb_index *ix, const float *d_q, size_t q_base, size_t nq, size
         pg_scan_kernel<<<1, 1024, 0, st>>>(sl->pg_ctl.p, ix->part_off.p, (int)P, PSCAN_VCH, (int)pj, sl->pg_pstart.p, sl->pg_istart.p);
         pg_scatter_kernel<<<(unsigned)((npairs + 255) / 256), 256, 0, st>>>(chunk_probes, sl->pg_slot.p, sl->pg_pstart.p, npairs,
                                                                             pscan_split ? (int)nprobe : 0, (int)P, sl->pg_pairs.p);
-        pg_items_kernel<<<(unsigned)((2 * P + 3) / 4), 128, 0, st>>>(sl->pg_ctl.p, sl->pg_pstart.p, sl->pg_istart.p,
+        pg_items_kernel<<<(unsigned)(2 * P), 128, 0, st>>>(sl->pg_ctl.p, sl->pg_pstart.p, sl->pg_istart.p,
                                                                      sl->pg_pairs.p, ix->part_off.p, (int)P, PSCAN_VCH,
                                                                      (int)pj, sl->pg_desc.p);
         PScanParams pp;

@@ -125,24 +125,25 @@ __global__ void __launch_bounds__(256) pg_scatter_kernel(const uint32_t *probes,
     if (i < npairs) pairs_of[pstart[pg_bucket(probes, i, nprobe, P)] + pair_slot[i]] = (uint32_t)i;
 }
 
-// item descriptors: one warp per bucket walks the bucket's (group, chunk of vectors) items
+// item descriptors: one CTA per bucket, one thread per (group, chunk of vectors) item
 __global__ void __launch_bounds__(128) pg_items_kernel(const uint32_t *count, const uint32_t *pstart,
                                                        const uint32_t *istart, const uint32_t *pairs_of,
                                                        const uint32_t *part_off, int P, int vch, int pj, uint32_t *desc) {
-    const int b = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int b = blockIdx.x;
     if (b >= 2 * P) return;
     const int p = b >= P ? b - P : b;
     const uint32_t cnt = count[b], np = part_off[p + 1] - part_off[p];
     const uint32_t nv = (np + (uint32_t)vch - 1) / (uint32_t)vch, ng = (cnt + (uint32_t)pj - 1) / (uint32_t)pj;
-    for (uint32_t it = 0; it < ng * nv; ++it) {
+    const uint32_t first = istart[b], ps = pstart[b];
+    for (uint32_t it = threadIdx.x; it < ng * nv; it += blockDim.x) {
         const uint32_t g = it / nv, c = it - g * nv;
         const uint32_t members = min((uint32_t)pj, cnt - g * (uint32_t)pj);
-        uint32_t *d = desc + (size_t)(istart[b] + it) * (4 + pj);
-        if (lane == 0) d[0] = (uint32_t)p;
-        if (lane == 1) d[1] = c * (uint32_t)vch;
-        if (lane == 2) d[2] = min(np, (c + 1) * (uint32_t)vch);
-        if (lane == 3) d[3] = members;
-        for (uint32_t m = lane; m < (uint32_t)pj; m += 32) d[4 + m] = m < members ? pairs_of[pstart[b] + g * pj + m] : 0u;
+        uint32_t *d = desc + (size_t)(first + it) * (4 + pj);
+        d[0] = (uint32_t)p;
+        d[1] = c * (uint32_t)vch;
+        d[2] = min(np, (c + 1) * (uint32_t)vch);
+        d[3] = members;
+        for (uint32_t m = 0; m < (uint32_t)pj; ++m) d[4 + m] = m < members ? pairs_of[ps + g * pj + m] : 0u;
     }
 }
 

@@ -91,24 +91,59 @@ __device__ __forceinline__ void load_code_words(const unsigned char *lst, int v,
     }
 }
 
+// Table layout in shared memory: conflict free by construction.  A 128-bit look-up is served one quarter warp (8
+// lanes) per wavefront when the 8 lanes hit 8 different 16-byte bank groups.  The divisions are taken in groups of
+// 8: the rows (d0 .. d0+7, c) of a code c form ONE 128-byte line, slot s = d - d0 at byte 16 s -- and lane l walks the
+// group in the rotated order s = (l + t) mod 8, t = 0..7, so at every step the lanes of a quarter warp sit in 8
+// different slots = 8 different bank groups, whatever their codes are.  A trailing group of 4 divisions uses 64
+// bytes per code (slot = (c & 1) * 4 + d - d0 within the line): lanes l and l + 4 share a slot and collide only when
+// their codes have the same parity (1.5 wavefronts per quarter warp on average).  Measured against the plain
+// [d][c] layout (8 random rows per quarter warp: 2.9 wavefronts): 56 instead of 140 wavefronts per warp step at D = 12.
+template <int W>
+struct VLayout {
+    static constexpr int D = 4 * W;
+    static constexpr int NF = D / 8;             // full groups (8 divisions, 128 bytes per code)
+    static constexpr bool HALF = (D % 8) != 0;   // one trailing group of 4 divisions (64 bytes per code)
+    static constexpr int F_BYTES = PT_STRIDE * 128, H_BYTES = PT_STRIDE * 64;
+    static constexpr int ROWS = D * PT_STRIDE;   // 16-byte rows; row r of the table lives at byte 16 r
+    static constexpr int BYTES = ROWS * 16;
+};
+// row r -> (division, code)
+template <int W>
+__device__ __forceinline__ void vrow_to_dc(int r, int &d, int &c) {
+    using L = VLayout<W>;
+    if (r < L::NF * PT_STRIDE * 8) {
+        const int g = r / (PT_STRIDE * 8), rr = r - g * (PT_STRIDE * 8);
+        c = rr >> 3;
+        d = g * 8 + (rr & 7);
+    } else {
+        const int rr = r - L::NF * PT_STRIDE * 8;
+        c = rr >> 2;
+        d = L::NF * 8 + (rr & 3);
+    }
+}
+
 template <int W>
 __global__ void __launch_bounds__(VWARPS * 32, W <= 3 ? 4 : 3) vscan_kernel(PScanParams p) {
+    using L = VLayout<W>;
     constexpr int D = 4 * W;
     extern __shared__ __align__(16) unsigned char vsm[];
-    uint4 *T = reinterpret_cast<uint4 *>(vsm);                                   // [D][256] rows of 8 x u16
-    uint32_t *bkeys = reinterpret_cast<uint32_t *>(vsm + (size_t)D * PT_STRIDE * 16);   // [VJ][VB]
+    uint4 *T = reinterpret_cast<uint4 *>(vsm);                                   // VLayout rows of 8 x u16
+    uint32_t *bkeys = reinterpret_cast<uint32_t *>(vsm + L::BYTES);              // [VJ][VB]
     uint32_t *bpos = bkeys + VJ * VB;
     __shared__ int bcnt[VJ];
     __shared__ unsigned bthr[VJ], bflag[VJ];
-    __shared__ uint32_t bq[VJ], bql[VJ];
+    __shared__ uint32_t bq[VJ], bgoff[VJ];
     __shared__ __align__(16) float qm[D][VJ];   // lower bound m_jd of table row d of member j
-    __shared__ float qinv[VJ], qdelta[VJ], qbase[VJ];
-    __shared__ uint32_t tinit[VJ / 2];     // accumulator start values: (0x8000 - t_j) per half word
-    __shared__ unsigned s_next, s_act;
+    __shared__ __align__(16) float qinv[VJ];
+    __shared__ float qdelta[VJ], qbase[VJ];
+    __shared__ __align__(16) unsigned short tinit[VJ];   // accumulator start values: 0x8000 - t_j per half word
+    __shared__ unsigned s_next, s_act, s_warm, s_retry;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int C = p.C, DC = D * C;
     const unsigned nitems = *p.nitems;
     const uint32_t tb = (uint32_t)__cvta_generic_to_shared(T);
+    const uint32_t phase = (uint32_t)lane & 7u;
 
     if (tid == 0) s_next = atomicAdd(p.work, 1u);
     if (tid < VJ) bflag[tid] = 0u;
@@ -143,16 +178,23 @@ __global__ void __launch_bounds__(VWARPS * 32, W <= 3 ? 4 : 3) vscan_kernel(PSca
             const float K = active ? __ldg(&p.Kq[qg * p.nprobe + (pair - ql * p.nprobe)]) : 0.0f;
             float rsum = 0.0f, msum = 0.0f, mabs = 0.0f;
             if (active) {
+                float2 g[D], c[D];
 #pragma unroll
                 for (int d = 0; d < D; ++d) {
-                    const float2 g = __ldg(reinterpret_cast<const float2 *>(p.gmm) + (size_t)ql * D + d);
-                    const float2 c = __ldg(reinterpret_cast<const float2 *>(p.pcmm) + (size_t)part * D + d);
-                    const float m = g.x + c.x;
+                    g[d] = __ldg(reinterpret_cast<const float2 *>(p.gmm) + (size_t)ql * D + d);
+                    c[d] = __ldg(reinterpret_cast<const float2 *>(p.pcmm) + (size_t)part * D + d);
+                }
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                    const float m = g[d].x + c[d].x;
                     qm[d][j] = m;
-                    rsum += (g.y - g.x) + (c.y - c.x);
+                    rsum += (g[d].y - g[d].x) + (c[d].y - c[d].x);
                     msum += m;
                     mabs += fabsf(m);
                 }
+            } else {
+#pragma unroll
+                for (int d = 0; d < D; ++d) qm[d][j] = 0.0f;
             }
             // sum_d round(range_d / delta) <= (32767 - D) / 1.0002 + D / 2: the 15-bit sums cannot overflow
             const float delta = fmaxf(rsum * (1.0002f / (float)(32767 - D)), 1e-30f);
@@ -160,6 +202,7 @@ __global__ void __launch_bounds__(VWARPS * 32, W <= 3 ? 4 : 3) vscan_kernel(PSca
             // NaN bounds (a non-finite G row), overflow, or tables so far from zero that the f32 entries do not
             // resolve delta: the query goes to the exact pipeline and its entries are zero
             const bool ok = active && fabsf(K) < 1e30f && rsum < 1e30f && mabs < 1e30f && (mabs + fabsf(K)) * 2.4e-7f <= delta;
+            const unsigned thr0 = ok ? __ldcg(&p.thrg[qg]) : 0u;   // 0: nothing is a candidate
             if (active) {
                 // per entry |m + delta u - t| <= delta / 2 + the roundings of t - m and of the fma (a few ulp of the
                 // range); then base = K + sum m and the final fma
@@ -172,90 +215,105 @@ __global__ void __launch_bounds__(VWARPS * 32, W <= 3 ? 4 : 3) vscan_kernel(PSca
             qbase[j] = K + msum;
             bcnt[j] = 0;
             bq[j] = (uint32_t)qg;
-            bql[j] = ql;
-            bthr[j] = ok ? __ldcg(&p.thrg[qg]) : 0u;   // 0: nothing is a candidate
+            bgoff[j] = (ok ? ql : 0u) * (uint32_t)DC;    // (a member that is not ok copies row 0 and is masked)
+            bthr[j] = thr0;
             const unsigned okm = __ballot_sync(0xffu, ok);
-            if (j == 0) s_act = okm;
+            const unsigned warm = __ballot_sync(0xffu, !ok || thr0 != 0xffffffffu);
+            if (j == 0) {
+                s_act = okm;
+                s_warm = warm == 0xffu && okm != 0u;     // every member starts with an inherited threshold
+                s_retry = 0u;
+            }
         }
         __syncthreads();
-        // ---- tables: thread c fills row (d, c) for d = 0 .. D - 1: 8 coalesced 4-byte loads, one 16-byte store
+        // ---- tables: thread r fills row r (+ 256 i): 8 coalesced 4-byte loads, one conflict-free 16-byte store
         {
             const unsigned act = s_act;
-            const int c = tid;
-            if (c < C) {
-                const float *pcp = p.pc + (size_t)part * DC + c;
-                const float *gc = p.G + c;
-                uint32_t go[VJ];     // offset of member j's G row (chunks hold < 2^32 floats)
-                float inv[VJ];
+            // half-word masks of the members whose entries count
+            const uint32_t k0 = ((act & 1u) ? 0xffffu : 0u) | ((act & 2u) ? 0xffff0000u : 0u);
+            const uint32_t k1 = ((act & 4u) ? 0xffffu : 0u) | ((act & 8u) ? 0xffff0000u : 0u);
+            const uint32_t k2 = ((act & 16u) ? 0xffffu : 0u) | ((act & 32u) ? 0xffff0000u : 0u);
+            const uint32_t k3 = ((act & 64u) ? 0xffffu : 0u) | ((act & 128u) ? 0xffff0000u : 0u);
+            const float4 i0 = *reinterpret_cast<const float4 *>(&qinv[0]), i1 = *reinterpret_cast<const float4 *>(&qinv[4]);
+            const float inv[VJ] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+            uint32_t go[VJ];
 #pragma unroll
-                for (int j = 0; j < VJ; ++j) {
-                    go[j] = bql[j] * (uint32_t)DC;
-                    inv[j] = qinv[j];
-                }
+            for (int j = 0; j < VJ; ++j) go[j] = bgoff[j];
+            const float *pcp = p.pc + (size_t)part * DC;
 #pragma unroll 2
-                for (int d = 0; d < D; ++d) {
-                    const float pcv = __ldg(pcp + d * C);
+            for (int r = tid; r < L::ROWS; r += VWARPS * 32) {
+                int d, c;
+                vrow_to_dc<W>(r, d, c);
+                uint4 row = make_uint4(0u, 0u, 0u, 0u);
+                if (c < C) {
+                    const uint32_t e = (uint32_t)(d * C + c);
+                    const float pcv = __ldg(pcp + e);
                     float g[VJ];
 #pragma unroll
-                    for (int j = 0; j < VJ; ++j) g[j] = (act >> j & 1u) ? __ldg(gc + go[j] + d * C) : 0.0f;
+                    for (int j = 0; j < VJ; ++j) g[j] = __ldg(p.G + (go[j] + e));
                     const float4 m0 = *reinterpret_cast<const float4 *>(&qm[d][0]), m1 = *reinterpret_cast<const float4 *>(&qm[d][4]);
                     const float m[VJ] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
                     uint32_t u[VJ];
 #pragma unroll
-                    for (int j = 0; j < VJ; ++j) {
-                        // (t - m) >= 0 exactly (rounded addition is monotone), so the fma never goes below 2^23
-                        const float x = fmaf((g[j] + pcv) - m[j], inv[j], VMAGIC);
-                        u[j] = (act >> j & 1u) ? __float_as_uint(x) : 0u;
-                    }
-                    uint4 row;
-                    row.x = __byte_perm(u[0], u[1], 0x5410);
-                    row.y = __byte_perm(u[2], u[3], 0x5410);
-                    row.z = __byte_perm(u[4], u[5], 0x5410);
-                    row.w = __byte_perm(u[6], u[7], 0x5410);
-                    T[d * PT_STRIDE + c] = row;
+                    for (int j = 0; j < VJ; ++j)   // (t - m) >= 0 exactly (rounded addition is monotone): the fma stays >= 2^23
+                        u[j] = __float_as_uint(fmaf((g[j] + pcv) - m[j], inv[j], VMAGIC));
+                    row.x = __byte_perm(u[0], u[1], 0x5410) & k0;
+                    row.y = __byte_perm(u[2], u[3], 0x5410) & k1;
+                    row.z = __byte_perm(u[4], u[5], 0x5410) & k2;
+                    row.w = __byte_perm(u[6], u[7], 0x5410) & k3;
                 }
+                T[r] = row;
             }
         }
-        if (tid < VJ / 2) {
-            const uint32_t t0 = int_threshold(2 * tid), t1 = int_threshold(2 * tid + 1);
-            tinit[tid] = (0x8000u - t0) | ((0x8000u - t1) << 16);
-        }
+        if (tid < VJ) tinit[tid] = (unsigned short)(0x8000u - int_threshold(tid));
         if (tid == 0) s_next = grabbed;
         __syncthreads();
         const unsigned next_item = s_next;
 
-        // ---- rounds: [rs, re) is handled by all warps, 32 vectors per warp step; a round never brings more
-        //      than about ncap new entries per query (as many vectors as have been seen so far)
-        int rs = v0, rsize = 32, seen = 0;
+        // ---- rounds: [rs, re) is handled by all warps, 32 vectors per warp step.  Cold start (no threshold yet): a
+        //      round never brings more than about ncap new entries per query (as many vectors as have been seen so
+        //      far).  With inherited thresholds the whole item is one round.  A buffer that overflows is cut back, the
+        //      round's entries are dropped and the round runs again with the tighter threshold.
+        int rs = v0, seen = 0, retries = 0;
+        int rsize = s_warm ? min(v1 - v0, 4096) : 64;
         uint32_t cw[W], nw[W];
         int cwb = rs + 32 * warp;     // the step whose code words cw holds
         load_code_words<W>(lst, min(cwb + lane, v1 - 1), cw);
         while (rs < v1) {
             const int re = min(v1, rs + rsize);
-            const uint32_t i0 = tinit[0], i1 = tinit[1], i2 = tinit[2], i3 = tinit[3];
+            const uint4 iv = *reinterpret_cast<const uint4 *>(&tinit[0]);
             for (int b = rs + 32 * warp; b < re; b += 32 * VWARPS) {
-                if (cwb != b) load_code_words<W>(lst, min(b + lane, v1 - 1), cw);   // (a short round skipped this warp)
+                if (cwb != b) load_code_words<W>(lst, min(b + lane, v1 - 1), cw);   // (a short or repeated round)
                 // the warp's next step (in this round, or its first one of the next round) travels now
                 const int nb = b + 32 * VWARPS < re ? b + 32 * VWARPS : re + 32 * warp;
                 load_code_words<W>(lst, min(nb + lane, v1 - 1), nw);
                 cwb = nb;
                 const int v = b + lane;
-                uint32_t a0 = i0, a1 = i1, a2 = i2, a3 = i3;
+                uint32_t a0 = iv.x, a1 = iv.y, a2 = iv.z, a3 = iv.w;
 #pragma unroll
-                for (int w = 0; w < W; ++w) {
-                    const uint32_t x = cw[w];
-                    const uint4 t0 = lds_v4(tb + (4 * w) * (PT_STRIDE * 16) + ((x << 4) & 0xff0u));
-                    const uint4 t1 = lds_v4(tb + (4 * w + 1) * (PT_STRIDE * 16) + ((x >> 4) & 0xff0u));
-                    const uint4 t2 = lds_v4(tb + (4 * w + 2) * (PT_STRIDE * 16) + ((x >> 12) & 0xff0u));
-                    const uint4 t3 = lds_v4(tb + (4 * w + 3) * (PT_STRIDE * 16) + ((x >> 20) & 0xff0u));
-                    a0 += (t0.x + t1.x) + (t2.x + t3.x);
-                    a1 += (t0.y + t1.y) + (t2.y + t3.y);
-                    a2 += (t0.z + t1.z) + (t2.z + t3.z);
-                    a3 += (t0.w + t1.w) + (t2.w + t3.w);
+                for (int g = 0; g < L::NF; ++g) {
+                    const uint32_t lo = cw[2 * g], hi = cw[(2 * g + 1) < W ? 2 * g + 1 : 0];
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) {
+                        const uint32_t s = (phase + (uint32_t)t) & 7u;
+                        const uint32_t code = __byte_perm(lo, hi, s) & 0xffu;
+                        const uint4 e = lds_v4(tb + (uint32_t)(g * L::F_BYTES) + code * 128u + s * 16u);
+                        a0 += e.x, a1 += e.y, a2 += e.z, a3 += e.w;
+                    }
+                }
+                if (L::HALF) {
+                    const uint32_t x = cw[W - 1];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const uint32_t s = (phase + (uint32_t)t) & 3u;
+                        const uint32_t code = __byte_perm(x, 0u, s) & 0xffu;
+                        const uint4 e = lds_v4(tb + (uint32_t)(L::NF * L::F_BYTES) + code * 64u + s * 16u);
+                        a0 += e.x, a1 += e.y, a2 += e.z, a3 += e.w;
+                    }
                 }
                 const uint32_t below = ~(a0 & a1 & a2 & a3) & 0x80008000u;
                 if (below != 0u && v < re) {
-                    const uint32_t aw[4] = {a0, a1, a2, a3}, iw[4] = {i0, i1, i2, i3};
+                    const uint32_t aw[4] = {a0, a1, a2, a3}, iw[4] = {iv.x, iv.y, iv.z, iv.w};
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
 #pragma unroll
@@ -270,8 +328,6 @@ __global__ void __launch_bounds__(VWARPS * 32, W <= 3 ? 4 : 3) vscan_kernel(PSca
                                     if (slot < VB) {
                                         bkeys[j * VB + slot] = key;
                                         bpos[j * VB + slot] = (uint32_t)v;
-                                    } else {
-                                        bflag[j] = 2u;   // overflow
                                     }
                                 }
                             }
@@ -281,29 +337,56 @@ __global__ void __launch_bounds__(VWARPS * 32, W <= 3 ? 4 : 3) vscan_kernel(PSca
 #pragma unroll
                 for (int w = 0; w < W; ++w) cw[w] = nw[w];
             }
-            seen += re - rs;
-            rs = re;
-            rsize = p.ncap <= 16 ? seen : max(32, (seen >> 1) & ~31);
             __syncthreads();
             // buffers that outgrew the list: keep the ncap smallest, tighten the threshold
             if (warp < members) {
-                const int n = min(bcnt[warp], VB);
-                if (n > p.ncap) {
-                    const int kept = cut_to_smallest(bkeys + warp * VB, bpos + warp * VB, n, p.ncap, &bthr[warp], lane);
-                    if (lane == 0) bcnt[warp] = kept;
+                const int j = warp;
+                const int n = bcnt[j];
+                if (n > VB) {
+                    // overflow: the VB entries that made it are real candidates, so their ncap-th smallest bounds the
+                    // final one.  Keep what was there before the round (<= the new bound), run the round again.
+                    cut_to_smallest(bkeys + j * VB, bpos + j * VB, VB, p.ncap, &bthr[j], lane);
+                    const int nk = min(VB, p.ncap);
+                    const bool mine = lane < nk && bpos[j * VB + lane] < (uint32_t)rs;
+                    const uint32_t kk = lane < nk ? bkeys[j * VB + lane] : 0u, pp = lane < nk ? bpos[j * VB + lane] : 0u;
+                    const unsigned keep = __ballot_sync(0xffffffffu, mine);
+                    __syncwarp();
+                    if (mine) {
+                        const int o = __popc(keep & ((1u << lane) - 1u));
+                        bkeys[j * VB + o] = kk;
+                        bpos[j * VB + o] = pp;
+                    }
+                    if (lane == 0) {
+                        bcnt[j] = __popc(keep);
+                        // entries equal to the bound must come back in: "<" against bound + 1
+                        if (bthr[j] != 0xffffffffu) bthr[j] += 1u;
+                        if (retries >= 3) bflag[j] = 2u;   // (degenerate: more than VB equal keys) -> exact pipeline
+                        else s_retry = 1u;
+                    }
+                } else if (n > p.ncap) {
+                    const int kept = cut_to_smallest(bkeys + j * VB, bpos + j * VB, n, p.ncap, &bthr[j], lane);
+                    if (lane == 0) bcnt[j] = kept;
                 }
+                __syncwarp();
+                if (lane == 0) tinit[j] = (unsigned short)(0x8000u - int_threshold(j));
             }
             __syncthreads();
-            if (tid < VJ / 2) {
-                const uint32_t t0 = int_threshold(2 * tid), t1 = int_threshold(2 * tid + 1);
-                tinit[tid] = (0x8000u - t0) | ((0x8000u - t1) << 16);
+            if (s_retry) {           // uniform: read by everyone between the two barriers' release and the reset below
+                ++retries;
+                __syncthreads();
+                if (tid == 0) s_retry = 0u;
+                // (a member that was flagged keeps its partial list; the query is handed to the exact pipeline)
+                continue;
             }
-            __syncthreads();
+            retries = 0;
+            seen += re - rs;
+            rs = re;
+            rsize = p.ncap <= 16 ? max(64, seen) : max(64, (seen >> 1) & ~31);
         }
         // ---- hand the item's lists over (at most ncap entries each, in no particular order)
         if (warp < members) {
             const int jj = warp;
-            const int n = bcnt[jj];
+            const int n = min(bcnt[jj], p.ncap);
             const size_t o = ((size_t)item * VJ + jj) * PLK;
             const uint32_t kv = lane < n ? bkeys[jj * VB + lane] : 0u;
             if (lane < n) {

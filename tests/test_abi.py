@@ -24,6 +24,22 @@ def test_library_exports_every_declared_symbol():
     assert sorted(capi.SIGNATURES) == names
 
 
+def test_rust_bindings_are_generated_from_the_header():
+    """rust_shim/src/ffi.rs declares every function of the header, with the same number of arguments: the committed
+    file is exactly what tools/gen_ffi.py prints for the current header."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gen_ffi", os.path.join(ROOT, "tools", "gen_ffi.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    text, funcs = gen.generate()
+    assert sorted(f[0] for f in funcs) == header_functions()
+    committed = open(os.path.join(ROOT, "rust_shim", "src", "ffi.rs")).read()
+    assert committed == text, "rust_shim/src/ffi.rs is stale: run python tools/gen_ffi.py --write"
+    from flechasdb_b200 import _capi as capi
+    for name, ret, params in funcs:
+        assert len(params) == len(capi.SIGNATURES[name][1]), name
+
+
 def test_error_codes_match_header():
     from flechasdb_b200 import _capi as capi
     text = open(os.path.join(ROOT, "include", "flechasdb_b200.h")).read()

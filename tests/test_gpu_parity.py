@@ -1041,6 +1041,25 @@ def test_cross_rank_merge_kernel_equals_the_host_merge(eng, ctx, oracle):
     full.close()
 
 
+def test_library_owned_comm_world_1_and_2():
+    """The multi-GPU entry points of the C ABI (fdb_comm, fdb_kmeans_*_sharded, fdb_index_query_sharded) against the
+    oracle: at world = 1 in this process' GPU, and over 2 ranks (NCCL inside the library) when the box has 2 GPUs."""
+    import os
+    import subprocess
+    import sys
+    from flechasdb_b200 import _capi as capi
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    tool = os.path.join(root, "tools", "dist_check2.py")
+    env = dict(os.environ, RANK="0", WORLD_SIZE="1", LOCAL_RANK="0")
+    out = subprocess.run([sys.executable, tool], capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0 and "ALL_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+    if capi.lib().fdb_device_count() >= 2:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+               "--master-addr", "127.0.0.1", "--master-port", "29534", tool]
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0 and "ALL_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
 def test_multi_gpu_sharded_build_and_query():
     import os
     import subprocess
