@@ -267,6 +267,34 @@ def run_ours(args, rank, world, local_rank, dist):
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop()
 
+    # the same call from PAGEABLE caller memory (a plain numpy array, what a Rust Vec<f32> is), and from the same
+    # array after fdb_host_register
+    e2e_other = {}
+    pageable_q = np.array(host_q, copy=True)
+    pg_out = [np.zeros((nq, K), np.uint32), np.zeros((nq, K), np.uint32), np.zeros((nq, K), np.float32), np.zeros(nq, np.uint32)]
+
+    def step_plain():
+        capi.check(capi.lib().fdb_index_query(ix.h, capi.f32p(pageable_q), nq, K, NPROBE, capi.QUERY_STORED,
+                                              capi.u32p(pg_out[0]), capi.u32p(pg_out[1]), capi.f32p(pg_out[2]),
+                                              capi.u32p(pg_out[3])))
+    for label in ("pageable", "registered"):
+        if label == "registered":
+            t0 = time.perf_counter()
+            for a in [pageable_q] + pg_out:
+                ctx.host_register(a)
+            e2e_other["register_ms_once"] = (time.perf_counter() - t0) * 1e3
+        for _ in range(2):
+            step_plain()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_plain()
+        ctx.sync()
+        dt = time.perf_counter() - t0
+        e2e_other[label] = {"queries_per_s": nq * args.steps / dt, "ms_per_step": dt * 1e3 / args.steps,
+                            "same_results": bool((pg_out[1] == o_vidx).all() and (pg_out[2] == o_dist).all())}
+    for a in [pageable_q] + pg_out:
+        ctx.host_unregister(a)
+
     # ---- configs[0]: sequential single queries through the host call (the README's usage) ------
     nsingle = 200
     step_e2e_single = lambda i: capi.check(capi.lib().fdb_index_query(
@@ -405,7 +433,8 @@ def run_ours(args, rank, world, local_rank, dist):
                    "nprobe": NPROBE, "l2": "flushed between timed steps (256 MiB write)",
                    "parallelism": "index replicated, queries sharded x%d" % world},
         "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": nq * N * 4,
-                "d2h_bytes_per_step": nq * K * 12 + nq * 4, "ms_per_step": e2e_ms / args.steps},
+                "d2h_bytes_per_step": nq * K * 12 + nq * 4, "ms_per_step": e2e_ms / args.steps,
+                "host_buffers": "pinned (torch pin_memory)", "other_host_buffers": e2e_other},
         "gpu_launches": int(step_launches),
         "roofline": roofline_scan, "roofline_other_kernels": rooflines_other,
         "phase_ms_per_step": {n_: float(v) for n_, v in zip(names, ph)},

@@ -118,6 +118,8 @@ SIGNATURES = {
     "fdb_kmeans_run_sharded": (C.c_int, [VP, VP, SZ, C.c_float, F32P, U32P, U32P]),
     "fdb_index_query_sharded": (C.c_int, [VP, VP, VP, SZ, SZ, SZ, C.c_int, VP, VP, VP, VP]),
     "fdb_index_last_sharded_ties": (C.c_int, [VP, U32P]),
+    "fdb_host_register": (C.c_int, [VP, VP, SZ]),
+    "fdb_host_unregister": (C.c_int, [VP, VP]),
     "fdb_device_alloc": (C.c_int, [VP, SZ, C.POINTER(VP)]),
     "fdb_device_free": (C.c_int, [VP, VP]),
     "fdb_device_upload": (C.c_int, [VP, VP, VP, SZ]),

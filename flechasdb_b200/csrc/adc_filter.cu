@@ -44,6 +44,9 @@ namespace fdb {
 struct FilterState {
     DevBuf<float> pc;            // [P][D][C]
     DevBuf<float> pcmm;          // [P][D][2] min and max of every PC row (16-bit tables of adc_pscan.cuh)
+    DevBuf<float> pct;           // [P][D * 256] PC - row minimum in the row order of the vector-lane scan (adc_vscan.cuh)
+    DevBuf<float> pcpar;         // [P][4] sum of the row minima, of their magnitudes, of the row ranges
+    DevBuf<unsigned> pc_range_max;   // max over the partitions of the summed row ranges (float bits)
     DevBuf<float> cbmax;         // [D]
     DevBuf<unsigned> bounds;     // float bits: [0] cb2, [1] pcmax
     DevBuf<uint8_t> rec;         // records (RECORDS layout), empty when the lists are long
@@ -79,6 +82,8 @@ struct FilterState {
         DevBuf<unsigned> pg_thr;     // [nq]
         DevBuf<uint32_t> it_keys, it_pos, it_cnt;
         DevBuf<float> gmm;           // [chunk_q][D][2] min and max of every G row
+        DevBuf<unsigned short> Gq;   // [chunk_q][D * 256] fixed-point tables of the vector-lane scan, in its row order
+        DevBuf<float> qpar;          // [chunk_q][4] scale, sum of the row minima, of their magnitudes, of the row ranges
         DevBuf<unsigned> eadd;       // [nq] extra error of the 16-bit tables (float bits)
         DevBuf<unsigned long long> counters;  // [0] fallbacks, [1] exact candidates, [2] scanned vectors, [4..] reasons
         cudaStream_t stream = nullptr;
@@ -1323,10 +1328,12 @@ __global__ void __launch_bounds__(128) fselect_kernel(FSelParams p) {
         // S = the k smallest approximations; max_S R <= (a_(k) + E)(1 + eta) =: Rmax >= the k-th smallest R,
         // and every v with R(v) <= Rmax (the reference's k best and anything tied with the k-th) has
         // A(v) <= Rmax / (1 - eta) + E
-        const float E = p.coef * p.Wq[q] + (p.eadd ? __uint_as_float(p.eadd[q]) : 0.0f);
+        // (Eg: the GEMM / f32 error model, widened by BAND_SAFETY; Ea: the fixed-point tables' quantisation error,
+        //  a rigorous bound that needs no widening)
+        const float Eg = p.coef * p.Wq[q], Ea = p.eadd ? __uint_as_float(p.eadd[q]) : 0.0f;
         const float tau = __shfl_sync(0xffffffffu, a, k - 1);
-        const float hi = (tau + E) * (1.0f + p.eta3) + E;
-        const float thr = tau + BAND_SAFETY * (hi - tau);
+        const float hi_g = (tau + Eg) * (1.0f + p.eta3) + Eg;
+        const float thr = tau + BAND_SAFETY * (hi_g - tau) + Ea * (2.0f + p.eta3) * 1.0001f;
         int why = 0;
         if (!(fabsf(thr) < 1e30f)) fb = true, why = 6;  // NaN or overflow
         ncand = __popc(__ballot_sync(0xffffffffu, lane < cnt && a <= thr));
@@ -1573,12 +1580,33 @@ bool pscan16_smem_ok(size_t D) {
 }
 #include "adc_vscan.cuh"
 
-PScanFn vscan_fn(size_t D) {
+typedef void (*VScanFn)(PScanParams, VScanExtra);
+VScanFn vscan_fn(size_t D) {
     switch (D) {
         case 4: return vscan_kernel<1>;
         case 8: return vscan_kernel<2>;
         case 12: return vscan_kernel<3>;
         case 16: return vscan_kernel<4>;
+        default: return nullptr;
+    }
+}
+typedef void (*VQuantFn)(const float *, int, const unsigned *, unsigned short *, float4 *);
+VQuantFn vquant_fn(size_t D) {
+    switch (D) {
+        case 4: return vq_quant_kernel<1>;
+        case 8: return vq_quant_kernel<2>;
+        case 12: return vq_quant_kernel<3>;
+        case 16: return vq_quant_kernel<4>;
+        default: return nullptr;
+    }
+}
+typedef void (*VPctFn)(const float *, const float *, int, float *, float4 *, unsigned *);
+VPctFn vpct_fn(size_t D) {
+    switch (D) {
+        case 4: return vq_pct_kernel<1>;
+        case 8: return vq_pct_kernel<2>;
+        case 12: return vq_pct_kernel<3>;
+        case 16: return vq_pct_kernel<4>;
         default: return nullptr;
     }
 }
@@ -1654,6 +1682,17 @@ int filter_prepare(fdb_index *ix) {
     g_minmax_kernel<<<(unsigned)((P * D + 7) / 8), 256, 0, st>>>(fs->pc.p, P * D, (int)C, fs->pcmm.p);
     ctx->launches++;
     FDB_CHECK_LAUNCH();
+    // the vector-lane scan (adc_vscan.cuh) reads PC in its own row order, row minimum subtracted
+    if (vpct_fn(D) && C <= (size_t)PT_STRIDE && P * D * PT_STRIDE * sizeof(float) <= (4ull << 30) && !getenv("FDB_NO_VSCAN")) {
+        FDB_TRY(fs->pct.alloc(P * D * PT_STRIDE));
+        FDB_TRY(fs->pcpar.alloc(P * 4));
+        FDB_TRY(fs->pc_range_max.alloc(1));
+        FDB_CUDA(cudaMemsetAsync(fs->pc_range_max.p, 0, sizeof(unsigned), st));
+        vpct_fn(D)<<<(unsigned)P, 256, 0, st>>>(fs->pc.p, fs->pcmm.p, (int)C, fs->pct.p, reinterpret_cast<float4 *>(fs->pcpar.p),
+                                                fs->pc_range_max.p);
+        ctx->launches++;
+        FDB_CHECK_LAUNCH();
+    }
     float hb[2];
     FDB_CUDA(cudaMemcpyAsync(hb, fs->bounds.p, sizeof(hb), cudaMemcpyDeviceToHost, st));
     FDB_CUDA(cudaStreamSynchronize(st));
@@ -1700,8 +1739,13 @@ bool filter_eligible(const fdb_index *ix, size_t nq, size_t k, size_t nprobe) {
 
 // when the vector-lane scan (adc_vscan.cuh) is the default
 static bool vscan_default(const fdb_index *ix, size_t nq, size_t nprobe) {
-    (void)ix, (void)nq, (void)nprobe;
-    return getenv("FDB_VSCAN_DEFAULT") != nullptr;
+    // Measured.  Lists of thousands of vectors: ahead of the query-major kernel from about two
+    // queries per list on (0.77 of the HBM bandwidth at 8 queries per list, 1.1 from 32 on; fscan_kernel: 0.35).
+    // Short lists (the README shape, 1 000 vectors): a table per (8 queries, list) costs as much as scanning the list,
+    // the query-major kernel builds one table per query for all its lists -- level at nprobe = 5, ahead from ~8 on.
+    if (getenv("FDB_VSCAN_OFF")) return false;
+    if ((double)nq * (double)nprobe < 2.0 * (double)ix->P) return false;
+    return ix->M >= 2048 * ix->P || nprobe >= 8;
 }
 
 // E_q = coef * W_q (header): gamma of the GEMM that produces G (tensor pipe or FMA chain)
@@ -1934,7 +1978,7 @@ int filter_query(fdb_index *ix, const float *d_q, size_t q_base, size_t nq, size
     // scan kernel: FDB_FILTER_SCAN = "query" / "partition" / "partition16" / "vector" forces one (tests, profiling)
     const char *scan_env = getenv("FDB_FILTER_SCAN");
     // vector-lane scan with packed 16-bit tables (adc_vscan.cuh): D = 4, 8, 12, 16, compact codes
-    const bool v_ok = vscan_fn(D) && C <= (size_t)PT_STRIDE && ix->M > 0;
+    const bool v_ok = vscan_fn(D) && fs->pct.p && ix->M > 0;
     bool use_vscan = v_ok && vscan_default(ix, nq, nprobe);
     if (scan_env) use_vscan = !strcmp(scan_env, "vector");
     if (use_vscan && !v_ok) {
@@ -1972,7 +2016,8 @@ int filter_query(fdb_index *ix, const float *d_q, size_t q_base, size_t nq, size
     const FScanFn scan = scan_fn(D, records);
     FDB_CUDA(cudaFuncSetAttribute(scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // list capacity: k plus head room for the vectors inside the error band
-    const int ncap = (int)std::min<size_t>(RCAP, k + 6);
+    // (the fixed-point tables of the vector-lane scan widen the band: four more places)
+    const int ncap = (int)std::min<size_t>(RCAP, k + (use_vscan ? 10 : 6));
     const bool vec = (s % 4 == 0) && (N % 4 == 0) && ((uintptr_t)d_q % 16 == 0);
     const float coef = adc_coef(s, D, tc_g);
     const float eta3 = (float)(2.1 * ((double)s / 16.0 + 40.0 + (double)D) * U24);
@@ -2001,7 +2046,8 @@ int filter_query(fdb_index *ix, const float *d_q, size_t q_base, size_t nq, size
         }
     }
     const size_t pj = use_vscan ? VJ : use_p16 ? QJ : PJ;
-    const PScanFn pscan = use_vscan ? vscan_fn(D) : use_p16 ? pscan16_fn(D) : pscan_fn(D, records);
+    const PScanFn pscan = use_vscan ? nullptr : use_p16 ? pscan16_fn(D) : pscan_fn(D, records);
+    const VScanFn vscan = use_vscan ? vscan_fn(D) : nullptr;
     const size_t psmem = use_vscan ? vscan_smem_bytes(D) : pscan_smem_bytes(D, rb);
     // probe rank 0 first (two buckets per partition) only when both buckets fill their groups
     const bool pscan_split = pairs_per_list >= 4.0 * (double)pj && nprobe > 1 && !getenv("FDB_PSCAN_NO_SPLIT");
@@ -2011,7 +2057,8 @@ int filter_query(fdb_index *ix, const float *d_q, size_t q_base, size_t nq, size
         const size_t bound = pscan_items_bound(ix, cq * nprobe, pj);
         if (bound * pj * PLK * 8 > (2ull << 30)) use_pscan = false;
         else {
-            FDB_CUDA(cudaFuncSetAttribute(pscan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+            if (use_vscan) FDB_CUDA(cudaFuncSetAttribute(vscan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+            else FDB_CUDA(cudaFuncSetAttribute(pscan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
             FDB_TRY(sl->pg_ctl.ensure(2 * ix->P + 1));
             FDB_TRY(sl->pg_pstart.ensure(2 * ix->P + 1));
             FDB_TRY(sl->pg_istart.ensure(2 * ix->P + 1));
@@ -2022,7 +2069,11 @@ int filter_query(fdb_index *ix, const float *d_q, size_t q_base, size_t nq, size
             FDB_TRY(sl->it_keys.ensure(bound * pj * PLK));
             FDB_TRY(sl->it_pos.ensure(bound * pj * PLK));
             FDB_TRY(sl->it_cnt.ensure(bound * pj));
-            if (use_p16 || use_vscan) FDB_TRY(sl->gmm.ensure(cq * D * 2));
+            if (use_p16) FDB_TRY(sl->gmm.ensure(cq * D * 2));
+            if (use_vscan) {
+                FDB_TRY(sl->Gq.ensure(cq * D * PT_STRIDE));
+                FDB_TRY(sl->qpar.ensure(cq * 4));
+            }
             FDB_CUDA(cudaMemsetAsync(sl->pg_thr.p, 0xff, nq * sizeof(unsigned), st));
         }
     }
@@ -2077,8 +2128,12 @@ int filter_query(fdb_index *ix, const float *d_q, size_t q_base, size_t nq, size
         const size_t P = ix->P, npairs = nc * nprobe;
         FDB_CUDA(cudaMemsetAsync(sl->pg_ctl.p, 0, (2 * P + 1) * sizeof(uint32_t), st));
         const uint32_t *chunk_probes = d_probes + q0 * nprobe;
-        pg_count_kernel<<<(unsigned)((npairs + 255) / 256), 256, 0, st>>>(chunk_probes, npairs, pscan_split ? (int)nprobe : 0, (int)P,
-                                                                          sl->pg_ctl.p, sl->pg_slot.p);
+        if (2 * P <= (size_t)PG_SMEM_BUCKETS)
+            pg_count_smem_kernel<<<(unsigned)((npairs + 1023) / 1024), 1024, 0, st>>>(chunk_probes, npairs, pscan_split ? (int)nprobe : 0,
+                                                                                   (int)P, sl->pg_ctl.p, sl->pg_slot.p);
+        else
+            pg_count_kernel<<<(unsigned)((npairs + 255) / 256), 256, 0, st>>>(chunk_probes, npairs, pscan_split ? (int)nprobe : 0, (int)P,
+                                                                              sl->pg_ctl.p, sl->pg_slot.p);
         pg_scan_kernel<<<1, 1024, 0, st>>>(sl->pg_ctl.p, ix->part_off.p, (int)P, PSCAN_VCH, (int)pj, sl->pg_pstart.p, sl->pg_istart.p);
         pg_scatter_kernel<<<(unsigned)((npairs + 255) / 256), 256, 0, st>>>(chunk_probes, sl->pg_slot.p, sl->pg_pstart.p, npairs,
                                                                             pscan_split ? (int)nprobe : 0, (int)P, sl->pg_pairs.p);
@@ -2107,8 +2162,13 @@ int filter_query(fdb_index *ix, const float *d_q, size_t q_base, size_t nq, size
         pp.gmm = sl->gmm.p;
         pp.pcmm = fs->pcmm.p;
         pp.eadd = sl->eadd.p;
+        VScanExtra vx;
+        vx.Gq = sl->Gq.p;
+        vx.qpar = reinterpret_cast<const float4 *>(sl->qpar.p);
+        vx.pct = fs->pct.p;
+        vx.pcpar = reinterpret_cast<const float4 *>(fs->pcpar.p);
         if (use_vscan) {
-            vq_minmax_kernel<<<(unsigned)((nc * D + 7) / 8), 256, 0, st>>>(sl->G.p, nc * D, (int)C, sl->gmm.p);
+            vquant_fn(D)<<<(unsigned)nc, 256, 0, st>>>(sl->G.p, (int)C, fs->pc_range_max.p, sl->Gq.p, reinterpret_cast<float4 *>(sl->qpar.p));
             ctx->launches++;
         } else if (use_p16) {
             g_minmax_kernel<<<(unsigned)((nc * D + 7) / 8), 256, 0, st>>>(sl->G.p, nc * D, (int)C, sl->gmm.p);
@@ -2116,7 +2176,8 @@ int filter_query(fdb_index *ix, const float *d_q, size_t q_base, size_t nq, size
         }
         const size_t ctas = use_vscan ? (size_t)ctx->sm_count * vscan_ctas_per_sm(D) : (size_t)ctx->sm_count;
         const unsigned pgrid = (unsigned)std::min<size_t>(pscan_items_bound(ix, npairs, pj), ctas);
-        pscan<<<pgrid, use_vscan ? VWARPS * 32 : PW * 32, psmem, st>>>(pp);
+        if (use_vscan) vscan<<<pgrid, VWARPS * 32, psmem, st>>>(pp, vx);
+        else pscan<<<pgrid, PW * 32, psmem, st>>>(pp);
         PMergeParams mp;
         mp.probes = d_probes;
         mp.part_off = ix->part_off.p;

@@ -70,6 +70,30 @@ __global__ void __launch_bounds__(256) pg_count_kernel(const uint32_t *probes, s
     if (i < npairs) pair_slot[i] = atomicAdd(&count[pg_bucket(probes, i, nprobe, P)], 1u);
 }
 
+// few buckets (2 P <= 4096): the pairs of a CTA are counted in shared memory first, one global atomic per bucket and
+// CTA (the plain kernel above spends its time on 50 000 atomics that hit 200 addresses)
+constexpr int PG_SMEM_BUCKETS = 4096;
+__global__ void __launch_bounds__(1024) pg_count_smem_kernel(const uint32_t *probes, size_t npairs, int nprobe, int P,
+                                                             uint32_t *count, uint32_t *pair_slot) {
+    __shared__ uint32_t h[PG_SMEM_BUCKETS];
+    const int NB = 2 * P;
+    for (int b = threadIdx.x; b < NB; b += blockDim.x) h[b] = 0u;
+    __syncthreads();
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t b = 0, local = 0;
+    if (i < npairs) {
+        b = pg_bucket(probes, i, nprobe, P);
+        local = atomicAdd(&h[b], 1u);
+    }
+    __syncthreads();
+    for (int bb = threadIdx.x; bb < NB; bb += blockDim.x) {
+        const uint32_t c = h[bb];
+        if (c) h[bb] = atomicAdd(&count[bb], c);   // the CTA's first slot in the bucket
+    }
+    __syncthreads();
+    if (i < npairs) pair_slot[i] = h[b] + local;
+}
+
 // exclusive scans over the buckets: pairs (pstart) and items (istart); one CTA
 __global__ void __launch_bounds__(1024) pg_scan_kernel(const uint32_t *count, const uint32_t *part_off, int P, int vch,
                                                        int pj, uint32_t *pstart, uint32_t *istart) {

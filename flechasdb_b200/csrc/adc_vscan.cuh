@@ -8,27 +8,29 @@
 // owns a VECTOR and one look-up serves EIGHT queries:
 //
 //   item     = (partition, up to VJ = 8 queries that probe it, chunk of its vectors)   [pg_*_kernel, pj = 8]
-//   table    T[d][c] = one 16-byte row = the 8 queries' 16-bit fixed-point entries
-//                u_j[d][c] = round((G[q_j][d][c] + PC[p][d][c] - m_jd) / delta_j),
-//                m_jd = min bound of the row, delta_j = sum_d range_jd / (32767 - D)   (so sum_d u <= 32767)
-//   look-up  one LDS.128 at (d, code): 8 entries; the four 32-bit words are added as they are -- two 15-bit sums
-//            per word never carry into each other.  D look-ups + D adds per lane serve 8 x 32 pairs per warp.
-//   select   the accumulators start at 0x8000 - t_j (t_j = the query's threshold in table units), so bit 15 of
-//            a half word says "sum >= threshold": one AND over the four words tells a lane that none of its 8
-//            sums is interesting (the steady state: 12 LDS.128, 2 x 12 address instructions, 12 x 4 adds, 3
-//            logic instructions per 256 pairs).  The rare lane that sees a candidate converts the sum back to
-//            a float (base_j + delta_j * S), re-checks it against the float threshold and appends it to the
-//            query's buffer, exactly like the other scan kernels (rounds that double, cut_to_smallest between
-//            rounds, thresholds shared between a query's items through thrg[q]).
+//   table    one 16-byte row per (division d, code c) = the 8 queries' 16-bit fixed-point entries
+//                u_j[d][c] = round((G[q_j][d][c] - mG_jd) / delta_j) + round((PC[p][d][c] - mPC_pd) / delta_j)
+//            (mG / mPC = the minimum of the table row; delta_j such that sum_d u <= 65535 for every list).  The first
+//            term is made once per query and batch (vq_quant_kernel, u16, already in the table's row order), the
+//            second when the item's table is assembled: one coalesced pass over 6 KB per query and 12 KB of PC.
+//   look-up  one LDS.128 at (d, code): 8 entries; the four 32-bit words are added as they are -- the two 16-bit
+//            sums of a word never carry into each other (delta_j makes sum_d u <= 65535).  The rows are laid out so that the look-ups of a quarter warp
+//            never share a bank group (VLayout below): one wavefront per quarter warp.
+//   select   t_j = the query's threshold in table units, two per word like the sums: min.u16x2(S, t) != t in some
+//            half word <=> that sum is below its threshold.  Four packed minima and four logic instructions tell a
+//            lane that none of its 8 sums is interesting (the steady state: D LDS.128, 4 D adds, ~10 instructions of
+//            selection per 256 pairs).
+//            The rare lane that sees a candidate converts the sum back to a float (base_j + delta_j * S),
+//            re-checks it against the float threshold and appends it to the query's buffer, like the other scan
+//            kernels (cut_to_smallest between rounds, thresholds shared between a query's items through thrg[q]).
 //
 // The table costs 4 KB per division (48 KB at D = 12): four CTAs of 8 warps per SM.  The quantisation error
-// (D delta_j / 2 + roundings, delta_j ~ 24 x that of pscan16_kernel) goes to fselect_kernel through eadd[q],
-// which widens the band by it: the results stay the reference's bit for bit, only the number of candidates
-// that get an exact distance grows (measured: +0.1 per query on the README shape).
+// (D delta_j + roundings) goes to fselect_kernel through eadd[q], which widens the band by it: the results stay
+// the reference's bit for bit, only the number of candidates that get an exact distance grows slightly.
 //
 // Non-finite numbers never reach the packed sums (a garbage entry could carry into the neighbouring query's
-// half word): vq_minmax_kernel marks rows of G that hold a non-finite value with NaN bounds, such a member is
-// flagged (exact pipeline) and gets zero entries; PC is finite or the index has no filter state at all.
+// half word): vq_quant_kernel gives a query whose table holds a non-finite value a NaN delta, such a member is
+// flagged (exact pipeline) and its entries are masked; PC is finite or the index has no filter state at all.
 
 constexpr int VJ = 8;            // queries per item
 constexpr int VWARPS = 8;        // warps per CTA
@@ -36,37 +38,187 @@ constexpr int VB = 64;           // append buffer entries per query
 constexpr int VDESC = 4 + VJ;    // words of an item descriptor (pg_items_kernel with pj = VJ)
 constexpr float VMAGIC = 8388608.0f;   // 2^23: fma(x, 1, 2^23) leaves round(x) in the low mantissa bits
 
-// min and max of every row of C floats, one warp per row; a row with a non-finite (or huge) value gets NaN
-// bounds, which the scan turns into "flag this query"
-__global__ void __launch_bounds__(256) vq_minmax_kernel(const float *a, size_t nrows, int C, float *mm) {
-    const size_t row = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (row >= nrows) return;
-    float mn = INFINITY, mx = -INFINITY;
-    bool bad = false;
-    const float *r = a + row * (size_t)C;
-    if (C % 4 == 0 && (reinterpret_cast<uintptr_t>(r) & 15) == 0) {
-        for (int c = lane * 4; c < C; c += 128) {
-            const float4 v = __ldg(reinterpret_cast<const float4 *>(r + c));
-            bad |= !(fabsf(v.x) + fabsf(v.y) + fabsf(v.z) + fabsf(v.w) < 1e30f);
-            mn = fminf(fminf(mn, v.x), fminf(fminf(v.y, v.z), v.w));
-            mx = fmaxf(fmaxf(mx, v.x), fmaxf(fmaxf(v.y, v.z), v.w));
-        }
+// Table layout in shared memory: conflict free by construction.  A 128-bit look-up is served one quarter warp (8
+// lanes) per wavefront when the 8 lanes hit 8 different 16-byte bank groups.  The divisions are taken in groups of
+// 8: the rows (d0 .. d0+7, c) of a code c form ONE 128-byte line, slot s = d - d0 at byte 16 s -- and lane l walks the
+// group in the rotated order s = (l + t) mod 8, t = 0..7, so at every step the lanes of a quarter warp sit in 8
+// different slots = 8 different bank groups, whatever their codes are.  A trailing group of 4 divisions uses 64
+// bytes per code (slot = (c & 1) * 4 + d - d0 within the line): lanes l and l + 4 share a slot and collide when
+// their codes have the same parity.  Measured against the plain [d][c] layout (8 random rows per quarter warp, 2.9
+// wavefronts each): 6.5 instead of 11.7 wavefronts per look-up at D = 12.
+template <int W>
+struct VLayout {
+    static constexpr int D = 4 * W;
+    static constexpr int NF = D / 8;             // full groups (8 divisions, 128 bytes per code)
+    static constexpr bool HALF = (D % 8) != 0;   // one trailing group of 4 divisions (64 bytes per code)
+    static constexpr int F_BYTES = PT_STRIDE * 128, H_BYTES = PT_STRIDE * 64;
+    static constexpr int ROWS = D * PT_STRIDE;   // 16-byte rows; row r of the table lives at byte 16 r
+    static constexpr int BYTES = ROWS * 16;
+};
+// row r -> (division, code)
+template <int W>
+__device__ __forceinline__ void vrow_to_dc(int r, int &d, int &c) {
+    using L = VLayout<W>;
+    if (r < L::NF * PT_STRIDE * 8) {
+        const int g = r / (PT_STRIDE * 8), rr = r - g * (PT_STRIDE * 8);
+        c = rr >> 3;
+        d = g * 8 + (rr & 7);
     } else {
-        for (int c = lane; c < C; c += 32) {
-            const float v = r[c];
-            bad |= !(fabsf(v) < 1e30f);
-            mn = fminf(mn, v);
-            mx = fmaxf(mx, v);
+        const int rr = r - L::NF * PT_STRIDE * 8;
+        c = rr >> 2;
+        d = L::NF * 8 + (rr & 3);
+    }
+}
+// (division, code) -> row
+template <int W>
+__device__ __forceinline__ int vdc_to_row(int d, int c) {
+    using L = VLayout<W>;
+    return d < L::NF * 8 ? (d >> 3) * (PT_STRIDE * 8) + c * 8 + (d & 7) : L::NF * PT_STRIDE * 8 + c * 4 + (d & 3);
+}
+
+// ---- per index: PC in the table's row order, minimum subtracted -------------------------------------------
+// pct[p][r] = PC[p][d][c] - min_c PC[p][d][.] for row r = (d, c) (0 for c >= C); pcpar[p] = (sum_d min, sum_d |min|,
+// sum_d range, 0); *range_max_bits = max_p sum_d range (float bits, atomicMax).  One CTA per partition.
+template <int W>
+__global__ void __launch_bounds__(256) vq_pct_kernel(const float *pc, const float *pcmm, int C, float *pct, float4 *pcpar,
+                                                     unsigned *range_max_bits) {
+    using L = VLayout<W>;
+    constexpr int D = 4 * W;
+    const size_t p = blockIdx.x;
+    __shared__ float mn[D];
+    if (threadIdx.x < D) mn[threadIdx.x] = pcmm[(p * D + threadIdx.x) * 2];
+    __syncthreads();
+    for (int r = threadIdx.x; r < L::ROWS; r += blockDim.x) {
+        int d, c;
+        vrow_to_dc<W>(r, d, c);
+        pct[p * L::ROWS + r] = c < C ? pc[(p * D + d) * C + c] - mn[d] : 0.0f;
+    }
+    if (threadIdx.x == 0) {
+        float ms = 0.0f, ma = 0.0f, rs = 0.0f;
+        for (int d = 0; d < D; ++d) {
+            const float lo = pcmm[(p * D + d) * 2], hi = pcmm[(p * D + d) * 2 + 1];
+            ms += lo;
+            ma += fabsf(lo);
+            rs += hi - lo;
         }
+        pcpar[p] = make_float4(ms, ma, rs, 0.0f);
+        atomicMax(range_max_bits, __float_as_uint(fmaxf(rs, 0.0f)));
+    }
+}
+
+// ---- per batch: every query's table, quantised, in the table's row order -----------------------------------
+// One CTA per query: Gq[q][r] = round((G[q][d][c] - m_qd) / delta_q) as u16 for row r = (d, c) (0 for c >= C),
+//   m_qd = min_c G[q][d][.],  delta_q = (sum_d range_qd + max_p sum_d rangePC_pd) * 1.0002 / (65535 - 2 D),
+// so that sum_d (uG + uPC) <= 65535 for every list.  qpar[q] = (delta, sum_d m, sum_d |m|, sum_d range); a
+// non-finite or huge entry anywhere in the query's table makes delta NaN ("flag this query").
+template <int W>
+__global__ void __launch_bounds__(256) vq_quant_kernel(const float *G, int C, const unsigned *range_max_bits,
+                                                       unsigned short *Gq, float4 *qpar) {
+    using L = VLayout<W>;
+    constexpr int D = 4 * W;
+    __shared__ float wmn[8][D], wmx[8][D];
+    __shared__ float smn[D], smx[D];
+    __shared__ float s_inv;
+    __shared__ int s_bad;
+    __shared__ __align__(16) unsigned short stage[L::ROWS];
+    const size_t q = blockIdx.x;
+    const int c = threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float *g0 = G + q * (size_t)(D * C);
+    float g[D];
+    bool bad = false;
+    if (threadIdx.x == 0) s_bad = 0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        g[d] = c < C ? __ldg(g0 + d * C + c) : 0.0f;
+        bad |= !(fabsf(g[d]) < 1e30f);
     }
 #pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, off));
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    for (int d = 0; d < D; ++d) {
+        // warp minimum / maximum through the order-preserving integer key (one REDUX each instead of five shuffles)
+        const uint32_t kv = fkey(g[d]);
+        const uint32_t kmn = __reduce_min_sync(0xffffffffu, c < C ? kv : 0xffffffffu);
+        const uint32_t kmx = __reduce_max_sync(0xffffffffu, c < C ? kv : 0u);
+        if (lane == 0) wmn[warp][d] = kmn == 0xffffffffu ? INFINITY : fkey_inv(kmn), wmx[warp][d] = kmx == 0u ? -INFINITY : fkey_inv(kmx);
     }
-    bad = __any_sync(0xffffffffu, bad);
-    if (lane == 0) mm[2 * row] = bad ? NAN : mn, mm[2 * row + 1] = bad ? NAN : mx;
+    __syncthreads();
+    if (bad) s_bad = 1;
+    if (threadIdx.x < D) {
+        float mn = INFINITY, mx = -INFINITY;
+        for (int w = 0; w < 8; ++w) mn = fminf(mn, wmn[w][threadIdx.x]), mx = fmaxf(mx, wmx[w][threadIdx.x]);
+        smn[threadIdx.x] = mn;
+        smx[threadIdx.x] = mx;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float rs = 0.0f, ms = 0.0f, ma = 0.0f;
+        for (int d = 0; d < D; ++d) {
+            rs += smx[d] - smn[d];
+            ms += smn[d];
+            ma += fabsf(smn[d]);
+        }
+        const float rpc = __uint_as_float(*range_max_bits);
+        float delta = fmaxf((rs + rpc) * (1.0002f / (float)(65535 - 2 * D)), 1e-30f);
+        if (s_bad || !(rs < 1e30f) || !(ma < 1e30f) || !(delta < 1e30f)) delta = NAN;
+        s_inv = delta == delta ? 1.0f / delta : 0.0f;
+        qpar[q] = make_float4(delta, ms, ma, rs);
+    }
+    __syncthreads();
+    const float inv = s_inv;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        // (g - m) >= 0 exactly, so the fma stays >= 2^23 and its low mantissa bits are round((g - m) / delta)
+        const float x = fmaf(g[d] - smn[d], inv, VMAGIC);
+        stage[vdc_to_row<W>(d, c)] = (c < C && inv > 0.0f) ? (unsigned short)(__float_as_uint(x) & 0xffffu) : (unsigned short)0;
+    }
+    __syncthreads();
+    uint4 *dst = reinterpret_cast<uint4 *>(Gq + q * (size_t)L::ROWS);
+    const uint4 *src = reinterpret_cast<const uint4 *>(stage);
+    for (int i = threadIdx.x; i < L::ROWS / 8; i += blockDim.x) dst[i] = src[i];
+}
+
+// (key, pos) compare-exchange with the lane j away (ascending block: the lower lane keeps the smaller pair)
+__device__ __forceinline__ void cmpx_lanes(uint32_t &key, uint32_t &pos, int j, bool asc, int lane) {
+    const uint32_t ok = __shfl_xor_sync(0xffffffffu, key, j), op = __shfl_xor_sync(0xffffffffu, pos, j);
+    const bool keep_min = ((lane & j) == 0) == asc;
+    const bool other_less = (ok < key) || (ok == key && op < pos);
+    const bool other_more = (ok > key) || (ok == key && op > pos);
+    if (keep_min ? other_less : other_more) key = ok, pos = op;
+}
+// cuts a buffer of n <= 64 entries back to its ncap <= 32 smallest, sorted ascending at the front of the buffer; one
+// warp, two entries per lane (bitonic sort of 64).  Returns the new count; *thr = min(*thr, largest kept) when full.
+__device__ __forceinline__ int cut_to_smallest64(uint32_t *bk, uint32_t *bp, int n, int ncap, unsigned *thr, int lane) {
+    if (n <= 0) return 0;
+    uint32_t k0 = lane < n ? bk[lane] : 0xffffffffu, p0 = lane < n ? bp[lane] : 0xffffffffu;
+    if (n <= 32) {
+        warp_sort32(k0, p0, lane);
+    } else {
+        uint32_t k1 = 32 + lane < n ? bk[32 + lane] : 0xffffffffu, p1 = 32 + lane < n ? bp[32 + lane] : 0xffffffffu;
+#pragma unroll
+        for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+            for (int j = k >> 1; j >= 1; j >>= 1) {
+                // element i = lane (register 0) or 32 + lane (register 1); block direction = bit k of i
+                cmpx_lanes(k0, p0, j, (lane & k) == 0, lane);
+                cmpx_lanes(k1, p1, j, k == 32 ? false : (lane & k) == 0, lane);
+            }
+        }
+        // k = 64, j = 32: the partner is the lane's other register; then both halves ascending
+        if (k1 < k0 || (k1 == k0 && p1 < p0)) {
+            const uint32_t tk = k0, tp = p0;
+            k0 = k1, p0 = p1, k1 = tk, p1 = tp;
+        }
+#pragma unroll
+        for (int j = 16; j >= 1; j >>= 1) cmpx_lanes(k0, p0, j, true, lane);   // (only the smaller 32 are needed)
+    }
+    const int kept = min(n, ncap);
+    __syncwarp();
+    if (lane < kept) bk[lane] = k0, bp[lane] = p0;
+    if (kept == ncap) {
+        const uint32_t last = __shfl_sync(0xffffffffu, k0, ncap - 1);
+        if (lane == 0) *thr = min(*thr, last);
+    }
+    __syncwarp();
+    return kept;
 }
 
 __device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
@@ -91,40 +243,15 @@ __device__ __forceinline__ void load_code_words(const unsigned char *lst, int v,
     }
 }
 
-// Table layout in shared memory: conflict free by construction.  A 128-bit look-up is served one quarter warp (8
-// lanes) per wavefront when the 8 lanes hit 8 different 16-byte bank groups.  The divisions are taken in groups of
-// 8: the rows (d0 .. d0+7, c) of a code c form ONE 128-byte line, slot s = d - d0 at byte 16 s -- and lane l walks the
-// group in the rotated order s = (l + t) mod 8, t = 0..7, so at every step the lanes of a quarter warp sit in 8
-// different slots = 8 different bank groups, whatever their codes are.  A trailing group of 4 divisions uses 64
-// bytes per code (slot = (c & 1) * 4 + d - d0 within the line): lanes l and l + 4 share a slot and collide only when
-// their codes have the same parity (1.5 wavefronts per quarter warp on average).  Measured against the plain
-// [d][c] layout (8 random rows per quarter warp: 2.9 wavefronts): 56 instead of 140 wavefronts per warp step at D = 12.
-template <int W>
-struct VLayout {
-    static constexpr int D = 4 * W;
-    static constexpr int NF = D / 8;             // full groups (8 divisions, 128 bytes per code)
-    static constexpr bool HALF = (D % 8) != 0;   // one trailing group of 4 divisions (64 bytes per code)
-    static constexpr int F_BYTES = PT_STRIDE * 128, H_BYTES = PT_STRIDE * 64;
-    static constexpr int ROWS = D * PT_STRIDE;   // 16-byte rows; row r of the table lives at byte 16 r
-    static constexpr int BYTES = ROWS * 16;
+struct VScanExtra {
+    const unsigned short *Gq;    // [queries of this chunk][ROWS]
+    const float4 *qpar;          // [queries of this chunk]
+    const float *pct;            // [P][ROWS]
+    const float4 *pcpar;         // [P]
 };
-// row r -> (division, code)
-template <int W>
-__device__ __forceinline__ void vrow_to_dc(int r, int &d, int &c) {
-    using L = VLayout<W>;
-    if (r < L::NF * PT_STRIDE * 8) {
-        const int g = r / (PT_STRIDE * 8), rr = r - g * (PT_STRIDE * 8);
-        c = rr >> 3;
-        d = g * 8 + (rr & 7);
-    } else {
-        const int rr = r - L::NF * PT_STRIDE * 8;
-        c = rr >> 2;
-        d = L::NF * 8 + (rr & 3);
-    }
-}
 
 template <int W>
-__global__ void __launch_bounds__(VWARPS * 32, W <= 3 ? 4 : 3) vscan_kernel(PScanParams p) {
+__global__ void __launch_bounds__(VWARPS * 32, W <= 3 ? 4 : 3) vscan_kernel(PScanParams p, VScanExtra x) {
     using L = VLayout<W>;
     constexpr int D = 4 * W;
     extern __shared__ __align__(16) unsigned char vsm[];
@@ -134,13 +261,11 @@ __global__ void __launch_bounds__(VWARPS * 32, W <= 3 ? 4 : 3) vscan_kernel(PSca
     __shared__ int bcnt[VJ];
     __shared__ unsigned bthr[VJ], bflag[VJ];
     __shared__ uint32_t bq[VJ], bgoff[VJ];
-    __shared__ __align__(16) float qm[D][VJ];   // lower bound m_jd of table row d of member j
     __shared__ __align__(16) float qinv[VJ];
     __shared__ float qdelta[VJ], qbase[VJ];
-    __shared__ __align__(16) unsigned short tinit[VJ];   // accumulator start values: 0x8000 - t_j per half word
+    __shared__ __align__(16) unsigned short tthr[VJ];    // thresholds in table units, two per word like the sums
     __shared__ unsigned s_next, s_act, s_warm, s_retry;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int C = p.C, DC = D * C;
     const unsigned nitems = *p.nitems;
     const uint32_t tb = (uint32_t)__cvta_generic_to_shared(T);
     const uint32_t phase = (uint32_t)lane & 7u;
@@ -155,11 +280,11 @@ __global__ void __launch_bounds__(VWARPS * 32, W <= 3 ? 4 : 3) vscan_kernel(PSca
     auto int_threshold = [&](int j) -> uint32_t {
         const unsigned th = bthr[j];
         if (th == 0u) return 0u;                       // inactive member: nothing is a candidate
-        if (th == 0xffffffffu) return 32768u;          // no threshold yet: everything is
-        const float x = (fkey_inv(th) - qbase[j]) * qinv[j];
-        if (!(x < 32766.0f)) return 32768u;
-        if (!(x > -2.0f)) return 1u;                   // (keeps the lane honest: S = 0 still gets the float check)
-        return (uint32_t)(int)ceilf(x) + 2u;
+        if (th == 0xffffffffu) return 65535u;          // no threshold yet: everything is (the sums stay below 65535)
+        const float xx = (fkey_inv(th) - qbase[j]) * qinv[j];
+        if (!(xx < 65532.0f)) return 65535u;
+        if (!(xx > -2.0f)) return 1u;                  // (keeps the lane honest: S = 0 still gets the float check)
+        return (uint32_t)(int)ceilf(xx) + 2u;
     };
 
     while (item < nitems) {
@@ -168,7 +293,7 @@ __global__ void __launch_bounds__(VWARPS * 32, W <= 3 ? 4 : 3) vscan_kernel(PSca
         const uint32_t *dsc = p.desc + (size_t)item * VDESC;
         const int part = (int)__ldg(dsc), v0 = (int)__ldg(dsc + 1), v1 = (int)__ldg(dsc + 2), members = (int)__ldg(dsc + 3);
         const unsigned char *lst = p.codes + p.part_start[part];
-        // ---- members: pair constant, quantisation of the 8 tables
+        // ---- members: pair constant, scale and base of the query's fixed-point table
         if (tid < VJ) {
             const int j = tid;
             const bool active = j < members;
@@ -176,46 +301,26 @@ __global__ void __launch_bounds__(VWARPS * 32, W <= 3 ? 4 : 3) vscan_kernel(PSca
             const uint32_t ql = pair / (uint32_t)p.nprobe;
             const size_t qg = p.q0 + ql;
             const float K = active ? __ldg(&p.Kq[qg * p.nprobe + (pair - ql * p.nprobe)]) : 0.0f;
-            float rsum = 0.0f, msum = 0.0f, mabs = 0.0f;
-            if (active) {
-                float2 g[D], c[D];
-#pragma unroll
-                for (int d = 0; d < D; ++d) {
-                    g[d] = __ldg(reinterpret_cast<const float2 *>(p.gmm) + (size_t)ql * D + d);
-                    c[d] = __ldg(reinterpret_cast<const float2 *>(p.pcmm) + (size_t)part * D + d);
-                }
-#pragma unroll
-                for (int d = 0; d < D; ++d) {
-                    const float m = g[d].x + c[d].x;
-                    qm[d][j] = m;
-                    rsum += (g[d].y - g[d].x) + (c[d].y - c[d].x);
-                    msum += m;
-                    mabs += fabsf(m);
-                }
-            } else {
-#pragma unroll
-                for (int d = 0; d < D; ++d) qm[d][j] = 0.0f;
-            }
-            // sum_d round(range_d / delta) <= (32767 - D) / 1.0002 + D / 2: the 15-bit sums cannot overflow
-            const float delta = fmaxf(rsum * (1.0002f / (float)(32767 - D)), 1e-30f);
-            const float inv = 1.0f / delta;
-            // NaN bounds (a non-finite G row), overflow, or tables so far from zero that the f32 entries do not
-            // resolve delta: the query goes to the exact pipeline and its entries are zero
-            const bool ok = active && fabsf(K) < 1e30f && rsum < 1e30f && mabs < 1e30f && (mabs + fabsf(K)) * 2.4e-7f <= delta;
+            const float4 qp = active ? __ldg(x.qpar + ql) : make_float4(1.0f, 0.0f, 0.0f, 0.0f);   // delta, sum m, sum |m|, sum range
+            const float4 pp = __ldg(x.pcpar + part);
+            const float delta = qp.x, msum = qp.y + pp.x, mabs = qp.z + pp.y, rsum = qp.w + pp.z;
+            // a NaN delta (non-finite table), overflow, or tables so far from zero that f32 does not resolve delta:
+            // the query goes to the exact pipeline and its entries are masked
+            const bool ok = active && delta == delta && fabsf(K) < 1e30f && mabs < 1e30f && (mabs + fabsf(K)) * 2.4e-7f <= delta;
             const unsigned thr0 = ok ? __ldcg(&p.thrg[qg]) : 0u;   // 0: nothing is a candidate
             if (active) {
-                // per entry |m + delta u - t| <= delta / 2 + the roundings of t - m and of the fma (a few ulp of the
-                // range); then base = K + sum m and the final fma
-                const float qerr = (float)D * delta * 0.51f + (float)(D + 8) * 5.9604645e-08f * (fabsf(K) + mabs + 2.0f * rsum);
+                // per entry |m + delta u - t| <= delta / 2 for each of the two rounded terms (+ a few ulp of the range);
+                // then base = K + sum m and the final fma
+                const float qerr = (float)D * delta * 1.02f + (float)(D + 8) * 5.9604645e-08f * (fabsf(K) + mabs + 2.0f * rsum);
                 if (ok && qerr < 1e30f) atomicMax(&p.eadd[qg], __float_as_uint(qerr));
                 else bflag[j] = 1u;
             }
             qdelta[j] = delta;
-            qinv[j] = ok ? inv : 0.0f;
+            qinv[j] = ok ? 1.0f / delta : 0.0f;
             qbase[j] = K + msum;
             bcnt[j] = 0;
             bq[j] = (uint32_t)qg;
-            bgoff[j] = (ok ? ql : 0u) * (uint32_t)DC;    // (a member that is not ok copies row 0 and is masked)
+            bgoff[j] = (ok ? ql : 0u) * (uint32_t)(L::ROWS / 2);   // in row pairs (a member that is not ok is masked)
             bthr[j] = thr0;
             const unsigned okm = __ballot_sync(0xffu, ok);
             const unsigned warm = __ballot_sync(0xffu, !ok || thr0 != 0xffffffffu);
@@ -226,7 +331,8 @@ __global__ void __launch_bounds__(VWARPS * 32, W <= 3 ? 4 : 3) vscan_kernel(PSca
             }
         }
         __syncthreads();
-        // ---- tables: thread r fills row r (+ 256 i): 8 coalesced 4-byte loads, one conflict-free 16-byte store
+        // ---- table: thread t assembles the rows 2t and 2t+1 (+ 512 i): 8 coalesced 4-byte loads (two entries of each
+        //      query's table) + 8 bytes of PC, two 16-byte stores
         {
             const unsigned act = s_act;
             // half-word masks of the members whose entries count
@@ -236,44 +342,45 @@ __global__ void __launch_bounds__(VWARPS * 32, W <= 3 ? 4 : 3) vscan_kernel(PSca
             const uint32_t k3 = ((act & 64u) ? 0xffffu : 0u) | ((act & 128u) ? 0xffff0000u : 0u);
             const float4 i0 = *reinterpret_cast<const float4 *>(&qinv[0]), i1 = *reinterpret_cast<const float4 *>(&qinv[4]);
             const float inv[VJ] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+            const uint32_t *gq2 = reinterpret_cast<const uint32_t *>(x.Gq);
             uint32_t go[VJ];
 #pragma unroll
             for (int j = 0; j < VJ; ++j) go[j] = bgoff[j];
-            const float *pcp = p.pc + (size_t)part * DC;
+            const float2 *pc2 = reinterpret_cast<const float2 *>(x.pct + (size_t)part * L::ROWS);
 #pragma unroll 2
-            for (int r = tid; r < L::ROWS; r += VWARPS * 32) {
-                int d, c;
-                vrow_to_dc<W>(r, d, c);
-                uint4 row = make_uint4(0u, 0u, 0u, 0u);
-                if (c < C) {
-                    const uint32_t e = (uint32_t)(d * C + c);
-                    const float pcv = __ldg(pcp + e);
-                    float g[VJ];
+            for (int t = tid; t < L::ROWS / 2; t += VWARPS * 32) {
+                const float2 pcv = __ldg(pc2 + t);
+                uint32_t g[VJ];
 #pragma unroll
-                    for (int j = 0; j < VJ; ++j) g[j] = __ldg(p.G + (go[j] + e));
-                    const float4 m0 = *reinterpret_cast<const float4 *>(&qm[d][0]), m1 = *reinterpret_cast<const float4 *>(&qm[d][4]);
-                    const float m[VJ] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-                    uint32_t u[VJ];
+                for (int j = 0; j < VJ; ++j) g[j] = __ldg(gq2 + (go[j] + (uint32_t)t));
+                uint32_t ua[VJ], ub[VJ];
 #pragma unroll
-                    for (int j = 0; j < VJ; ++j)   // (t - m) >= 0 exactly (rounded addition is monotone): the fma stays >= 2^23
-                        u[j] = __float_as_uint(fmaf((g[j] + pcv) - m[j], inv[j], VMAGIC));
-                    row.x = __byte_perm(u[0], u[1], 0x5410) & k0;
-                    row.y = __byte_perm(u[2], u[3], 0x5410) & k1;
-                    row.z = __byte_perm(u[4], u[5], 0x5410) & k2;
-                    row.w = __byte_perm(u[6], u[7], 0x5410) & k3;
+                for (int j = 0; j < VJ; ++j) {   // PC - min >= 0: the fma stays >= 2^23; inv = 0 for masked members
+                    ua[j] = __float_as_uint(fmaf(pcv.x, inv[j], VMAGIC));
+                    ub[j] = __float_as_uint(fmaf(pcv.y, inv[j], VMAGIC));
                 }
-                T[r] = row;
+                uint4 ra, rb;
+                ra.x = (__byte_perm(ua[0], ua[1], 0x5410) + __byte_perm(g[0], g[1], 0x5410)) & k0;
+                ra.y = (__byte_perm(ua[2], ua[3], 0x5410) + __byte_perm(g[2], g[3], 0x5410)) & k1;
+                ra.z = (__byte_perm(ua[4], ua[5], 0x5410) + __byte_perm(g[4], g[5], 0x5410)) & k2;
+                ra.w = (__byte_perm(ua[6], ua[7], 0x5410) + __byte_perm(g[6], g[7], 0x5410)) & k3;
+                rb.x = (__byte_perm(ub[0], ub[1], 0x5410) + __byte_perm(g[0], g[1], 0x7632)) & k0;
+                rb.y = (__byte_perm(ub[2], ub[3], 0x5410) + __byte_perm(g[2], g[3], 0x7632)) & k1;
+                rb.z = (__byte_perm(ub[4], ub[5], 0x5410) + __byte_perm(g[4], g[5], 0x7632)) & k2;
+                rb.w = (__byte_perm(ub[6], ub[7], 0x5410) + __byte_perm(g[6], g[7], 0x7632)) & k3;
+                T[2 * t] = ra;
+                T[2 * t + 1] = rb;
             }
         }
-        if (tid < VJ) tinit[tid] = (unsigned short)(0x8000u - int_threshold(tid));
+        if (tid < VJ) tthr[tid] = (unsigned short)int_threshold(tid);
         if (tid == 0) s_next = grabbed;
         __syncthreads();
         const unsigned next_item = s_next;
 
         // ---- rounds: [rs, re) is handled by all warps, 32 vectors per warp step.  Cold start (no threshold yet): a
         //      round never brings more than about ncap new entries per query (as many vectors as have been seen so
-        //      far).  With inherited thresholds the whole item is one round.  A buffer that overflows is cut back, the
-        //      round's entries are dropped and the round runs again with the tighter threshold.
+        //      far).  With inherited thresholds the whole item is one round.  When a buffer overflows, every buffer is
+        //      cut back and loses the round's entries, and the round runs again, shorter, with the tighter thresholds.
         int rs = v0, seen = 0, retries = 0;
         int rsize = s_warm ? min(v1 - v0, 4096) : 64;
         uint32_t cw[W], nw[W];
@@ -281,7 +388,7 @@ __global__ void __launch_bounds__(VWARPS * 32, W <= 3 ? 4 : 3) vscan_kernel(PSca
         load_code_words<W>(lst, min(cwb + lane, v1 - 1), cw);
         while (rs < v1) {
             const int re = min(v1, rs + rsize);
-            const uint4 iv = *reinterpret_cast<const uint4 *>(&tinit[0]);
+            const uint4 tv = *reinterpret_cast<const uint4 *>(&tthr[0]);
             for (int b = rs + 32 * warp; b < re; b += 32 * VWARPS) {
                 if (cwb != b) load_code_words<W>(lst, min(b + lane, v1 - 1), cw);   // (a short or repeated round)
                 // the warp's next step (in this round, or its first one of the next round) travels now
@@ -289,7 +396,7 @@ __global__ void __launch_bounds__(VWARPS * 32, W <= 3 ? 4 : 3) vscan_kernel(PSca
                 load_code_words<W>(lst, min(nb + lane, v1 - 1), nw);
                 cwb = nb;
                 const int v = b + lane;
-                uint32_t a0 = iv.x, a1 = iv.y, a2 = iv.z, a3 = iv.w;
+                uint32_t a0 = 0u, a1 = 0u, a2 = 0u, a3 = 0u;
 #pragma unroll
                 for (int g = 0; g < L::NF; ++g) {
                     const uint32_t lo = cw[2 * g], hi = cw[(2 * g + 1) < W ? 2 * g + 1 : 0];
@@ -302,26 +409,27 @@ __global__ void __launch_bounds__(VWARPS * 32, W <= 3 ? 4 : 3) vscan_kernel(PSca
                     }
                 }
                 if (L::HALF) {
-                    const uint32_t x = cw[W - 1];
+                    const uint32_t xw = cw[W - 1];
 #pragma unroll
                     for (int t = 0; t < 4; ++t) {
                         const uint32_t s = (phase + (uint32_t)t) & 3u;
-                        const uint32_t code = __byte_perm(x, 0u, s) & 0xffu;
+                        const uint32_t code = __byte_perm(xw, 0u, s) & 0xffu;
                         const uint4 e = lds_v4(tb + (uint32_t)(L::NF * L::F_BYTES) + code * 64u + s * 16u);
                         a0 += e.x, a1 += e.y, a2 += e.z, a3 += e.w;
                     }
                 }
-                const uint32_t below = ~(a0 & a1 & a2 & a3) & 0x80008000u;
+                // a half word of min(S, t) differs from t  <=>  that sum is below its threshold
+                const uint32_t below = ((__vminu2(a0, tv.x) ^ tv.x) | (__vminu2(a1, tv.y) ^ tv.y)) |
+                                       ((__vminu2(a2, tv.z) ^ tv.z) | (__vminu2(a3, tv.w) ^ tv.w));
                 if (below != 0u && v < re) {
-                    const uint32_t aw[4] = {a0, a1, a2, a3}, iw[4] = {iv.x, iv.y, iv.z, iv.w};
+                    const uint32_t aw[4] = {a0, a1, a2, a3}, tw[4] = {tv.x, tv.y, tv.z, tv.w};
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
-                            const uint32_t e = (aw[i] >> (16 * h)) & 0xffffu;
-                            if (!(e & 0x8000u)) {
+                            const uint32_t S = (aw[i] >> (16 * h)) & 0xffffu;
+                            if (S < ((tw[i] >> (16 * h)) & 0xffffu)) {
                                 const int j = 2 * i + h;
-                                const uint32_t S = e - ((iw[i] >> (16 * h)) & 0xffffu);
                                 const uint32_t key = fkey(fmaf(qdelta[j], (float)S, qbase[j]));
                                 if (key < bthr[j]) {
                                     const int slot = atomicAdd(&bcnt[j], 1);
@@ -338,17 +446,35 @@ __global__ void __launch_bounds__(VWARPS * 32, W <= 3 ? 4 : 3) vscan_kernel(PSca
                 for (int w = 0; w < W; ++w) cw[w] = nw[w];
             }
             __syncthreads();
-            // buffers that outgrew the list: keep the ncap smallest, tighten the threshold
+            // ---- round end: buffers that outgrew the list keep their ncap smallest entries, the thresholds tighten
             if (warp < members) {
                 const int j = warp;
                 const int n = bcnt[j];
                 if (n > VB) {
                     // overflow: the VB entries that made it are real candidates, so their ncap-th smallest bounds the
-                    // final one.  Keep what was there before the round (<= the new bound), run the round again.
-                    cut_to_smallest(bkeys + j * VB, bpos + j * VB, VB, p.ncap, &bthr[j], lane);
-                    const int nk = min(VB, p.ncap);
-                    const bool mine = lane < nk && bpos[j * VB + lane] < (uint32_t)rs;
-                    const uint32_t kk = lane < nk ? bkeys[j * VB + lane] : 0u, pp = lane < nk ? bpos[j * VB + lane] : 0u;
+                    // final one.  The round runs again (below) unless this keeps happening (more than VB equal keys).
+                    cut_to_smallest64(bkeys + j * VB, bpos + j * VB, VB, p.ncap, &bthr[j], lane);
+                    if (lane == 0) {
+                        bcnt[j] = min(VB, p.ncap);
+                        if (retries >= 10) bflag[j] = 2u;   // -> exact pipeline
+                        else s_retry = 1u;
+                    }
+                } else if (n > p.ncap) {
+                    const int kept = cut_to_smallest64(bkeys + j * VB, bpos + j * VB, n, p.ncap, &bthr[j], lane);
+                    if (lane == 0) bcnt[j] = kept;
+                }
+                __syncwarp();
+                if (lane == 0) tthr[j] = (unsigned short)int_threshold(j);
+            }
+            __syncthreads();
+            if (s_retry) {   // uniform
+                // every member drops the entries of this round (they come back) and admits keys EQUAL to its bound
+                // again: the bound may be one of the dropped entries
+                if (warp < members) {
+                    const int j = warp;
+                    const int n = min(bcnt[j], 32);       // <= ncap <= 32 after the cuts above
+                    const bool mine = lane < n && bpos[j * VB + lane] < (uint32_t)rs;
+                    const uint32_t kk = lane < n ? bkeys[j * VB + lane] : 0u, pp = lane < n ? bpos[j * VB + lane] : 0u;
                     const unsigned keep = __ballot_sync(0xffffffffu, mine);
                     __syncwarp();
                     if (mine) {
@@ -356,26 +482,17 @@ __global__ void __launch_bounds__(VWARPS * 32, W <= 3 ? 4 : 3) vscan_kernel(PSca
                         bkeys[j * VB + o] = kk;
                         bpos[j * VB + o] = pp;
                     }
+                    __syncwarp();
                     if (lane == 0) {
                         bcnt[j] = __popc(keep);
-                        // entries equal to the bound must come back in: "<" against bound + 1
-                        if (bthr[j] != 0xffffffffu) bthr[j] += 1u;
-                        if (retries >= 3) bflag[j] = 2u;   // (degenerate: more than VB equal keys) -> exact pipeline
-                        else s_retry = 1u;
+                        if (bthr[j] != 0xffffffffu && bthr[j] != 0u) bthr[j] += 1u;
+                        tthr[j] = (unsigned short)int_threshold(j);
                     }
-                } else if (n > p.ncap) {
-                    const int kept = cut_to_smallest(bkeys + j * VB, bpos + j * VB, n, p.ncap, &bthr[j], lane);
-                    if (lane == 0) bcnt[j] = kept;
                 }
-                __syncwarp();
-                if (lane == 0) tinit[j] = (unsigned short)(0x8000u - int_threshold(j));
-            }
-            __syncthreads();
-            if (s_retry) {           // uniform: read by everyone between the two barriers' release and the reset below
                 ++retries;
+                rsize = max(64, (rsize >> 3) & ~31);
                 __syncthreads();
                 if (tid == 0) s_retry = 0u;
-                // (a member that was flagged keeps its partial list; the query is handed to the exact pipeline)
                 continue;
             }
             retries = 0;

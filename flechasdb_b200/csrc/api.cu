@@ -182,6 +182,22 @@ int fdb_device_free(fdb_ctx *ctx, void *p) {
     return FDB_OK;
 }
 
+/* page-locks caller memory (a Rust Vec<f32>, a numpy array) so that host <-> device copies of it are asynchronous
+ * DMA transfers: fdb_index_query then overlaps the copy of a batch with answering it */
+int fdb_host_register(fdb_ctx *ctx, void *p, size_t bytes) {
+    ARG(ctx && p && bytes, "null argument");
+    FDB_TRY(ctx->use());
+    FDB_CUDA(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+    return FDB_OK;
+}
+
+int fdb_host_unregister(fdb_ctx *ctx, void *p) {
+    ARG(ctx && p, "null argument");
+    FDB_TRY(ctx->use());
+    FDB_CUDA(cudaHostUnregister(p));
+    return FDB_OK;
+}
+
 int fdb_device_upload(fdb_ctx *ctx, void *d_dst, const void *src, size_t bytes) {
     ARG(ctx && (bytes == 0 || (d_dst && src)), "null argument");
     FDB_TRY(ctx->use());

@@ -1014,12 +1014,23 @@ int fdb_index_query(fdb_index *ix, const float *queries, size_t nq, size_t k, si
     // the copy stream must not overwrite q_dev while an earlier call's kernels still read it
     FDB_CUDA(cudaEventRecord(ix->copy_events[nslices], st));
     FDB_CUDA(cudaStreamWaitEvent(ix->copy_stream, ix->copy_events[nslices], 0));
-    for (size_t i = 0; i < nslices; ++i) {
+    // Pinned (or registered: fdb_host_register) caller memory: every copy is queued up front, they travel while the
+    // earlier slices are answered.  Pageable memory: cudaMemcpyAsync stages through the driver and returns only when
+    // the slice has left the caller's buffer, so the slices are copied one by one, each right before its kernels are
+    // enqueued -- the host stages slice i + 1 while the GPU answers slice i.
+    cudaPointerAttributes attr;
+    bool pinned = cudaPointerGetAttributes(&attr, queries) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (getenv("FDB_QUERY_ASSUME_PAGEABLE")) pinned = false;
+    auto copy_slice = [&](size_t i) -> int {
         const size_t q0 = bounds[i], nc = bounds[i + 1] - q0;
         FDB_CUDA(cudaMemcpyAsync(ix->q_dev.p + q0 * ix->N, queries + q0 * ix->N, nc * ix->N * sizeof(float),
                                  cudaMemcpyHostToDevice, ix->copy_stream));
         FDB_CUDA(cudaEventRecord(ix->copy_events[i], ix->copy_stream));
-    }
+        return FDB_OK;
+    };
+    if (pinned)
+        for (size_t i = 0; i < nslices; ++i) FDB_TRY(copy_slice(i));
     const bool trace = getenv("FDB_QUERY_TRACE") != nullptr;
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t0 = trace ? now() : 0.0;
@@ -1028,6 +1039,7 @@ int fdb_index_query(fdb_index *ix, const float *queries, size_t nq, size_t k, si
     FDB_TRY(batch_begin(b));
     for (size_t i = 0; i < nslices; ++i) {
         const size_t q0 = bounds[i], nc = bounds[i + 1] - q0;
+        if (!pinned) FDB_TRY(copy_slice(i));
         FDB_TRY(batch_slice(b, ix->q_dev.p + q0 * ix->N, q0, nc, ix->out_p.p + q0 * k, ix->out_v.p + q0 * k,
                             ix->out_d.p + q0 * k, ix->out_c.p + q0, ix->copy_events[i]));
     }

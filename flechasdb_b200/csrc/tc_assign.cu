@@ -244,6 +244,24 @@ __global__ void __launch_bounds__(128) prep_centroids_kernel(const float *c, siz
     }
 }
 
+// shared memory plan: when both centroid pieces of a problem (all K chunks) fit beside two stages of row pieces they
+// stay resident -- the rows are the only operand that streams (the PQ shape: 128 KB of centroids, read once per
+// problem instead of once per 128-row tile)
+static inline void tc_smem_plan(size_t np, size_t bk, size_t m, int *stages, int *bres, size_t *smem) {
+    const size_t a2 = 2 * (size_t)BM * bk * 2, b2 = 2 * np * bk * 2, kchunks = m / bk;
+    const size_t budget = 200 * 1024;
+    const bool off = getenv("FDB_TC_NO_BRES") != nullptr;
+    if (!off && kchunks * b2 + 2 * a2 <= budget) {
+        *bres = 1;
+        *stages = (int)std::min<size_t>(4, (budget - kchunks * b2) / a2);
+        *smem = kchunks * b2 + (size_t)*stages * a2 + 1024;
+    } else {
+        *bres = 0;
+        *stages = (int)std::min<size_t>(4, budget / (a2 + b2));
+        *smem = (size_t)*stages * (a2 + b2) + 1024;
+    }
+}
+
 struct TcParams {
     size_t n, m, nb, k, col_off;
     size_t xcol_stride;         // operand columns of problem b start at col_off + b * xcol_stride
@@ -260,6 +278,7 @@ struct TcParams {
     int bk;                     // bf16 elements per K chunk: 64 (m % 64 == 0) or 16
     int row_tiles;              // ceil(n / 128)
     int stages;
+    int bres;                   // 1: the centroid pieces of a problem stay in shared memory (all K chunks), only the rows stream
     const float *h;             // [nb][np]
     const float *xn2;           // [nb][n]
     const unsigned *cmax2_bits; // [nb]
@@ -280,7 +299,7 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
                  TcParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    __shared__ __align__(8) uint64_t full_bar[4], empty_bar[4], tmem_full[2], tmem_empty[2];
+    __shared__ __align__(8) uint64_t full_bar[4], empty_bar[4], tmem_full[2], tmem_empty[2], b_full, b_free;
     __shared__ uint32_t tmem_base_s;
     __shared__ float rowmax_s[2][BM], rowsec_s[2][BM];
     __shared__ uint16_t rowarg_s[2][BM];
@@ -293,9 +312,13 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
     const int BKr = p.bk;                             // 64, or 16 when m is not a multiple of 64
     const uint32_t a_bytes = BM * BKr * 2;            // 16 KB per piece (bk = 64)
     const uint32_t b_bytes = (uint32_t)NP * BKr * 2;  // NP * 128 B per piece
-    const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
     const int S = p.stages;
     const int kchunks = (int)(p.m / BKr);
+    // B resident: [kchunks][c1 | c2] of the current problem at the front, then the stages hold the two row pieces only
+    const bool bres = p.bres != 0;
+    const uint32_t stage_bytes = bres ? 2 * a_bytes : 2 * a_bytes + 2 * b_bytes;
+    unsigned char *bsm = smem;
+    if (bres) smem += (size_t)kchunks * 2 * b_bytes;
     const int total_tiles = (int)p.nb * p.row_tiles;
     // contiguous tile ranges per CTA (a CTA mostly stays inside one problem: its centroids stay hot in L2)
     const int per_cta = (total_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -311,6 +334,8 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
             mbar_init(&tmem_full[s], 1);
             mbar_init(&tmem_empty[s], EPI_THREADS / 32);
         }
+        mbar_init(&b_full, 1);
+        mbar_init(&b_free, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (threadIdx.x < BM) cnt_s[threadIdx.x] = 0;
@@ -327,22 +352,35 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
+            int stage = 0, cur_b = -1;
+            uint32_t phase = 0, bphase = 0;
             for (int t = t_begin; t < t_end; ++t) {
                 const int b = t / p.row_tiles, rt = t - b * p.row_tiles;
                 if (p.active && !p.active[p.mode == 2 ? 0 : b]) continue;
                 const int row0 = rt * BM;
                 const int kcol0 = (int)(p.col_off + (size_t)b * p.xcol_stride);
                 const int crow0 = (int)((size_t)b * p.crow_stride);
+                if (bres && b != cur_b) {
+                    // the MMAs of the previous problem have retired (the issuer commits b_free when it moves on)
+                    mbar_wait(&b_free, bphase ^ 1);
+                    bphase ^= 1;
+                    mbar_expect_tx(&b_full, (uint32_t)kchunks * 2 * b_bytes);
+                    for (int kc = 0; kc < kchunks; ++kc) {
+                        tma_load_2d(bsm + (size_t)(2 * kc) * b_bytes, &map_c1, kc * BKr, crow0, &b_full);
+                        tma_load_2d(bsm + (size_t)(2 * kc + 1) * b_bytes, &map_c2, kc * BKr, crow0, &b_full);
+                    }
+                    cur_b = b;
+                }
                 for (int kc = 0; kc < kchunks; ++kc) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     unsigned char *st = smem + (size_t)stage * stage_bytes;
                     mbar_expect_tx(&full_bar[stage], stage_bytes);
                     tma_load_2d(st, &map_x1, kcol0 + kc * BKr, row0, &full_bar[stage]);
                     tma_load_2d(st + a_bytes, &map_x2, kcol0 + kc * BKr, row0, &full_bar[stage]);
-                    tma_load_2d(st + 2 * a_bytes, &map_c1, kc * BKr, crow0, &full_bar[stage]);
-                    tma_load_2d(st + 2 * a_bytes + b_bytes, &map_c2, kc * BKr, crow0, &full_bar[stage]);
+                    if (!bres) {
+                        tma_load_2d(st + 2 * a_bytes, &map_c1, kc * BKr, crow0, &full_bar[stage]);
+                        tma_load_2d(st + 2 * a_bytes + b_bytes, &map_c2, kc * BKr, crow0, &full_bar[stage]);
+                    }
                     if (++stage == S) {
                         stage = 0;
                         phase ^= 1;
@@ -357,11 +395,18 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
             // N>>3 at [17,23), M>>4 at [24,29)   (cute::UMMA::InstrDescriptor)
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NP >> 3) << 17) |
                                    ((uint32_t)(BM >> 4) << 24);
-            int stage = 0, as = 0;
-            uint32_t phase = 0, aphase = 0;
+            int stage = 0, as = 0, cur_b = -1;
+            uint32_t phase = 0, aphase = 0, bphase = 0;
             for (int t = t_begin; t < t_end; ++t) {
                 const int b = t / p.row_tiles;
                 if (p.active && !p.active[p.mode == 2 ? 0 : b]) continue;
+                if (bres && b != cur_b) {
+                    if (cur_b >= 0) umma_commit(&b_free);   // arrives when the previous problem's MMAs have retired
+                    mbar_wait(&b_full, bphase);
+                    bphase ^= 1;
+                    tc_fence_after();
+                    cur_b = b;
+                }
                 mbar_wait(&tmem_empty[as], aphase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * NP);
@@ -370,8 +415,9 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
                     const uint64_t a1 = make_smem_desc(sa, BKr), a2 = make_smem_desc(sa + a_bytes, BKr);
-                    const uint64_t b1 = make_smem_desc(sa + 2 * a_bytes, BKr);
-                    const uint64_t b2 = make_smem_desc(sa + 2 * a_bytes + b_bytes, BKr);
+                    const uint32_t sb = bres ? smem_u32(bsm + (size_t)(2 * kc) * b_bytes) : sa + 2 * a_bytes;
+                    const uint64_t b1 = make_smem_desc(sb, BKr);
+                    const uint64_t b2 = make_smem_desc(sb + b_bytes, BKr);
                     for (int ks = 0; ks < BKr / 16; ++ks) {
                         const uint64_t off = (uint64_t)(ks * 32 >> 4);  // 16 bf16 = 32 bytes along K
                         umma_bf16(d_tmem, a2 + off, b1 + off, idesc, (kc | ks) != 0);  // small terms first
@@ -988,8 +1034,8 @@ int tc_reassign(fdb_km *km, const int *d_active) {
     p.np = np;
     p.row_tiles = (int)((n + BM - 1) / BM);
     p.bk = bk;
-    const size_t stage_bytes = 2 * (size_t)BM * bk * 2 + 2 * (size_t)np * bk * 2;
-    p.stages = (int)std::min<size_t>(4, (200 * 1024) / stage_bytes);
+    size_t smem = 0;
+    tc_smem_plan((size_t)np, (size_t)bk, mp, &p.stages, &p.bres, &smem);
     p.h = tc->h.p;
     p.xn2 = tc->xn2.p;
     p.cmax2_bits = tc->cmax2.p;
@@ -1005,7 +1051,6 @@ int tc_reassign(fdb_km *km, const int *d_active) {
     p.work_cnt = tc->work_cnt.p;
     p.work_cap = (unsigned)(nb * n);
     p.stats = tc->stats.p;
-    const size_t smem = (size_t)p.stages * stage_bytes + 1024;
     FDB_CUDA(cudaFuncSetAttribute(tc_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int total_tiles = (int)pnb * p.row_tiles;
     const int grid = std::min(total_tiles, ctx->sm_count);
@@ -1121,10 +1166,9 @@ int tc_gemm_raw(fdb_ctx *ctx, const TcRows &rows, const TcCentroids &cent, size_
     p.row_tiles = (int)((rows.n + BM - 1) / BM);
     const int bk = cent.m % BK == 0 ? BK : 16;
     p.bk = bk;
-    const size_t stage_bytes = 2 * (size_t)BM * bk * 2 + 2 * (size_t)cent.np * bk * 2;
-    p.stages = (int)std::min<size_t>(4, (200 * 1024) / stage_bytes);
+    size_t smem = 0;
+    tc_smem_plan((size_t)cent.np, (size_t)bk, p.m, &p.stages, &p.bres, &smem);
     p.h = cent.h.p;
-    const size_t smem = (size_t)p.stages * stage_bytes + 1024;
     FDB_CUDA(cudaFuncSetAttribute(tc_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int total_tiles = (int)p.nb * p.row_tiles;
     if (total_tiles == 0) return FDB_OK;

@@ -42,6 +42,13 @@ class Context:
     def free(self, p):
         check(capi.lib().fdb_device_free(self.h, p))
 
+    def host_register(self, array):
+        """page-locks a numpy array in place (asynchronous copies from / to it); undo with host_unregister"""
+        check(capi.lib().fdb_host_register(self.h, array.ctypes.data_as(VP), array.nbytes))
+
+    def host_unregister(self, array):
+        check(capi.lib().fdb_host_unregister(self.h, array.ctypes.data_as(VP)))
+
     def upload(self, dptr, array):
         a = np.ascontiguousarray(array)
         check(capi.lib().fdb_device_upload(self.h, dptr, a.ctypes.data_as(VP), a.nbytes))

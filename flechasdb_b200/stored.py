@@ -353,6 +353,9 @@ def load_database(base, path):
         if data.size % D:
             raise Error("InvalidData", "encoded vectors of partition %d are not a multiple of %d" % (p, D))
         n_p = data.size // D
+        # a code indexes table[di * num_codes + code] (src/db/stored.rs:585): the reference panics past the table
+        if data.size and int(data.max()) >= C:
+            raise Error("InvalidData", "partition %d holds the code %d, num_codes is %d" % (p, int(data.max()), C))
         pid = np.zeros((n_p, 16), np.uint8)
         msgs = f.get(12, [])
         if len(msgs) != n_p:

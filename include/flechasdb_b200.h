@@ -302,6 +302,14 @@ int fdb_index_query_sharded(fdb_index *ix, fdb_comm *comm, const float *d_querie
 /* how many queries of the last fdb_index_query_sharded call were merged a second time (distance ties) */
 int fdb_index_last_sharded_ties(fdb_index *ix, uint32_t *ties);
 
+/* Host buffers.  The query / upload / download calls take any host pointer.  Page-locked memory (registered
+ * here, or allocated pinned by the caller) is copied by asynchronous DMA, so fdb_index_query overlaps the copy of
+ * a batch with answering it; pageable memory (a plain Vec<f32>) is staged by the driver slice by slice while the
+ * GPU answers the previous slice.  Registering costs about as much as one copy: worth it for buffers that are
+ * reused.  No reference analogue (the reference never leaves host memory). */
+int fdb_host_register(fdb_ctx *ctx, void *p, size_t bytes);
+int fdb_host_unregister(fdb_ctx *ctx, void *p);
+
 /* raw device buffers for benches that keep inputs resident */
 int fdb_device_alloc(fdb_ctx *ctx, size_t bytes, void **out);
 int fdb_device_free(fdb_ctx *ctx, void *p);

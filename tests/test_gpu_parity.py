@@ -729,21 +729,28 @@ def test_vector_lane_scan_packed_tables(eng, ctx, oracle, monkeypatch, N, P, D, 
     ix.close()
 
 
-def test_vector_lane_scan_equals_exact_pipeline_on_a_large_batch(eng, ctx, oracle, monkeypatch):
-    """4096 queries against the README shape and 2048 against long lists: equal to the exact pipeline bit for bit."""
+@pytest.mark.parametrize("N,P,D,Cn,M,k,nprobe,nq", [
+    (1536, 100, 12, 256, 50000, 10, 5, 4096),     # the README shape: 200 queries per list, inherited thresholds
+    (96, 256, 12, 256, 1500000, 10, 16, 2048),    # long lists (5 860 vectors), 128 queries per list
+    (96, 2048, 12, 256, 2000000, 10, 8, 1024),    # 4 queries per list: half-empty groups, mostly cold starts
+    (128, 64, 16, 256, 400000, 10, 4, 1024),      # D = 16: two full groups of divisions
+])
+def test_vector_lane_scan_equals_exact_pipeline_on_a_large_batch(eng, ctx, oracle, monkeypatch, N, P, D, Cn, M, k, nprobe, nq):
+    """Large batches (thresholds inherited between a query's lists, rounds that overflow and run again): equal to
+    the exact pipeline bit for bit."""
     monkeypatch.setenv("FDB_FILTER_SCAN", "vector")
-    for (N, P, D, Cn, M, k, nprobe, nq) in [(1536, 100, 12, 256, 50000, 10, 5, 4096), (96, 256, 12, 256, 1500000, 10, 16, 2048)]:
-        coarse, cbs, off, codes = random_index(oracle, N, P, D, Cn, M)
-        ix = eng.Index.create(ctx, coarse, cbs, off, codes.astype(np.uint8))
-        q = data(oracle, nq, N, SEED + 80)
-        got = ix.query(q, k, nprobe)
-        assert ix.last_stats()[0] >= 0.99 * nq, ix.last_stats()
-        monkeypatch.setenv("FDB_QUERY_EXACT", "1")
-        want = ix.query(q, k, nprobe)
-        monkeypatch.delenv("FDB_QUERY_EXACT")
-        for g, w in zip(got, want):
-            assert (g == w).all()
-        ix.close()
+    coarse, cbs, off, codes = random_index(oracle, N, P, D, Cn, M)
+    ix = eng.Index.create(ctx, coarse, cbs, off, codes.astype(np.uint8))
+    q = data(oracle, nq, N, SEED + 80)
+    got = ix.query(q, k, nprobe)
+    assert ix.last_stats()[0] >= 0.98 * nq, ix.last_stats()
+    monkeypatch.setenv("FDB_QUERY_EXACT", "1")
+    want = ix.query(q, k, nprobe)
+    monkeypatch.delenv("FDB_QUERY_EXACT")
+    for name, g, w in zip(("partition", "vector_index", "distance", "count"), got, want):
+        bad = np.nonzero((g != w).reshape(nq, -1).any(axis=1))[0]
+        assert len(bad) == 0, (name, len(bad), bad[:8], g[bad[:2]], w[bad[:2]])
+    ix.close()
 
 
 def test_forced_scan_mode_fails_loudly_when_the_shape_is_not_taken(eng, ctx, oracle, monkeypatch):
