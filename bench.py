@@ -643,28 +643,36 @@ def run_sharded_query(args, engine, sharded, ctx, comm, dist, rank, world, steps
     k = K
     outs = [ctx.alloc(NQ4 * k * 4) for _ in range(3)] + [ctx.alloc(NQ4 * 4)]
     rows = {}
-    for nprobe in NPROBES4:
-        ms = []
-        c0 = comm.collectives
-        for it in range(warmup + steps):
-            ctx.flush_l2()
-            comm.barrier()
-            ctx.timer_start()
-            ix.query_sharded(comm, d_q, NQ4, k, nprobe, *outs, mode=capi.QUERY_STORED)
-            t = comm.max_f64([ctx.timer_stop()])
-            if it >= warmup:
-                ms.append(float(t[0]))
-        st = ix.last_stats()
-        scanned = comm_sum(comm, float(st[3]))
-        m = float(np.mean(ms))
-        gbs = scanned * D4 / (m * 1e-3) / 1e9
-        rows["nprobe_%d" % nprobe] = {
-            "ms_per_batch": m, "queries_per_s": NQ4 / (m * 1e-3), "scanned_vectors_all_ranks": int(scanned),
-            "algorithmic_scan_GBps_all_ranks": gbs, "frac_of_hbm_per_gpu": gbs / world / hbm_peak,
-            "collectives_per_batch": (comm.collectives - c0) // (warmup + steps) - 1,   # minus the timing all-reduce
-            "tied_queries_remerged": ix.last_sharded_ties(),
-            "note": "whole call (probe + tables + scan + all-gather + merge), device-timed, max over ranks; the "
-                    "fraction divides the whole call, not the scan kernel, by the HBM peak"}
+    for sem, mode in (("build", capi.QUERY_BUILD), ("stored", capi.QUERY_STORED)):
+        for nprobe in NPROBES4:
+            ms, scan_ms = [], []
+            c0 = comm.collectives
+            for it in range(warmup + steps):
+                ctx.flush_l2()
+                comm.barrier()
+                ctx.timer_start()
+                ix.query_sharded(comm, d_q, NQ4, k, nprobe, *outs, mode=mode)
+                t = comm.max_f64([ctx.timer_stop()])
+                if it >= warmup:
+                    ms.append(float(t[0]))
+            ix.set_timing(True)      # one more batch with per-phase events (they add synchronisation: not timed above)
+            ix.query_sharded(comm, d_q, NQ4, k, nprobe, *outs, mode=mode)
+            scan_ms.append(float(ix.last_timing()[0][4]))
+            ix.set_timing(False)
+            st = ix.last_stats()
+            scanned = comm_sum(comm, float(st[3]))
+            m = float(np.mean(ms))
+            sm = float(comm.max_f64([float(np.mean(scan_ms))])[0])
+            gbs = scanned * D4 / (m * 1e-3) / 1e9
+            rows["%s_nprobe_%d" % (sem, nprobe)] = {
+                "semantic": sem + "::Database::query", "ms_per_batch": m, "queries_per_s": NQ4 / (m * 1e-3),
+                "scanned_vectors_all_ranks": int(scanned), "code_scan_ms_max_over_ranks": sm,
+                "code_scan_frac_of_hbm_per_gpu": (scanned * D4 / world / (sm * 1e-3) / 1e9 / hbm_peak) if sm > 0 else None,
+                "whole_call_frac_of_hbm_per_gpu": gbs / world / hbm_peak,
+                "collectives_per_batch": (comm.collectives - c0) // (warmup + steps) - 1,   # minus the timing all-reduce
+                "tied_queries_remerged": ix.last_sharded_ties(),
+                "note": "whole call = probe + tables + scan + all-gather + merge, device-timed, max over ranks; the coarse "
+                        "probe (16 384 centroids) is replicated on every rank"}
     # ---- parity: the first queries against the CPU oracle on the lists they probe
     from oracle import pyoracle as oracle
     ns, nprobe = 200, 8
@@ -904,6 +912,11 @@ def run_reference(args, rank, world):
 
 
 def main():
+    # stdout carries exactly ONE line (the JSON): libraries that chat on fd 1 (NCCL's version banner under
+    # NCCL_DEBUG=VERSION) are pointed at stderr for the whole run
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

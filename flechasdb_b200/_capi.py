@@ -93,6 +93,10 @@ SIGNATURES = {
     "fdb_index_last_probes_device": (C.c_int, [VP, SZ, SZ, VP]),
     "fdb_merge_topk_device": (C.c_int, [VP, C.c_int, SZ, SZ, SZ, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP]),
     "fdb_index_create": (C.c_int, [VP, SZ, SZ, SZ, SZ, F32P, F32P, U64P, U8P, C.POINTER(VP)]),
+    "fdb_index_create_lazy": (C.c_int, [VP, SZ, SZ, SZ, SZ, F32P, F32P, C.POINTER(VP)]),
+    "fdb_index_set_partition": (C.c_int, [VP, SZ, U8P, SZ]),
+    "fdb_index_partition_loaded": (C.c_int, [VP, SZ]),
+    "fdb_index_missing_partitions": (C.c_int, [VP, F32P, SZ, SZ, C.c_int, U32P, SZ, C.POINTER(SZ)]),
     "fdb_index_from_build": (C.c_int, [VP, VP, VP, C.POINTER(VP)]),
     "fdb_index_get_layout": (C.c_int, [VP, U64P, U32P, U8P]),
     "fdb_index_num_vectors": (SZ, [VP]),

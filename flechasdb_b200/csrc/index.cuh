@@ -19,6 +19,12 @@ struct fdb_index {
     fdb::DevBuf<uint32_t> order;       // [M] global vector index at each partition-major position
     std::vector<uint32_t> h_off;
     std::vector<uint64_t> h_cstart;
+    // lazily loaded partitions (fdb_index_create_lazy / fdb_index_set_partition): the code lists arrive one by one
+    // and are appended to `codes`; the offsets are rebuilt before the next query
+    bool lazy = false, layout_dirty = false;
+    std::vector<uint8_t> loaded;       // [P]
+    std::vector<uint32_t> sizes;       // [P] vectors per partition (0 while not loaded)
+    size_t codes_used = 0;             // bytes of `codes` in use
     // scratch
     fdb::DevBuf<float> q_dev, dist, loc, tables, part_d, out_d, probe_d;
     fdb::DevBuf<uint32_t> probes, part_v, part_cnt, out_p, out_v, out_c;

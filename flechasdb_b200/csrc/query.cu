@@ -512,6 +512,73 @@ int fdb_index_create(fdb_ctx *ctx, size_t N, size_t P, size_t D, size_t C, const
     return FDB_OK;
 }
 
+/* stored::Database with lazily loaded partitions (src/db/stored.rs:269-293): the index starts with the partition
+ * centroids and the codebooks; a partition's code list is uploaded when the host first needs it. */
+int fdb_index_create_lazy(fdb_ctx *ctx, size_t N, size_t P, size_t D, size_t C, const float *coarse,
+                          const float *codebooks, fdb_index **out) {
+    ARG(coarse && codebooks && out, "null argument");
+    *out = nullptr;
+    fdb_index *raw = nullptr;
+    FDB_TRY(index_alloc(ctx, N, P, D, C, &raw));
+    std::unique_ptr<fdb_index> ix(raw);
+    FDB_TRY(index_layout(ix.get(), std::vector<uint32_t>(P + 1, 0u)));
+    ix->lazy = true;
+    ix->loaded.assign(P, 0);
+    ix->sizes.assign(P, 0u);
+    ix->codes_used = 0;
+    cudaStream_t st = ctx->stream;
+    FDB_CUDA(cudaMemcpyAsync(ix->coarse.p, coarse, P * N * sizeof(float), cudaMemcpyHostToDevice, st));
+    FDB_CUDA(cudaMemcpyAsync(ix->codebooks.p, codebooks, D * C * ix->s * sizeof(float), cudaMemcpyHostToDevice, st));
+    FDB_CUDA(cudaStreamSynchronize(st));
+    FDB_TRY(filter_prepare(ix.get()));
+    *out = ix.release();
+    return FDB_OK;
+}
+
+/* Partition p = n vectors of D codes each (u8, ascending vector index: the order of the stored Partition message,
+ * src/db/stored.rs:800-880).  May be called again for the same partition (the new list replaces the old one). */
+int fdb_index_set_partition(fdb_index *ix, size_t p, const uint8_t *codes, size_t n) {
+    ARG(ix && (codes || n == 0), "null argument");
+    ARG(ix->lazy, "the index was not created with fdb_index_create_lazy");
+    ARG(p < ix->P, "partition %zu out of range", p);
+    ARG(n < (1ull << 32), "partition too large");
+    fdb_ctx *ctx = ix->ctx;
+    FDB_TRY(ctx->use());
+    cudaStream_t st = ctx->stream;
+    for (size_t i = 0; i < n * ix->D && ix->C < 256; ++i)
+        if (codes[i] >= ix->C) {
+            set_error("partition %zu holds the code %u, num_codes is %zu", p, (unsigned)codes[i], ix->C);
+            return FDB_ERR_INVALID_DATA;
+        }
+    const size_t bytes = (n * ix->D + 15) & ~(size_t)15;
+    if (ix->codes_used + bytes + 16 > ix->codes.n) {
+        // grow the arena (the lists in use move with it)
+        const size_t cap = std::max<size_t>(2 * ix->codes.n, ix->codes_used + bytes + (1u << 20));
+        uint8_t *np = nullptr;
+        FDB_CUDA(cudaStreamSynchronize(st));
+        FDB_CUDA(cudaMalloc((void **)&np, cap));
+        FDB_CUDA(cudaMemsetAsync(np, 0, cap, st));
+        if (ix->codes_used) FDB_CUDA(cudaMemcpyAsync(np, ix->codes.p, ix->codes_used, cudaMemcpyDeviceToDevice, st));
+        FDB_CUDA(cudaStreamSynchronize(st));
+        if (ix->codes.p) cudaFree(ix->codes.p);
+        ix->codes.p = np;
+        ix->codes.n = cap;
+    }
+    if (n) FDB_CUDA(cudaMemcpyAsync(ix->codes.p + ix->codes_used, codes, n * ix->D, cudaMemcpyHostToDevice, st));
+    FDB_CUDA(cudaStreamSynchronize(st));   // the caller's buffer is free again
+    ix->h_cstart[p] = ix->codes_used;
+    ix->codes_used += bytes;
+    ix->sizes[p] = (uint32_t)n;
+    ix->loaded[p] = 1;
+    ix->layout_dirty = true;
+    return FDB_OK;
+}
+
+int fdb_index_partition_loaded(const fdb_index *ix, size_t p) {
+    if (!ix || p >= ix->P) return 0;
+    return ix->lazy ? (int)ix->loaded[p] : 1;
+}
+
 int fdb_index_from_build(fdb_ctx *ctx, const fdb_km *coarse, const fdb_km *pq, fdb_index **out) {
     ARG(ctx && coarse && pq && out, "null argument");
     *out = nullptr;
@@ -592,6 +659,28 @@ void fdb_index_destroy(fdb_index *ix) {
 
 namespace {
 
+// lazily loaded partitions: offsets and list positions follow the lists that have arrived
+int sync_layout(fdb_index *ix) {
+    if (!ix->layout_dirty) return FDB_OK;
+    uint64_t total = 0;
+    for (size_t p = 0; p < ix->P; ++p) {
+        ix->h_off[p] = (uint32_t)total;
+        total += ix->sizes[p];
+    }
+    if (total >= (1ull << 32)) {
+        set_error("more than 2^32 vectors");
+        return FDB_ERR_UNSUPPORTED;
+    }
+    ix->h_off[ix->P] = (uint32_t)total;
+    ix->M = total;
+    cudaStream_t st = ix->ctx->stream;
+    FDB_CUDA(cudaMemcpyAsync(ix->part_off.p, ix->h_off.data(), (ix->P + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    FDB_CUDA(cudaMemcpyAsync(ix->part_cstart.p, ix->h_cstart.data(), ix->P * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    FDB_CUDA(cudaStreamSynchronize(st));
+    ix->layout_dirty = false;
+    return FDB_OK;
+}
+
 int probe_device(fdb_index *ix, const float *d_q, size_t nq, size_t nprobe, int mode, EventLog *log) {
     fdb_ctx *ctx = ix->ctx;
     FDB_TRY(ix->dist.ensure(nq * ix->P));
@@ -624,6 +713,7 @@ int probe_device(fdb_index *ix, const float *d_q, size_t nq, size_t nprobe, int 
 
 int check_query_args(fdb_index *ix, size_t nq, size_t k, size_t nprobe, int mode) {
     ARG(ix, "ix is null");
+    FDB_TRY(sync_layout(ix));
     ARG(k > 0 && nprobe > 0, "k and nprobe must be non-zero (NonZeroUsize)");
     ARG(mode == FDB_QUERY_STORED || mode == FDB_QUERY_BUILD, "unknown mode %d", mode);
     /* src/db/stored.rs:403-409 */
@@ -951,9 +1041,38 @@ __global__ void pack_pairs_kernel(const float *pd, const uint32_t *pv, const uin
     }
     if (t < np) out[2 * np * k + t] = pc[t];
 }
-__global__ void compact_flags_kernel(const uint32_t *flags, size_t nq, uint32_t *list, uint32_t *count) {
-    const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q < nq && flags[q]) list[atomicAdd(count, 1u)] = (uint32_t)q;
+// the flagged queries in ascending order (every rank must build the SAME list: the per-pair lists of the second
+// pass travel by position); one CTA, 1024 queries per step
+__global__ void __launch_bounds__(1024) compact_flags_kernel(const uint32_t *flags, size_t nq, uint32_t *list, uint32_t *count) {
+    __shared__ uint32_t wexcl[32];
+    __shared__ uint32_t carry, chunk_total;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (size_t base = 0; base < nq; base += 1024) {
+        const size_t q = base + threadIdx.x;
+        const bool f = q < nq && flags[q] != 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, f);
+        if (lane == 0) wexcl[warp] = __popc(bal);
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t v = wexcl[lane];
+            uint32_t s = v;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, s, off);
+                if (lane >= off) s += o;
+            }
+            wexcl[lane] = s - v;
+            if (lane == 31) chunk_total = s;
+        }
+        __syncthreads();
+        if (f) list[carry + wexcl[warp] + __popc(bal & ((1u << lane) - 1u))] = (uint32_t)q;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += chunk_total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *count = carry;
 }
 }  // namespace
 }  // namespace fdb
@@ -1242,7 +1361,7 @@ int fdb_index_query_sharded(fdb_index *ix, fdb_comm *comm, const float *d_querie
         ctx->launches++;
     };
     merge(nq, have_probes ? ix->probes.p : nullptr, nullptr, mode == FDB_QUERY_STORED, ix->sh_flags.p);
-    compact_flags_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(ix->sh_flags.p, nq, ix->sh_list.p, ix->sh_flags.p + nq);
+    compact_flags_kernel<<<1, 1024, 0, st>>>(ix->sh_flags.p, nq, ix->sh_list.p, ix->sh_flags.p + nq);
     ctx->launches++;
     FDB_CHECK_LAUNCH();
     uint32_t nt = 0;
@@ -1297,5 +1416,28 @@ int fdb_index_last_sharded_ties(fdb_index *ix, uint32_t *ties) {
     return FDB_OK;
 }
 
-}  // extern "C"
+/* The distinct partitions the batch probes that have not been loaded yet (lazy index), in ascending order: the host
+ * loads them (fdb_index_set_partition) before it queries -- what get_partition does inside the reference's query
+ * (src/db/stored.rs:269-293,343-357).  out (may be NULL) receives up to cap of them, *n_missing their number. */
+int fdb_index_missing_partitions(fdb_index *ix, const float *queries, size_t nq, size_t nprobe, int mode, uint32_t *out,
+                                 size_t cap, size_t *n_missing) {
+    ARG(n_missing, "null argument");
+    *n_missing = 0;
+    FDB_TRY(check_query_args(ix, nq, 1, nprobe, mode));
+    if (!ix->lazy || nq == 0) return FDB_OK;
+    std::vector<uint32_t> probes(nq * nprobe);
+    FDB_TRY(fdb_index_probe(ix, queries, nq, nprobe, mode, probes.data(), nullptr));
+    std::vector<uint8_t> seen(ix->P, 0);
+    for (uint32_t p : probes)
+        if (p < ix->P && !ix->loaded[p]) seen[p] = 1;
+    size_t n = 0;
+    for (size_t p = 0; p < ix->P; ++p)
+        if (seen[p]) {
+            if (out && n < cap) out[n] = (uint32_t)p;
+            ++n;
+        }
+    *n_missing = n;
+    return FDB_OK;
+}
 
+}  // extern "C"

@@ -73,8 +73,13 @@ class DatabaseBuilder:
     engine.VectorSet already resident in HBM; it is consumed (the residues reuse its
     buffer, src/partitions.rs:17-22,120)."""
 
-    def __init__(self, vs, ctx=None, seeds=None, exact_sampler=False, profile=None):
+    def __init__(self, vs, ctx=None, seeds=None, exact_sampler=False, profile=None, live_events=False):
         self.vs = vs
+        # live_events: every k-means is driven round by round from the host (fdb_kmeans_update / _reassign), so each
+        # ClusterEvent fires when its phase starts / ends like the reference's (src/kmeans.rs:121-137) and callers that
+        # time the phases between events (src/main.rs:53-94) see real durations; the divisions then run one after the
+        # other like src/db/build.rs:110-118.  Default: whole loops on the device, events replayed afterwards.
+        self.live_events = live_events
         self.profile = profile   # optional dict: phase name -> seconds (adds a sync per phase)
         self.ctx = ctx
         self.seeds = seeds if seeds is not None else SeedSource()
@@ -107,10 +112,15 @@ class DatabaseBuilder:
     def build_with_events(self, event):
         own_ctx = self.ctx is None
         ctx = self.ctx if self.ctx is not None else Context(0)
+        self._made = []     # handles created by this build: closed again if it fails
         try:
             return self._build(ctx, own_ctx, event)
-        except capi.FdbError as e:
-            if e.code == capi.ERR_INVALID_ARGS:
+        except BaseException as e:
+            for h in reversed(self._made):
+                h.close()
+            if own_ctx:
+                ctx.close()
+            if isinstance(e, capi.FdbError) and e.code == capi.ERR_INVALID_ARGS:
                 raise _invalid_args(e.message) from e
             raise
 
@@ -123,11 +133,32 @@ class DatabaseBuilder:
             return t1
         return t0
 
+    def _cluster_live(self, km, first, u01, event):
+        """cluster_with_events (src/kmeans.rs:104-139), one problem, events fired as the phases happen"""
+        event(("ClusterEvent", ("StartingCentroidInitialization",)))
+        km.seed_run(first, u01, self.exact_sampler)
+        event(("ClusterEvent", ("FinishedCentroidInitialization",)))
+        grads, reas = [], 0
+        for r in range(capi.KMEANS_MAX_ROUNDS):
+            event(("ClusterEvent", ("StartingCentroidUpdate", r)))
+            g = float(km.update()[0])
+            grads.append(g)
+            event(("ClusterEvent", ("FinishedCentroidUpdate", r, g)))
+            if g < capi.KMEANS_EPSILON:
+                break
+            event(("ClusterEvent", ("StartingCentroidReassignment", r)))
+            km.reassign()
+            reas += 1
+            event(("ClusterEvent", ("FinishedCentroidReassignment", r)))
+        return grads, reas
+
     def _build(self, ctx, own_ctx, event):
         import time
         t = time.perf_counter()
         P, D, Cn = self.num_partitions, self.num_divisions, self.num_clusters
         vs = self.vs if isinstance(self.vs, VectorSet) else VectorSet.upload(ctx, self.vs)
+        if vs is not self.vs:
+            self._made.append(vs)
         M, N = len(vs), vs.vector_size
         # assigns IDs to vectors: Uuid::new_v4() per vector (src/db/build.rs:86-91)
         event(("StartingIdAssignment",))
@@ -139,11 +170,15 @@ class DatabaseBuilder:
         # partitions all the data (src/db/build.rs:93-98 -> src/partitions.rs:119-143)
         event(("StartingPartitioning",))
         ckm = KMeans(vs, P)
-        ckm.seed_run(self.seeds.first(M, 1), self.seeds.draws(1, P - 1), self.exact_sampler)
-        t = self._tick(ctx, "coarse_seeding", t)
-        grads, _, reas = ckm.run()
-        t = self._tick(ctx, "coarse_lloyd", t)
-        _replay_cluster_events(event, lambda e: ("ClusterEvent", e), grads[0], int(reas[0]))
+        self._made.append(ckm)
+        if self.live_events:
+            self._cluster_live(ckm, self.seeds.first(M, 1), self.seeds.draws(1, P - 1), event)
+        else:
+            ckm.seed_run(self.seeds.first(M, 1), self.seeds.draws(1, P - 1), self.exact_sampler)
+            t = self._tick(ctx, "coarse_seeding", t)
+            grads, _, reas = ckm.run()
+            t = self._tick(ctx, "coarse_lloyd", t)
+            _replay_cluster_events(event, lambda e: ("ClusterEvent", e), grads[0], int(reas[0]))
         vs.subtract_assigned(ckm)
         event(("FinishedPartitioning",))
         t = self._tick(ctx, "residues", t)
@@ -154,14 +189,34 @@ class DatabaseBuilder:
         event(("FinishedSubvectorDivision",))
         # builds codebooks for residues (src/db/build.rs:110-118): all divisions side by side
         pkm = KMeans(vs, Cn, col_off=0, dim=N // D, nb=D)
-        pkm.seed_run(self.seeds.first(M, D), self.seeds.draws(D, Cn - 1), self.exact_sampler)
-        t = self._tick(ctx, "pq_seeding", t)
-        grads, _, reas = pkm.run()
-        t = self._tick(ctx, "pq_lloyd", t)
-        for di in range(D):
-            event(("StartingQuantization", di))
-            _replay_cluster_events(event, lambda e: ("ClusterEvent", e), grads[di], int(reas[di]))
-            event(("FinishedQuantization", di))
+        self._made.append(pkm)
+        first_p, u_p = self.seeds.first(M, D), self.seeds.draws(D, Cn - 1)
+        if self.live_events:
+            # one division after the other, each on its own strided view; the finished codebooks and codes are
+            # then handed to the batched handle (fdb_kmeans_set_state) that the index is built from
+            s = N // D
+            cents = np.zeros((D, Cn, s), np.float32)
+            idx = np.zeros((D, M), np.uint32)
+            for di in range(D):
+                event(("StartingQuantization", di))
+                one = KMeans(vs, Cn, col_off=di * s, dim=s, nb=1)
+                try:
+                    self._cluster_live(one, first_p[di:di + 1], u_p[di:di + 1], event)
+                    c, i = one.get()
+                    cents[di], idx[di] = c[0], i[0]
+                finally:
+                    one.close()
+                event(("FinishedQuantization", di))
+            pkm.set_state(cents, idx)
+        else:
+            pkm.seed_run(first_p, u_p, self.exact_sampler)
+            t = self._tick(ctx, "pq_seeding", t)
+            grads, _, reas = pkm.run()
+            t = self._tick(ctx, "pq_lloyd", t)
+            for di in range(D):
+                event(("StartingQuantization", di))
+                _replay_cluster_events(event, lambda e: ("ClusterEvent", e), grads[di], int(reas[di]))
+                event(("FinishedQuantization", di))
         index = Index.from_build(ctx, ckm, pkm)
         t = self._tick(ctx, "events_and_index", t)
         return Database(ctx, own_ctx, vs, ckm, pkm, index, raw, P, D, Cn)
@@ -218,6 +273,9 @@ class Database:
         v = np.ascontiguousarray(v, np.float32).reshape(1, -1)
         m = capi.QUERY_BUILD if mode == "build" else capi.QUERY_STORED
         try:
+            if mode != "build":   # stored::Database loads its codebooks on the first query (src/db/stored.rs:343-360)
+                event(("StartingQueryInitialization",))
+                event(("FinishedQueryInitialization",))
             event(("StartingPartitionSelection",))
             probes, _ = self.index.probe(v, nprobe, m)
             event(("FinishedPartitionSelection",))

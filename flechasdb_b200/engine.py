@@ -309,6 +309,30 @@ class Index:
         return cls(ctx, h, N, P, D, Cn)
 
     @classmethod
+    def create_lazy(cls, ctx, coarse, codebooks):
+        """partition centroids + codebooks only; the code lists arrive with set_partition (src/db/stored.rs:269-293)"""
+        coarse, codebooks = as_f32(coarse), as_f32(codebooks)
+        P, N = coarse.shape
+        D, Cn, _ = codebooks.shape
+        h = VP()
+        check(capi.lib().fdb_index_create_lazy(ctx.h, N, P, D, Cn, f32p(coarse), f32p(codebooks), C.byref(h)))
+        return cls(ctx, h, N, P, D, Cn)
+
+    def set_partition(self, p, codes):
+        codes = np.ascontiguousarray(codes, np.uint8).reshape(-1, self.D)
+        check(capi.lib().fdb_index_set_partition(self.h, int(p), u8p(codes), codes.shape[0]))
+
+    def partition_loaded(self, p):
+        return bool(capi.lib().fdb_index_partition_loaded(self.h, int(p)))
+
+    def missing_partitions(self, q, nprobe, mode=capi.QUERY_STORED):
+        q = as_f32(q).reshape(-1, self.N)
+        out = np.zeros(self.P, np.uint32)
+        n = C.c_size_t()
+        check(capi.lib().fdb_index_missing_partitions(self.h, f32p(q), q.shape[0], nprobe, mode, u32p(out), self.P, C.byref(n)))
+        return out[:n.value].copy()
+
+    @classmethod
     def from_build(cls, ctx, coarse_km, pq_km):
         h = VP()
         check(capi.lib().fdb_index_from_build(ctx.h, coarse_km.h, pq_km.h, C.byref(h)))

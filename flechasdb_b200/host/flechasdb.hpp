@@ -160,6 +160,39 @@ inline std::unique_ptr<KMeansRun> cluster_device(const BlockVectorSet &vs, size_
     return run;
 }
 
+// The same loop driven step by step from the host (fdb_kmeans_update / fdb_kmeans_reassign per round), so that
+// every ClusterEvent fires WHEN its phase starts / ends, like the reference's (src/kmeans.rs:121-137): callers that
+// time the phases with Instant::now() between events (src/main.rs:53-94) see real durations.  One host
+// synchronisation per phase; cluster_device above runs the whole loop on the device and replays the events.
+inline std::unique_ptr<KMeansRun> cluster_device_live(const BlockVectorSet &vs, size_t col_off, size_t dim, size_t k,
+                                                      SeedSource &seeds, const ClusterEventHandler &ev) {
+    auto run = std::make_unique<KMeansRun>();
+    check(fdb_kmeans_begin(vs.handle(), col_off, dim, 1, k, &run->km));
+    ev({ClusterEvent::StartingCentroidInitialization});
+    const uint32_t first = seeds.first(vs.len());
+    std::vector<float> u(k > 0 ? k - 1 : 0);
+    for (float &x : u) x = seeds.draw();
+    check(fdb_kmeans_seed_run(run->km, &first, u.data(), /*exact=*/0, nullptr));
+    ev({ClusterEvent::FinishedCentroidInitialization});
+    run->gradients.assign(FDB_KMEANS_MAX_ROUNDS, 0.0f);
+    run->rounds.assign(1, 0);
+    run->reassigns.assign(1, 0);
+    for (size_t r = 0; r < FDB_KMEANS_MAX_ROUNDS; ++r) {
+        ev({ClusterEvent::StartingCentroidUpdate, r});
+        float g = 0.0f;
+        check(fdb_kmeans_update(run->km, nullptr, &g));
+        run->gradients[r] = g;
+        run->rounds[0] = (uint32_t)(r + 1);
+        ev({ClusterEvent::FinishedCentroidUpdate, r, g});
+        if (g < FDB_KMEANS_EPSILON) break;
+        ev({ClusterEvent::StartingCentroidReassignment, r});
+        check(fdb_kmeans_reassign(run->km, nullptr));
+        run->reassigns[0] = (uint32_t)(r + 1);
+        ev({ClusterEvent::FinishedCentroidReassignment, r});
+    }
+    return run;
+}
+
 inline Codebook cluster_with_events(const BlockVectorSet &vs, size_t k, SeedSource &seeds,
                                     const ClusterEventHandler &ev = [](const ClusterEvent &) {}) {
     if (k == 0) throw Error(Error::InvalidArgs, "k must be non-zero");
@@ -241,6 +274,11 @@ class Database {
         check(fdb_index_query(index_, queries, nq, k, nprobe, mode, part, vidx, dist, count));
     }
     fdb_index *index() const { return index_; }
+    // partition centroids [P][N] and codebooks [D][C][N/D] (what serialize_database writes)
+    void quantisers(float *coarse, float *codebooks) const {
+        check(fdb_kmeans_get(coarse_->km, coarse, nullptr));
+        check(fdb_kmeans_get(pq_->km, codebooks, nullptr));
+    }
     ~Database() {
         fdb_index_destroy(index_);
         pq_.reset();

@@ -373,27 +373,121 @@ def load_database(base, path):
     return StoredArrays(N, P, D, C, coarse.reshape(P, N), cbs, np.array(offsets, np.uint64), codes_pm, ids16)
 
 
-class StoredDatabase:
-    """stored::Database<f32, LocalFileSystem> resident on the GPU (src/db/stored.rs:41-57,315-389)."""
+def load_header(base, path):
+    """load_database proper (src/db/stored.rs:659-727): the header, the partition centroids and the codebooks; the
+    partitions stay on disk.  Returns (N, P, D, C, coarse [P][N], codebooks [D][C][s], partition_ids)."""
+    hdr = parse(_open(base, path, True))
 
-    def __init__(self, ctx, arrays):
+    def u(field):
+        v = hdr.get(field)
+        return int(v[0][1]) if v else 0
+
+    def strs(field):
+        return [v.decode() for _, v in hdr.get(field, [])]
+
+    N, P, D, C = u(1), u(2), u(3), u(4)
+    for name, v in (("vector_size", N), ("num_divisions", D), ("num_partitions", P), ("num_codes", C)):
+        if v == 0:
+            raise Error("InvalidData", "%s is zero" % name)
+    if N % D:
+        raise Error("InvalidData", "vector_size %d is not multiple of num_divisions %d" % (N, D))
+    partition_ids, codebook_ids = strs(10), strs(12)
+    if len(partition_ids) != P:
+        raise Error("InvalidData", "num_partitions %d and partition_ids.len() %d do not match" % (P, len(partition_ids)))
+    if len(codebook_ids) != D:
+        raise Error("InvalidData", "num_divisions %d and codebook_ids.len() %d do not match" % (D, len(codebook_ids)))
+    cen = _open(base, "partitions/%s.%s" % (strs(11)[0], EXT), False, verify=False)
+    coarse = _parse_floats(cen, 10)
+    if coarse.size != P * N:
+        raise Error("InvalidData", "partition centroids data length mismatch: expected %d, got %d" % (P, coarse.size // N))
+    s = N // D
+    cbs = np.zeros((D, C, s), np.float32)
+    for d in range(D):
+        data = _parse_floats(_open(base, "codebooks/%s.%s" % (codebook_ids[d], EXT), False), 10)
+        if data.size != C * s:
+            raise Error("InvalidData", "codebook %d has %d elements, expected %d" % (d, data.size, C * s))
+        cbs[d] = data.reshape(C, s)
+    return N, P, D, C, coarse.reshape(P, N), cbs, partition_ids
+
+
+def load_partition(base, partition_id, p, N, D, C):
+    """load_partition (src/db/stored.rs:800-880): codes [n][D] and vector ids [n][16] of one partition"""
+    f = parse(_open(base, "partitions/%s.%s" % (partition_id, EXT), True))
+    pv, pd = int(f.get(1, [(0, 0)])[0][1]), int(f.get(2, [(0, 0)])[0][1])
+    if pv != N or pd != D:
+        raise Error("InvalidData", "partition %d shape mismatch" % p)
+    enc = f.get(11)
+    data = _parse_uint32s(enc[0][1], 10) if enc else np.zeros(0, np.uint32)
+    if data.size % D:
+        raise Error("InvalidData", "encoded vectors of partition %d are not a multiple of %d" % (p, D))
+    if data.size and int(data.max()) >= C:
+        raise Error("InvalidData", "partition %d holds the code %d, num_codes is %d" % (p, int(data.max()), C))
+    n_p = data.size // D
+    msgs = f.get(12, [])
+    if len(msgs) != n_p:
+        raise Error("InvalidData", "partition %d: %d vector ids for %d vectors" % (p, len(msgs), n_p))
+    pid = np.zeros((n_p, 16), np.uint8)
+    for i, (_, m) in enumerate(msgs):
+        g = parse(m)
+        upper = struct.unpack("<Q", g[1][0][1])[0] if 1 in g else 0
+        lower = struct.unpack("<Q", g[2][0][1])[0] if 2 in g else 0
+        pid[i] = np.frombuffer(struct.pack(">QQ", upper, lower), np.uint8)
+    return data.reshape(n_p, D), pid
+
+
+class StoredDatabase:
+    """stored::Database<f32, LocalFileSystem> on the GPU (src/db/stored.rs:41-57,315-389).  Like the reference it
+    loads lazily: load_database reads the header, the partition centroids and the codebooks; a partition's file is
+    read (and its codes uploaded, fdb_index_set_partition) when a query first probes it (get_partition,
+    src/db/stored.rs:269-293)."""
+
+    def __init__(self, ctx, base, N, P, D, C, coarse, codebooks, partition_ids):
         from .engine import Index
-        self.arrays = arrays
-        if arrays.num_codes > 256:
+        if C > 256:
             raise Error("InvalidData", "num_codes > 256 is not supported by the u8 device layout")
-        self.index = Index.create(ctx, arrays.coarse, arrays.codebooks, arrays.offsets,
-                                  arrays.codes_pm.astype(np.uint8))
+        self.base, self.partition_ids = base, partition_ids
+        self.vector_size, self.num_partitions, self.num_divisions, self.num_codes = N, P, D, C
+        self.index = Index.create_lazy(ctx, coarse, codebooks)
+        self.ids = [None] * P
+        self.partition_loads = 0
 
     @classmethod
     def load_database(cls, ctx, base, path):
-        return cls(ctx, load_database(base, path))
+        return cls(ctx, base, *load_header(base, path))
 
-    def query(self, v, k, nprobe):
+    def _get_partition(self, p):
+        if self.ids[p] is None:
+            codes, ids = load_partition(self.base, self.partition_ids[p], p, self.vector_size, self.num_divisions,
+                                        self.num_codes)
+            self.index.set_partition(p, codes.astype(np.uint8))
+            self.ids[p] = ids
+            self.partition_loads += 1
+
+    def query(self, v, k, nprobe, event=lambda e: None):
+        """stored::Database::query_with_events (src/db/stored.rs:331-389), QueryEvent order included"""
         from . import _capi as capi
         from .db import QueryResult
-        p, vi, d, c = self.index.query(np.asarray(v, np.float32).reshape(1, -1), k, nprobe, capi.QUERY_STORED)
-        return [QueryResult(int(p[0, i]), self.arrays.vector_id(int(p[0, i]), int(vi[0, i])), int(vi[0, i]),
-                            float(d[0, i])) for i in range(int(c[0]))]
+        v = np.asarray(v, np.float32).reshape(1, -1)
+        event(("StartingPartitionSelection",))
+        probes, _ = self.index.probe(v, nprobe, capi.QUERY_STORED)
+        event(("FinishedPartitionSelection",))
+        for p in probes[0]:
+            event(("StartingPartitionQuery", int(p)))
+            self._get_partition(int(p))
+            event(("FinishedPartitionQuery", int(p)))
+        p, vi, d, c = self.index.query(v, k, nprobe, capi.QUERY_STORED)
+        event(("StartingResultSelection",))
+        out = [QueryResult(int(p[0, i]), uuid.UUID(bytes=bytes(self.ids[int(p[0, i])][int(vi[0, i])])), int(vi[0, i]),
+                           float(d[0, i])) for i in range(int(c[0]))]
+        event(("FinishedResultSelection",))
+        return out
+
+    def query_batch(self, queries, k, nprobe):
+        """batched form: loads whatever the batch probes, then one device batch"""
+        from . import _capi as capi
+        for p in self.index.missing_partitions(queries, nprobe, capi.QUERY_STORED):
+            self._get_partition(int(p))
+        return self.index.query(queries, k, nprobe, capi.QUERY_STORED)
 
     def close(self):
         self.index.close()

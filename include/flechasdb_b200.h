@@ -189,6 +189,18 @@ int fdb_kmeans_sharded_loop_end(fdb_km *km, float *gradients, uint32_t *rounds, 
 int fdb_index_create(fdb_ctx *ctx, size_t N, size_t P, size_t D, size_t C, const float *coarse,
                      const float *codebooks, const uint64_t *offsets, const uint8_t *codes,
                      fdb_index **out);
+/* stored::Database loads its partitions lazily (get_partition, src/db/stored.rs:269-293): create_lazy uploads the
+ * partition centroids and the codebooks only (what load_database reads, src/db/stored.rs:659-798); a partition's
+ * code list ([n][D] u8, ascending vector index) is uploaded by set_partition when the host first needs it -- a
+ * partition that has not arrived is an empty list to the kernels.  missing_partitions runs the probe selection of a
+ * batch and returns the distinct probed partitions that have not been loaded (ascending; out may be NULL, up to
+ * cap are written, *n_missing is their number): the host loads them, then queries. */
+int fdb_index_create_lazy(fdb_ctx *ctx, size_t N, size_t P, size_t D, size_t C, const float *coarse,
+                          const float *codebooks, fdb_index **out);
+int fdb_index_set_partition(fdb_index *ix, size_t p, const uint8_t *codes, size_t n);
+int fdb_index_partition_loaded(const fdb_index *ix, size_t p);
+int fdb_index_missing_partitions(fdb_index *ix, const float *queries, size_t nq, size_t nprobe, int mode,
+                                 uint32_t *out, size_t cap, size_t *n_missing);
 /* Device-side constructor straight from a finished build (no host round trip):
  * coarse = nb=1 problem with k=P, pq = nb=D problem with k=C over the residues.
  * order_out (may be NULL) receives [M] the global vector index stored at each

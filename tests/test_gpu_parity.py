@@ -1116,5 +1116,86 @@ def test_database_builder_events_serialize_and_stored_query(eng, ctx, oracle, tm
         b = sdb.query(q[qi], 7, 3)
         assert [(r.partition_index, r.vector_index, r.squared_distance, r.vector_id) for r in a] == \
                [(r.partition_index, r.vector_index, r.squared_distance, r.vector_id) for r in b]
+    # lazily: load_database read no partition file, the five queries loaded only what they probed
+    assert 0 < sdb.partition_loads <= 8 and sdb.partition_loads == sum(i is not None for i in sdb.ids)
+    qe = []
+    sdb.query(q[0], 7, 3, qe.append)
+    assert [e[0] for e in qe][:2] == ["StartingPartitionSelection", "FinishedPartitionSelection"]
+    # batched form: loads what the batch probes, answers like the in-memory index
+    qb = data(oracle, 64, N, SEED + 9)
+    got = sdb.query_batch(qb, 7, 3)
+    want = db.query_batch(qb, 7, 3, mode="stored")
+    for g, w in zip(got, want):
+        assert (g == w).all()
     sdb.close()
     db.index.close(); db.pkm.close(); db.ckm.close(); db.vs.close()
+
+
+def test_live_cluster_events_give_the_same_database(eng, ctx, oracle):
+    """live_events=True drives every k-means round by round from the host (events fire when the phases happen, the
+    divisions run one after the other like src/db/build.rs:110-118): same quantisers, same codes, same event order
+    as the device-side loops with replayed events."""
+    from flechasdb_b200.db import DatabaseBuilder, SeedSource
+    M, N = 4000, 48
+    x = data(oracle, M, N)
+    ev_a, ev_b = [], []
+    a = DatabaseBuilder(x.copy(), ctx=ctx, seeds=SeedSource(5)).with_partitions(6).with_divisions(3).with_clusters(16) \
+        .build_with_events(ev_a.append)
+    b = DatabaseBuilder(x.copy(), ctx=ctx, seeds=SeedSource(5), live_events=True).with_partitions(6).with_divisions(3) \
+        .with_clusters(16).build_with_events(ev_b.append)
+    assert ev_a == ev_b
+    for ka, kb in ((a.ckm, b.ckm), (a.pkm, b.pkm)):
+        ca, ia = ka.get()
+        cb, ib = kb.get()
+        assert (ca == cb).all() and (ia == ib).all()
+    q = data(oracle, 8, N, SEED + 3)
+    for g, w in zip(a.query_batch(q, 5, 3), b.query_batch(q, 5, 3)):
+        assert (g == w).all()
+    for db in (a, b):
+        db.index.close(); db.pkm.close(); db.ckm.close(); db.vs.close()
+
+
+def test_cpp_host_mirror_serialize_load_lazily_and_query():
+    """flechasdb_b200/host: build -> serialize_database -> load_database -> stored query in C++ (protobuf, zlib,
+    SHA-256 names written natively; partitions uploaded on their first probe), then the same files through the Python
+    mirror."""
+    import subprocess
+    import tempfile
+    from flechasdb_b200.host import build as hb
+    from flechasdb_b200 import stored
+    hb.build()
+    with tempfile.TemporaryDirectory() as d:
+        out = subprocess.run([hb.EXE_STORED, d], capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0 and "STORED_OK" in out.stdout, out.stdout[-1000:] + out.stderr[-2000:]
+        header = out.stdout.split("header=")[1].split()[0]
+        arrays = stored.load_database(d, header + ".binpb")   # the C++ writer's files verify and parse in Python
+        assert arrays.num_partitions == 16 and arrays.num_divisions == 4 and int(arrays.offsets[-1]) == 6000
+    out = subprocess.run([hb.EXE, "20000", "64", "4", "16", "32"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "built database in" in out.stdout and "vector_index=" in out.stdout, out.stderr[-2000:]
+
+
+def test_codes_beyond_num_codes_are_refused(eng, ctx, oracle):
+    """a code >= C would index past the ADC tables; the reference panics on such a file"""
+    from flechasdb_b200 import _capi as capi
+    coarse, cbs, off, codes = random_index(oracle, 32, 4, 4, 17, 400)
+    bad = codes.astype(np.uint8)
+    bad[77, 2] = 17
+    with pytest.raises(capi.FdbError) as e:
+        eng.Index.create(ctx, coarse, cbs, off, bad)
+    assert e.value.code == capi.ERR_INVALID_DATA
+    ix = eng.Index.create_lazy(ctx, coarse, cbs)
+    with pytest.raises(capi.FdbError) as e:
+        ix.set_partition(1, bad[int(off[1]):int(off[2])] if 77 >= off[1] and 77 < off[2] else bad[77:78])
+    assert e.value.code == capi.ERR_INVALID_DATA
+    ix.close()
+
+
+def test_query_with_the_largest_k(eng, ctx, oracle):
+    """k = 1024 needs more than 48 KB of shared memory in the final merge"""
+    coarse, cbs, off, codes = random_index(oracle, 32, 6, 2, 32, 9000)
+    ix = eng.Index.create(ctx, coarse, cbs, off, codes.astype(np.uint8))
+    oix = oracle.QueryIndex(coarse, cbs, off, codes)
+    q = data(oracle, 6, 32, SEED + 12)
+    for mode in (0, 1):
+        _check_query(ix, oix, q, 1024, 3, mode)
+    ix.close()

@@ -94,3 +94,70 @@ def test_integrity_and_validation_errors(tmp_path):
     with pytest.raises(stored.Error) as e:
         stored.load_database(base, hb + ".binpb")
     assert "partition_ids.len()" in str(e.value)
+
+
+# ---- the native (C++) writer / reader of flechasdb_b200/host/flechasdb_stored.hpp against this Python mirror -------
+def _fnv(arr):
+    h = 1469598103934665603
+    for b in np.ascontiguousarray(arr).view(np.uint8).reshape(-1).tolist():
+        h = ((h ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return "%016x" % h
+
+
+def _tool():
+    import subprocess
+    from flechasdb_b200.host import build as hb
+    hb.build()
+    return hb.EXE_TOOL, subprocess
+
+
+def test_cpp_writer_is_read_by_the_python_reader_and_back(tmp_path):
+    """stored_tool (C++ serialize_arrays / read_header / read_partition, no GPU needed) and stored.py read each
+    other's files: same protobuf wire bytes, zlib streams, SHA-256 names."""
+    tool, subprocess = _tool()
+    base = str(tmp_path / "cpp")
+    N, P, D, C, M = 16, 5, 4, 20, 200
+    out = subprocess.run([tool, "write", base, "5", str(N), str(P), str(D), str(C), str(M)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    h = out.stdout.strip()
+    got = stored.load_database(base, h + ".binpb")          # verifies every content-addressed name on the way
+    assert (got.vector_size, got.num_partitions, got.num_divisions, got.num_codes) == (N, P, D, C)
+    assert got.offsets[2] == got.offsets[1]                  # the tool leaves partition 1 empty
+    rd = subprocess.run([tool, "read", base, h + ".binpb"], capture_output=True, text=True)
+    assert rd.returncode == 0, rd.stderr
+    line = rd.stdout.strip()
+    assert "N=%d P=%d D=%d C=%d M=%d" % (N, P, D, C, int(got.offsets[-1])) in line
+    assert "coarse=" + _fnv(got.coarse) in line and "codebooks=" + _fnv(got.codebooks) in line
+    assert "codes=" + _fnv(got.codes_pm.astype(np.uint8)) in line and "ids=" + _fnv(got.ids16) in line
+    # the other direction: Python writes, the C++ reader parses the same arrays
+    coarse, cbs, off, codes, ids = _arrays(3, C=16)
+    base2 = str(tmp_path / "py")
+    h2 = stored.serialize_arrays(base2, coarse, cbs, off, codes, ids)
+    rd = subprocess.run([tool, "read", base2, h2 + ".binpb"], capture_output=True, text=True)
+    assert rd.returncode == 0, rd.stderr
+    line = rd.stdout.strip()
+    assert "coarse=" + _fnv(coarse) in line and "codebooks=" + _fnv(cbs) in line
+    assert "codes=" + _fnv(codes.astype(np.uint8)) in line and "ids=" + _fnv(ids) in line
+    # a flipped byte fails the native verify() too
+    cdir = os.path.join(base2, "codebooks")
+    victim = os.path.join(cdir, sorted(os.listdir(cdir))[0])
+    raw = bytearray(open(victim, "rb").read())
+    raw[-1] ^= 1
+    open(victim, "wb").write(bytes(raw))
+    rd = subprocess.run([tool, "read", base2, h2 + ".binpb"], capture_output=True, text=True)
+    assert rd.returncode == 1 and "VerificationFailure" in rd.stderr
+
+
+def test_a_code_beyond_num_codes_is_invalid_data(tmp_path):
+    """a stored partition whose codes do not fit num_codes must not reach the device tables"""
+    coarse, cbs, off, codes, ids = _arrays(2, C=16)
+    codes = codes.copy()
+    codes[3, 1] = 16                                          # == num_codes: one past the table
+    base = str(tmp_path / "bad")
+    h = stored.serialize_arrays(base, coarse, cbs, off, codes, ids)
+    with pytest.raises(stored.Error) as e:
+        stored.load_database(base, h + ".binpb")
+    assert e.value.kind == "InvalidData" and "num_codes" in str(e.value)
+    tool, subprocess = _tool()
+    rd = subprocess.run([tool, "read", base, h + ".binpb"], capture_output=True, text=True)
+    assert rd.returncode == 1 and "holds the code" in rd.stderr
