@@ -791,14 +791,19 @@ int fdb_kmeans_run(fdb_km *km, size_t max_rounds, float epsilon, float *gradient
     FDB_CUDA(cudaMemsetAsync(km->rounds.p, 0, nb * sizeof(uint32_t), ctx->stream));
     FDB_CUDA(cudaMemsetAsync(km->reassigns.p, 0, nb * sizeof(uint32_t), ctx->stream));
     FDB_CUDA(cudaMemsetAsync(km->grad_hist.p, 0, nb * km->max_rounds * sizeof(float), ctx->stream));
+    // The host looks at the convergence flags of round r - LAG while it enqueues round r: the stream never drains
+    // between rounds.  A converged problem clears its own flag on the device and is skipped by every later kernel,
+    // so the rounds enqueued past its convergence change nothing.
+    constexpr size_t LAG = 3, SLOTS = LAG + 1;
     int *h_active = (int *)ctx->h_pinned;
-    if (nb * sizeof(int) > ctx->h_pinned_bytes) {
+    if (SLOTS * nb * sizeof(int) > ctx->h_pinned_bytes / 2) {
         set_error("too many problems for the staging buffer");
         return FDB_ERR_UNSUPPORTED;
     }
-    // One round = update + reassignment + the read-back of the active flags: ~16 stream operations,
-    // several of them shorter than a launch.  Round 0 runs eagerly (it allocates), round 1 is
-    // captured into a CUDA graph, the later rounds replay it: one launch per round instead of 16.
+    cudaEvent_t ev[SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+    for (auto &e : ev) FDB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    // One round = update + reassignment: ~16 stream operations, several of them shorter than a launch.  Round 0
+    // runs eagerly (it allocates), round 1 is captured into a CUDA graph, the later rounds replay it.
     cudaGraphExec_t round_graph = nullptr;
     uint64_t graph_launches = 0;
     const bool use_graph = !getenv("FDB_NO_GRAPH") && !getenv("FDB_TC_STATS");
@@ -807,12 +812,21 @@ int fdb_kmeans_run(fdb_km *km, size_t max_rounds, float epsilon, float *gradient
         // so the reassignment that follows skips it (src/kmeans.rs:130-132)
         FDB_TRY(km_update(km, km->active.p, 1, epsilon, km->max_rounds));
         FDB_TRY(km_reassign(km, km->active.p));
-        FDB_CUDA(cudaMemcpyAsync(h_active, km->active.p, nb * sizeof(int), cudaMemcpyDeviceToHost,
-                                 ctx->stream));
         return FDB_OK;
     };
     int rc_loop = FDB_OK;
     for (size_t r = 0; r < max_rounds; ++r) {
+        if (r >= LAG) {
+            const size_t s = (r - LAG) % SLOTS;
+            if (cudaEventSynchronize(ev[s]) != cudaSuccess) {
+                set_error("cudaEventSynchronize failed: %s", cudaGetErrorString(cudaGetLastError()));
+                rc_loop = FDB_ERR_CUDA;
+                break;
+            }
+            bool any = false;
+            for (size_t b = 0; b < nb; ++b) any |= h_active[s * nb + b] != 0;
+            if (!any) break;
+        }
         if (round_graph) {
             if (cudaGraphLaunch(round_graph, ctx->stream) != cudaSuccess) {
                 set_error("cudaGraphLaunch failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -847,15 +861,15 @@ int fdb_kmeans_run(fdb_km *km, size_t max_rounds, float epsilon, float *gradient
         } else {
             if ((rc_loop = one_round()) != FDB_OK) break;
         }
-        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
-            set_error("cudaStreamSynchronize failed: %s", cudaGetErrorString(cudaGetLastError()));
+        const size_t s = r % SLOTS;
+        if (cudaMemcpyAsync(h_active + s * nb, km->active.p, nb * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+            cudaEventRecord(ev[s], ctx->stream) != cudaSuccess) {
+            set_error("flag read-back failed: %s", cudaGetErrorString(cudaGetLastError()));
             rc_loop = FDB_ERR_CUDA;
             break;
         }
-        bool any = false;
-        for (size_t b = 0; b < nb; ++b) any |= h_active[b] != 0;
-        if (!any) break;
     }
+    for (auto &e : ev) cudaEventDestroy(e);
     if (round_graph) cudaGraphExecDestroy(round_graph);
     FDB_TRY(rc_loop);
     std::vector<float> gh(nb * km->max_rounds);

@@ -143,15 +143,15 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const float *x, size_t 
                                                          size_t col_off, size_t m, size_t nb,
                                                          const float *mu, __nv_bfloat16 *x1,
                                                          __nv_bfloat16 *x2, float *xn2, size_t out_ld,
-                                                         size_t out_off, size_t out_m) {
+                                                         size_t out_off, size_t out_m, size_t out_bstride = 0) {
     const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= n * nb) return;
     const size_t row = warp / nb, b = warp - row * nb;
     const float *xr = x + row * ldx + col_off + b * m;
     const float *mr = mu + col_off + b * m;
-    __nv_bfloat16 *o1 = x1 + row * out_ld + out_off + b * out_m;
-    __nv_bfloat16 *o2 = x2 + row * out_ld + out_off + b * out_m;
+    __nv_bfloat16 *o1 = x1 + b * out_bstride + row * out_ld + out_off + b * out_m;
+    __nv_bfloat16 *o2 = x2 + b * out_bstride + row * out_ld + out_off + b * out_m;
     double acc = 0.0;
     // four elements per lane (one 16-byte load, two 8-byte stores) when everything is aligned
     const bool vec = m % 4 == 0 && ((uintptr_t)xr % 16 == 0) && ((uintptr_t)mr % 16 == 0) && ((uintptr_t)o1 % 8 == 0) &&
@@ -265,6 +265,7 @@ static inline void tc_smem_plan(size_t np, size_t bk, size_t m, int *stages, int
 struct TcParams {
     size_t n, m, nb, k, col_off;
     size_t xcol_stride;         // operand columns of problem b start at col_off + b * xcol_stride
+    size_t xrow_stride;         // ... and its rows at b * xrow_stride (problem-major pieces: every problem's rows contiguous)
     size_t crow_stride;         // centroid rows of problem b start at b * crow_stride
     int mode;                   // 0: assignment epilogue, 1: raw scores out = alpha * acc - (sub_h ? h : 0),
                                 // 2: the three largest scores of every (row, column tile) for tc_combine_kernel
@@ -357,7 +358,7 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
             for (int t = t_begin; t < t_end; ++t) {
                 const int b = t / p.row_tiles, rt = t - b * p.row_tiles;
                 if (p.active && !p.active[p.mode == 2 ? 0 : b]) continue;
-                const int row0 = rt * BM;
+                const int row0 = rt * BM + (int)((size_t)b * p.xrow_stride);
                 const int kcol0 = (int)(p.col_off + (size_t)b * p.xcol_stride);
                 const int crow0 = (int)((size_t)b * p.crow_stride);
                 if (bres && b != cur_b) {
@@ -949,14 +950,20 @@ int tc_reassign(fdb_km *km, const int *d_active) {
     const int np = tiled ? 256 : (int)((k + 63) / 64 * 64);
     // Piece layout: the rows' own layout when every problem's columns start on a 16-byte boundary and
     // m is a multiple of 16; else a compact copy, every problem padded with zeros to mp columns
-    const bool own_layout = m % 16 == 0 && ld % 8 == 0 && km->col_off % 8 == 0;
+    // Several problems side by side (the PQ divisions): problem-major pieces [nb][n][mp] -- a 128-row tile of a problem
+    // is one contiguous block of HBM (the rows' own layout hands TMA 128 rows x 256 bytes at a 3 KB stride: measured
+    // 1.3 TB/s instead of 4.9 on the PQ shape of the README database)
     const size_t mp = (m + 15) / 16 * 16;
-    const size_t ldp = own_layout ? ld : nb * mp, coff = own_layout ? km->col_off : 0;
+    const bool prob_major = !tiled && nb > 1 && !getenv("FDB_TC_ROW_MAJOR");
+    const bool rows_aligned = m % 16 == 0 && ld % 8 == 0 && km->col_off % 8 == 0;
+    const bool own_layout = !prob_major && rows_aligned;
+    const size_t ldp = prob_major ? mp : own_layout ? ld : nb * mp, coff = own_layout ? km->col_off : 0;
+    const size_t piece_elems = prob_major ? (nb * n + BM) * mp : n * ldp;
     const int bk = mp % BK == 0 ? BK : 16;
     cudaStream_t st = ctx->stream;
     if (tc->rows_version != km->vs->version || tc->np != np || tc->pnb != pnb) {
-        FDB_TRY(tc->x1.ensure(n * ldp));
-        FDB_TRY(tc->x2.ensure(n * ldp));
+        FDB_TRY(tc->x1.ensure(piece_elems));
+        FDB_TRY(tc->x2.ensure(piece_elems));
         FDB_TRY(tc->xn2.ensure(nb * n));
         FDB_TRY(tc->c1.ensure(pnb * pk * mp + 256 * mp));  // slack: the last problem's box reads past its rows
         FDB_TRY(tc->c2.ensure(pnb * pk * mp + 256 * mp));
@@ -974,8 +981,8 @@ int tc_reassign(fdb_km *km, const int *d_active) {
         FDB_CUDA(cudaMemsetAsync(tc->c1.p, 0, (pnb * pk * mp + 256 * mp) * 2, st));
         FDB_CUDA(cudaMemsetAsync(tc->c2.p, 0, (pnb * pk * mp + 256 * mp) * 2, st));
         if (!own_layout) {
-            FDB_CUDA(cudaMemsetAsync(tc->x1.p, 0, n * ldp * 2, st));
-            FDB_CUDA(cudaMemsetAsync(tc->x2.p, 0, n * ldp * 2, st));
+            FDB_CUDA(cudaMemsetAsync(tc->x1.p, 0, piece_elems * 2, st));
+            FDB_CUDA(cudaMemsetAsync(tc->x2.p, 0, piece_elems * 2, st));
         }
         // mu = column means of this problem's columns (any mu is valid; the mean minimises |x'|)
         const size_t ncols = nb * m;
@@ -992,11 +999,11 @@ int tc_reassign(fdb_km *km, const int *d_active) {
         const size_t warps = n * nb;
         split_rows_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(
             km->vs->d, n, ld, km->col_off, m, nb, tc->mu.p, tc->x1.p, tc->x2.p, tc->xn2.p, ldp, coff,
-            own_layout ? m : mp);
+            prob_major ? 0 : own_layout ? m : mp, prob_major ? n * mp : 0);
         ctx->launches++;
         FDB_CHECK_LAUNCH();
-        FDB_TRY(make_map(&tc->map_x1, tc->x1.p, ldp, n, BM, bk));
-        FDB_TRY(make_map(&tc->map_x2, tc->x2.p, ldp, n, BM, bk));
+        FDB_TRY(make_map(&tc->map_x1, tc->x1.p, ldp, prob_major ? nb * n + BM : n, BM, bk));
+        FDB_TRY(make_map(&tc->map_x2, tc->x2.p, ldp, prob_major ? nb * n + BM : n, BM, bk));
         FDB_TRY(make_map(&tc->map_c1, tc->c1.p, mp, pnb * pk + 256, (uint32_t)np, bk));
         FDB_TRY(make_map(&tc->map_c2, tc->c2.p, mp, pnb * pk + 256, (uint32_t)np, bk));
         tc->rows_version = km->vs->version;
@@ -1022,7 +1029,8 @@ int tc_reassign(fdb_km *km, const int *d_active) {
     p.nb = pnb;
     p.k = pk;
     p.col_off = coff;
-    p.xcol_stride = tiled ? 0 : (own_layout ? m : mp);
+    p.xcol_stride = (tiled || prob_major) ? 0 : (own_layout ? m : mp);
+    p.xrow_stride = prob_major ? n : 0;
     p.crow_stride = pk;
     p.mode = tiled ? 2 : 0;
     p.tile_v = tc->tile_v.p;
@@ -1062,7 +1070,7 @@ int tc_reassign(fdb_km *km, const int *d_active) {
         ctx->launches++;
         FDB_CHECK_LAUNCH();
     }
-    if (own_layout && (uintptr_t)km->vs->d % 16 == 0 && ld % 4 == 0)
+    if (rows_aligned && (uintptr_t)km->vs->d % 16 == 0 && ld % 4 == 0)
         recheck_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(km->vs->d, n, ld, km->col_off, m, k, km->centroids.p,
                                                           tc->work_count.p, p.work_cap, tc->work_rows.p,
                                                           tc->work_cand.p, tc->work_cnt.p, km->indices.p,
@@ -1155,6 +1163,7 @@ int tc_gemm_raw(fdb_ctx *ctx, const TcRows &rows, const TcCentroids &cent, size_
     p.k = cent.k;
     p.col_off = 0;
     p.xcol_stride = xcol_stride;
+    p.xrow_stride = 0;
     p.crow_stride = cent.k;
     p.mode = 1;
     p.out = out;
