@@ -38,6 +38,7 @@ namespace {
 constexpr int BM = 128;          // rows per tile (UMMA M)
 constexpr int BK = 64;           // bf16 elements per K chunk = one 128-byte swizzle row
 constexpr int CAP = 8;           // candidates kept per row before falling back to all k
+constexpr unsigned ALL_CAP = 1u << 18;   // rows decided over all k that get a CTA of their own (the others: a warp)
 constexpr int TC_THREADS = 384;
 constexpr int EPI_WARP0 = 4;
 constexpr int EPI_THREADS = 256;
@@ -292,6 +293,10 @@ struct TcParams {
     uint8_t *work_cnt;          // [cap] number of candidates (CAP+1 = overflow)
     unsigned work_cap;
     unsigned *stats;            // [2]: (unused), rows that overflowed CAP
+    unsigned long long *dbg;    // FDB_TC_DEBUG & 16: cycle counters of the assignment epilogue [8]
+    int debug;                  // FDB_TC_DEBUG (timing experiments, WRONG results): 1 = the producer skips the loads, 2 = the
+                                // assignment epilogue only releases the accumulator, 4 = ... only loads it, 8 = ... does its
+                                // arithmetic on registers and writes nothing, 16 = cycle counters (dbg)
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -304,9 +309,8 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
     __shared__ uint32_t tmem_base_s;
     __shared__ float rowmax_s[2][BM], rowsec_s[2][BM];
     __shared__ uint16_t rowarg_s[2][BM];
-    __shared__ __align__(16) float h_s[256];
-    __shared__ unsigned cnt_s[BM];
-    __shared__ uint16_t cand_s[BM][CAP];
+    __shared__ __align__(16) float h_s[2][256];          // mode 0: one copy per epilogue group
+    __shared__ uint16_t cand_s[2][BM][CAP];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int NP = p.np;
@@ -333,13 +337,12 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tmem_full[s], 1);
-            mbar_init(&tmem_empty[s], EPI_THREADS / 32);
+            mbar_init(&tmem_empty[s], p.mode == 0 ? 4 : EPI_THREADS / 32);   // mode 0: a stage belongs to one group of 4 warps
         }
         mbar_init(&b_full, 1);
         mbar_init(&b_free, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (threadIdx.x < BM) cnt_s[threadIdx.x] = 0;
     if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
                      "r"(512));
@@ -375,6 +378,14 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
                 for (int kc = 0; kc < kchunks; ++kc) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     unsigned char *st = smem + (size_t)stage * stage_bytes;
+                    if ((p.debug & 1) && t >= t_begin + 2) {
+                        mbar_arrive(&full_bar[stage]);
+                        if (++stage == S) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                        continue;
+                    }
                     mbar_expect_tx(&full_bar[stage], stage_bytes);
                     tma_load_2d(st, &map_x1, kcol0 + kc * BKr, row0, &full_bar[stage]);
                     tma_load_2d(st + a_bytes, &map_x2, kcol0 + kc * BKr, row0, &full_bar[stage]);
@@ -438,8 +449,202 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
                 }
             }
         }
+    } else if (warp >= EPI_WARP0 && p.mode == 0) {
+        // ===== assignment epilogue: two groups of four warps, group g owns accumulator stage g (every other tile);
+        //       one thread per row over all NP columns -- the warps share nothing, so a tile costs no CTA barrier,
+        //       a warp that needs the (rare) second pass delays nobody, and while one group reduces tile t the other
+        //       reduces tile t + 1 =====
+        const int ew = warp - EPI_WARP0;
+        const int q = ew & 3, g = ew >> 2;
+        const int row = 32 * q + lane;
+        const int gt = threadIdx.x - (EPI_WARP0 + 4 * g) * 32;   // 0..127 inside the group
+        float *hg = h_s[g];
+        const float NEG_INF = -__int_as_float(0x7f800000);
+        int h_loaded = -1, seq = 0;
+        uint32_t aphase = 0;
+        unsigned tk_end = p.dbg ? (unsigned)clock() : 0u;
+        int b = t_begin / p.row_tiles, rt = t_begin - b * p.row_tiles - 1;
+        bool b_on = !p.active || (t_begin < t_end && p.active[b] != 0);
+        for (int t = t_begin; t < t_end; ++t) {
+            if (++rt == p.row_tiles) {
+                rt = 0;
+                ++b;
+                b_on = !p.active || p.active[b] != 0;
+            }
+            if (!b_on) continue;
+            if ((seq++ & 1) != g) continue;
+            const size_t grow = (size_t)rt * BM + row;
+            const bool valid = grow < p.n;
+            // h_j = |c'_j|^2/2 of this problem in the group's shared copy (reloaded when the problem changes)
+            if (b != h_loaded) {
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");  // nobody in the group still reads the old values
+                for (int j = gt; j < NP; j += 128) hg[j] = p.h ? p.h[(size_t)b * NP + j] : 0.0f;
+                h_loaded = b;
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+            }
+            // the row's band inputs travel while the tile is still being multiplied
+            float xn2 = valid ? __ldg(p.xn2 + (size_t)b * p.n + grow) : 0.0f;
+            float cmax2 = __uint_as_float(__ldg(p.cmax2_bits + b));
+            const unsigned tk0 = p.dbg ? (unsigned)clock() : 0u;
+            mbar_wait(&tmem_full[g], aphase);
+            aphase ^= 1;
+            tc_fence_after();
+            const unsigned tk1 = p.dbg ? (unsigned)clock() : 0u;
+            const uint32_t taddr = tmem_base + (uint32_t)(g * NP) + ((uint32_t)(32 * q) << 16);
+            if (p.debug & 2) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[g]);
+                continue;
+            }
+            if (p.debug & 4) {   // the TMEM loads alone
+                float va[32];
+                uint32_t x = 0;
+                for (int c0 = 0; c0 < NP; c0 += 32) {
+                    tmem_ld32_issue(taddr + c0, va);
+                    tmem_ld_wait();
+                    x ^= va_bits(va, 0) ^ va_bits(va, 31);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[g]);
+                if (x == 0x12345678u) p.indices[0] = x;
+                continue;
+            }
+            // pass 1 (software pipelined TMEM loads): the two largest s = acc - h and the argmax, as two independent
+            // chains (even / odd columns).  Measured with FDB_TC_DEBUG=16: ~4.4k cycles per 32 rows x 256 columns, of
+            // which ~1.3k are the shared-memory reads of h (they compete with the tensor pipe's operand fetches); four
+            // chains, or a block-of-four top-2 network with fewer ALU-pipe instructions, measured the same.
+            float m1a = NEG_INF, m2a = NEG_INF, m1b = NEG_INF, m2b = NEG_INF;
+            int ia = 0, ib = 1;
+            {
+                float va[32], vb[32];
+                const bool ld = !(p.debug & 8);
+                if (!ld) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) va[i] = vb[i] = (float)(lane + i);
+                }
+                if (ld) tmem_ld32_issue(taddr, va);
+                for (int c0 = 0; c0 < NP; c0 += 64) {   // NP is a multiple of 64
+                    tmem_ld_wait();
+                    if (ld) tmem_ld32_issue(taddr + c0 + 32, vb);
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) {
+                        const float s0 = __uint_as_float(va_bits(va, i)) - hg[c0 + i];
+                        const float s1 = __uint_as_float(va_bits(va, i + 1)) - hg[c0 + i + 1];
+                        m2a = fmaxf(m2a, fminf(s0, m1a));
+                        ia = s0 > m1a ? c0 + i : ia;
+                        m1a = fmaxf(m1a, s0);
+                        m2b = fmaxf(m2b, fminf(s1, m1b));
+                        ib = s1 > m1b ? c0 + i + 1 : ib;
+                        m1b = fmaxf(m1b, s1);
+                    }
+                    tmem_ld_wait();
+                    if (ld && c0 + 64 < NP) tmem_ld32_issue(taddr + c0 + 64, va);
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) {
+                        const float s0 = __uint_as_float(va_bits(vb, i)) - hg[c0 + 32 + i];
+                        const float s1 = __uint_as_float(va_bits(vb, i + 1)) - hg[c0 + 32 + i + 1];
+                        m2a = fmaxf(m2a, fminf(s0, m1a));
+                        ia = s0 > m1a ? c0 + 32 + i : ia;
+                        m1a = fmaxf(m1a, s0);
+                        m2b = fmaxf(m2b, fminf(s1, m1b));
+                        ib = s1 > m1b ? c0 + 32 + i + 1 : ib;
+                        m1b = fmaxf(m1b, s1);
+                    }
+                }
+            }
+            const float smax = fmaxf(m1a, m1b);
+            const float second = fmaxf(fminf(m1a, m1b), fmaxf(m2a, m2b));
+            const int imax = m1a > m1b ? ia : (m1b > m1a ? ib : min(ia, ib));
+            const unsigned tk2 = p.dbg ? (unsigned)clock() : 0u;
+            // band (see the header of this file).  (The empty asm pins the first use of the two loads here, after
+            // pass 1: otherwise the arithmetic that depends on them alone is hoisted above the wait for the
+            // accumulator and the warp sits on the load latency before it even starts waiting.)
+            asm volatile("" : "+f"(xn2), "+f"(cmax2));
+            const float E = p.gamma1 * sqrtf(xn2 * cmax2) * 1.0001f + 1.2e-7f * (0.5f * cmax2);
+            const float dmin = fmaxf(0.0f, xn2 - 2.0f * smax + 2.0f * E);
+            // rounding of the shift: |d(x',c') - d(x,c)| <= 2 sqrt(d) 2^-24 (|x'| + |c'|)
+            const float shift = 1.3e-7f * sqrtf(dmin) * (sqrtf(xn2) + sqrtf(cmax2));
+            const float band = 2.0f * (2.0f * E + 1.01f * p.eta * dmin + shift);
+            const float thresh = smax - band;
+            // a single column inside the band <=> the runner-up is below the threshold (the
+            // negation also catches NaN scores, which must go to the exact kernel)
+            bool single = valid && (second < thresh) && (smax > NEG_INF);
+            bool need2 = valid && !single;
+            if (p.debug & 8) single = need2 = (smax == 1.2345f);   // (timing experiment: nothing is written)
+            // pass 2 (rare, this warp only): the columns inside the band as one bit mask per 32 columns (three
+            // instructions per column, no branch), then the positions of the few set bits in ascending order
+            unsigned c = 0;
+            if (__any_sync(0xffffffffu, need2)) {
+                float v[32];
+                uint16_t *cs = cand_s[g][row];
+                tmem_ld32_issue(taddr, v);
+                for (int c0 = 0; c0 < NP; c0 += 32) {
+                    tmem_ld_wait();
+                    uint32_t hits = 0u;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float sv = __uint_as_float(va_bits(v, i)) - hg[c0 + i];
+                        hits |= sv >= thresh ? (1u << i) : 0u;
+                    }
+                    if (c0 + 32 < NP) tmem_ld32_issue(taddr + c0 + 32, v);
+                    if (!need2) hits = 0u;
+                    while (hits) {   // (a handful of bits on a handful of lanes)
+                        const int i = __ffs(hits) - 1;
+                        hits &= hits - 1u;
+                        if (c < CAP) cs[c] = (uint16_t)(c0 + i);
+                        ++c;
+                    }
+                }
+            }
+            // the accumulator stage is free again
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[g]);
+            const unsigned tk3 = p.dbg ? (unsigned)clock() : 0u;
+            if (p.dbg && lane == 0) {
+                atomicAdd(p.dbg + 5, (unsigned long long)(tk0 - tk_end));   // end of the previous tile -> ready to wait
+                atomicAdd(p.dbg + 0, (unsigned long long)(tk1 - tk0));   // waiting for the accumulator
+                atomicAdd(p.dbg + 1, (unsigned long long)(tk2 - tk1));   // pass 1
+                atomicAdd(p.dbg + 2, (unsigned long long)(tk3 - tk2));   // band + pass 2
+                atomicAdd(p.dbg + 3, 1ull);                               // warp-tiles
+                if (c) atomicAdd(p.dbg + 4, 1ull);
+            }
+            // rows with exactly one column inside the band are final; the others go to the
+            // re-check list (c < 2: non-finite scores, c > CAP: too many -> all k centroids)
+            const unsigned bal = __ballot_sync(0xffffffffu, need2);
+            if (single) p.indices[(size_t)b * p.n + grow] = (uint32_t)imax;
+            if (bal) {
+                unsigned base = 0;
+                if (lane == 0) base = atomicAdd(p.work_count, (unsigned)__popc(bal));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (need2) {
+                    const unsigned slot = base + __popc(bal & ((1u << lane) - 1u));
+                    if (slot < p.work_cap) {
+                        p.work_rows[slot] = (uint32_t)((size_t)b * p.n + grow);
+                        const unsigned cc = (c < 2 || c > CAP) ? CAP + 1 : c;
+                        p.work_cnt[slot] = (uint8_t)cc;
+                        uint16_t cv[CAP];
+#pragma unroll
+                        for (unsigned u = 0; u < CAP; ++u) cv[u] = u < c ? cand_s[g][row][u] : (uint16_t)0;
+                        uint4 pk;
+                        pk.x = (uint32_t)cv[0] | ((uint32_t)cv[1] << 16);
+                        pk.y = (uint32_t)cv[2] | ((uint32_t)cv[3] << 16);
+                        pk.z = (uint32_t)cv[4] | ((uint32_t)cv[5] << 16);
+                        pk.w = (uint32_t)cv[6] | ((uint32_t)cv[7] << 16);
+                        *reinterpret_cast<uint4 *>(p.work_cand + (size_t)slot * CAP) = pk;
+                        if (cc > CAP) atomicAdd(&p.stats[1], 1u);
+                    }
+                }
+            }
+            if (p.dbg) {
+                tk_end = (unsigned)clock();
+                if (lane == 0) atomicAdd(p.dbg + 6, (unsigned long long)(tk_end - tk3));   // stores and appends
+            }
+        }
     } else if (warp >= EPI_WARP0) {
-        // ===== epilogue: 2 threads per row (column halves) =====
+        // ===== epilogue of the raw / tile modes: 2 threads per row (column halves) =====
         const int ew = warp - EPI_WARP0;
         const int q = ew & 3, hf = ew >> 2;
         const int row = 32 * q + lane;
@@ -455,11 +660,11 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
             // h_j = |c'_j|^2/2 of this problem in shared memory (reloaded when the problem changes)
             if (b != h_loaded) {
                 asm volatile("bar.sync 1, 256;" ::: "memory");  // nobody still reads the old values
-                for (int j = et; j < NP; j += EPI_THREADS) h_s[j] = p.h ? p.h[(size_t)b * NP + j] : 0.0f;
+                for (int j = et; j < NP; j += EPI_THREADS) h_s[0][j] = p.h ? p.h[(size_t)b * NP + j] : 0.0f;
                 h_loaded = b;
                 asm volatile("bar.sync 1, 256;" ::: "memory");
             }
-            const float *hb = h_s + hf * half;
+            const float *hb = h_s[0] + hf * half;
             mbar_wait(&tmem_full[as], aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (uint32_t)(as * NP + hf * half) + ((uint32_t)(32 * q) << 16);
@@ -550,109 +755,6 @@ tc_assign_kernel(const __grid_constant__ CUtensorMap map_x1, const __grid_consta
                 }
                 continue;
             }
-            // pass 1 (software pipelined TMEM loads): the two largest s = acc - h and the argmax
-            const float NEG_INF = -__int_as_float(0x7f800000);
-            float m1 = NEG_INF, m2 = NEG_INF;
-            int i1 = 0;
-            {
-                float va[32], vb[32];
-                tmem_ld32_issue(taddr, va);
-                for (int c0 = 0; c0 < half; c0 += 64) {
-                    tmem_ld_wait();
-                    if (c0 + 32 < half) tmem_ld32_issue(taddr + c0 + 32, vb);
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const float sv = __uint_as_float(va_bits(va, i)) - hb[c0 + i];
-                        m2 = fmaxf(m2, fminf(sv, m1));
-                        i1 = sv > m1 ? c0 + i : i1;
-                        m1 = fmaxf(m1, sv);
-                    }
-                    if (c0 + 32 < half) {
-                        tmem_ld_wait();
-                        if (c0 + 64 < half) tmem_ld32_issue(taddr + c0 + 64, va);
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const float sv = __uint_as_float(va_bits(vb, i)) - hb[c0 + 32 + i];
-                            m2 = fmaxf(m2, fminf(sv, m1));
-                            i1 = sv > m1 ? c0 + 32 + i : i1;
-                            m1 = fmaxf(m1, sv);
-                        }
-                    }
-                }
-            }
-            rowmax_s[hf][row] = m1;
-            rowsec_s[hf][row] = m2;
-            rowarg_s[hf][row] = (uint16_t)(hf * half + i1);
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            const float o1 = rowmax_s[hf ^ 1][row], o2 = rowsec_s[hf ^ 1][row];
-            const float smax = fmaxf(m1, o1);
-            const float second = fmaxf(fminf(m1, o1), fmaxf(m2, o2));
-            // band (see the header of this file)
-            const float xn2 = valid ? p.xn2[(size_t)b * p.n + grow] : 0.0f;
-            const float cmax2 = __uint_as_float(p.cmax2_bits[b]);
-            const float E = p.gamma1 * sqrtf(xn2 * cmax2) * 1.0001f + 1.2e-7f * (0.5f * cmax2);
-            const float dmin = fmaxf(0.0f, xn2 - 2.0f * smax + 2.0f * E);
-            // rounding of the shift: |d(x',c') - d(x,c)| <= 2 sqrt(d) 2^-24 (|x'| + |c'|)
-            const float shift = 1.3e-7f * sqrtf(dmin) * (sqrtf(xn2) + sqrtf(cmax2));
-            const float band = 2.0f * (2.0f * E + 1.01f * p.eta * dmin + shift);
-            const float thresh = smax - band;
-            // a single column inside the band <=> the runner-up is below the threshold (the
-            // negation also catches NaN scores, which must go to the exact kernel)
-            const bool single = valid && (second < thresh) && (smax > NEG_INF);
-            const bool need2 = valid && !single;
-            // pass 2 (rare): collect every column inside the band
-            if (__any_sync(0xffffffffu, need2)) {
-                for (int c0 = 0; c0 < half; c0 += 32) {
-                    float v[32];
-                    tmem_ld32_issue(taddr + c0, v);
-                    tmem_ld_wait();
-                    if (need2) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const float sv = __uint_as_float(va_bits(v, i)) - hb[c0 + i];
-                            if (sv >= thresh) {
-                                const unsigned pos = atomicAdd(&cnt_s[row], 1u);
-                                if (pos < CAP) cand_s[row][pos] = (uint16_t)(hf * half + c0 + i);
-                            }
-                        }
-                    }
-                }
-            }
-            // the accumulator stage is free again
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[as]);
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (hf == 0) {
-                const unsigned c = cnt_s[row];
-                cnt_s[row] = 0;
-                // rows with exactly one column inside the band are final; the others go to the
-                // re-check list (c == 0: non-finite scores, c > CAP: too many -> all k centroids)
-                const bool need = need2;
-                const unsigned bal = __ballot_sync(0xffffffffu, need);
-                unsigned base = 0;
-                if (lane == 0 && bal) base = atomicAdd(p.work_count, (unsigned)__popc(bal));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (single)
-                    p.indices[(size_t)b * p.n + grow] = m1 >= o1 ? rowarg_s[0][row] : rowarg_s[1][row];
-                if (need) {
-                    const unsigned slot = base + __popc(bal & ((1u << lane) - 1u));
-                    if (slot < p.work_cap) {
-                        p.work_rows[slot] = (uint32_t)((size_t)b * p.n + grow);
-                        const unsigned cc = (c < 2 || c > CAP) ? CAP + 1 : c;
-                        p.work_cnt[slot] = (uint8_t)cc;
-                        for (unsigned u = 0; u < CAP; ++u)
-                            p.work_cand[(size_t)slot * CAP + u] = u < c ? cand_s[row][u] : 0;
-                        if (cc > CAP) atomicAdd(&p.stats[1], 1u);
-                    }
-                }
-            }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            (void)et;
-            if (++as == 2) {
-                as = 0;
-                aphase ^= 1;
-            }
         }
     }
     tc_fence_before();
@@ -674,7 +776,7 @@ __global__ void __launch_bounds__(256) recheck_kernel(const float *x, size_t n, 
                                                       const unsigned *work_count, unsigned work_cap,
                                                       const uint32_t *work_rows, const uint16_t *work_cand,
                                                       const uint8_t *work_cnt, uint32_t *indices,
-                                                      unsigned *flags) {
+                                                      unsigned *flags, unsigned *all_count, uint32_t *all_list, unsigned all_cap) {
     const unsigned total = min(*work_count, work_cap);
     const int lane = threadIdx.x & 31, quad = lane >> 2, tq = lane & 3;
     const int qbase = lane & ~3;
@@ -684,6 +786,15 @@ __global__ void __launch_bounds__(256) recheck_kernel(const float *x, size_t n, 
         const size_t b = br / n, row = br - b * n;
         const unsigned cnt = work_cnt[w];
         const bool all = cnt > CAP;
+        if (all && all_list) {   // uniform over the warp: a whole CTA takes such a row (recheck_all_kernel)
+            unsigned slot = 0;
+            if (lane == 0) slot = atomicAdd(all_count, 1u);
+            slot = __shfl_sync(0xffffffffu, slot, 0);
+            if (slot < all_cap) {
+                if (lane == 0) all_list[slot] = w;
+                continue;
+            }
+        }
         const unsigned ncand = all ? (unsigned)k : cnt;
         const float *xr = x + row * ldx + col_off + b * m;
         const float *cb = cent + b * k * m;
@@ -771,7 +882,7 @@ __global__ void __launch_bounds__(256) recheck_generic_kernel(const float *x, si
                                                               const unsigned *work_count, unsigned work_cap,
                                                               const uint32_t *work_rows, const uint16_t *work_cand,
                                                               const uint8_t *work_cnt, uint32_t *indices,
-                                                              unsigned *flags) {
+                                                              unsigned *flags, unsigned *all_count, uint32_t *all_list, unsigned all_cap) {
     const unsigned total = min(*work_count, work_cap);
     const int lane = threadIdx.x & 31;
     for (unsigned w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < total;
@@ -780,6 +891,15 @@ __global__ void __launch_bounds__(256) recheck_generic_kernel(const float *x, si
         const size_t b = br / n, row = br - b * n;
         const unsigned cnt = work_cnt[w];
         const bool all = cnt > CAP;
+        if (all && all_list) {   // uniform over the warp: a whole CTA takes such a row (recheck_all_kernel)
+            unsigned slot = 0;
+            if (lane == 0) slot = atomicAdd(all_count, 1u);
+            slot = __shfl_sync(0xffffffffu, slot, 0);
+            if (slot < all_cap) {
+                if (lane == 0) all_list[slot] = w;
+                continue;
+            }
+        }
         const unsigned ncand = all ? (unsigned)k : cnt;
         const float *xr = x + row * ldx + col_off + b * m;
         const float *cb = cent + b * k * m;
@@ -807,6 +927,92 @@ __global__ void __launch_bounds__(256) recheck_generic_kernel(const float *x, si
             if (bi == 0xFFFFFFFFu) atomicOr(flags, FLAG_NO_ARGMIN);
             else indices[b * n + row] = bi;
         }
+    }
+}
+
+// Rows whose band holds more than CAP columns are decided over all k centroids.  One warp per such row is a
+// tail of hundreds of microseconds (k = 1024, m = 768: 786k subtract-multiply-adds in one warp), so a whole CTA takes
+// the row: the warps share the centroids, every distance in the reference's order, lexicographic (distance, index)
+// minimum == first strict minimum in index order.
+template <bool ALIGNED>
+__global__ void __launch_bounds__(256) recheck_all_kernel(const float *x, size_t n, size_t ldx, size_t col_off, size_t m,
+                                                          size_t k, const float *cent, const unsigned *all_count,
+                                                          unsigned all_cap, const uint32_t *all_list,
+                                                          const uint32_t *work_rows, uint32_t *indices, unsigned *flags) {
+    __shared__ float sd[8];
+    __shared__ uint32_t si[8];
+    const unsigned total = min(*all_count, all_cap);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, quad = lane >> 2, tq = lane & 3;
+    const int qbase = lane & ~3;
+    for (unsigned e = blockIdx.x; e < total; e += gridDim.x) {
+        const uint32_t br = work_rows[all_list[e]];
+        const size_t b = br / n, row = br - b * n;
+        const float *xr = x + row * ldx + col_off + b * m;
+        const float *cb = cent + b * k * m;
+        float bd = __int_as_float(0x7f800000);
+        uint32_t bi = 0xFFFFFFFFu;
+        if (ALIGNED) {
+            for (unsigned c0 = 8 * warp; c0 < k; c0 += 64) {
+                const uint32_t j = c0 + quad;
+                const bool act = j < k;
+                const float *cr = cb + (size_t)(act ? j : 0) * m;
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                if (act) {
+                    for (size_t el = 4 * tq; el < m; el += 16) {
+                        const float4 xv = *reinterpret_cast<const float4 *>(xr + el);
+                        const float4 cv = *reinterpret_cast<const float4 *>(cr + el);
+                        a0 = sq_acc(a0, xv.x, cv.x);
+                        a1 = sq_acc(a1, xv.y, cv.y);
+                        a2 = sq_acc(a2, xv.z, cv.z);
+                        a3 = sq_acc(a3, xv.w, cv.w);
+                    }
+                }
+                float s = 0.0f;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    if (tq == t) {
+                        s = __fadd_rn(s, a0);
+                        s = __fadd_rn(s, a1);
+                        s = __fadd_rn(s, a2);
+                        s = __fadd_rn(s, a3);
+                    }
+                    s = __shfl_sync(0xffffffffu, s, qbase + t);
+                }
+                if (act && (s < bd || (s == bd && j < bi))) {
+                    bd = s;
+                    bi = j;
+                }
+            }
+        } else {
+            for (uint32_t j = threadIdx.x; j < k; j += 256) {
+                const float d = sqdist_generic(xr, cb + (size_t)j * m, m);
+                if (d < bd || (d == bd && j < bi)) {
+                    bd = d;
+                    bi = j;
+                }
+            }
+        }
+#pragma unroll
+        for (int off = 1; off <= 16; off <<= 1) {
+            const float od = __shfl_xor_sync(0xffffffffu, bd, off);
+            const uint32_t oi = __shfl_xor_sync(0xffffffffu, bi, off);
+            if (oi != 0xFFFFFFFFu && (bi == 0xFFFFFFFFu || od < bd || (od == bd && oi < bi))) {
+                bd = od;
+                bi = oi;
+            }
+        }
+        if (lane == 0) sd[warp] = bd, si[warp] = bi;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < 8; ++w)
+                if (si[w] != 0xFFFFFFFFu && (bi == 0xFFFFFFFFu || sd[w] < bd || (sd[w] == bd && si[w] < bi))) {
+                    bd = sd[w];
+                    bi = si[w];
+                }
+            if (bi == 0xFFFFFFFFu) atomicOr(flags, FLAG_NO_ARGMIN);
+            else indices[b * n + row] = bi;
+        }
+        __syncthreads();
     }
 }
 
@@ -907,10 +1113,11 @@ struct TcState {
     DevBuf<float> xn2, h, mu;
     DevBuf<double> mean_partial;
     DevBuf<unsigned> cmax2, work_count, stats;
+    DevBuf<unsigned long long> dbg;
     DevBuf<float> tile_v;       // k > 256: [n][tiles][4] largest scores per (row, column tile)
     DevBuf<uint16_t> tile_i;    //          [n][tiles][2] their columns
     size_t pnb = 0;
-    DevBuf<uint32_t> work_rows;
+    DevBuf<uint32_t> work_rows, all_list;
     DevBuf<uint16_t> work_cand;
     DevBuf<uint8_t> work_cnt;
     CUtensorMap map_x1, map_x2, map_c1, map_c2;
@@ -973,7 +1180,8 @@ int tc_reassign(fdb_km *km, const int *d_active) {
             FDB_TRY(tc->tile_v.ensure(n * pnb * 4));
             FDB_TRY(tc->tile_i.ensure(n * pnb * 2));
         }
-        FDB_TRY(tc->work_count.ensure(1));
+        FDB_TRY(tc->work_count.ensure(2));   // [0] rows to re-check, [1] of those: rows decided over all k
+        FDB_TRY(tc->all_list.ensure(ALL_CAP));
         FDB_TRY(tc->stats.ensure(2));
         FDB_TRY(tc->work_rows.ensure(nb * n));
         FDB_TRY(tc->work_cand.ensure(nb * n * CAP));
@@ -1011,7 +1219,7 @@ int tc_reassign(fdb_km *km, const int *d_active) {
         tc->pnb = pnb;
     }
     FDB_CUDA(cudaMemsetAsync(tc->cmax2.p, 0, pnb * sizeof(unsigned), st));
-    FDB_CUDA(cudaMemsetAsync(tc->work_count.p, 0, sizeof(unsigned), st));
+    FDB_CUDA(cudaMemsetAsync(tc->work_count.p, 0, 2 * sizeof(unsigned), st));
     FDB_CUDA(cudaMemsetAsync(tc->stats.p, 0, 2 * sizeof(unsigned), st));
     {
         dim3 grid((unsigned)np, (unsigned)pnb);
@@ -1059,6 +1267,13 @@ int tc_reassign(fdb_km *km, const int *d_active) {
     p.work_cnt = tc->work_cnt.p;
     p.work_cap = (unsigned)(nb * n);
     p.stats = tc->stats.p;
+    p.debug = getenv("FDB_TC_DEBUG") ? atoi(getenv("FDB_TC_DEBUG")) : 0;
+    p.dbg = nullptr;
+    if (p.debug & 16) {
+        FDB_TRY(tc->dbg.ensure(8));
+        FDB_CUDA(cudaMemsetAsync(tc->dbg.p, 0, 8 * sizeof(unsigned long long), st));
+        p.dbg = tc->dbg.p;
+    }
     FDB_CUDA(cudaFuncSetAttribute(tc_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int total_tiles = (int)pnb * p.row_tiles;
     const int grid = std::min(total_tiles, ctx->sm_count);
@@ -1070,18 +1285,40 @@ int tc_reassign(fdb_km *km, const int *d_active) {
         ctx->launches++;
         FDB_CHECK_LAUNCH();
     }
-    if (rows_aligned && (uintptr_t)km->vs->d % 16 == 0 && ld % 4 == 0)
+    const bool rc_aligned = rows_aligned && (uintptr_t)km->vs->d % 16 == 0 && ld % 4 == 0;
+    unsigned *all_count = tc->work_count.p + 1;
+    if (rc_aligned)
         recheck_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(km->vs->d, n, ld, km->col_off, m, k, km->centroids.p,
                                                           tc->work_count.p, p.work_cap, tc->work_rows.p,
                                                           tc->work_cand.p, tc->work_cnt.p, km->indices.p,
-                                                          ctx->d_flags);
+                                                          ctx->d_flags, all_count, tc->all_list.p, ALL_CAP);
     else
         recheck_generic_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(km->vs->d, n, ld, km->col_off, m, k,
                                                                   km->centroids.p, tc->work_count.p, p.work_cap,
                                                                   tc->work_rows.p, tc->work_cand.p, tc->work_cnt.p,
-                                                                  km->indices.p, ctx->d_flags);
+                                                                  km->indices.p, ctx->d_flags, all_count, tc->all_list.p,
+                                                                  ALL_CAP);
     ctx->launches++;
     FDB_CHECK_LAUNCH();
+    // the rows that go over all k centroids: one CTA each (a no-op launch when there are none)
+    if (rc_aligned)
+        recheck_all_kernel<true><<<ctx->sm_count * 2, 256, 0, st>>>(km->vs->d, n, ld, km->col_off, m, k, km->centroids.p,
+                                                                    all_count, ALL_CAP, tc->all_list.p, tc->work_rows.p,
+                                                                    km->indices.p, ctx->d_flags);
+    else
+        recheck_all_kernel<false><<<ctx->sm_count * 2, 256, 0, st>>>(km->vs->d, n, ld, km->col_off, m, k, km->centroids.p,
+                                                                     all_count, ALL_CAP, tc->all_list.p, tc->work_rows.p,
+                                                                     km->indices.p, ctx->d_flags);
+    ctx->launches++;
+    FDB_CHECK_LAUNCH();
+    if (p.dbg) {
+        unsigned long long hd[8];
+        FDB_CUDA(cudaMemcpyAsync(hd, tc->dbg.p, sizeof(hd), cudaMemcpyDeviceToHost, st));
+        FDB_CUDA(cudaStreamSynchronize(st));
+        const double wt = hd[3] ? (double)hd[3] : 1.0;
+        fprintf(stderr, "[fdb tc dbg] warp-tiles %llu: head %.0f, wait %.0f, pass 1 %.0f, band + pass 2 %.0f, tail %.0f cycles per warp-tile; warps with candidates %llu\n",
+                hd[3], hd[5] / wt, hd[0] / wt, hd[1] / wt, hd[2] / wt, hd[6] / wt, hd[4]);
+    }
     if (getenv("FDB_TC_STATS")) {
         unsigned hs[3];
         FDB_CUDA(cudaMemcpyAsync(hs, tc->stats.p, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
