@@ -235,6 +235,7 @@ def run_ours(args, rank, world, local_rank, dist):
         step_ms.append(ctx.timer_stop())
         ms, scan_bytes = ix.last_timing()
         phase_ms += ms
+        scan_kernel_name = ix.last_scan_kernel()
     step_launches = (ctx.launches - launches0) // max(args.steps, 1)
     ctx.sync()
     total_ms = float(sum(step_ms))
@@ -351,9 +352,9 @@ def run_ours(args, rank, world, local_rank, dist):
     ph = phase_ms / args.steps
     scan_ms, table_ms, coarse_ms = ph[4], ph[3], ph[0]
     scan_gbs = scan_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else None
-    traffic = ncu_traffic("fscan_kernel")
+    traffic = ncu_traffic(scan_kernel_name.split()[0])
     roofline_scan = {
-        "kernel": "fscan_kernel (dominant kernel of the step: code lists, u8 codes + per-vector term)",
+        "kernel": scan_kernel_name + " -- the code scan, dominant phase of the step",
         "bound": "hbm", "achieved": scan_gbs, "peak": hbm_peak, "unit": "GB/s",
         "frac": (scan_gbs / hbm_peak) if scan_gbs else None, "peak_source": peak_src,
         "traffic": traffic, "algorithmic_bytes_per_launch": scan_bytes,
@@ -419,8 +420,7 @@ def run_ours(args, rank, world, local_rank, dist):
         try:
             scan_large = run_scan_large(ctx, engine, hbm_peak, peak_src)
             # many queries per list: the partition-major kernel (adc_pscan.cuh) takes over
-            scan_large_pm = run_scan_large(ctx, engine, hbm_peak, peak_src, m=10_000_000, p=1024, nq=4096, nprobe=16,
-                                           kernel="pscan16_kernel (partition-major, 32 queries per item, 16-bit tables)")
+            scan_large_pm = run_scan_large(ctx, engine, hbm_peak, peak_src, m=10_000_000, p=1024, nq=4096, nprobe=16)
         except Exception as exc:  # the headline numbers do not depend on it
             scan_large = {"error": str(exc)}
 
@@ -445,7 +445,7 @@ def run_ours(args, rank, world, local_rank, dist):
                          "same_ids_as_batch": single_ok, "published_reference_ms": 1.476},
         "nprobe_sweep": sweep,
         "scan_large": scan_large,
-        "scan_large_partition_major": scan_large_pm,
+        "scan_large_64_queries_per_list": scan_large_pm,
         "cpu_baseline": cpu_baseline,
         "parity": {"queries_checked": ns, "id_mismatches": mism, "distances_bit_equal": dist_bits},
         "build": {"metric": "ivfpq_build_sec_100kx1536", "sec": min(builds[1:]), "sec_cold": builds[0],
@@ -761,6 +761,17 @@ def run_sharded(args, rank, world, local_rank, dist):
                                                                 max(2, min(args.steps, 3)), 2, hbm_peak)
     sizes = gather_objects(dist, build.pop("local_partition_sizes"), world)
     comm.close()
+    # the same build on ONE GPU of this box in the same run (rank 0 alone, the others wait): the base of the strong-
+    # scaling curve, so that the N-GPU value can be read against a 1-GPU value measured minutes apart, not on another box
+    base1 = None
+    if world > 1 and not args.no_single_gpu_base:
+        if rank == 0:
+            comm1 = engine.Comm(ctx, 1, 0, None)
+            b1 = run_sharded_build(args, engine, sharded, ctx, comm1, 0, 1, 1, 1)
+            comm1.close()
+            base1 = {"value": b1["rows_per_s"], "unit": "rows/s", "sec": b1["sec"], "phase_sec": b1["phase_sec"],
+                     "note": "configs[2] on rank 0's GPU alone (world = 1, no collectives), 1 warm-up + 1 timed build"}
+        dist.barrier()
     ctx.close()
     if rank != 0:
         return None
@@ -790,7 +801,7 @@ def run_sharded(args, rank, world, local_rank, dist):
              "achieved": seed_bytes / seed_sec / 1e9 / world, "peak": hbm_peak, "unit": "GB/s",
              "frac": seed_bytes / seed_sec / 1e9 / world / hbm_peak,
              "note": "per GPU; phase time includes the pick, the packed all-gather and the launch gaps of every round"}],
-        "parity": parity_build, "sharded_query": query, "clocks": clocks,
+        "parity": parity_build, "sharded_query": query, "clocks": clocks, "single_gpu_same_run": base1,
         "limiter": "see phase_sec: the k-means++ rounds are latency (kernel launches + one small all-gather each), "
                    "the Lloyd rounds one all-reduce of %.1f MB (coarse) / %.1f MB (PQ) each"
                    % ((P2 * N2 + P2) * 4 / 1e6, (D2 * C2 * (N2 // D2) + D2 * C2) * 4 / 1e6),
@@ -798,8 +809,7 @@ def run_sharded(args, rank, world, local_rank, dist):
 
 
 # ------------------------------------------------------------------------------------------
-def run_scan_large(ctx, engine, hbm_peak, peak_src, m=40_000_000, p=4096, nq=2048, nprobe=16,
-                   kernel="fscan_kernel (query-major, compact code lists)"):
+def run_scan_large(ctx, engine, hbm_peak, peak_src, m=40_000_000, p=4096, nq=2048, nprobe=16):
     """The code scan where its bytes really come from HBM (BASELINE.json configs[4] scaled to one
     GPU and a few seconds): a synthesised index of m x 12 u8 codes in p lists (40M -> 480 MB, L2 is
     126 MB), nq queries, nprobe lists each.  Reports the scan phase alone."""
@@ -827,6 +837,7 @@ def run_scan_large(ctx, engine, hbm_peak, peak_src, m=40_000_000, p=4096, nq=204
             ms.append(float(phases[4]))
             tot.append(t)
     stats = ix.last_stats()
+    kernel = ix.last_scan_kernel()
     ix.close()
     for h in [d_q] + outs:
         ctx.free(h)
@@ -928,6 +939,8 @@ def main():
     ap.add_argument("--no-sharded", action="store_true",
                     help="N = 1: skip the sharded workloads (configs[2] build, configs[4] query) at world = 1")
     ap.add_argument("--no-sharded-query", action="store_true", help="skip configs[4] (100M codes) in the sharded run")
+    ap.add_argument("--no-single-gpu-base", action="store_true",
+                    help="N > 1: skip the world = 1 build rank 0 runs at the end as the base of the scaling curve")
     ap.add_argument("--no-scan-large", action="store_true",
                     help="skip the secondary measurement of the code scan on lists that exceed L2")
     args = ap.parse_args()

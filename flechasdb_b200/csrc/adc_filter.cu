@@ -1245,12 +1245,29 @@ __device__ __forceinline__ float sq_diff2(float qv, float cv, float bv) {
 // dot (src/linalg.rs:12-40).  Candidates are in lanes 0..ncand-1, sorted by partition.
 template <int ITERS>
 __device__ __forceinline__ void quad_groups(const FSelParams &p, const float *qv, uint32_t my_part,
-                                            uint32_t my_vidx, int ncand, unsigned gmask, float *tbuf, int lane) {
+                                            uint32_t my_vidx, int ncand, unsigned gmask, float *tbuf,
+                                            unsigned char *cds, int lane) {
     const int g = lane >> 2, tq = lane & 3, qbase = lane & ~3;
     const int D = (int)p.D;
     const size_t s = p.s;
     const int ngroups = __popc(gmask);
     const int nitems = ngroups * D;
+    // the candidates' code bytes, staged once (cds[c * D + d]): the walk below then depends on one global
+    // latency per candidate (the code vector's row) instead of two
+    if (lane < ncand) {
+        const uint8_t *src = p.codes + p.part_cstart[my_part] + (size_t)my_vidx * D;
+        if ((D & 3) == 0 && D <= 16) {
+            uint32_t w[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) w[i] = 4 * i < D ? __ldg(reinterpret_cast<const uint32_t *>(src) + i) : 0u;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (4 * i < D) reinterpret_cast<uint32_t *>(cds + (size_t)lane * D)[i] = w[i];
+        } else {
+            for (int d = 0; d < D; ++d) cds[(size_t)lane * D + d] = src[d];
+        }
+    }
+    __syncwarp();
     for (int it0 = 0; it0 < nitems; it0 += 8) {
         const int item = it0 + g;
         const bool act = item < nitems;
@@ -1262,6 +1279,16 @@ __device__ __forceinline__ void quad_groups(const FSelParams &p, const float *qv
         const uint32_t part = __shfl_sync(0xffffffffu, my_part, gs);
         const float *xq = qv + d * s;
         const float *xc = p.coarse + (size_t)part * p.N + d * s;
+        // the code vector's row of candidate gs + t (row 0 of the division for a quad that has run out: harmless)
+        auto load_rows = [&](int t, float4 (&b)[ITERS]) {
+            const int c = gs + t;
+            const unsigned code = c < ge ? cds[(size_t)c * D + d] : 0u;
+            const float *xb = p.codebooks + (d * p.C + code) * s;
+#pragma unroll
+            for (int it = 0; it < ITERS; ++it) b[it] = __ldg(reinterpret_cast<const float4 *>(xb + 4 * tq + 16 * it));
+        };
+        float4 bc[ITERS], bn[ITERS];
+        load_rows(0, bc);                       // travels together with q_d and c_pd
         float4 l[ITERS];
 #pragma unroll
         for (int it = 0; it < ITERS; ++it) {
@@ -1277,13 +1304,11 @@ __device__ __forceinline__ void quad_groups(const FSelParams &p, const float *qv
         for (int t = 0; t < tmax; ++t) {
             const int c = gs + t;
             const bool cact = c < ge;
-            const uint32_t vidx = __shfl_sync(0xffffffffu, my_vidx, cact ? c : 0);
-            const uint8_t code = cact ? p.codes[p.part_cstart[part] + (size_t)vidx * D + d] : (uint8_t)0;
-            const float *xb = p.codebooks + (d * p.C + code) * s;
+            if (t + 1 < tmax) load_rows(t + 1, bn);   // the next candidate's row is in flight while this one is summed
             float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
 #pragma unroll
             for (int it = 0; it < ITERS; ++it) {
-                const float4 b = __ldg(reinterpret_cast<const float4 *>(xb + 4 * tq + 16 * it));
+                const float4 b = bc[it];
                 float dd = __fsub_rn(l[it].x, b.x);   // subtract, src/db/stored.rs:565-571
                 a0 = __fadd_rn(a0, __fmul_rn(dd, dd));
                 dd = __fsub_rn(l[it].y, b.y);
@@ -1293,6 +1318,8 @@ __device__ __forceinline__ void quad_groups(const FSelParams &p, const float *qv
                 dd = __fsub_rn(l[it].w, b.w);
                 a3 = __fadd_rn(a3, __fmul_rn(dd, dd));
             }
+#pragma unroll
+            for (int it = 0; it < ITERS; ++it) bc[it] = bn[it];
             float T = 0.0f;  // sum_naive over the 16 accumulators, src/linalg.rs:39
 #pragma unroll
             for (int t4 = 0; t4 < 4; ++t4) {
@@ -1309,7 +1336,7 @@ __device__ __forceinline__ void quad_groups(const FSelParams &p, const float *qv
     }
 }
 
-__global__ void __launch_bounds__(128) fselect_kernel(FSelParams p) {
+__global__ void __launch_bounds__(128, 4) fselect_kernel(FSelParams p) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t q = p.q0 + (size_t)blockIdx.x * 4 + warp;
     if (q >= p.q1) return;
@@ -1368,6 +1395,7 @@ __global__ void __launch_bounds__(128) fselect_kernel(FSelParams p) {
         // loads 128 bits at a time; the lane sums are chained through the quad in lane order
         extern __shared__ float tbuf_all[];
         float *tbuf = tbuf_all + (size_t)warp * RCAP * D;   // [candidate][division]
+        unsigned char *cds = reinterpret_cast<unsigned char *>(tbuf_all + 4 * RCAP * D) + (size_t)warp * RCAP * D;   // code bytes
         const int iters = (int)(s >> 4);
         if (iters == 8 || iters == 4 || iters == 2 || iters == 1) {
             // candidates ordered by partition; a group = the candidates of one partition
@@ -1382,10 +1410,10 @@ __global__ void __launch_bounds__(128) fselect_kernel(FSelParams p) {
             my_vidx = __shfl_sync(0xffffffffu, my_vidx, psrc);
             const uint32_t prevp = __shfl_up_sync(0xffffffffu, my_part, 1);
             const unsigned gmask = __ballot_sync(0xffffffffu, lane < ncand && (lane == 0 || prevp != my_part));
-            if (iters == 8) quad_groups<8>(p, qv, my_part, my_vidx, ncand, gmask, tbuf, lane);
-            else if (iters == 4) quad_groups<4>(p, qv, my_part, my_vidx, ncand, gmask, tbuf, lane);
-            else if (iters == 2) quad_groups<2>(p, qv, my_part, my_vidx, ncand, gmask, tbuf, lane);
-            else quad_groups<1>(p, qv, my_part, my_vidx, ncand, gmask, tbuf, lane);
+            if (iters == 8) quad_groups<8>(p, qv, my_part, my_vidx, ncand, gmask, tbuf, cds, lane);
+            else if (iters == 4) quad_groups<4>(p, qv, my_part, my_vidx, ncand, gmask, tbuf, cds, lane);
+            else if (iters == 2) quad_groups<2>(p, qv, my_part, my_vidx, ncand, gmask, tbuf, cds, lane);
+            else quad_groups<1>(p, qv, my_part, my_vidx, ncand, gmask, tbuf, cds, lane);
         } else {
         const int g = lane >> 2, tq = lane & 3, qbase = lane & ~3;
             const int nitems = ncand * (int)D;
@@ -1741,11 +1769,13 @@ bool filter_eligible(const fdb_index *ix, size_t nq, size_t k, size_t nprobe) {
 static bool vscan_default(const fdb_index *ix, size_t nq, size_t nprobe) {
     // Measured.  Lists of thousands of vectors: ahead of the query-major kernel from about two
     // queries per list on (0.77 of the HBM bandwidth at 8 queries per list, 1.1 from 32 on; fscan_kernel: 0.35).
-    // Short lists (the README shape, 1 000 vectors): a table per (8 queries, list) costs as much as scanning the list,
-    // the query-major kernel builds one table per query for all its lists -- level at nprobe = 5, ahead from ~8 on.
+    // Short lists (the README shape, 1 000 vectors): a table per (8 queries, list) costs about as much as scanning
+    // the list, but with the two-pass cold start the scan phase is 0.32 ms against the query-major kernel's 0.39 ms
+    // (10 000 queries, nprobe 5).  Lists of a few hundred vectors stay with the query-major kernel, which builds
+    // one table per query for all its lists.
     if (getenv("FDB_VSCAN_OFF")) return false;
     if ((double)nq * (double)nprobe < 2.0 * (double)ix->P) return false;
-    return ix->M >= 2048 * ix->P || nprobe >= 8;
+    return ix->M >= 512 * ix->P || (nprobe >= 8 && ix->M >= 128 * ix->P);
 }
 
 // E_q = coef * W_q (header): gamma of the GEMM that produces G (tensor pipe or FMA chain)
@@ -2078,6 +2108,7 @@ int filter_query(fdb_index *ix, const float *d_q, size_t q_base, size_t nq, size
         }
     }
 
+    ix->last_scan_kind = !use_pscan ? 1 : use_vscan ? 4 : use_p16 ? 3 : 2;
     for (size_t q0 = 0; q0 < nq; q0 += chunk) {
         const size_t nc = std::min(chunk, nq - q0);
         FDB_TRY(log->mark(3));
@@ -2167,6 +2198,7 @@ int filter_query(fdb_index *ix, const float *d_q, size_t q_base, size_t nq, size
         vx.qpar = reinterpret_cast<const float4 *>(sl->qpar.p);
         vx.pct = fs->pct.p;
         vx.pcpar = reinterpret_cast<const float4 *>(fs->pcpar.p);
+        vx.two_pass_max = getenv("FDB_VSCAN_2PASS_MAX") ? atoi(getenv("FDB_VSCAN_2PASS_MAX")) : 6144;
         if (use_vscan) {
             vquant_fn(D)<<<(unsigned)nc, 256, 0, st>>>(sl->G.p, (int)C, fs->pc_range_max.p, sl->Gq.p, reinterpret_cast<float4 *>(sl->qpar.p));
             ctx->launches++;
@@ -2229,7 +2261,7 @@ int filter_query(fdb_index *ix, const float *d_q, size_t q_base, size_t nq, size
     fp.nprobe = (int)nprobe;
     fp.k = (int)k;
     fp.ncap = ncap;
-    fp.quad = (s % 16 == 0) && (N % 4 == 0) && ((uintptr_t)d_q % 16 == 0) && (4 * RCAP * D * sizeof(float) <= 48 * 1024);
+    fp.quad = (s % 16 == 0) && (N % 4 == 0) && ((uintptr_t)d_q % 16 == 0) && (4 * RCAP * D * (sizeof(float) + 1) <= 48 * 1024);
     fp.coef = coef;
     fp.eta3 = eta3;
     sl->last_coef = coef;
@@ -2242,7 +2274,7 @@ int filter_query(fdb_index *ix, const float *d_q, size_t q_base, size_t nq, size
     fp.out_d = d_d;
     fp.fb_list = sl->fb_list.p;
     fp.counters = sl->counters.p;
-    fselect_kernel<<<(unsigned)((nq + 3) / 4), 128, fp.quad ? 4 * RCAP * D * sizeof(float) : 0, st>>>(fp);
+    fselect_kernel<<<(unsigned)((nq + 3) / 4), 128, fp.quad ? 4 * RCAP * D * (sizeof(float) + 1) : 0, st>>>(fp);
     ctx->launches++;
     FDB_CHECK_LAUNCH();
     stash_undecided_kernel<<<1, 256, 0, st>>>(sl->counters.p, sl->fb_list.p, d_probes, q_base, (int)nprobe,

@@ -248,6 +248,7 @@ struct VScanExtra {
     const float4 *qpar;          // [queries of this chunk]
     const float *pct;            // [P][ROWS]
     const float4 *pcpar;         // [P]
+    int two_pass_max;            // items of at most this many vectors take the two-pass cold start (0: never)
 };
 
 template <int W>
@@ -377,15 +378,95 @@ __global__ void __launch_bounds__(VWARPS * 32, W <= 3 ? 4 : 3) vscan_kernel(PSca
         __syncthreads();
         const unsigned next_item = s_next;
 
+        // the D look-ups of one vector (code words cw): packed 16-bit sums of the 8 members
+        auto table_sums = [&](const uint32_t (&cwv)[W], uint32_t &a0, uint32_t &a1, uint32_t &a2, uint32_t &a3) {
+            a0 = 0u, a1 = 0u, a2 = 0u, a3 = 0u;
+#pragma unroll
+            for (int g = 0; g < L::NF; ++g) {
+                const uint32_t lo = cwv[2 * g], hi = cwv[(2 * g + 1) < W ? 2 * g + 1 : 0];
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    const uint32_t s = (phase + (uint32_t)t) & 7u;
+                    const uint32_t code = __byte_perm(lo, hi, s) & 0xffu;
+                    const uint4 e = lds_v4(tb + (uint32_t)(g * L::F_BYTES) + code * 128u + s * 16u);
+                    a0 += e.x, a1 += e.y, a2 += e.z, a3 += e.w;
+                }
+            }
+            if (L::HALF) {
+                const uint32_t xw = cwv[W - 1];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const uint32_t s = (phase + (uint32_t)t) & 3u;
+                    const uint32_t code = __byte_perm(xw, 0u, s) & 0xffu;
+                    const uint4 e = lds_v4(tb + (uint32_t)(L::NF * L::F_BYTES) + code * 64u + s * 16u);
+                    a0 += e.x, a1 += e.y, a2 += e.z, a3 += e.w;
+                }
+            }
+        };
+
         // ---- rounds: [rs, re) is handled by all warps, 32 vectors per warp step.  Cold start (no threshold yet): a
         //      round never brings more than about ncap new entries per query (as many vectors as have been seen so
         //      far).  With inherited thresholds the whole item is one round.  When a buffer overflows, every buffer is
         //      cut back and loses the round's entries, and the round runs again, shorter, with the tighter thresholds.
         int rs = v0, seen = 0, retries = 0;
-        int rsize = s_warm ? min(v1 - v0, 4096) : 64;
         uint32_t cw[W], nw[W];
         int cwb = rs + 32 * warp;     // the step whose code words cw holds
         load_code_words<W>(lst, min(cwb + lane, v1 - 1), cw);
+        // ---- cold start on a short item: two passes instead of doubling rounds.  Pass 1 keeps, per lane and member,
+        //      the minimum of the sums the lane sees (four packed minima per step); the 256 lane minima of a member
+        //      belong to 256 different vectors, so their ncap-th smallest T bounds the item's ncap-th smallest sum --
+        //      and it is close to it (two of the ncap smallest rarely share a lane).  Pass 2 is then ONE round with
+        //      the final thresholds: about ncap appends per member, one cut, no retries.
+        const bool two_pass = !s_warm && (v1 - v0) <= x.two_pass_max;   // uniform
+        if (two_pass) {
+            uint32_t m0 = 0xffffffffu, m1 = 0xffffffffu, m2 = 0xffffffffu, m3 = 0xffffffffu;
+            for (int b = v0 + 32 * warp; b < v1; b += 32 * VWARPS) {
+                const int nb = b + 32 * VWARPS;
+                if (nb < v1) load_code_words<W>(lst, min(nb + lane, v1 - 1), nw);
+                uint32_t a0, a1, a2, a3;
+                table_sums(cw, a0, a1, a2, a3);
+                if (b + lane < v1) m0 = __vminu2(m0, a0), m1 = __vminu2(m1, a1), m2 = __vminu2(m2, a2), m3 = __vminu2(m3, a3);
+#pragma unroll
+                for (int w = 0; w < W; ++w) cw[w] = nw[w];
+            }
+            cwb = -1;                                          // pass 2 loads its first step again
+            unsigned short *mins = reinterpret_cast<unsigned short *>(bkeys);   // [VJ][256] = the two append buffers
+            mins[0 * 256 + tid] = (unsigned short)(m0 & 0xffffu), mins[1 * 256 + tid] = (unsigned short)(m0 >> 16);
+            mins[2 * 256 + tid] = (unsigned short)(m1 & 0xffffu), mins[3 * 256 + tid] = (unsigned short)(m1 >> 16);
+            mins[4 * 256 + tid] = (unsigned short)(m2 & 0xffffu), mins[5 * 256 + tid] = (unsigned short)(m2 >> 16);
+            mins[6 * 256 + tid] = (unsigned short)(m3 & 0xffffu), mins[7 * 256 + tid] = (unsigned short)(m3 >> 16);
+            __syncthreads();
+            uint32_t T = 0xffffu;
+            if (warp < members && bthr[warp] != 0u) {
+                const uint4 mv = reinterpret_cast<const uint4 *>(mins + warp * 256)[lane];
+                const uint32_t xv[8] = {mv.x & 0xffffu, mv.x >> 16, mv.y & 0xffffu, mv.y >> 16,
+                                        mv.z & 0xffffu, mv.z >> 16, mv.w & 0xffffu, mv.w >> 16};
+                uint32_t lo = 0u, hi = 0xffffu;                // count(x <= hi) >= ncap holds for hi = 0xffff (256 values)
+                while (lo < hi) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    int c = 0;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) c += xv[i] <= mid ? 1 : 0;
+                    c = __reduce_add_sync(0xffffffffu, c);
+                    if (c >= p.ncap) hi = mid;
+                    else lo = mid + 1u;
+                }
+                T = lo;
+            }
+            __syncthreads();                                   // the minima are read: the region is the buffers again
+            if (warp < members && lane == 0 && bthr[warp] != 0u) {
+                const int j = warp;
+                unsigned th = min(bthr[j], __ldcg(&p.thrg[bq[j]]));            // (another list may have finished meanwhile)
+                if (T < 0xffffu) {                                             // 0xffff: fewer than ncap vectors, no bound
+                    const uint32_t key = fkey(fmaf(qdelta[j], (float)T, qbase[j]));
+                    th = min(th, key == 0xffffffffu ? key : key + 1u);         // S <= T stays a candidate
+                }
+                bthr[j] = th;
+                tthr[j] = (unsigned short)int_threshold(j);
+            }
+            __syncthreads();
+        }
+        int rsize = two_pass ? v1 - v0 : s_warm ? min(v1 - v0, 4096) : 64;
         while (rs < v1) {
             const int re = min(v1, rs + rsize);
             const uint4 tv = *reinterpret_cast<const uint4 *>(&tthr[0]);
@@ -396,48 +477,29 @@ __global__ void __launch_bounds__(VWARPS * 32, W <= 3 ? 4 : 3) vscan_kernel(PSca
                 load_code_words<W>(lst, min(nb + lane, v1 - 1), nw);
                 cwb = nb;
                 const int v = b + lane;
-                uint32_t a0 = 0u, a1 = 0u, a2 = 0u, a3 = 0u;
-#pragma unroll
-                for (int g = 0; g < L::NF; ++g) {
-                    const uint32_t lo = cw[2 * g], hi = cw[(2 * g + 1) < W ? 2 * g + 1 : 0];
-#pragma unroll
-                    for (int t = 0; t < 8; ++t) {
-                        const uint32_t s = (phase + (uint32_t)t) & 7u;
-                        const uint32_t code = __byte_perm(lo, hi, s) & 0xffu;
-                        const uint4 e = lds_v4(tb + (uint32_t)(g * L::F_BYTES) + code * 128u + s * 16u);
-                        a0 += e.x, a1 += e.y, a2 += e.z, a3 += e.w;
-                    }
-                }
-                if (L::HALF) {
-                    const uint32_t xw = cw[W - 1];
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        const uint32_t s = (phase + (uint32_t)t) & 3u;
-                        const uint32_t code = __byte_perm(xw, 0u, s) & 0xffu;
-                        const uint4 e = lds_v4(tb + (uint32_t)(L::NF * L::F_BYTES) + code * 64u + s * 16u);
-                        a0 += e.x, a1 += e.y, a2 += e.z, a3 += e.w;
-                    }
-                }
+                uint32_t a0, a1, a2, a3;
+                table_sums(cw, a0, a1, a2, a3);
                 // a half word of min(S, t) differs from t  <=>  that sum is below its threshold
                 const uint32_t below = ((__vminu2(a0, tv.x) ^ tv.x) | (__vminu2(a1, tv.y) ^ tv.y)) |
                                        ((__vminu2(a2, tv.z) ^ tv.z) | (__vminu2(a3, tv.w) ^ tv.w));
                 if (below != 0u && v < re) {
-                    const uint32_t aw[4] = {a0, a1, a2, a3}, tw[4] = {tv.x, tv.y, tv.z, tv.w};
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const uint32_t S = (aw[i] >> (16 * h)) & 0xffffu;
-                            if (S < ((tw[i] >> (16 * h)) & 0xffffu)) {
-                                const int j = 2 * i + h;
-                                const uint32_t key = fkey(fmaf(qdelta[j], (float)S, qbase[j]));
-                                if (key < bthr[j]) {
-                                    const int slot = atomicAdd(&bcnt[j], 1);
-                                    if (slot < VB) {
-                                        bkeys[j * VB + slot] = key;
-                                        bpos[j * VB + slot] = (uint32_t)v;
-                                    }
-                                }
+                    // the members whose sum is below its threshold, one bit each; a lane rarely has more than one
+                    const uint32_t e0 = __vminu2(a0, tv.x) ^ tv.x, e1 = __vminu2(a1, tv.y) ^ tv.y;
+                    const uint32_t e2 = __vminu2(a2, tv.z) ^ tv.z, e3 = __vminu2(a3, tv.w) ^ tv.w;
+                    uint32_t mm = ((e0 & 0xffffu) ? 1u : 0u) | ((e0 >> 16) ? 2u : 0u) | ((e1 & 0xffffu) ? 4u : 0u) |
+                                  ((e1 >> 16) ? 8u : 0u) | ((e2 & 0xffffu) ? 16u : 0u) | ((e2 >> 16) ? 32u : 0u) |
+                                  ((e3 & 0xffffu) ? 64u : 0u) | ((e3 >> 16) ? 128u : 0u);
+                    while (mm != 0u) {
+                        const int j = __ffs((int)mm) - 1;
+                        mm &= mm - 1u;
+                        const uint32_t wv = (j & 4) ? ((j & 2) ? a3 : a2) : ((j & 2) ? a1 : a0);
+                        const uint32_t S = (j & 1) ? (wv >> 16) : (wv & 0xffffu);
+                        const uint32_t key = fkey(fmaf(qdelta[j], (float)S, qbase[j]));
+                        if (key < bthr[j]) {
+                            const int slot = atomicAdd(&bcnt[j], 1);
+                            if (slot < VB) {
+                                bkeys[j * VB + slot] = key;
+                                bpos[j * VB + slot] = (uint32_t)v;
                             }
                         }
                     }

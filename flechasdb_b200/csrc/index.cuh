@@ -39,6 +39,7 @@ struct fdb_index {
     fdb::DevBuf<float> fb_q, fb_d;        // queries the filter path handed to the exact pipeline
     fdb::DevBuf<uint32_t> fb_p, fb_v, fb_c, fb_probes;
     bool last_filter = false;
+    int last_scan_kind = 0;   // fdb_index_last_scan_kernel
     fdb::FilterState *filter = nullptr;   // ADC filter path (adc_filter.cu), null when not usable
     bool last_probes_exact = false;       // `probes` holds the last device batch's lists in the reference's order
     size_t last_probes_nq = 0, last_probes_nprobe = 0;

@@ -148,6 +148,84 @@ __global__ void __launch_bounds__(256) seed_round_kernel(SeedParams p) {
     }
 }
 
+// The same round for MANY SHORT problems side by side (PQ divisions of 16..64 elements: 48 x 16 at BASELINE configs[2]).
+// The per-(problem, row) state lives in [nb][n] arrays, so the kernel above -- consecutive quads = consecutive problems of
+// one row -- touches a separate 32-byte sector of w_old / w_new / indices / chosen for every 64 bytes of row it reads
+// (measured 1.6 TB/s of row bytes).  Here a CTA takes R rows x all problems: distances go to a shared-memory tile, then
+// the state is read and written with consecutive threads on consecutive rows of one problem (coalesced).
+constexpr int SEED_TILE_R = 32;
+__global__ void __launch_bounds__(256) seed_round_tile_kernel(SeedParams p) {
+    extern __shared__ float dtile[];   // [nb][R + 1]
+    constexpr int R = SEED_TILE_R;
+    if (blockIdx.x == 0) {
+        for (size_t t = threadIdx.x; t < p.nb * p.m; t += blockDim.x) {
+            const size_t b = t / p.m, e = t - b * p.m;
+            p.centroids[(b * p.k + p.round) * p.m + e] =
+                p.centre ? p.centre[b * p.m + e] : p.x[(size_t)p.ci[b] * p.ldx + p.col_off + b * p.m + e];
+        }
+    }
+    const size_t row0 = (size_t)blockIdx.x * R;
+    const int nrows = (int)min((size_t)R, p.n - row0);
+    const int nb = (int)p.nb, npairs = nrows * nb;
+    const int tq = threadIdx.x & 3, qbase = (threadIdx.x & 31) & ~3;
+#pragma unroll 4
+    for (int base = 0; base < npairs; base += 64) {
+        const int pair = base + (threadIdx.x >> 2);
+        const bool valid = pair < npairs;
+        const int r = valid ? pair / nb : 0, b = valid ? pair - r * nb : 0;
+        const float *x = p.x + (row0 + r) * p.ldx + p.col_off + (size_t)b * p.m;
+        const float *c = p.centre ? p.centre + (size_t)b * p.m : p.x + (size_t)p.ci[b] * p.ldx + p.col_off + (size_t)b * p.m;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        if (valid) {
+            for (size_t e = 4 * tq; e < p.m; e += 16) {
+                const float4 xv = *reinterpret_cast<const float4 *>(x + e);
+                const float4 cv = *reinterpret_cast<const float4 *>(c + e);
+                a0 = sq_acc(a0, xv.x, cv.x);
+                a1 = sq_acc(a1, xv.y, cv.y);
+                a2 = sq_acc(a2, xv.z, cv.z);
+                a3 = sq_acc(a3, xv.w, cv.w);
+            }
+        }
+        float s = 0.0f;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            if (tq == t) {
+                s = __fadd_rn(s, a0);
+                s = __fadd_rn(s, a1);
+                s = __fadd_rn(s, a2);
+                s = __fadd_rn(s, a3);
+            }
+            s = __shfl_sync(0xffffffffu, s, qbase + t);
+        }
+        if (valid && tq == 0) dtile[b * (R + 1) + r] = s;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < nb * R; t += blockDim.x) {
+        const int b = t / R, r = t - b * R;
+        if (r >= nrows) continue;
+        const size_t row = row0 + r, o = (size_t)b * p.n + row;
+        const float d = dtile[b * (R + 1) + r];
+        if (row == p.ci[b]) {  // chosen[ci] = true; indices[ci] = i; weight -> 0 (:203-207)
+            p.chosen[o] = 1;
+            p.indices[o] = p.round;
+            p.w_new[o] = 0.0f;
+            continue;
+        }
+        if (p.round == 0) {
+            p.indices[o] = 0;
+            p.w_new[o] = d;  // :192-196 (not chosen)
+            continue;
+        }
+        const float w = p.w_old[o];
+        if (!p.chosen[o] && d < w) {  // :208-219
+            p.w_new[o] = d;
+            p.indices[o] = p.round;
+        } else {
+            p.w_new[o] = w;
+        }
+    }
+}
+
 // ---- WeightedIndex, exact mode: the reference's sequential f32 arithmetic ---------
 // sum(): src/linalg.rs:208-235 (16 lanes, first 16 elements seed them)
 __global__ void total_init_exact_kernel(const float *w, size_t n, float *total, unsigned *flags) {
@@ -913,7 +991,11 @@ int km_seed_round(fdb_km *km, uint32_t round, int exact, const float *d_centre) 
                      ((uintptr_t)p.x % 16 == 0) && (!d_centre || (uintptr_t)d_centre % 16 == 0);
     const size_t threads = km->n * km->nb * (vec ? 4 : 1);
     const unsigned grid = (unsigned)((threads + 255) / 256);
-    if (vec) seed_round_kernel<true><<<grid, 256, 0, ctx->stream>>>(p);
+    const size_t tile_smem = km->nb * (SEED_TILE_R + 1) * sizeof(float);
+    static const bool no_tile = getenv("FDB_SEED_NO_TILE") != nullptr;
+    if (vec && km->nb >= 2 && km->m <= 64 && tile_smem <= 48 * 1024 && !no_tile)
+        seed_round_tile_kernel<<<(unsigned)((km->n + SEED_TILE_R - 1) / SEED_TILE_R), 256, tile_smem, ctx->stream>>>(p);
+    else if (vec) seed_round_kernel<true><<<grid, 256, 0, ctx->stream>>>(p);
     else seed_round_kernel<false><<<grid, 256, 0, ctx->stream>>>(p);
     ctx->launches++;
     if (exact) {

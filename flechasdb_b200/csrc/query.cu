@@ -841,6 +841,7 @@ int batch_begin(QueryBatch &b) {
     fdb_index *ix = b.ix;
     ix->scan_bytes = 0;
     ix->last_filter = false;
+    ix->last_scan_kind = 0;
     for (int i = 0; i < 4; ++i) ix->last_stats[i] = 0;
     b.filter = b.nq_total > 0 && filter_eligible(ix, b.nq_total, b.k, b.nprobe);
     if (b.filter) FDB_TRY(filter_batch_begin(ix, b.nq_total, b.nprobe));
@@ -1233,6 +1234,12 @@ int fdb_index_table(fdb_index *ix, const float *query, uint32_t partition, float
 int fdb_index_last_stats(fdb_index *ix, uint64_t out[4]) {
     ARG(ix && out, "null argument");
     for (int i = 0; i < 4; ++i) out[i] = ix->last_stats[i];
+    return FDB_OK;
+}
+
+int fdb_index_last_scan_kernel(fdb_index *ix, int *kind) {
+    ARG(ix && kind, "null argument");
+    *kind = ix->last_scan_kind;
     return FDB_OK;
 }
 

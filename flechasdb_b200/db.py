@@ -38,6 +38,14 @@ class QueryResult:
     vector_id: uuid.UUID
     vector_index: int
     squared_distance: float
+    db: object = None        # the stored database the result came from (src/db/stored.rs:603)
+
+    def get_attribute(self, key):
+        """QueryResult::get_attribute (src/db/stored.rs:621-634): loads only the attributes log of the result's
+        partition on first use"""
+        if self.db is None:
+            raise Error("InvalidContext", "the result does not belong to a stored database")
+        return self.db.get_attribute_in_partition(self.partition_index, self.vector_id, key)
 
 
 class SeedSource:
@@ -233,6 +241,7 @@ class Database:
         self._num_partitions, self._num_divisions, self._num_clusters = P, D, Cn
         self._order = None
         self._offsets = None
+        self._attribute_table = {}      # vector id (16 bytes) -> {name: str | int}
 
     def num_vectors(self):
         return self.index.num_vectors
@@ -254,6 +263,28 @@ class Database:
 
     def vector_ids(self):
         return (uuid.UUID(bytes=bytes(b)) for b in self._id_bytes)
+
+    # ---- attributes (src/db/build.rs:225-285): host-side hash maps, never on the device ----
+    def get_attribute(self, vector_id, key):
+        """Database::get_attribute (src/db/build.rs:228-245): the value (str or int) or None; fails with
+        InvalidArgs when no vector has this id"""
+        idb = vector_id.bytes if isinstance(vector_id, uuid.UUID) else bytes(vector_id)
+        if idb not in self._attribute_table:
+            # (the reference looks the id up in attribute_table only: a vector without attributes is "no such id")
+            raise _invalid_args("no such vector ID: %s" % uuid.UUID(bytes=idb))
+        return self._attribute_table[idb].get(key)
+
+    def set_attribute_at(self, i, attribute):
+        """Database::set_attribute_at (src/db/build.rs:252-285): attribute = (key, value), value a str or a u64;
+        replaces an existing value; InvalidArgs when i is out of bounds"""
+        if not 0 <= int(i) < len(self._id_bytes):
+            raise _invalid_args("vector index out of bounds: %d" % i)
+        key, value = attribute
+        if not isinstance(value, str):
+            value = int(value)
+            if not 0 <= value < (1 << 64):
+                raise _invalid_args("attribute value does not fit a u64: %d" % value)
+        self._attribute_table.setdefault(bytes(self._id_bytes[int(i)]), {})[str(key)] = value
 
     def _layout(self):
         if self._order is None:

@@ -407,6 +407,17 @@ class Index:
         check(capi.lib().fdb_index_last_stats(self.h, u64p(st)))
         return tuple(int(x) for x in st)
 
+    SCAN_KERNELS = ("none (exact pipeline)", "fscan_kernel (query-major, f32 table per query)",
+                    "pscan_kernel (partition-major, f32 tables, 16 queries per item)",
+                    "pscan16_kernel (partition-major, 16-bit tables, 32 queries per item)",
+                    "vscan_kernel (vector-lane, packed 16-bit tables, 8 queries per 128-bit look-up)")
+
+    def last_scan_kernel(self):
+        """name of the code-scan kernel the last query call ran"""
+        kind = C.c_int()
+        check(capi.lib().fdb_index_last_scan_kernel(self.h, C.byref(kind)))
+        return self.SCAN_KERNELS[kind.value]
+
     def debug_band(self, nq, nprobe):
         """Test hook (after query_device): error bound E[q], the candidates' approximate distances and
         flat positions, their count, and the probe lists the filter path scanned."""

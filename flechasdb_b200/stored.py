@@ -264,9 +264,37 @@ def database_message(N, P, D, C, partition_ids, centroids_id, codebook_ids, attr
     return out
 
 
-def serialize_arrays(base, coarse, codebooks, offsets, codes_pm, ids16):
+def attribute_value_message(value):
+    """AttributeValue (src/db/proto.rs:15-24): oneof { string string_value = 1; uint64 uint64_value = 2; }.  A oneof
+    member is written even when it holds the default value."""
+    if isinstance(value, str):
+        b = value.encode()
+        return _tag(1, 2) + _varint(len(b)) + b
+    return _tag(2, 0) + _varint(int(value))
+
+
+def attributes_log_message(partition_id, ids16, attribute_table, attribute_names):
+    """AttributesLog of one partition (src/db/build/proto.rs:174-200): one OperationSetAttribute per (vector of the
+    partition in ascending vector index, attribute of that vector); name_index = position in the sorted names."""
+    out = _string_field(1, partition_id)
+    index = {n: i for i, n in enumerate(attribute_names)}
+    for u in ids16:
+        attrs = attribute_table.get(bytes(u)) if attribute_table else None
+        if not attrs:
+            continue
+        for name, value in attrs.items():
+            if name not in index:
+                raise Error("InvalidContext", "attribute name must be encoded: %s" % name)
+            entry = _message_field(1, _uuid_message(u)) + _uint32_field(2, index[name]) + \
+                _message_field(3, attribute_value_message(value))
+            out += _message_field(10, entry)
+    return out
+
+
+def serialize_arrays(base, coarse, codebooks, offsets, codes_pm, ids16, attribute_table=None):
     """serialize_database from plain arrays: coarse [P][N], codebooks [D][C][s], offsets [P+1],
-    codes_pm [M][D] partition-major, ids16 [M][16] uint8 partition-major.  Returns the header id."""
+    codes_pm [M][D] partition-major, ids16 [M][16] uint8 partition-major; attribute_table: {16 id bytes: {name:
+    str | int}} (src/db/build.rs:174-175).  Returns the header id."""
     coarse = np.ascontiguousarray(coarse, np.float32)
     codebooks = np.ascontiguousarray(codebooks, np.float32)
     P, N = coarse.shape
@@ -279,8 +307,13 @@ def serialize_arrays(base, coarse, codebooks, offsets, codes_pm, ids16):
         partition_ids.append(_persist(base, "partitions", msg, True))
     centroids_id = _persist(base, "partitions", vector_set_message(coarse), False)
     codebook_ids = [_persist(base, "codebooks", vector_set_message(codebooks[d]), False) for d in range(D)]
-    log_ids = [_persist(base, "attributes", _string_field(1, pid), True) for pid in partition_ids]
-    return _persist(base, "", database_message(N, P, D, C, partition_ids, centroids_id, codebook_ids, log_ids), True)
+    # get_sorted_attribute_names (src/db/build/proto.rs:149-158): a BTreeSet, i.e. sorted by bytes
+    names = sorted({n for a in (attribute_table or {}).values() for n in a}, key=lambda n: n.encode())
+    log_ids = []
+    for p, pid in enumerate(partition_ids):
+        lo, hi = int(offsets[p]), int(offsets[p + 1])
+        log_ids.append(_persist(base, "attributes", attributes_log_message(pid, ids16[lo:hi], attribute_table, names), True))
+    return _persist(base, "", database_message(N, P, D, C, partition_ids, centroids_id, codebook_ids, log_ids, names), True)
 
 
 def serialize_database(db, base):
@@ -289,15 +322,24 @@ def serialize_database(db, base):
     coarse, _ = db.ckm.get()
     cbs, _ = db.pkm.get()
     off, order, codes = db.index.layout(order=True)
-    return serialize_arrays(base, coarse[0], cbs, off, codes, db._id_bytes[order])
+    return serialize_arrays(base, coarse[0], cbs, off, codes, db._id_bytes[order], db._attribute_table)
 
 
 class StoredArrays:
     """what stored::Database holds after all lazy loads"""
 
-    def __init__(self, N, P, D, C, coarse, codebooks, offsets, codes_pm, ids16):
+    def __init__(self, N, P, D, C, coarse, codebooks, offsets, codes_pm, ids16, attribute_names=(), attribute_table=None):
         self.vector_size, self.num_partitions, self.num_divisions, self.num_codes = N, P, D, C
         self.coarse, self.codebooks, self.offsets, self.codes_pm, self.ids16 = coarse, codebooks, offsets, codes_pm, ids16
+        self.attribute_names = list(attribute_names)
+        self.attribute_table = attribute_table if attribute_table is not None else {}
+
+    def get_attribute(self, vector_id, key):
+        """stored::Database::get_attribute (src/db/stored.rs:118-131) once everything is loaded"""
+        idb = vector_id.bytes if isinstance(vector_id, uuid.UUID) else bytes(vector_id)
+        if idb not in self.attribute_table:
+            raise Error("InvalidArgs", "no such vector ID: %s" % uuid.UUID(bytes=idb))
+        return self.attribute_table[idb].get(key)
 
     def vector_id(self, partition_index, vector_index):
         return uuid.UUID(bytes=bytes(self.ids16[int(self.offsets[partition_index]) + vector_index]))
@@ -370,7 +412,15 @@ def load_database(base, path):
         offsets.append(offsets[-1] + n_p)
     codes_pm = np.concatenate(codes) if codes else np.zeros((0, D), np.uint32)
     ids16 = np.concatenate(ids) if ids else np.zeros((0, 16), np.uint8)
-    return StoredArrays(N, P, D, C, coarse.reshape(P, N), cbs, np.array(offsets, np.uint64), codes_pm, ids16)
+    # load_attribute_table (src/db/stored.rs:173-178): every partition's log; vectors without attributes get empty maps
+    log_ids, names = strs(13), strs(14)
+    table = {}
+    for p in range(min(P, len(log_ids))):
+        for idb, name, value in load_attributes_log(base, log_ids[p], partition_ids[p], p, names):
+            table.setdefault(idb, {})[name] = value
+    for row in ids16:
+        table.setdefault(bytes(row), {})
+    return StoredArrays(N, P, D, C, coarse.reshape(P, N), cbs, np.array(offsets, np.uint64), codes_pm, ids16, names, table)
 
 
 def load_header(base, path):
@@ -407,7 +457,41 @@ def load_header(base, path):
         if data.size != C * s:
             raise Error("InvalidData", "codebook %d has %d elements, expected %d" % (d, data.size, C * s))
         cbs[d] = data.reshape(C, s)
-    return N, P, D, C, coarse.reshape(P, N), cbs, partition_ids
+    return N, P, D, C, coarse.reshape(P, N), cbs, partition_ids, strs(13), strs(14)
+
+
+def parse_attribute_value(buf):
+    """AttributeValue -> str | int (src/db/proto.rs:26-37); InvalidData when neither member is present"""
+    f = parse(buf)
+    if 1 in f:
+        return f[1][-1][1].decode()
+    if 2 in f:
+        return int(f[2][-1][1])
+    raise Error("InvalidData", "missing attribute value")
+
+
+def load_attributes_log(base, log_id, partition_id, partition_index, attribute_names):
+    """the entries of one AttributesLog as (16 id bytes, name, value), validated like load_attributes_log
+    (src/db/stored.rs:185-249)"""
+    f = parse(_open(base, "attributes/%s.%s" % (log_id, EXT), True))
+    got = f[1][0][1].decode() if 1 in f else ""
+    if got != partition_id:
+        raise Error("InvalidData", "inconsistent partition IDs: %s vs %s" % (got, partition_id))
+    out = []
+    for i, (_, m) in enumerate(f.get(10, [])):
+        e = parse(m)
+        ni = int(e[2][0][1]) if 2 in e else 0
+        if ni >= len(attribute_names):
+            raise Error("InvalidData", "attribute name index out of bounds: %d" % ni)
+        if 1 not in e:
+            raise Error("InvalidData", "attributes log[%d, %d]: missing vector ID" % (partition_index, i))
+        if 3 not in e:
+            raise Error("InvalidData", "attributes log[%d, %d]: missing value" % (partition_index, i))
+        g = parse(e[1][0][1])
+        upper = struct.unpack("<Q", g[1][0][1])[0] if 1 in g else 0
+        lower = struct.unpack("<Q", g[2][0][1])[0] if 2 in g else 0
+        out.append((struct.pack(">QQ", upper, lower), attribute_names[ni], parse_attribute_value(e[3][0][1])))
+    return out
 
 
 def load_partition(base, partition_id, p, N, D, C):
@@ -441,7 +525,8 @@ class StoredDatabase:
     read (and its codes uploaded, fdb_index_set_partition) when a query first probes it (get_partition,
     src/db/stored.rs:269-293)."""
 
-    def __init__(self, ctx, base, N, P, D, C, coarse, codebooks, partition_ids):
+    def __init__(self, ctx, base, N, P, D, C, coarse, codebooks, partition_ids, attributes_log_ids=(),
+                 attribute_names=()):
         from .engine import Index
         if C > 256:
             raise Error("InvalidData", "num_codes > 256 is not supported by the u8 device layout")
@@ -450,6 +535,10 @@ class StoredDatabase:
         self.index = Index.create_lazy(ctx, coarse, codebooks)
         self.ids = [None] * P
         self.partition_loads = 0
+        # attributes stay on the host (src/db/stored.rs:53-56): one log per partition, loaded on first use
+        self.attributes_log_ids, self.attribute_names = list(attributes_log_ids), list(attribute_names)
+        self.attributes_log_load_flags = [False] * P
+        self.attribute_table = None
 
     @classmethod
     def load_database(cls, ctx, base, path):
@@ -462,6 +551,44 @@ class StoredDatabase:
             self.index.set_partition(p, codes.astype(np.uint8))
             self.ids[p] = ids
             self.partition_loads += 1
+
+    # ---- attributes (src/db/stored.rs:108-260) ----------------------------------------------------------------
+    def get_attribute(self, vector_id, key):
+        """Database::get_attribute: loads every attributes log on the first call; None when the vector exists but
+        has no such attribute; InvalidArgs when no vector has this id"""
+        if self.attribute_table is None:
+            for p in range(self.num_partitions):
+                self.load_attributes_log(p)
+        return self._get_attribute_internal(vector_id, key)
+
+    def get_attribute_in_partition(self, partition_index, vector_id, key):
+        self.load_attributes_log(partition_index)
+        return self._get_attribute_internal(vector_id, key)
+
+    def _get_attribute_internal(self, vector_id, key):
+        idb = vector_id.bytes if isinstance(vector_id, uuid.UUID) else bytes(vector_id)
+        attrs = (self.attribute_table or {}).get(idb)
+        if attrs is None:
+            raise Error("InvalidArgs", "no such vector ID: %s" % uuid.UUID(bytes=idb))
+        return attrs.get(key)
+
+    def load_attributes_log(self, p):
+        """load_attributes_log (src/db/stored.rs:185-260): also loads the partition, whose vector ids get empty
+        attribute maps so that get_attribute does not fail for a vector without attributes"""
+        if self.attributes_log_load_flags[p]:
+            return
+        self._get_partition(p)
+        if p >= len(self.attributes_log_ids):
+            raise Error("InvalidData", "no attributes log for partition %d" % p)
+        entries = load_attributes_log(self.base, self.attributes_log_ids[p], self.partition_ids[p], p,
+                                      self.attribute_names)
+        if self.attribute_table is None:
+            self.attribute_table = {}
+        for idb, name, value in entries:
+            self.attribute_table.setdefault(idb, {})[name] = value      # the last set operation wins
+        for row in self.ids[p]:
+            self.attribute_table.setdefault(bytes(row), {})
+        self.attributes_log_load_flags[p] = True
 
     def query(self, v, k, nprobe, event=lambda e: None):
         """stored::Database::query_with_events (src/db/stored.rs:331-389), QueryEvent order included"""
@@ -478,7 +605,7 @@ class StoredDatabase:
         p, vi, d, c = self.index.query(v, k, nprobe, capi.QUERY_STORED)
         event(("StartingResultSelection",))
         out = [QueryResult(int(p[0, i]), uuid.UUID(bytes=bytes(self.ids[int(p[0, i])][int(vi[0, i])])), int(vi[0, i]),
-                           float(d[0, i])) for i in range(int(c[0]))]
+                           float(d[0, i]), self) for i in range(int(c[0]))]
         event(("FinishedResultSelection",))
         return out
 

@@ -132,6 +132,27 @@ def test_seeding_with_fixed_seeds_bit_exact(eng, ctx, oracle, n, m, k):
     vs.close()
 
 
+@pytest.mark.parametrize("n,m,nb,k", [(1000, 16, 5, 7), (4100, 32, 3, 20), (333, 64, 2, 9), (70, 16, 48, 5)])
+def test_seeding_of_many_short_problems_side_by_side(eng, ctx, oracle, n, m, nb, k):
+    """seed_round_tile_kernel (divisions of 16..64 elements side by side, a CTA per 32 rows x all divisions):
+    weights / indices / centroids of every division equal the oracle's, ragged last tile included; the
+    one-quad-per-pair kernel (FDB_SEED_NO_TILE is read once per process, so it is compared through the oracle only)."""
+    x = data(oracle, n, m * nb)
+    rng = np.random.default_rng(12)
+    chosen = np.stack([rng.choice(n, k, replace=False) for _ in range(nb)]).astype(np.uint32)
+    vs = eng.VectorSet.upload(ctx, x)
+    km = eng.KMeans(vs, k, col_off=0, dim=m, nb=nb)
+    km.seed_chosen(chosen)
+    cent, idx = km.get()
+    w = km.weights()
+    for b in range(nb):
+        rc, want_c, want_i, want_w, _ = oracle.kmeans_init(x, k, int(chosen[b, 0]), chosen=chosen[b, 1:], off=b * m, dim=m)
+        assert rc == 0
+        assert (cent[b] == want_c).all() and (idx[b] == want_i).all() and (w[b] == want_w).all(), b
+    km.close()
+    vs.close()
+
+
 @pytest.mark.parametrize("n,m,k", [(4000, 64, 30), (900, 20, 8)])
 def test_seeding_exact_sampler_follows_the_same_draws(eng, ctx, oracle, n, m, k):
     """exact mode reproduces WeightedIndex (running f32 total, cumulative scan) bit for bit."""
@@ -751,6 +772,33 @@ def test_vector_lane_scan_equals_exact_pipeline_on_a_large_batch(eng, ctx, oracl
         bad = np.nonzero((g != w).reshape(nq, -1).any(axis=1))[0]
         assert len(bad) == 0, (name, len(bad), bad[:8], g[bad[:2]], w[bad[:2]])
     ix.close()
+
+
+@pytest.mark.parametrize("two_pass_max", ["0", "1000000"])
+def test_vector_lane_scan_cold_start_schemes(eng, ctx, oracle, monkeypatch, two_pass_max):
+    """The two cold starts of vscan_kernel -- doubling rounds (FDB_VSCAN_2PASS_MAX=0) and the two-pass start (lane
+    minima -> threshold -> one round) -- give the oracle's results: short lists, lists of fewer vectors than a
+    candidate list holds, and duplicated code vectors (every sum shared by many vectors: overflowing buffers,
+    retries, hand-back to the exact pipeline)."""
+    monkeypatch.setenv("FDB_FILTER_SCAN", "vector")
+    monkeypatch.setenv("FDB_VSCAN_2PASS_MAX", two_pass_max)
+    for (N, P, D, Cn, M, k, nprobe, nq, dup) in [
+        (1536, 100, 12, 256, 30000, 10, 5, 700, False),
+        (64, 9, 4, 256, 60, 5, 9, 64, False),
+        (96, 16, 12, 256, 80000, 10, 3, 200, False),      # 5 000-vector lists: below / above the two-pass limit
+        (64, 8, 4, 64, 3000, 6, 4, 64, True),
+        (64, 4, 8, 16, 40000, 10, 2, 100, True),          # 10 000-vector lists of duplicates
+    ]:
+        coarse, cbs, off, codes = random_index(oracle, N, P, D, Cn, M, dup=dup)
+        ix = eng.Index.create(ctx, coarse, cbs, off, codes.astype(np.uint8))
+        oix = oracle.QueryIndex(coarse, cbs, off, codes)
+        q = data(oracle, nq, N, SEED + 93)
+        for mode in (0, 1):
+            fast, exact, cand, scanned = _check_query(ix, oix, q, k, nprobe, mode)
+            assert fast + exact == nq
+            if not dup:
+                assert fast >= 0.9 * nq, (fast, exact)
+        ix.close()
 
 
 def test_forced_scan_mode_fails_loudly_when_the_shape_is_not_taken(eng, ctx, oracle, monkeypatch):

@@ -161,3 +161,46 @@ def test_a_code_beyond_num_codes_is_invalid_data(tmp_path):
     tool, subprocess = _tool()
     rd = subprocess.run([tool, "read", base, h + ".binpb"], capture_output=True, text=True)
     assert rd.returncode == 1 and "holds the code" in rd.stderr
+
+
+def test_attributes_log_wire_bytes_and_round_trip(tmp_path):
+    """AttributeValue / OperationSetAttribute / AttributesLog (src/protos/database.proto:92-123) byte for byte against
+    hand-derived answers, sorted attribute names in the header (src/db/build/proto.rs:149-158), and
+    get_attribute's semantics after load (src/db/stored.rs:118-260)."""
+    # oneof members are written even when they hold the default value
+    assert stored.attribute_value_message("ab") == bytes([0x0A, 2]) + b"ab"
+    assert stored.attribute_value_message("") == bytes([0x0A, 0])
+    assert stored.attribute_value_message(300) == bytes([0x10, 0xAC, 0x02])
+    assert stored.attribute_value_message(0) == bytes([0x10, 0x00])
+    assert stored.parse_attribute_value(stored.attribute_value_message(0x123456789ABCDEF0)) == 0x123456789ABCDEF0   # src/db/proto.rs:63-76
+    assert stored.parse_attribute_value(stored.attribute_value_message("string")) == "string"
+    uid = bytes(range(1, 17))
+    log = stored.attributes_log_message("pid", [uid], {uid: {"b": 7}}, ["a", "b"])
+    uuid_msg = bytes([0x09]) + bytes(range(8, 0, -1)) + bytes([0x11]) + bytes(range(16, 8, -1))
+    entry = bytes([0x0A, len(uuid_msg)]) + uuid_msg + bytes([0x10, 1]) + bytes([0x1A, 2, 0x10, 7])
+    assert log == bytes([0x0A, 3]) + b"pid" + bytes([0x52, len(entry)]) + entry
+
+    coarse, cbs, off, codes, ids = _arrays(4, C=16)
+    table = {bytes(ids[0]): {"title": "first", "year": 2023}, bytes(ids[5]): {"year": 0, "empty": ""},
+             bytes(ids[int(off[-1]) - 1]): {"title": "last"}}
+    base = str(tmp_path / "attrs")
+    h = stored.serialize_arrays(base, coarse, cbs, off, codes, ids, table)
+    got = stored.load_database(base, h + ".binpb")
+    assert got.attribute_names == ["empty", "title", "year"]
+    assert got.get_attribute(bytes(ids[0]), "title") == "first" and got.get_attribute(bytes(ids[0]), "year") == 2023
+    assert got.get_attribute(bytes(ids[5]), "year") == 0 and got.get_attribute(bytes(ids[5]), "empty") == ""
+    assert got.get_attribute(bytes(ids[5]), "title") is None
+    assert got.get_attribute(bytes(ids[1]), "title") is None          # a vector without attributes exists
+    with pytest.raises(stored.Error) as e:
+        got.get_attribute(bytes(16), "title")
+    assert e.value.kind == "InvalidArgs" and "no such vector ID" in str(e.value)
+    # a log that names another partition is InvalidData (src/db/stored.rs:196-202)
+    hdr = stored.parse(stored._open(base, h + ".binpb", True))
+    pids = [v.decode() for _, v in hdr[10]]
+    lids = [v.decode() for _, v in hdr[13]]
+    with pytest.raises(stored.Error) as e:
+        stored.load_attributes_log(base, lids[0], pids[1], 1, got.attribute_names)
+    assert e.value.kind == "InvalidData" and "inconsistent partition IDs" in str(e.value)
+    with pytest.raises(stored.Error) as e:                             # name index past the header's list
+        stored.load_attributes_log(base, lids[0], pids[0], 0, [])
+    assert e.value.kind == "InvalidData" and "out of bounds" in str(e.value)
