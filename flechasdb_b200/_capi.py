@@ -108,7 +108,7 @@ SIGNATURES = {
     "fdb_index_set_timing": (C.c_int, [VP, C.c_int]),
     "fdb_index_last_timing": (C.c_int, [VP, F32P, U64P]),
     "fdb_index_last_stats": (C.c_int, [VP, U64P]),
-    "fdb_index_last_scan_kernel": (C.c_int, [VP, C.POINTER(C.c_int)]),
+    "fdb_index_last_scan_kernel": (C.c_int, [VP, C.POINTER(C.c_int), F32P]),
     "fdb_index_debug_band": (C.c_int, [VP, SZ, SZ, F32P, F32P, U32P, U32P, U32P]),
     "fdb_comm_unique_id": (C.c_int, [U8P]),
     "fdb_comm_create": (C.c_int, [VP, C.c_int, C.c_int, U8P, C.POINTER(VP)]),

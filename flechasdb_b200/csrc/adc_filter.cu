@@ -1727,7 +1727,7 @@ int filter_prepare(fdb_index *ix) {
     if (const char *e = getenv("FDB_FILTER_CHUNK_Q")) fs->chunk_q = (size_t)std::max(1L, atol(e));
     // short lists: records (codes + bv) instead of a table per probed list
     const char *layout = getenv("FDB_FILTER_LAYOUT");  // "records" / "tables" override the heuristic
-    bool records = ix->M < (size_t)1.5 * D * C * P;
+    bool records = 2 * ix->M < 3 * D * C * P;   // M / P < 1.5 D C: short lists
     if (layout && !strcmp(layout, "records")) records = true;
     if (layout && !strcmp(layout, "tables")) records = false;
     if (records && ix->M > 0) {
@@ -2150,7 +2150,9 @@ int filter_query(fdb_index *ix, const float *d_q, size_t q_base, size_t nq, size
         sp.hard = sl->hard.p;
         sp.counters = sl->counters.p;
         if (!use_pscan) {
+            FDB_TRY(ix->kev_mark());
             scan<<<(unsigned)nc, FS_WARPS * 32, smem, st>>>(sp);
+            FDB_TRY(ix->kev_mark());
             ctx->launches++;
             FDB_CHECK_LAUNCH();
             continue;
@@ -2208,8 +2210,10 @@ int filter_query(fdb_index *ix, const float *d_q, size_t q_base, size_t nq, size
         }
         const size_t ctas = use_vscan ? (size_t)ctx->sm_count * vscan_ctas_per_sm(D) : (size_t)ctx->sm_count;
         const unsigned pgrid = (unsigned)std::min<size_t>(pscan_items_bound(ix, npairs, pj), ctas);
+        FDB_TRY(ix->kev_mark());
         if (use_vscan) vscan<<<pgrid, VWARPS * 32, psmem, st>>>(pp, vx);
         else pscan<<<pgrid, PW * 32, psmem, st>>>(pp);
+        FDB_TRY(ix->kev_mark());
         PMergeParams mp;
         mp.probes = d_probes;
         mp.part_off = ix->part_off.p;

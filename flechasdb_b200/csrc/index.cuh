@@ -40,6 +40,20 @@ struct fdb_index {
     fdb::DevBuf<uint32_t> fb_p, fb_v, fb_c, fb_probes;
     bool last_filter = false;
     int last_scan_kind = 0;   // fdb_index_last_scan_kernel
+    // timing mode: events around the code-scan kernel itself (its launches of the last call, summed)
+    std::vector<cudaEvent_t> kev;
+    size_t kev_used = 0;
+    float scan_kernel_ms = 0.f;
+    int kev_mark() {
+        if (!timing) return FDB_OK;
+        if (kev_used == kev.size()) {
+            cudaEvent_t e;
+            FDB_CUDA(cudaEventCreate(&e));
+            kev.push_back(e);
+        }
+        FDB_CUDA(cudaEventRecord(kev[kev_used++], ctx->stream));
+        return FDB_OK;
+    }
     fdb::FilterState *filter = nullptr;   // ADC filter path (adc_filter.cu), null when not usable
     bool last_probes_exact = false;       // `probes` holds the last device batch's lists in the reference's order
     size_t last_probes_nq = 0, last_probes_nprobe = 0;
@@ -71,7 +85,13 @@ struct EventLog {
     }
     int finish() {
         for (int i = 0; i < 6; ++i) ix->phase_ms[i] = 0.f;
+        ix->scan_kernel_ms = 0.f;
         if (!ix->timing) return FDB_OK;
+        for (size_t i = 0; i + 1 < ix->kev_used; i += 2) {
+            float ms = 0.f;
+            FDB_CUDA(cudaEventElapsedTime(&ms, ix->kev[i], ix->kev[i + 1]));
+            ix->scan_kernel_ms += ms;
+        }
         for (size_t i = 0; i + 1 < marks.size(); ++i) {
             if (marks[i].first < 0) continue;
             float ms = 0.f;

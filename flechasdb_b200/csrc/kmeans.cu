@@ -167,61 +167,79 @@ __global__ void __launch_bounds__(256) seed_round_tile_kernel(SeedParams p) {
     const size_t row0 = (size_t)blockIdx.x * R;
     const int nrows = (int)min((size_t)R, p.n - row0);
     const int nb = (int)p.nb, npairs = nrows * nb;
-    const int tq = threadIdx.x & 3, qbase = (threadIdx.x & 31) & ~3;
-#pragma unroll 4
-    for (int base = 0; base < npairs; base += 64) {
-        const int pair = base + (threadIdx.x >> 2);
-        const bool valid = pair < npairs;
-        const int r = valid ? pair / nb : 0, b = valid ? pair - r * nb : 0;
-        const float *x = p.x + (row0 + r) * p.ldx + p.col_off + (size_t)b * p.m;
-        const float *c = p.centre ? p.centre + (size_t)b * p.m : p.x + (size_t)p.ci[b] * p.ldx + p.col_off + (size_t)b * p.m;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        if (valid) {
-            for (size_t e = 4 * tq; e < p.m; e += 16) {
-                const float4 xv = *reinterpret_cast<const float4 *>(x + e);
-                const float4 cv = *reinterpret_cast<const float4 *>(c + e);
-                a0 = sq_acc(a0, xv.x, cv.x);
-                a1 = sq_acc(a1, xv.y, cv.y);
-                a2 = sq_acc(a2, xv.z, cv.z);
-                a3 = sq_acc(a3, xv.w, cv.w);
-            }
-        }
-        float s = 0.0f;
+    // One THREAD per (row, problem): its 16 lanes of the reference's dot (src/linalg.rs:12-40) are 16 registers --
+    // no shuffles, a fifth of the instructions of the quad-per-pair kernel.  Consecutive threads take consecutive
+    // problems of a row, so a warp's loads cover 32 x m contiguous floats (every sector is used, through L1).
+    const int blocks16 = (int)(p.m >> 4);
+#pragma unroll 2
+    for (int pair = threadIdx.x; pair < npairs; pair += blockDim.x) {
+        const int r = pair / nb, b = pair - r * nb;
+        const float4 *x4 = reinterpret_cast<const float4 *>(p.x + (row0 + r) * p.ldx + p.col_off + (size_t)b * p.m);
+        const float4 *c4 = reinterpret_cast<const float4 *>(
+            p.centre ? p.centre + (size_t)b * p.m : p.x + (size_t)p.ci[b] * p.ldx + p.col_off + (size_t)b * p.m);
+        float acc[16];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            if (tq == t) {
-                s = __fadd_rn(s, a0);
-                s = __fadd_rn(s, a1);
-                s = __fadd_rn(s, a2);
-                s = __fadd_rn(s, a3);
+        for (int j = 0; j < 16; ++j) acc[j] = 0.0f;
+        for (int blk = 0; blk < blocks16; ++blk) {
+            float4 xv[4], cv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) xv[i] = x4[4 * blk + i];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) cv[i] = c4[4 * blk + i];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                acc[4 * i + 0] = sq_acc(acc[4 * i + 0], xv[i].x, cv[i].x);
+                acc[4 * i + 1] = sq_acc(acc[4 * i + 1], xv[i].y, cv[i].y);
+                acc[4 * i + 2] = sq_acc(acc[4 * i + 2], xv[i].z, cv[i].z);
+                acc[4 * i + 3] = sq_acc(acc[4 * i + 3], xv[i].w, cv[i].w);
             }
-            s = __shfl_sync(0xffffffffu, s, qbase + t);
         }
-        if (valid && tq == 0) dtile[b * (R + 1) + r] = s;
+        float sum = 0.0f;   // sum_naive over the 16 accumulators, src/linalg.rs:39
+#pragma unroll
+        for (int j = 0; j < 16; ++j) sum = __fadd_rn(sum, acc[j]);
+        dtile[b * (R + 1) + r] = sum;
     }
     __syncthreads();
-    for (int t = threadIdx.x; t < nb * R; t += blockDim.x) {
-        const int b = t / R, r = t - b * R;
-        if (r >= nrows) continue;
-        const size_t row = row0 + r, o = (size_t)b * p.n + row;
-        const float d = dtile[b * (R + 1) + r];
-        if (row == p.ci[b]) {  // chosen[ci] = true; indices[ci] = i; weight -> 0 (:203-207)
-            p.chosen[o] = 1;
-            p.indices[o] = p.round;
-            p.w_new[o] = 0.0f;
-            continue;
+    // state update, consecutive threads on consecutive rows of one problem; V outputs per thread and step, their
+    // loads first
+    constexpr int V = 4;
+    const int nout = nb * R;
+    for (int t0 = threadIdx.x; t0 < nout; t0 += blockDim.x * V) {
+        float w[V];
+        uint8_t ch[V];
+        uint32_t ci[V];
+        size_t o[V];
+        bool act[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const int t = t0 + v * (int)blockDim.x;
+            const int b = t / R, r = t - b * R;
+            act[v] = t < nout && r < nrows;
+            o[v] = act[v] ? (size_t)b * p.n + row0 + r : 0;
+            ci[v] = act[v] ? p.ci[b] : 0u;
+            w[v] = (act[v] && p.round != 0) ? p.w_old[o[v]] : 0.0f;
+            ch[v] = (act[v] && p.round != 0) ? p.chosen[o[v]] : (uint8_t)0;
         }
-        if (p.round == 0) {
-            p.indices[o] = 0;
-            p.w_new[o] = d;  // :192-196 (not chosen)
-            continue;
-        }
-        const float w = p.w_old[o];
-        if (!p.chosen[o] && d < w) {  // :208-219
-            p.w_new[o] = d;
-            p.indices[o] = p.round;
-        } else {
-            p.w_new[o] = w;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            if (!act[v]) continue;
+            const int t = t0 + v * (int)blockDim.x;
+            const int b = t / R, r = t - b * R;
+            const size_t row = row0 + r;
+            const float d = dtile[b * (R + 1) + r];
+            if (row == ci[v]) {  // chosen[ci] = true; indices[ci] = i; weight -> 0 (:203-207)
+                p.chosen[o[v]] = 1;
+                p.indices[o[v]] = p.round;
+                p.w_new[o[v]] = 0.0f;
+            } else if (p.round == 0) {
+                p.indices[o[v]] = 0;
+                p.w_new[o[v]] = d;  // :192-196 (not chosen)
+            } else if (!ch[v] && d < w[v]) {  // :208-219
+                p.w_new[o[v]] = d;
+                p.indices[o[v]] = p.round;
+            } else {
+                p.w_new[o[v]] = w[v];
+            }
         }
     }
 }

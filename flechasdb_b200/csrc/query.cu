@@ -646,6 +646,7 @@ void fdb_index_destroy(fdb_index *ix) {
     cudaSetDevice(ix->ctx->device);
     cudaStreamSynchronize(ix->ctx->stream);
     for (cudaEvent_t e : ix->events) cudaEventDestroy(e);
+    for (cudaEvent_t e : ix->kev) cudaEventDestroy(e);
     for (cudaEvent_t e : ix->copy_events) cudaEventDestroy(e);
     if (ix->copy_stream) {
         cudaStreamSynchronize(ix->copy_stream);
@@ -835,6 +836,13 @@ struct QueryBatch {
     EventLog log;
     bool overlap = false;   // slices alternate between two streams (host batches of several slices)
     size_t nslices = 1, islice = 0;
+    // host batches with page-locked outputs: a slice's results start their way back as soon as the slice is answered
+    // (they travel while the later slices are computed); the few handed-back queries are patched in at the end
+    bool early_out = false;
+    uint32_t *h_p = nullptr, *h_v = nullptr, *h_c = nullptr;
+    float *h_d = nullptr;
+    unsigned nfb = 0;                 // handed-back queries of the batch (batch_end)
+    const uint32_t *d_fb = nullptr;   // their indices (device)
 };
 
 int batch_begin(QueryBatch &b) {
@@ -842,6 +850,7 @@ int batch_begin(QueryBatch &b) {
     ix->scan_bytes = 0;
     ix->last_filter = false;
     ix->last_scan_kind = 0;
+    ix->kev_used = 0;
     for (int i = 0; i < 4; ++i) ix->last_stats[i] = 0;
     b.filter = b.nq_total > 0 && filter_eligible(ix, b.nq_total, b.k, b.nprobe);
     if (b.filter) FDB_TRY(filter_batch_begin(ix, b.nq_total, b.nprobe));
@@ -880,6 +889,13 @@ int batch_slice(QueryBatch &b, const float *d_q, size_t q_base, size_t nq, uint3
             ix->last_npairs = nq * b.nprobe;
             ix->last_stats[1] += nq;
         }
+        if (rc == FDB_OK && b.early_out && b.filter) {
+            const size_t k = b.k;
+            FDB_CUDA(cudaMemcpyAsync(b.h_p + q_base * k, d_p, nq * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            FDB_CUDA(cudaMemcpyAsync(b.h_v + q_base * k, d_v, nq * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            FDB_CUDA(cudaMemcpyAsync(b.h_d + q_base * k, d_d, nq * k * sizeof(float), cudaMemcpyDeviceToHost, st));
+            FDB_CUDA(cudaMemcpyAsync(b.h_c + q_base, d_c, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        }
     } while (0);
     ctx->stream = main_stream;
     FDB_TRY(rc);
@@ -898,6 +914,8 @@ int batch_end(QueryBatch &b, const float *d_q, uint32_t *d_p, uint32_t *d_v, flo
         unsigned nfb = 0, nhard = 0;
         FDB_TRY(filter_batch_end(ix, b.nq_total, &d_fb, &d_fbp, &nfb, &nhard));
         ix->last_filter = true;
+        b.nfb = nfb;
+        b.d_fb = d_fb;
         if (nfb) {
             cudaStream_t st = ctx->stream;
             FDB_TRY(ix->fb_q.ensure((size_t)nfb * ix->N));
@@ -1157,6 +1175,18 @@ int fdb_index_query(fdb_index *ix, const float *queries, size_t nq, size_t k, si
     QueryBatch b{ix, nq, k, nprobe, mode, false, EventLog{ix}};
     b.nslices = nslices;
     FDB_TRY(batch_begin(b));
+    {
+        // early result copies need page-locked outputs (a pageable destination would block the enqueue loop)
+        auto locked = [](const void *ptr) {
+            cudaPointerAttributes a;
+            const bool ok = cudaPointerGetAttributes(&a, ptr) == cudaSuccess && a.type == cudaMemoryTypeHost;
+            cudaGetLastError();
+            return ok;
+        };
+        b.early_out = b.overlap && pinned && !getenv("FDB_QUERY_NO_EARLY_OUT") && locked(out_partition) &&
+                      locked(out_vector_index) && locked(out_sqdist) && locked(out_count);
+        b.h_p = out_partition, b.h_v = out_vector_index, b.h_d = out_sqdist, b.h_c = out_count;
+    }
     for (size_t i = 0; i < nslices; ++i) {
         const size_t q0 = bounds[i], nc = bounds[i + 1] - q0;
         if (!pinned) FDB_TRY(copy_slice(i));
@@ -1170,11 +1200,34 @@ int fdb_index_query(fdb_index *ix, const float *queries, size_t nq, size_t k, si
     const double t1c = trace ? now() : 0.0;
     FDB_TRY(batch_end(b, ix->q_dev.p, ix->out_p.p, ix->out_v.p, ix->out_d.p, ix->out_c.p));
     const double t2 = trace ? now() : 0.0;
-    FDB_CUDA(cudaMemcpyAsync(out_partition, ix->out_p.p, nq * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    FDB_CUDA(cudaMemcpyAsync(out_vector_index, ix->out_v.p, nq * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    FDB_CUDA(cudaMemcpyAsync(out_sqdist, ix->out_d.p, nq * k * sizeof(float), cudaMemcpyDeviceToHost, st));
-    FDB_CUDA(cudaMemcpyAsync(out_count, ix->out_c.p, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    const int rc = finish_query(ctx);
+    int rc;
+    if (b.early_out) {
+        // the slices' results are on their way (or there); only the handed-back queries' rows follow
+        const size_t nfb = b.nfb;
+        std::vector<uint32_t> fq(nfb), fp(nfb * k), fv(nfb * k), fc(nfb);
+        std::vector<float> fd(nfb * k);
+        if (nfb) {
+            FDB_CUDA(cudaMemcpyAsync(fq.data(), b.d_fb, nfb * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            FDB_CUDA(cudaMemcpyAsync(fp.data(), ix->fb_p.p, nfb * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            FDB_CUDA(cudaMemcpyAsync(fv.data(), ix->fb_v.p, nfb * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            FDB_CUDA(cudaMemcpyAsync(fd.data(), ix->fb_d.p, nfb * k * sizeof(float), cudaMemcpyDeviceToHost, st));
+            FDB_CUDA(cudaMemcpyAsync(fc.data(), ix->fb_c.p, nfb * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        }
+        rc = finish_query(ctx);
+        for (size_t i = 0; i < nfb && rc == FDB_OK; ++i) {
+            const size_t q = fq[i];
+            memcpy(out_partition + q * k, fp.data() + i * k, k * sizeof(uint32_t));
+            memcpy(out_vector_index + q * k, fv.data() + i * k, k * sizeof(uint32_t));
+            memcpy(out_sqdist + q * k, fd.data() + i * k, k * sizeof(float));
+            out_count[q] = fc[i];
+        }
+    } else {
+        FDB_CUDA(cudaMemcpyAsync(out_partition, ix->out_p.p, nq * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        FDB_CUDA(cudaMemcpyAsync(out_vector_index, ix->out_v.p, nq * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        FDB_CUDA(cudaMemcpyAsync(out_sqdist, ix->out_d.p, nq * k * sizeof(float), cudaMemcpyDeviceToHost, st));
+        FDB_CUDA(cudaMemcpyAsync(out_count, ix->out_c.p, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        rc = finish_query(ctx);
+    }
     if (trace)
         fprintf(stderr, "[fdb query] nq=%zu slices=%zu: enqueue %.3f ms, copies done +%.3f, batch end (sync + hand-back) +%.3f, "
                         "results +%.3f, total %.3f ms\n", nq, nslices, t1 - t0, t1c - t1, t2 - t1c, now() - t2, now() - t0);
@@ -1237,9 +1290,10 @@ int fdb_index_last_stats(fdb_index *ix, uint64_t out[4]) {
     return FDB_OK;
 }
 
-int fdb_index_last_scan_kernel(fdb_index *ix, int *kind) {
+int fdb_index_last_scan_kernel(fdb_index *ix, int *kind, float *kernel_ms) {
     ARG(ix && kind, "null argument");
     *kind = ix->last_scan_kind;
+    if (kernel_ms) *kernel_ms = ix->scan_kernel_ms;
     return FDB_OK;
 }
 

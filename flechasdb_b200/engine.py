@@ -415,8 +415,14 @@ class Index:
     def last_scan_kernel(self):
         """name of the code-scan kernel the last query call ran"""
         kind = C.c_int()
-        check(capi.lib().fdb_index_last_scan_kernel(self.h, C.byref(kind)))
+        check(capi.lib().fdb_index_last_scan_kernel(self.h, C.byref(kind), None))
         return self.SCAN_KERNELS[kind.value]
+
+    def last_scan_kernel_ms(self):
+        """device milliseconds of the code-scan kernel's launches alone in the last query call (timing enabled)"""
+        kind, ms = C.c_int(), C.c_float()
+        check(capi.lib().fdb_index_last_scan_kernel(self.h, C.byref(kind), C.byref(ms)))
+        return float(ms.value)
 
     def debug_band(self, nq, nprobe):
         """Test hook (after query_device): error bound E[q], the candidates' approximate distances and

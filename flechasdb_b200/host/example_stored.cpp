@@ -41,6 +41,12 @@ int main(int argc, char **argv) {
             }
         }
         auto db = DatabaseBuilder(BlockVectorSet::chunk(ctx, data, N)).with_partitions(P).with_divisions(D).with_clusters(C).with_seed(7).build();
+        // attributes (src/db/build.rs:252-285): set on the built database, written as one log per partition
+        for (size_t i = 0; i < M; i += 3) {
+            db->set_attribute_at(i, "index", AttributeValue((uint64_t)i));
+            if (i % 2 == 0) db->set_attribute_at(i, "label", AttributeValue("vector " + std::to_string(i)));
+        }
+        db->set_attribute_at(0, "label", AttributeValue("replaced"));
         const std::string header = stored::serialize_database(*db, base);
         auto sdb = stored::Database::load_database(ctx, base, header + ".binpb");
         if (sdb->loaded_partitions() != 0) {
@@ -63,6 +69,19 @@ int main(int argc, char **argv) {
                     fprintf(stderr, "query %zu result %zu differs\n", qi, i);
                     return 1;
                 }
+            // QueryResult::get_attribute (src/db/stored.rs:621-634): what the built database holds for that vector id
+            for (const auto &r : got) {
+                size_t gi = 0;
+                while (gi < M && db->vector_ids()[gi] != r.vector_id) ++gi;
+                const AttributeValue *a = sdb->get_attribute(r, "index"), *l = sdb->get_attribute(r, "label");
+                const bool has = gi % 3 == 0;
+                const std::string label = gi == 0 ? "replaced" : "vector " + std::to_string(gi);
+                if (gi == M || (a != nullptr) != has || (a && (a->is_string || a->uint64_value != gi)) ||
+                    (l != nullptr) != (has && gi % 2 == 0) || (l && (!l->is_string || l->string_value != label))) {
+                    fprintf(stderr, "query %zu: attributes of vector %zu differ\n", qi, gi);
+                    return 1;
+                }
+            }
             if (qi == 0 && sdb->loaded_partitions() > NPROBE) {
                 fprintf(stderr, "the first query loaded %zu partitions, it probes %zu\n", sdb->loaded_partitions(), NPROBE);
                 return 1;
@@ -78,6 +97,18 @@ int main(int argc, char **argv) {
         db->query_batch(batch.data(), NQ, K, NPROBE, FDB_QUERY_STORED, part2.data(), vidx2.data(), dist2.data(), cnt2.data());
         if (part != part2 || vidx != vidx2 || dist != dist2 || cnt != cnt2) {
             fprintf(stderr, "batched stored query differs from the in-memory database\n");
+            return 1;
+        }
+        // Database::get_attribute loads every log; an unknown id is InvalidArgs
+        const AttributeValue *v0 = sdb->get_attribute(db->vector_ids()[0], "label");
+        bool threw = false;
+        try {
+            sdb->get_attribute(Uuid{}, "label");
+        } catch (const Error &e) {
+            threw = e.kind == Error::InvalidArgs;
+        }
+        if (!v0 || v0->string_value != "replaced" || !threw || sdb->loaded_partitions() != P) {
+            fprintf(stderr, "get_attribute over the whole table is wrong\n");
             return 1;
         }
         printf("STORED_OK header=%s results=%zu loaded_partitions=%zu/%zu\n", header.c_str(), checked, sdb->loaded_partitions(), P);

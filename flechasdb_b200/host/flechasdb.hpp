@@ -15,6 +15,7 @@
 #include <array>
 #include <cstdint>
 #include <functional>
+#include <map>
 #include <memory>
 #include <random>
 #include <stdexcept>
@@ -234,6 +235,23 @@ struct QueryResult {
     float squared_distance;
 };
 
+// AttributeValue { String, Uint64 } (src/db/mod.rs), Attributes = name -> value, AttributeTable = vector id -> Attributes.
+// Attributes live on the host only.
+struct AttributeValue {
+    bool is_string = false;
+    std::string string_value;
+    uint64_t uint64_value = 0;
+    AttributeValue() = default;
+    AttributeValue(const std::string &s) : is_string(true), string_value(s) {}
+    AttributeValue(const char *s) : is_string(true), string_value(s) {}
+    AttributeValue(uint64_t v) : uint64_value(v) {}
+    bool operator==(const AttributeValue &o) const {
+        return is_string == o.is_string && string_value == o.string_value && uint64_value == o.uint64_value;
+    }
+};
+using Attributes = std::map<std::string, AttributeValue>;
+using AttributeTable = std::map<Uuid, Attributes>;
+
 class Database {
   public:
     size_t num_vectors() const { return vector_ids_.size(); }
@@ -273,6 +291,20 @@ class Database {
                      uint32_t *vidx, float *dist, uint32_t *count) const {
         check(fdb_index_query(index_, queries, nq, k, nprobe, mode, part, vidx, dist, count));
     }
+    // Database::get_attribute (src/db/build.rs:228-245): null when the vector has no such attribute; InvalidArgs when
+    // no attribute was ever set for this id (the reference looks the id up in its attribute table only)
+    const AttributeValue *get_attribute(const Uuid &id, const std::string &key) const {
+        auto it = attribute_table_.find(id);
+        if (it == attribute_table_.end()) throw Error(Error::InvalidArgs, "no such vector ID");
+        auto a = it->second.find(key);
+        return a == it->second.end() ? nullptr : &a->second;
+    }
+    // Database::set_attribute_at (src/db/build.rs:252-285): replaces an existing value; InvalidArgs when i is out of bounds
+    void set_attribute_at(size_t i, const std::string &key, const AttributeValue &value) {
+        if (i >= vector_ids_.size()) throw Error(Error::InvalidArgs, "vector index out of bounds: " + std::to_string(i));
+        attribute_table_[vector_ids_[i]][key] = value;
+    }
+    const AttributeTable &attribute_table() const { return attribute_table_; }
     fdb_index *index() const { return index_; }
     // partition centroids [P][N] and codebooks [D][C][N/D] (what serialize_database writes)
     void quantisers(float *coarse, float *codebooks) const {
@@ -290,6 +322,7 @@ class Database {
     Database() = default;
     size_t vector_size_ = 0, num_partitions_ = 0, num_divisions_ = 0, num_clusters_ = 0;
     std::vector<Uuid> vector_ids_;
+    AttributeTable attribute_table_;
     std::vector<uint64_t> offsets_;
     std::vector<uint32_t> order_;
     std::unique_ptr<KMeansRun> coarse_, pq_;

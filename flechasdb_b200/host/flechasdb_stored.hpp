@@ -20,7 +20,9 @@
 #include <cstdio>
 #include <cstring>
 #include <fstream>
+#include <algorithm>
 #include <map>
+#include <set>
 #include <sstream>
 #include <sys/stat.h>
 
@@ -292,8 +294,46 @@ inline std::string vector_set_message(const float *data, size_t n, size_t vector
 
 // serialize_database (src/db/build/proto.rs:25-267) from plain arrays: coarse [P][N], codebooks [D][C][N/D],
 // offsets [P+1], codes [M][D] partition-major, ids [M] partition-major.  Returns the header id.
+inline std::string uuid_message(const Uuid &id) {   // Uuid { fixed64 upper = 1; fixed64 lower = 2 } (src/protos/mod.rs:21-27)
+    uint64_t upper = 0, lower = 0;
+    for (int i = 0; i < 8; ++i) upper = (upper << 8) | id[i], lower = (lower << 8) | id[8 + i];
+    Writer u;
+    u.fixed64_field(1, upper);
+    u.fixed64_field(2, lower);
+    return u.b;
+}
+// AttributeValue (src/db/proto.rs:15-24): a oneof member is written even when it holds the default value
+inline std::string attribute_value_message(const AttributeValue &v) {
+    Writer w;
+    if (v.is_string) w.tag(1, 2), w.varint(v.string_value.size()), w.b += v.string_value;
+    else w.tag(2, 0), w.varint(v.uint64_value);
+    return w.b;
+}
+// AttributesLog of one partition (src/db/build/proto.rs:174-200): one OperationSetAttribute per (vector of the
+// partition in ascending vector index, attribute of that vector); name_index = position in the sorted names
+inline std::string attributes_log_message(const std::string &partition_id, const Uuid *ids, size_t n,
+                                          const AttributeTable *table, const std::vector<std::string> &names) {
+    Writer w;
+    w.string_field(1, partition_id, false);
+    for (size_t v = 0; v < n && table; ++v) {
+        auto it = table->find(ids[v]);
+        if (it == table->end()) continue;
+        for (const auto &kv : it->second) {
+            const auto pos = std::lower_bound(names.begin(), names.end(), kv.first);
+            if (pos == names.end() || *pos != kv.first) throw Error(Error::InvalidContext, "attribute name must be encoded: " + kv.first);
+            Writer e;
+            e.message_field(1, uuid_message(ids[v]));
+            e.uint32_field(2, (uint32_t)(pos - names.begin()));
+            e.message_field(3, attribute_value_message(kv.second));
+            w.message_field(10, e.b);
+        }
+    }
+    return w.b;
+}
+
 inline std::string serialize_arrays(const std::string &base, size_t N, size_t P, size_t D, size_t C, const float *coarse,
-                                    const float *codebooks, const uint64_t *offsets, const uint8_t *codes, const Uuid *ids) {
+                                    const float *codebooks, const uint64_t *offsets, const uint8_t *codes, const Uuid *ids,
+                                    const AttributeTable *attributes = nullptr) {
     std::vector<std::string> partition_ids, codebook_ids, log_ids;
     for (size_t p = 0; p < P; ++p) {
         const size_t lo = offsets[p], hi = offsets[p + 1];
@@ -304,30 +344,30 @@ inline std::string serialize_arrays(const std::string &base, size_t N, size_t P,
         w.uint32_field(2, (uint32_t)D);
         w.floats_unpacked(10, coarse + p * N, N);
         w.message_field(11, enc.b);
-        for (size_t v = lo; v < hi; ++v) {   // Uuid { fixed64 upper = 1; fixed64 lower = 2 } (src/protos/mod.rs:21-27)
-            uint64_t upper = 0, lower = 0;
-            for (int i = 0; i < 8; ++i) upper = (upper << 8) | ids[v][i], lower = (lower << 8) | ids[v][8 + i];
-            Writer u;
-            u.fixed64_field(1, upper);
-            u.fixed64_field(2, lower);
-            w.message_field(12, u.b);
-        }
+        for (size_t v = lo; v < hi; ++v) w.message_field(12, uuid_message(ids[v]));
         partition_ids.push_back(persist(base, "partitions", w.b, true));
     }
     const std::string centroids_id = persist(base, "partitions", vector_set_message(coarse, P, N), false);
     const size_t s = N / D;
     for (size_t d = 0; d < D; ++d) codebook_ids.push_back(persist(base, "codebooks", vector_set_message(codebooks + d * C * s, C, s), false));
-    for (const std::string &pid : partition_ids) {
-        Writer w;
-        w.string_field(1, pid, false);
-        log_ids.push_back(persist(base, "attributes", w.b, true));
+    // get_sorted_attribute_names (src/db/build/proto.rs:149-158): a BTreeSet<String>, i.e. sorted by bytes
+    std::vector<std::string> names;
+    if (attributes) {
+        std::set<std::string> sorted;
+        for (const auto &kv : *attributes)
+            for (const auto &a : kv.second) sorted.insert(a.first);
+        names.assign(sorted.begin(), sorted.end());
     }
+    for (size_t p = 0; p < P; ++p)
+        log_ids.push_back(persist(base, "attributes",
+                                  attributes_log_message(partition_ids[p], ids + offsets[p], offsets[p + 1] - offsets[p], attributes, names), true));
     Writer h;
     h.uint32_field(1, (uint32_t)N), h.uint32_field(2, (uint32_t)P), h.uint32_field(3, (uint32_t)D), h.uint32_field(4, (uint32_t)C);
     for (const auto &x : partition_ids) h.string_field(10, x, true);
     h.string_field(11, centroids_id, false);
     for (const auto &x : codebook_ids) h.string_field(12, x, true);
     for (const auto &x : log_ids) h.string_field(13, x, true);
+    for (const auto &x : names) h.string_field(14, x, true);
     return persist(base, "", h.b, true);
 }
 
@@ -342,13 +382,13 @@ inline std::string serialize_database(const flechasdb::Database &db, const std::
     check(fdb_index_get_layout(db.index(), off.data(), order.data(), codes.data()));
     std::vector<Uuid> ids(M);
     for (size_t i = 0; i < M; ++i) ids[i] = db.vector_ids()[order[i]];
-    return serialize_arrays(base, N, P, D, C, coarse.data(), cbs.data(), off.data(), codes.data(), ids.data());
+    return serialize_arrays(base, N, P, D, C, coarse.data(), cbs.data(), off.data(), codes.data(), ids.data(), &db.attribute_table());
 }
 
 // what load_database reads (src/db/stored.rs:659-798): the header, the partition centroids, the codebooks
 struct Header {
     size_t N = 0, P = 0, D = 0, C = 0;
-    std::vector<std::string> partition_ids;
+    std::vector<std::string> partition_ids, attributes_log_ids, attribute_names;
     std::vector<float> coarse, codebooks;   // [P][N], [D][C][N/D]
 };
 inline Header read_header(const std::string &base, const std::string &path) {
@@ -369,6 +409,8 @@ inline Header read_header(const std::string &base, const std::string &path) {
         throw Error(Error::InvalidData, "num_divisions " + std::to_string(D) + " and codebook_ids.len() " + std::to_string(codebook_ids.size()) + " do not match");
     if (centroid_ids.empty()) throw Error(Error::InvalidData, "partition_centroids_id is missing");
     h.N = N, h.P = P, h.D = D, h.C = C;
+    h.attributes_log_ids = strings_of(hdr, 13);
+    h.attribute_names = strings_of(hdr, 14);
     // load_partition_centroids never calls verify() (src/db/stored.rs:729-755)
     const auto cen = parse(open_file(base, "partitions/" + centroid_ids[0] + ".binpb", false, false));
     if (uint32_of(cen, 1) != N) throw Error(Error::InvalidData, "partition centroids vector size mismatch");
@@ -418,6 +460,52 @@ inline PartitionData read_partition(const std::string &base, const std::string &
     return out;
 }
 
+// one AttributesLog, validated like load_attributes_log (src/db/stored.rs:185-249): (vector id, name, value) per entry
+struct AttributeEntry {
+    Uuid id;
+    std::string name;
+    AttributeValue value;
+};
+inline Uuid uuid_of(const std::string &bytes) {
+    const auto u = parse(bytes);
+    uint64_t upper = 0, lower = 0;
+    auto a = u.find(1), b = u.find(2);
+    if (a != u.end()) upper = a->second.value;
+    if (b != u.end()) lower = b->second.value;
+    Uuid uid;
+    for (int i = 0; i < 8; ++i) uid[i] = (uint8_t)(upper >> (56 - 8 * i)), uid[8 + i] = (uint8_t)(lower >> (56 - 8 * i));
+    return uid;
+}
+inline std::vector<AttributeEntry> read_attributes_log(const std::string &base, const std::string &log_id, const std::string &partition_id,
+                                                       size_t p, const std::vector<std::string> &names) {
+    const auto f = parse(open_file(base, "attributes/" + log_id + ".binpb", true));
+    auto pid = f.find(1);
+    const std::string got = pid == f.end() ? std::string() : pid->second.bytes;
+    if (got != partition_id) throw Error(Error::InvalidData, "inconsistent partition IDs: " + got + " vs " + partition_id);
+    std::vector<AttributeEntry> out;
+    auto r = f.equal_range(10);
+    size_t i = 0;
+    for (auto it = r.first; it != r.second; ++it, ++i) {
+        const auto e = parse(it->second.bytes);
+        const uint32_t ni = uint32_of(e, 2);
+        if (ni >= names.size()) throw Error(Error::InvalidData, "attribute name index out of bounds: " + std::to_string(ni));
+        auto id = e.find(1), val = e.find(3);
+        const std::string where = "attributes log[" + std::to_string(p) + ", " + std::to_string(i) + "]: ";
+        if (id == e.end()) throw Error(Error::InvalidData, where + "missing vector ID");
+        if (val == e.end()) throw Error(Error::InvalidData, where + "missing value");
+        const auto v = parse(val->second.bytes);
+        AttributeEntry ent;
+        ent.id = uuid_of(id->second.bytes);
+        ent.name = names[ni];
+        auto sv = v.find(1), uv = v.find(2);
+        if (sv != v.end()) ent.value = AttributeValue(sv->second.bytes);
+        else if (uv != v.end()) ent.value = AttributeValue((uint64_t)uv->second.value);
+        else throw Error(Error::InvalidData, where + "missing value");
+        out.push_back(std::move(ent));
+    }
+    return out;
+}
+
 // stored::Database<f32, LocalFileSystem> (src/db/stored.rs:41-57): header, partition centroids and codebooks are
 // read by load_database; a partition (codes + vector ids) is read and uploaded when a query first probes it
 // (get_partition, src/db/stored.rs:269-293).
@@ -430,6 +518,9 @@ class Database {
         const Header h = read_header(base, path);
         db->N_ = h.N, db->P_ = h.P, db->D_ = h.D, db->C_ = h.C;
         db->partition_ids_ = h.partition_ids;
+        db->attributes_log_ids_ = h.attributes_log_ids;
+        db->attribute_names_ = h.attribute_names;
+        db->log_loaded_.assign(h.P, false);
         check(fdb_index_create_lazy(ctx->h, h.N, h.P, h.D, h.C, h.coarse.data(), h.codebooks.data(), &db->index_));
         db->ids_.resize(h.P);
         return db;
@@ -477,6 +568,31 @@ class Database {
         for (size_t i = 0; i < missing; ++i) load_partition(need[i]);
         check(fdb_index_query(index_, queries, nq, k, nprobe, FDB_QUERY_STORED, part, vidx, dist, count));
     }
+    // Database::get_attribute (src/db/stored.rs:118-131): loads every attributes log on the first call; null when the
+    // vector exists but has no such attribute, InvalidArgs when no vector has this id
+    const AttributeValue *get_attribute(const Uuid &id, const std::string &key) {
+        if (!table_loaded_) {
+            for (size_t p = 0; p < P_; ++p) load_attributes_log(p);
+            table_loaded_ = true;
+        }
+        return get_attribute_internal(id, key);
+    }
+    // QueryResult::get_attribute (src/db/stored.rs:621-634): only the log of the result's partition is loaded
+    const AttributeValue *get_attribute(const QueryResult &r, const std::string &key) {
+        load_attributes_log(r.partition_index);
+        return get_attribute_internal(r.vector_id, key);
+    }
+    // load_attributes_log (src/db/stored.rs:185-260): also loads the partition; its vectors get empty attribute maps
+    void load_attributes_log(size_t p) {
+        if (p >= P_) throw Error(Error::InvalidArgs, "partition index out of bounds");
+        if (log_loaded_[p]) return;
+        load_partition(p);
+        if (p >= attributes_log_ids_.size()) throw Error(Error::InvalidData, "no attributes log for partition " + std::to_string(p));
+        for (auto &e : read_attributes_log(base_, attributes_log_ids_[p], partition_ids_[p], p, attribute_names_))
+            attribute_table_[e.id][e.name] = e.value;      // the last set operation wins
+        for (const Uuid &id : ids_[p]) attribute_table_[id];
+        log_loaded_[p] = true;
+    }
     size_t loaded_partitions() const {
         size_t n = 0;
         for (size_t p = 0; p < P_; ++p) n += fdb_index_partition_loaded(index_, p);
@@ -490,6 +606,16 @@ class Database {
 
   private:
     Database() = default;
+    const AttributeValue *get_attribute_internal(const Uuid &id, const std::string &key) const {
+        auto it = attribute_table_.find(id);
+        if (it == attribute_table_.end()) throw Error(Error::InvalidArgs, "no such vector ID");
+        auto a = it->second.find(key);
+        return a == it->second.end() ? nullptr : &a->second;
+    }
+    std::vector<std::string> attributes_log_ids_, attribute_names_;
+    std::vector<bool> log_loaded_;
+    bool table_loaded_ = false;
+    AttributeTable attribute_table_;
     std::shared_ptr<Context> ctx_;
     std::string base_;
     size_t N_ = 0, P_ = 0, D_ = 0, C_ = 0;

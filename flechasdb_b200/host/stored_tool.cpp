@@ -1,5 +1,5 @@
 // The stored layout without a GPU (tests/test_stored_layout.py cross-checks it against the Python mirror):
-//   stored_tool write <dir> <seed> <N> <P> <D> <C> <M>   writes a database of pseudo-random arrays, prints its header id
+//   stored_tool write <dir> <seed> <N> <P> <D> <C> <M> [attrs]   writes a database of pseudo-random arrays (and attributes), prints its header id
 //   stored_tool read  <dir> <header.binpb>               reads it back (header, centroids, codebooks, every partition)
 //                                                         and prints shapes + an FNV-1a checksum of every array
 #include <cstdio>
@@ -35,7 +35,15 @@ int main(int argc, char **argv) {
             std::vector<Uuid> ids(total);
             for (auto &id : ids)
                 for (auto &b : id) b = (uint8_t)lcg(s);
-            const std::string h = stored::serialize_arrays(argv[2], N, P, D, C, coarse.data(), cbs.data(), off.data(), codes.data(), ids.data());
+            // optional 9th argument "attrs": vector i (partition-major) gets idx = i when i % 7 == 0 and name = "v<i>" when i % 5 == 0
+            AttributeTable table;
+            if (argc >= 10 && std::string(argv[9]) == "attrs")
+                for (size_t i = 0; i < total; ++i) {
+                    if (i % 7 == 0) table[ids[i]]["idx"] = AttributeValue((uint64_t)i);
+                    if (i % 5 == 0) table[ids[i]]["name"] = AttributeValue("v" + std::to_string(i));
+                }
+            const std::string h = stored::serialize_arrays(argv[2], N, P, D, C, coarse.data(), cbs.data(), off.data(), codes.data(), ids.data(),
+                                                           table.empty() ? nullptr : &table);
             printf("%s\n", h.c_str());
             return 0;
         }
@@ -51,8 +59,20 @@ int main(int argc, char **argv) {
                 for (const Uuid &u : pd.ids) hi = fnv(hi, u.data(), 16);
                 total += pd.ids.size();
             }
-            printf("N=%zu P=%zu D=%zu C=%zu M=%zu coarse=%016llx codebooks=%016llx codes=%016llx ids=%016llx\n", h.N, h.P, h.D, h.C, total,
-                   (unsigned long long)hc, (unsigned long long)hb, (unsigned long long)hk, (unsigned long long)hi);
+            // the attributes logs in file order: id bytes, name, value ("s:<string>" / "u:<number>")
+            uint64_t ha = 1469598103934665603ULL;
+            size_t entries = 0;
+            for (size_t p = 0; p < h.P && p < h.attributes_log_ids.size(); ++p)
+                for (const auto &e : stored::read_attributes_log(argv[2], h.attributes_log_ids[p], h.partition_ids[p], p, h.attribute_names)) {
+                    const std::string v = e.value.is_string ? "s:" + e.value.string_value : "u:" + std::to_string(e.value.uint64_value);
+                    ha = fnv(fnv(fnv(ha, e.id.data(), 16), e.name.data(), e.name.size()), v.data(), v.size());
+                    ++entries;
+                }
+            std::string names;
+            for (const auto &n : h.attribute_names) names += (names.empty() ? "" : ",") + n;
+            printf("N=%zu P=%zu D=%zu C=%zu M=%zu coarse=%016llx codebooks=%016llx codes=%016llx ids=%016llx attr_entries=%zu attr_names=%s attrs=%016llx\n",
+                   h.N, h.P, h.D, h.C, total, (unsigned long long)hc, (unsigned long long)hb, (unsigned long long)hk, (unsigned long long)hi,
+                   entries, names.c_str(), (unsigned long long)ha);
             return 0;
         }
     } catch (const Error &e) {

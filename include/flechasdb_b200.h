@@ -260,8 +260,11 @@ int fdb_index_last_timing(fdb_index *ix, float ms[6], uint64_t *scan_bytes);
 int fdb_index_last_stats(fdb_index *ix, uint64_t out[4]);
 /* which code-scan kernel the last fdb_index_query* call ran (the choice depends on the shape):
  * 0 none (exact pipeline only), 1 fscan_kernel (query-major), 2 pscan_kernel (partition-major, f32 tables),
- * 3 pscan16_kernel (partition-major, 16-bit tables), 4 vscan_kernel (vector-lane, packed 16-bit tables) */
-int fdb_index_last_scan_kernel(fdb_index *ix, int *kind);
+ * 3 pscan16_kernel (partition-major, 16-bit tables), 4 vscan_kernel (vector-lane, packed 16-bit tables).
+ * kernel_ms (may be NULL; timing enabled): device milliseconds of that kernel's launches alone, CUDA events on the
+ * launching stream right around them -- the code-scan PHASE of fdb_index_last_timing also holds the helpers around it
+ * (grouping of the pairs by partition, table quantisation, per-query merge of the item lists) */
+int fdb_index_last_scan_kernel(fdb_index *ix, int *kind, float *kernel_ms);
 /* test hook: the filter path's view of the nq queries of the last fdb_index_query_device call
  * (one slice): E[q] = its bound on |approximate - true| distance, the up to 32 smallest approximate
  * distances per query (ascending) with their positions in the concatenation of the probed lists,

@@ -801,6 +801,45 @@ def test_vector_lane_scan_cold_start_schemes(eng, ctx, oracle, monkeypatch, two_
         ix.close()
 
 
+def test_host_batch_with_page_locked_buffers_sends_results_early(eng, ctx, oracle, monkeypatch):
+    """fdb_index_query with registered (page-locked) query and result buffers: the batch is cut into slices, every
+    slice's results travel back while the later slices are answered, the handed-back queries (duplicated vectors:
+    exact ties) are patched in at the end -- same arrays as the plain call, and the oracle's on a sample."""
+    from flechasdb_b200 import _capi as capi
+    N, P, D, Cn, M, k, nprobe, nq = 128, 64, 8, 256, 40000, 10, 4, 6000
+    coarse, cbs, off, codes = random_index(oracle, N, P, D, Cn, M)
+    codes[1::40] = codes[0::40][:len(codes[1::40])]          # neighbours with identical codes: tied distances
+    ix = eng.Index.create(ctx, coarse, cbs, off, codes.astype(np.uint8))
+    q = data(oracle, nq, N, SEED + 95)
+    want = ix.query(q, k, nprobe)
+    fast, exact, _, _ = ix.last_stats()
+    assert exact > 0 and fast > 0.5 * nq, (fast, exact)      # some queries are handed back, most are not
+    bufs = [q.copy(), np.zeros((nq, k), np.uint32), np.zeros((nq, k), np.uint32), np.zeros((nq, k), np.float32),
+            np.zeros(nq, np.uint32)]
+    for a in bufs:
+        ctx.host_register(a)
+    try:
+        for _ in range(2):
+            for a in bufs[1:]:
+                a[...] = 0
+            capi.check(capi.lib().fdb_index_query(ix.h, capi.f32p(bufs[0]), nq, k, nprobe, capi.QUERY_STORED,
+                                                  capi.u32p(bufs[1]), capi.u32p(bufs[2]), capi.f32p(bufs[3]), capi.u32p(bufs[4])))
+            for g, w in zip(bufs[1:], want):
+                assert (g == w).all()
+        monkeypatch.setenv("FDB_QUERY_NO_EARLY_OUT", "1")      # the same batch with the results copied at the end
+        capi.check(capi.lib().fdb_index_query(ix.h, capi.f32p(bufs[0]), nq, k, nprobe, capi.QUERY_STORED,
+                                              capi.u32p(bufs[1]), capi.u32p(bufs[2]), capi.f32p(bufs[3]), capi.u32p(bufs[4])))
+        for g, w in zip(bufs[1:], want):
+            assert (g == w).all()
+    finally:
+        for a in bufs:
+            ctx.host_unregister(a)
+    oix = oracle.QueryIndex(coarse, cbs, off, codes)
+    rc, wp, wv, wd, wc = oix.query(q[:100], k, nprobe, 0)
+    assert rc == 0 and (want[0][:100] == wp).all() and (want[1][:100] == wv).all() and (want[2][:100] == wd).all()
+    ix.close()
+
+
 def test_forced_scan_mode_fails_loudly_when_the_shape_is_not_taken(eng, ctx, oracle, monkeypatch):
     """FDB_FILTER_SCAN forces a scan kernel; a shape that kernel does not take is an error, not a silent fallback."""
     from flechasdb_b200.db import Error
@@ -1155,15 +1194,37 @@ def test_database_builder_events_serialize_and_stored_query(eng, ctx, oracle, tm
     with pytest.raises(Error) as e:      # nprobe > P -> Err(InvalidArgs)
         db.query(q[0], 10, 9)
     assert e.value.kind == "InvalidArgs"
+    # attributes (src/db/build.rs:225-285): host-side maps keyed by vector id
+    ids = list(db.vector_ids())
+    for i in range(0, M, 3):
+        db.set_attribute_at(i, ("index", i))
+        if i % 2 == 0:
+            db.set_attribute_at(i, ("label", "vector %d" % i))
+    db.set_attribute_at(0, ("label", "replaced"))
+    assert db.get_attribute(ids[0], "label") == "replaced" and db.get_attribute(ids[3], "index") == 3
+    assert db.get_attribute(ids[3], "label") is None
+    with pytest.raises(Error) as e:
+        db.set_attribute_at(M, ("index", 1))
+    assert e.value.kind == "InvalidArgs"
+    with pytest.raises(Error) as e:      # no attribute was ever set for this vector (src/db/build.rs:238-243)
+        db.get_attribute(ids[1], "index")
+    assert e.value.kind == "InvalidArgs"
     # serialize -> load (reference layout) -> stored query == in-memory stored-mode query
     base = str(tmp_path / "testdb")
     h = stored.serialize_database(db, base)
     sdb = stored.StoredDatabase.load_database(ctx, base, h + ".binpb")
+    assert sdb.attribute_names == ["index", "label"]
+    index_of = {u: i for i, u in enumerate(ids)}
     for qi in range(5):
         a = db.query(q[qi], 7, 3, mode="stored")
         b = sdb.query(q[qi], 7, 3)
         assert [(r.partition_index, r.vector_index, r.squared_distance, r.vector_id) for r in a] == \
                [(r.partition_index, r.vector_index, r.squared_distance, r.vector_id) for r in b]
+        for r in b:     # QueryResult::get_attribute loads only the result's partition log (src/db/stored.rs:621-634)
+            gi = index_of[r.vector_id]
+            assert r.get_attribute("index") == (gi if gi % 3 == 0 else None)
+            assert r.get_attribute("label") == (None if gi % 6 else ("replaced" if gi == 0 else "vector %d" % gi))
+    assert 0 < sum(sdb.attributes_log_load_flags) <= sdb.partition_loads
     # lazily: load_database read no partition file, the five queries loaded only what they probed
     assert 0 < sdb.partition_loads <= 8 and sdb.partition_loads == sum(i is not None for i in sdb.ids)
     qe = []
@@ -1175,6 +1236,36 @@ def test_database_builder_events_serialize_and_stored_query(eng, ctx, oracle, tm
     want = db.query_batch(qb, 7, 3, mode="stored")
     for g, w in zip(got, want):
         assert (g == w).all()
+    # the async twin (src/asyncdb/stored/query.rs:221-355): concurrent lazy loads, same answers, attributes as coroutines
+    import asyncio
+    from flechasdb_b200 import asyncdb
+
+    async def arun():
+        adb = await asyncdb.AsyncStoredDatabase.load_database(ctx, base, h + ".binpb")
+        assert adb.index is None
+        ev = []
+        for qi in range(5):
+            a = db.query(q[qi], 7, 3, mode="stored")
+            b = await adb.query(q[qi], 7, 3, ev.append)
+            assert [(r.partition_index, r.vector_index, r.squared_distance, r.vector_id) for r in a] == \
+                   [(r.partition_index, r.vector_index, r.squared_distance, r.vector_id) for r in b]
+            for r in b:
+                gi = index_of[r.vector_id]
+                assert await r.get_attribute("index") == (gi if gi % 3 == 0 else None)
+        assert ev[0] == ("StartingLoadingPartitionCentroids",) and ev[-1] == ("FinishedKNNSelection",)
+        assert 0 < adb.partition_loads <= 8
+        assert await adb.get_attribute(ids[0], "label") == "replaced"
+        adb.close()
+    asyncio.run(arun())
+    # Database::get_attribute loads every log (and with it every partition); an unknown id is InvalidArgs
+    # (like the reference, it does so only while NO log has been loaded yet, src/db/stored.rs:127-129: a fresh handle)
+    sdb2 = stored.StoredDatabase.load_database(ctx, base, h + ".binpb")
+    assert sdb2.get_attribute(ids[0], "label") == "replaced" and sdb2.get_attribute(ids[1], "label") is None
+    assert all(sdb2.attributes_log_load_flags) and sdb2.partition_loads == 8
+    with pytest.raises(stored.Error) as e:
+        sdb2.get_attribute(bytes(16), "label")
+    assert e.value.kind == "InvalidArgs"
+    sdb2.close()
     sdb.close()
     db.index.close(); db.pkm.close(); db.ckm.close(); db.vs.close()
 

@@ -204,3 +204,38 @@ def test_attributes_log_wire_bytes_and_round_trip(tmp_path):
     with pytest.raises(stored.Error) as e:                             # name index past the header's list
         stored.load_attributes_log(base, lids[0], pids[0], 0, [])
     assert e.value.kind == "InvalidData" and "out of bounds" in str(e.value)
+
+
+def test_attributes_cross_the_language_border(tmp_path):
+    """C++ writes attributes logs that the Python reader understands and vice versa (same wire bytes, sorted names,
+    entries in ascending vector index per partition)."""
+    tool, subprocess = _tool()
+    base = str(tmp_path / "cpp")
+    N, P, D, C, M = 16, 4, 4, 20, 120
+    out = subprocess.run([tool, "write", base, "9", str(N), str(P), str(D), str(C), str(M), "attrs"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    got = stored.load_database(base, out.stdout.strip() + ".binpb")
+    assert got.attribute_names == ["idx", "name"]
+    total = int(got.offsets[-1])
+    for i in range(total):
+        idb = bytes(got.ids16[i])
+        assert got.get_attribute(idb, "idx") == (i if i % 7 == 0 else None)
+        assert got.get_attribute(idb, "name") == ("v%d" % i if i % 5 == 0 else None)
+    # Python writes, C++ reads: the tool hashes (id, name, value) of every entry in file order
+    coarse, cbs, off, codes, ids = _arrays(3, C=16)
+    table = {}
+    for i in range(0, len(ids), 3):
+        table[bytes(ids[i])] = {"zeta": "z%d" % i, "alpha": i * 1000003}
+    base2 = str(tmp_path / "py")
+    h2 = stored.serialize_arrays(base2, coarse, cbs, off, codes, ids, table)
+    rd = subprocess.run([tool, "read", base2, h2 + ".binpb"], capture_output=True, text=True)
+    assert rd.returncode == 0, rd.stderr
+    want, n = 1469598103934665603, 0
+    for i in range(len(ids)):
+        for name, value in table.get(bytes(ids[i]), {}).items():
+            v = ("s:" + value) if isinstance(value, str) else ("u:%d" % value)
+            for b in bytes(ids[i]) + name.encode() + v.encode():
+                want = ((want ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+            n += 1
+    line = rd.stdout.strip()
+    assert "attr_entries=%d attr_names=alpha,zeta attrs=%016x" % (n, want) in line, line
