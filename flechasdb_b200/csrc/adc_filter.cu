@@ -1040,6 +1040,55 @@ __global__ void __launch_bounds__(256) probe_exact_kernel(ProbeParams p) {
     }
 }
 
+// The same distances with the two rows of a pair staged in shared memory: a warp per pair requests both rows at once
+// (cp.async, 16 bytes per lane and request: ONE memory round trip per pair instead of N / 64), then lanes 0..15 own the
+// 16 accumulators of the reference's dot (src/linalg.rs:12-40) and walk the rows in order.  The quad-per-pair loop
+// above keeps 8 loads in flight per lane and needs ~24 dependent round trips for N = 1536: 55-69 us per batch
+// whatever the number of pairs; this one is bound by the number of pairs.  N % 16 == 0, rows 16-byte aligned.
+constexpr int PXS_WARPS = 8;
+__global__ void __launch_bounds__(PXS_WARPS * 32) probe_exact_smem_kernel(ProbeParams p) {
+    extern __shared__ __align__(16) float pxs[];
+    const unsigned total = *p.item_count;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *xs = pxs + (size_t)warp * 2 * p.N, *cs = xs + p.N;
+    const unsigned nwarps = gridDim.x * PXS_WARPS;
+    const int n16 = (int)(p.N >> 2);   // 16-byte pieces per row
+    // a warp takes a run of consecutive pairs: the pairs of one query are consecutive in the list (probe_select_kernel
+    // appends them together), so the query's row is staged once per query, not once per pair
+    const unsigned per = (total + nwarps - 1) / nwarps;
+    const unsigned w = blockIdx.x * PXS_WARPS + warp;
+    const unsigned first = w * per, last = min(total, first + per);
+    uint32_t have_q = 0xffffffffu;
+    for (unsigned item = first; item < last; ++item) {
+        const uint32_t qi = p.items[2 * (size_t)item], pc = p.items[2 * (size_t)item + 1];
+        const float *qv = p.q + (size_t)qi * p.N;
+        const float *cv = p.coarse + (size_t)pc * p.N;
+        for (int i = lane; i < n16; i += 32) {
+            if (qi != have_q) cp_async16(xs + 4 * i, qv + 4 * i);
+            cp_async16(cs + 4 * i, cv + 4 * i);
+        }
+        have_q = qi;
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncwarp();
+        float T = 0.0f;
+        if (lane < 16) {
+            float acc = 0.0f;   // accumulator `lane`: elements lane, lane + 16, ... in order
+#pragma unroll 8
+            for (size_t e = lane; e < p.N; e += 16) {
+                const float d = __fsub_rn(xs[e], cs[e]);          // localise, src/db/stored.rs:421
+                acc = __fadd_rn(acc, __fmul_rn(d, d));
+            }
+            T = acc;
+        }
+        float sum = 0.0f;   // sum_naive over the 16 accumulators, src/linalg.rs:39
+#pragma unroll
+        for (int j = 0; j < 16; ++j) sum = __fadd_rn(sum, __shfl_sync(0xffffffffu, T, j));
+        if (lane == 0) p.item_d[item] = sum;
+        __syncwarp();   // the rows are consumed before the next pair's land
+    }
+}
+
 // ---- probes for nprobe beyond the probe filter's 24 (build semantic): dense distance rows with the exact
 // value only where it can matter.  The reference evaluates all P distances and keeps the nprobe smallest; here
 // the tensor-pipe scores pick the partitions that can be among them: a lower bound t0 of the nprobe-th largest
@@ -1775,13 +1824,33 @@ static bool vscan_default(const fdb_index *ix, size_t nq, size_t nprobe) {
     // one table per query for all its lists.
     if (getenv("FDB_VSCAN_OFF")) return false;
     if ((double)nq * (double)nprobe < 2.0 * (double)ix->P) return false;
-    return ix->M >= 512 * ix->P || (nprobe >= 8 && ix->M >= 128 * ix->P);
+    if (ix->M >= 2048 * ix->P) return true;
+    // short lists: only batches that fill the groups several times over (slices of a host batch -- 2 500 queries,
+    // 125 per list on the README shape -- are answered faster by the query-major kernel: measured 1.65 vs 1.72 ms
+    // end to end)
+    const double pairs_per_list = (double)nq * (double)nprobe / (double)ix->P;
+    return (ix->M >= 512 * ix->P && pairs_per_list >= 256.0) || (nprobe >= 8 && ix->M >= 128 * ix->P);
 }
 
 // E_q = coef * W_q (header): gamma of the GEMM that produces G (tensor pipe or FMA chain)
 static float adc_coef(size_t s, size_t D, bool tc_g) {
     const double gamma = tc_g ? (double)tc_gamma(s) : (double)s * U24 / (1.0 - (double)s * U24);
     return (float)((2.0 * gamma + (double)(D + 4) * U24) * 1.01);
+}
+
+// exact distances of the listed pairs (device-side count, at most `cap`): rows staged in shared memory when they fit
+static int launch_probe_exact(fdb_ctx *ctx, const ProbeParams &pp, size_t cap, cudaStream_t st) {
+    const size_t smem = (size_t)PXS_WARPS * 2 * pp.N * sizeof(float);
+    static const bool off = getenv("FDB_PROBE_EXACT_NO_SMEM") != nullptr;
+    if (pp.quad && smem <= 200 * 1024 && !off) {
+        FDB_CUDA(cudaFuncSetAttribute(probe_exact_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const size_t per_sm = std::max<size_t>(1, (220 * 1024) / smem);
+        const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((cap + PXS_WARPS - 1) / PXS_WARPS, (size_t)ctx->sm_count * per_sm));
+        probe_exact_smem_kernel<<<grid, PXS_WARPS * 32, smem, st>>>(pp);
+    } else {
+        probe_exact_kernel<<<(unsigned)std::min<size_t>((cap * 4 + 255) / 256, (size_t)ctx->sm_count * 8), 256, 0, st>>>(pp);
+    }
+    return FDB_OK;
 }
 
 // probes through the tensor pipe + the probe filter; *done = false when the shape is not taken
@@ -1851,7 +1920,7 @@ int filter_probe(fdb_index *ix, const float *d_q, size_t nq, size_t nprobe, Even
     // select (scores -> candidates, band) -> exact distances of the ambiguous pairs, spread over the
     // whole GPU -> finalize (probe list, K, W)
     probe_select_kernel<<<(unsigned)((nq + 3) / 4), 128, psmem, st>>>(pp);
-    probe_exact_kernel<<<(unsigned)std::min<size_t>((nq * 32 * 4 + 255) / 256, (size_t)ctx->sm_count * 8), 256, 0, st>>>(pp);
+    FDB_TRY(launch_probe_exact(ctx, pp, nq * 32, st));
     probe_finalize_kernel<<<(unsigned)((nq + 3) / 4), 128, 0, st>>>(pp);
     ctx->launches += 3;
     FDB_CHECK_LAUNCH();
@@ -1897,7 +1966,7 @@ int filter_probe_dense(fdb_index *ix, const float *d_q, size_t nq, size_t nprobe
     pp.items = sl->ps_items.p;
     pp.item_d = sl->ps_dist.p;
     pp.item_count = sl->ps_count.p;
-    probe_exact_kernel<<<(unsigned)std::min<size_t>((cap * 4 + 255) / 256, (size_t)ctx->sm_count * 8), 256, 0, st>>>(pp);
+    FDB_TRY(launch_probe_exact(ctx, pp, cap, st));
     probe_scatter_kernel<<<(unsigned)ctx->sm_count * 4, 256, 0, st>>>(sl->ps_items.p, sl->ps_dist.p, sl->ps_count.p,
                                                                     (unsigned)cap, P, d_dist);
     ctx->launches += 3;

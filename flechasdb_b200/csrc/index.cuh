@@ -40,6 +40,8 @@ struct fdb_index {
     fdb::DevBuf<uint32_t> fb_p, fb_v, fb_c, fb_probes;
     bool last_filter = false;
     int last_scan_kind = 0;   // fdb_index_last_scan_kernel
+    uint32_t *h_stage = nullptr;   // page-locked staging for the handed-back rows of a host batch
+    size_t h_stage_words = 0;
     // timing mode: events around the code-scan kernel itself (its launches of the last call, summed)
     std::vector<cudaEvent_t> kev;
     size_t kev_used = 0;

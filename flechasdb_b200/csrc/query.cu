@@ -647,6 +647,7 @@ void fdb_index_destroy(fdb_index *ix) {
     cudaStreamSynchronize(ix->ctx->stream);
     for (cudaEvent_t e : ix->events) cudaEventDestroy(e);
     for (cudaEvent_t e : ix->kev) cudaEventDestroy(e);
+    if (ix->h_stage) cudaFreeHost(ix->h_stage);
     for (cudaEvent_t e : ix->copy_events) cudaEventDestroy(e);
     if (ix->copy_stream) {
         cudaStreamSynchronize(ix->copy_stream);
@@ -1139,7 +1140,22 @@ int fdb_index_query(fdb_index *ix, const float *queries, size_t nq, size_t k, si
             nslices = (nq + slice - 1) / slice;
         }
         bounds.push_back(0);
-        for (size_t i = 0; i + 1 < nslices && bounds.back() + slice < nq; ++i) bounds.push_back(bounds.back() + slice);
+        if (const char *plan = getenv("FDB_QUERY_HOST_PLAN")) {
+            // experiment hook: slice sizes in per cent of the batch, e.g. "10,30,30,20,10" (a short first slice starts
+            // the pipeline early, a short last one shortens the tail after the last copy)
+            double acc = 0.0;
+            for (const char *c = plan; *c;) {
+                char *end = nullptr;
+                const double pct = strtod(c, &end);
+                if (end == c) break;
+                acc += pct;
+                const size_t b = std::min(nq, (size_t)((double)nq * acc / 100.0));
+                if (b > bounds.back() && b < nq) bounds.push_back(b);
+                c = *end == ',' ? end + 1 : end;
+            }
+        } else {
+            for (size_t i = 0; i + 1 < nslices && bounds.back() + slice < nq; ++i) bounds.push_back(bounds.back() + slice);
+        }
         bounds.push_back(nq);
     }
     const size_t nslices = bounds.size() - 1;
@@ -1203,22 +1219,31 @@ int fdb_index_query(fdb_index *ix, const float *queries, size_t nq, size_t k, si
     int rc;
     if (b.early_out) {
         // the slices' results are on their way (or there); only the handed-back queries' rows follow
+        // (through a page-locked staging area of the index: a pageable destination would cost a driver staging
+        //  round trip per copy)
         const size_t nfb = b.nfb;
-        std::vector<uint32_t> fq(nfb), fp(nfb * k), fv(nfb * k), fc(nfb);
-        std::vector<float> fd(nfb * k);
+        const size_t words = nfb * (2 + 3 * k);
+        if (words > ix->h_stage_words) {
+            if (ix->h_stage) cudaFreeHost(ix->h_stage);
+            ix->h_stage = nullptr;
+            ix->h_stage_words = std::max<size_t>(words, 4096);
+            FDB_CUDA(cudaMallocHost((void **)&ix->h_stage, ix->h_stage_words * sizeof(uint32_t)));
+        }
+        uint32_t *fq = ix->h_stage, *fc = fq + nfb, *fp = fc + nfb, *fv = fp + nfb * k;
+        float *fd = reinterpret_cast<float *>(fv + nfb * k);
         if (nfb) {
-            FDB_CUDA(cudaMemcpyAsync(fq.data(), b.d_fb, nfb * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-            FDB_CUDA(cudaMemcpyAsync(fp.data(), ix->fb_p.p, nfb * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-            FDB_CUDA(cudaMemcpyAsync(fv.data(), ix->fb_v.p, nfb * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-            FDB_CUDA(cudaMemcpyAsync(fd.data(), ix->fb_d.p, nfb * k * sizeof(float), cudaMemcpyDeviceToHost, st));
-            FDB_CUDA(cudaMemcpyAsync(fc.data(), ix->fb_c.p, nfb * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            FDB_CUDA(cudaMemcpyAsync(fq, b.d_fb, nfb * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            FDB_CUDA(cudaMemcpyAsync(fc, ix->fb_c.p, nfb * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            FDB_CUDA(cudaMemcpyAsync(fp, ix->fb_p.p, nfb * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            FDB_CUDA(cudaMemcpyAsync(fv, ix->fb_v.p, nfb * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            FDB_CUDA(cudaMemcpyAsync(fd, ix->fb_d.p, nfb * k * sizeof(float), cudaMemcpyDeviceToHost, st));
         }
         rc = finish_query(ctx);
         for (size_t i = 0; i < nfb && rc == FDB_OK; ++i) {
             const size_t q = fq[i];
-            memcpy(out_partition + q * k, fp.data() + i * k, k * sizeof(uint32_t));
-            memcpy(out_vector_index + q * k, fv.data() + i * k, k * sizeof(uint32_t));
-            memcpy(out_sqdist + q * k, fd.data() + i * k, k * sizeof(float));
+            memcpy(out_partition + q * k, fp + i * k, k * sizeof(uint32_t));
+            memcpy(out_vector_index + q * k, fv + i * k, k * sizeof(uint32_t));
+            memcpy(out_sqdist + q * k, fd + i * k, k * sizeof(float));
             out_count[q] = fc[i];
         }
     } else {

@@ -79,3 +79,27 @@ for slice_q in [None] + [int(s) for s in os.environ.get("SLICES", "1000,1250,166
     os.environ["FDB_QUERY_TRACE"] = "1"
     host_query()
     sys.stderr.flush()
+
+# tapered plans (per cent of the batch per slice) x scan kernel of the slices
+os.environ.pop("FDB_QUERY_HOST_SLICE", None)
+for scan in (None, "query"):
+    if scan:
+        os.environ["FDB_FILTER_SCAN"] = scan
+    else:
+        os.environ.pop("FDB_FILTER_SCAN", None)
+    for plan in os.environ.get("PLANS", "25,25,25,25;10,30,30,20,10;10,25,25,25,15;15,35,35,15;5,20,25,25,15,10;20,30,30,20;12,22,22,22,22").split(";"):
+        os.environ["FDB_QUERY_HOST_PLAN"] = plan
+        os.environ.pop("FDB_QUERY_TRACE", None)
+        for _ in range(3):
+            host_query()
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            host_query()
+            ts.append((time.perf_counter() - t0) * 1e3)
+        print("scan %s plan %s: min %.3f ms, median %.3f ms" % (scan or "default", plan, min(ts), sorted(ts)[len(ts) // 2]), flush=True)
+        os.environ["FDB_QUERY_TRACE"] = "1"
+        host_query()
+        sys.stderr.flush()
+os.environ.pop("FDB_QUERY_HOST_PLAN", None)
+os.environ.pop("FDB_FILTER_SCAN", None)
