@@ -545,9 +545,10 @@ def sharded_build_parity(engine, sharded, ctx, comm, dist, rank, world):
             "gradient_rel_err": float(abs(float(grads[0][-1]) - float(og[-1])) / max(abs(float(og[-1])), 1e-30))}
 
 
-def run_sharded_build(args, engine, sharded, ctx, comm, rank, world, steps, warmup):
-    """configs[2] with the rows sharded.  Device-timed (events on the library's stream, which carries the
-    collectives), max over ranks."""
+def run_sharded_build(args, engine, sharded, ctx, comm, rank, world, steps, warmup, shape=None):
+    """configs[2] (or `shape` = (M, N, P, D, C)) with the rows sharded.  Device-timed (events on the library's stream,
+    which carries the collectives), max over ranks."""
+    M2, N2, P2, D2, C2 = shape or (globals()["M2"], globals()["N2"], globals()["P2"], globals()["D2"], globals()["C2"])
     lo, hi = engine.shard_rows(M2, world, rank)
     phase_names = ("coarse_seeding", "coarse_lloyd", "residues", "pq_seeding", "pq_lloyd")
     secs, phases, launches, colls, stats = [], [], 0, 0, None
@@ -702,12 +703,18 @@ def run_sharded_query(args, engine, sharded, ctx, comm, dist, rank, world, steps
         for p in probed:
             ocodes[int(ooff[p]):int(ooff[p + 1])] = list_codes(p, sizes[p])
         oix = oracle.QueryIndex(coarse, cbs, ooff, ocodes)
+        t0 = time.perf_counter()
         rc, wp, wv, wd, wc = oix.query(q, k, nprobe, 0, nthreads=os.cpu_count() or 1)
+        cpu_s = time.perf_counter() - t0
         covered = all(int(p) in probed for p in wp.ravel())
         parity = {"queries_checked": ns, "nprobe": nprobe, "semantic": "stored::Database::query",
                   "oracle_lists_cover_the_probes": bool(covered),
                   "id_mismatches": int((wp != got[0]).any(axis=1).sum() + (wv != got[1]).any(axis=1).sum()),
-                  "distances_bit_equal": bool(rc == 0 and (wd == got[2]).all() and (wc == got[3]).all())}
+                  "distances_bit_equal": bool(rc == 0 and (wd == got[2]).all() and (wc == got[3]).all()),
+                  "cpu_baseline": {"value": ns / cpu_s, "unit": "queries/s", "cores": os.cpu_count() or 1, "kind": "port",
+                                   "sample": "these %d queries at nprobe %d on all host threads (P = %d coarse distances, "
+                                             "%d tables and ~%d code rows per query); nprobe 128 scans 16x the rows"
+                                             % (ns, nprobe, P4, nprobe, nprobe * (M4 // P4))}}
     ix.close()
     for h in [d_q] + outs:
         ctx.free(h)
@@ -745,7 +752,24 @@ def cpu_baselines_sharded(oracle, native=None):
     t0 = time.perf_counter()
     oracle.kmeans_reassign(x, C2, cb, off=0, dim=N2 // D2, nthreads=cores, native=native)
     t_pq = (time.perf_counter() - t0) * M2 / ns * D2
-    return {"configs2_build": {"sec_per_coarse_pass": t_coarse, "sec_per_pq_pass_all_divisions": t_pq,
+    # configs[3] (SIFT-shaped: M = 10M, N = 128, P = 4096, D = 16 (s = 8: dot_naive order), C = 256), the same way
+    M3, N3, P3, D3 = 10_000_000, 128, 4096, 16
+    x3 = oracle.fill_uniform(ns * N3, SEED_DATA + 3).reshape(ns, N3)
+    cc3 = oracle.fill_uniform(P3 * N3, 7).reshape(P3, N3)
+    t0 = time.perf_counter()
+    oracle.kmeans_reassign(x3, P3, cc3, nthreads=cores, native=native)
+    t3_coarse = (time.perf_counter() - t0) * M3 / ns
+    cb3 = oracle.fill_uniform(C2 * (N3 // D3), 8).reshape(C2, N3 // D3)
+    t0 = time.perf_counter()
+    oracle.kmeans_reassign(x3, C2, cb3, off=0, dim=N3 // D3, nthreads=cores, native=native)
+    t3_pq = (time.perf_counter() - t0) * M3 / ns * D3
+    configs3 = {"sec_per_coarse_pass": t3_coarse, "sec_per_pq_pass_all_divisions": t3_pq,
+                "extrapolated_build_sec_100_rounds_each": (1 + 100) * t3_coarse + (1 + 100) * t3_pq,
+                "cores": cores, "kind": "port",
+                "sample": "one reassignment pass over %d of the %d rows (coarse k = %d; PQ division 0 x %d), x rows x "
+                          "(k-means++ counted as one pass + 100 Lloyd rounds)" % (ns, M3, P3, D3)}
+    return {"configs3_build": configs3,
+            "configs2_build": {"sec_per_coarse_pass": t_coarse, "sec_per_pq_pass_all_divisions": t_pq,
                                "extrapolated_build_sec_100_rounds_each": (1 + 100) * t_coarse + (1 + 100) * t_pq,
                                "cores": cores, "kind": "port",
                                "sample": "one reassignment pass over %d of the %d rows (coarse; PQ division 0 x %d), "
@@ -765,6 +789,15 @@ def run_sharded(args, rank, world, local_rank, dist):
     clocks = sampler.stop()
     e2e = run_sharded_build_e2e(args, engine, sharded, ctx, comm, rank, world, max(1, min(args.steps, 2)))
     parity_build = sharded_build_parity(engine, sharded, ctx, comm, dist, rank, world)
+    # configs[3] (SIFT-shaped: 10M x 128, P = 4096, D = 16 -> sub-vectors of 8, the dot_naive order): one build, N > 1 only
+    # (15 s on one GPU)
+    sift = None
+    if world > 1 and not args.no_sift:
+        b3 = run_sharded_build(args, engine, sharded, ctx, comm, rank, world, 1, 0, shape=(10_000_000, 128, 4096, 16, 256))
+        b3.pop("local_partition_sizes", None)
+        sift = {"workload": "configs[3] build: M=10M N=128 D=16 P=4096 C=256, rows sharded x%d, one build (cold)" % world,
+                "sec": b3["sec"], "rows_per_s": b3["rows_per_s"], "phase_sec": b3["phase_sec"],
+                "lloyd_rounds": b3["lloyd_rounds"], "collectives": b3["collectives"]}
     query = None if args.no_sharded_query else run_sharded_query(args, engine, sharded, ctx, comm, dist, rank, world,
                                                                 max(2, min(args.steps, 3)), 2, hbm_peak)
     sizes = gather_objects(dist, build.pop("local_partition_sizes"), world)
@@ -809,7 +842,7 @@ def run_sharded(args, rank, world, local_rank, dist):
              "achieved": seed_bytes / seed_sec / 1e9 / world, "peak": hbm_peak, "unit": "GB/s",
              "frac": seed_bytes / seed_sec / 1e9 / world / hbm_peak,
              "note": "per GPU; phase time includes the pick, the packed all-gather and the launch gaps of every round"}],
-        "parity": parity_build, "sharded_query": query, "clocks": clocks, "single_gpu_same_run": base1,
+        "parity": parity_build, "sharded_query": query, "clocks": clocks, "single_gpu_same_run": base1, "configs3_build": sift,
         "limiter": "see phase_sec: the k-means++ rounds are latency (kernel launches + one small all-gather each), "
                    "the Lloyd rounds one all-reduce of %.1f MB (coarse) / %.1f MB (PQ) each"
                    % ((P2 * N2 + P2) * 4 / 1e6, (D2 * C2 * (N2 // D2) + D2 * C2) * 4 / 1e6),
@@ -950,6 +983,7 @@ def main():
     ap.add_argument("--no-sharded", action="store_true",
                     help="N = 1: skip the sharded workloads (configs[2] build, configs[4] query) at world = 1")
     ap.add_argument("--no-sharded-query", action="store_true", help="skip configs[4] (100M codes) in the sharded run")
+    ap.add_argument("--no-sift", action="store_true", help="N > 1: skip the configs[3] build (10M x 128)")
     ap.add_argument("--no-single-gpu-base", action="store_true",
                     help="N > 1: skip the world = 1 build rank 0 runs at the end as the base of the scaling curve")
     ap.add_argument("--no-scan-large", action="store_true",
