@@ -40,6 +40,10 @@ struct fdb_index {
     fdb::DevBuf<uint32_t> fb_p, fb_v, fb_c, fb_probes;
     bool last_filter = false;
     int last_scan_kind = 0;   // fdb_index_last_scan_kernel
+    // stored-semantic probes from sparse rows: the queries with tied distances, their rows and full distance rows
+    fdb::DevBuf<uint32_t> tied_list;
+    fdb::DevBuf<float> tied_q, tied_dist;
+    unsigned last_probe_ties = 0;
     uint32_t *h_stage = nullptr;   // page-locked staging for the handed-back rows of a host batch
     size_t h_stage_words = 0;
     // timing mode: events around the code-scan kernel itself (its launches of the last call, summed)

@@ -724,7 +724,17 @@ __global__ void __launch_bounds__(128) accumulate_kernel(UpdateParams p, unsigne
 #pragma unroll
         for (int u = 0; u < U; ++u) s = __fadd_rn(s, v[u]);
     }
-    for (; t < end; ++t) s = __fadd_rn(s, xb[(size_t)mem[t] * p.ldx]);
+    if (t < end) {   // the last members (fewer than U): requested together as well
+        const int rem = (int)(end - t);
+        float v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) r[u] = u < rem ? mem[t + u] : 0u;
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u] = u < rem ? xb[(size_t)r[u] * p.ldx] : 0.0f;
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (u < rem) s = __fadd_rn(s, v[u]);
+    }
     const size_t o = (b * p.k + i) * p.m + e;
     const size_t count = end - start;
     if (p.partial) {

@@ -34,14 +34,19 @@ namespace {
 constexpr int PROBE_WARPS = 4;
 __global__ void __launch_bounds__(PROBE_WARPS * 32) probe_select_kernel(
     const float *dist, size_t nq, size_t P, int nprobe, int mode, uint32_t *probes, float *probe_d,
-    unsigned *flags) {
+    unsigned *flags, uint32_t *tied_list, unsigned *tied_count, const uint32_t *qlist) {
+    // dist: row r of the launch; results go to query qlist[r] (r itself without a list).  tied_list (stored
+    // semantic, sparse rows -- exact distances only where they can matter, +inf elsewhere): a query whose nprobe
+    // smallest distances tie cannot be decided from such a row (NBestByKey's history depends on every push): it is
+    // appended to the list and answered later from a full row.
     extern __shared__ unsigned char sm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const size_t q = (size_t)blockIdx.x * PROBE_WARPS + warp;
-    if (q >= nq) return;
+    const size_t r = (size_t)blockIdx.x * PROBE_WARPS + warp;
+    if (r >= nq) return;
+    const size_t q = qlist ? qlist[r] : r;
     float *sd = reinterpret_cast<float *>(sm) + (size_t)warp * 2 * nprobe;
     uint32_t *sa = reinterpret_cast<uint32_t *>(sd + nprobe);
-    const float *dq = dist + q * P;
+    const float *dq = dist + r * P;
     auto key = [&](int i) { return dq[i]; };
     uint32_t *op = probes + q * nprobe;
     float *od = probe_d + q * nprobe;
@@ -71,6 +76,10 @@ __global__ void __launch_bounds__(PROBE_WARPS * 32) probe_select_kernel(
                 od[i] = sd[i];
                 op[i] = sa[i];
             }
+            return;
+        }
+        if (tied_list) {   // sparse row: not decidable here
+            if (lane == 0) tied_list[atomicAdd(tied_count, 1u)] = (uint32_t)q;
             return;
         }
         __syncwarp();
@@ -700,16 +709,47 @@ int probe_device(fdb_index *ix, const float *d_q, size_t nq, size_t nprobe, int 
     dp.k = ix->P;
     // build semantic (canonical order, no push history): only the partitions the tensor-pipe scores cannot rule
     // out need their exact distance (adc_filter.cu, filter_probe_dense)
+    // Stored semantic (NBestByKey): the same sparse rows decide every query whose nprobe smallest distances are
+    // pairwise distinct (the kept set is then unique and the stable sort orders it); the queries with ties -- a few per
+    // cent at nprobe = 128 on uniform data -- are answered again from full rows, slot by slot.
     bool dense = false;
-    if (mode == FDB_QUERY_BUILD && nprobe > 24) FDB_TRY(filter_probe_dense(ix, d_q, nq, nprobe, ix->dist.p, &dense));
+    if (nprobe > 24 && !(mode == FDB_QUERY_STORED && getenv("FDB_PROBE_DENSE_STORED_OFF")))
+        FDB_TRY(filter_probe_dense(ix, d_q, nq, nprobe, ix->dist.p, &dense));
     if (!dense) FDB_TRY(launch_exact_matrix(ctx, dp, ix->dist.p));
     if (log) FDB_TRY(log->mark(1));
     const size_t smem = (size_t)PROBE_WARPS * 2 * nprobe * sizeof(float);
+    const bool sparse_stored = dense && mode == FDB_QUERY_STORED;
+    if (sparse_stored) {
+        FDB_TRY(ix->tied_list.ensure(nq + 1));
+        FDB_CUDA(cudaMemsetAsync(ix->tied_list.p + nq, 0, sizeof(uint32_t), ctx->stream));
+    }
     probe_select_kernel<<<(unsigned)((nq + PROBE_WARPS - 1) / PROBE_WARPS), PROBE_WARPS * 32, smem,
                           ctx->stream>>>(ix->dist.p, nq, ix->P, (int)nprobe, mode, ix->probes.p,
-                                         ix->probe_d.p, ctx->d_flags);
+                                         ix->probe_d.p, ctx->d_flags, sparse_stored ? ix->tied_list.p : nullptr,
+                                         sparse_stored ? ix->tied_list.p + nq : nullptr, nullptr);
     ctx->launches++;
     FDB_CHECK_LAUNCH();
+    if (sparse_stored) {
+        unsigned nt = 0;
+        FDB_CUDA(cudaMemcpyAsync(&nt, ix->tied_list.p + nq, sizeof(nt), cudaMemcpyDeviceToHost, ctx->stream));
+        FDB_CUDA(cudaStreamSynchronize(ctx->stream));
+        ix->last_probe_ties = nt;
+        if (nt) {
+            FDB_TRY(ix->tied_q.ensure((size_t)nt * ix->N));
+            FDB_TRY(ix->tied_dist.ensure((size_t)nt * ix->P));
+            gather_rows_kernel<<<(unsigned)(((size_t)nt * ix->N + 255) / 256), 256, 0, ctx->stream>>>(d_q, ix->tied_list.p, nt,
+                                                                                                    ix->N, ix->tied_q.p);
+            DistProblem dt = dp;
+            dt.x = ix->tied_q.p;
+            dt.n = nt;
+            FDB_TRY(launch_exact_matrix(ctx, dt, ix->tied_dist.p));
+            probe_select_kernel<<<(unsigned)((nt + PROBE_WARPS - 1) / PROBE_WARPS), PROBE_WARPS * 32, smem, ctx->stream>>>(
+                ix->tied_dist.p, nt, ix->P, (int)nprobe, mode, ix->probes.p, ix->probe_d.p, ctx->d_flags, nullptr, nullptr,
+                ix->tied_list.p);
+            ctx->launches += 2;
+            FDB_CHECK_LAUNCH();
+        }
+    }
     return FDB_OK;
 }
 
