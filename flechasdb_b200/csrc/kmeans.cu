@@ -704,37 +704,20 @@ __global__ void __launch_bounds__(128) accumulate_kernel(UpdateParams p, unsigne
     const float *xb = p.x + p.col_off + b * p.m + e;
     float s = 0.0f;  // new_centroid.fill(0) then add_in per member, ascending j (:249-258)
     size_t t = start;
-    // U members in flight per thread; the row indices of the NEXT U members are requested before the current rows
-    // are summed, so a step costs one memory round trip (the rows), not two (indices, then rows).  The adds stay in
-    // ascending member order.
-    constexpr int U = 16;
-    uint32_t r[U];
-    if (t + U <= end) {
+    // (tried in round 2: 16 members in flight with the next batch's indices requested ahead -- the README build went
+    //  from 0.151 to 0.166 s; with the last < 16 members batched under predicates as well the kernel took 1.27 ms
+    //  instead of 0.22 ms: the straightforward batches of 8 stay)
+    for (; t + 8 <= end; t += 8) {
+        uint32_t r[8];
+        float v[8];
 #pragma unroll
-        for (int u = 0; u < U; ++u) r[u] = mem[t + u];
+        for (int u = 0; u < 8; ++u) r[u] = mem[t + u];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = xb[(size_t)r[u] * p.ldx];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s = __fadd_rn(s, v[u]);
     }
-    for (; t + U <= end; t += U) {
-        float v[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) v[u] = xb[(size_t)r[u] * p.ldx];
-        if (t + 2 * U <= end) {
-#pragma unroll
-            for (int u = 0; u < U; ++u) r[u] = mem[t + U + u];
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) s = __fadd_rn(s, v[u]);
-    }
-    if (t < end) {   // the last members (fewer than U): requested together as well
-        const int rem = (int)(end - t);
-        float v[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) r[u] = u < rem ? mem[t + u] : 0u;
-#pragma unroll
-        for (int u = 0; u < U; ++u) v[u] = u < rem ? xb[(size_t)r[u] * p.ldx] : 0.0f;
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-            if (u < rem) s = __fadd_rn(s, v[u]);
-    }
+    for (; t < end; ++t) s = __fadd_rn(s, xb[(size_t)mem[t] * p.ldx]);
     const size_t o = (b * p.k + i) * p.m + e;
     const size_t count = end - start;
     if (p.partial) {

@@ -49,27 +49,42 @@ struct WarpNBest {
             return;
         }
         if (!(cd < maxd)) return;
-        for (;;) {
-            int found = -1;
-            for (int base = 0; base < n; base += 32) {
-                const int s = base + lane;
-                const unsigned bal = __ballot_sync(0xffffffffu, s < n && cd < d[s]);
-                if (bal) {
-                    found = base + __ffs(bal) - 1;
-                    break;
-                }
+        // The reference loops { find the FIRST slot with key(cand) < key(slot); swap; the evicted entry becomes cand }
+        // until no slot is larger (src/nbest.rs:52-64).  The evicted entry is larger than cand, and every slot before
+        // the one it came from is <= cand, so the search for the evicted entry's slot can only succeed further right:
+        // the whole chain is ONE left-to-right sweep  "if carry < slot: swap(carry, slot)".  Before slot s the carry is
+        // the first entry attaining max(cand, slots[0..s)) (a swap needs a strict <, so the earlier entry wins ties),
+        // and the slot becomes that carry iff carry < slot: a prefix maximum -- 32 slots per warp step instead of one
+        // swap per step (a chain is ~n/2 swaps long when n is large: nprobe = 128 probe selection).
+        for (int base = 0; base < n; base += 32) {
+            const int s = base + lane;
+            const bool in = s < n;
+            const float sk = in ? d[s] : -INF;      // (-INF never takes the carry over: "carry < slot" is false)
+            const uint32_t sp = in ? a[s] : 0u;
+            // inclusive scan of (key, payload) over the lanes with  combine(earlier, later) = earlier.key < later.key ?
+            // later : earlier
+            float ik = sk == sk ? sk : -INF;        // (a NaN slot never takes the carry over either)
+            uint32_t ip = sp;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const float ok = __shfl_up_sync(0xffffffffu, ik, off);
+                const uint32_t op = __shfl_up_sync(0xffffffffu, ip, off);
+                if (lane >= off && !(ok < ik)) ik = ok, ip = op;
             }
-            if (found < 0) break;
-            const float od = d[found];
-            const uint32_t oa = a[found];
+            // exclusive value = the carry when it reaches this lane's slot (the incoming carry is the earliest entry)
+            float ek = __shfl_up_sync(0xffffffffu, ik, 1);
+            uint32_t ep = __shfl_up_sync(0xffffffffu, ip, 1);
+            if (lane == 0 || !(cd < ek)) ek = cd, ep = ca;
             __syncwarp();
-            if (lane == 0) {
-                d[found] = cd;
-                a[found] = ca;
+            if (in && ek < sk) {
+                d[s] = ek;
+                a[s] = ep;
             }
+            // the carry that leaves this group of slots
+            const float lk = __shfl_sync(0xffffffffu, ik, 31);
+            const uint32_t lp = __shfl_sync(0xffffffffu, ip, 31);
+            if (cd < lk) cd = lk, ca = lp;
             __syncwarp();
-            cd = od;
-            ca = oa;
         }
         refresh_max(lane);
     }

@@ -511,15 +511,19 @@ def test_probes_beyond_the_probe_filter_use_dense_rows(eng, ctx, oracle, monkeyp
 def test_stored_probe_selection_with_many_slots_and_ties(eng, ctx, oracle):
     """nprobe > 24 in the stored semantic: the sorted selection when the distances are distinct, the slot
     emulation when they tie (duplicated centroids: every distance occurs several times)."""
-    N, P, D, Cn, M = 32, 400, 4, 32, 6000
+    N, P, D, Cn, M = 32, 600, 4, 32, 6000
     coarse, cbs, off, codes = random_index(oracle, N, P, D, Cn, M)
-    coarse[200:] = coarse[:200]                    # every centroid twice: ties everywhere
+    coarse[300:] = coarse[:300]                    # every centroid twice: ties everywhere
     coarse[37] = coarse[5]
+    part = random_index(oracle, N, P, D, Cn, M)[0].copy()
+    part[450:] = part[:150]                        # a quarter of the centroids twice: some queries tie, some do not
     q = data(oracle, 40, N, SEED + 89)
-    for c in (coarse, random_index(oracle, N, P, D, Cn, M)[0]):
+    # (nprobe 25 .. 130 with P >= 4 nprobe: sparse distance rows -- exact only where it can matter -- decide the queries
+    #  without ties, the tied ones are answered again from full rows; nprobe 200: full rows for everyone)
+    for c in (coarse, part, random_index(oracle, N, P, D, Cn, M)[0]):
         ix = eng.Index.create(ctx, c, cbs, off, codes.astype(np.uint8))
         oix = oracle.QueryIndex(c, cbs, off, codes)
-        for nprobe in (25, 64, 130):
+        for nprobe in (25, 64, 130, 200):
             got_p, got_d = ix.probe(q, nprobe, 0)
             for qi in range(len(q)):
                 rc, want_p, want_d = oix.probe(q[qi], nprobe, 0)
