@@ -221,7 +221,8 @@ struct BuildEvent {
 struct QueryEvent {
     enum Kind {
         StartingPartitionSelection, FinishedPartitionSelection, StartingPartitionQuery,
-        FinishedPartitionQuery, StartingResultSelection, FinishedResultSelection
+        FinishedPartitionQuery, StartingResultSelection, FinishedResultSelection,
+        StartingQueryInitialization, FinishedQueryInitialization   // stored::Database only (src/db/stored.rs:342-360)
     } kind;
     size_t partition_index = 0;
 };

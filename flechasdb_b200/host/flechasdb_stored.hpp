@@ -539,6 +539,9 @@ class Database {
                                    const std::function<void(const QueryEvent &)> &ev = [](const QueryEvent &) {}) {
         if (k == 0 || nprobe == 0) throw Error(Error::InvalidArgs, "NonZeroUsize");
         if (v.size() != N_) throw Error(Error::InvalidArgs, "query vector size mismatch");
+        // (the partition centroids and the codebooks are resident since load_database: nothing to initialise lazily)
+        ev({QueryEvent::StartingQueryInitialization});
+        ev({QueryEvent::FinishedQueryInitialization});
         ev({QueryEvent::StartingPartitionSelection});
         std::vector<uint32_t> probes(nprobe);
         check(fdb_index_probe(index_, v.data(), 1, nprobe, FDB_QUERY_STORED, probes.data(), nullptr));

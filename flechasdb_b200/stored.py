@@ -595,6 +595,8 @@ class StoredDatabase:
         from . import _capi as capi
         from .db import QueryResult
         v = np.asarray(v, np.float32).reshape(1, -1)
+        event(("StartingQueryInitialization",))     # centroids and codebooks are resident since load_database
+        event(("FinishedQueryInitialization",))
         event(("StartingPartitionSelection",))
         probes, _ = self.index.probe(v, nprobe, capi.QUERY_STORED)
         event(("FinishedPartitionSelection",))

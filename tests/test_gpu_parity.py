@@ -1233,7 +1233,8 @@ def test_database_builder_events_serialize_and_stored_query(eng, ctx, oracle, tm
     assert 0 < sdb.partition_loads <= 8 and sdb.partition_loads == sum(i is not None for i in sdb.ids)
     qe = []
     sdb.query(q[0], 7, 3, qe.append)
-    assert [e[0] for e in qe][:2] == ["StartingPartitionSelection", "FinishedPartitionSelection"]
+    assert [e[0] for e in qe][:4] == ["StartingQueryInitialization", "FinishedQueryInitialization",
+                                      "StartingPartitionSelection", "FinishedPartitionSelection"]   # src/db/stored.rs:342-362
     # batched form: loads what the batch probes, answers like the in-memory index
     qb = data(oracle, 64, N, SEED + 9)
     got = sdb.query_batch(qb, 7, 3)
