@@ -40,6 +40,11 @@ SEED_KMEANS = 0xF1EC4A5D0003
 M, N, P, D, CN = 100000, 1536, 100, 12, 256
 NQ, K, NPROBE = 10000, 10, 5
 METRIC = "ivfpq_query_qps_k10_nprobe5_100kx1536"
+# (both arms print the same config, so the two notes name both)
+L2_NOTE = "GPU arm: flushed between timed steps (256 MiB write); CPU arm: not applicable"
+PAR_NOTE = "GPU arm: index replicated, queries sharded x%d; CPU arm: independent queries on all host threads"
+L2_NOTE_SHARDED = "GPU arm: inputs (3 GB of rows) exceed L2; CPU arm: not applicable"
+PAR_NOTE_SHARDED = "GPU arm: rows sharded x%d; CPU arm: a row sample on all host threads, extrapolated"
 WORKLOAD = "configs[1]: 10k random queries vs 100k x 1536 DB (P=100 D=12 C=256), K=10 NPROBE=5"
 
 
@@ -438,8 +443,7 @@ def run_ours(args, rank, world, local_rank, dist):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "M": m, "N": N, "P": P, "D": D, "C": CN, "nq": nq, "k": K,
-                   "nprobe": NPROBE, "l2": "flushed between timed steps (256 MiB write)",
-                   "parallelism": "index replicated, queries sharded x%d" % world},
+                   "nprobe": NPROBE, "l2": L2_NOTE, "parallelism": PAR_NOTE % world},
         "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": nq * N * 4,
                 "d2h_bytes_per_step": nq * K * 12 + nq * 4, "ms_per_step": e2e_ms / args.steps,
                 "host_buffers": "pinned (torch pin_memory)", "other_host_buffers": e2e_other},
@@ -827,7 +831,7 @@ def run_sharded(args, rank, world, local_rank, dist):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": build["sec"] * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD_SHARDED, "M": M2, "N": N2, "P": P2, "D": D2, "C": C2,
-                   "l2": "inputs (3 GB of rows) exceed L2", "parallelism": "rows sharded x%d" % world},
+                   "l2": L2_NOTE_SHARDED, "parallelism": PAR_NOTE_SHARDED % world},
         "e2e": e2e, "gpu_launches": build["gpu_launches"], "collectives_per_step": build["collectives"],
         "build": {k_: v for k_, v in build.items() if k_ != "rows_per_s"},
         "partition_sizes_sum": int(tot.sum()), "partition_sizes_min_max": [int(tot.min()), int(tot.max())],
@@ -934,7 +938,8 @@ def run_reference(args, rank, world):
             "impl": "reference", "metric": METRIC_SHARDED, "value": value, "unit": "rows/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": M2 / value * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD_SHARDED, "M": M2, "N": N2, "P": P2, "D": D2, "C": C2},
+            "config": {"workload": WORKLOAD_SHARDED, "M": M2, "N": N2, "P": P2, "D": D2, "C": C2,
+                       "l2": L2_NOTE_SHARDED, "parallelism": PAR_NOTE_SHARDED % world},
             "cpu_baseline": {"value": value, "unit": "rows/s", "cores": cores, "kind": "port", "sample": b["sample"]},
             "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
@@ -958,7 +963,7 @@ def run_reference(args, rank, world):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "M": args.m, "N": N, "P": P, "D": D, "C": CN, "nq": args.nq,
-                   "k": K, "nprobe": NPROBE},
+                   "k": K, "nprobe": NPROBE, "l2": L2_NOTE, "parallelism": PAR_NOTE % world},
         "cpu_baseline": {"value": value, "unit": "queries/s", "cores": cores, "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

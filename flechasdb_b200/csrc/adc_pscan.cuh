@@ -754,24 +754,65 @@ __global__ void __launch_bounds__(128) pmerge_kernel(PMergeParams p) {
     sel.init(p.ncap);
     uint32_t flat0 = 0;
     unsigned bad = 0;
-    for (int pr = 0; pr < p.nprobe; ++pr) {
-        const uint32_t part = p.probes[q * p.nprobe + pr];
-        const uint32_t np = p.part_off[part + 1] - p.part_off[part];
-        const uint32_t slot = p.pair_slot[ql * p.nprobe + pr];
+    // The descriptors of a query's probes (partition, list length, slot, first item, count word of the first chunk)
+    // are fetched by one lane per probe -- four dependent loads for ALL probes together instead of four per probe --
+    // and the item lists of probe j + 1 are requested before the entries of probe j are pushed.
+    for (int pr0 = 0; pr0 < p.nprobe; pr0 += 32) {
+        const int pr = pr0 + lane;
+        const bool act = pr < p.nprobe;
+        const uint32_t part = act ? p.probes[q * p.nprobe + pr] : 0u;
+        const uint32_t np = act ? p.part_off[part + 1] - p.part_off[part] : 0u;
+        const uint32_t slot = act ? p.pair_slot[ql * p.nprobe + pr] : 0u;
         const uint32_t g = slot / (uint32_t)p.pj, jj = slot % (uint32_t)p.pj;
         const uint32_t nv = (np + (uint32_t)p.vch - 1) / (uint32_t)p.vch;
-        const size_t first = p.istart[part + (pr ? (uint32_t)p.P : 0u)];
-        for (uint32_t c = 0; c < nv; ++c) {
-            const size_t item = first + (size_t)g * nv + c;
-            const uint32_t cf = p.item_cnt[item * p.pj + jj];
-            const int cnt = (int)(cf & 0xffffu);
-            bad |= cf >> 30;
-            const size_t o = (item * p.pj + jj) * PLK;
-            const uint32_t kv = lane < cnt ? p.item_keys[o + lane] : 0xffffffffu;
-            const uint32_t pv = lane < cnt ? p.item_pos[o + lane] : 0u;
-            push_lanes(sel, kv, flat0 + pv, lane < cnt && kv < sel.maxkey, lane);
+        const uint32_t first = act ? p.istart[part + (pr ? (uint32_t)p.P : 0u)] : 0u;
+        const uint32_t cf_first = (act && nv > 0) ? p.item_cnt[((size_t)first + (size_t)g * nv) * p.pj + jj] : 0u;
+        // position of the probe's list in the concatenation of the query's lists
+        uint32_t incl = np;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += o;
         }
-        flat0 += np;
+        const uint32_t excl = incl - np;
+        const int nj = min(32, p.nprobe - pr0);
+        // entries of (probe j, chunk 0), requested one probe ahead
+        auto fetch = [&](int j, uint32_t &kv, uint32_t &pv, int &cnt, uint32_t &cfw) {
+            const uint32_t nvj = __shfl_sync(0xffffffffu, nv, j), fj = __shfl_sync(0xffffffffu, first, j);
+            const uint32_t gj = __shfl_sync(0xffffffffu, g, j), jjj = __shfl_sync(0xffffffffu, jj, j);
+            cfw = __shfl_sync(0xffffffffu, cf_first, j);
+            cnt = nvj > 0 ? (int)(cfw & 0xffffu) : 0;
+            const size_t o = (((size_t)fj + (size_t)gj * nvj) * p.pj + jjj) * PLK;
+            kv = lane < cnt ? p.item_keys[o + lane] : 0xffffffffu;
+            pv = lane < cnt ? p.item_pos[o + lane] : 0u;
+        };
+        uint32_t kv, pv, cfw;
+        int cnt;
+        fetch(0, kv, pv, cnt, cfw);
+        for (int j = 0; j < nj; ++j) {
+            uint32_t kn = 0xffffffffu, pn = 0u, cfn = 0u;
+            int cn = 0;
+            if (j + 1 < nj) fetch(j + 1, kn, pn, cn, cfn);
+            const uint32_t nvj = __shfl_sync(0xffffffffu, nv, j), fj = __shfl_sync(0xffffffffu, first, j);
+            const uint32_t gj = __shfl_sync(0xffffffffu, g, j), jjj = __shfl_sync(0xffffffffu, jj, j);
+            const uint32_t fl = flat0 + __shfl_sync(0xffffffffu, excl, j);
+            if (nvj > 0) {
+                bad |= cfw >> 30;
+                push_lanes(sel, kv, fl + pv, lane < cnt && kv < sel.maxkey, lane);
+            }
+            for (uint32_t c = 1; c < nvj; ++c) {   // further chunks of a long list
+                const size_t item = (size_t)fj + (size_t)gj * nvj + c;
+                const uint32_t cf = p.item_cnt[item * p.pj + jjj];
+                const int cc = (int)(cf & 0xffffu);
+                bad |= cf >> 30;
+                const size_t o = (item * p.pj + jjj) * PLK;
+                const uint32_t k2 = lane < cc ? p.item_keys[o + lane] : 0xffffffffu;
+                const uint32_t p2 = lane < cc ? p.item_pos[o + lane] : 0u;
+                push_lanes(sel, k2, fl + p2, lane < cc && k2 < sel.maxkey, lane);
+            }
+            kv = kn, pv = pn, cnt = cn, cfw = cfn;
+        }
+        flat0 += __shfl_sync(0xffffffffu, incl, 31);
     }
     int rank = 0;
     for (int jx = 0; jx < sel.len; ++jx) {

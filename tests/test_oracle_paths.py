@@ -155,3 +155,46 @@ def test_oracle_reproduces_golden_fixture(oracle):
         rc, p, v, d, c = ix.query(g["q"], int(g["q_k"]), int(g["q_nprobe"]), mode)
         assert (p == g["q%d_part" % mode]).all() and (v == g["q%d_vidx" % mode]).all()
         assert (d == g["q%d_dist" % mode]).all() and (c == g["q%d_cnt" % mode]).all()
+
+
+def test_nbest_push_chain_is_one_prefix_maximum_sweep():
+    """NBestByKey::push (src/nbest.rs:52-64) loops { find the FIRST slot with key(cand) < key(slot); swap; the evicted
+    entry becomes cand }.  The device emulation (WarpNBest::push, csrc/nbest.cuh) does it as ONE left-to-right sweep
+    with a prefix maximum (the earlier entry wins ties).  Both formulations, slot for slot, on random streams with many
+    ties (payloads tell tied entries apart)."""
+    rng = np.random.default_rng(31)
+
+    def push_reference(slots, cand):
+        while True:
+            for i, s in enumerate(slots):
+                if cand[0] < s[0]:
+                    slots[i], cand = cand, s
+                    break
+            else:
+                return
+
+    def push_sweep(slots, cand):
+        # carry before slot s = first entry attaining max(cand, slots[0..s)); the slot takes it iff carry < slot
+        keys = [cand[0]] + [s[0] for s in slots]
+        new = list(slots)
+        best = 0                                   # index into [cand] + slots of the current carry
+        for s in range(len(slots)):
+            carry = cand if best == 0 else slots[best - 1]
+            if carry[0] < slots[s][0]:
+                new[s] = carry
+            if keys[best] < keys[s + 1]:
+                best = s + 1
+        slots[:] = new
+
+    for trial in range(200):
+        n = int(rng.integers(1, 40))
+        stream = [(float(rng.integers(0, 12)), i) for i in range(int(rng.integers(n, 6 * n + 2)))]
+        a, b = [], []
+        for item in stream:
+            if len(a) < n:
+                a.append(item)
+                b.append(item)
+                continue
+            push_reference(a, item)
+            push_sweep(b, item)
+            assert a == b, (trial, n)
