@@ -6,8 +6,10 @@
 
 namespace fdb { struct FilterState; }
 #ifndef FDB_FILTER_SLOTS
-#define FDB_FILTER_SLOTS 2   // scratch slots = compute streams that slices of a host batch rotate through
+#define FDB_FILTER_SLOTS 8   // scratch slots (upper bound) = compute streams that slices of a host batch rotate through
 #endif
+// how many of them a host batch uses (FDB_QUERY_STREAMS in the environment, read once)
+int fdb_filter_slots_in_use();
 
 struct fdb_index {
     fdb_ctx *ctx = nullptr;
