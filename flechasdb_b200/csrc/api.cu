@@ -132,6 +132,7 @@ void fdb_ctx_destroy(fdb_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     ctx->flush_buf.release();
+    fdb::dev_trim();   // the cache of freed blocks goes back to the driver with the context
     if (ctx->d_flags) cudaFree(ctx->d_flags);
     if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
@@ -244,7 +245,7 @@ static int vs_new(fdb_ctx *ctx, size_t n, size_t dim, fdb_vs **out) {
     v->n = n;
     v->dim = dim;
     v->owned = true;
-    FDB_CUDA(cudaMalloc((void **)&v->d, std::max<size_t>(n * dim, 4) * sizeof(float)));
+    FDB_TRY(fdb::dev_alloc((void **)&v->d, std::max<size_t>(n * dim, 4) * sizeof(float)));
     *out = v.release();
     return FDB_OK;
 }
@@ -308,7 +309,7 @@ void fdb_vs_destroy(fdb_vs *vs) {
     if (!vs) return;
     cudaSetDevice(vs->ctx->device);
     cudaStreamSynchronize(vs->ctx->stream);
-    if (vs->owned && vs->d) cudaFree(vs->d);
+    if (vs->owned && vs->d) fdb::dev_free(vs->d);
     delete vs;
 }
 

@@ -42,6 +42,12 @@ enum : unsigned {
     FLAG_WEIGHTS = 8u,        // k-means++ total weight <= 0 / nothing left to pick
 };
 
+// device memory behind a cache of freed blocks (devmem.cu): exact-size reuse, emptied on out-of-memory and when a
+// context is destroyed
+int dev_alloc(void **out, size_t bytes);
+void dev_free(void *p);
+void dev_trim();
+
 template <typename T>
 struct DevBuf {
     T *p = nullptr;
@@ -50,15 +56,16 @@ struct DevBuf {
         release();
         n = count;
         if (count == 0) return FDB_OK;
-        FDB_CUDA(cudaMalloc((void **)&p, count * sizeof(T)));
-        return FDB_OK;
+        const int rc = dev_alloc((void **)&p, count * sizeof(T));
+        if (rc != FDB_OK) n = 0;
+        return rc;
     }
     int ensure(size_t count) {
         if (count <= n && p) return FDB_OK;
         return alloc(count);
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p) dev_free(p);
         p = nullptr;
         n = 0;
     }
