@@ -617,8 +617,9 @@ def run_sharded_build_e2e(args, engine, sharded, ctx, comm, rank, world, steps):
         b.close()
         vs.close()
     sec = float(np.mean(secs))
+    d2h_all = int(comm_sum(comm, float(d2h))) if world > 1 else int(d2h)
     return {"value": M2 / sec, "unit": "rows/s", "sec": sec,
-            "h2d_bytes_per_step": int(M2) * N2 * 4, "d2h_bytes_per_step": int(d2h) * 1 if world == 1 else None,
+            "h2d_bytes_per_step": int(M2) * N2 * 4, "d2h_bytes_per_step": d2h_all,
             "d2h_bytes_per_step_rank0": int(d2h),
             "note": "wall clock around upload (pinned host rows) + build + read-back of the quantisers and of this "
                     "rank's partition ids / PQ codes, max over ranks; h2d bytes are the whole job's"}
