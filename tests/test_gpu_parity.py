@@ -844,6 +844,26 @@ def test_host_batch_with_page_locked_buffers_sends_results_early(eng, ctx, oracl
     ix.close()
 
 
+def test_last_scan_kernel_reports_what_ran(eng, ctx, oracle, monkeypatch):
+    """fdb_index_last_scan_kernel: which code-scan kernel answered the last call, and (timing enabled) its own launch
+    time -- what bench.py's roofline is computed from."""
+    N, P, D, Cn, M, k, nprobe = 96, 16, 12, 256, 40000, 10, 4
+    coarse, cbs, off, codes = random_index(oracle, N, P, D, Cn, M)
+    ix = eng.Index.create(ctx, coarse, cbs, off, codes.astype(np.uint8))
+    q = data(oracle, 2048, N, SEED + 97)
+    ix.set_timing(True)
+    ix.query(q[:4], k, nprobe)                       # a handful of queries (fewer pairs than 2 P): the query-major kernel
+    assert ix.last_scan_kernel().startswith("fscan_kernel")
+    ix.query(q, k, nprobe)                           # 512 (query, probe) pairs per list of 2 500 vectors: vector-lane scan
+    assert ix.last_scan_kernel().startswith("vscan_kernel")
+    phases, _ = ix.last_timing()
+    assert 0.0 < ix.last_scan_kernel_ms() <= float(phases[4]) * 1.05 + 0.01
+    monkeypatch.setenv("FDB_QUERY_EXACT", "1")
+    ix.query(q[:8], k, nprobe)
+    assert ix.last_scan_kernel().startswith("none")
+    ix.close()
+
+
 def test_forced_scan_mode_fails_loudly_when_the_shape_is_not_taken(eng, ctx, oracle, monkeypatch):
     """FDB_FILTER_SCAN forces a scan kernel; a shape that kernel does not take is an error, not a silent fallback."""
     from flechasdb_b200.db import Error
