@@ -46,6 +46,8 @@ struct fdb_index {
     fdb::DevBuf<uint32_t> tied_list;
     fdb::DevBuf<float> tied_q, tied_dist;
     unsigned last_probe_ties = 0;
+    float *h_qstage = nullptr;     // page-locked ring (two slots) pageable query batches are staged through
+    size_t h_qstage_floats = 0;
     uint32_t *h_stage = nullptr;   // page-locked staging for the handed-back rows of a host batch
     size_t h_stage_words = 0;
     // timing mode: events around the code-scan kernel itself (its launches of the last call, summed)

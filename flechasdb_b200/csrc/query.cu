@@ -20,6 +20,7 @@
 #include <chrono>
 #include <cstdlib>
 #include <memory>
+#include <thread>
 
 #include "index.cuh"
 #include "comm.cuh"
@@ -657,6 +658,7 @@ void fdb_index_destroy(fdb_index *ix) {
     for (cudaEvent_t e : ix->events) cudaEventDestroy(e);
     for (cudaEvent_t e : ix->kev) cudaEventDestroy(e);
     if (ix->h_stage) cudaFreeHost(ix->h_stage);
+    if (ix->h_qstage) cudaFreeHost(ix->h_qstage);
     for (cudaEvent_t e : ix->copy_events) cudaEventDestroy(e);
     if (ix->copy_stream) {
         cudaStreamSynchronize(ix->copy_stream);
@@ -898,6 +900,30 @@ int fdb_filter_slots_in_use() {
 }
 
 namespace {
+
+// host copy of `bytes` bytes by a few threads (pageable caller memory -> the page-locked staging ring)
+void parallel_copy(void *dst, const void *src, size_t bytes) {
+    static const int nthreads = [] {
+        const char *e = getenv("FDB_STAGE_THREADS");
+        const int hw = (int)std::thread::hardware_concurrency();
+        const int v = e ? atoi(e) : std::min(8, std::max(1, hw / 2));
+        return std::max(1, std::min(v, 32));
+    }();
+    if (nthreads == 1 || bytes < ((size_t)1 << 20)) {
+        memcpy(dst, src, bytes);
+        return;
+    }
+    const size_t chunk = ((bytes / (size_t)nthreads) + 4095) & ~(size_t)4095;
+    std::vector<std::thread> workers;
+    for (int t = 1; t < nthreads; ++t) {
+        const size_t o = (size_t)t * chunk;
+        if (o >= bytes) break;
+        const size_t len = std::min(chunk, bytes - o);
+        workers.emplace_back([=] { memcpy((char *)dst + o, (const char *)src + o, len); });
+    }
+    memcpy(dst, src, std::min(chunk, bytes));
+    for (std::thread &w : workers) w.join();
+}
 
 int batch_begin(QueryBatch &b) {
     fdb_index *ix = b.ix;
@@ -1231,10 +1257,33 @@ int fdb_index_query(fdb_index *ix, const float *queries, size_t nq, size_t k, si
     bool pinned = cudaPointerGetAttributes(&attr, queries) == cudaSuccess && attr.type == cudaMemoryTypeHost;
     cudaGetLastError();
     if (getenv("FDB_QUERY_ASSUME_PAGEABLE")) pinned = false;
+    // Pageable caller memory, batches of several slices: the slice is first copied by a few host threads into a
+    // page-locked ring of the index (two slots), then travels by asynchronous DMA like pinned memory does -- the host
+    // stages slice i + 1 while the GPU copies and answers slice i.  (cudaMemcpyAsync from pageable memory goes
+    // through the driver's own staging at ~12 GB/s: 5.1 ms for the 61 MB of the README batch.)
+    const bool stage = !pinned && nslices > 1 && !getenv("FDB_QUERY_NO_STAGING");
+    if (stage) {
+        size_t slot_floats = 0;
+        for (size_t i = 0; i < nslices; ++i) slot_floats = std::max(slot_floats, (bounds[i + 1] - bounds[i]) * ix->N);
+        if (2 * slot_floats > ix->h_qstage_floats) {
+            if (ix->h_qstage) cudaFreeHost(ix->h_qstage);
+            ix->h_qstage = nullptr;
+            ix->h_qstage_floats = 0;
+            FDB_CUDA(cudaMallocHost((void **)&ix->h_qstage, 2 * slot_floats * sizeof(float)));
+            ix->h_qstage_floats = 2 * slot_floats;
+        }
+    }
     auto copy_slice = [&](size_t i) -> int {
         const size_t q0 = bounds[i], nc = bounds[i + 1] - q0;
-        FDB_CUDA(cudaMemcpyAsync(ix->q_dev.p + q0 * ix->N, queries + q0 * ix->N, nc * ix->N * sizeof(float),
-                                 cudaMemcpyHostToDevice, ix->copy_stream));
+        const float *src = queries + q0 * ix->N;
+        const size_t bytes = nc * ix->N * sizeof(float);
+        if (stage) {
+            float *slot = ix->h_qstage + (i & 1) * (ix->h_qstage_floats / 2);
+            if (i >= 2) FDB_CUDA(cudaEventSynchronize(ix->copy_events[i - 2]));   // the slot's previous slice has left it
+            parallel_copy(slot, src, bytes);
+            src = slot;
+        }
+        FDB_CUDA(cudaMemcpyAsync(ix->q_dev.p + q0 * ix->N, src, bytes, cudaMemcpyHostToDevice, ix->copy_stream));
         FDB_CUDA(cudaEventRecord(ix->copy_events[i], ix->copy_stream));
         return FDB_OK;
     };

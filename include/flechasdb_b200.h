@@ -323,8 +323,8 @@ int fdb_index_last_sharded_ties(fdb_index *ix, uint32_t *ties);
 
 /* Host buffers.  The query / upload / download calls take any host pointer.  Page-locked memory (registered
  * here, or allocated pinned by the caller) is copied by asynchronous DMA, so fdb_index_query overlaps the copy of
- * a batch with answering it; pageable memory (a plain Vec<f32>) is staged by the driver slice by slice while the
- * GPU answers the previous slice.  Registering costs about as much as one copy: worth it for buffers that are
+ * a batch with answering it; pageable memory (a plain Vec<f32>) is staged slice by slice -- by a few host threads
+ * into a page-locked ring of the index, then by DMA -- while the GPU answers the previous slice.  Registering costs about as much as one copy: worth it for buffers that are
  * reused.  No reference analogue (the reference never leaves host memory). */
 int fdb_host_register(fdb_ctx *ctx, void *p, size_t bytes);
 int fdb_host_unregister(fdb_ctx *ctx, void *p);
