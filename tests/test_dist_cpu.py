@@ -131,3 +131,37 @@ def test_partition_sharding_and_merge_equal_unsharded(oracle):
     gp, gv, gd, gc = (np.stack([r[i] for r in res]) for i in range(4))
     mp_, mv, md, mc = fd.merge_topk(gp, gv, gd, gc, probes, k)
     assert (mc == wc).all() and (mp_ == wp).all() and (mv == wv).all() and (md == wd).all()
+
+
+def test_partition_ownership_is_balanced_and_consistent():
+    """sharded.owned_partitions / shard_offsets (code lists sharded by partition): every partition
+    has exactly one owner, the greedy assignment is size balanced, and a rank's offsets hold exactly its own lists."""
+    import numpy as np
+    from flechasdb_b200 import sharded
+    rng = np.random.default_rng(3)
+    for world in (1, 2, 4, 8):
+        sizes = rng.multinomial(1_000_000, np.ones(4096) / 4096)
+        sizes[:5] = [0, 0, 50_000, 1, 0]                       # empty lists and one very long one
+        owner = sharded.owned_partitions(sizes, world)
+        assert owner.shape == sizes.shape and owner.min() >= 0 and owner.max() < world
+        load = np.bincount(owner, weights=sizes, minlength=world)
+        assert load.sum() == sizes.sum()
+        assert load.max() - load.min() <= sizes.max()          # greedy on descending sizes: within one list of each other
+        total = 0
+        for r in range(world):
+            off = sharded.shard_offsets(sizes, owner, r)
+            mine = np.diff(off.astype(np.int64))
+            assert (mine[owner == r] == sizes[owner == r]).all() and (mine[owner != r] == 0).all()
+            total += int(off[-1])
+        assert total == int(sizes.sum())
+    assert (sharded.owned_partitions(sizes, 1) == 0).all()
+
+
+def test_shard_rows_cover_the_rows_once():
+    from flechasdb_b200 import engine
+    for n in (1, 7, 1000, 1_000_003):
+        for world in (1, 2, 3, 8):
+            cuts = [engine.shard_rows(n, world, r) for r in range(world)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == n
+            assert all(cuts[r][1] == cuts[r + 1][0] for r in range(world - 1))
+            assert all(lo == n * r // world for r, (lo, _) in enumerate(cuts))     # fdb_kmeans_seed_run_sharded's rule
