@@ -117,10 +117,14 @@ class AsyncStoredDatabase:
         """one partition: file -> codes + ids on a worker thread, upload on the caller's thread"""
         loop = asyncio.get_running_loop()
         event(("StartingLoadingPartition", p))
-        codes, ids = await loop.run_in_executor(
-            None, stored.load_partition, self.base, self.partition_ids[p], p, self.vector_size, self.num_divisions,
-            self.num_codes)
-        self.index.set_partition(p, codes.astype(np.uint8))     # the other probed partitions are still being read
+        try:
+            codes, ids = await loop.run_in_executor(
+                None, stored.load_partition, self.base, self.partition_ids[p], p, self.vector_size, self.num_divisions,
+                self.num_codes)
+            self.index.set_partition(p, codes.astype(np.uint8))     # the other probed partitions are still being read
+        except BaseException:
+            self._partition_tasks.pop(p, None)      # a failed load is not cached: the next query tries again
+            raise
         self.ids[p] = ids
         self.partition_loads += 1
         event(("FinishedLoadingPartition", p))
@@ -149,7 +153,11 @@ class AsyncStoredDatabase:
         plist = [int(p) for p in probes[0]]
         if not plist:
             raise stored.Error("InvalidContext", "no partitions selected for query")
-        await asyncio.gather(*[self._partition_task(p, event) for p in plist])
+        # (every load is awaited before an error is reported: no load of this query is left running behind it)
+        loaded = await asyncio.gather(*[self._partition_task(p, event) for p in plist], return_exceptions=True)
+        for r in loaded:
+            if isinstance(r, BaseException):
+                raise r
         for p in plist:
             event(("StartingPartitionQueryExecution", p))
         part, vi, d, c = self.index.query(v, k, nprobe, capi.QUERY_STORED)

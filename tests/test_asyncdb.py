@@ -114,3 +114,33 @@ def test_async_query_event_order_lazy_loading_and_attributes(tmp_path, monkeypat
         db.close()
 
     asyncio.run(run())
+
+
+def test_async_query_reports_a_broken_partition_file_and_retries(tmp_path, monkeypatch):
+    """a partition file that fails verification is an error of the query that probes it (src/io.rs:283-299), not a
+    cached state: once the file is whole again the next query loads it"""
+    from flechasdb_b200 import engine
+    monkeypatch.setattr(engine.Index, "create_lazy", staticmethod(lambda ctx, coarse, cbs: OracleIndex(coarse, cbs)))
+    base, h, _ = _db(tmp_path, with_attrs=False)
+    q = np.random.default_rng(23).random((1, 32), dtype=np.float32)
+    hdr = stored.parse(stored._open(base, h + ".binpb", True))
+    pids = [v.decode() for _, v in hdr[10]]
+
+    async def run():
+        db = await asyncdb.AsyncStoredDatabase.load_database(None, base, h + ".binpb")
+        files = {pid: os.path.join(base, "partitions", pid + ".binpb") for pid in pids}
+        saved = {pid: open(f, "rb").read() for pid, f in files.items()}
+        for pid, f in files.items():                    # flip a byte in every partition file
+            raw = bytearray(saved[pid])
+            raw[len(raw) // 2] ^= 0x55
+            open(f, "wb").write(bytes(raw))
+        with pytest.raises(Exception):
+            await db.query(q[0], 5, 6)
+        assert db.partition_loads == 0
+        for pid, f in files.items():
+            open(f, "wb").write(saved[pid])
+        res = await db.query(q[0], 5, 6)
+        assert len(res) == 5 and db.partition_loads == 6
+        db.close()
+
+    asyncio.run(run())
