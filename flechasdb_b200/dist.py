@@ -1,4 +1,8 @@
-"""Multi-GPU orchestration: one process per GPU, torch.distributed for the plumbing.
+"""Multi-GPU orchestration with the collectives issued from the HOST (round 1): one process per GPU,
+torch.distributed for the plumbing.  Since round 2 the library issues its collectives itself (csrc/comm.cu:
+fdb_comm_*, fdb_kmeans_*_sharded, fdb_index_query_sharded; host mirror flechasdb_b200/sharded.py), which is what
+bench.py --gpus N times; this module stays as the host-driven variant of the same protocol -- the step-wise sharded
+entry points of the C ABI -- and as the part of the sharded logic that runs on CPU tensors over gloo in the tests.
 
 Build: rows are sharded contiguously over the ranks, centroids are
 replicated.  k-means++ needs two tiny exchanges per round (the shards' weight totals; the
